@@ -1,0 +1,61 @@
+"""Import the UNMODIFIED reference NumPy env in the build container (oracle tooling only).
+
+Puts oracle/gymnasium_shim (only when real gymnasium is absent) and /root/reference on
+sys.path.  /root/reference does not exist on the GPU box: `available()` is False there and
+everything that needs the live reference is skipped.
+"""
+import os
+import sys
+
+REF = os.environ.get("TETRIS_REFERENCE", "/root/reference")
+SHIM = os.path.join(os.path.dirname(os.path.abspath(__file__)), "gymnasium_shim")
+
+
+def available():
+    return os.path.isdir(os.path.join(REF, "tetris_gymnasium"))
+
+
+def load():
+    if not available():
+        raise RuntimeError("reference not present")
+    try:
+        import gymnasium  # noqa: F401
+    except ImportError:
+        sys.path.insert(0, SHIM)
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    import tetris_gymnasium.envs  # noqa: F401  (registers the env id)
+    from tetris_gymnasium.components.tetromino_queue import TetrominoQueue
+    from tetris_gymnasium.components.tetromino_randomizer import Randomizer
+    from tetris_gymnasium.envs.tetris import Tetris
+    from tetris_gymnasium.wrappers.grouped import GroupedActionsObservations
+    from tetris_gymnasium.wrappers.observation import FeatureVectorObservation, RgbObservation
+
+    class Scripted(Randomizer):
+        """Injected piece stream: the same hook SURVEY 8c describes (post-construction patch)."""
+
+        def __init__(self, seq):
+            super().__init__(7)
+            self.seq = [int(v) for v in seq]
+            self.cur = 0
+
+        def get_next_tetromino(self):
+            v = self.seq[self.cur % len(self.seq)]
+            self.cur += 1
+            return v
+
+        def reset(self, seed=None):
+            pass
+
+    def make(width=10, height=20, gravity=True, queue_size=4, seq=None, **kw):
+        env = Tetris(width=width, height=height, gravity=gravity, **kw)
+        if seq is not None:
+            env.randomizer = Scripted(seq)
+            env.queue = TetrominoQueue(env.randomizer, size=queue_size)
+        elif queue_size != 4:
+            env.queue = TetrominoQueue(env.randomizer, size=queue_size)
+        return env
+
+    return dict(Tetris=Tetris, make=make, Scripted=Scripted, TetrominoQueue=TetrominoQueue,
+                GroupedActionsObservations=GroupedActionsObservations,
+                FeatureVectorObservation=FeatureVectorObservation, RgbObservation=RgbObservation)

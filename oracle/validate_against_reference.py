@@ -1,0 +1,143 @@
+"""Step-for-step check of the C oracle against the LIVE, unmodified reference NumPy env.
+
+Build-container tool (needs /root/reference); run as `python -m oracle.validate_against_reference`.
+It is also exercised by tests/test_oracle_vs_reference.py (skipped where the reference is absent).
+Covers: base env (all 8 actions, gravity on/off, holder, queue sizes 4/5/7, default and wide
+boards, seeded numpy 7-bag and injected streams, stepping after game over), the
+FeatureVector / Rgb wrappers on the base env, and GroupedActionsObservations (boards, features,
+legal mask, info["board"], illegal actions in both termination modes).
+"""
+import sys
+
+import numpy as np
+
+from . import _refload
+from .tetris_oracle import OracleEnv
+
+
+def _same_obs(a, b):
+    return all(np.array_equal(a[k], b[k]) and a[k].dtype == b[k].dtype for k in ("board", "active_tetromino_mask", "holder", "queue"))
+
+
+def check_base(ref, episodes, width, height, gravity, queue_size, seed0, injected, steps_after_over=3, max_steps=4000):
+    R = ref
+    rng = np.random.default_rng(seed0)
+    n_steps = 0
+    for ep in range(episodes):
+        seq = rng.integers(0, 7, size=512) if injected else None
+        env = R["make"](width=width, height=height, gravity=gravity, queue_size=queue_size, seq=seq)
+        orc = OracleEnv(width=width, height=height, gravity=gravity, queue_size=queue_size)
+        rgbw = R["RgbObservation"](env)
+        featw = R["FeatureVectorObservation"](env)
+        if injected:
+            orc.set_sequence(seq)
+            o_ref, _ = env.reset()
+            o_orc, _ = orc.reset()
+        else:
+            seed = int(rng.integers(1, 2**31))
+            o_ref, _ = env.reset(seed=seed)
+            o_orc, _ = orc.reset(seed=seed)
+        assert _same_obs(o_ref, o_orc), "reset obs"
+        over_left = steps_after_over
+        for t in range(max_steps):
+            a = int(rng.integers(0, 8))
+            o_ref, r_ref, term_ref, trunc_ref, info_ref = env.step(a)
+            o_orc, r_orc, term_orc, _, info_orc = orc.step(a)
+            n_steps += 1
+            assert _same_obs(o_ref, o_orc), f"obs ep{ep} t{t} a{a}"
+            assert float(r_ref) == r_orc and bool(term_ref) == term_orc, f"reward/term ep{ep} t{t}"
+            assert int(info_ref["lines_cleared"]) == info_orc["lines_cleared"]
+            s = orc.scalars()
+            assert (env.x, env.y, bool(env.has_swapped)) == (s["x"], s["y"], s["has_swapped"])
+            assert np.array_equal(env.board, orc.board)
+            assert np.array_equal(env.active_tetromino.matrix, orc.active_matrix())
+            if t % 7 == 0:
+                assert np.array_equal(rgbw.observation(o_ref), orc.rgb()), "rgb"
+                f_ref = featw.observation({k: v.copy() for k, v in o_ref.items()})
+                f_orc = orc.features({k: v.copy() for k, v in o_orc.items()})
+                assert np.array_equal(f_ref, f_orc) and f_ref.dtype == f_orc.dtype, "features"
+            if term_ref:
+                over_left -= 1
+                if over_left < 0:
+                    break
+    return n_steps
+
+
+def check_grouped(ref, episodes, width, height, gravity, queue_size, seed0, use_features, terminate_on_illegal, max_steps=600, greedy=False):
+    from .make_golden import greedy_action
+
+    R = ref
+    rng = np.random.default_rng(seed0)
+    n_steps = 0
+    for ep in range(episodes):
+        seq = rng.integers(0, 7, size=512)
+        base = R["make"](width=width, height=height, gravity=gravity, queue_size=queue_size, seq=seq)
+        wrappers = [R["FeatureVectorObservation"](base)] if use_features else None
+        env = R["GroupedActionsObservations"](base, observation_wrappers=wrappers, terminate_on_illegal_action=terminate_on_illegal)
+        orc = OracleEnv(width=width, height=height, gravity=gravity, queue_size=queue_size)
+        orc.set_sequence(seq)
+        g_ref, info = env.reset()
+        o0, _ = orc.reset()
+        ib = orc.features(o0) if use_features else None
+        f, b, legal = orc.grouped_observe(features=use_features, boards=not use_features)
+        g_orc = f if use_features else b
+        assert np.array_equal(g_ref, g_orc) and g_ref.dtype == g_orc.dtype, "grouped reset obs"
+        assert np.array_equal(info["action_mask"].astype(np.uint8), legal)
+        if use_features:
+            assert np.array_equal(info["board"], ib)
+        for t in range(max_steps):
+            # mostly legal actions, sometimes any action (to hit the illegal path)
+            if greedy and use_features and rng.random() > 0.05:
+                a = greedy_action(g_ref, legal, width)
+            elif rng.random() < 0.1:
+                a = int(rng.integers(0, 4 * width))
+            else:
+                a = int(rng.choice(np.flatnonzero(legal)))
+            g_ref, r_ref, term_ref, _, info = env.step(a)
+            code, r_orc, term_orc, l_orc = orc.grouped_step(a, terminate_on_illegal)
+            n_steps += 1
+            assert float(r_ref) == r_orc and bool(term_ref) == term_orc, f"grouped reward/term ep{ep} t{t} a{a}"
+            assert int(info["lines_cleared"]) == l_orc
+            if code == 1:
+                # illegal + terminate: reference returns ones * high (float), env untouched
+                assert np.all(g_ref == float(height * width))
+                break
+            o = orc.obs()
+            if code == 0 and use_features:
+                assert np.array_equal(info["board"], orc.features(o)), "info board"
+            elif code == 0:
+                assert _same_obs(info["board"], o), "info board dict"
+            f, b, legal = orc.grouped_observe(features=use_features, boards=not use_features)
+            g_orc = f if use_features else b
+            assert np.array_equal(g_ref, g_orc), f"grouped obs ep{ep} t{t}"
+            assert np.array_equal(info["action_mask"].astype(np.uint8), legal)
+            assert np.array_equal(base.board, orc.board)
+            if term_ref:
+                break
+    return n_steps
+
+
+def run(scale=1):
+    ref = _refload.load()
+    n = 0
+    n += check_base(ref, 6 * scale, 10, 20, True, 4, 1, injected=False)
+    n += check_base(ref, 6 * scale, 10, 20, True, 4, 2, injected=True)
+    n += check_base(ref, 4 * scale, 10, 20, False, 7, 3, injected=True, max_steps=1500)
+    n += check_base(ref, 3 * scale, 20, 40, True, 5, 4, injected=True)
+    n += check_base(ref, 3 * scale, 6, 8, True, 4, 5, injected=False)
+    n += check_base(ref, 3 * scale, 13, 9, True, 3, 6, injected=True)
+    g = 0
+    g += check_grouped(ref, 4 * scale, 10, 20, False, 4, 11, True, True)
+    g += check_grouped(ref, 3 * scale, 10, 20, False, 4, 12, False, False)
+    g += check_grouped(ref, 3 * scale, 10, 20, True, 4, 13, True, False)
+    g += check_grouped(ref, 2 * scale, 20, 40, False, 5, 14, True, True, max_steps=300)
+    g += check_grouped(ref, 2 * scale, 7, 10, False, 4, 15, False, True)
+    g += check_grouped(ref, 2 * scale, 10, 20, False, 4, 16, True, True, max_steps=400, greedy=True)
+    g += check_grouped(ref, 1 * scale, 20, 40, False, 5, 17, True, False, max_steps=250, greedy=True)
+    return n, g
+
+
+if __name__ == "__main__":
+    scale = int(sys.argv[1]) if len(sys.argv) > 1 else 1
+    n, g = run(scale)
+    print(f"oracle == reference on {n} base steps and {g} grouped steps")
