@@ -1,0 +1,402 @@
+// tg_api.cu -- host side of libtetris_b200.so: the C ABI declared in include/tetris_b200.h.
+// No torch types, no CPU fallback: every entry point launches sm_100a kernels on the caller's stream.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/tetris_b200.h"
+#include "tg_device.cuh"
+#include "tg_step.cuh"
+#include "tg_aux.cuh"
+
+using namespace tg;
+
+struct tg_env {
+    tg_config cfg;
+    DevCfg dev;
+    tg_layout layout;
+    int device;
+    int num_sms;
+    int col64;
+    int tile;  // envs per CTA tile of the step kernel
+    std::string err;
+    // tg_step_host staging
+    cudaStream_t hs[3];
+    bool hs_init;
+    void* stage[16];
+    size_t stage_bytes[16];
+};
+
+static std::string g_create_err;
+
+static int fail(tg_env* env, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (env) env->err = buf; else g_create_err = buf;
+    return code;
+}
+#define CUDA_TRY(env, call)                                                                          \
+    do {                                                                                             \
+        cudaError_t _e = (call);                                                                     \
+        if (_e != cudaSuccess) return fail(env, TG_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(_e)); \
+    } while (0)
+
+// ---- constant tables: rotate the reference's base matrices (envs/tetris.py:47-75) with rot90 -----
+static const int kN[7] = {4, 2, 3, 3, 3, 3, 3};
+static const unsigned char kBase[7][16] = {
+    {0, 0, 0, 0, 1, 1, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0}, {1, 1, 1, 1},
+    {0, 1, 0, 1, 1, 1, 0, 0, 0}, {0, 1, 1, 1, 1, 0, 0, 0, 0}, {1, 1, 0, 0, 1, 1, 0, 0, 0},
+    {1, 0, 0, 1, 1, 1, 0, 0, 0}, {0, 0, 1, 1, 1, 1, 0, 0, 0}};
+static const unsigned char kColors[9][3] = {{0, 0, 0}, {128, 128, 128}, {0, 240, 240}, {240, 240, 0}, {160, 0, 240},
+                                            {0, 240, 0}, {240, 0, 0}, {0, 0, 240}, {240, 160, 0}};
+
+static int upload_tables(tg_env* env) {
+    unsigned short cells[7][4];
+    unsigned int rowbytes[7][4][4];
+    unsigned char colors[16][4];
+    memset(colors, 0, sizeof colors);
+    for (int v = 0; v < 9; v++) for (int k = 0; k < 3; k++) colors[v][k] = kColors[v][k];
+    for (int p = 0; p < 7; p++) {
+        int n = kN[p];
+        unsigned char m[16], t[16];
+        memcpy(m, kBase[p], 16);
+        for (int r = 0; r < 4; r++) {
+            if (r > 0) {  // np.rot90(m, k=1): out[i][j] = m[j][n-1-i]  (Tetris.rotate, envs/tetris.py:429-443)
+                for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) t[i * n + j] = m[j * n + (n - 1 - i)];
+                memcpy(m, t, 16);
+            }
+            unsigned short c = 0;
+            int k = 0;
+            for (int i = 0; i < 4; i++) {
+                unsigned int w = 0;
+                for (int j = 0; j < 4; j++)
+                    if (i < n && j < n && m[i * n + j]) {
+                        c |= (unsigned short)(((i << 2) | j) << (4 * k));
+                        k++;
+                        w |= (unsigned int)(p + 2) << (8 * j);
+                    }
+                rowbytes[p][r][i] = w;
+            }
+            if (k != 4) return fail(env, TG_ERR_CONFIG, "piece table: %d cells", k);
+            cells[p][r] = c;
+        }
+    }
+    CUDA_TRY(env, cudaMemcpyToSymbol(c_cells, cells, sizeof cells));
+    CUDA_TRY(env, cudaMemcpyToSymbol(c_rowbytes, rowbytes, sizeof rowbytes));
+    CUDA_TRY(env, cudaMemcpyToSymbol(c_n, kN, sizeof kN));
+    CUDA_TRY(env, cudaMemcpyToSymbol(c_colors, colors, sizeof colors));
+    return TG_OK;
+}
+
+static int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+extern "C" int tg_version(void) { return TG_VERSION; }
+
+extern "C" const char* tg_last_error(const tg_env* env) { return env ? env->err.c_str() : g_create_err.c_str(); }
+
+extern "C" int tg_create(const tg_config* cfg, int device, tg_env** out) {
+    if (!cfg || !out) return fail(nullptr, TG_ERR_POINTER, "tg_create: NULL argument");
+    *out = nullptr;
+    if (cfg->width < 4 || cfg->width + 2 * TG_PADDING > 32)
+        return fail(nullptr, TG_ERR_CONFIG, "width %d unsupported (4 <= W <= 24: a padded row must fit 32 bits)", cfg->width);
+    if (cfg->height < 4 || cfg->height + TG_PADDING > 64)
+        return fail(nullptr, TG_ERR_CONFIG, "height %d unsupported (4 <= H <= 60)", cfg->height);
+    if (cfg->queue_size < 1 || cfg->queue_size > TG_MAX_QUEUE)
+        return fail(nullptr, TG_ERR_CONFIG, "queue_size %d unsupported (1..16)", cfg->queue_size);
+    if (cfg->rng_mode < 0 || cfg->rng_mode > 2) return fail(nullptr, TG_ERR_CONFIG, "rng_mode %d", cfg->rng_mode);
+    if (cfg->autoreset < 0 || cfg->autoreset > 2) return fail(nullptr, TG_ERR_CONFIG, "autoreset %d", cfg->autoreset);
+    if (cfg->rng_mode == TG_RNG_SEQUENCE && cfg->seq_len < 1) return fail(nullptr, TG_ERR_CONFIG, "seq_len must be >= 1");
+    for (int i = 0; i < 8; i++)
+        if (cfg->action_map[i] < 0 || cfg->action_map[i] >= 8)
+            return fail(nullptr, TG_ERR_CONFIG, "action_map[%d] = %d outside Discrete(8)", i, cfg->action_map[i]);
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0)
+        return fail(nullptr, TG_ERR_CUDA, "no CUDA device (%s); this library has no CPU fallback", cudaGetErrorString(ce));
+    if (device < 0 || device >= ndev) return fail(nullptr, TG_ERR_ARG, "device %d of %d", device, ndev);
+    tg_env* env = new tg_env();
+    env->cfg = *cfg;
+    env->device = device;
+    env->hs_init = false;
+    memset(env->stage, 0, sizeof env->stage);
+    memset(env->stage_bytes, 0, sizeof env->stage_bytes);
+    cudaError_t e1 = cudaSetDevice(device);
+    if (e1 != cudaSuccess) { int rc = fail(nullptr, TG_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e1)); delete env; return rc; }
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    env->num_sms = prop.multiProcessorCount;
+
+    DevCfg& d = env->dev;
+    memset(&d, 0, sizeof d);
+    d.W = cfg->width; d.H = cfg->height; d.Wp = d.W + 2 * TG_PADDING; d.Hp = d.H + TG_PADDING; d.Q = cfg->queue_size;
+    d.gravity = cfg->gravity != 0; d.autoreset = cfg->autoreset; d.rng_mode = cfg->rng_mode;
+    d.terminate_on_illegal = cfg->terminate_on_illegal != 0;
+    env->col64 = d.Hp > 32;
+    int col_bytes = env->col64 ? 8 : 4;
+    d.ids_off = d.W * col_bytes;
+    d.ids_words = (d.H * d.W + 7) / 8;
+    int bs = round_up(d.ids_off + d.ids_words * 4, 16);
+    if (((bs / 16) & 1) == 0) bs += 16;  // odd multiple of 16 B: conflict-free 128-bit shared-memory access
+    d.board_stride = bs;
+    d.rng_stride = cfg->rng_mode == TG_RNG_NUMPY ? 48 : 16;
+    d.OB = d.Hp * d.Wp; d.OQ = 16 * d.Q; d.A = 4 * d.W; d.F = d.W + 3;
+    d.rgb_w = d.Wp + 4 * (d.Q > 1 ? d.Q : 1);
+    for (int p = 0; p < 7; p++) d.spawn_x[p] = d.Wp / 2 - kN[p] / 2;
+    // elif chain of Tetris.step (envs/tetris.py:223-256): first matching name wins
+    static const int order[8] = {0, 1, 2, 3, 4, 6, 5, 7};  // left,right,down,cw,ccw,swap,hard_drop,no_op
+    static const int ops[8] = {OP_LEFT, OP_RIGHT, OP_DOWN, OP_CW, OP_CCW, OP_HARD, OP_SWAP, OP_NOOP};
+    for (int a = 0; a < 8; a++) {
+        d.op_lut[a] = OP_NOOP;
+        for (int k = 0; k < 8; k++)
+            if (cfg->action_map[order[k]] == a) { d.op_lut[a] = (unsigned char)ops[order[k]]; break; }
+        d.skipgrav[a] = (unsigned char)(a == cfg->action_map[5]);
+    }
+    d.act_hard = cfg->action_map[5]; d.act_noop = cfg->action_map[7];
+    d.r_alife = cfg->reward_alife; d.r_go = cfg->reward_game_over; d.r_invalid = cfg->reward_invalid_action;
+    d.seq_len = cfg->seq_len; d.env_id_offset = cfg->env_id_offset;
+
+    tg_layout& L = env->layout;
+    memset(&L, 0, sizeof L);
+    L.width_padded = d.Wp; L.height_padded = d.Hp; L.hot_stride = 32; L.board_stride = d.board_stride;
+    L.rng_stride = d.rng_stride; L.obs_board_bytes = d.OB; L.obs_holder_bytes = 16; L.obs_queue_bytes = d.OQ;
+    L.n_placements = d.A; L.n_features = d.F; L.rgb_width = d.rgb_w;
+
+    env->tile = 64;
+    if (const char* t = getenv("TG_TILE")) { int v = atoi(t); if (v == 32 || v == 64 || v == 96 || v == 128) env->tile = v; }
+    int rc = upload_tables(env);
+    if (rc != TG_OK) { g_create_err = env->err; delete env; return rc; }
+    *out = env;
+    return TG_OK;
+}
+
+extern "C" int tg_destroy(tg_env* env) {
+    if (!env) return TG_OK;
+    cudaSetDevice(env->device);
+    if (env->hs_init) for (int i = 0; i < 3; i++) cudaStreamDestroy(env->hs[i]);
+    for (int i = 0; i < 16; i++) if (env->stage[i]) cudaFree(env->stage[i]);
+    delete env;
+    return TG_OK;
+}
+
+extern "C" int tg_get_layout(const tg_env* env, tg_layout* out) {
+    if (!env || !out) return TG_ERR_POINTER;
+    *out = env->layout;
+    return TG_OK;
+}
+
+static bool misaligned(const void* p) { return ((uintptr_t)p & 15u) != 0; }
+static int check_state(tg_env* env, const tg_state& st) {
+    if (!st.hot || !st.board || !st.rng) return fail(env, TG_ERR_POINTER, "state pointer is NULL");
+    if (misaligned(st.hot) || misaligned(st.board) || misaligned(st.rng)) return fail(env, TG_ERR_POINTER, "state pointer not 16-byte aligned");
+    if (env->cfg.rng_mode == TG_RNG_SEQUENCE && !st.piece_seq) return fail(env, TG_ERR_POINTER, "piece_seq is NULL in TG_RNG_SEQUENCE mode");
+    return TG_OK;
+}
+
+// ---- step / reset launcher ----------------------------------------------------------------------
+template <int WT, int HT, class COLT>
+static int launch_step_t(tg_env* env, StepParams& p, int E, size_t smem, cudaStream_t s) {
+    auto kern = k_step<WT, HT, COLT>;
+    CUDA_TRY(env, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CUDA_TRY(env, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, E, smem));
+    if (per_sm < 1) return fail(env, TG_ERR_CONFIG, "step kernel does not fit: %zu B shared memory per CTA", smem);
+    int64_t ntiles = (p.n + E - 1) / E;
+    int64_t grid = (int64_t)env->num_sms * per_sm;
+    if (grid > ntiles) grid = ntiles;
+    kern<<<(unsigned)grid, E, smem, s>>>(p);
+    CUDA_TRY(env, cudaGetLastError());
+    return TG_OK;
+}
+
+static int launch_step(tg_env* env, StepParams& p, cudaStream_t s) {
+    const DevCfg& d = env->dev;
+    int E = env->tile;
+    // shared-memory carve-up
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 127) / 128 * 128; return (int)o; };
+    for (;;) {
+        off = 0;
+        p.off_hot = take((size_t)E * 32);
+        p.off_brd = take((size_t)E * d.board_stride + 16);
+        p.off_iboard = take((size_t)E * d.OB);
+        p.off_imask = take((size_t)E * d.OB);
+        p.off_iholder = take((size_t)E * 16);
+        p.off_iqueue = take((size_t)E * d.OQ);
+        p.off_bar = take(16);
+        if (off <= 200 * 1024 || E == 32) break;
+        E -= 32;
+    }
+    if (off > 227 * 1024) return fail(env, TG_ERR_CONFIG, "board too large for the shared-memory tile (%zu B)", off);
+    p.cfg = d;
+    if (d.W == 10 && d.H == 20) return launch_step_t<10, 20, uint32_t>(env, p, E, off, s);
+    if (d.W == 20 && d.H == 40) return launch_step_t<20, 40, uint64_t>(env, p, E, off, s);
+    if (env->col64) return launch_step_t<0, 0, uint64_t>(env, p, E, off, s);
+    return launch_step_t<0, 0, uint32_t>(env, p, E, off, s);
+}
+
+static int check_obs(tg_env* env, const tg_obs& o) {
+    if (!o.board || !o.mask || !o.holder || !o.queue) return fail(env, TG_ERR_POINTER, "observation pointer is NULL");
+    if (misaligned(o.board) || misaligned(o.mask) || misaligned(o.holder) || misaligned(o.queue))
+        return fail(env, TG_ERR_POINTER, "observation pointer not 16-byte aligned");
+    return TG_OK;
+}
+
+extern "C" int tg_reset(tg_env* env, tg_state st, int64_t n, const uint64_t* d_seeds, const uint8_t* d_reset_mask,
+                        tg_obs obs, void* stream) {
+    if (!env) return TG_ERR_POINTER;
+    if (n <= 0) return fail(env, TG_ERR_ARG, "n must be positive");
+    int rc = check_state(env, st); if (rc) return rc;
+    rc = check_obs(env, obs); if (rc) return rc;
+    CUDA_TRY(env, cudaSetDevice(env->device));
+    StepParams p;
+    memset(&p, 0, sizeof p);
+    p.n = n; p.hot = (uint8_t*)st.hot; p.board = (uint8_t*)st.board; p.rng = (uint8_t*)st.rng; p.seq = st.piece_seq;
+    p.seeds = d_seeds; p.reset_mask = d_reset_mask;
+    p.o_board = obs.board; p.o_mask = obs.mask; p.o_holder = obs.holder; p.o_queue = obs.queue;
+    p.mode = 1;
+    return launch_step(env, p, (cudaStream_t)stream);
+}
+
+extern "C" int tg_step(tg_env* env, tg_state st, int64_t n, const int32_t* d_actions, tg_obs obs, tg_step_out out,
+                       tg_stats* d_stats, void* stream) {
+    if (!env) return TG_ERR_POINTER;
+    if (n <= 0) return fail(env, TG_ERR_ARG, "n must be positive");
+    int rc = check_state(env, st); if (rc) return rc;
+    rc = check_obs(env, obs); if (rc) return rc;
+    if (!d_actions || !out.reward || !out.terminated || !out.truncated || !out.lines)
+        return fail(env, TG_ERR_POINTER, "actions / step outputs pointer is NULL");
+    CUDA_TRY(env, cudaSetDevice(env->device));
+    StepParams p;
+    memset(&p, 0, sizeof p);
+    p.n = n; p.hot = (uint8_t*)st.hot; p.board = (uint8_t*)st.board; p.rng = (uint8_t*)st.rng; p.seq = st.piece_seq;
+    p.actions = d_actions;
+    p.o_board = obs.board; p.o_mask = obs.mask; p.o_holder = obs.holder; p.o_queue = obs.queue;
+    p.reward = out.reward; p.terminated = out.terminated; p.truncated = out.truncated; p.lines = out.lines;
+    p.stats = (double*)d_stats;
+    p.mode = 0;
+    return launch_step(env, p, (cudaStream_t)stream);
+}
+
+// ---- host-buffer step (e2e path): H2D actions, step, D2H observation dict + 5-tuple -----------------
+static int ensure_stage(tg_env* env, int slot, size_t bytes) {
+    if (env->stage_bytes[slot] >= bytes) return TG_OK;
+    if (env->stage[slot]) cudaFree(env->stage[slot]);
+    env->stage[slot] = nullptr; env->stage_bytes[slot] = 0;
+    CUDA_TRY(env, cudaMalloc(&env->stage[slot], bytes));
+    env->stage_bytes[slot] = bytes;
+    return TG_OK;
+}
+
+extern "C" int tg_step_host(tg_env* env, tg_state st, int64_t n, const int32_t* h_actions, tg_obs h_obs, tg_step_out h_out) {
+    if (!env) return TG_ERR_POINTER;
+    if (n <= 0) return fail(env, TG_ERR_ARG, "n must be positive");
+    if (!h_actions || !h_obs.board || !h_obs.mask || !h_obs.holder || !h_obs.queue || !h_out.reward || !h_out.terminated ||
+        !h_out.truncated || !h_out.lines)
+        return fail(env, TG_ERR_POINTER, "host buffer is NULL");
+    int rc = check_state(env, st); if (rc) return rc;
+    CUDA_TRY(env, cudaSetDevice(env->device));
+    if (!env->hs_init) {
+        for (int i = 0; i < 3; i++) CUDA_TRY(env, cudaStreamCreateWithFlags(&env->hs[i], cudaStreamNonBlocking));
+        env->hs_init = true;
+    }
+    const DevCfg& d = env->dev;
+    // chunk the env range so that the D2H of chunk k overlaps the kernel of chunk k+1
+    const int NCH = 3;
+    int64_t chunk = (n + NCH - 1) / NCH;
+    chunk = (chunk + 127) / 128 * 128;  // keeps every chunk's base 16-byte aligned in all arrays
+    auto r16 = [](size_t v) { return (v + 15) / 16 * 16; };
+    const size_t o_mask = r16((size_t)n * d.OB), o_holder = o_mask + r16((size_t)n * d.OB), o_queue = o_holder + (size_t)n * 16;
+    const size_t obs_total = o_queue + (size_t)n * d.OQ;
+    const size_t o_lines = r16((size_t)n * 4), o_term = o_lines + r16((size_t)n * 4), o_trunc = o_term + r16((size_t)n);
+    const size_t out_total = o_trunc + r16((size_t)n);
+    rc = ensure_stage(env, 0, (size_t)n * 4); if (rc) return rc;   // actions
+    rc = ensure_stage(env, 1, obs_total); if (rc) return rc;       // observation dict
+    rc = ensure_stage(env, 2, out_total); if (rc) return rc;       // reward, lines, terminated, truncated
+    uint8_t* s_board = (uint8_t*)env->stage[1];
+    uint8_t* s_mask = s_board + o_mask;
+    uint8_t* s_holder = s_board + o_holder;
+    uint8_t* s_queue = s_board + o_queue;
+    uint8_t* so = (uint8_t*)env->stage[2];
+    float* s_rew = (float*)so;
+    int32_t* s_lines = (int32_t*)(so + o_lines);
+    uint8_t* s_term = so + o_term;
+    uint8_t* s_trunc = so + o_trunc;
+    int32_t* s_act = (int32_t*)env->stage[0];
+    int k = 0;
+    for (int64_t b = 0; b < n; b += chunk, k++) {
+        int64_t m = n - b < chunk ? n - b : chunk;
+        cudaStream_t s = env->hs[k % 3];
+        CUDA_TRY(env, cudaMemcpyAsync(s_act + b, h_actions + b, (size_t)m * 4, cudaMemcpyHostToDevice, s));
+        tg_state sc = st;
+        sc.hot = (uint8_t*)st.hot + b * 32; sc.board = (uint8_t*)st.board + b * d.board_stride; sc.rng = (uint8_t*)st.rng + b * d.rng_stride;
+        if (st.piece_seq) sc.piece_seq = st.piece_seq + b * d.seq_len;
+        StepParams p;
+        memset(&p, 0, sizeof p);
+        p.n = m; p.hot = (uint8_t*)sc.hot; p.board = (uint8_t*)sc.board; p.rng = (uint8_t*)sc.rng; p.seq = sc.piece_seq;
+        p.actions = s_act + b;
+        p.o_board = s_board + b * d.OB; p.o_mask = s_mask + b * d.OB; p.o_holder = s_holder + b * 16; p.o_queue = s_queue + b * d.OQ;
+        p.reward = s_rew + b; p.terminated = s_term + b; p.truncated = s_trunc + b; p.lines = s_lines + b;
+        p.mode = 0;
+        DevCfg saved = env->dev;
+        env->dev.env_id_offset += (unsigned long long)b;
+        rc = launch_step(env, p, s);
+        env->dev = saved;
+        if (rc) return rc;
+        CUDA_TRY(env, cudaMemcpyAsync(h_obs.board + b * d.OB, p.o_board, (size_t)m * d.OB, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(env, cudaMemcpyAsync(h_obs.mask + b * d.OB, p.o_mask, (size_t)m * d.OB, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(env, cudaMemcpyAsync(h_obs.holder + b * 16, p.o_holder, (size_t)m * 16, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(env, cudaMemcpyAsync(h_obs.queue + b * d.OQ, p.o_queue, (size_t)m * d.OQ, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(env, cudaMemcpyAsync(h_out.reward + b, p.reward, (size_t)m * 4, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(env, cudaMemcpyAsync(h_out.lines + b, p.lines, (size_t)m * 4, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(env, cudaMemcpyAsync(h_out.terminated + b, p.terminated, (size_t)m, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(env, cudaMemcpyAsync(h_out.truncated + b, p.truncated, (size_t)m, cudaMemcpyDeviceToHost, s));
+    }
+    for (int i = 0; i < 3; i++) CUDA_TRY(env, cudaStreamSynchronize(env->hs[i]));
+    return TG_OK;
+}
+
+// ---- numpy-exact seeding ------------------------------------------------------------------------
+extern "C" int tg_seed_numpy(tg_env* env, tg_state st, int64_t n, const uint64_t* d_pcg, const uint8_t* d_mask, void* stream) {
+    if (!env) return TG_ERR_POINTER;
+    if (env->cfg.rng_mode != TG_RNG_NUMPY) return fail(env, TG_ERR_ARG, "tg_seed_numpy needs rng_mode = TG_RNG_NUMPY");
+    if (!d_pcg || !st.rng) return fail(env, TG_ERR_POINTER, "NULL pointer");
+    CUDA_TRY(env, cudaSetDevice(env->device));
+    int T = 256;
+    k_seed_numpy<<<(unsigned)((n + T - 1) / T), T, 0, (cudaStream_t)stream>>>((uint8_t*)st.rng, env->dev.rng_stride, n, d_pcg, d_mask);
+    CUDA_TRY(env, cudaGetLastError());
+    return TG_OK;
+}
+
+// ---- state access -----------------------------------------------------------------------------------
+extern "C" int tg_get_state(tg_env* env, tg_state st, int64_t n, uint8_t* d_board, int32_t* d_scalars, void* stream) {
+    if (!env) return TG_ERR_POINTER;
+    int rc = check_state(env, st); if (rc) return rc;
+    CUDA_TRY(env, cudaSetDevice(env->device));
+    int T = 128;
+    if (env->col64) k_get_state<uint64_t><<<(unsigned)((n + T - 1) / T), T, 0, (cudaStream_t)stream>>>(env->dev, n, (const uint8_t*)st.hot, (const uint8_t*)st.board, d_board, d_scalars);
+    else k_get_state<uint32_t><<<(unsigned)((n + T - 1) / T), T, 0, (cudaStream_t)stream>>>(env->dev, n, (const uint8_t*)st.hot, (const uint8_t*)st.board, d_board, d_scalars);
+    CUDA_TRY(env, cudaGetLastError());
+    return TG_OK;
+}
+
+extern "C" int tg_set_state(tg_env* env, tg_state st, int64_t n, const uint8_t* d_board, const int32_t* d_scalars,
+                            const uint8_t* d_mask, void* stream) {
+    if (!env) return TG_ERR_POINTER;
+    int rc = check_state(env, st); if (rc) return rc;
+    CUDA_TRY(env, cudaSetDevice(env->device));
+    int T = 128;
+    if (env->col64) k_set_state<uint64_t><<<(unsigned)((n + T - 1) / T), T, 0, (cudaStream_t)stream>>>(env->dev, n, (uint8_t*)st.hot, (uint8_t*)st.board, d_board, d_scalars, d_mask);
+    else k_set_state<uint32_t><<<(unsigned)((n + T - 1) / T), T, 0, (cudaStream_t)stream>>>(env->dev, n, (uint8_t*)st.hot, (uint8_t*)st.board, d_board, d_scalars, d_mask);
+    CUDA_TRY(env, cudaGetLastError());
+    return TG_OK;
+}
+
+// ---- wrappers (tg_wrappers.cuh) ------------------------------------------------------------------------
+#include "tg_wrappers.cuh"

@@ -1,0 +1,424 @@
+// tg_device.cuh -- device-side building blocks of the B200 Tetris simulator.
+//
+// Data layout in HBM (per env, structure-of-records; all strides are multiples of 16 B so a tile
+// of consecutive envs is one contiguous TMA bulk copy):
+//   hot   [32 B]  w0 = x|y|piece|rot|holder|flags, w1 = 7-bag nibbles + index, w2:w3 = queue nibbles,
+//                 w4..w6 = episode return / length / lines, w7 spare
+//   board [BS B]  W column bitboards (bit r = row r occupied, floor rows H..H_pad-1 always set;
+//                 u32 when H_pad <= 32 else u64)  followed by the piece-id plane, nibble-packed
+//                 row-major (row r = nibbles [r*W, (r+1)*W))
+//   rng   [16|48 B] Philox key+counter | stream cursor | PCG64 state (numpy-exact mode)
+//
+// Bitboard formulation (ours; the reference works on byte matrices, envs/tetris.py:408-564):
+//   B(piece,rot,x) = OR over the 4 cells (i,j) of  col[x+j-P] >> i      (walls read as all-ones)
+//   collision at y  <=>  bit y of B          (Tetris.collision, envs/tetris.py:408-427)
+//   hard drop from y = y + ctz(B >> (y+1))   (Tetris.drop_active_tetromino, envs/tetris.py:445-448)
+//   full rows       = AND over columns       (Tetris.clear_filled_rows, envs/tetris.py:481-512)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace tg {
+
+constexpr int P = 4;  // padding (envs/tetris.py:130)
+
+enum Op : int { OP_LEFT = 0, OP_RIGHT, OP_DOWN, OP_CW, OP_CCW, OP_SWAP, OP_HARD, OP_NOOP };
+
+// Everything a kernel needs to know about the env configuration (passed by value).
+struct DevCfg {
+    int W, H, Wp, Hp, Q;
+    int gravity, autoreset, rng_mode, terminate_on_illegal;
+    int board_stride;  // bytes per env in state.board
+    int ids_off;       // byte offset of the nibble id plane inside a board record
+    int ids_words;     // u32 words of the id plane (ceil(H*W/8))
+    int rng_stride;
+    int OB;            // obs board bytes = Hp*Wp
+    int OQ;            // obs queue bytes = 16*Q
+    int A, F;          // placements 4W, features W+3
+    int rgb_w;         // Wp + 4*max(Q,1)
+    int spawn_x[7];    // W_pad//2 - n//2  (Tetris.reset_tetromino_position, envs/tetris.py:536-541)
+    unsigned char op_lut[8];    // action id -> Op following the elif order of envs/tetris.py:223-256
+    unsigned char skipgrav[8];  // action == actions.hard_drop (envs/tetris.py:259)
+    int act_hard, act_noop;
+    double r_alife, r_go, r_invalid;
+    long long seq_len;
+    unsigned long long env_id_offset;
+};
+
+// Constant piece tables, generated on the host by literally rotating the reference's base
+// matrices with rot90 (tg_api.cu: build_tables) and uploaded once per device.
+//   c_cells[p][r]  : 4 cells, nibble k = (i << 2) | j   (row i, column j inside the n x n box)
+//   c_rowbytes[p][r][i] : row i of the matrix zero-padded to 4x4, one id-valued byte per cell
+//   c_n[p]         : matrix size n
+//   c_colors[v]    : RGB of cell value v (envs/tetris.py:45-75)
+__constant__ unsigned short c_cells[7][4];
+__constant__ unsigned int c_rowbytes[7][4][4];
+__constant__ int c_n[7];
+__constant__ unsigned char c_colors[16][4];
+
+// ---- hot record ------------------------------------------------------------------------------
+struct Hot {
+    int x, y, p, r, hold, hold_r, swapped, over, pending;
+    uint32_t bag;  // 7 nibbles + index in bits 28..30
+    uint64_t queue;
+    float ep_ret;
+    uint32_t ep_len, ep_lines;
+};
+__device__ __forceinline__ void hot_load(Hot& h, const uint32_t* w) {
+    uint32_t a = w[0];
+    h.x = a & 63; h.y = (a >> 6) & 127; h.p = (a >> 13) & 7; h.r = (a >> 16) & 3;
+    h.hold = (a >> 18) & 15; h.hold_r = (a >> 22) & 3;
+    h.swapped = (a >> 24) & 1; h.over = (a >> 25) & 1; h.pending = (a >> 26) & 1;
+    h.bag = w[1];
+    h.queue = (uint64_t)w[2] | ((uint64_t)w[3] << 32);
+    h.ep_ret = __uint_as_float(w[4]); h.ep_len = w[5]; h.ep_lines = w[6];
+}
+__device__ __forceinline__ void hot_store(const Hot& h, uint32_t* w) {
+    w[0] = (uint32_t)h.x | ((uint32_t)h.y << 6) | ((uint32_t)h.p << 13) | ((uint32_t)h.r << 16) |
+           ((uint32_t)h.hold << 18) | ((uint32_t)h.hold_r << 22) | ((uint32_t)h.swapped << 24) |
+           ((uint32_t)h.over << 25) | ((uint32_t)h.pending << 26);
+    w[1] = h.bag;
+    w[2] = (uint32_t)h.queue; w[3] = (uint32_t)(h.queue >> 32);
+    w[4] = __float_as_uint(h.ep_ret); w[5] = h.ep_len; w[6] = h.ep_lines; w[7] = 0;
+}
+
+// ---- column bitboards -----------------------------------------------------------------------
+template <class COLT> __device__ __forceinline__ int ctz_t(COLT v);
+template <> __device__ __forceinline__ int ctz_t<uint32_t>(uint32_t v) { return __ffs((int)v) - 1; }
+template <> __device__ __forceinline__ int ctz_t<uint64_t>(uint64_t v) { return __ffsll((long long)v) - 1; }
+template <class COLT> __device__ __forceinline__ int popc_t(COLT v);
+template <> __device__ __forceinline__ int popc_t<uint32_t>(uint32_t v) { return __popc(v); }
+template <> __device__ __forceinline__ int popc_t<uint64_t>(uint64_t v) { return __popcll(v); }
+
+template <class COLT>
+__device__ __forceinline__ COLT col_at(const COLT* cols, int cx, int W) {
+    return (unsigned)cx < (unsigned)W ? cols[cx] : ~COLT(0);  // bedrock walls
+}
+// B mask of a piece orientation at padded x (see header comment)
+template <class COLT>
+__device__ __forceinline__ COLT bmask(const COLT* cols, int W, uint32_t cells, int x) {
+    COLT B = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        int c = (cells >> (4 * k)) & 15;
+        B |= col_at(cols, x + (c & 3) - P, W) >> (c >> 2);
+    }
+    return B;
+}
+template <class COLT>
+__device__ __forceinline__ COLT floor_bits(int H, int Hp) {
+    return (Hp >= (int)(8 * sizeof(COLT)) ? ~COLT(0) : ((COLT(1) << Hp) - 1)) & ~((COLT(1) << H) - 1);
+}
+
+// ---- nibble-packed id plane ---------------------------------------------------------------
+__device__ __forceinline__ uint32_t ids_get8(const uint32_t* ids, int nib_off) {
+    int b = nib_off * 4;
+    return __funnelshift_r(ids[b >> 5], ids[(b >> 5) + 1], b & 31);
+}
+__device__ __forceinline__ void ids_put(uint32_t* ids, int nib_off, int cnt, uint32_t v) {
+    int b = nib_off * 4, wi = b >> 5, sh = b & 31;
+    uint64_t m = (cnt >= 8 ? 0xFFFFFFFFull : ((1ull << (4 * cnt)) - 1)) << sh;
+    uint64_t vv = (uint64_t)v << sh;
+    uint32_t lm = (uint32_t)m, hm = (uint32_t)(m >> 32);
+    ids[wi] = (ids[wi] & ~lm) | ((uint32_t)vv & lm);
+    if (hm) ids[wi + 1] = (ids[wi + 1] & ~hm) | ((uint32_t)(vv >> 32) & hm);
+}
+__device__ __forceinline__ void ids_set1(uint32_t* ids, int nib_off, uint32_t v) {
+    int wi = nib_off >> 3, sh = (nib_off & 7) * 4;
+    ids[wi] = (ids[wi] & ~(0xFu << sh)) | (v << sh);
+}
+__device__ __forceinline__ uint32_t ids_get1(const uint32_t* ids, int nib_off) {
+    return (ids[nib_off >> 3] >> ((nib_off & 7) * 4)) & 15u;
+}
+
+// ---- randomizers ------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al. 2011), counter-based: one call -> 4 x u32.
+__device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int i = 0; i < 10; i++) {
+        uint32_t h0 = __umulhi(0xD2511F53u, c[0]), l0 = 0xD2511F53u * c[0];
+        uint32_t h1 = __umulhi(0xCD9E8D57u, c[2]), l1 = 0xCD9E8D57u * c[2];
+        uint32_t n0 = h1 ^ c[1] ^ k0, n2 = h0 ^ c[3] ^ k1;
+        c[0] = n0; c[1] = l1; c[2] = n2; c[3] = l0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+}
+
+struct Rng {
+    // view over one env's rng record in GLOBAL memory (touched only when a piece is drawn)
+    uint32_t* rec;
+    const uint8_t* seq;  // this env's injected stream (TG_RNG_SEQUENCE)
+    uint64_t gid;        // global env id
+};
+
+// PCG64 (numpy): state = state * MULT + inc; out = rotr64(hi ^ lo, hi >> 58)
+__device__ __forceinline__ uint64_t pcg64_next64(uint32_t* rec) {
+    unsigned __int128 st = ((unsigned __int128)(((uint64_t*)rec)[0]) << 64) | ((uint64_t*)rec)[1];
+    unsigned __int128 inc = ((unsigned __int128)(((uint64_t*)rec)[2]) << 64) | ((uint64_t*)rec)[3];
+    const unsigned __int128 MULT = ((unsigned __int128)0x2360ED051FC65DA4ULL << 64) | 0x4385DF649FCCF645ULL;
+    st = st * MULT + inc;
+    uint64_t hi = (uint64_t)(st >> 64), lo = (uint64_t)st;
+    ((uint64_t*)rec)[0] = hi; ((uint64_t*)rec)[1] = lo;
+    uint64_t x = hi ^ lo;
+    unsigned rot = (unsigned)(hi >> 58);
+    return (x >> rot) | (x << ((64 - rot) & 63));
+}
+__device__ __forceinline__ uint32_t pcg64_next32(uint32_t* rec) {
+    if (rec[8]) { rec[8] = 0; return rec[9]; }
+    uint64_t v = pcg64_next64(rec);
+    rec[8] = 1; rec[9] = (uint32_t)(v >> 32);
+    return (uint32_t)v;
+}
+
+// in-place Fisher-Yates of the 7-bag (BagRandomizer.shuffle_bag, components/tetromino_randomizer.py:82-85)
+__device__ __noinline__ uint32_t shuffle_bag(const DevCfg& cfg, Rng& g, uint32_t bag) {
+    uint32_t j6[6];
+    if (cfg.rng_mode == 2) {
+        // numpy Generator.shuffle: for i = 6..1: j = random_interval(i) (masked rejection on next_uint32)
+        for (int i = 6; i >= 1; i--) {
+            uint32_t mask = i | (i >> 1); mask |= mask >> 2;
+            uint32_t v;
+            do { v = pcg64_next32(g.rec) & mask; } while (v > (uint32_t)i);
+            j6[6 - i] = v;
+        }
+    } else {
+        uint64_t seed = ((uint64_t*)g.rec)[0];
+        uint32_t ctr = g.rec[2];
+        g.rec[2] = ctr + 1;
+        uint32_t c[4] = {ctr, (uint32_t)g.gid, (uint32_t)(g.gid >> 32), 0u};
+        uint32_t d[4] = {ctr, (uint32_t)g.gid, (uint32_t)(g.gid >> 32), 1u};
+        philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+        philox4x32_10(d, (uint32_t)seed, (uint32_t)(seed >> 32));
+        j6[0] = __umulhi(c[0], 7u); j6[1] = __umulhi(c[1], 6u); j6[2] = __umulhi(c[2], 5u);
+        j6[3] = __umulhi(c[3], 4u); j6[4] = __umulhi(d[0], 3u); j6[5] = __umulhi(d[1], 2u);
+    }
+#pragma unroll
+    for (int i = 6; i >= 1; i--) {
+        uint32_t j = j6[6 - i];
+        uint32_t vi = (bag >> (4 * i)) & 15u, vj = (bag >> (4 * j)) & 15u;
+        bag = (bag & ~(15u << (4 * i))) | (vj << (4 * i));
+        bag = (bag & ~(15u << (4 * j))) | (vi << (4 * j));
+    }
+    return bag & 0x0FFFFFFFu;  // index = 0
+}
+
+// Randomizer.get_next_tetromino
+__device__ __forceinline__ int draw_piece(const DevCfg& cfg, Rng& g, Hot& h) {
+    if (cfg.rng_mode == 1) {
+        uint64_t cur = ((uint64_t*)g.rec)[0];
+        ((uint64_t*)g.rec)[0] = cur + 1;
+        return g.seq[cur % (uint64_t)cfg.seq_len];
+    }
+    // BagRandomizer.get_next_tetromino (components/tetromino_randomizer.py:67-80)
+    int idx = (h.bag >> 28) & 7;
+    int v = (h.bag >> (4 * idx)) & 15;
+    idx++;
+    if (idx >= 7) h.bag = shuffle_bag(cfg, g, h.bag);
+    else h.bag = (h.bag & 0x0FFFFFFFu) | ((uint32_t)idx << 28);
+    return v;
+}
+// TetrominoQueue.get_next_tetromino (components/tetromino_queue.py:35-42)
+__device__ __forceinline__ int queue_pop(const DevCfg& cfg, Rng& g, Hot& h) {
+    int v = (int)(h.queue & 15u);
+    uint64_t nv = (uint64_t)draw_piece(cfg, g, h);
+    h.queue = (h.queue >> 4) | (nv << (4 * (cfg.Q - 1)));
+    return v;
+}
+
+// ---- env logic (one thread = one env; board record in shared memory) --------------------------
+// Tetris.reset (envs/tetris.py:274-307) + TetrominoQueue.reset + BagRandomizer.reset
+template <class COLT>
+__device__ __forceinline__ void env_reset(const DevCfg& cfg, Hot& h, uint32_t* rec, Rng& g) {
+    COLT* cols = (COLT*)rec;
+    uint32_t* ids = rec + cfg.ids_off / 4;
+    COLT fl = floor_bits<COLT>(cfg.H, cfg.Hp);
+    for (int c = 0; c < cfg.W; c++) cols[c] = fl;
+    for (int i = 0; i < cfg.ids_words; i++) ids[i] = 0;
+    h.over = 0; h.pending = 0;
+    if (cfg.rng_mode != 1) h.bag = shuffle_bag(cfg, g, 0x06543210u);
+    h.queue = 0;
+    for (int i = 0; i < cfg.Q; i++) h.queue |= (uint64_t)draw_piece(cfg, g, h) << (4 * i);
+    h.p = queue_pop(cfg, g, h);
+    h.r = 0; h.x = cfg.spawn_x[h.p]; h.y = 0;
+    h.hold = 0; h.hold_r = 0; h.swapped = 0;
+    h.ep_ret = 0.f; h.ep_len = 0; h.ep_lines = 0;
+}
+
+// row compaction after a line clear (Tetris.clear_filled_rows, envs/tetris.py:481-512)
+template <class COLT>
+__device__ __noinline__ void clear_rows(const DevCfg& cfg, COLT* cols, uint32_t* ids, COLT full) {
+    const int W = cfg.W, H = cfg.H;
+    COLT any = 0;
+    for (int c = 0; c < W; c++) any |= cols[c];
+    int top = ctz_t<COLT>(any);  // rows above `top` are empty (floor bits guarantee any != 0)
+    // id plane: surviving rows slide down, keeping order
+    int dst = H - 1;
+    for (int src = H - 1; src >= top; --src) {
+        if ((full >> src) & 1) continue;
+        if (dst != src)
+            for (int k = 0; k < W; k += 8) {
+                int cnt = min(8, W - k);
+                ids_put(ids, dst * W + k, cnt, ids_get8(ids, src * W + k));
+            }
+        dst--;
+    }
+    for (; dst >= top; --dst)
+        for (int k = 0; k < W; k += 8) ids_put(ids, dst * W + k, min(8, W - k), 0u);
+    // column bitboards: delete the full rows' bits, upper bits move down (towards higher row index)
+    for (int c = 0; c < W; c++) {
+        COLT v = cols[c], f = full;
+        while (f) {
+            int r = ctz_t<COLT>(f);
+            f &= f - 1;
+            COLT below = (COLT(1) << r) - 1;  // rows above r (smaller index)
+            v = (v & ~((below << 1) | 1)) | ((v & below) << 1);
+        }
+        cols[c] = v;
+    }
+}
+
+struct StepResult {
+    double reward;
+    int lines;
+    int terminated;
+    int dirty;  // board record changed
+    int did_reset;
+};
+
+// Tetris.commit_active_tetromino (envs/tetris.py:450-479); B = bmask of the active piece at h.x
+template <class COLT>
+__device__ __forceinline__ void env_commit(const DevCfg& cfg, Hot& h, uint32_t* rec, Rng& g, COLT B,
+                                           StepResult& res) {
+    COLT* cols = (COLT*)rec;
+    uint32_t* ids = rec + cfg.ids_off / 4;
+    if ((B >> h.y) & 1) {
+        res.reward = cfg.r_go;
+        h.over = 1;
+        return;
+    }
+    h.y += ctz_t<COLT>(B >> (h.y + 1));  // drop_active_tetromino
+    uint32_t cells = c_cells[h.p][h.r];
+    COLT touched = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {  // place_active_tetromino / project_tetromino
+        int c = (cells >> (4 * k)) & 15;
+        int row = h.y + (c >> 2), col = h.x + (c & 3) - P;
+        cols[col] |= COLT(1) << row;
+        touched |= COLT(1) << row;
+        ids_set1(ids, row * cfg.W + col, (uint32_t)(h.p + 2));
+    }
+    COLT full = touched;
+    for (int c = 0; c < cfg.W; c++) full &= cols[c];
+    int lines = popc_t<COLT>(full);
+    if (lines) clear_rows<COLT>(cfg, cols, ids, full);
+    res.lines = lines;
+    res.reward = (double)(lines * lines * cfg.W);  // Tetris.score (envs/tetris.py:621-630)
+    // spawn_tetromino (envs/tetris.py:393-401)
+    h.p = queue_pop(cfg, g, h);
+    h.r = 0; h.x = cfg.spawn_x[h.p]; h.y = 0;
+    COLT Bn = bmask<COLT>(cols, cfg.W, c_cells[h.p][0], h.x);
+    h.over = (int)(Bn & 1);
+    res.reward += cfg.r_alife;
+    if (h.over) res.reward = cfg.r_go;
+    h.swapped = 0;
+    res.dirty = 1;
+}
+
+// Tetris.step (envs/tetris.py:203-272) with the vector-env autoreset policy around it.
+// `force_x/force_r` >= 0: grouped placement (GroupedActionsObservations.step sets env.x and the
+// rotated piece, y untouched, then base hard_drop; wrappers/grouped.py:241-259).
+template <class COLT>
+__device__ __forceinline__ void env_step(const DevCfg& cfg, Hot& h, uint32_t* rec, Rng& g, int action,
+                                         StepResult& res) {
+    COLT* cols = (COLT*)rec;
+    res.reward = 0.0; res.lines = 0; res.dirty = 0; res.did_reset = 0;
+    int op = OP_NOOP, skipgrav = 0;
+    if ((unsigned)action < 8u) { op = cfg.op_lut[action]; skipgrav = cfg.skipgrav[action]; }
+    if (op == OP_SWAP && !h.swapped) {  // envs/tetris.py:242-252 + TetrominoHolder.swap
+        int np, nr;
+        if (h.hold == 0) { np = queue_pop(cfg, g, h); nr = 0; }
+        else { np = h.hold - 1; nr = h.hold_r; }
+        h.hold = h.p + 1; h.hold_r = h.r;
+        h.p = np; h.r = nr; h.swapped = 1;
+        h.x = cfg.spawn_x[np]; h.y = 0;
+    }
+    int dx = (op == OP_LEFT) ? -1 : (op == OP_RIGHT ? 1 : 0);
+    int dr = (op == OP_CW) ? 1 : (op == OP_CCW ? 3 : 0);
+    int dy = (op == OP_DOWN) ? 1 : 0;
+    int cx = h.x + dx, cr = (h.r + dr) & 3, cy = h.y + dy;
+    COLT B = bmask<COLT>(cols, cfg.W, c_cells[h.p][cr], cx);
+    if (!((B >> cy) & 1)) { h.x = cx; h.r = cr; h.y = cy; }
+    else if (dx | dr) B = bmask<COLT>(cols, cfg.W, c_cells[h.p][h.r], h.x);
+    bool do_commit = (op == OP_HARD);
+    if (cfg.gravity && !skipgrav) {  // envs/tetris.py:259-264
+        if (!((B >> (h.y + 1)) & 1)) h.y += 1;
+        else do_commit = true;
+    }
+    if (do_commit) env_commit<COLT>(cfg, h, rec, g, B, res);
+    res.terminated = h.over;
+}
+
+// ---- features from column bitboards (FeatureVectorObservation, wrappers/observation.py:177-278) --
+// `cols` already has the rows the reference zeroes (row 0, or rows 0-1) cleared by the caller.
+template <class COLT>
+__device__ __forceinline__ void col_features(COLT col, int H, int& height, int& holes) {
+    COLT v = col & ((COLT(1) << H) - 1);
+    if (v == 0) { height = 0; holes = 0; return; }
+    int first = ctz_t<COLT>(v);
+    height = H - first;                               // calc_height
+    holes = height - popc_t<COLT>(v);                 // empty cells below the first filled one
+}
+
+// Features of (cols | optional piece cells), after deleting `full` rows and zeroing `rowzero` rows.
+// Q1: the reference zeroes padded rows 0 (mask all zero) or 0-1 (mask has a 1) through
+// integer fancy indexing, it does NOT mask the active piece (wrappers/observation.py:252).
+template <class COLT>
+__device__ __forceinline__ void placement_features(const DevCfg& cfg, const COLT* cols, uint32_t cells, int x, int y,
+                                                   bool place, bool do_clear, COLT rowzero, uint8_t* out, int& lines_out) {
+    const int W = cfg.W, H = cfg.H;
+    int crow[4], ccol[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        int c = (cells >> (4 * k)) & 15;
+        crow[k] = y + (c >> 2);
+        ccol[k] = place ? x + (c & 3) - P : -1;
+    }
+    COLT full = 0;
+    if (place && do_clear) {
+        full = (COLT(1) << crow[0]) | (COLT(1) << crow[1]) | (COLT(1) << crow[2]) | (COLT(1) << crow[3]);
+        for (int c = 0; c < W; c++) {
+            COLT v = cols[c];
+#pragma unroll
+            for (int k = 0; k < 4; k++) if (ccol[k] == c) v |= COLT(1) << crow[k];
+            full &= v;
+        }
+        full &= (COLT(1) << H) - 1;
+    }
+    lines_out = popc_t<COLT>(full);
+    int prev = 0, maxh = 0, holes = 0, bump = 0;
+    for (int c = 0; c < W; c++) {
+        COLT v = cols[c];
+#pragma unroll
+        for (int k = 0; k < 4; k++) if (ccol[k] == c) v |= COLT(1) << crow[k];
+        COLT f = full;
+        while (f) {  // Tetris.clear_filled_rows on the projected copy (wrappers/grouped.py:171-177)
+            int r = ctz_t<COLT>(f);
+            f &= f - 1;
+            COLT below = (COLT(1) << r) - 1;
+            v = (v & ~((below << 1) | 1)) | ((v & below) << 1);
+        }
+        v &= ~rowzero;
+        int hgt, hol;
+        col_features<COLT>(v, H, hgt, hol);
+        out[c] = (uint8_t)hgt;
+        holes += hol;
+        maxh = max(maxh, hgt);
+        if (c > 0) bump += abs(hgt - prev);
+        prev = hgt;
+    }
+    out[W] = (uint8_t)maxh;
+    out[W + 1] = (uint8_t)holes;  // uint8 wrap (wrappers/observation.py:277)
+    out[W + 2] = (uint8_t)bump;
+}
+
+}  // namespace tg

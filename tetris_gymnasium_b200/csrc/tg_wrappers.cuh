@@ -1,0 +1,343 @@
+// tg_wrappers.cuh -- observation wrappers and the grouped (placement) path.
+//   FeatureVectorObservation  (wrappers/observation.py:118-278)  -> k_features / placement_features
+//   RgbObservation            (wrappers/observation.py:11-74)    -> k_rgb
+//   GroupedActionsObservations(wrappers/grouped.py:16-294)       -> k_grouped_feats / k_grouped_boards
+//                                                                   (+ k_step mode 2 executes the placement)
+// Included at the end of tg_api.cu (uses tg_env, fail, CUDA_TRY, check_state).
+#pragma once
+
+namespace tg {
+
+// FeatureVectorObservation applied to the base env's observation (rows 0-1 zeroed, active piece projected)
+template <class COLT>
+__global__ void k_features(const DevCfg cfg, int64_t n, const uint8_t* hot, const uint8_t* board, uint8_t* feats) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    Hot h;
+    hot_load(h, (const uint32_t*)(hot + e * 32));
+    const COLT* cols = (const COLT*)(board + e * cfg.board_stride);
+    uint32_t cells = c_cells[h.p][h.r];
+    COLT B = bmask<COLT>(cols, cfg.W, cells, h.x);
+    int lines;
+    uint8_t f[32];
+    placement_features<COLT>(cfg, cols, cells, h.x, h.y, !((B >> h.y) & 1), false, COLT(3), f, lines);
+    for (int i = 0; i < cfg.F; i++) feats[e * cfg.F + i] = f[i];
+}
+
+// One placement of GroupedActionsObservations.observation (wrappers/grouped.py:148-181).
+struct Placement { int x, y, rot, kind; };  // kind: 0 regular, 1 illegal (frame), 2 game over
+template <class COLT>
+__device__ __forceinline__ Placement eval_placement(const DevCfg& cfg, const COLT* cols, int piece, int rot0, int a, COLT& Bout) {
+    Placement pl;
+    int xb = a >> 2, rr = a & 3;
+    pl.rot = (rot0 + rr) & 3;              // cumulative rot90 presses (wrappers/grouped.py:153-154)
+    pl.x = xb + P - c_n[piece] / 2;        // wrappers/grouped.py:157-158
+    uint32_t cells = c_cells[piece][pl.rot];
+    COLT B = bmask<COLT>(cols, cfg.W, cells, pl.x);
+    pl.y = ctz_t<COLT>(B >> 1);            // while !collision(y+1): y++  from y = 0, no test at y = 0 (Q3)
+    bool frame = false;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        int c = (cells >> (4 * k)) & 15;
+        frame |= (unsigned)(pl.x + (c & 3) - P) >= (unsigned)cfg.W;
+    }
+    pl.kind = frame ? 1 : (((B >> pl.y) & 1) ? 2 : 0);
+    Bout = B;
+    return pl;
+}
+
+// grouped observation with FeatureVectorObservation: feats u8[n][A][F], legal u8[n][A]
+template <class COLT>
+__global__ void k_grouped_feats(const DevCfg cfg, int64_t n, const uint8_t* hot, const uint8_t* board, uint8_t* feats,
+                                uint8_t* legal, const uint8_t* fill_high, int EPB) {
+    extern __shared__ __align__(16) uint8_t sm[];
+    const int W = cfg.W, A = cfg.A, F = cfg.F;
+    COLT* s_cols = (COLT*)sm;                                   // EPB * W
+    uint32_t* s_w0 = (uint32_t*)(sm + (size_t)EPB * W * sizeof(COLT));  // EPB
+    uint8_t* s_feats = (uint8_t*)(s_w0 + EPB);                  // EPB * A * F (16-aligned by construction of EPB)
+    uint8_t* s_legal = s_feats + (size_t)EPB * A * F;           // EPB * A
+    const int64_t base = (int64_t)blockIdx.x * EPB;
+    const int nv = (int)min((int64_t)EPB, n - base);
+    for (int i = threadIdx.x; i < nv * W; i += blockDim.x) {
+        int e = i / W, c = i - e * W;
+        s_cols[i] = ((const COLT*)(board + (base + e) * cfg.board_stride))[c];
+    }
+    for (int i = threadIdx.x; i < nv; i += blockDim.x) s_w0[i] = *(const uint32_t*)(hot + (base + i) * 32);
+    __syncthreads();
+    for (int it = threadIdx.x; it < nv * A; it += blockDim.x) {
+        int e = it / A, a = it - e * A;
+        uint32_t w0 = s_w0[e];
+        int piece = (w0 >> 13) & 7, rot0 = (w0 >> 16) & 3;
+        const COLT* cols = s_cols + e * W;
+        uint8_t* out = s_feats + (size_t)it * F;
+        if (fill_high && fill_high[base + e]) {
+            // illegal action + terminate: obs = ones * high (wrappers/grouped.py:221-226); legal mask unchanged
+            for (int i = 0; i < F; i++) out[i] = (uint8_t)(cfg.H * cfg.W);
+            s_legal[it] = legal[(base + e) * A + a];
+            continue;
+        }
+        COLT B;
+        Placement pl = eval_placement<COLT>(cfg, cols, piece, rot0, a, B);
+        s_legal[it] = pl.kind != 1;
+        if (pl.kind == 1) {          // ones board, row 0 zeroed -> heights H-1
+            for (int i = 0; i <= W; i++) out[i] = (uint8_t)(cfg.H - 1);
+            out[W + 1] = 0; out[W + 2] = 0;
+        } else if (pl.kind == 2) {   // zeros board
+            for (int i = 0; i < F; i++) out[i] = 0;
+        } else {
+            int lines;
+            placement_features<COLT>(cfg, cols, c_cells[piece][pl.rot], pl.x, pl.y, true, true, COLT(1), out, lines);
+        }
+    }
+    __syncthreads();
+    // coalesced copy-out of the tile (contiguous in global memory)
+    {
+        size_t bytes = (size_t)nv * A * F;
+        uint8_t* g = feats + (size_t)base * A * F;
+        if ((bytes & 15) == 0 && (((uintptr_t)g) & 15) == 0) {
+            for (size_t i = threadIdx.x; i < bytes / 16; i += blockDim.x) ((uint4*)g)[i] = ((const uint4*)s_feats)[i];
+        } else {
+            for (size_t i = threadIdx.x; i < bytes; i += blockDim.x) g[i] = s_feats[i];
+        }
+        size_t lb = (size_t)nv * A;
+        uint8_t* gl = legal + (size_t)base * A;
+        if ((lb & 3) == 0 && (((uintptr_t)gl) & 3) == 0) {
+            for (size_t i = threadIdx.x; i < lb / 4; i += blockDim.x) ((uint32_t*)gl)[i] = ((const uint32_t*)s_legal)[i];
+        } else {
+            for (size_t i = threadIdx.x; i < lb; i += blockDim.x) gl[i] = s_legal[i];
+        }
+    }
+}
+
+// grouped observation without wrappers: boards u8[n][A][Hp][Wp]; one warp per (env, placement)
+template <class COLT>
+__global__ void k_grouped_boards(const DevCfg cfg, int64_t n, const uint8_t* hot, const uint8_t* board, uint8_t* boards,
+                                 uint8_t* legal, const uint8_t* fill_high) {
+    extern __shared__ __align__(16) uint8_t sm[];
+    const int W = cfg.W, H = cfg.H, Wp = cfg.Wp, A = cfg.A, OB = cfg.OB;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int OBr = (OB + 15) & ~15;
+    uint8_t* buf = sm + (size_t)warp * OBr;
+    const int64_t items = n * A;
+    for (int64_t it = (int64_t)blockIdx.x * nwarps + warp; it < items; it += (int64_t)gridDim.x * nwarps) {
+        int64_t e = it / A;
+        int a = (int)(it - e * A);
+        const uint8_t* rec = board + e * cfg.board_stride;
+        const COLT* cols = (const COLT*)rec;
+        const uint32_t* ids = (const uint32_t*)(rec + cfg.ids_off);
+        uint32_t w0 = *(const uint32_t*)(hot + e * 32);
+        int piece = (w0 >> 13) & 7, rot0 = (w0 >> 16) & 3;
+        uint8_t* g = boards + (size_t)it * OB;
+        int fillv = -1;
+        Placement pl;
+        COLT B;
+        if (fill_high && fill_high[e]) fillv = (uint8_t)(cfg.H * cfg.W);
+        else {
+            pl = eval_placement<COLT>(cfg, cols, piece, rot0, a, B);
+            if (lane == 0) legal[it] = pl.kind != 1;
+            if (pl.kind == 1) fillv = 1;
+            else if (pl.kind == 2) fillv = 0;
+        }
+        __syncwarp();
+        if (fillv >= 0) {
+            for (int i = lane; i < OB; i += 32) buf[i] = (uint8_t)fillv;
+        } else {
+            uint32_t cells = c_cells[piece][pl.rot];
+            int crow[4], ccol[4];
+            COLT full = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                int c = (cells >> (4 * k)) & 15;
+                crow[k] = pl.y + (c >> 2); ccol[k] = pl.x + (c & 3) - P;
+                full |= COLT(1) << crow[k];
+            }
+            for (int c = 0; c < W; c++) {
+                COLT v = cols[c];
+#pragma unroll
+                for (int k = 0; k < 4; k++) if (ccol[k] == c) v |= COLT(1) << crow[k];
+                full &= v;
+            }
+            full &= (COLT(1) << H) - 1;
+            int nclr = popc_t<COLT>(full);
+            for (int r = lane; r < cfg.Hp; r += 32) {
+                uint8_t* row = buf + r * Wp;
+                if (r >= H) { for (int c = 0; c < Wp; c++) row[c] = 1; continue; }
+                for (int c = 0; c < P; c++) { row[c] = 1; row[P + W + c] = 1; }
+                if (r < nclr) { for (int c = 0; c < W; c++) row[P + c] = 0; continue; }
+                int s = r - nclr;  // (r - nclr)-th surviving source row
+                COLT f = full;
+                while (f) { int fr = ctz_t<COLT>(f); f &= f - 1; if (fr <= s) s++; }
+                for (int c = 0; c < W; c++) row[P + c] = (uint8_t)ids_get1(ids, s * W + c);
+#pragma unroll
+                for (int k = 0; k < 4; k++) if (crow[k] == s) row[P + ccol[k]] = (uint8_t)(piece + 2);
+            }
+        }
+        __syncwarp();
+        if ((OB & 15) == 0 && (((uintptr_t)g) & 15) == 0) {
+            for (int i = lane; i < OB / 16; i += 32) ((uint4*)g)[i] = ((const uint4*)buf)[i];
+        } else {
+            for (int i = lane; i < OB; i += 32) g[i] = buf[i];
+        }
+        __syncwarp();
+    }
+}
+
+// RgbObservation.observation (wrappers/observation.py:38-74): one warp per env.
+template <class COLT>
+__global__ void k_rgb(const DevCfg cfg, int64_t n, const uint8_t* hot, const uint8_t* board, uint8_t* img) {
+    extern __shared__ __align__(16) uint8_t sm[];
+    const int W = cfg.W, H = cfg.H, Wp = cfg.Wp, Hp = cfg.Hp, RW = cfg.rgb_w, Q = cfg.Q;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int NP = Hp * RW;
+    const int NPr = (NP + 15) & ~15;
+    uint8_t* pix = sm + (size_t)warp * NPr;
+    for (int64_t e = (int64_t)blockIdx.x * nwarps + warp; e < n; e += (int64_t)gridDim.x * nwarps) {
+        Hot h;
+        hot_load(h, (const uint32_t*)(hot + e * 32));
+        const uint8_t* rec = board + e * cfg.board_stride;
+        const COLT* cols = (const COLT*)rec;
+        const uint32_t* ids = (const uint32_t*)(rec + cfg.ids_off);
+        uint32_t cells = c_cells[h.p][h.r];
+        COLT B = bmask<COLT>(cols, W, cells, h.x);
+        bool show = !((B >> h.y) & 1);
+        for (int i = lane; i < NP; i += 32) {
+            int r = i / RW, c = i - r * RW;
+            int v = 1;
+            if (c < Wp) {
+                if (r < H && c >= P && c < P + W) v = (int)ids_get1(ids, r * W + c - P);
+            } else {
+                int cc = c - Wp;
+                if (r < P) {                       // queue on the top right
+                    int q = cc >> 2;
+                    v = q < Q ? (int)((c_rowbytes[(int)((h.queue >> (4 * q)) & 15u)][0][r] >> (8 * (cc & 3))) & 255u) : 1;
+                } else if (r >= Hp - P) {          // holder on the bottom right, padded with bedrock
+                    if (cc < P) v = h.hold ? (int)((c_rowbytes[h.hold - 1][h.hold_r][r - (Hp - P)] >> (8 * cc)) & 255u) : 1;
+                }
+            }
+            pix[i] = (uint8_t)v;
+        }
+        __syncwarp();
+        if (show && lane < 4) {
+            int c = (cells >> (4 * lane)) & 15;
+            pix[(h.y + (c >> 2)) * RW + h.x + (c & 3)] = (uint8_t)(h.p + 2);
+        }
+        __syncwarp();
+        uint8_t* g = img + (size_t)e * NP * 3;
+        // 4 pixels -> 3 words
+        const uint32_t* col32 = (const uint32_t*)c_colors;
+        if ((NP & 3) == 0 && (((uintptr_t)g) & 3) == 0) {
+            for (int q4 = lane; q4 < NP / 4; q4 += 32) {
+                uint32_t pv = ((const uint32_t*)pix)[q4];
+                uint32_t c0 = col32[pv & 15], c1 = col32[(pv >> 8) & 15], c2 = col32[(pv >> 16) & 15], c3 = col32[(pv >> 24) & 15];
+                uint32_t w0 = (c0 & 0xFFFFFFu) | (c1 << 24);
+                uint32_t w1 = ((c1 >> 8) & 0xFFFFu) | (c2 << 16);
+                uint32_t w2 = ((c2 >> 16) & 0xFFu) | (c3 << 8);
+                uint32_t* o = (uint32_t*)g + 3 * q4;
+                o[0] = w0; o[1] = w1; o[2] = w2;
+            }
+        } else {
+            for (int i = lane; i < NP * 3; i += 32) { int px = i / 3; g[i] = c_colors[pix[px]][i - 3 * px]; }
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace tg
+
+// ---- host entry points -------------------------------------------------------------------------------
+extern "C" int tg_features(tg_env* env, tg_state st, int64_t n, uint8_t* d_feats, void* stream) {
+    if (!env) return TG_ERR_POINTER;
+    int rc = check_state(env, st); if (rc) return rc;
+    if (!d_feats) return fail(env, TG_ERR_POINTER, "d_feats is NULL");
+    CUDA_TRY(env, cudaSetDevice(env->device));
+    int T = 128;
+    unsigned g = (unsigned)((n + T - 1) / T);
+    if (env->col64) k_features<uint64_t><<<g, T, 0, (cudaStream_t)stream>>>(env->dev, n, (const uint8_t*)st.hot, (const uint8_t*)st.board, d_feats);
+    else k_features<uint32_t><<<g, T, 0, (cudaStream_t)stream>>>(env->dev, n, (const uint8_t*)st.hot, (const uint8_t*)st.board, d_feats);
+    CUDA_TRY(env, cudaGetLastError());
+    return TG_OK;
+}
+
+extern "C" int tg_render_rgb(tg_env* env, tg_state st, int64_t n, uint8_t* d_img, void* stream) {
+    if (!env) return TG_ERR_POINTER;
+    int rc = check_state(env, st); if (rc) return rc;
+    if (!d_img) return fail(env, TG_ERR_POINTER, "d_img is NULL");
+    CUDA_TRY(env, cudaSetDevice(env->device));
+    const DevCfg& d = env->dev;
+    int T = 256, nw = T / 32;
+    size_t smem = (size_t)nw * (((size_t)d.Hp * d.rgb_w + 15) & ~(size_t)15);
+    int64_t blocks = (n + nw - 1) / nw;
+    int64_t cap = (int64_t)env->num_sms * 16;
+    if (blocks > cap) blocks = cap;
+    if (env->col64) k_rgb<uint64_t><<<(unsigned)blocks, T, smem, (cudaStream_t)stream>>>(d, n, (const uint8_t*)st.hot, (const uint8_t*)st.board, d_img);
+    else k_rgb<uint32_t><<<(unsigned)blocks, T, smem, (cudaStream_t)stream>>>(d, n, (const uint8_t*)st.hot, (const uint8_t*)st.board, d_img);
+    CUDA_TRY(env, cudaGetLastError());
+    return TG_OK;
+}
+
+static int launch_grouped_observe(tg_env* env, tg_state st, int64_t n, uint8_t* d_feats, uint8_t* d_boards, uint8_t* d_legal,
+                                  const uint8_t* fill_high, cudaStream_t s) {
+    const DevCfg& d = env->dev;
+    if (d_feats) {
+        int EPB = 8, T = 256;
+        size_t colb = env->col64 ? 8 : 4;
+        size_t smem = (size_t)EPB * d.W * colb + (size_t)EPB * 4 + (size_t)EPB * d.A * d.F + (size_t)EPB * d.A;
+        unsigned g = (unsigned)((n + EPB - 1) / EPB);
+        if (env->col64) k_grouped_feats<uint64_t><<<g, T, smem, s>>>(d, n, (const uint8_t*)st.hot, (const uint8_t*)st.board, d_feats, d_legal, fill_high, EPB);
+        else k_grouped_feats<uint32_t><<<g, T, smem, s>>>(d, n, (const uint8_t*)st.hot, (const uint8_t*)st.board, d_feats, d_legal, fill_high, EPB);
+        CUDA_TRY(env, cudaGetLastError());
+    }
+    if (d_boards) {
+        int T = 256, nw = T / 32;
+        size_t smem = (size_t)nw * (((size_t)d.OB + 15) & ~(size_t)15);
+        int64_t blocks = (n * d.A + nw - 1) / nw;
+        int64_t cap = (int64_t)env->num_sms * 8;
+        if (blocks > cap) blocks = cap;
+        if (env->col64) k_grouped_boards<uint64_t><<<(unsigned)blocks, T, smem, s>>>(d, n, (const uint8_t*)st.hot, (const uint8_t*)st.board, d_boards, d_legal, fill_high);
+        else k_grouped_boards<uint32_t><<<(unsigned)blocks, T, smem, s>>>(d, n, (const uint8_t*)st.hot, (const uint8_t*)st.board, d_boards, d_legal, fill_high);
+        CUDA_TRY(env, cudaGetLastError());
+    }
+    return TG_OK;
+}
+
+extern "C" int tg_grouped_observe(tg_env* env, tg_state st, int64_t n, uint8_t* d_feats, uint8_t* d_boards, uint8_t* d_legal,
+                                  void* stream) {
+    if (!env) return TG_ERR_POINTER;
+    int rc = check_state(env, st); if (rc) return rc;
+    if (!d_legal || (!d_feats && !d_boards)) return fail(env, TG_ERR_POINTER, "grouped_observe: need d_legal and d_feats or d_boards");
+    CUDA_TRY(env, cudaSetDevice(env->device));
+    return launch_grouped_observe(env, st, n, d_feats, d_boards, d_legal, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int tg_grouped_step(tg_env* env, tg_state st, int64_t n, const int32_t* d_actions, uint8_t* d_legal, uint8_t* d_feats,
+                               uint8_t* d_boards, uint8_t* d_info_board, tg_obs obs, tg_step_out out, tg_stats* d_stats,
+                               void* stream) {
+    if (!env) return TG_ERR_POINTER;
+    if (n <= 0) return fail(env, TG_ERR_ARG, "n must be positive");
+    int rc = check_state(env, st); if (rc) return rc;
+    if (!d_actions || !d_legal || !out.reward || !out.terminated || !out.truncated || !out.lines)
+        return fail(env, TG_ERR_POINTER, "grouped_step: NULL pointer");
+    bool any_obs = obs.board || obs.mask || obs.holder || obs.queue;
+    if (any_obs) { rc = check_obs(env, obs); if (rc) return rc; }
+    CUDA_TRY(env, cudaSetDevice(env->device));
+    rc = ensure_stage(env, 3, (size_t)n); if (rc) return rc;  // per-env "illegal + terminate" flags
+    StepParams p;
+    memset(&p, 0, sizeof p);
+    p.n = n; p.hot = (uint8_t*)st.hot; p.board = (uint8_t*)st.board; p.rng = (uint8_t*)st.rng; p.seq = st.piece_seq;
+    p.actions = d_actions;
+    p.o_board = obs.board; p.o_mask = obs.mask; p.o_holder = obs.holder; p.o_queue = obs.queue;
+    p.reward = out.reward; p.terminated = out.terminated; p.truncated = out.truncated; p.lines = out.lines;
+    p.stats = (double*)d_stats;
+    p.legal = d_legal; p.info_board = d_info_board; p.fill_high = (uint8_t*)env->stage[3];
+    p.mode = 2;
+    rc = launch_step(env, p, (cudaStream_t)stream); if (rc) return rc;
+    if (d_feats || d_boards) return launch_grouped_observe(env, st, n, d_feats, d_boards, d_legal, (const uint8_t*)env->stage[3], (cudaStream_t)stream);
+    return TG_OK;
+}
+
+extern "C" int tg_rollout(tg_env* env, tg_state st, int64_t n, const int32_t weights[4], int32_t k_steps, tg_stats* d_stats,
+                          void* stream) {
+    (void)st; (void)n; (void)weights; (void)k_steps; (void)d_stats; (void)stream;
+    if (!env) return TG_ERR_POINTER;
+    return fail(env, TG_ERR_ARG, "tg_rollout: not built yet");
+}

@@ -1,0 +1,350 @@
+"""Batched Tetris env on B200 -- host-side mirror of the reference `Tetris(gym.Env)`.
+
+Reference: tetris_gymnasium/envs/tetris.py (constructor :77-91, step :203-272, reset :274-307,
+_get_obs :566-615, get_state/set_state :681-708).  Same constructor options, same action /
+reward mappings, same observation-dict layout -- with a leading env axis: every array is a torch
+CUDA tensor `[num_envs, ...]`.  All game logic runs in libtetris_b200.so (hand-written sm_100a
+CUDA behind a C ABI, include/tetris_b200.h); torch only owns memory and streams.  No CPU path.
+"""
+from dataclasses import fields
+from typing import Any, Optional
+
+import ctypes as C
+import numpy as np
+import torch
+
+from .. import _lib
+from ..mappings.actions import ActionsMapping
+from ..mappings.rewards import RewardsMapping
+
+PADDING = 4  # max tetromino matrix dim (reference envs/tetris.py:130)
+
+
+class _Space:
+    """Tiny stand-in used when gymnasium is not importable (shape / dtype / n only)."""
+
+    def __init__(self, shape=(), dtype=np.uint8, low=0, high=0, n=None):
+        self.shape, self.dtype, self.low, self.high, self.n = tuple(shape), np.dtype(dtype), low, high, n
+
+    def contains(self, x):
+        if self.n is not None:
+            return isinstance(x, (int, np.integer)) and 0 <= int(x) < self.n
+        return True
+
+
+def _spaces(env):
+    try:
+        import gymnasium as gym
+        from gymnasium.spaces import Box, Discrete
+
+        mk_box = lambda hi, shape: Box(low=0, high=hi, shape=shape, dtype=np.uint8)  # noqa: E731
+        disc = Discrete(8)
+        dct = gym.spaces.Dict
+    except Exception:  # gymnasium absent: attribute-compatible stand-ins
+        mk_box = lambda hi, shape: _Space(shape, np.uint8, 0, hi)  # noqa: E731
+        disc = _Space(n=8, dtype=np.int64)
+        dct = dict
+    n_pix = 9  # len(self.pixels): 2 base pixels + 7 tetrominoes (reference envs/tetris.py:127)
+    obs = dct({
+        "board": mk_box(n_pix, (env.height_padded, env.width_padded)),
+        "active_tetromino_mask": mk_box(1, (env.height_padded, env.width_padded)),
+        "holder": mk_box(n_pix, (env.padding, env.padding * env.holder_size)),
+        "queue": mk_box(n_pix, (env.padding, env.padding * env.queue_size)),
+    })
+    return obs, disc
+
+
+class Tetris:
+    """`num_envs` independent Tetris games stepped by one CUDA kernel launch.
+
+    Positional / keyword options are the reference's (envs/tetris.py:77-91); the keyword-only
+    ones are ours:
+
+      num_envs        number of envs on this device
+      device          torch device (default: current CUDA device)
+      queue_size      visible queue length (reference TetrominoQueue default 4; EnvConfig.queue_size)
+      padding         must be 4 (derived in the reference, EnvConfig field in the functional env)
+      autoreset_mode  "next_step" (gymnasium 1.x vector default) | "same_step" | "disabled"
+      randomizer_mode "philox" (device-native 7-bag) | "numpy" (bit-exact BagRandomizer: PCG64 +
+                      Generator.shuffle) | "sequence" (injected piece streams, `piece_sequences`)
+      env_id_offset   global id of env 0 (multi-GPU sharding keeps Philox streams independent of #GPUs)
+    """
+
+    metadata = {"render_modes": ["rgb_array", "ansi"], "render_fps": 1}
+
+    def __init__(self, render_mode=None, width=10, height=20, gravity=True,
+                 actions_mapping=ActionsMapping(), rewards_mapping=RewardsMapping(),
+                 queue=None, holder=None, randomizer=None, base_pixels=None, tetrominoes=None,
+                 render_upscale: int = 10, *, num_envs: int = 1, device=None, queue_size: Optional[int] = None,
+                 padding: Optional[int] = None, autoreset_mode: str = "next_step",
+                 randomizer_mode: str = "philox", piece_sequences=None, env_id_offset: int = 0,
+                 terminate_on_illegal_action: bool = True):
+        if base_pixels is not None or tetrominoes is not None:
+            raise NotImplementedError("custom pixel / tetromino sets are not supported yet (SURVEY 8 f4)")
+        if padding not in (None, PADDING):
+            raise ValueError("padding is derived from the tetromino set and must be 4")
+        if holder is not None and getattr(holder, "size", 1) != 1:
+            raise NotImplementedError("holder size > 1 is not supported yet (SURVEY 8 f4)")
+        if queue is not None and queue_size is None:
+            queue_size = int(getattr(queue, "size", queue))
+        if randomizer is not None and isinstance(randomizer, str):
+            randomizer_mode = randomizer
+        if not torch.cuda.is_available():
+            raise RuntimeError("tetris_gymnasium_b200 needs a CUDA device: there is no CPU fallback")
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        if self.device.type != "cuda":
+            raise RuntimeError("tetris_gymnasium_b200 runs on CUDA devices only")
+        self.num_envs = int(num_envs)
+        self.width, self.height = int(width), int(height)
+        self.padding = PADDING
+        self.width_padded = self.width + 2 * self.padding
+        self.height_padded = self.height + self.padding
+        self.queue_size = 4 if queue_size is None else int(queue_size)
+        self.holder_size = 1
+        self.gravity_enabled = bool(gravity)
+        self.actions, self.rewards = actions_mapping, rewards_mapping
+        self.render_mode = render_mode
+        self.render_scaling_factor = render_upscale
+        self.autoreset_mode = autoreset_mode
+        self.randomizer_mode = randomizer_mode
+        self.env_id_offset = int(env_id_offset)
+        self.observation_space, self.action_space = _spaces(self)
+        self.single_observation_space, self.single_action_space = self.observation_space, self.action_space
+        self.reward_range = (min(vars(self.rewards).values()), max(vars(self.rewards).values()))
+
+        self._seq = None
+        seq_len = 0
+        if randomizer_mode == "sequence":
+            if piece_sequences is None:
+                raise ValueError("randomizer_mode='sequence' needs piece_sequences [num_envs, L]")
+            self._seq = torch.as_tensor(np.asarray(piece_sequences) if not torch.is_tensor(piece_sequences) else piece_sequences)
+            self._seq = self._seq.to(self.device, torch.uint8).contiguous()
+            if self._seq.dim() == 1:
+                self._seq = self._seq.unsqueeze(0).expand(self.num_envs, -1).contiguous()
+            assert self._seq.shape[0] == self.num_envs
+            seq_len = self._seq.shape[1]
+
+        cfg = _lib.TgConfig()
+        cfg.width, cfg.height, cfg.queue_size, cfg.gravity = self.width, self.height, self.queue_size, int(self.gravity_enabled)
+        cfg.autoreset = _lib.AUTORESET[autoreset_mode]
+        cfg.rng_mode = _lib.RNG[randomizer_mode]
+        for i, f in enumerate(fields(ActionsMapping)):
+            cfg.action_map[i] = int(getattr(self.actions, f.name))
+        cfg.terminate_on_illegal = int(bool(terminate_on_illegal_action))
+        cfg.reward_alife, cfg.reward_clear_line = float(self.rewards.alife), float(self.rewards.clear_line)
+        cfg.reward_game_over, cfg.reward_invalid_action = float(self.rewards.game_over), float(self.rewards.invalid_action)
+        cfg.seq_len, cfg.env_id_offset = seq_len, self.env_id_offset
+        self._cfg = cfg
+        self._L = _lib.load()
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.tg_create(C.byref(cfg), self.device.index or 0, C.byref(h)))
+        self._h = h
+        lay = _lib.TgLayout()
+        _lib.check(self._L.tg_get_layout(self._h, C.byref(lay)), self._h)
+        self.layout = lay
+
+        n, dev, u8 = self.num_envs, self.device, torch.uint8
+        # state: caller-owned device memory (see tg_state in include/tetris_b200.h)
+        self._hot = torch.zeros(n * lay.hot_stride, dtype=u8, device=dev)
+        self._brd = torch.zeros(n * lay.board_stride, dtype=u8, device=dev)
+        self._rng = torch.zeros(n * lay.rng_stride, dtype=u8, device=dev)
+        # outputs (overwritten by every reset/step call)
+        self._o_board = torch.empty((n, lay.height_padded, lay.width_padded), dtype=u8, device=dev)
+        self._o_mask = torch.empty_like(self._o_board)
+        self._o_holder = torch.empty((n, PADDING, PADDING), dtype=u8, device=dev)
+        self._o_queue = torch.empty((n, PADDING, PADDING * self.queue_size), dtype=u8, device=dev)
+        self._reward = torch.zeros(n, dtype=torch.float32, device=dev)
+        self._terminated = torch.zeros(n, dtype=u8, device=dev)
+        self._truncated = torch.zeros(n, dtype=u8, device=dev)
+        self._lines = torch.zeros(n, dtype=torch.int32, device=dev)
+        self._stats = torch.zeros(4, dtype=torch.float64, device=dev)
+        self._seeded = False
+        self._has_reset = False
+
+    # ---- plumbing ---------------------------------------------------------------------------
+    def _state(self):
+        return _lib.TgState(self._hot.data_ptr(), self._brd.data_ptr(), self._rng.data_ptr(),
+                            self._seq.data_ptr() if self._seq is not None else None)
+
+    def _obs_struct(self):
+        return _lib.TgObs(self._o_board.data_ptr(), self._o_mask.data_ptr(), self._o_holder.data_ptr(), self._o_queue.data_ptr())
+
+    def _out_struct(self):
+        return _lib.TgStepOut(self._reward.data_ptr(), self._terminated.data_ptr(), self._truncated.data_ptr(), self._lines.data_ptr())
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _obs(self):
+        return {"board": self._o_board, "active_tetromino_mask": self._o_mask, "holder": self._o_holder, "queue": self._o_queue}
+
+    @property
+    def unwrapped(self):
+        return self
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.tg_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- Tetris.reset (reference envs/tetris.py:274-307) -----------------------------------------
+    def _per_env_seeds(self, seed):
+        if torch.is_tensor(seed):
+            seed = seed.cpu().numpy()
+        if np.ndim(seed) == 0:
+            return (np.uint64(int(seed)) + np.arange(self.num_envs, dtype=np.uint64) + np.uint64(self.env_id_offset)).astype(np.uint64)
+        s = np.asarray(seed).astype(np.uint64)
+        assert s.shape == (self.num_envs,)
+        return s
+
+    def _seed_numpy(self, seeds, mask=None):
+        """Randomizer.reset (components/tetromino_randomizer.py:34-46): PCG64(SeedSequence(seed)) for seed > 0."""
+        st = np.empty((self.num_envs, 4), dtype=np.uint64)
+        m64 = (1 << 64) - 1
+        sel = np.ones(self.num_envs, dtype=np.uint8) if mask is None else mask.copy()
+        for i in range(self.num_envs):
+            if not sel[i]:
+                continue
+            s = None if seeds is None else int(seeds[i])
+            if s is not None and s <= 0:
+                if self._seeded:      # "if seed and seed > 0" -- seed 0 keeps the running generator
+                    sel[i] = 0
+                    continue
+                s = None
+            pcg = np.random.PCG64(np.random.SeedSequence(s)).state["state"]
+            st[i] = (pcg["state"] >> 64, pcg["state"] & m64, pcg["inc"] >> 64, pcg["inc"] & m64)
+        d_st = torch.from_numpy(st.view(np.int64)).to(self.device)
+        d_m = torch.from_numpy(sel).to(self.device)
+        _lib.check(self._L.tg_seed_numpy(self._h, self._state(), self.num_envs, d_st.data_ptr(), d_m.data_ptr(), self._stream()), self._h)
+
+    def reset(self, *, seed=None, options: "dict[str, Any] | None" = None):
+        """Reset all envs (or `options["reset_mask"]`).  `seed`: int (env i gets seed + i, like
+        gymnasium's vector envs) or one seed per env.  Returns (obs dict, {"lines_cleared": 0})."""
+        mask = None
+        if options and options.get("reset_mask") is not None:
+            mask = torch.as_tensor(options["reset_mask"]).to(self.device).to(torch.uint8).contiguous()
+        d_seeds = None
+        if self.randomizer_mode == "numpy":
+            if seed is not None or not self._seeded:
+                seeds = None if seed is None else self._per_env_seeds(seed)
+                self._seed_numpy(seeds, None if mask is None else mask.cpu().numpy())
+                self._seeded = True
+        elif self.randomizer_mode == "philox":
+            if seed is not None or not self._seeded:
+                seeds = self._per_env_seeds(0x5EED if seed is None else seed)
+                d_seeds = torch.from_numpy(seeds.view(np.int64)).to(self.device)
+                self._seeded = True
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.tg_reset(self._h, self._state(), self.num_envs,
+                                        d_seeds.data_ptr() if d_seeds is not None else None,
+                                        mask.data_ptr() if mask is not None else None,
+                                        self._obs_struct(), self._stream()), self._h)
+        self._has_reset = True
+        self._lines.zero_()
+        return self._obs(), {"lines_cleared": self._lines}
+
+    # ---- Tetris.step (reference envs/tetris.py:203-272) -------------------------------------------
+    def _actions(self, actions):
+        a = actions if torch.is_tensor(actions) else torch.as_tensor(np.asarray(actions))
+        a = a.to(device=self.device, dtype=torch.int32, non_blocking=True).contiguous()
+        if a.dim() == 0:
+            a = a.reshape(1)
+        assert a.shape == (self.num_envs,), f"actions must have shape ({self.num_envs},)"
+        return a
+
+    def step(self, actions):
+        """One step of every env.  Returns (obs, reward f32[n], terminated bool[n], truncated bool[n],
+        {"lines_cleared": i32[n]}) -- tensors are the env's output buffers, overwritten by the next call."""
+        a = self._actions(actions)
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.tg_step(self._h, self._state(), self.num_envs, a.data_ptr(), self._obs_struct(),
+                                       self._out_struct(), self._stats.data_ptr(), self._stream()), self._h)
+        return (self._obs(), self._reward, self._terminated.view(torch.bool), self._truncated.view(torch.bool),
+                {"lines_cleared": self._lines})
+
+    def step_host(self, actions: np.ndarray, out: "dict[str, np.ndarray] | None" = None):
+        """Same step through host buffers (tg_step_host): actions H2D, observation dict + 5-tuple D2H.
+        `out` may hold preallocated (ideally pinned) numpy arrays; returns numpy arrays."""
+        n, lay = self.num_envs, self.layout
+        a = np.ascontiguousarray(actions, dtype=np.int32)
+        if out is None:
+            out = self.alloc_host_buffers(pinned=False)
+        ho = _lib.TgObs(out["board"].ctypes.data, out["active_tetromino_mask"].ctypes.data, out["holder"].ctypes.data, out["queue"].ctypes.data)
+        so = _lib.TgStepOut(out["reward"].ctypes.data, out["terminated"].ctypes.data, out["truncated"].ctypes.data, out["lines_cleared"].ctypes.data)
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.tg_step_host(self._h, self._state(), n, a.ctypes.data, ho, so), self._h)
+        return out
+
+    def alloc_host_buffers(self, pinned=True):
+        n, lay = self.num_envs, self.layout
+        def mk(shape, dt):
+            t = torch.empty(shape, dtype=dt, pin_memory=pinned)
+            return t.numpy()
+        return {
+            "board": mk((n, lay.height_padded, lay.width_padded), torch.uint8),
+            "active_tetromino_mask": mk((n, lay.height_padded, lay.width_padded), torch.uint8),
+            "holder": mk((n, PADDING, PADDING), torch.uint8),
+            "queue": mk((n, PADDING, PADDING * self.queue_size), torch.uint8),
+            "reward": mk((n,), torch.float32), "terminated": mk((n,), torch.uint8),
+            "truncated": mk((n,), torch.uint8), "lines_cleared": mk((n,), torch.int32),
+        }
+
+    # ---- episode statistics (RecordEpisodeStatistics-style, accumulated on device) ----------------
+    def episode_stats(self, reset=False):
+        s = self._stats.clone()
+        if reset:
+            self._stats.zero_()
+        return {"episodes": s[0], "sum_return": s[1], "sum_length": s[2], "sum_lines": s[3]}
+
+    # ---- state access (reference get_state/set_state :681-708 and the tests' env.unwrapped pokes) --
+    def get_state(self):
+        """Unpacked state: board u8[n,Hp,Wp] (locked cells), x, y, piece, rotation, holder, ... tensors."""
+        n, lay = self.num_envs, self.layout
+        board = torch.empty((n, lay.height_padded, lay.width_padded), dtype=torch.uint8, device=self.device)
+        sc = torch.empty((n, _lib.TG_SCALARS + self.queue_size), dtype=torch.int32, device=self.device)
+        _lib.check(self._L.tg_get_state(self._h, self._state(), n, board.data_ptr(), sc.data_ptr(), self._stream()), self._h)
+        return {"board": board, "x": sc[:, 0], "y": sc[:, 1], "piece": sc[:, 2], "rotation": sc[:, 3],
+                "holder_piece": sc[:, 4], "holder_rotation": sc[:, 5], "has_swapped": sc[:, 6], "game_over": sc[:, 7],
+                "queue": sc[:, 8:], "_scalars": sc,
+                "_raw": (self._hot.clone(), self._brd.clone(), self._rng.clone())}
+
+    def set_state(self, state=None, *, board=None, env_mask=None, **scalars):
+        """Restore a `get_state()` snapshot, or poke fields: set_state(board=..., x=..., piece=..., ...)."""
+        n = self.num_envs
+        if state is not None and "_raw" in state and board is None and not scalars:
+            self._hot.copy_(state["_raw"][0]); self._brd.copy_(state["_raw"][1]); self._rng.copy_(state["_raw"][2])
+            return
+        cur = self.get_state() if state is None else state
+        sc = cur["_scalars"].clone()
+        names = {"x": 0, "y": 1, "piece": 2, "rotation": 3, "holder_piece": 4, "holder_rotation": 5, "has_swapped": 6, "game_over": 7}
+        for k, v in scalars.items():
+            if k == "queue":
+                sc[:, 8:] = torch.as_tensor(v, device=self.device).to(torch.int32)
+            else:
+                sc[:, names[k]] = torch.as_tensor(v, device=self.device).to(torch.int32)
+        b = None
+        if board is not None:
+            b = torch.as_tensor(np.asarray(board) if not torch.is_tensor(board) else board).to(self.device, torch.uint8)
+            if b.dim() == 2:
+                b = b.unsqueeze(0).expand(n, -1, -1)
+            b = b.contiguous()
+        elif state is not None:
+            b = state["board"].contiguous()
+        m = None if env_mask is None else torch.as_tensor(env_mask).to(self.device).to(torch.uint8).contiguous()
+        _lib.check(self._L.tg_set_state(self._h, self._state(), n, b.data_ptr() if b is not None else None,
+                                        sc.data_ptr(), m.data_ptr() if m is not None else None, self._stream()), self._h)
+
+    def observe(self):
+        """Re-emit the observation dict of the current state (Tetris._get_obs) without stepping."""
+        with torch.cuda.device(self.device):
+            zero = torch.zeros(self.num_envs, dtype=torch.uint8, device=self.device)
+            _lib.check(self._L.tg_reset(self._h, self._state(), self.num_envs, None, zero.data_ptr(),
+                                        self._obs_struct(), self._stream()), self._h)
+        return self._obs()
