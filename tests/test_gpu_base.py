@@ -147,26 +147,35 @@ def test_philox_bag_properties_and_replay():
     from tetris_gymnasium_b200.envs.tetris import Tetris
     from gpu_util import OracleBatch, assert_obs_equal, np_
 
-    n, T = 64, 150
-    env = Tetris(num_envs=n, gravity=False, autoreset_mode="disabled", queue_size=1)
+    n = 64
+    kw = dict(width=24, height=60, gravity=False, autoreset_mode="disabled", queue_size=1)
+    env = Tetris(num_envs=n, **kw)
     obs, _ = env.reset(seed=11)
     streams = [[int(v)] for v in np_(env.get_state()["piece"])]
     q0 = np_(env.get_state()["queue"])[:, 0]
     for i in range(n):
         streams[i].append(int(q0[i]))
-    a = torch.full((n,), 5)
-    for t in range(T):
-        env.step(a)
-        q = np_(env.get_state()["queue"])[:, 0]
-        for i in range(n):
-            streams[i].append(int(q[i]))
-    s = np.array(streams)[:, : (T // 7) * 7].reshape(n, -1, 7)
+    rng = np.random.default_rng(0)
+    for t in range(1200):
+        if t % 6 == 5:
+            _, _, term, _, _ = env.step(torch.full((n,), 5))
+            if np_(term).any():
+                break
+            q = np_(env.get_state()["queue"])[:, 0]
+            for i in range(n):
+                streams[i].append(int(q[i]))
+        else:
+            env.step(torch.from_numpy(rng.integers(0, 2, size=n)))
+    nb = len(streams[0]) // 7
+    assert nb >= 8, nb
+    s = np.array(streams)[:, : nb * 7].reshape(n, -1, 7)
     assert (np.sort(s, axis=2) == np.arange(7)).all()
     assert len({tuple(r) for r in np.array(streams)}) > n // 2  # streams differ between envs
     # sharding invariance: envs 32..63 as a second shard with env_id_offset=32 give the same pieces
-    env2 = Tetris(num_envs=32, gravity=False, autoreset_mode="disabled", queue_size=1, env_id_offset=32)
+    env2 = Tetris(num_envs=32, env_id_offset=32, **kw)
     env2.reset(seed=11)
     assert np.array_equal(np_(env2.get_state()["piece"]), np.array(streams)[32:, 0])
+    assert np.array_equal(np_(env2.get_state()["queue"])[:, 0], np.array(streams)[32:, 1])
     # replay through the oracle with the drawn streams injected
     seqs = np.array(streams, np.uint8)
     env3 = Tetris(num_envs=n, autoreset_mode="disabled", queue_size=1)

@@ -86,7 +86,7 @@ __device__ __forceinline__ void nib8_to_bytes(uint32_t x, uint32_t& b0, uint32_t
 // Writes the W cell bytes of playfield row `row` of one env into its padded board image.
 // Only words that contain cell bytes are touched; the spill-over bytes are bedrock (1).
 template <int WT>
-__device__ __forceinline__ void fill_board_row(const DevCfg& cfg, const uint32_t* ids, uint8_t* img, int row) {
+__device__ __forceinline__ void fill_board_row(const DevCfg& cfg, const uint32_t* ids, uint8_t* tile, int env_off, int row) {
     const int W = WT ? WT : cfg.W;
     const int Wp = W + 2 * P;
     constexpr int MAXC = WT ? (WT + 7) / 8 : 3;       // 8-nibble chunks per row (W <= 24)
@@ -109,9 +109,11 @@ __device__ __forceinline__ void fill_board_row(const DevCfg& cfg, const uint32_t
         if (valid <= 0) cw[j] = 0x01010101u;
         else if (valid < 4) { uint32_t m = (1u << (8 * valid)) - 1; cw[j] = (cw[j] & m) | (0x01010101u & ~m); }
     }
-    const int cbase = row * Wp + P;  // byte offset of the first cell
+    // byte offset of the first cell inside the image TILE (env images are packed back to back, so
+    // the bytes just before an unaligned start are the previous row's / previous env's bedrock)
+    const int cbase = env_off + row * Wp + P;
     const int a = cbase & 3;
-    uint32_t* out = (uint32_t*)(img + (cbase - a));
+    uint32_t* out = (uint32_t*)(tile + (cbase - a));
     const uint32_t sel = 0x7654u - 0x1111u * (uint32_t)a;
     const int nout = (a + W + 3) >> 2;
     uint32_t prev = 0x01010101u;
@@ -250,7 +252,7 @@ __global__ void k_step(const __grid_constant__ StepParams p) {
         if (want_obs)
         for (int it = tid; it < nv * H; it += E) {
             int e = it / H, row = it - e * H;
-            fill_board_row<WT>(cfg, (const uint32_t*)(s_brd + e * BS + cfg.ids_off), i_board + e * OB, row);
+            fill_board_row<WT>(cfg, (const uint32_t*)(s_brd + e * BS + cfg.ids_off), i_board, e * OB, row);
         }
         if (want_obs) {
             const int Q = cfg.Q;
