@@ -22,7 +22,8 @@ struct tg_env {
     int device;
     int num_sms;
     int col64;
-    int tile;  // envs per CTA tile of the step kernel
+    int tile;             // envs per CTA tile of the step kernel
+    int threads_per_env;  // CTA threads = tile * threads_per_env (logic uses one thread per env, image fill uses all)
     std::string err;
     // tg_step_host staging
     cudaStream_t hs[3];
@@ -168,8 +169,10 @@ extern "C" int tg_create(const tg_config* cfg, int device, tg_env** out) {
     L.rng_stride = d.rng_stride; L.obs_board_bytes = d.OB; L.obs_holder_bytes = 16; L.obs_queue_bytes = d.OQ;
     L.n_placements = d.A; L.n_features = d.F; L.rgb_width = d.rgb_w;
 
-    env->tile = 64;
+    env->tile = 32;
+    env->threads_per_env = 4;
     if (const char* t = getenv("TG_TILE")) { int v = atoi(t); if (v == 32 || v == 64 || v == 96 || v == 128) env->tile = v; }
+    if (const char* t = getenv("TG_TPE")) { int v = atoi(t); if (v >= 1 && v <= 8) env->threads_per_env = v; }
     int rc = upload_tables(env);
     if (rc != TG_OK) { g_create_err = env->err; delete env; return rc; }
     *out = env;
@@ -201,16 +204,16 @@ static int check_state(tg_env* env, const tg_state& st) {
 
 // ---- step / reset launcher ----------------------------------------------------------------------
 template <int WT, int HT, class COLT>
-static int launch_step_t(tg_env* env, StepParams& p, int E, size_t smem, cudaStream_t s) {
+static int launch_step_t(tg_env* env, StepParams& p, int T, size_t smem, cudaStream_t s) {
     auto kern = k_step<WT, HT, COLT>;
     CUDA_TRY(env, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    CUDA_TRY(env, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, E, smem));
+    CUDA_TRY(env, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, T, smem));
     if (per_sm < 1) return fail(env, TG_ERR_CONFIG, "step kernel does not fit: %zu B shared memory per CTA", smem);
-    int64_t ntiles = (p.n + E - 1) / E;
+    int64_t ntiles = (p.n + p.E - 1) / p.E;
     int64_t grid = (int64_t)env->num_sms * per_sm;
     if (grid > ntiles) grid = ntiles;
-    kern<<<(unsigned)grid, E, smem, s>>>(p);
+    kern<<<(unsigned)grid, T, smem, s>>>(p);
     CUDA_TRY(env, cudaGetLastError());
     return TG_OK;
 }
@@ -225,20 +228,25 @@ static int launch_step(tg_env* env, StepParams& p, cudaStream_t s) {
         off = 0;
         p.off_hot = take((size_t)E * 32);
         p.off_brd = take((size_t)E * d.board_stride + 16);
-        p.off_iboard = take((size_t)E * d.OB);
-        p.off_imask = take((size_t)E * d.OB);
+        p.off_iboard = take((size_t)E * d.OB + 16);
+        p.off_imask = take((size_t)E * d.OB + 16);
         p.off_iholder = take((size_t)E * 16);
         p.off_iqueue = take((size_t)E * d.OQ);
         p.off_bar = take(16);
-        if (off <= 200 * 1024 || E == 32) break;
+        p.off_box = take((size_t)E * 4);
+        p.off_tab = take(112 * 4 + 64 + 32);
+        if (off <= 100 * 1024 || E == 32) break;
         E -= 32;
     }
     if (off > 227 * 1024) return fail(env, TG_ERR_CONFIG, "board too large for the shared-memory tile (%zu B)", off);
     p.cfg = d;
-    if (d.W == 10 && d.H == 20) return launch_step_t<10, 20, uint32_t>(env, p, E, off, s);
-    if (d.W == 20 && d.H == 40) return launch_step_t<20, 40, uint64_t>(env, p, E, off, s);
-    if (env->col64) return launch_step_t<0, 0, uint64_t>(env, p, E, off, s);
-    return launch_step_t<0, 0, uint32_t>(env, p, E, off, s);
+    p.E = E;
+    int T = E * env->threads_per_env;
+    if (T > 256) T = 256;
+    if (d.W == 10 && d.H == 20) return launch_step_t<10, 20, uint32_t>(env, p, T, off, s);
+    if (d.W == 20 && d.H == 40) return launch_step_t<20, 40, uint64_t>(env, p, T, off, s);
+    if (env->col64) return launch_step_t<0, 0, uint64_t>(env, p, T, off, s);
+    return launch_step_t<0, 0, uint32_t>(env, p, T, off, s);
 }
 
 static int check_obs(tg_env* env, const tg_obs& o) {

@@ -56,6 +56,19 @@ __constant__ unsigned int c_rowbytes[7][4][4];
 __constant__ int c_n[7];
 __constant__ unsigned char c_colors[16][4];
 
+// Piece tables as seen by device functions: the hot kernels copy them to shared memory first
+// (per-thread piece indices make constant-cache reads serialise), the others read the __constant__ copy.
+struct Tabs {
+    const unsigned short* cells;  // [p * 4 + r]
+    const unsigned int* rowbytes; // [(p * 4 + r) * 4 + i]
+    const int* n;                 // [p]
+};
+__device__ __forceinline__ Tabs const_tabs() {
+    Tabs t;
+    t.cells = &c_cells[0][0]; t.rowbytes = &c_rowbytes[0][0][0]; t.n = &c_n[0];
+    return t;
+}
+
 // ---- hot record ------------------------------------------------------------------------------
 struct Hot {
     int x, y, p, r, hold, hold_r, swapped, over, pending;
@@ -287,7 +300,7 @@ struct StepResult {
 
 // Tetris.commit_active_tetromino (envs/tetris.py:450-479); B = bmask of the active piece at h.x
 template <class COLT>
-__device__ __forceinline__ void env_commit(const DevCfg& cfg, Hot& h, uint32_t* rec, Rng& g, COLT B,
+__device__ __forceinline__ void env_commit(const DevCfg& cfg, const Tabs& tb, Hot& h, uint32_t* rec, Rng& g, COLT B,
                                            StepResult& res) {
     COLT* cols = (COLT*)rec;
     uint32_t* ids = rec + cfg.ids_off / 4;
@@ -297,7 +310,7 @@ __device__ __forceinline__ void env_commit(const DevCfg& cfg, Hot& h, uint32_t* 
         return;
     }
     h.y += ctz_t<COLT>(B >> (h.y + 1));  // drop_active_tetromino
-    uint32_t cells = c_cells[h.p][h.r];
+    uint32_t cells = tb.cells[h.p * 4 + h.r];
     COLT touched = 0;
 #pragma unroll
     for (int k = 0; k < 4; k++) {  // place_active_tetromino / project_tetromino
@@ -316,7 +329,7 @@ __device__ __forceinline__ void env_commit(const DevCfg& cfg, Hot& h, uint32_t* 
     // spawn_tetromino (envs/tetris.py:393-401)
     h.p = queue_pop(cfg, g, h);
     h.r = 0; h.x = cfg.spawn_x[h.p]; h.y = 0;
-    COLT Bn = bmask<COLT>(cols, cfg.W, c_cells[h.p][0], h.x);
+    COLT Bn = bmask<COLT>(cols, cfg.W, tb.cells[h.p * 4], h.x);
     h.over = (int)(Bn & 1);
     res.reward += cfg.r_alife;
     if (h.over) res.reward = cfg.r_go;
@@ -328,7 +341,7 @@ __device__ __forceinline__ void env_commit(const DevCfg& cfg, Hot& h, uint32_t* 
 // `force_x/force_r` >= 0: grouped placement (GroupedActionsObservations.step sets env.x and the
 // rotated piece, y untouched, then base hard_drop; wrappers/grouped.py:241-259).
 template <class COLT>
-__device__ __forceinline__ void env_step(const DevCfg& cfg, Hot& h, uint32_t* rec, Rng& g, int action,
+__device__ __forceinline__ void env_step(const DevCfg& cfg, const Tabs& tb, Hot& h, uint32_t* rec, Rng& g, int action,
                                          StepResult& res) {
     COLT* cols = (COLT*)rec;
     res.reward = 0.0; res.lines = 0; res.dirty = 0; res.did_reset = 0;
@@ -346,15 +359,15 @@ __device__ __forceinline__ void env_step(const DevCfg& cfg, Hot& h, uint32_t* re
     int dr = (op == OP_CW) ? 1 : (op == OP_CCW ? 3 : 0);
     int dy = (op == OP_DOWN) ? 1 : 0;
     int cx = h.x + dx, cr = (h.r + dr) & 3, cy = h.y + dy;
-    COLT B = bmask<COLT>(cols, cfg.W, c_cells[h.p][cr], cx);
+    COLT B = bmask<COLT>(cols, cfg.W, tb.cells[h.p * 4 + cr], cx);
     if (!((B >> cy) & 1)) { h.x = cx; h.r = cr; h.y = cy; }
-    else if (dx | dr) B = bmask<COLT>(cols, cfg.W, c_cells[h.p][h.r], h.x);
+    else if (dx | dr) B = bmask<COLT>(cols, cfg.W, tb.cells[h.p * 4 + h.r], h.x);
     bool do_commit = (op == OP_HARD);
     if (cfg.gravity && !skipgrav) {  // envs/tetris.py:259-264
         if (!((B >> (h.y + 1)) & 1)) h.y += 1;
         else do_commit = true;
     }
-    if (do_commit) env_commit<COLT>(cfg, h, rec, g, B, res);
+    if (do_commit) env_commit<COLT>(cfg, tb, h, rec, g, B, res);
     res.terminated = h.over;
 }
 

@@ -1,10 +1,10 @@
 // tg_step.cuh -- the per-call batched step / reset kernel (BASELINE config 2).
 //
-// One persistent CTA loops over tiles of E = blockDim.x consecutive envs:
+// One persistent CTA (T threads) loops over tiles of E consecutive envs (T = 4E by default):
 //   1. TMA bulk loads (cp.async.bulk, mbarrier completion) bring the tile's hot records and board
 //      records HBM -> shared memory as two contiguous copies;
-//   2. thread e runs the game logic of env e on shared memory (bitboard collision / drop / commit);
-//   3. all threads expand the nibble id planes into the padded uint8 board image, the mask image,
+//   2. thread e < E runs the game logic of env e on shared memory (bitboard collision / drop / commit);
+//   3. all T threads expand the nibble id planes into the padded uint8 board image, the mask image,
 //      the holder and the queue images, which live in shared memory with their constant parts
 //      (bedrock, zeros) written once per CTA;
 //   4. TMA bulk stores write the four observation tiles and the hot tile back as contiguous,
@@ -72,8 +72,9 @@ struct StepParams {
     uint8_t* info_board;             // grouped mode (nullable): features of the real observation u8[n][F]
     uint8_t* fill_high;              // grouped mode: u8[n], 1 = illegal action terminated the episode
     int mode;                        // 0 = step, 1 = reset, 2 = grouped placement step
+    int E;                           // envs per tile
     // shared-memory carve-up (bytes from the 128-aligned base)
-    int off_hot, off_brd, off_iboard, off_imask, off_iholder, off_iqueue, off_bar;
+    int off_hot, off_brd, off_iboard, off_imask, off_iholder, off_iqueue, off_bar, off_box, off_tab;
 };
 
 // expand 8 nibbles -> 8 id bytes (two words)
@@ -127,14 +128,57 @@ __device__ __forceinline__ void fill_board_row(const DevCfg& cfg, const uint32_t
     }
 }
 
+
+// ---- specialised row expansion -------------------------------------------------------------------
+// W = 10: 4 rows = 160 bits = 5 words of the id plane -> 72 output bytes (8-byte aligned); only the
+// 12 words that contain cells are written (4 x STS.64 + 4 x STS.32), the bedrock words persist.
+__device__ __forceinline__ uint32_t w10_tail(uint32_t hi8) { return (hi8 & 15u) | ((hi8 & 0xF0u) << 4); }
+__device__ __forceinline__ void fill_rows4_w10(const uint32_t* ids5, uint8_t* out72) {
+    uint32_t w0 = ids5[0], w1 = ids5[1], w2 = ids5[2], w3 = ids5[3], w4 = ids5[4];
+    uint32_t a0, a1, b0, b1, c0, c1, d0, d1;
+    nib8_to_bytes(w0, a0, a1);
+    nib8_to_bytes(__funnelshift_r(w1, w2, 8), b0, b1);
+    nib8_to_bytes(__funnelshift_r(w2, w3, 16), c0, c1);
+    nib8_to_bytes(__funnelshift_r(w3, w4, 24), d0, d1);
+    uint32_t at = w10_tail(w1 & 0xFFu), bt = w10_tail((w2 >> 8) & 0xFFu), ct = w10_tail((w3 >> 16) & 0xFFu), dt = w10_tail(w4 >> 24);
+    uint32_t* o = (uint32_t*)out72;
+    o[1] = a0;
+    *(uint2*)(o + 2) = make_uint2(a1, at | 0x01010000u);
+    o[5] = 0x0101u | (b0 << 16);
+    *(uint2*)(o + 6) = make_uint2(__funnelshift_r(b0, b1, 16), (b1 >> 16) | (bt << 16));
+    *(uint2*)(o + 10) = make_uint2(c0, c1);
+    o[12] = ct | 0x01010000u;
+    *(uint2*)(o + 14) = make_uint2(0x0101u | (d0 << 16), __funnelshift_r(d0, d1, 16));
+    o[16] = (d1 >> 16) | (dt << 16);
+}
+// W = 20: 2 rows = 160 bits = 5 words -> 56 output bytes (8-byte aligned); 10 cell words written.
+__device__ __forceinline__ void fill_rows2_w20(const uint32_t* ids5, uint8_t* out56) {
+    uint32_t w0 = ids5[0], w1 = ids5[1], w2 = ids5[2], w3 = ids5[3], w4 = ids5[4];
+    uint32_t a0, a1, a2, a3, a4, ax, b0, b1, b2, b3, b4, bx;
+    nib8_to_bytes(w0, a0, a1);
+    nib8_to_bytes(w1, a2, a3);
+    nib8_to_bytes(w2 & 0xFFFFu, a4, ax);
+    nib8_to_bytes(__funnelshift_r(w2, w3, 16), b0, b1);
+    nib8_to_bytes(__funnelshift_r(w3, w4, 16), b2, b3);
+    nib8_to_bytes(w4 >> 16, b4, bx);
+    (void)ax; (void)bx;
+    uint32_t* o = (uint32_t*)out56;
+    o[1] = a0;
+    *(uint2*)(o + 2) = make_uint2(a1, a2);
+    *(uint2*)(o + 4) = make_uint2(a3, a4);
+    *(uint2*)(o + 8) = make_uint2(b0, b1);
+    *(uint2*)(o + 10) = make_uint2(b2, b3);
+    o[12] = b4;
+}
+
 template <int WT, int HT, class COLT>
-__global__ void k_step(const __grid_constant__ StepParams p) {
+__global__ void __launch_bounds__(256) k_step(const __grid_constant__ StepParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const DevCfg& cfg = p.cfg;
-    const int E = blockDim.x, tid = threadIdx.x;
+    const int E = p.E, T = blockDim.x, tid = threadIdx.x;
     const int W = WT ? WT : cfg.W, H = HT ? HT : cfg.H;
     const int Wp = W + 2 * P, Hp = H + P;
-    const int OB = Hp * Wp, OQ = cfg.OQ, BS = cfg.board_stride;
+    const int OB = Hp * Wp, OQ = cfg.OQ, BS = cfg.board_stride, Q = cfg.Q;
 
     uint32_t* s_hot = (uint32_t*)(smem + p.off_hot);
     uint8_t* s_brd = smem + p.off_brd;
@@ -143,20 +187,33 @@ __global__ void k_step(const __grid_constant__ StepParams p) {
     uint8_t* i_holder = smem + p.off_iholder;
     uint8_t* i_queue = smem + p.off_iqueue;
     uint64_t* bar = (uint64_t*)(smem + p.off_bar);
+    uint32_t* s_box = (uint32_t*)(smem + p.off_box);   // per env: x | y<<8 | n<<16 | show<<20 | piece<<24 | rot<<28
+    uint32_t* s_rowbytes = (uint32_t*)(smem + p.off_tab);            // 112 words
+    unsigned short* s_cells = (unsigned short*)(s_rowbytes + 112);   // 28 halves
+    int* s_n = (int*)(s_rowbytes + 112 + 16);                        // 7 ints
+    Tabs tb;
+    tb.cells = s_cells; tb.rowbytes = s_rowbytes; tb.n = s_n;
 
-    // constant parts of the images: bedrock frame, empty mask (written once per CTA)
-    for (int i = tid; i < E * OB; i += E) {
-        int b = i % OB, r = b / Wp, c = b - r * Wp;
+    // once per CTA: piece tables to shared memory; constant parts of the images (bedrock frame, empty mask)
+    for (int i = tid; i < 112; i += T) s_rowbytes[i] = (&c_rowbytes[0][0][0])[i];
+    for (int i = tid; i < 28; i += T) s_cells[i] = (&c_cells[0][0])[i];
+    for (int i = tid; i < 7; i += T) s_n[i] = c_n[i];
+    for (int i = tid; i < E; i += T) s_box[i] = 0;
+    for (int i = tid; i < OB; i += T) {  // env 0's template ...
+        int r = i / Wp, c = i - r * Wp;
         i_board[i] = (r < H && c >= P && c < P + W) ? 0 : 1;
-        i_mask[i] = 0;
     }
+    for (int i = tid; i < (E * OB + 3) / 4; i += T) ((uint32_t*)i_mask)[i] = 0;
     if (tid == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    __syncthreads();
+    for (int i = OB + tid; i < E * OB; i += T) i_board[i] = i_board[i % OB];  // ... replicated
     __syncthreads();
 
     const int64_t ntiles = (p.n + E - 1) / E;
     uint32_t parity = 0;
-    int pm_x = 0, pm_y = 0, pm_n = 0;  // bounding box this thread drew into the mask image last tile
     double st_ep = 0, st_ret = 0, st_len = 0, st_lines = 0;
+    const bool want_obs = p.o_board != nullptr;
+    int nv_prev = 0;
 
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t base = tile * E;
@@ -164,9 +221,7 @@ __global__ void k_step(const __grid_constant__ StepParams p) {
         // (A) previous tile's stores must have finished reading shared memory
         bulk_wait_read();
         __syncthreads();
-        for (int i = 0; i < pm_n; i++)
-            for (int j = 0; j < pm_n; j++) i_mask[tid * OB + (pm_y + i) * Wp + pm_x + j] = 0;
-        // (B) bulk loads of the tile's state
+        // (B) bulk loads of the tile's state (async) ...
         if (tid == 0) {
             mbar_expect_tx(bar, (uint32_t)(nv * 32 + nv * BS));
             bulk_g2s(s_hot, p.hot + base * 32, (uint32_t)(nv * 32), bar);
@@ -174,16 +229,24 @@ __global__ void k_step(const __grid_constant__ StepParams p) {
         }
         int action = 0;
         if (p.mode != 1 && tid < nv) action = p.actions[base + tid];
+        // ... while all threads erase the bounding boxes drawn into the mask image for the previous tile
+        if (want_obs)
+            for (int it = tid; it < nv_prev * 16; it += T) {
+                int e = it >> 4, i = (it >> 2) & 3, j = it & 3;
+                uint32_t bx = s_box[e];
+                int n = (bx >> 16) & 15;
+                if (i < n && j < n) i_mask[e * OB + (((bx >> 8) & 255) + i) * Wp + (bx & 255) + j] = 0;
+            }
+        __syncthreads();   // s_box is rewritten by the logic threads below
         mbar_wait(bar, parity);
         parity ^= 1;
 
         // (C) game logic, one thread per env
-        Hot h;
         StepResult res;
         res.dirty = 0;
-        uint32_t* rec = (uint32_t*)(s_brd + tid * BS);
-        COLT Bact = 0;
         if (tid < nv) {
+            Hot h;
+            uint32_t* rec = (uint32_t*)(s_brd + tid * BS);
             const int64_t e = base + tid;
             hot_load(h, s_hot + tid * 8);
             Rng g;
@@ -198,26 +261,23 @@ __global__ void k_step(const __grid_constant__ StepParams p) {
             } else if (cfg.autoreset == 1 && h.pending) {
                 need_reset = true;  // gymnasium NEXT_STEP autoreset: the action is ignored, the env is reset
             } else {
-                bool stepped = true;
                 if (p.mode == 2) {
                     // GroupedActionsObservations.step (wrappers/grouped.py:209-269)
                     bool ok = (unsigned)action < (unsigned)cfg.A && p.legal[e * cfg.A + action] != 0;
                     p.fill_high[e] = (uint8_t)(!ok && cfg.terminate_on_illegal);
                     if (ok) {
-                        h.x = (action >> 2) + P - c_n[h.p] / 2;   // y untouched (wrappers/grouped.py:244-254)
+                        h.x = (action >> 2) + P - tb.n[h.p] / 2;   // y untouched (wrappers/grouped.py:244-254)
                         h.r = (h.r + (action & 3)) & 3;
-                        env_step<COLT>(cfg, h, rec, g, cfg.act_hard, res);
+                        env_step<COLT>(cfg, tb, h, rec, g, cfg.act_hard, res);
                     } else if (cfg.terminate_on_illegal) {
-                        stepped = false;                           // env untouched, episode ends
-                        res.reward = cfg.r_invalid; res.terminated = 1;
+                        res.reward = cfg.r_invalid; res.terminated = 1;   // env untouched, episode ends
                     } else {
-                        env_step<COLT>(cfg, h, rec, g, cfg.act_noop, res);
+                        env_step<COLT>(cfg, tb, h, rec, g, cfg.act_noop, res);
                         res.reward = cfg.r_invalid;
                     }
                 } else {
-                    env_step<COLT>(cfg, h, rec, g, action, res);
+                    env_step<COLT>(cfg, tb, h, rec, g, action, res);
                 }
-                (void)stepped;
                 h.ep_ret += (float)res.reward; h.ep_len += 1; h.ep_lines += res.lines;
                 if (res.terminated) {
                     st_ep += 1; st_ret += h.ep_ret; st_len += h.ep_len; st_lines += h.ep_lines;
@@ -227,72 +287,77 @@ __global__ void k_step(const __grid_constant__ StepParams p) {
                 }
             }
             if (need_reset) { env_reset<COLT>(cfg, h, rec, g); res.dirty = 1; }
-            hot_store(h, s_hot + tid * 8);
             if (p.mode == 2 && need_reset) p.fill_high[e] = 0;
+            hot_store(h, s_hot + tid * 8);
             if (p.mode != 1) {
                 p.reward[e] = (float)res.reward;
                 p.terminated[e] = (uint8_t)res.terminated;
                 p.truncated[e] = 0;
                 p.lines[e] = res.lines;
             }
-            Bact = bmask<COLT>((const COLT*)rec, W, c_cells[h.p][h.r], h.x);
+            COLT Bact = bmask<COLT>((const COLT*)rec, W, tb.cells[h.p * 4 + h.r], h.x);
+            const uint32_t show = !((Bact >> h.y) & 1);
+            s_box[tid] = (uint32_t)h.x | ((uint32_t)h.y << 8) | ((uint32_t)tb.n[h.p] << 16) | (show << 20) |
+                         ((uint32_t)h.p << 24) | ((uint32_t)h.r << 28);
             if (p.mode == 2 && p.info_board) {
                 // info["board"]: FeatureVectorObservation of the real observation (wrappers/grouped.py:260-264)
                 uint8_t f[32];
                 int ln;
-                placement_features<COLT>(cfg, (const COLT*)rec, c_cells[h.p][h.r], h.x, h.y, !((Bact >> h.y) & 1), false,
-                                         COLT(3), f, ln);
+                placement_features<COLT>(cfg, (const COLT*)rec, tb.cells[h.p * 4 + h.r], h.x, h.y, show != 0, false, COLT(3), f, ln);
                 for (int i = 0; i < cfg.F; i++) p.info_board[e * cfg.F + i] = f[i];
             }
         }
         __syncthreads();
-        const bool want_obs = p.o_board != nullptr;
 
-        // (D) observation images: board rows, queue, holder
-        if (want_obs)
-        for (int it = tid; it < nv * H; it += E) {
-            int e = it / H, row = it - e * H;
-            fill_board_row<WT>(cfg, (const uint32_t*)(s_brd + e * BS + cfg.ids_off), i_board, e * OB, row);
-        }
         if (want_obs) {
-            const int Q = cfg.Q;
-            for (int it = tid; it < nv * 4 * Q; it += E) {
-                int e = it / (4 * Q), rem = it - e * 4 * Q, i = rem / Q, q = rem - i * Q;
-                uint32_t w2 = s_hot[e * 8 + 2], w3 = s_hot[e * 8 + 3];
-                uint64_t queue = (uint64_t)w2 | ((uint64_t)w3 << 32);
-                int pc = (int)((queue >> (4 * q)) & 15u);
-                ((uint32_t*)i_queue)[e * 4 * Q + i * Q + q] = c_rowbytes[pc][0][i];
-            }
-            for (int it = tid; it < nv * 4; it += E) {
-                int e = it >> 2, i = it & 3;
-                uint32_t a = s_hot[e * 8];
-                int hold = (a >> 18) & 15, hr = (a >> 22) & 3;
-                ((uint32_t*)i_holder)[e * 4 + i] = hold ? c_rowbytes[hold - 1][hr][i] : 0x01010101u;
-            }
-        }
-        __syncthreads();
-        // (E) active piece overlay + bounding-box mask (Tetris._get_obs, envs/tetris.py:566-576)
-        if (tid < nv && want_obs) {
-            uint8_t* ib = i_board + tid * OB;
-            if (!((Bact >> h.y) & 1)) {
-                uint32_t cells = c_cells[h.p][h.r];
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    int c = (cells >> (4 * k)) & 15;
-                    ib[(h.y + (c >> 2)) * Wp + h.x + (c & 3)] = (uint8_t)(h.p + 2);
+            // (D) observation images: board rows, queue, holder (all threads)
+            if (WT == 10 && (HT % 4) == 0) {
+                constexpr int G = HT ? HT / 4 : 1;
+                for (int it = tid; it < nv * G; it += T) {
+                    int e = it / G, g4 = it - e * G;
+                    fill_rows4_w10((const uint32_t*)(s_brd + e * BS + 40) + 5 * g4, i_board + e * OB + g4 * 72);
+                }
+            } else if (WT == 20 && (HT % 2) == 0) {
+                constexpr int G = HT ? HT / 2 : 1;
+                for (int it = tid; it < nv * G; it += T) {
+                    int e = it / G, g2 = it - e * G;
+                    fill_rows2_w20((const uint32_t*)(s_brd + e * BS + cfg.ids_off) + 5 * g2, i_board + e * OB + g2 * 56);
+                }
+            } else {
+                for (int it = tid; it < nv * H; it += T) {
+                    int e = it / H, row = it - e * H;
+                    fill_board_row<WT>(cfg, (const uint32_t*)(s_brd + e * BS + cfg.ids_off), i_board, e * OB, row);
                 }
             }
-            pm_n = c_n[h.p]; pm_x = h.x; pm_y = h.y;
-            for (int i = 0; i < pm_n; i++)
-                for (int j = 0; j < pm_n; j++) i_mask[tid * OB + (pm_y + i) * Wp + pm_x + j] = 1;
-        } else pm_n = 0;
+            for (int it = tid; it < nv * 4; it += T) {
+                int e = it >> 2, i = it & 3;
+                uint32_t w0 = s_hot[e * 8];
+                uint64_t queue = (uint64_t)s_hot[e * 8 + 2] | ((uint64_t)s_hot[e * 8 + 3] << 32);
+                uint32_t* qo = (uint32_t*)i_queue + e * 4 * Q + i * Q;
+                for (int q = 0; q < Q; q++) qo[q] = s_rowbytes[((int)((queue >> (4 * q)) & 15u)) * 16 + i];
+                int hold = (w0 >> 18) & 15, hr = (w0 >> 22) & 3;
+                ((uint32_t*)i_holder)[it] = hold ? s_rowbytes[((hold - 1) * 4 + hr) * 4 + i] : 0x01010101u;
+            }
+            __syncthreads();
+            // (E) active piece overlay + bounding-box mask (Tetris._get_obs, envs/tetris.py:566-576)
+            for (int it = tid; it < nv * 16; it += T) {
+                int e = it >> 4, i = (it >> 2) & 3, j = it & 3;
+                uint32_t bx = s_box[e];
+                int n = (bx >> 16) & 15, x = bx & 255, y = (bx >> 8) & 255;
+                if (i < n && j < n) i_mask[e * OB + (y + i) * Wp + x + j] = 1;
+                if (i == 0 && ((bx >> 20) & 1)) {
+                    int pc = (bx >> 24) & 7, c = (s_cells[pc * 4 + (bx >> 28)] >> (4 * j)) & 15;
+                    i_board[e * OB + (y + (c >> 2)) * Wp + x + (c & 3)] = (uint8_t)(pc + 2);
+                }
+            }
+        }
         // (F) stores
         fence_async_smem();
         __syncthreads();
         const bool leader = (tid == 0);
         if (want_obs) {
-            tile_store(p.o_board + base * OB, i_board, (uint32_t)(nv * OB), leader, tid, E);
-            tile_store(p.o_mask + base * OB, i_mask, (uint32_t)(nv * OB), leader, tid, E);
+            tile_store(p.o_board + base * OB, i_board, (uint32_t)(nv * OB), leader, tid, T);
+            tile_store(p.o_mask + base * OB, i_mask, (uint32_t)(nv * OB), leader, tid, T);
             if (leader) {
                 bulk_s2g(p.o_holder + base * 16, i_holder, (uint32_t)(nv * 16));
                 bulk_s2g(p.o_queue + base * OQ, i_queue, (uint32_t)(nv * OQ));
@@ -301,6 +366,7 @@ __global__ void k_step(const __grid_constant__ StepParams p) {
         if (leader) bulk_s2g(p.hot + base * 32, s_hot, (uint32_t)(nv * 32));
         if (res.dirty && tid < nv) bulk_s2g(p.board + (base + tid) * BS, s_brd + tid * BS, (uint32_t)BS);
         bulk_commit();
+        nv_prev = nv;
     }
     bulk_wait_all();
     if (p.stats) {
