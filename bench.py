@@ -80,8 +80,9 @@ def bytes_per_step(layout, queue, commit_frac):
     """Algorithmic (compulsory) HBM bytes per env-step of OUR layout ('Roofline')."""
     ob = layout.obs_board_bytes
     obs = 2 * ob + 16 + 16 * queue
-    read = layout.hot_stride + layout.board_stride + 4
-    write = layout.hot_stride + obs + 10 + commit_frac * layout.board_stride
+    # rng record: read every step; written back when a bag is reshuffled (one commit in seven)
+    read = layout.hot_stride + layout.board_stride + layout.rng_stride + 4
+    write = layout.hot_stride + obs + 10 + commit_frac * layout.board_stride + commit_frac / 7.0 * layout.rng_stride
     return read + write, obs
 
 

@@ -226,14 +226,18 @@ static int launch_step(tg_env* env, StepParams& p, cudaStream_t s) {
     auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 127) / 128 * 128; return (int)o; };
     for (;;) {
         off = 0;
-        p.off_hot = take((size_t)E * 32);
-        p.off_brd = take((size_t)E * d.board_stride + 16);
+        p.st_hot = (int)(((size_t)E * 32 + 127) / 128 * 128);
+        p.st_brd = (int)(((size_t)E * d.board_stride + 16 + 127) / 128 * 128);
+        p.st_rng = (int)(((size_t)E * d.rng_stride + 127) / 128 * 128);
+        p.off_hot = take((size_t)2 * p.st_hot);
+        p.off_brd = take((size_t)2 * p.st_brd);
+        p.off_rng = take((size_t)2 * p.st_rng);
         p.off_iboard = take((size_t)E * d.OB + 16);
         p.off_imask = take((size_t)E * d.OB + 16);
         p.off_iholder = take((size_t)E * 16);
         p.off_iqueue = take((size_t)E * d.OQ);
         p.off_bar = take(16);
-        p.off_box = take((size_t)E * 4);
+        p.off_box = take((size_t)2 * E * 4);
         p.off_tab = take(112 * 4 + 64 + 32);
         if (off <= 100 * 1024 || E == 32) break;
         E -= 32;

@@ -158,8 +158,9 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32
 }
 
 struct Rng {
-    // view over one env's rng record in GLOBAL memory (touched only when a piece is drawn)
+    // view over one env's rng record (staged in shared memory by the step kernel)
     uint32_t* rec;
+    bool dirty;          // record modified -> must be written back
     const uint8_t* seq;  // this env's injected stream (TG_RNG_SEQUENCE)
     uint64_t gid;        // global env id
 };
@@ -186,6 +187,7 @@ __device__ __forceinline__ uint32_t pcg64_next32(uint32_t* rec) {
 // in-place Fisher-Yates of the 7-bag (BagRandomizer.shuffle_bag, components/tetromino_randomizer.py:82-85)
 __device__ __noinline__ uint32_t shuffle_bag(const DevCfg& cfg, Rng& g, uint32_t bag) {
     uint32_t j6[6];
+    g.dirty = true;
     if (cfg.rng_mode == 2) {
         // numpy Generator.shuffle: for i = 6..1: j = random_interval(i) (masked rejection on next_uint32)
         for (int i = 6; i >= 1; i--) {
@@ -220,6 +222,7 @@ __device__ __forceinline__ int draw_piece(const DevCfg& cfg, Rng& g, Hot& h) {
     if (cfg.rng_mode == 1) {
         uint64_t cur = ((uint64_t*)g.rec)[0];
         ((uint64_t*)g.rec)[0] = cur + 1;
+        g.dirty = true;
         return g.seq[cur % (uint64_t)cfg.seq_len];
     }
     // BagRandomizer.get_next_tetromino (components/tetromino_randomizer.py:67-80)

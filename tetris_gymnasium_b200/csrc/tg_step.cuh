@@ -74,7 +74,8 @@ struct StepParams {
     int mode;                        // 0 = step, 1 = reset, 2 = grouped placement step
     int E;                           // envs per tile
     // shared-memory carve-up (bytes from the 128-aligned base)
-    int off_hot, off_brd, off_iboard, off_imask, off_iholder, off_iqueue, off_bar, off_box, off_tab;
+    int off_hot, off_brd, off_rng, off_iboard, off_imask, off_iholder, off_iqueue, off_bar, off_box, off_tab;
+    int st_hot, st_brd, st_rng;      // bytes between the two pipeline stages of each state buffer
 };
 
 // expand 8 nibbles -> 8 id bytes (two words)
@@ -178,16 +179,14 @@ __global__ void __launch_bounds__(256) k_step(const __grid_constant__ StepParams
     const int E = p.E, T = blockDim.x, tid = threadIdx.x;
     const int W = WT ? WT : cfg.W, H = HT ? HT : cfg.H;
     const int Wp = W + 2 * P, Hp = H + P;
-    const int OB = Hp * Wp, OQ = cfg.OQ, BS = cfg.board_stride, Q = cfg.Q;
+    const int OB = Hp * Wp, OQ = cfg.OQ, BS = cfg.board_stride, RS = cfg.rng_stride, Q = cfg.Q;
 
-    uint32_t* s_hot = (uint32_t*)(smem + p.off_hot);
-    uint8_t* s_brd = smem + p.off_brd;
     uint8_t* i_board = smem + p.off_iboard;
     uint8_t* i_mask = smem + p.off_imask;
     uint8_t* i_holder = smem + p.off_iholder;
     uint8_t* i_queue = smem + p.off_iqueue;
-    uint64_t* bar = (uint64_t*)(smem + p.off_bar);
-    uint32_t* s_box = (uint32_t*)(smem + p.off_box);   // per env: x | y<<8 | n<<16 | show<<20 | piece<<24 | rot<<28
+    uint64_t* bar = (uint64_t*)(smem + p.off_bar);     // bar[0], bar[1]: one per state stage
+    uint32_t* s_box2 = (uint32_t*)(smem + p.off_box);  // [2][E]: x | y<<8 | n<<16 | show<<20 | piece<<24 | rot<<28
     uint32_t* s_rowbytes = (uint32_t*)(smem + p.off_tab);            // 112 words
     unsigned short* s_cells = (unsigned short*)(s_rowbytes + 112);   // 28 halves
     int* s_n = (int*)(s_rowbytes + 112 + 16);                        // 7 ints
@@ -198,66 +197,66 @@ __global__ void __launch_bounds__(256) k_step(const __grid_constant__ StepParams
     for (int i = tid; i < 112; i += T) s_rowbytes[i] = (&c_rowbytes[0][0][0])[i];
     for (int i = tid; i < 28; i += T) s_cells[i] = (&c_cells[0][0])[i];
     for (int i = tid; i < 7; i += T) s_n[i] = c_n[i];
-    for (int i = tid; i < E; i += T) s_box[i] = 0;
+    for (int i = tid; i < 2 * E; i += T) s_box2[i] = 0;
     for (int i = tid; i < OB; i += T) {  // env 0's template ...
         int r = i / Wp, c = i - r * Wp;
         i_board[i] = (r < H && c >= P && c < P + W) ? 0 : 1;
     }
     for (int i = tid; i < (E * OB + 3) / 4; i += T) ((uint32_t*)i_mask)[i] = 0;
-    if (tid == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (tid == 0) { mbar_init(bar, 1); mbar_init(bar + 1, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     __syncthreads();
-    for (int i = OB + tid; i < E * OB; i += T) i_board[i] = i_board[i % OB];  // ... replicated
-    __syncthreads();
+    for (int e = 1; e < E; e++)          // ... replicated to the other env slots
+        for (int i = tid; i < OB; i += T) i_board[e * OB + i] = i_board[i];
 
     const int64_t ntiles = (p.n + E - 1) / E;
-    uint32_t parity = 0;
     double st_ep = 0, st_ret = 0, st_len = 0, st_lines = 0;
     const bool want_obs = p.o_board != nullptr;
     int nv_prev = 0;
 
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    auto issue_load = [&](int64_t tile, int b) {   // TMA bulk loads of one tile's state into stage b (one thread)
         const int64_t base = tile * E;
         const int nv = (int)min((int64_t)E, p.n - base);
-        // (A) previous tile's stores must have finished reading shared memory
-        bulk_wait_read();
-        __syncthreads();
-        // (B) bulk loads of the tile's state (async) ...
-        if (tid == 0) {
-            mbar_expect_tx(bar, (uint32_t)(nv * 32 + nv * BS));
-            bulk_g2s(s_hot, p.hot + base * 32, (uint32_t)(nv * 32), bar);
-            bulk_g2s(s_brd, p.board + base * BS, (uint32_t)(nv * BS), bar);
-        }
-        int action = 0;
-        if (p.mode != 1 && tid < nv) action = p.actions[base + tid];
-        // ... while all threads erase the bounding boxes drawn into the mask image for the previous tile
-        if (want_obs)
-            for (int it = tid; it < nv_prev * 16; it += T) {
-                int e = it >> 4, i = (it >> 2) & 3, j = it & 3;
-                uint32_t bx = s_box[e];
-                int n = (bx >> 16) & 15;
-                if (i < n && j < n) i_mask[e * OB + (((bx >> 8) & 255) + i) * Wp + (bx & 255) + j] = 0;
-            }
-        __syncthreads();   // s_box is rewritten by the logic threads below
-        mbar_wait(bar, parity);
-        parity ^= 1;
+        mbar_expect_tx(bar + b, (uint32_t)(nv * (32 + BS + RS)));
+        bulk_g2s(smem + p.off_hot + b * p.st_hot, p.hot + base * 32, (uint32_t)(nv * 32), bar + b);
+        bulk_g2s(smem + p.off_brd + b * p.st_brd, p.board + base * BS, (uint32_t)(nv * BS), bar + b);
+        bulk_g2s(smem + p.off_rng + b * p.st_rng, p.rng + base * RS, (uint32_t)(nv * RS), bar + b);
+    };
+    if (tid == 0 && (int64_t)blockIdx.x < ntiles) issue_load(blockIdx.x, 0);
+    __syncthreads();
 
-        // (C) game logic, one thread per env
+    int k = 0;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, k++) {
+        const int b = k & 1;
+        const int64_t base = tile * E;
+        const int nv = (int)min((int64_t)E, p.n - base);
+        uint32_t* s_hot = (uint32_t*)(smem + p.off_hot + b * p.st_hot);
+        uint8_t* s_brd = smem + p.off_brd + b * p.st_brd;
+        uint8_t* s_rng = smem + p.off_rng + b * p.st_rng;
+        uint32_t* s_box = s_box2 + b * E;
+        const uint32_t* s_box_prev = s_box2 + (b ^ 1) * E;
+
+        // (C) game logic, one thread per env, on the state that was prefetched into stage b
         StepResult res;
         res.dirty = 0;
+        bool rng_dirty = false;
         if (tid < nv) {
+            const int64_t e = base + tid;
+            int action = 0;
+            if (p.mode != 1) action = p.actions[e];
+            mbar_wait(bar + b, (uint32_t)((k >> 1) & 1));
             Hot h;
             uint32_t* rec = (uint32_t*)(s_brd + tid * BS);
-            const int64_t e = base + tid;
             hot_load(h, s_hot + tid * 8);
             Rng g;
-            g.rec = (uint32_t*)(p.rng + e * cfg.rng_stride);
+            g.rec = (uint32_t*)(s_rng + tid * RS);
             g.seq = p.seq ? p.seq + e * cfg.seq_len : nullptr;
             g.gid = cfg.env_id_offset + (uint64_t)e;
+            g.dirty = false;
             res.reward = 0; res.lines = 0; res.terminated = 0;
             bool need_reset = false;
             if (p.mode == 1) {
                 need_reset = (!p.reset_mask || p.reset_mask[e]);
-                if (need_reset && p.seeds && cfg.rng_mode == 0) { ((uint64_t*)g.rec)[0] = p.seeds[e]; g.rec[2] = 0; }
+                if (need_reset && p.seeds && cfg.rng_mode == 0) { ((uint64_t*)g.rec)[0] = p.seeds[e]; g.rec[2] = 0; g.dirty = true; }
             } else if (cfg.autoreset == 1 && h.pending) {
                 need_reset = true;  // gymnasium NEXT_STEP autoreset: the action is ignored, the env is reset
             } else {
@@ -288,6 +287,7 @@ __global__ void __launch_bounds__(256) k_step(const __grid_constant__ StepParams
             }
             if (need_reset) { env_reset<COLT>(cfg, h, rec, g); res.dirty = 1; }
             if (p.mode == 2 && need_reset) p.fill_high[e] = 0;
+            rng_dirty = g.dirty;
             hot_store(h, s_hot + tid * 8);
             if (p.mode != 1) {
                 p.reward[e] = (float)res.reward;
@@ -307,10 +307,25 @@ __global__ void __launch_bounds__(256) k_step(const __grid_constant__ StepParams
                 for (int i = 0; i < cfg.F; i++) p.info_board[e * cfg.F + i] = f[i];
             }
         }
+        // the previous tile's stores must have finished reading shared memory (images + the other state stage)
+        bulk_wait_read();
         __syncthreads();
+        if (tid >= nv) mbar_wait(bar + b, (uint32_t)((k >> 1) & 1));  // phase already complete: acquire the TMA writes
+        // prefetch the next tile's state into the other stage while this tile's images are produced
+        if (tid == 0 && tile + gridDim.x < ntiles) issue_load(tile + gridDim.x, b ^ 1);
 
         if (want_obs) {
-            // (D) observation images: board rows, queue, holder (all threads)
+            // (D) erase last tile's bounding boxes; observation images: board rows, queue, holder (all threads)
+            for (int it = tid; it < nv_prev * 4; it += T) {
+                int e = it >> 2, i = it & 3;
+                uint32_t bx = s_box_prev[e];
+                int n = (bx >> 16) & 15;
+                if (i < n) {
+                    int addr = e * OB + (((bx >> 8) & 255) + i) * Wp + (bx & 255), a = addr & 3;
+                    *(uint32_t*)(i_mask + addr - a) = 0;
+                    if (a + n > 4) *(uint32_t*)(i_mask + addr - a + 4) = 0;
+                }
+            }
             if (WT == 10 && (HT % 4) == 0) {
                 constexpr int G = HT ? HT / 4 : 1;
                 for (int it = tid; it < nv * G; it += T) {
@@ -329,24 +344,33 @@ __global__ void __launch_bounds__(256) k_step(const __grid_constant__ StepParams
                     fill_board_row<WT>(cfg, (const uint32_t*)(s_brd + e * BS + cfg.ids_off), i_board, e * OB, row);
                 }
             }
+            for (int it = tid; it < nv * Q; it += T) {   // queue: one piece per item, its 4 matrix rows in one 128-bit read
+                int e = it / Q, q = it - e * Q;
+                uint64_t queue = (uint64_t)s_hot[e * 8 + 2] | ((uint64_t)s_hot[e * 8 + 3] << 32);
+                uint4 rb = *(const uint4*)(s_rowbytes + ((int)((queue >> (4 * q)) & 15u)) * 16);
+                uint32_t* qo = (uint32_t*)i_queue + e * 4 * Q + q;
+                qo[0] = rb.x; qo[Q] = rb.y; qo[2 * Q] = rb.z; qo[3 * Q] = rb.w;
+            }
             for (int it = tid; it < nv * 4; it += T) {
                 int e = it >> 2, i = it & 3;
                 uint32_t w0 = s_hot[e * 8];
-                uint64_t queue = (uint64_t)s_hot[e * 8 + 2] | ((uint64_t)s_hot[e * 8 + 3] << 32);
-                uint32_t* qo = (uint32_t*)i_queue + e * 4 * Q + i * Q;
-                for (int q = 0; q < Q; q++) qo[q] = s_rowbytes[((int)((queue >> (4 * q)) & 15u)) * 16 + i];
                 int hold = (w0 >> 18) & 15, hr = (w0 >> 22) & 3;
                 ((uint32_t*)i_holder)[it] = hold ? s_rowbytes[((hold - 1) * 4 + hr) * 4 + i] : 0x01010101u;
             }
             __syncthreads();
             // (E) active piece overlay + bounding-box mask (Tetris._get_obs, envs/tetris.py:566-576)
-            for (int it = tid; it < nv * 16; it += T) {
-                int e = it >> 4, i = (it >> 2) & 3, j = it & 3;
+            for (int it = tid; it < nv * 4; it += T) {
+                int e = it >> 2, i = it & 3;
                 uint32_t bx = s_box[e];
                 int n = (bx >> 16) & 15, x = bx & 255, y = (bx >> 8) & 255;
-                if (i < n && j < n) i_mask[e * OB + (y + i) * Wp + x + j] = 1;
-                if (i == 0 && ((bx >> 20) & 1)) {
-                    int pc = (bx >> 24) & 7, c = (s_cells[pc * 4 + (bx >> 28)] >> (4 * j)) & 15;
+                if (i < n) {
+                    int addr = e * OB + (y + i) * Wp + x, a = addr & 3;
+                    uint64_t v = (uint64_t)(0x01010101u >> (8 * (4 - n))) << (8 * a);
+                    *(uint32_t*)(i_mask + addr - a) = (uint32_t)v;
+                    if (a + n > 4) *(uint32_t*)(i_mask + addr - a + 4) = (uint32_t)(v >> 32);
+                }
+                if ((bx >> 20) & 1) {
+                    int pc = (bx >> 24) & 7, c = (s_cells[pc * 4 + (bx >> 28)] >> (4 * i)) & 15;
                     i_board[e * OB + (y + (c >> 2)) * Wp + x + (c & 3)] = (uint8_t)(pc + 2);
                 }
             }
@@ -364,9 +388,12 @@ __global__ void __launch_bounds__(256) k_step(const __grid_constant__ StepParams
             }
         }
         if (leader) bulk_s2g(p.hot + base * 32, s_hot, (uint32_t)(nv * 32));
-        if (res.dirty && tid < nv) bulk_s2g(p.board + (base + tid) * BS, s_brd + tid * BS, (uint32_t)BS);
+        if (tid < nv) {
+            if (res.dirty) bulk_s2g(p.board + (base + tid) * BS, s_brd + tid * BS, (uint32_t)BS);
+            if (rng_dirty) bulk_s2g(p.rng + (base + tid) * RS, s_rng + tid * RS, (uint32_t)RS);
+        }
         bulk_commit();
-        nv_prev = nv;
+        nv_prev = want_obs ? nv : 0;
     }
     bulk_wait_all();
     if (p.stats) {
