@@ -69,7 +69,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.02)
+            time.sleep(0.004)
 
     def result(self):
         return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
@@ -146,12 +146,13 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="envs per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-probe", action="store_true", help="skip the commit-fraction probe (torch kernels) e.g. under ncu")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -179,14 +180,6 @@ def main():
     acts = torch.randint(0, 8, (Wm + K, n), dtype=torch.int32, device=dev, generator=g)
     for t in range(Wm):
         env.step(acts[t])
-    # commit fraction (board-record write-backs) measured outside the timed region
-    prev_q = env._o_queue.clone()
-    changed = 0.0
-    for t in range(8):
-        env.step(acts[t % (Wm + K)])
-        changed += float((env._o_queue != prev_q).flatten(1).any(1).float().mean())
-        prev_q.copy_(env._o_queue)
-    commit_frac = changed / 8
     env.episode_stats(reset=True)
 
     sampler = ClockSampler(local)
@@ -212,6 +205,19 @@ def main():
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
     ms_max = float(tms[0])
     value = world * n * K / (ms_max * 1e-3)
+
+    # commit fraction (share of env-steps that write their board record back), probed AFTER the timed region
+    commit_frac = 0.0
+    if not args.no_probe:
+        prev_q = env._o_queue.clone()
+        changed = 0.0
+        for t in range(8):
+            env.step(acts[t % (Wm + K)])
+            changed += float((env._o_queue != prev_q).flatten(1).any(1).float().mean())
+            prev_q.copy_(env._o_queue)
+        commit_frac = changed / 8
+    else:
+        commit_frac = 0.148
 
     # end-to-end through host buffers (tg_step_host): pinned actions H2D, obs dict + 5-tuple D2H every step
     e2e = None

@@ -24,6 +24,8 @@ struct tg_env {
     int col64;
     int tile;             // envs per CTA tile of the step kernel
     int threads_per_env;  // CTA threads = tile * threads_per_env (logic uses one thread per env, image fill uses all)
+    int warp_specialized; // 1: k_step_ws (logic warp runs a tile ahead of the image warps)
+    int fill_warps;       // image/store warps per CTA of k_step_ws
     std::string err;
     // tg_step_host staging
     cudaStream_t hs[3];
@@ -173,6 +175,10 @@ extern "C" int tg_create(const tg_config* cfg, int device, tg_env** out) {
     env->threads_per_env = 4;
     if (const char* t = getenv("TG_TILE")) { int v = atoi(t); if (v == 32 || v == 64 || v == 96 || v == 128) env->tile = v; }
     if (const char* t = getenv("TG_TPE")) { int v = atoi(t); if (v >= 1 && v <= 8) env->threads_per_env = v; }
+    env->warp_specialized = 1;
+    env->fill_warps = 3;
+    if (const char* t = getenv("TG_WS")) env->warp_specialized = atoi(t) != 0;
+    if (const char* t = getenv("TG_NF")) { int v = atoi(t); if (v >= 1 && v <= 3) env->fill_warps = v; }
     int rc = upload_tables(env);
     if (rc != TG_OK) { g_create_err = env->err; delete env; return rc; }
     *out = env;
@@ -204,8 +210,8 @@ static int check_state(tg_env* env, const tg_state& st) {
 
 // ---- step / reset launcher ----------------------------------------------------------------------
 template <int WT, int HT, class COLT>
-static int launch_step_t(tg_env* env, StepParams& p, int T, size_t smem, cudaStream_t s) {
-    auto kern = k_step<WT, HT, COLT>;
+static int launch_step_t(tg_env* env, StepParams& p, int T, size_t smem, bool ws, cudaStream_t s) {
+    auto kern = ws ? k_step_ws<WT, HT, COLT> : k_step<WT, HT, COLT>;
     CUDA_TRY(env, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     CUDA_TRY(env, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, T, smem));
@@ -218,9 +224,11 @@ static int launch_step_t(tg_env* env, StepParams& p, int T, size_t smem, cudaStr
     return TG_OK;
 }
 
-static int launch_step(tg_env* env, StepParams& p, cudaStream_t s) {
+static int launch_step(tg_env* env, StepParams& p, cudaStream_t s, int force_plain = 0) {
     const DevCfg& d = env->dev;
-    int E = env->tile;
+    const bool ws = env->warp_specialized && !force_plain;
+    int E = ws ? 32 : env->tile;
+    const int NS = ws ? 3 : 2;
     // shared-memory carve-up
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 127) / 128 * 128; return (int)o; };
@@ -229,28 +237,31 @@ static int launch_step(tg_env* env, StepParams& p, cudaStream_t s) {
         p.st_hot = (int)(((size_t)E * 32 + 127) / 128 * 128);
         p.st_brd = (int)(((size_t)E * d.board_stride + 16 + 127) / 128 * 128);
         p.st_rng = (int)(((size_t)E * d.rng_stride + 127) / 128 * 128);
-        p.off_hot = take((size_t)2 * p.st_hot);
-        p.off_brd = take((size_t)2 * p.st_brd);
-        p.off_rng = take((size_t)2 * p.st_rng);
+        p.off_hot = take((size_t)NS * p.st_hot);
+        p.off_brd = take((size_t)NS * p.st_brd);
+        p.off_rng = take((size_t)NS * p.st_rng);
         p.off_iboard = take((size_t)E * d.OB + 16);
         p.off_imask = take((size_t)E * d.OB + 16);
         p.off_iholder = take((size_t)E * 16);
         p.off_iqueue = take((size_t)E * d.OQ);
-        p.off_bar = take(16);
-        p.off_box = take((size_t)2 * E * 4);
+        p.off_bar = take(32);
+        p.off_box = take((size_t)(2 * NS + 1) * E * 4);
         p.off_tab = take(112 * 4 + 64 + 32);
         if (off <= 100 * 1024 || E == 32) break;
         E -= 32;
     }
-    if (off > 227 * 1024) return fail(env, TG_ERR_CONFIG, "board too large for the shared-memory tile (%zu B)", off);
+    if (off > 227 * 1024) {
+        if (ws) return launch_step(env, p, s, 1);   // three state stages do not fit: two-stage kernel
+        return fail(env, TG_ERR_CONFIG, "board too large for the shared-memory tile (%zu B)", off);
+    }
     p.cfg = d;
     p.E = E;
-    int T = E * env->threads_per_env;
+    int T = ws ? 32 * (1 + env->fill_warps) : E * env->threads_per_env;
     if (T > 256) T = 256;
-    if (d.W == 10 && d.H == 20) return launch_step_t<10, 20, uint32_t>(env, p, T, off, s);
-    if (d.W == 20 && d.H == 40) return launch_step_t<20, 40, uint64_t>(env, p, T, off, s);
-    if (env->col64) return launch_step_t<0, 0, uint64_t>(env, p, T, off, s);
-    return launch_step_t<0, 0, uint32_t>(env, p, T, off, s);
+    if (d.W == 10 && d.H == 20) return launch_step_t<10, 20, uint32_t>(env, p, T, off, ws, s);
+    if (d.W == 20 && d.H == 40) return launch_step_t<20, 40, uint64_t>(env, p, T, off, ws, s);
+    if (env->col64) return launch_step_t<0, 0, uint64_t>(env, p, T, off, ws, s);
+    return launch_step_t<0, 0, uint32_t>(env, p, T, off, ws, s);
 }
 
 static int check_obs(tg_env* env, const tg_obs& o) {

@@ -172,6 +172,175 @@ __device__ __forceinline__ void fill_rows2_w20(const uint32_t* ids5, uint8_t* ou
     o[12] = b4;
 }
 
+// ---- per-env logic of one tile slot (shared by both step kernels) -----------------------------------
+struct TileStats { double ep, ret, len, lines; };
+
+// Runs reset / step / grouped placement for env `e` whose records sit at slot `slot` of the staged tile.
+// Returns bit0 = board record dirty, bit1 = rng record dirty.  Writes the 5-tuple scalars and s_box[slot].
+template <class COLT>
+__device__ __forceinline__ uint32_t logic_one_env(const StepParams& p, const Tabs& tb, int64_t e, int slot, int action,
+                                                  uint32_t* s_hot, uint8_t* s_brd, uint8_t* s_rng, uint32_t* s_box,
+                                                  TileStats& st) {
+    const DevCfg& cfg = p.cfg;
+    const int BS = cfg.board_stride, RS = cfg.rng_stride;
+    StepResult res;
+    res.dirty = 0; res.reward = 0; res.lines = 0; res.terminated = 0;
+    Hot h;
+    uint32_t* rec = (uint32_t*)(s_brd + slot * BS);
+    hot_load(h, s_hot + slot * 8);
+    Rng g;
+    g.rec = (uint32_t*)(s_rng + slot * RS);
+    g.seq = p.seq ? p.seq + e * cfg.seq_len : nullptr;
+    g.gid = cfg.env_id_offset + (uint64_t)e;
+    g.dirty = false;
+    bool need_reset = false;
+    if (p.mode == 1) {
+        need_reset = (!p.reset_mask || p.reset_mask[e]);
+        if (need_reset && p.seeds && cfg.rng_mode == 0) { ((uint64_t*)g.rec)[0] = p.seeds[e]; g.rec[2] = 0; g.dirty = true; }
+    } else if (cfg.autoreset == 1 && h.pending) {
+        need_reset = true;  // gymnasium NEXT_STEP autoreset: the action is ignored, the env is reset
+    } else {
+        if (p.mode == 2) {
+            // GroupedActionsObservations.step (wrappers/grouped.py:209-269)
+            bool ok = (unsigned)action < (unsigned)cfg.A && p.legal[e * cfg.A + action] != 0;
+            p.fill_high[e] = (uint8_t)(!ok && cfg.terminate_on_illegal);
+            if (ok) {
+                h.x = (action >> 2) + P - tb.n[h.p] / 2;   // y untouched (wrappers/grouped.py:244-254)
+                h.r = (h.r + (action & 3)) & 3;
+                env_step<COLT>(cfg, tb, h, rec, g, cfg.act_hard, res);
+            } else if (cfg.terminate_on_illegal) {
+                res.reward = cfg.r_invalid; res.terminated = 1;   // env untouched, episode ends
+            } else {
+                env_step<COLT>(cfg, tb, h, rec, g, cfg.act_noop, res);
+                res.reward = cfg.r_invalid;
+            }
+        } else {
+            env_step<COLT>(cfg, tb, h, rec, g, action, res);
+        }
+        h.ep_ret += (float)res.reward; h.ep_len += 1; h.ep_lines += res.lines;
+        if (res.terminated) {
+            st.ep += 1; st.ret += h.ep_ret; st.len += h.ep_len; st.lines += h.ep_lines;
+            h.ep_ret = 0; h.ep_len = 0; h.ep_lines = 0;
+            if (cfg.autoreset == 1) h.pending = 1;
+            else if (cfg.autoreset == 2) need_reset = true;
+        }
+    }
+    if (need_reset) { env_reset<COLT>(cfg, h, rec, g); res.dirty = 1; }
+    if (p.mode == 2 && need_reset) p.fill_high[e] = 0;
+    hot_store(h, s_hot + slot * 8);
+    if (p.mode != 1) {
+        p.reward[e] = (float)res.reward;
+        p.terminated[e] = (uint8_t)res.terminated;
+        p.truncated[e] = 0;
+        p.lines[e] = res.lines;
+    }
+    COLT Bact = bmask<COLT>((const COLT*)rec, cfg.W, tb.cells[h.p * 4 + h.r], h.x);
+    const uint32_t show = !((Bact >> h.y) & 1);
+    s_box[slot] = (uint32_t)h.x | ((uint32_t)h.y << 8) | ((uint32_t)tb.n[h.p] << 16) | (show << 20) |
+                  ((uint32_t)h.p << 24) | ((uint32_t)h.r << 28);
+    if (p.mode == 2 && p.info_board) {
+        // info["board"]: FeatureVectorObservation of the real observation (wrappers/grouped.py:260-264)
+        uint8_t f[32];
+        int ln;
+        placement_features<COLT>(cfg, (const COLT*)rec, tb.cells[h.p * 4 + h.r], h.x, h.y, show != 0, false, COLT(3), f, ln);
+        for (int i = 0; i < cfg.F; i++) p.info_board[e * cfg.F + i] = f[i];
+    }
+    return (uint32_t)res.dirty | ((uint32_t)g.dirty << 1);
+}
+
+// ---- observation images of one tile (called by `nt` cooperating threads, `t` = index among them) ------
+__device__ __forceinline__ void mask_clear_boxes(const uint32_t* boxes, int n_env, uint8_t* i_mask, int OB, int Wp, int t, int nt) {
+    for (int it = t; it < n_env * 4; it += nt) {
+        int e = it >> 2, i = it & 3;
+        uint32_t bx = boxes[e];
+        int n = (bx >> 16) & 15;
+        if (i < n) {
+            int addr = e * OB + (((bx >> 8) & 255) + i) * Wp + (bx & 255), a = addr & 3;
+            *(uint32_t*)(i_mask + addr - a) = 0;
+            if (a + n > 4) *(uint32_t*)(i_mask + addr - a + 4) = 0;
+        }
+    }
+}
+template <int WT, int HT>
+__device__ __forceinline__ void fill_images(const DevCfg& cfg, int nv, const uint32_t* s_hot, const uint8_t* s_brd,
+                                            const uint32_t* s_rowbytes, uint8_t* i_board, uint8_t* i_holder, uint8_t* i_queue,
+                                            int t, int nt) {
+    const int W = WT ? WT : cfg.W, H = HT ? HT : cfg.H;
+    const int OB = (H + P) * (W + 2 * P), BS = cfg.board_stride, Q = cfg.Q;
+    if (WT == 10 && (HT % 4) == 0) {
+        constexpr int G = HT ? HT / 4 : 1;
+        for (int it = t; it < nv * G; it += nt) {
+            int e = it / G, g4 = it - e * G;
+            fill_rows4_w10((const uint32_t*)(s_brd + e * BS + 40) + 5 * g4, i_board + e * OB + g4 * 72);
+        }
+    } else if (WT == 20 && (HT % 2) == 0) {
+        constexpr int G = HT ? HT / 2 : 1;
+        for (int it = t; it < nv * G; it += nt) {
+            int e = it / G, g2 = it - e * G;
+            fill_rows2_w20((const uint32_t*)(s_brd + e * BS + cfg.ids_off) + 5 * g2, i_board + e * OB + g2 * 56);
+        }
+    } else {
+        for (int it = t; it < nv * H; it += nt) {
+            int e = it / H, row = it - e * H;
+            fill_board_row<WT>(cfg, (const uint32_t*)(s_brd + e * BS + cfg.ids_off), i_board, e * OB, row);
+        }
+    }
+    const uint32_t invQ = 65536u / (uint32_t)Q + 1u;   // it / Q for it < 4096 without a division
+    for (int it = t; it < nv * Q; it += nt) {          // queue: one piece per item, its 4 matrix rows in one 128-bit read
+        int e = (int)(((uint32_t)it * invQ) >> 16), q = it - e * Q;
+        uint64_t queue = (uint64_t)s_hot[e * 8 + 2] | ((uint64_t)s_hot[e * 8 + 3] << 32);
+        uint4 rb = *(const uint4*)(s_rowbytes + ((int)((queue >> (4 * q)) & 15u)) * 16);
+        uint32_t* qo = (uint32_t*)i_queue + e * 4 * Q + q;
+        qo[0] = rb.x; qo[Q] = rb.y; qo[2 * Q] = rb.z; qo[3 * Q] = rb.w;
+    }
+    for (int it = t; it < nv * 4; it += nt) {
+        int e = it >> 2, i = it & 3;
+        uint32_t w0 = s_hot[e * 8];
+        int hold = (w0 >> 18) & 15, hr = (w0 >> 22) & 3;
+        ((uint32_t*)i_holder)[it] = hold ? s_rowbytes[((hold - 1) * 4 + hr) * 4 + i] : 0x01010101u;
+    }
+}
+// active piece overlay + bounding-box mask (Tetris._get_obs, envs/tetris.py:566-576)
+__device__ __forceinline__ void mask_set_and_overlay(const uint32_t* boxes, int nv, const unsigned short* s_cells, uint8_t* i_board,
+                                                     uint8_t* i_mask, int OB, int Wp, int t, int nt) {
+    for (int it = t; it < nv * 4; it += nt) {
+        int e = it >> 2, i = it & 3;
+        uint32_t bx = boxes[e];
+        int n = (bx >> 16) & 15, x = bx & 255, y = (bx >> 8) & 255;
+        if (i < n) {
+            int addr = e * OB + (y + i) * Wp + x, a = addr & 3;
+            uint64_t v = (uint64_t)(0x01010101u >> (8 * (4 - n))) << (8 * a);
+            *(uint32_t*)(i_mask + addr - a) = (uint32_t)v;
+            if (a + n > 4) *(uint32_t*)(i_mask + addr - a + 4) = (uint32_t)(v >> 32);
+        }
+        if ((bx >> 20) & 1) {
+            int pc = (bx >> 24) & 7, c = (s_cells[pc * 4 + (bx >> 28)] >> (4 * i)) & 15;
+            i_board[e * OB + (y + (c >> 2)) * Wp + x + (c & 3)] = (uint8_t)(pc + 2);
+        }
+    }
+}
+// once per CTA: piece tables to shared memory; constant parts of the images (bedrock frame, empty mask)
+__device__ __forceinline__ void init_cta(int E, int W, int H, uint32_t* s_rowbytes, unsigned short* s_cells, int* s_n,
+                                         uint8_t* i_board, uint8_t* i_mask, int tid, int T) {
+    const int Wp = W + 2 * P, OB = (H + P) * Wp;
+    for (int i = tid; i < 112; i += T) s_rowbytes[i] = (&c_rowbytes[0][0][0])[i];
+    for (int i = tid; i < 28; i += T) s_cells[i] = (&c_cells[0][0])[i];
+    for (int i = tid; i < 7; i += T) s_n[i] = c_n[i];
+    for (int i = tid; i < OB; i += T) {  // env 0's template ...
+        int r = i / Wp, c = i - r * Wp;
+        i_board[i] = (r < H && c >= P && c < P + W) ? 0 : 1;
+    }
+    for (int i = tid; i < (E * OB + 3) / 4; i += T) ((uint32_t*)i_mask)[i] = 0;
+    __syncthreads();
+    if ((OB & 3) == 0) {
+        for (int e = 1; e < E; e++)      // ... replicated to the other env slots
+            for (int i = tid; i < OB / 4; i += T) ((uint32_t*)(i_board + e * OB))[i] = ((const uint32_t*)i_board)[i];
+    } else {
+        for (int e = 1; e < E; e++)
+            for (int i = tid; i < OB; i += T) i_board[e * OB + i] = i_board[i];
+    }
+}
+
 template <int WT, int HT, class COLT>
 __global__ void __launch_bounds__(256) k_step(const __grid_constant__ StepParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -179,7 +348,7 @@ __global__ void __launch_bounds__(256) k_step(const __grid_constant__ StepParams
     const int E = p.E, T = blockDim.x, tid = threadIdx.x;
     const int W = WT ? WT : cfg.W, H = HT ? HT : cfg.H;
     const int Wp = W + 2 * P, Hp = H + P;
-    const int OB = Hp * Wp, OQ = cfg.OQ, BS = cfg.board_stride, RS = cfg.rng_stride, Q = cfg.Q;
+    const int OB = Hp * Wp, OQ = cfg.OQ, BS = cfg.board_stride, RS = cfg.rng_stride;
 
     uint8_t* i_board = smem + p.off_iboard;
     uint8_t* i_mask = smem + p.off_imask;
@@ -193,23 +362,12 @@ __global__ void __launch_bounds__(256) k_step(const __grid_constant__ StepParams
     Tabs tb;
     tb.cells = s_cells; tb.rowbytes = s_rowbytes; tb.n = s_n;
 
-    // once per CTA: piece tables to shared memory; constant parts of the images (bedrock frame, empty mask)
-    for (int i = tid; i < 112; i += T) s_rowbytes[i] = (&c_rowbytes[0][0][0])[i];
-    for (int i = tid; i < 28; i += T) s_cells[i] = (&c_cells[0][0])[i];
-    for (int i = tid; i < 7; i += T) s_n[i] = c_n[i];
     for (int i = tid; i < 2 * E; i += T) s_box2[i] = 0;
-    for (int i = tid; i < OB; i += T) {  // env 0's template ...
-        int r = i / Wp, c = i - r * Wp;
-        i_board[i] = (r < H && c >= P && c < P + W) ? 0 : 1;
-    }
-    for (int i = tid; i < (E * OB + 3) / 4; i += T) ((uint32_t*)i_mask)[i] = 0;
     if (tid == 0) { mbar_init(bar, 1); mbar_init(bar + 1, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-    __syncthreads();
-    for (int e = 1; e < E; e++)          // ... replicated to the other env slots
-        for (int i = tid; i < OB; i += T) i_board[e * OB + i] = i_board[i];
+    init_cta(E, W, H, s_rowbytes, s_cells, s_n, i_board, i_mask, tid, T);
 
     const int64_t ntiles = (p.n + E - 1) / E;
-    double st_ep = 0, st_ret = 0, st_len = 0, st_lines = 0;
+    TileStats st = {0, 0, 0, 0};
     const bool want_obs = p.o_board != nullptr;
     int nv_prev = 0;
 
@@ -236,76 +394,13 @@ __global__ void __launch_bounds__(256) k_step(const __grid_constant__ StepParams
         const uint32_t* s_box_prev = s_box2 + (b ^ 1) * E;
 
         // (C) game logic, one thread per env, on the state that was prefetched into stage b
-        StepResult res;
-        res.dirty = 0;
-        bool rng_dirty = false;
+        uint32_t dirty = 0;
         if (tid < nv) {
             const int64_t e = base + tid;
             int action = 0;
             if (p.mode != 1) action = p.actions[e];
             mbar_wait(bar + b, (uint32_t)((k >> 1) & 1));
-            Hot h;
-            uint32_t* rec = (uint32_t*)(s_brd + tid * BS);
-            hot_load(h, s_hot + tid * 8);
-            Rng g;
-            g.rec = (uint32_t*)(s_rng + tid * RS);
-            g.seq = p.seq ? p.seq + e * cfg.seq_len : nullptr;
-            g.gid = cfg.env_id_offset + (uint64_t)e;
-            g.dirty = false;
-            res.reward = 0; res.lines = 0; res.terminated = 0;
-            bool need_reset = false;
-            if (p.mode == 1) {
-                need_reset = (!p.reset_mask || p.reset_mask[e]);
-                if (need_reset && p.seeds && cfg.rng_mode == 0) { ((uint64_t*)g.rec)[0] = p.seeds[e]; g.rec[2] = 0; g.dirty = true; }
-            } else if (cfg.autoreset == 1 && h.pending) {
-                need_reset = true;  // gymnasium NEXT_STEP autoreset: the action is ignored, the env is reset
-            } else {
-                if (p.mode == 2) {
-                    // GroupedActionsObservations.step (wrappers/grouped.py:209-269)
-                    bool ok = (unsigned)action < (unsigned)cfg.A && p.legal[e * cfg.A + action] != 0;
-                    p.fill_high[e] = (uint8_t)(!ok && cfg.terminate_on_illegal);
-                    if (ok) {
-                        h.x = (action >> 2) + P - tb.n[h.p] / 2;   // y untouched (wrappers/grouped.py:244-254)
-                        h.r = (h.r + (action & 3)) & 3;
-                        env_step<COLT>(cfg, tb, h, rec, g, cfg.act_hard, res);
-                    } else if (cfg.terminate_on_illegal) {
-                        res.reward = cfg.r_invalid; res.terminated = 1;   // env untouched, episode ends
-                    } else {
-                        env_step<COLT>(cfg, tb, h, rec, g, cfg.act_noop, res);
-                        res.reward = cfg.r_invalid;
-                    }
-                } else {
-                    env_step<COLT>(cfg, tb, h, rec, g, action, res);
-                }
-                h.ep_ret += (float)res.reward; h.ep_len += 1; h.ep_lines += res.lines;
-                if (res.terminated) {
-                    st_ep += 1; st_ret += h.ep_ret; st_len += h.ep_len; st_lines += h.ep_lines;
-                    h.ep_ret = 0; h.ep_len = 0; h.ep_lines = 0;
-                    if (cfg.autoreset == 1) h.pending = 1;
-                    else if (cfg.autoreset == 2) need_reset = true;
-                }
-            }
-            if (need_reset) { env_reset<COLT>(cfg, h, rec, g); res.dirty = 1; }
-            if (p.mode == 2 && need_reset) p.fill_high[e] = 0;
-            rng_dirty = g.dirty;
-            hot_store(h, s_hot + tid * 8);
-            if (p.mode != 1) {
-                p.reward[e] = (float)res.reward;
-                p.terminated[e] = (uint8_t)res.terminated;
-                p.truncated[e] = 0;
-                p.lines[e] = res.lines;
-            }
-            COLT Bact = bmask<COLT>((const COLT*)rec, W, tb.cells[h.p * 4 + h.r], h.x);
-            const uint32_t show = !((Bact >> h.y) & 1);
-            s_box[tid] = (uint32_t)h.x | ((uint32_t)h.y << 8) | ((uint32_t)tb.n[h.p] << 16) | (show << 20) |
-                         ((uint32_t)h.p << 24) | ((uint32_t)h.r << 28);
-            if (p.mode == 2 && p.info_board) {
-                // info["board"]: FeatureVectorObservation of the real observation (wrappers/grouped.py:260-264)
-                uint8_t f[32];
-                int ln;
-                placement_features<COLT>(cfg, (const COLT*)rec, tb.cells[h.p * 4 + h.r], h.x, h.y, show != 0, false, COLT(3), f, ln);
-                for (int i = 0; i < cfg.F; i++) p.info_board[e * cfg.F + i] = f[i];
-            }
+            dirty = logic_one_env<COLT>(p, tb, e, tid, action, s_hot, s_brd, s_rng, s_box, st);
         }
         // the previous tile's stores must have finished reading shared memory (images + the other state stage)
         bulk_wait_read();
@@ -315,65 +410,12 @@ __global__ void __launch_bounds__(256) k_step(const __grid_constant__ StepParams
         if (tid == 0 && tile + gridDim.x < ntiles) issue_load(tile + gridDim.x, b ^ 1);
 
         if (want_obs) {
-            // (D) erase last tile's bounding boxes; observation images: board rows, queue, holder (all threads)
-            for (int it = tid; it < nv_prev * 4; it += T) {
-                int e = it >> 2, i = it & 3;
-                uint32_t bx = s_box_prev[e];
-                int n = (bx >> 16) & 15;
-                if (i < n) {
-                    int addr = e * OB + (((bx >> 8) & 255) + i) * Wp + (bx & 255), a = addr & 3;
-                    *(uint32_t*)(i_mask + addr - a) = 0;
-                    if (a + n > 4) *(uint32_t*)(i_mask + addr - a + 4) = 0;
-                }
-            }
-            if (WT == 10 && (HT % 4) == 0) {
-                constexpr int G = HT ? HT / 4 : 1;
-                for (int it = tid; it < nv * G; it += T) {
-                    int e = it / G, g4 = it - e * G;
-                    fill_rows4_w10((const uint32_t*)(s_brd + e * BS + 40) + 5 * g4, i_board + e * OB + g4 * 72);
-                }
-            } else if (WT == 20 && (HT % 2) == 0) {
-                constexpr int G = HT ? HT / 2 : 1;
-                for (int it = tid; it < nv * G; it += T) {
-                    int e = it / G, g2 = it - e * G;
-                    fill_rows2_w20((const uint32_t*)(s_brd + e * BS + cfg.ids_off) + 5 * g2, i_board + e * OB + g2 * 56);
-                }
-            } else {
-                for (int it = tid; it < nv * H; it += T) {
-                    int e = it / H, row = it - e * H;
-                    fill_board_row<WT>(cfg, (const uint32_t*)(s_brd + e * BS + cfg.ids_off), i_board, e * OB, row);
-                }
-            }
-            for (int it = tid; it < nv * Q; it += T) {   // queue: one piece per item, its 4 matrix rows in one 128-bit read
-                int e = it / Q, q = it - e * Q;
-                uint64_t queue = (uint64_t)s_hot[e * 8 + 2] | ((uint64_t)s_hot[e * 8 + 3] << 32);
-                uint4 rb = *(const uint4*)(s_rowbytes + ((int)((queue >> (4 * q)) & 15u)) * 16);
-                uint32_t* qo = (uint32_t*)i_queue + e * 4 * Q + q;
-                qo[0] = rb.x; qo[Q] = rb.y; qo[2 * Q] = rb.z; qo[3 * Q] = rb.w;
-            }
-            for (int it = tid; it < nv * 4; it += T) {
-                int e = it >> 2, i = it & 3;
-                uint32_t w0 = s_hot[e * 8];
-                int hold = (w0 >> 18) & 15, hr = (w0 >> 22) & 3;
-                ((uint32_t*)i_holder)[it] = hold ? s_rowbytes[((hold - 1) * 4 + hr) * 4 + i] : 0x01010101u;
-            }
+            // (D) erase last tile's bounding boxes; board rows, queue, holder images (all threads)
+            mask_clear_boxes(s_box_prev, nv_prev, i_mask, OB, Wp, tid, T);
+            fill_images<WT, HT>(cfg, nv, s_hot, s_brd, s_rowbytes, i_board, i_holder, i_queue, tid, T);
             __syncthreads();
-            // (E) active piece overlay + bounding-box mask (Tetris._get_obs, envs/tetris.py:566-576)
-            for (int it = tid; it < nv * 4; it += T) {
-                int e = it >> 2, i = it & 3;
-                uint32_t bx = s_box[e];
-                int n = (bx >> 16) & 15, x = bx & 255, y = (bx >> 8) & 255;
-                if (i < n) {
-                    int addr = e * OB + (y + i) * Wp + x, a = addr & 3;
-                    uint64_t v = (uint64_t)(0x01010101u >> (8 * (4 - n))) << (8 * a);
-                    *(uint32_t*)(i_mask + addr - a) = (uint32_t)v;
-                    if (a + n > 4) *(uint32_t*)(i_mask + addr - a + 4) = (uint32_t)(v >> 32);
-                }
-                if ((bx >> 20) & 1) {
-                    int pc = (bx >> 24) & 7, c = (s_cells[pc * 4 + (bx >> 28)] >> (4 * i)) & 15;
-                    i_board[e * OB + (y + (c >> 2)) * Wp + x + (c & 3)] = (uint8_t)(pc + 2);
-                }
-            }
+            // (E) active piece overlay + bounding-box mask
+            mask_set_and_overlay(s_box, nv, s_cells, i_board, i_mask, OB, Wp, tid, T);
         }
         // (F) stores
         fence_async_smem();
@@ -389,8 +431,8 @@ __global__ void __launch_bounds__(256) k_step(const __grid_constant__ StepParams
         }
         if (leader) bulk_s2g(p.hot + base * 32, s_hot, (uint32_t)(nv * 32));
         if (tid < nv) {
-            if (res.dirty) bulk_s2g(p.board + (base + tid) * BS, s_brd + tid * BS, (uint32_t)BS);
-            if (rng_dirty) bulk_s2g(p.rng + (base + tid) * RS, s_rng + tid * RS, (uint32_t)RS);
+            if (dirty & 1) bulk_s2g(p.board + (base + tid) * BS, s_brd + tid * BS, (uint32_t)BS);
+            if (dirty & 2) bulk_s2g(p.rng + (base + tid) * RS, s_rng + tid * RS, (uint32_t)RS);
         }
         bulk_commit();
         nv_prev = want_obs ? nv : 0;
@@ -398,15 +440,147 @@ __global__ void __launch_bounds__(256) k_step(const __grid_constant__ StepParams
     bulk_wait_all();
     if (p.stats) {
         for (int o = 16; o > 0; o >>= 1) {
-            st_ep += __shfl_xor_sync(0xffffffffu, st_ep, o);
-            st_ret += __shfl_xor_sync(0xffffffffu, st_ret, o);
-            st_len += __shfl_xor_sync(0xffffffffu, st_len, o);
-            st_lines += __shfl_xor_sync(0xffffffffu, st_lines, o);
+            st.ep += __shfl_xor_sync(0xffffffffu, st.ep, o);
+            st.ret += __shfl_xor_sync(0xffffffffu, st.ret, o);
+            st.len += __shfl_xor_sync(0xffffffffu, st.len, o);
+            st.lines += __shfl_xor_sync(0xffffffffu, st.lines, o);
         }
-        if ((tid & 31) == 0 && st_ep > 0) {
-            atomicAdd(p.stats + 0, st_ep); atomicAdd(p.stats + 1, st_ret);
-            atomicAdd(p.stats + 2, st_len); atomicAdd(p.stats + 3, st_lines);
+        if ((tid & 31) == 0 && st.ep > 0) {
+            atomicAdd(p.stats + 0, st.ep); atomicAdd(p.stats + 1, st.ret);
+            atomicAdd(p.stats + 2, st.len); atomicAdd(p.stats + 3, st.lines);
         }
+    }
+}
+
+// ---- warp-specialised variant: warp 0 runs the game logic one tile ahead, the other warps produce and
+// store the observation images.  Three state stages (hot + board + rng records of 32 envs each) are kept
+// in flight by TMA; the roles meet on named barriers (ready[stage]) and mbarriers (full[stage]). ----------
+__device__ __forceinline__ void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void named_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+template <int WT, int HT, class COLT>
+__global__ void __launch_bounds__(128) k_step_ws(const __grid_constant__ StepParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const DevCfg& cfg = p.cfg;
+    constexpr int E = 32, NS = 3;
+    const int T = blockDim.x, tid = threadIdx.x;
+    const int FT = T - 32, ft = tid - 32;           // fill threads
+    const int W = WT ? WT : cfg.W, H = HT ? HT : cfg.H;
+    const int Wp = W + 2 * P, Hp = H + P;
+    const int OB = Hp * Wp, OQ = cfg.OQ, BS = cfg.board_stride, RS = cfg.rng_stride;
+
+    uint8_t* i_board = smem + p.off_iboard;
+    uint8_t* i_mask = smem + p.off_imask;
+    uint8_t* i_holder = smem + p.off_iholder;
+    uint8_t* i_queue = smem + p.off_iqueue;
+    uint64_t* bar = (uint64_t*)(smem + p.off_bar);     // full[NS]
+    uint32_t* s_boxes = (uint32_t*)(smem + p.off_box); // [NS][E] boxes, [NS][E] dirty flags, [E] boxes of the previous tile (fill-private)
+    uint32_t* s_flags = s_boxes + NS * E;
+    uint32_t* s_boxprev = s_flags + NS * E;
+    uint32_t* s_rowbytes = (uint32_t*)(smem + p.off_tab);
+    unsigned short* s_cells = (unsigned short*)(s_rowbytes + 112);
+    int* s_n = (int*)(s_rowbytes + 112 + 16);
+    Tabs tb;
+    tb.cells = s_cells; tb.rowbytes = s_rowbytes; tb.n = s_n;
+
+    for (int i = tid; i < (2 * NS + 1) * E; i += T) s_boxes[i] = 0;
+    if (tid == 0) {
+        for (int s = 0; s < NS; s++) mbar_init(bar + s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    init_cta(E, W, H, s_rowbytes, s_cells, s_n, i_board, i_mask, tid, T);
+
+    const int64_t ntiles = (p.n + E - 1) / E;
+    const bool want_obs = p.o_board != nullptr;
+    auto issue_load = [&](int64_t tile, int s) {
+        const int64_t base = tile * E;
+        const int nv = (int)min((int64_t)E, p.n - base);
+        mbar_expect_tx(bar + s, (uint32_t)(nv * (32 + BS + RS)));
+        bulk_g2s(smem + p.off_hot + s * p.st_hot, p.hot + base * 32, (uint32_t)(nv * 32), bar + s);
+        bulk_g2s(smem + p.off_brd + s * p.st_brd, p.board + base * BS, (uint32_t)(nv * BS), bar + s);
+        bulk_g2s(smem + p.off_rng + s * p.st_rng, p.rng + base * RS, (uint32_t)(nv * RS), bar + s);
+    };
+    if (tid == 32) {   // the fill leader owns all TMA traffic
+        if ((int64_t)blockIdx.x < ntiles) issue_load(blockIdx.x, 0);
+        if ((int64_t)blockIdx.x + gridDim.x < ntiles) issue_load((int64_t)blockIdx.x + gridDim.x, 1);
+    }
+    __syncthreads();
+
+    if (tid < 32) {
+        // ===== logic warp =====
+        TileStats st = {0, 0, 0, 0};
+        int k = 0;
+        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, k++) {
+            const int s = k % NS;
+            const int64_t base = tile * E;
+            const int nv = (int)min((int64_t)E, p.n - base);
+            int action = 0;
+            if (p.mode != 1 && tid < nv) action = p.actions[base + tid];
+            mbar_wait(bar + s, (uint32_t)((k / NS) & 1));
+            uint32_t dirty = 0;
+            if (tid < nv)
+                dirty = logic_one_env<COLT>(p, tb, base + tid, tid, action, (uint32_t*)(smem + p.off_hot + s * p.st_hot),
+                                            smem + p.off_brd + s * p.st_brd, smem + p.off_rng + s * p.st_rng, s_boxes + s * E, st);
+            s_flags[s * E + tid] = dirty;
+            __syncwarp();
+            named_arrive(1 + s, T);   // ready[s]: the fill warps may consume stage s
+        }
+        if (p.stats) {
+            for (int o = 16; o > 0; o >>= 1) {
+                st.ep += __shfl_xor_sync(0xffffffffu, st.ep, o);
+                st.ret += __shfl_xor_sync(0xffffffffu, st.ret, o);
+                st.len += __shfl_xor_sync(0xffffffffu, st.len, o);
+                st.lines += __shfl_xor_sync(0xffffffffu, st.lines, o);
+            }
+            if (tid == 0 && st.ep > 0) {
+                atomicAdd(p.stats + 0, st.ep); atomicAdd(p.stats + 1, st.ret);
+                atomicAdd(p.stats + 2, st.len); atomicAdd(p.stats + 3, st.lines);
+            }
+        }
+    } else {
+        // ===== image / store warps =====
+        const bool leader = (ft == 0);
+        int nv_prev = 0, k = 0;
+        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, k++) {
+            const int s = k % NS;
+            const int64_t base = tile * E;
+            const int nv = (int)min((int64_t)E, p.n - base);
+            uint32_t* s_hot = (uint32_t*)(smem + p.off_hot + s * p.st_hot);
+            uint8_t* s_brd = smem + p.off_brd + s * p.st_brd;
+            uint8_t* s_rng = smem + p.off_rng + s * p.st_rng;
+            named_sync(1 + s, T);                       // logic of this tile is done, stage s is final
+            mbar_wait(bar + s, (uint32_t)((k / NS) & 1));   // (already complete) acquire the TMA writes
+            bulk_wait_read();                           // stores of the previous tile have left shared memory
+            named_sync(4, FT);
+            // stage (k+2)%NS == (k-1)%NS is free again: prefetch two tiles ahead
+            if (leader && tile + 2 * (int64_t)gridDim.x < ntiles) issue_load(tile + 2 * (int64_t)gridDim.x, (k + 2) % NS);
+            if (want_obs) {
+                mask_clear_boxes(s_boxprev, nv_prev, i_mask, OB, Wp, ft, FT);
+                fill_images<WT, HT>(cfg, nv, s_hot, s_brd, s_rowbytes, i_board, i_holder, i_queue, ft, FT);
+                named_sync(4, FT);
+                mask_set_and_overlay(s_boxes + s * E, nv, s_cells, i_board, i_mask, OB, Wp, ft, FT);
+                for (int i = ft; i < nv; i += FT) s_boxprev[i] = s_boxes[s * E + i];
+            }
+            fence_async_smem();
+            named_sync(4, FT);
+            if (want_obs) {
+                tile_store(p.o_board + base * OB, i_board, (uint32_t)(nv * OB), leader, ft, FT);
+                tile_store(p.o_mask + base * OB, i_mask, (uint32_t)(nv * OB), leader, ft, FT);
+                if (leader) {
+                    bulk_s2g(p.o_holder + base * 16, i_holder, (uint32_t)(nv * 16));
+                    bulk_s2g(p.o_queue + base * OQ, i_queue, (uint32_t)(nv * OQ));
+                }
+            }
+            if (leader) bulk_s2g(p.hot + base * 32, s_hot, (uint32_t)(nv * 32));
+            for (int i = ft; i < nv; i += FT) {
+                uint32_t d = s_flags[s * E + i];
+                if (d & 1) bulk_s2g(p.board + (base + i) * BS, s_brd + i * BS, (uint32_t)BS);
+                if (d & 2) bulk_s2g(p.rng + (base + i) * RS, s_rng + i * RS, (uint32_t)RS);
+            }
+            bulk_commit();
+            nv_prev = want_obs ? nv : 0;
+        }
+        bulk_wait_all();
     }
 }
 
