@@ -188,6 +188,9 @@ int tg_grouped_step(tg_env *env, tg_state st, int64_t n, const int32_t *d_action
 int tg_rollout(tg_env *env, tg_state st, int64_t n, const int32_t weights[4], int32_t k_steps,
                tg_stats *d_stats, void *stream);
 
+/* test hook: i32[n] device buffer receiving the placement chosen at the last step of tg_rollout (NULL = off) */
+int tg_debug_set_rollout_trace(tg_env *env, int32_t *d_last_action);
+
 /* ---- state access (replaces Tetris.get_state/set_state, envs/tetris.py:681-708, and the direct
  * env.unwrapped.board/x/y/active_tetromino pokes of the reference tests) ---------------------- */
 /* canonical, unpacked views: board u8[n][H_pad][W_pad] (locked cells, bedrock = 1);

@@ -448,8 +448,10 @@ void orc_features(const orc_env *e, uint8_t *board, const uint8_t *mask, uint8_t
 }
 
 /* ---- GroupedActionsObservations.observation (wrappers/grouped.py:124-207) ----------------- */
-/* boards: NULL or u8[4W][Hp][Wp]; feats: NULL or u8[4W][W+3]; legal: u8[4W] */
-void orc_grouped_observe(const orc_env *e, uint8_t *boards, uint8_t *feats, uint8_t *legal) {
+/* boards: NULL or u8[4W][Hp][Wp]; feats: NULL or u8[4W][W+3]; legal: u8[4W];
+ * lines: NULL or i32[4W] = rows cleared by a regular placement, -1 for a game-over placement, -2 illegal
+ * (not part of the reference observation; used by the heuristic-rollout parity test) */
+void orc_grouped_observe_ex(const orc_env *e, uint8_t *boards, uint8_t *feats, uint8_t *legal, int32_t *lines) {
     int Wp = e->Wp, Hp = e->Hp, W = e->W;
     size_t bsz = (size_t)Hp * Wp;
     uint8_t *tmp = (uint8_t *)malloc(bsz), *zeros = (uint8_t *)calloc(bsz, 1);
@@ -465,11 +467,14 @@ void orc_grouped_observe(const orc_env *e, uint8_t *boards, uint8_t *feats, uint
             if (collision_with_frame(e, e->board, &t, x, y)) {
                 legal[a] = 0;
                 memset(tmp, 1, bsz);
+                if (lines) lines[a] = -2;
             } else if (collision(e, e->board, &t, x, y)) {
                 memset(tmp, 0, bsz);
+                if (lines) lines[a] = -1;
             } else {
                 project(e, e->board, &t, x, y, tmp);
-                clear_filled_rows(e, tmp);
+                int nl = clear_filled_rows(e, tmp);
+                if (lines) lines[a] = nl;
             }
             if (boards) memcpy(boards + (size_t)a * bsz, tmp, bsz);
             if (feats) orc_features(e, tmp, zeros, feats + (size_t)a * (W + 3));
@@ -478,6 +483,10 @@ void orc_grouped_observe(const orc_env *e, uint8_t *boards, uint8_t *feats, uint
     }
     free(tmp);
     free(zeros);
+}
+
+void orc_grouped_observe(const orc_env *e, uint8_t *boards, uint8_t *feats, uint8_t *legal) {
+    orc_grouped_observe_ex(e, boards, feats, legal, NULL);
 }
 
 /* GroupedActionsObservations.step (wrappers/grouped.py:209-269).

@@ -38,7 +38,7 @@ def lib():
             "orc_destroy orc_set_sequence orc_seed_numpy orc_get_obs orc_reset orc_features "
             "orc_grouped_observe orc_rgb orc_get_board orc_set_board orc_get_scalars "
             "orc_get_active_matrix orc_get_held_matrix orc_set_active orc_set_flags orc_set_holder "
-            "orc_set_queue orc_vec_step orc_vec_grouped_step orc_rnd_stream"
+            "orc_set_queue orc_vec_step orc_vec_grouped_step orc_rnd_stream orc_grouped_observe_ex"
         ).split():
             getattr(L, name).restype = None
         L.orc_step.restype = C.c_int
@@ -149,6 +149,14 @@ class OracleEnv:
         b = np.empty((A, self.Hp, self.Wp), np.uint8) if boards else None
         lib().orc_grouped_observe(self.h, _p(b), _p(f), _p(self.legal))
         return f, b, self.legal.copy()
+
+    def grouped_observe_lines(self):
+        """(features u8[A, W+3], legal u8[A], lines i32[A]) -- lines: rows cleared, -1 game-over placement, -2 illegal."""
+        A = 4 * self.W
+        f = np.empty((A, self.W + 3), np.uint8)
+        ln = np.empty(A, np.int32)
+        lib().orc_grouped_observe_ex(self.h, None, _p(f), _p(self.legal), _p(ln))
+        return f, self.legal.copy(), ln
 
     def grouped_step(self, action, terminate_on_illegal=True):
         r, t, l = C.c_double(), C.c_int(), C.c_int()

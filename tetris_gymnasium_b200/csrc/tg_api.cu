@@ -12,6 +12,7 @@
 #include "tg_device.cuh"
 #include "tg_step.cuh"
 #include "tg_aux.cuh"
+#include "tg_rollout.cuh"
 
 using namespace tg;
 
@@ -26,6 +27,7 @@ struct tg_env {
     int threads_per_env;  // CTA threads = tile * threads_per_env (logic uses one thread per env, image fill uses all)
     int warp_specialized; // 1: k_step_ws (logic warp runs a tile ahead of the image warps)
     int fill_warps;       // image/store warps per CTA of k_step_ws
+    void* rollout_last_action;
     std::string err;
     // tg_step_host staging
     cudaStream_t hs[3];
@@ -128,6 +130,7 @@ extern "C" int tg_create(const tg_config* cfg, int device, tg_env** out) {
     env->cfg = *cfg;
     env->device = device;
     env->hs_init = false;
+    env->rollout_last_action = nullptr;
     memset(env->stage, 0, sizeof env->stage);
     memset(env->stage_bytes, 0, sizeof env->stage_bytes);
     cudaError_t e1 = cudaSetDevice(device);

@@ -388,9 +388,10 @@ __device__ __forceinline__ void col_features(COLT col, int H, int& height, int& 
 // Features of (cols | optional piece cells), after deleting `full` rows and zeroing `rowzero` rows.
 // Q1: the reference zeroes padded rows 0 (mask all zero) or 0-1 (mask has a 1) through
 // integer fancy indexing, it does NOT mask the active piece (wrappers/observation.py:252).
+struct FeatSum { int sum_h, max_h, holes, bump, lines; };
 template <class COLT>
-__device__ __forceinline__ void placement_features(const DevCfg& cfg, const COLT* cols, uint32_t cells, int x, int y,
-                                                   bool place, bool do_clear, COLT rowzero, uint8_t* out, int& lines_out) {
+__device__ __forceinline__ FeatSum placement_eval(const DevCfg& cfg, const COLT* cols, uint32_t cells, int x, int y,
+                                                  bool place, bool do_clear, COLT rowzero, uint8_t* out) {
     const int W = cfg.W, H = cfg.H;
     int crow[4], ccol[4];
 #pragma unroll
@@ -410,8 +411,9 @@ __device__ __forceinline__ void placement_features(const DevCfg& cfg, const COLT
         }
         full &= (COLT(1) << H) - 1;
     }
-    lines_out = popc_t<COLT>(full);
-    int prev = 0, maxh = 0, holes = 0, bump = 0;
+    FeatSum fs;
+    fs.lines = popc_t<COLT>(full);
+    int prev = 0, maxh = 0, holes = 0, bump = 0, sumh = 0;
     for (int c = 0; c < W; c++) {
         COLT v = cols[c];
 #pragma unroll
@@ -426,15 +428,47 @@ __device__ __forceinline__ void placement_features(const DevCfg& cfg, const COLT
         v &= ~rowzero;
         int hgt, hol;
         col_features<COLT>(v, H, hgt, hol);
-        out[c] = (uint8_t)hgt;
+        if (out) out[c] = (uint8_t)hgt;
         holes += hol;
+        sumh += hgt;
         maxh = max(maxh, hgt);
         if (c > 0) bump += abs(hgt - prev);
         prev = hgt;
     }
-    out[W] = (uint8_t)maxh;
-    out[W + 1] = (uint8_t)holes;  // uint8 wrap (wrappers/observation.py:277)
-    out[W + 2] = (uint8_t)bump;
+    if (out) {
+        out[W] = (uint8_t)maxh;
+        out[W + 1] = (uint8_t)holes;  // uint8 wrap (wrappers/observation.py:277)
+        out[W + 2] = (uint8_t)bump;
+    }
+    fs.sum_h = sumh; fs.max_h = maxh; fs.holes = holes; fs.bump = bump;
+    return fs;
+}
+template <class COLT>
+__device__ __forceinline__ void placement_features(const DevCfg& cfg, const COLT* cols, uint32_t cells, int x, int y,
+                                                   bool place, bool do_clear, COLT rowzero, uint8_t* out, int& lines_out) {
+    lines_out = placement_eval<COLT>(cfg, cols, cells, x, y, place, do_clear, rowzero, out).lines;
+}
+
+// One placement of GroupedActionsObservations.observation (wrappers/grouped.py:148-181).
+struct Placement { int x, y, rot, kind; };  // kind: 0 regular, 1 illegal (frame), 2 game over
+template <class COLT>
+__device__ __forceinline__ Placement eval_placement(const DevCfg& cfg, const Tabs& tb, const COLT* cols, int piece, int rot0, int a, COLT& Bout) {
+    Placement pl;
+    int xb = a >> 2, rr = a & 3;
+    pl.rot = (rot0 + rr) & 3;              // cumulative rot90 presses (wrappers/grouped.py:153-154)
+    pl.x = xb + P - tb.n[piece] / 2;        // wrappers/grouped.py:157-158
+    uint32_t cells = tb.cells[piece * 4 + pl.rot];
+    COLT B = bmask<COLT>(cols, cfg.W, cells, pl.x);
+    pl.y = ctz_t<COLT>(B >> 1);            // while !collision(y+1): y++  from y = 0, no test at y = 0 (Q3)
+    bool frame = false;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        int c = (cells >> (4 * k)) & 15;
+        frame |= (unsigned)(pl.x + (c & 3) - P) >= (unsigned)cfg.W;
+    }
+    pl.kind = frame ? 1 : (((B >> pl.y) & 1) ? 2 : 0);
+    Bout = B;
+    return pl;
 }
 
 }  // namespace tg

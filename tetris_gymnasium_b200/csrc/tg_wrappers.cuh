@@ -24,28 +24,6 @@ __global__ void k_features(const DevCfg cfg, int64_t n, const uint8_t* hot, cons
     for (int i = 0; i < cfg.F; i++) feats[e * cfg.F + i] = f[i];
 }
 
-// One placement of GroupedActionsObservations.observation (wrappers/grouped.py:148-181).
-struct Placement { int x, y, rot, kind; };  // kind: 0 regular, 1 illegal (frame), 2 game over
-template <class COLT>
-__device__ __forceinline__ Placement eval_placement(const DevCfg& cfg, const COLT* cols, int piece, int rot0, int a, COLT& Bout) {
-    Placement pl;
-    int xb = a >> 2, rr = a & 3;
-    pl.rot = (rot0 + rr) & 3;              // cumulative rot90 presses (wrappers/grouped.py:153-154)
-    pl.x = xb + P - c_n[piece] / 2;        // wrappers/grouped.py:157-158
-    uint32_t cells = c_cells[piece][pl.rot];
-    COLT B = bmask<COLT>(cols, cfg.W, cells, pl.x);
-    pl.y = ctz_t<COLT>(B >> 1);            // while !collision(y+1): y++  from y = 0, no test at y = 0 (Q3)
-    bool frame = false;
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        int c = (cells >> (4 * k)) & 15;
-        frame |= (unsigned)(pl.x + (c & 3) - P) >= (unsigned)cfg.W;
-    }
-    pl.kind = frame ? 1 : (((B >> pl.y) & 1) ? 2 : 0);
-    Bout = B;
-    return pl;
-}
-
 // grouped observation with FeatureVectorObservation: feats u8[n][A][F], legal u8[n][A]
 template <class COLT>
 __global__ void k_grouped_feats(const DevCfg cfg, int64_t n, const uint8_t* hot, const uint8_t* board, uint8_t* feats,
@@ -77,7 +55,7 @@ __global__ void k_grouped_feats(const DevCfg cfg, int64_t n, const uint8_t* hot,
             continue;
         }
         COLT B;
-        Placement pl = eval_placement<COLT>(cfg, cols, piece, rot0, a, B);
+        Placement pl = eval_placement<COLT>(cfg, const_tabs(), cols, piece, rot0, a, B);
         s_legal[it] = pl.kind != 1;
         if (pl.kind == 1) {          // ones board, row 0 zeroed -> heights H-1
             for (int i = 0; i <= W; i++) out[i] = (uint8_t)(cfg.H - 1);
@@ -133,7 +111,7 @@ __global__ void k_grouped_boards(const DevCfg cfg, int64_t n, const uint8_t* hot
         COLT B;
         if (fill_high && fill_high[e]) fillv = (uint8_t)(cfg.H * cfg.W);
         else {
-            pl = eval_placement<COLT>(cfg, cols, piece, rot0, a, B);
+            pl = eval_placement<COLT>(cfg, const_tabs(), cols, piece, rot0, a, B);
             if (lane == 0) legal[it] = pl.kind != 1;
             if (pl.kind == 1) fillv = 1;
             else if (pl.kind == 2) fillv = 0;
@@ -337,7 +315,36 @@ extern "C" int tg_grouped_step(tg_env* env, tg_state st, int64_t n, const int32_
 
 extern "C" int tg_rollout(tg_env* env, tg_state st, int64_t n, const int32_t weights[4], int32_t k_steps, tg_stats* d_stats,
                           void* stream) {
-    (void)st; (void)n; (void)weights; (void)k_steps; (void)d_stats; (void)stream;
     if (!env) return TG_ERR_POINTER;
-    return fail(env, TG_ERR_ARG, "tg_rollout: not built yet");
+    if (n <= 0 || k_steps < 0 || !weights) return fail(env, TG_ERR_ARG, "tg_rollout: bad argument");
+    int rc = check_state(env, st); if (rc) return rc;
+    CUDA_TRY(env, cudaSetDevice(env->device));
+    const DevCfg& d = env->dev;
+    RolloutParams p;
+    memset(&p, 0, sizeof p);
+    p.cfg = d; p.n = n; p.hot = (uint8_t*)st.hot; p.board = (uint8_t*)st.board; p.rng = (uint8_t*)st.rng; p.seq = st.piece_seq;
+    for (int i = 0; i < 4; i++) p.w[i] = weights[i];
+    p.k_steps = k_steps; p.stats = (double*)d_stats;
+    p.last_action = (int32_t*)env->rollout_last_action;
+    int words = d.board_stride / 4;
+    // u32 columns: odd word stride; u64 columns: stride = 2 (mod 4) words keeps 8-byte alignment and spreads the banks
+    if (env->col64) { words += 2; while ((words & 3) != 2) words += 2; } else { words |= 1; }
+    p.rec_words = words;
+    const int T = 128;
+    size_t smem = (size_t)T * words * 4;
+    auto launch = [&](auto kern) -> int {
+        CUDA_TRY(env, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<(unsigned)((n + T - 1) / T), T, smem, (cudaStream_t)stream>>>(p);
+        CUDA_TRY(env, cudaGetLastError());
+        return TG_OK;
+    };
+    if (smem > 227 * 1024) return fail(env, TG_ERR_CONFIG, "tg_rollout: board record too large for shared memory");
+    return env->col64 ? launch(k_rollout<uint64_t>) : launch(k_rollout<uint32_t>);
+}
+
+/* test hook: device buffer (i32[n]) that receives the action chosen at the last rollout step; NULL disables */
+extern "C" int tg_debug_set_rollout_trace(tg_env* env, int32_t* d_last_action) {
+    if (!env) return TG_ERR_POINTER;
+    env->rollout_last_action = d_last_action;
+    return TG_OK;
 }

@@ -296,6 +296,22 @@ class Tetris:
             "truncated": mk((n,), torch.uint8), "lines_cleared": mk((n,), torch.int32),
         }
 
+    # ---- fused heuristic rollout (tg_rollout; BASELINE config 4) ----------------------------------------
+    def rollout(self, weights, k_steps: int, trace: bool = False):
+        """K grouped-placement steps of the integer linear policy
+        score = w0*sum(heights) + w1*lines + w2*holes + w3*bumpiness (lowest index among the legal maxima),
+        fused in one kernel launch with boards resident on chip.  State advances in place; episode statistics
+        accumulate into `episode_stats()`.  With trace=True returns the action chosen at the last step."""
+        w = (C.c_int32 * 4)(*[int(v) for v in weights])
+        last = None
+        if trace:
+            last = torch.full((self.num_envs,), -1, dtype=torch.int32, device=self.device)
+        _lib.check(self._L.tg_debug_set_rollout_trace(self._h, last.data_ptr() if last is not None else None), self._h)
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.tg_rollout(self._h, self._state(), self.num_envs, w, int(k_steps), self._stats.data_ptr(),
+                                          self._stream()), self._h)
+        return last
+
     # ---- episode statistics (RecordEpisodeStatistics-style, accumulated on device) ----------------
     def episode_stats(self, reset=False):
         s = self._stats.clone()
