@@ -171,9 +171,12 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
+    from tetris_gymnasium_b200.sharding import allreduce_episode_stats, shard_range
+
     n, K, Wm = args.envs, args.steps, args.warmup
-    env = Tetris(width=WIDTH, height=HEIGHT, gravity=True, queue_size=QUEUE, num_envs=n, device=dev,
-                 autoreset_mode="next_step", randomizer_mode="philox", env_id_offset=rank * n)
+    start, stop = shard_range(world * n, rank, world)      # weak scaling: n envs per GPU, global ids keyed by shard
+    env = Tetris(width=WIDTH, height=HEIGHT, gravity=True, queue_size=QUEUE, num_envs=stop - start, device=dev,
+                 autoreset_mode="next_step", randomizer_mode="philox", env_id_offset=start)
     env.reset(seed=42)
     g = torch.Generator(device=dev)
     g.manual_seed(42 + rank)
@@ -191,9 +194,7 @@ def main():
     ev0.record()
     for t in range(K):
         env.step(acts[Wm + t])
-    stats = env._stats
-    if world > 1:
-        dist.all_reduce(stats)      # the only collective: episode statistics (4 doubles) over NCCL
+    allreduce_episode_stats(env._stats)   # the only collective: episode statistics (4 doubles) over NCCL
     ev1.record()
     torch.cuda.synchronize()
     if world > 1:
