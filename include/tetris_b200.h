@@ -188,6 +188,22 @@ int tg_grouped_step(tg_env *env, tg_state st, int64_t n, const int32_t *d_action
 int tg_rollout(tg_env *env, tg_state st, int64_t n, const int32_t weights[4], int32_t k_steps,
                tg_stats *d_stats, void *stream);
 
+/* ---- functional env facade (envs/tetris_fn.py:276-367: reset / step on an explicit State) ----------
+ * The functional env is a different game from the NumPy env (7 actions, no holder, queue == bag, score-delta
+ * rewards).  State arrays are caller-owned and passed in AND out (aliasing allowed):
+ *   board   i8[n][H_pad][W_pad]
+ *   scalars i32[n][TG_FN_SCALARS + queue_size] = active_tetromino, rotation, x, y, queue_index, game_over,
+ *           score (float32 bits), rng_key[0], rng_key[1], then the queue
+ *   obs     i8[n][H][W] in {-1, 0, 1}   (get_observation, envs/tetris_fn.py:137-158)
+ * d_actions == NULL performs reset (scalars_in then only provides rng_key).  d_piece_seq (nullable, u8[n][seq_len])
+ * injects the bags: bag k of env e = seq[e][k*Q .. k*Q+Q); otherwise bags come from Philox(rng_key). */
+#define TG_FN_SCALARS 9
+int tg_fn_step(int32_t width, int32_t height, int32_t queue_size, int32_t gravity, int64_t n,
+               const int8_t *d_board_in, const int32_t *d_scalars_in, const int32_t *d_actions,
+               const uint8_t *d_piece_seq, int64_t seq_len,
+               int8_t *d_board_out, int32_t *d_scalars_out, int8_t *d_obs, float *d_reward,
+               uint8_t *d_terminated, int32_t *d_lines, void *stream);
+
 /* test hook: i32[n] device buffer receiving the placement chosen at the last step of tg_rollout (NULL = off) */
 int tg_debug_set_rollout_trace(tg_env *env, int32_t *d_last_action);
 

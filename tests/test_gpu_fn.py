@@ -1,0 +1,59 @@
+"""GPU parity of the functional facade (tg_fn_step through envs/tetris_fn.py) against the numpy restatement
+of the reference functional env, with injected bags."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("W,H,gravity", [(10, 20, True), (10, 20, False), (8, 12, True), (20, 40, True)])
+def test_functional_facade_vs_oracle(W, H, gravity):
+    from oracle.tetris_fn_oracle import FnOracle
+    from tetris_gymnasium_b200.envs import tetris_fn as fn
+    from tetris_gymnasium_b200.functional import TETROMINOES, EnvConfig
+
+    B, T, Q = 96, 300, 7
+    rng = np.random.default_rng(W * H)
+    seqs = np.stack([np.concatenate([rng.permutation(7) for _ in range(9)]) for _ in range(B)]).astype(np.uint8)
+    cfg = EnvConfig(width=W, height=H, padding=4, queue_size=Q, gravity_enabled=gravity)
+    keys = torch.zeros((B, 2), dtype=torch.int64)
+    keys, states, obs = fn.batched_reset(TETROMINOES, keys, config=cfg, create_queue_fn=seqs)
+    orcs = [FnOracle(W, H, Q, gravity, seq=seqs[i]) for i in range(B)]
+    want = np.stack([o.reset() for o in orcs])
+    assert obs.dtype == torch.int8 and np.array_equal(obs.cpu().numpy(), want)
+    n_over = 0
+    for t in range(T):
+        a = rng.integers(0, 7, size=B)
+        states, obs, reward, term, info = fn.batched_step(TETROMINOES, states, a, config=cfg, queue_fn=seqs)
+        res = [o.step(int(a[i])) for i, o in enumerate(orcs)]
+        assert np.array_equal(obs.cpu().numpy(), np.stack([r[0] for r in res])), t
+        assert np.array_equal(reward.cpu().numpy(), np.array([r[1] for r in res], np.float32)), t
+        assert np.array_equal(term.cpu().numpy(), np.array([r[2] for r in res])), t
+        assert np.array_equal(info["lines_cleared"].cpu().numpy(), np.array([r[3] for r in res])), t
+        n_over = int(term.sum())
+    assert np.array_equal(states.board.cpu().numpy(), np.stack([o.board for o in orcs]))
+    assert np.array_equal(states.score.cpu().numpy(), np.array([o.score for o in orcs], np.float32))
+    assert n_over > 0
+
+
+def test_functional_single_env_signature_and_philox_bags():
+    from tetris_gymnasium_b200.envs import tetris_fn as fn
+    from tetris_gymnasium_b200.functional import TETROMINOES, EnvConfig
+
+    cfg = EnvConfig(width=10, height=20, padding=4, queue_size=7)
+    key, state, obs = fn.reset(TETROMINOES, torch.tensor([0, 42]), cfg)
+    assert obs.shape == (20, 10) and sorted(state.queue[0].tolist()) == list(range(7))
+    state2, obs2, reward, terminated, info = fn.step(TETROMINOES, state, 5, cfg)
+    assert float(reward) == float(state2.score[0]) - float(state.score[0]) and "lines_cleared" in info
+    # a finished game is frozen (test_env/test_step.py:16-25)
+    over = state.replace(game_over=torch.ones_like(state.game_over))
+    s3, _, r3, t3, _ = fn.step(TETROMINOES, over, 0, cfg)
+    assert bool(t3) and float(r3) == 0.0 and torch.equal(s3.board, over.board)
+    # every refill is a permutation
+    st = state
+    seen = []
+    for _ in range(40):
+        st, _, _, term, _ = fn.step(TETROMINOES, st, 6, cfg)
+        seen.append(sorted(st.queue[0].tolist()))
+    assert all(s == list(range(7)) for s in seen)

@@ -47,7 +47,7 @@ class TgStepOut(C.Structure):
 
 EXPORTS = (
     "tg_create tg_destroy tg_get_layout tg_last_error tg_version tg_reset tg_seed_numpy tg_step tg_step_host "
-    "tg_features tg_render_rgb tg_grouped_observe tg_grouped_step tg_rollout tg_get_state tg_set_state tg_debug_set_rollout_trace"
+    "tg_features tg_render_rgb tg_grouped_observe tg_grouped_step tg_rollout tg_get_state tg_set_state tg_debug_set_rollout_trace tg_fn_step"
 ).split()
 
 _LIB = None
@@ -87,6 +87,7 @@ def load():
     L.tg_grouped_step.argtypes = [vp, TgState, i64, vp, vp, vp, vp, vp, TgObs, TgStepOut, vp, vp]
     L.tg_rollout.argtypes = [vp, TgState, i64, C.POINTER(C.c_int32), C.c_int32, vp, vp]
     L.tg_debug_set_rollout_trace.argtypes = [vp, vp]
+    L.tg_fn_step.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, i64, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, vp]
     L.tg_get_state.argtypes = [vp, TgState, i64, vp, vp, vp]
     L.tg_set_state.argtypes = [vp, TgState, i64, vp, vp, vp, vp]
     for name in EXPORTS:

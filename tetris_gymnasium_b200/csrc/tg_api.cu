@@ -13,6 +13,7 @@
 #include "tg_step.cuh"
 #include "tg_aux.cuh"
 #include "tg_rollout.cuh"
+#include "tg_fn.cuh"
 
 using namespace tg;
 
@@ -421,6 +422,37 @@ extern "C" int tg_set_state(tg_env* env, tg_state st, int64_t n, const uint8_t* 
     if (env->col64) k_set_state<uint64_t><<<(unsigned)((n + T - 1) / T), T, 0, (cudaStream_t)stream>>>(env->dev, n, (uint8_t*)st.hot, (uint8_t*)st.board, d_board, d_scalars, d_mask);
     else k_set_state<uint32_t><<<(unsigned)((n + T - 1) / T), T, 0, (cudaStream_t)stream>>>(env->dev, n, (uint8_t*)st.hot, (uint8_t*)st.board, d_board, d_scalars, d_mask);
     CUDA_TRY(env, cudaGetLastError());
+    return TG_OK;
+}
+
+// ---- functional facade ------------------------------------------------------------------------------------
+static bool g_fn_tables[64] = {false};
+extern "C" int tg_fn_step(int32_t width, int32_t height, int32_t queue_size, int32_t gravity, int64_t n,
+                          const int8_t* d_board_in, const int32_t* d_scalars_in, const int32_t* d_actions,
+                          const uint8_t* d_piece_seq, int64_t seq_len, int8_t* d_board_out, int32_t* d_scalars_out,
+                          int8_t* d_obs, float* d_reward, uint8_t* d_terminated, int32_t* d_lines, void* stream) {
+    if (width < 4 || width + 2 * TG_PADDING > 32 || height < 4 || height + TG_PADDING > 64 || queue_size < 1 || queue_size > 16)
+        return fail(nullptr, TG_ERR_CONFIG, "tg_fn_step: unsupported width/height/queue_size");
+    if (queue_size > 7 && !d_piece_seq) return fail(nullptr, TG_ERR_CONFIG, "tg_fn_step: queue_size doubles as the number of piece types (<= 7)");
+    if (n <= 0 || !d_board_in || !d_board_out || !d_scalars_in || !d_scalars_out) return fail(nullptr, TG_ERR_POINTER, "tg_fn_step: NULL pointer");
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return fail(nullptr, TG_ERR_CUDA, "tg_fn_step: no CUDA device (no CPU fallback)");
+    if (!g_fn_tables[dev & 63]) {   // piece tables for the current device (same tables as tg_create uploads)
+        tg_env tmp;
+        int rc = upload_tables(&tmp);
+        if (rc) return fail(nullptr, rc, "tg_fn_step: %s", tmp.err.c_str());
+        g_fn_tables[dev & 63] = true;
+    }
+    FnParams p;
+    memset(&p, 0, sizeof p);
+    p.W = width; p.H = height; p.Wp = width + 2 * TG_PADDING; p.Hp = height + TG_PADDING; p.Q = queue_size; p.gravity = gravity != 0;
+    p.n = n; p.board_in = d_board_in; p.board_out = d_board_out; p.sc_in = d_scalars_in; p.sc_out = d_scalars_out;
+    p.actions = d_actions; p.seq = d_piece_seq; p.seq_len = seq_len;
+    p.obs = d_obs; p.reward = d_reward; p.terminated = d_terminated; p.lines = d_lines;
+    const int T = 64;
+    k_fn_step<<<(unsigned)((n + T - 1) / T), T, 0, (cudaStream_t)stream>>>(p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(nullptr, TG_ERR_CUDA, "k_fn_step: %s", cudaGetErrorString(e));
     return TG_OK;
 }
 

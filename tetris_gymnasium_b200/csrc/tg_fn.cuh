@@ -1,0 +1,169 @@
+// tg_fn.cuh -- the functional env facade (tetris_gymnasium/envs/tetris_fn.py + functional/core.py, queue.py).
+//
+// A different game from the NumPy env: 7 actions (L0 R1 D2 CCW3 CW4 NOOP5 HARD6), no holder,
+// the queue IS the bag (a permutation of arange(queue_size)), every piece is a 4x4 matrix spawned at
+// x = W_pad//2 - 2, reward = score delta (soft drop +1, hard drop 2/cell, lines 100/300/500/800),
+// lock when gravity could not move the piece or on hard drop, game over only on a blocked spawn, and a
+// finished game is frozen.  The state is explicit and functional: (board i8[n,Hp,Wp], scalars i32[n,FN_S+Q])
+// in, new arrays out (in == out aliases are allowed).  One thread per env on byte boards in global memory;
+// the observation (H x W int8 in {-1,0,1}) is produced cooperatively.
+#pragma once
+#include "tg_device.cuh"
+
+namespace tg {
+
+// scalar columns of the functional State
+enum { FN_ACTIVE = 0, FN_ROT, FN_X, FN_Y, FN_QIDX, FN_OVER, FN_SCORE /* float bits */, FN_KEY0, FN_KEY1, FN_S };
+
+struct FnParams {
+    int W, H, Wp, Hp, Q, gravity;
+    int64_t n;
+    const int8_t* board_in; int8_t* board_out;
+    const int32_t* sc_in; int32_t* sc_out;
+    const int32_t* actions;       // NULL = reset
+    const uint8_t* seq; int64_t seq_len;   // injected bags: bag k of env e = seq[e][k*Q .. k*Q+Q) (NULL = Philox bags)
+    int8_t* obs; float* reward; uint8_t* terminated; int32_t* lines;
+};
+
+// core.collision (functional/core.py:86-100) on the 4x4 zero-padded matrix of (piece, rot)
+__device__ __forceinline__ bool fn_collision(const FnParams& p, const int8_t* b, uint32_t cells, int x, int y) {
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        int c = (cells >> (4 * k)) & 15;
+        if (b[(y + (c >> 2)) * p.Wp + x + (c & 3)] > 0) return true;
+    }
+    return false;
+}
+
+// queue.create_bag_queue (functional/queue.py:20-35): a permutation of arange(Q).  The reference draws it with
+// jax.random.permutation (threefry); ours comes from Philox(key) or from the injected stream -- the facade's
+// piece sequences are not JAX-bit-compatible (parity unpinned for key-derived sequences).
+__device__ __forceinline__ void fn_new_bag(const FnParams& p, int64_t e, int32_t* sc) {
+    int32_t* q = sc + FN_S;
+    uint32_t bagno = (uint32_t)sc[FN_KEY1];
+    if (p.seq) {
+        for (int i = 0; i < p.Q; i++) q[i] = p.seq[e * p.seq_len + ((int64_t)bagno * p.Q + i) % p.seq_len];
+    } else {
+        for (int i = 0; i < p.Q; i++) q[i] = i;
+        for (int i = p.Q - 1; i >= 1; i--) {
+            uint32_t c[4] = {bagno, (uint32_t)i, (uint32_t)e, (uint32_t)(e >> 32)};
+            philox4x32_10(c, (uint32_t)sc[FN_KEY0], 0x7e7215u);
+            int j = (int)__umulhi(c[0], (uint32_t)(i + 1));
+            int t = q[i]; q[i] = q[j]; q[j] = t;
+        }
+    }
+    sc[FN_KEY1] = (int32_t)(bagno + 1);
+}
+
+__global__ void k_fn_step(const FnParams p) {
+    const int tid = threadIdx.x, T = blockDim.x;
+    const int64_t base = (int64_t)blockIdx.x * T;
+    const int nv = (int)min((int64_t)T, p.n - base);
+    const int OB = p.Hp * p.Wp, NS = FN_S + p.Q;
+    // 1. new_board = board (functional update); skipped when the caller aliases in and out
+    if (p.board_in != p.board_out) {
+        const int8_t* src = p.board_in + base * OB;
+        int8_t* dst = p.board_out + base * OB;
+        size_t bytes = (size_t)nv * OB;
+        if ((bytes & 3) == 0 && (((uintptr_t)src | (uintptr_t)dst) & 3) == 0)
+            for (size_t i = tid; i < bytes / 4; i += T) ((uint32_t*)dst)[i] = ((const uint32_t*)src)[i];
+        else
+            for (size_t i = tid; i < bytes; i += T) dst[i] = src[i];
+    }
+    __syncthreads();
+    if (tid < nv) {
+        const int64_t e = base + tid;
+        int8_t* b = p.board_out + e * OB;
+        int32_t sc[FN_S + 16];
+        for (int i = 0; i < NS; i++) sc[i] = p.sc_in[e * NS + i];
+        float old_score = __int_as_float(sc[FN_SCORE]);
+        int lines = 0;
+        const int spawn_x = p.Wp / 2 - 2;   // core.get_initial_x_y: 4x4 matrices (functional/core.py:66-83)
+        if (!p.actions) {
+            // tetris_fn.reset (envs/tetris_fn.py:318-367)
+            for (int r = 0; r < p.Hp; r++)
+                for (int c = 0; c < p.Wp; c++) b[r * p.Wp + c] = (r < p.H && c >= P && c < P + p.W) ? 0 : 1;
+            sc[FN_KEY1] = 0;
+            fn_new_bag(p, e, sc);
+            sc[FN_ACTIVE] = sc[FN_S]; sc[FN_QIDX] = 1;
+            sc[FN_ROT] = 0; sc[FN_X] = spawn_x; sc[FN_Y] = 0; sc[FN_OVER] = 0; sc[FN_SCORE] = __float_as_int(0.f);
+            old_score = 0.f;
+        } else if (!sc[FN_OVER]) {
+            // tetris_fn.update_state (envs/tetris_fn.py:161-273)
+            const int a = p.actions[e];
+            int piece = sc[FN_ACTIVE], rot = sc[FN_ROT], x = sc[FN_X], y = sc[FN_Y];
+            uint32_t cells = c_cells[piece][rot];
+            int drop_reward = 0;
+            if (a == 0) { if (!fn_collision(p, b, cells, x - 1, y)) x -= 1; }
+            else if (a == 1) { if (!fn_collision(p, b, cells, x + 1, y)) x += 1; }
+            else if (a == 2) { if (!fn_collision(p, b, cells, x, y + 1)) { y += 1; drop_reward = 1; } }
+            else if (a == 3 || a == 4) {
+                int nr = (rot + (a == 4 ? 1 : 3)) & 3;   // 3 = counter-clockwise, 4 = clockwise (envs/tetris_fn.py:470-478)
+                if (!fn_collision(p, b, c_cells[piece][nr], x, y)) { rot = nr; cells = c_cells[piece][nr]; }
+            } else if (a == 6) {                          // core.hard_drop (functional/core.py:230-251)
+                int ny = y;
+                while (!fn_collision(p, b, cells, x, ny + 1)) ny++;
+                drop_reward = 2 * (ny - y);
+                y = ny;
+            }
+            int yg = y;
+            if (p.gravity && !fn_collision(p, b, cells, x, y + 1)) yg = y + 1;   // core.graviy_step
+            bool should_lock = (yg == y) && p.gravity;
+            y = yg;
+            int lock_reward = 0;
+            if (should_lock || a == 6) {
+                // place_active_tetromino (envs/tetris_fn.py:370-413) / core.lock_active_tetromino
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    int c = (cells >> (4 * k)) & 15;
+                    b[(y + (c >> 2)) * p.Wp + x + (c & 3)] += (int8_t)(piece + 2);
+                }
+                // core.clear_filled_rows (functional/core.py:185-227): all(sub_board > 0); survivors keep order
+                int dst = p.H - 1;
+                for (int r = p.H - 1; r >= 0; r--) {
+                    bool full = true;
+                    for (int c = 0; c < p.W; c++) full &= b[r * p.Wp + P + c] > 0;
+                    if (full) { lines++; continue; }
+                    if (dst != r) for (int c = 0; c < p.W; c++) b[dst * p.Wp + P + c] = b[r * p.Wp + P + c];
+                    dst--;
+                }
+                for (; dst >= 0 && lines > 0; dst--) for (int c = 0; c < p.W; c++) b[dst * p.Wp + P + c] = 0;
+                lock_reward = lines == 0 ? 0 : (lines == 4 ? 800 : lines * 200 - 100);   // core.score
+                // next piece: queue.bag_queue_get_next_element (functional/queue.py:38-67)
+                if (sc[FN_QIDX] >= p.Q) { fn_new_bag(p, e, sc); piece = sc[FN_S]; sc[FN_QIDX] = 1; }
+                else { piece = sc[FN_S + sc[FN_QIDX]]; sc[FN_QIDX] += 1; }
+                rot = 0; x = spawn_x; y = 0;
+                sc[FN_OVER] = fn_collision(p, b, c_cells[piece][0], x, y) ? 1 : 0;   // core.check_game_over
+            }
+            sc[FN_ACTIVE] = piece; sc[FN_ROT] = rot; sc[FN_X] = x; sc[FN_Y] = y;
+            sc[FN_SCORE] = __float_as_int(old_score + (float)(drop_reward + lock_reward));
+        }
+        for (int i = 0; i < NS; i++) p.sc_out[e * NS + i] = sc[i];
+        if (p.reward) p.reward[e] = __int_as_float(sc[FN_SCORE]) - old_score;
+        if (p.terminated) p.terminated[e] = (uint8_t)sc[FN_OVER];
+        if (p.lines) p.lines[e] = lines;
+    }
+    __threadfence_block();
+    __syncthreads();
+    // 3. get_observation (envs/tetris_fn.py:137-158): (board > 0) + active piece * (-1), cropped to H x W
+    if (p.obs) {
+        const int HW = p.H * p.W, NSs = FN_S + p.Q;
+        for (int i = tid; i < nv * HW; i += T) {
+            int el = i / HW, rem = i - el * HW, r = rem / p.W, c = rem - r * p.W;
+            int64_t e = base + el;
+            const int32_t* sc = p.sc_out + e * NSs;
+            int v = p.board_out[e * OB + r * p.Wp + P + c] > 0 ? 1 : 0;
+            if (!sc[FN_OVER]) {
+                int rr = r - sc[FN_Y], cc = c + P - sc[FN_X];
+                if ((unsigned)rr < 4u && (unsigned)cc < 4u) {
+                    uint32_t cells = c_cells[sc[FN_ACTIVE]][sc[FN_ROT]];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) if (((cells >> (4 * k)) & 15) == (uint32_t)((rr << 2) | cc)) v -= 1;
+                }
+            }
+            p.obs[e * HW + rem] = (int8_t)v;
+        }
+    }
+}
+
+}  // namespace tg
