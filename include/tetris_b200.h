@@ -148,7 +148,8 @@ int tg_reset(tg_env *env, tg_state st, int64_t n, const uint64_t *d_seeds, const
  * PCG64(SeedSequence(seed)) (Randomizer.reset, components/tetromino_randomizer.py:40-43). */
 int tg_seed_numpy(tg_env *env, tg_state st, int64_t n, const uint64_t *d_pcg, const uint8_t *d_mask, void *stream);
 
-/* replaces Tetris.step (envs/tetris.py:203-272) for n envs, observation dict written every call.
+/* replaces Tetris.step (envs/tetris.py:203-272) for n envs, observation dict written every call
+ * (pass an all-NULL tg_obs to skip the dict, e.g. when only tg_render_rgb / tg_features output is consumed).
  * d_stats may be NULL. */
 int tg_step(tg_env *env, tg_state st, int64_t n, const int32_t *d_actions, tg_obs obs, tg_step_out out,
             tg_stats *d_stats, void *stream);

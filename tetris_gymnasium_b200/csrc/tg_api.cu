@@ -296,7 +296,7 @@ extern "C" int tg_step(tg_env* env, tg_state st, int64_t n, const int32_t* d_act
     if (!env) return TG_ERR_POINTER;
     if (n <= 0) return fail(env, TG_ERR_ARG, "n must be positive");
     int rc = check_state(env, st); if (rc) return rc;
-    rc = check_obs(env, obs); if (rc) return rc;
+    if (obs.board || obs.mask || obs.holder || obs.queue) { rc = check_obs(env, obs); if (rc) return rc; }  // all NULL = no dict
     if (!d_actions || !out.reward || !out.terminated || !out.truncated || !out.lines)
         return fail(env, TG_ERR_POINTER, "actions / step outputs pointer is NULL");
     CUDA_TRY(env, cudaSetDevice(env->device));

@@ -161,6 +161,7 @@ class Tetris:
         self._stats = torch.zeros(4, dtype=torch.float64, device=dev)
         self._seeded = False
         self._has_reset = False
+        self.emit_obs_dict = True   # wrappers that replace the observation (RgbObservation, FeatureVector) switch it off
 
     # ---- plumbing ---------------------------------------------------------------------------
     def _state(self):
@@ -264,7 +265,8 @@ class Tetris:
         {"lines_cleared": i32[n]}) -- tensors are the env's output buffers, overwritten by the next call."""
         a = self._actions(actions)
         with torch.cuda.device(self.device):
-            _lib.check(self._L.tg_step(self._h, self._state(), self.num_envs, a.data_ptr(), self._obs_struct(),
+            obs = self._obs_struct() if self.emit_obs_dict else _lib.TgObs(None, None, None, None)
+            _lib.check(self._L.tg_step(self._h, self._state(), self.num_envs, a.data_ptr(), obs,
                                        self._out_struct(), self._stats.data_ptr(), self._stream()), self._h)
         return (self._obs(), self._reward, self._terminated.view(torch.bool), self._truncated.view(torch.bool),
                 {"lines_cleared": self._lines})

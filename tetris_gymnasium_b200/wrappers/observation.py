@@ -13,9 +13,12 @@ from .. import _lib
 
 
 class _ObsWrapper:
-    def __init__(self, env):
+    def __init__(self, env, keep_obs_dict=False):
         self.env = env
         self.action_space = env.action_space
+        # the wrapper replaces the observation: the base env need not write the dict on step()
+        if not keep_obs_dict:
+            env.unwrapped.emit_obs_dict = False
 
     @property
     def unwrapped(self):
@@ -37,8 +40,8 @@ class RgbObservation(_ObsWrapper):
     """Board on the left, queue top right, holder bottom right, as one RGB image
     u8[n, H_pad, W_pad + max(queue, holder) * P, 3] (reference wrappers/observation.py:38-74)."""
 
-    def __init__(self, env):
-        super().__init__(env)
+    def __init__(self, env, keep_obs_dict=False):
+        super().__init__(env, keep_obs_dict)
         u = env.unwrapped
         self.shape = (u.height_padded, u.layout.rgb_width, 3)
         self._img = torch.empty((u.num_envs,) + self.shape, dtype=torch.uint8, device=u.device)
@@ -56,8 +59,9 @@ class FeatureVectorObservation(_ObsWrapper):
     """heights(W), max height, holes, bumpiness as u8[n, W+3] (reference wrappers/observation.py:238-278),
     including the reference's row-0/1 zeroing through integer indexing and the uint8 wrap (Q4)."""
 
-    def __init__(self, env, report_height=True, report_max_height=True, report_holes=True, report_bumpiness=True):
-        super().__init__(env)
+    def __init__(self, env, report_height=True, report_max_height=True, report_holes=True, report_bumpiness=True,
+                 keep_obs_dict=True):
+        super().__init__(env, keep_obs_dict)
         u = env.unwrapped
         self.report_height, self.report_max_height = report_height, report_max_height
         self.report_holes, self.report_bumpiness = report_holes, report_bumpiness
