@@ -33,7 +33,7 @@ def test_golden_base_trajectories(path):
         else:
             env = Tetris(randomizer_mode="numpy", **kw)
             obs, _ = env.reset(seed=int(ep["seed"]))
-        featw, rgbw = FeatureVectorObservation(env), RgbObservation(env)
+        featw, rgbw = FeatureVectorObservation(env), RgbObservation(env, keep_obs_dict=True)
         rgb_at = {int(t): i for i, t in enumerate(ep["rgb_t"])} if "rgb_t" in ep else {}
         T = len(ep["actions"])
         for t in range(T + 1):

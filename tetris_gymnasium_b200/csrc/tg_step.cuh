@@ -88,9 +88,10 @@ __device__ __forceinline__ void nib8_to_bytes(uint32_t x, uint32_t& b0, uint32_t
 // Writes the W cell bytes of playfield row `row` of one env into its padded board image.
 // Only words that contain cell bytes are touched; the spill-over bytes are bedrock (1).
 template <int WT>
-__device__ __forceinline__ void fill_board_row(const DevCfg& cfg, const uint32_t* ids, uint8_t* tile, int env_off, int row) {
+__device__ __forceinline__ void fill_board_row(const DevCfg& cfg, const uint32_t* ids, uint8_t* tile, int env_off, int row,
+                                               int row_stride = 0) {
     const int W = WT ? WT : cfg.W;
-    const int Wp = W + 2 * P;
+    const int Wp = row_stride ? row_stride : W + 2 * P;
     constexpr int MAXC = WT ? (WT + 7) / 8 : 3;       // 8-nibble chunks per row (W <= 24)
     constexpr int MAXW = 2 * MAXC + 1;
     uint32_t cw[MAXW + 1];

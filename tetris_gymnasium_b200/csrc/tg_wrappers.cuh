@@ -160,64 +160,86 @@ __global__ void k_grouped_boards(const DevCfg cfg, int64_t n, const uint8_t* hot
     }
 }
 
-// RgbObservation.observation (wrappers/observation.py:38-74): one warp per env.
+// RgbObservation.observation (wrappers/observation.py:38-74): one warp per env, everything per-warp in shared memory:
+//   record (cols + id plane) -> id image [Hp][RW] (bedrock / ones written once per warp, cells + queue + holder + active
+//   piece per env) -> RGB bytes through a 16-entry colour LUT (4 pixels -> 3 words) -> one TMA bulk store per env.
 template <class COLT>
-__global__ void k_rgb(const DevCfg cfg, int64_t n, const uint8_t* hot, const uint8_t* board, uint8_t* img) {
-    extern __shared__ __align__(16) uint8_t sm[];
+__global__ void __launch_bounds__(256) k_rgb(const DevCfg cfg, int64_t n, const uint8_t* hot, const uint8_t* board, uint8_t* img,
+                                             int rec_bytes, int pix_bytes, int rgb_bytes) {
+    extern __shared__ __align__(128) uint8_t sm[];
+    __shared__ uint32_t s_lut[16];
+    __shared__ uint32_t s_rowbytes[112];
     const int W = cfg.W, H = cfg.H, Wp = cfg.Wp, Hp = cfg.Hp, RW = cfg.rgb_w, Q = cfg.Q;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     const int NP = Hp * RW;
-    const int NPr = (NP + 15) & ~15;
-    uint8_t* pix = sm + (size_t)warp * NPr;
+    uint8_t* wbase = sm + (size_t)warp * (rec_bytes + pix_bytes + rgb_bytes);
+    uint32_t* rec = (uint32_t*)wbase;
+    uint8_t* pix = wbase + rec_bytes;
+    uint8_t* rgb = pix + pix_bytes;
+    if (threadIdx.x < 16) s_lut[threadIdx.x] = ((const uint32_t*)c_colors)[threadIdx.x];
+    for (int i = threadIdx.x; i < 112; i += blockDim.x) s_rowbytes[i] = (&c_rowbytes[0][0][0])[i];
+    // constant part of the id image: everything that is not a playfield cell, a queue cell or a holder cell is 1
+    for (int i = lane; i < NP; i += 32) {
+        int r = i / RW, c = i - r * RW;
+        pix[i] = (c < Wp && r < H && c >= P && c < P + W) ? 0 : 1;
+    }
+    __syncthreads();
+    const bool fast = (NP & 3) == 0;
+    const bool tma = ((NP * 3) & 15) == 0 && (((uintptr_t)img) & 15) == 0;
     for (int64_t e = (int64_t)blockIdx.x * nwarps + warp; e < n; e += (int64_t)gridDim.x * nwarps) {
+        // previous env's bulk store must have finished reading this warp's rgb buffer
+        if (lane == 0) bulk_wait_read();
+        __syncwarp();
+        const uint32_t* grec = (const uint32_t*)(board + e * cfg.board_stride);
+        for (int i = lane; i < cfg.board_stride / 4; i += 32) rec[i] = grec[i];
         Hot h;
         hot_load(h, (const uint32_t*)(hot + e * 32));
-        const uint8_t* rec = board + e * cfg.board_stride;
+        __syncwarp();
         const COLT* cols = (const COLT*)rec;
-        const uint32_t* ids = (const uint32_t*)(rec + cfg.ids_off);
-        uint32_t cells = c_cells[h.p][h.r];
-        COLT B = bmask<COLT>(cols, W, cells, h.x);
-        bool show = !((B >> h.y) & 1);
-        for (int i = lane; i < NP; i += 32) {
-            int r = i / RW, c = i - r * RW;
-            int v = 1;
-            if (c < Wp) {
-                if (r < H && c >= P && c < P + W) v = (int)ids_get1(ids, r * W + c - P);
-            } else {
-                int cc = c - Wp;
-                if (r < P) {                       // queue on the top right
-                    int q = cc >> 2;
-                    v = q < Q ? (int)((c_rowbytes[(int)((h.queue >> (4 * q)) & 15u)][0][r] >> (8 * (cc & 3))) & 255u) : 1;
-                } else if (r >= Hp - P) {          // holder on the bottom right, padded with bedrock
-                    if (cc < P) v = h.hold ? (int)((c_rowbytes[h.hold - 1][h.hold_r][r - (Hp - P)] >> (8 * cc)) & 255u) : 1;
-                }
-            }
-            pix[i] = (uint8_t)v;
+        const uint32_t* ids = rec + cfg.ids_off / 4;
+        // board rows (cells only; the frame persists)
+        for (int r = lane; r < H; r += 32) fill_board_row<0>(cfg, ids, pix, 0, r, RW);
+        // queue (top right) and holder (bottom right)
+        for (int it = lane; it < 4 * Q; it += 32) {
+            int i = it / Q, q = it - i * Q;
+            uint32_t wv = s_rowbytes[((int)((h.queue >> (4 * q)) & 15u)) * 16 + i];
+            uint8_t* d = pix + i * RW + Wp + 4 * q;
+            d[0] = (uint8_t)wv; d[1] = (uint8_t)(wv >> 8); d[2] = (uint8_t)(wv >> 16); d[3] = (uint8_t)(wv >> 24);
+        }
+        if (lane < 4) {
+            uint32_t wv = h.hold ? s_rowbytes[((h.hold - 1) * 4 + h.hold_r) * 4 + lane] : 0x01010101u;
+            uint8_t* d = pix + (Hp - P + lane) * RW + Wp;
+            d[0] = (uint8_t)wv; d[1] = (uint8_t)(wv >> 8); d[2] = (uint8_t)(wv >> 16); d[3] = (uint8_t)(wv >> 24);
         }
         __syncwarp();
-        if (show && lane < 4) {
+        uint32_t cells = c_cells[h.p][h.r];
+        COLT B = bmask<COLT>(cols, W, cells, h.x);
+        if (!((B >> h.y) & 1) && lane < 4) {   // active piece on top (project_tetromino, envs/tetris.py:543-564)
             int c = (cells >> (4 * lane)) & 15;
             pix[(h.y + (c >> 2)) * RW + h.x + (c & 3)] = (uint8_t)(h.p + 2);
         }
         __syncwarp();
         uint8_t* g = img + (size_t)e * NP * 3;
-        // 4 pixels -> 3 words
-        const uint32_t* col32 = (const uint32_t*)c_colors;
-        if ((NP & 3) == 0 && (((uintptr_t)g) & 3) == 0) {
+        if (fast) {
+            uint32_t* o = tma ? (uint32_t*)rgb : (uint32_t*)g;
             for (int q4 = lane; q4 < NP / 4; q4 += 32) {
                 uint32_t pv = ((const uint32_t*)pix)[q4];
-                uint32_t c0 = col32[pv & 15], c1 = col32[(pv >> 8) & 15], c2 = col32[(pv >> 16) & 15], c3 = col32[(pv >> 24) & 15];
-                uint32_t w0 = (c0 & 0xFFFFFFu) | (c1 << 24);
-                uint32_t w1 = ((c1 >> 8) & 0xFFFFu) | (c2 << 16);
-                uint32_t w2 = ((c2 >> 16) & 0xFFu) | (c3 << 8);
-                uint32_t* o = (uint32_t*)g + 3 * q4;
-                o[0] = w0; o[1] = w1; o[2] = w2;
+                uint32_t c0 = s_lut[pv & 15], c1 = s_lut[(pv >> 8) & 15], c2 = s_lut[(pv >> 16) & 15], c3 = s_lut[(pv >> 24) & 15];
+                o[3 * q4] = c0 | (c1 << 24);
+                o[3 * q4 + 1] = (c1 >> 8) | (c2 << 16);
+                o[3 * q4 + 2] = (c2 >> 16) | (c3 << 8);
+            }
+            if (tma) {
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) { bulk_s2g(g, rgb, (uint32_t)(NP * 3)); bulk_commit(); }
             }
         } else {
-            for (int i = lane; i < NP * 3; i += 32) { int px = i / 3; g[i] = c_colors[pix[px]][i - 3 * px]; }
+            for (int i = lane; i < NP * 3; i += 32) { int px = i / 3; g[i] = (uint8_t)(s_lut[pix[px]] >> (8 * (i - 3 * px))); }
         }
         __syncwarp();
     }
+    if (lane == 0) bulk_wait_all();
 }
 
 }  // namespace tg
@@ -242,15 +264,25 @@ extern "C" int tg_render_rgb(tg_env* env, tg_state st, int64_t n, uint8_t* d_img
     if (!d_img) return fail(env, TG_ERR_POINTER, "d_img is NULL");
     CUDA_TRY(env, cudaSetDevice(env->device));
     const DevCfg& d = env->dev;
-    int T = 256, nw = T / 32;
-    size_t smem = (size_t)nw * (((size_t)d.Hp * d.rgb_w + 15) & ~(size_t)15);
-    int64_t blocks = (n + nw - 1) / nw;
-    int64_t cap = (int64_t)env->num_sms * 16;
-    if (blocks > cap) blocks = cap;
-    if (env->col64) k_rgb<uint64_t><<<(unsigned)blocks, T, smem, (cudaStream_t)stream>>>(d, n, (const uint8_t*)st.hot, (const uint8_t*)st.board, d_img);
-    else k_rgb<uint32_t><<<(unsigned)blocks, T, smem, (cudaStream_t)stream>>>(d, n, (const uint8_t*)st.hot, (const uint8_t*)st.board, d_img);
-    CUDA_TRY(env, cudaGetLastError());
-    return TG_OK;
+    auto r128 = [](size_t v) { return (int)((v + 127) / 128 * 128); };
+    int rec_bytes = r128((size_t)d.board_stride + 16), pix_bytes = r128((size_t)d.Hp * d.rgb_w + 16), rgb_bytes = r128((size_t)d.Hp * d.rgb_w * 3);
+    size_t per_warp = (size_t)rec_bytes + pix_bytes + rgb_bytes;
+    int nw = 8;
+    while (nw > 1 && per_warp * nw > 72 * 1024) nw >>= 1;
+    size_t smem = per_warp * nw;
+    if (smem > 227 * 1024) return fail(env, TG_ERR_CONFIG, "tg_render_rgb: image too large for shared memory");
+    int T = nw * 32;
+    auto launch = [&](auto kern) -> int {
+        CUDA_TRY(env, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 1;
+        CUDA_TRY(env, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, T, smem));
+        int64_t blocks = (n + nw - 1) / nw, cap = (int64_t)env->num_sms * (per_sm > 0 ? per_sm : 1);
+        if (blocks > cap) blocks = cap;
+        kern<<<(unsigned)blocks, T, smem, (cudaStream_t)stream>>>(d, n, (const uint8_t*)st.hot, (const uint8_t*)st.board, d_img, rec_bytes, pix_bytes, rgb_bytes);
+        CUDA_TRY(env, cudaGetLastError());
+        return TG_OK;
+    };
+    return env->col64 ? launch(k_rgb<uint64_t>) : launch(k_rgb<uint32_t>);
 }
 
 static int launch_grouped_observe(tg_env* env, tg_state st, int64_t n, uint8_t* d_feats, uint8_t* d_boards, uint8_t* d_legal,
