@@ -449,6 +449,111 @@ __device__ __forceinline__ void placement_features(const DevCfg& cfg, const COLT
     lines_out = placement_eval<COLT>(cfg, cols, cells, x, y, place, do_clear, rowzero, out).lines;
 }
 
+// ---- incremental placement evaluation -------------------------------------------------------------------
+// Per env (once per enumeration): column heights / holes of the current board with the wrapper's row zeroing,
+// their sums, and prefix / suffix ANDs of the occupancy columns.  A placement touches <= 4 adjacent columns, so
+//   full rows = touched & pre[c0] & suf[c1] & AND_{c0..c1}(col | piece bits)
+// and when no row is cleared (the common case) only the touched columns' features change; the full
+// recomputation (placement_eval) is needed only when rows are cleared.
+template <class COLT>
+struct EnvBase {
+    uint8_t* h;       // [W]   heights
+    uint8_t* ho;      // [W]   holes per column
+    COLT* pre;        // [W]   AND of columns < c
+    COLT* suf;        // [W]   AND of columns > c
+    int sum_h, holes, bump, max_h;
+};
+template <class COLT>
+__device__ __forceinline__ void env_base_compute(const DevCfg& cfg, const COLT* cols, COLT rowzero, EnvBase<COLT>& b) {
+    const int W = cfg.W, H = cfg.H;
+    COLT acc = ~COLT(0);
+    int prev = 0;
+    b.sum_h = 0; b.holes = 0; b.bump = 0; b.max_h = 0;
+    for (int c = 0; c < W; c++) {
+        b.pre[c] = acc;
+        acc &= cols[c];
+        int hgt, hol;
+        col_features<COLT>(cols[c] & ~rowzero, H, hgt, hol);
+        b.h[c] = (uint8_t)hgt; b.ho[c] = (uint8_t)hol;
+        b.sum_h += hgt; b.holes += hol; b.max_h = max(b.max_h, hgt);
+        if (c > 0) b.bump += abs(hgt - prev);
+        prev = hgt;
+    }
+    acc = ~COLT(0);
+    for (int c = W - 1; c >= 0; c--) { b.suf[c] = acc; acc &= cols[c]; }
+}
+// regular placement at (x, y): same results as placement_eval(..., place=true, do_clear=true, rowzero, out).
+// defer_clear: when rows would be cleared return lines = -1 instead of running the full evaluation, so that the
+// caller can batch those (rare) placements instead of paying the slow path under warp divergence.
+template <class COLT>
+__device__ __forceinline__ FeatSum placement_eval_fast(const DevCfg& cfg, const COLT* cols, const EnvBase<COLT>& b, uint32_t cells,
+                                                       int x, int y, COLT rowzero, uint8_t* out, bool defer_clear = false) {
+    const int W = cfg.W, H = cfg.H;
+    int crow[4], ccol[4];
+    int c0 = 64, c1 = -1;
+    COLT touched = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        int c = (cells >> (4 * k)) & 15;
+        crow[k] = y + (c >> 2);
+        ccol[k] = x + (c & 3) - P;
+        c0 = min(c0, ccol[k]); c1 = max(c1, ccol[k]);
+        touched |= COLT(1) << crow[k];
+    }
+    COLT nv[4];
+    COLT full = touched & b.pre[c0] & b.suf[c1];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        int c = c0 + j;
+        COLT v = 0;
+        if (c <= c1) {
+            v = cols[c];
+#pragma unroll
+            for (int k = 0; k < 4; k++) if (ccol[k] == c) v |= COLT(1) << crow[k];
+            full &= v;
+        }
+        nv[j] = v;
+    }
+    full &= (COLT(1) << H) - 1;
+    FeatSum fs;
+    if (full) {
+        if (defer_clear) { fs.lines = -1; fs.sum_h = fs.max_h = fs.holes = fs.bump = 0; return fs; }
+        return placement_eval<COLT>(cfg, cols, cells, x, y, true, true, rowzero, out);
+    }
+    fs.lines = 0;
+    int sumh = b.sum_h, holes = b.holes, maxh = b.max_h, bump = b.bump;
+    int nh[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        int c = c0 + j;
+        nh[j] = 0;
+        if (c <= c1) {
+            int hgt, hol;
+            col_features<COLT>(nv[j] & ~rowzero, H, hgt, hol);
+            sumh += hgt - (int)b.h[c]; holes += hol - (int)b.ho[c]; maxh = max(maxh, hgt);
+            nh[j] = hgt;
+        }
+    }
+    // bumpiness: only the pairs that touch [c0, c1] change
+#pragma unroll
+    for (int j = -1; j < 4; j++) {
+        int c = c0 + j;          // pair (c, c+1)
+        if (c >= 0 && c <= c1 && c + 1 < W) {
+            int a0 = (j >= 0) ? nh[j] : (int)b.h[c];
+            int a1 = (c + 1 <= c1) ? nh[(j + 1) & 3] : (int)b.h[c + 1];
+            bump += abs(a1 - a0) - abs((int)b.h[c + 1] - (int)b.h[c]);
+        }
+    }
+    if (out) {
+        for (int c = 0; c < W; c++) out[c] = b.h[c];
+#pragma unroll
+        for (int j = 0; j < 4; j++) if (c0 + j <= c1) out[c0 + j] = (uint8_t)nh[j];
+        out[W] = (uint8_t)maxh; out[W + 1] = (uint8_t)holes; out[W + 2] = (uint8_t)bump;
+    }
+    fs.sum_h = sumh; fs.max_h = maxh; fs.holes = holes; fs.bump = bump;
+    return fs;
+}
+
 // One placement of GroupedActionsObservations.observation (wrappers/grouped.py:148-181).
 struct Placement { int x, y, rot, kind; };  // kind: 0 regular, 1 illegal (frame), 2 game over
 template <class COLT>

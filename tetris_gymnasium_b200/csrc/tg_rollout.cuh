@@ -22,6 +22,7 @@ struct RolloutParams {
     int k_steps;
     double* stats;
     int rec_words;   // shared-memory words per env record (odd / 8-byte friendly stride)
+    int base_off;    // word offset of the per-thread EnvBase arrays (pre[W], suf[W], h[32 B], ho[32 B]) inside the record slot
     int32_t* last_action;   // nullable: action chosen at the last step (tests)
 };
 
@@ -53,20 +54,42 @@ __global__ void __launch_bounds__(128) k_rollout(const __grid_constant__ Rollout
         g.dirty = false;
         const COLT* cols = (const COLT*)rec;
         const int A = cfg.A;
+        EnvBase<COLT> eb;
+        eb.pre = (COLT*)(rec + p.base_off);
+        eb.suf = eb.pre + cfg.W;
+        eb.h = (uint8_t*)(eb.suf + cfg.W);
+        eb.ho = eb.h + 32;
         int last = -1;
         for (int step = 0; step < p.k_steps; step++) {
             if (cfg.autoreset == 1 && h.pending) { env_reset<COLT>(cfg, h, rec, g); last = -1; continue; }
             // ---- enumerate + score ----
             int best = -1, best_score = 0, first_legal = -1;
+            env_base_compute<COLT>(cfg, cols, COLT(1), eb);
+            uint32_t slow[3] = {0u, 0u, 0u};   // placements that clear rows: evaluated in a second, short loop
             for (int a = 0; a < A; a++) {
                 COLT B;
                 Placement pl = eval_placement<COLT>(cfg, tb, cols, h.p, h.r, a, B);
                 if (pl.kind == 1) continue;
                 if (first_legal < 0) first_legal = a;
                 if (pl.kind == 2) continue;
-                FeatSum fs = placement_eval<COLT>(cfg, cols, tb.cells[h.p * 4 + pl.rot], pl.x, pl.y, true, true, COLT(1), nullptr);
-                int score = p.w[0] * fs.sum_h + p.w[1] * fs.lines + p.w[2] * (int)(uint8_t)fs.holes + p.w[3] * (int)(uint8_t)fs.bump;
+                FeatSum fs = placement_eval_fast<COLT>(cfg, cols, eb, tb.cells[h.p * 4 + pl.rot], pl.x, pl.y, COLT(1), nullptr, true);
+                if (fs.lines < 0) { slow[a >> 5] |= 1u << (a & 31); continue; }
+                int score = p.w[0] * fs.sum_h + p.w[2] * (int)(uint8_t)fs.holes + p.w[3] * (int)(uint8_t)fs.bump;
                 if (best < 0 || score > best_score) { best = a; best_score = score; }
+            }
+#pragma unroll
+            for (int wi = 0; wi < 3; wi++) {
+                uint32_t m = slow[wi];
+                while (m) {
+                    int a = wi * 32 + __ffs((int)m) - 1;
+                    m &= m - 1;
+                    COLT B;
+                    Placement pl = eval_placement<COLT>(cfg, tb, cols, h.p, h.r, a, B);
+                    FeatSum fs = placement_eval<COLT>(cfg, cols, tb.cells[h.p * 4 + pl.rot], pl.x, pl.y, true, true, COLT(1), nullptr);
+                    int score = p.w[0] * fs.sum_h + p.w[1] * fs.lines + p.w[2] * (int)(uint8_t)fs.holes + p.w[3] * (int)(uint8_t)fs.bump;
+                    // lowest index among the maxima: a later candidate wins only if strictly better, an earlier one on ties
+                    if (best < 0 || score > best_score || (score == best_score && a < best)) { best = a; best_score = score; }
+                }
             }
             int action = best >= 0 ? best : first_legal;
             last = action;

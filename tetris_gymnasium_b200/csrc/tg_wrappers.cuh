@@ -25,15 +25,30 @@ __global__ void k_features(const DevCfg cfg, int64_t n, const uint8_t* hot, cons
 }
 
 // grouped observation with FeatureVectorObservation: feats u8[n][A][F], legal u8[n][A]
+// CTA = EPB envs; one thread per env precomputes the EnvBase, then one thread per (env, placement).
 template <class COLT>
-__global__ void k_grouped_feats(const DevCfg cfg, int64_t n, const uint8_t* hot, const uint8_t* board, uint8_t* feats,
-                                uint8_t* legal, const uint8_t* fill_high, int EPB) {
+__global__ void __launch_bounds__(256) k_grouped_feats(const DevCfg cfg, int64_t n, const uint8_t* hot, const uint8_t* board, uint8_t* feats,
+                                                       uint8_t* legal, const uint8_t* fill_high, int EPB) {
     extern __shared__ __align__(16) uint8_t sm[];
     const int W = cfg.W, A = cfg.A, F = cfg.F;
-    COLT* s_cols = (COLT*)sm;                                   // EPB * W
-    uint32_t* s_w0 = (uint32_t*)(sm + (size_t)EPB * W * sizeof(COLT));  // EPB
-    uint8_t* s_feats = (uint8_t*)(s_w0 + EPB);                  // EPB * A * F (16-aligned by construction of EPB)
-    uint8_t* s_legal = s_feats + (size_t)EPB * A * F;           // EPB * A
+    COLT* s_cols = (COLT*)sm;                      // [EPB][W]
+    COLT* s_pre = s_cols + (size_t)EPB * W;        // [EPB][W]
+    COLT* s_suf = s_pre + (size_t)EPB * W;         // [EPB][W]
+    int* s_sum = (int*)(s_suf + (size_t)EPB * W);  // [EPB][4]: sum_h, holes, bump, max_h
+    uint32_t* s_w0 = (uint32_t*)(s_sum + EPB * 4); // [EPB]
+    uint8_t* s_h = (uint8_t*)(s_w0 + EPB);         // [EPB][32]
+    uint8_t* s_ho = s_h + EPB * 32;                // [EPB][32]
+    uint8_t* s_feats = s_ho + EPB * 32;            // [EPB][A][F]   (16-aligned: every block above is a multiple of 16 for EPB % 4 == 0)
+    uint8_t* s_legal = s_feats + (size_t)EPB * A * F;
+    __shared__ unsigned short s_cells[28];
+    __shared__ int s_n[8];
+    __shared__ unsigned short s_slow[16 * 96];   // EPB <= 16, A <= 96
+    __shared__ int s_nslow;
+    if (threadIdx.x < 28) s_cells[threadIdx.x] = (&c_cells[0][0])[threadIdx.x];
+    if (threadIdx.x < 7) s_n[threadIdx.x] = c_n[threadIdx.x];
+    if (threadIdx.x == 0) s_nslow = 0;
+    Tabs tb;
+    tb.cells = s_cells; tb.rowbytes = &c_rowbytes[0][0][0]; tb.n = s_n;
     const int64_t base = (int64_t)blockIdx.x * EPB;
     const int nv = (int)min((int64_t)EPB, n - base);
     for (int i = threadIdx.x; i < nv * W; i += blockDim.x) {
@@ -41,6 +56,14 @@ __global__ void k_grouped_feats(const DevCfg cfg, int64_t n, const uint8_t* hot,
         s_cols[i] = ((const COLT*)(board + (base + e) * cfg.board_stride))[c];
     }
     for (int i = threadIdx.x; i < nv; i += blockDim.x) s_w0[i] = *(const uint32_t*)(hot + (base + i) * 32);
+    __syncthreads();
+    if (threadIdx.x < nv) {
+        int e = threadIdx.x;
+        EnvBase<COLT> eb;
+        eb.h = s_h + e * 32; eb.ho = s_ho + e * 32; eb.pre = s_pre + e * W; eb.suf = s_suf + e * W;
+        env_base_compute<COLT>(cfg, s_cols + e * W, COLT(1), eb);
+        s_sum[e * 4] = eb.sum_h; s_sum[e * 4 + 1] = eb.holes; s_sum[e * 4 + 2] = eb.bump; s_sum[e * 4 + 3] = eb.max_h;
+    }
     __syncthreads();
     for (int it = threadIdx.x; it < nv * A; it += blockDim.x) {
         int e = it / A, a = it - e * A;
@@ -55,7 +78,7 @@ __global__ void k_grouped_feats(const DevCfg cfg, int64_t n, const uint8_t* hot,
             continue;
         }
         COLT B;
-        Placement pl = eval_placement<COLT>(cfg, const_tabs(), cols, piece, rot0, a, B);
+        Placement pl = eval_placement<COLT>(cfg, tb, cols, piece, rot0, a, B);
         s_legal[it] = pl.kind != 1;
         if (pl.kind == 1) {          // ones board, row 0 zeroed -> heights H-1
             for (int i = 0; i <= W; i++) out[i] = (uint8_t)(cfg.H - 1);
@@ -63,9 +86,21 @@ __global__ void k_grouped_feats(const DevCfg cfg, int64_t n, const uint8_t* hot,
         } else if (pl.kind == 2) {   // zeros board
             for (int i = 0; i < F; i++) out[i] = 0;
         } else {
-            int lines;
-            placement_features<COLT>(cfg, cols, c_cells[piece][pl.rot], pl.x, pl.y, true, true, COLT(1), out, lines);
+            EnvBase<COLT> eb;
+            eb.h = s_h + e * 32; eb.ho = s_ho + e * 32; eb.pre = s_pre + e * W; eb.suf = s_suf + e * W;
+            eb.sum_h = s_sum[e * 4]; eb.holes = s_sum[e * 4 + 1]; eb.bump = s_sum[e * 4 + 2]; eb.max_h = s_sum[e * 4 + 3];
+            FeatSum fs = placement_eval_fast<COLT>(cfg, cols, eb, tb.cells[piece * 4 + pl.rot], pl.x, pl.y, COLT(1), out, true);
+            if (fs.lines < 0) s_slow[atomicAdd(&s_nslow, 1)] = (unsigned short)it;   // rows get cleared: batch the full evaluation
         }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < s_nslow; k += blockDim.x) {
+        int it = s_slow[k], e = it / A, a = it - e * A;
+        uint32_t w0 = s_w0[e];
+        int piece = (w0 >> 13) & 7, rot0 = (w0 >> 16) & 3;
+        COLT B;
+        Placement pl = eval_placement<COLT>(cfg, tb, s_cols + e * W, piece, rot0, a, B);
+        placement_eval<COLT>(cfg, s_cols + e * W, tb.cells[piece * 4 + pl.rot], pl.x, pl.y, true, true, COLT(1), s_feats + (size_t)it * F);
     }
     __syncthreads();
     // coalesced copy-out of the tile (contiguous in global memory)
@@ -289,9 +324,13 @@ static int launch_grouped_observe(tg_env* env, tg_state st, int64_t n, uint8_t* 
                                   const uint8_t* fill_high, cudaStream_t s) {
     const DevCfg& d = env->dev;
     if (d_feats) {
-        int EPB = 8, T = 256;
+        int EPB = 16, T = 256;
         size_t colb = env->col64 ? 8 : 4;
-        size_t smem = (size_t)EPB * d.W * colb + (size_t)EPB * 4 + (size_t)EPB * d.A * d.F + (size_t)EPB * d.A;
+        size_t smem = (size_t)3 * EPB * d.W * colb + (size_t)EPB * 16 + (size_t)EPB * 4 + (size_t)EPB * 64 + (size_t)EPB * d.A * d.F + (size_t)EPB * d.A;
+        if (smem > 48 * 1024) {
+            if (env->col64) cudaFuncSetAttribute(k_grouped_feats<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            else cudaFuncSetAttribute(k_grouped_feats<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        }
         unsigned g = (unsigned)((n + EPB - 1) / EPB);
         if (env->col64) k_grouped_feats<uint64_t><<<g, T, smem, s>>>(d, n, (const uint8_t*)st.hot, (const uint8_t*)st.board, d_feats, d_legal, fill_high, EPB);
         else k_grouped_feats<uint32_t><<<g, T, smem, s>>>(d, n, (const uint8_t*)st.hot, (const uint8_t*)st.board, d_feats, d_legal, fill_high, EPB);
@@ -358,9 +397,12 @@ extern "C" int tg_rollout(tg_env* env, tg_state st, int64_t n, const int32_t wei
     for (int i = 0; i < 4; i++) p.w[i] = weights[i];
     p.k_steps = k_steps; p.stats = (double*)d_stats;
     p.last_action = (int32_t*)env->rollout_last_action;
-    int words = d.board_stride / 4;
+    int words = (d.board_stride + 4) / 4;                 // +1 word: ids_get8 may read one word past the id plane
+    if (env->col64) words = (words + 1) & ~1;             // keep the EnvBase arrays 8-byte aligned
+    p.base_off = words;
+    words += 2 * d.W * (env->col64 ? 2 : 1) + 16;         // pre[W], suf[W], h[32 B], ho[32 B]
     // u32 columns: odd word stride; u64 columns: stride = 2 (mod 4) words keeps 8-byte alignment and spreads the banks
-    if (env->col64) { words += 2; while ((words & 3) != 2) words += 2; } else { words |= 1; }
+    if (env->col64) { while ((words & 3) != 2) words += 1; } else { words |= 1; }
     p.rec_words = words;
     const int T = 128;
     size_t smem = (size_t)T * words * 4;
