@@ -182,7 +182,7 @@ extern "C" int tg_create(const tg_config* cfg, int device, tg_env** out) {
     env->warp_specialized = 1;
     env->fill_warps = 3;
     if (const char* t = getenv("TG_WS")) env->warp_specialized = atoi(t) != 0;
-    if (const char* t = getenv("TG_NF")) { int v = atoi(t); if (v >= 1 && v <= 3) env->fill_warps = v; }
+    if (const char* t = getenv("TG_NF")) { int v = atoi(t); if (v >= 1 && v <= 7) env->fill_warps = v; }
     int rc = upload_tables(env);
     if (rc != TG_OK) { g_create_err = env->err; delete env; return rc; }
     *out = env;

@@ -460,7 +460,7 @@ __device__ __forceinline__ void named_sync(int id, int count) { asm volatile("ba
 __device__ __forceinline__ void named_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
 template <int WT, int HT, class COLT>
-__global__ void __launch_bounds__(128) k_step_ws(const __grid_constant__ StepParams p) {
+__global__ void __launch_bounds__(256) k_step_ws(const __grid_constant__ StepParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const DevCfg& cfg = p.cfg;
     constexpr int E = 32, NS = 3;
