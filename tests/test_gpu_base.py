@@ -186,3 +186,70 @@ def test_philox_bag_properties_and_replay():
         obs, r, term, _, _ = env3.step(torch.from_numpy(act))
         o2, r2, t2, _ = orc.step(act, "disabled")
         assert_obs_equal(obs, o2, f"t={t}")
+
+
+def test_custom_action_and_reward_mappings_vs_oracle():
+    """ActionsMapping / RewardsMapping are honoured like the reference: permuted action ids, two names sharing
+    an id (first match in the elif chain wins; the hard_drop id also skips gravity), fractional rewards."""
+    from tetris_gymnasium_b200.envs.tetris import Tetris
+    from tetris_gymnasium_b200.mappings import ActionsMapping, RewardsMapping
+    from gpu_util import OracleBatch, assert_obs_equal, np_
+
+    cases = [
+        (dict(move_left=7, move_right=6, move_down=5, rotate_clockwise=4, rotate_counterclockwise=3, hard_drop=2, swap=1, no_op=0),
+         dict(alife=0.001, clear_line=1, game_over=-2.5, invalid_action=-0.1)),
+        (dict(move_left=0, move_right=1, move_down=2, rotate_clockwise=3, rotate_counterclockwise=4, hard_drop=0, swap=6, no_op=7),
+         dict(alife=1, clear_line=1, game_over=0, invalid_action=-0.1)),
+        (dict(move_left=3, move_right=3, move_down=2, rotate_clockwise=5, rotate_counterclockwise=4, hard_drop=1, swap=6, no_op=1),
+         dict(alife=0.3, clear_line=1, game_over=7.25, invalid_action=-1)),
+    ]
+    n, T = 120, 220
+    for amap, rmap in cases:
+        rng = np.random.default_rng(11)
+        seqs = rng.integers(0, 7, size=(n, 71)).astype(np.uint8)
+        env = Tetris(num_envs=n, randomizer_mode="sequence", piece_sequences=seqs, autoreset_mode="next_step",
+                     actions_mapping=ActionsMapping(**amap), rewards_mapping=RewardsMapping(**rmap))
+        assert env.reward_range == (min(rmap.values()), max(rmap.values()))
+        orc = OracleBatch(n, seqs=seqs, actions=amap, alife=rmap["alife"], game_over=rmap["game_over"], invalid_action=rmap["invalid_action"])
+        assert_obs_equal(env.reset()[0], orc.reset(), "reset")
+        for t in range(T):
+            a = rng.integers(0, 8, size=n)
+            obs, r, term, _, info = env.step(torch.from_numpy(a))
+            o2, r2, t2, l2 = orc.step(a)
+            assert_obs_equal(obs, o2, f"t={t}")
+            assert np.array_equal(np_(r), r2), (t, np_(r)[:8], r2[:8])
+            assert np.array_equal(np_(term), t2) and np.array_equal(np_(info["lines_cleared"]), l2)
+
+
+def test_masked_reset_and_state_roundtrip():
+    """options={'reset_mask': ...} resets only the selected envs; get_state/set_state round-trip restores a snapshot
+    (Tetris.get_state/set_state, envs/tetris.py:681-708)."""
+    from tetris_gymnasium_b200.envs.tetris import Tetris
+    from gpu_util import np_
+
+    n = 300
+    rng = np.random.default_rng(2)
+    seqs = rng.integers(0, 7, size=(n, 64)).astype(np.uint8)
+    env = Tetris(num_envs=n, randomizer_mode="sequence", piece_sequences=seqs, autoreset_mode="disabled")
+    env.reset()
+    for t in range(40):
+        env.step(torch.from_numpy(rng.integers(0, 8, size=n)))
+    snap = env.get_state()
+    acts = [torch.from_numpy(rng.integers(0, 8, size=n)) for _ in range(25)]
+    outs = []
+    for a in acts:
+        obs, r, term, _, _ = env.step(a)
+        outs.append((np_(obs["board"]).copy(), np_(r).copy(), np_(term).copy()))
+    env.set_state(snap)                       # restore and replay: identical trajectory
+    for a, (b, r0, t0) in zip(acts, outs):
+        obs, r, term, _, _ = env.step(a)
+        assert np.array_equal(np_(obs["board"]), b) and np.array_equal(np_(r), r0) and np.array_equal(np_(term), t0)
+    before = env.get_state()
+    mask = torch.from_numpy(rng.random(n) < 0.3)
+    env.reset(options={"reset_mask": mask})
+    after = env.get_state()
+    m = mask.numpy()
+    empty = np_(after["board"])[m][:, :20, 4:14]
+    assert (empty == 0).all() and (np_(after["y"])[m] == 0).all()
+    assert np.array_equal(np_(after["board"])[~m], np_(before["board"])[~m])
+    assert np.array_equal(np_(after["x"])[~m], np_(before["x"])[~m]) and np.array_equal(np_(after["queue"])[~m], np_(before["queue"])[~m])
