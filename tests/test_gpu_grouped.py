@@ -193,3 +193,63 @@ def test_grouped_random_and_greedy_vs_oracle(cfg):
     if cfg["feats"]:
         assert total_lines > 20
     assert np.array_equal(np_(base.get_state()["board"]), np.stack([o.board for o in orcs]))
+
+
+@pytest.mark.parametrize("W,H", [(10, 20), (20, 40), (13, 30), (24, 28)], ids=lambda v: str(v))
+def test_grouped_boards_with_line_clears_vs_oracle(W, H):
+    """Board-image enumeration (no observation wrappers) on constructed boards whose bottom rows are full but for
+    one or two wells, so that many of the 4W placements clear 1-4 rows: every placement image, the legal mask and the
+    executed placement vs the oracle.  (10,20)/(20,40)/(24,28) take the streaming kernel (image bytes % 16 == 0),
+    (13,30) the generic one."""
+    from gpu_util import np_
+    from oracle.tetris_oracle import OracleEnv
+    from tetris_gymnasium_b200.envs.tetris import Tetris
+    from tetris_gymnasium_b200.wrappers import GroupedActionsObservations
+
+    n, A = 96, 4 * W
+    rng = np.random.default_rng(7 * W + H)
+    seqs = rng.integers(0, 7, size=(n, 31)).astype(np.uint8)
+    base = Tetris(width=W, height=H, gravity=False, queue_size=3, num_envs=n, randomizer_mode="sequence",
+                  piece_sequences=seqs, autoreset_mode="disabled")
+    env = GroupedActionsObservations(base)
+    env.reset()
+    orcs = [OracleEnv(width=W, height=H, gravity=False, queue_size=3) for _ in range(n)]
+    boards = np.empty((n, H + 4, W + 8), np.uint8)
+    pieces, rots = rng.integers(0, 7, n), rng.integers(0, 4, n)
+    for i, o in enumerate(orcs):
+        o.set_sequence(seqs[i])
+        o.reset()
+        b = o.board
+        k = int(rng.integers(1, 6))                       # full rows at the bottom ...
+        b[H - k:H, 4:4 + W] = rng.integers(2, 9, size=(k, W))
+        wells = rng.choice(W, size=int(rng.integers(1, 3)), replace=False)
+        depth = int(rng.integers(1, k + 1))
+        b[H - k:H - k + depth, 4 + wells] = 0            # ... but for wells of random depth
+        noise = rng.random((3, W)) < 0.3                  # some rubble above
+        b[H - k - 3:H - k, 4:4 + W] = np.where(noise, rng.integers(2, 9, size=(3, W)), 0)
+        o.board = b
+        o.set_active(int(pieces[i]), int(rots[i]))
+        boards[i] = b
+    base.set_state(board=boards, piece=pieces, rotation=rots)
+    got = np_(env.observation())
+    cleared = 0
+    want_legal = np.empty((n, A), np.uint8)
+    for i, o in enumerate(orcs):
+        _, wb, wl = o.grouped_observe(features=False, boards=True)
+        _, _, ln = o.grouped_observe_lines()
+        cleared += int((ln > 0).sum())
+        want_legal[i] = wl
+        if not np.array_equal(got[i], wb):
+            bad = np.flatnonzero((got[i] != wb).reshape(A, -1).any(1))
+            raise AssertionError(f"env {i}: placement images {bad[:6]} differ\n got:\n{got[i][bad[0]]}\n want:\n{wb[bad[0]]}")
+    assert np.array_equal(np_(env.legal_actions_mask), want_legal)
+    assert cleared > n, "the constructed boards should produce many row-clearing placements"
+    # execute one legal placement per env and compare the locked boards and the re-enumeration
+    a = np.array([int(rng.choice(np.flatnonzero(want_legal[i]))) for i in range(n)])
+    g, r, term, _, info = env.step(torch.from_numpy(a))
+    for i, o in enumerate(orcs):
+        code, rr, tt, ll = o.grouped_step(int(a[i]), True)
+        assert (float(np_(r)[i]), bool(np_(term)[i]), int(np_(info["lines_cleared"])[i])) == (np.float32(rr), tt, ll), i
+        _, wb, wl = o.grouped_observe(features=False, boards=True)
+        assert np.array_equal(np_(g)[i], wb) and np.array_equal(np_(info["action_mask"])[i], wl), i
+    base.close()

@@ -314,16 +314,16 @@ __device__ __forceinline__ void env_commit(const DevCfg& cfg, const Tabs& tb, Ho
     }
     h.y += ctz_t<COLT>(B >> (h.y + 1));  // drop_active_tetromino
     uint32_t cells = tb.cells[h.p * 4 + h.r];
-    COLT touched = 0;
 #pragma unroll
     for (int k = 0; k < 4; k++) {  // place_active_tetromino / project_tetromino
         int c = (cells >> (4 * k)) & 15;
         int row = h.y + (c >> 2), col = h.x + (c & 3) - P;
         cols[col] |= COLT(1) << row;
-        touched |= COLT(1) << row;
         ids_set1(ids, row * cfg.W + col, (uint32_t)(h.p + 2));
     }
-    COLT full = touched;
+    // every filled playfield row is cleared, also ones the piece did not touch (a poked board may hold them;
+    // Tetris.clear_filled_rows scans the whole board, envs/tetris.py:481-512)
+    COLT full = (COLT(1) << cfg.H) - 1;
     for (int c = 0; c < cfg.W; c++) full &= cols[c];
     int lines = popc_t<COLT>(full);
     if (lines) clear_rows<COLT>(cfg, cols, ids, full);
@@ -402,7 +402,7 @@ __device__ __forceinline__ FeatSum placement_eval(const DevCfg& cfg, const COLT*
     }
     COLT full = 0;
     if (place && do_clear) {
-        full = (COLT(1) << crow[0]) | (COLT(1) << crow[1]) | (COLT(1) << crow[2]) | (COLT(1) << crow[3]);
+        full = (COLT(1) << H) - 1;   // all playfield rows are candidates (clear_filled_rows scans the whole board)
         for (int c = 0; c < W; c++) {
             COLT v = cols[c];
 #pragma unroll
@@ -491,17 +491,15 @@ __device__ __forceinline__ FeatSum placement_eval_fast(const DevCfg& cfg, const 
     const int W = cfg.W, H = cfg.H;
     int crow[4], ccol[4];
     int c0 = 64, c1 = -1;
-    COLT touched = 0;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         int c = (cells >> (4 * k)) & 15;
         crow[k] = y + (c >> 2);
         ccol[k] = x + (c & 3) - P;
         c0 = min(c0, ccol[k]); c1 = max(c1, ccol[k]);
-        touched |= COLT(1) << crow[k];
     }
     COLT nv[4];
-    COLT full = touched & b.pre[c0] & b.suf[c1];
+    COLT full = b.pre[c0] & b.suf[c1];
 #pragma unroll
     for (int j = 0; j < 4; j++) {
         int c = c0 + j;

@@ -157,12 +157,11 @@ __global__ void k_grouped_boards(const DevCfg cfg, int64_t n, const uint8_t* hot
         } else {
             uint32_t cells = c_cells[piece][pl.rot];
             int crow[4], ccol[4];
-            COLT full = 0;
+            COLT full = ~COLT(0);
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 int c = (cells >> (4 * k)) & 15;
                 crow[k] = pl.y + (c >> 2); ccol[k] = pl.x + (c & 3) - P;
-                full |= COLT(1) << crow[k];
             }
             for (int c = 0; c < W; c++) {
                 COLT v = cols[c];
@@ -192,6 +191,169 @@ __global__ void k_grouped_boards(const DevCfg cfg, int64_t n, const uint8_t* hot
             for (int i = lane; i < OB; i += 32) g[i] = buf[i];
         }
         __syncwarp();
+    }
+}
+
+// grouped observation without wrappers, streaming variant (OB % 16 == 0): one warp per ENV.
+//   1. the env's record is staged in the warp's shared memory and its id plane expanded ONCE into the padded byte image
+//      (bedrock frame persists in shared memory); every lane keeps its 16-byte slices of that image in registers;
+//   2. lane a evaluates placement a (landing row, frame / game-over class, full-row mask) -- 32 placements per round;
+//   3. per placement the warp streams the base image (or a constant fill) with one 128-bit store per lane: the output
+//      of one env is 4W * OB contiguous bytes (17.3 KB at 10x20), written exactly once;
+//   4. after a __syncwarp (orders the stores of the warp), the lane that owns a regular placement drops the four piece
+//      cells on top of its board image with byte stores (they merge in L2);
+//   5. placements that clear rows (rare) are composed row by row in a scratch image and stored from there.
+// HBM bytes per env-step: 4W * OB written + record read; no re-reads.  Bound: HBM write bandwidth.
+template <class COLT, int NV>
+__global__ void __launch_bounds__(256) k_grouped_boards_stream(const DevCfg cfg, int64_t n, const uint8_t* hot, const uint8_t* board,
+                                                               uint8_t* boards, uint8_t* legal, const uint8_t* fill_high, int rec_bytes,
+                                                               int img_bytes) {
+    extern __shared__ __align__(128) uint8_t sm[];
+    __shared__ unsigned short s_cells[28];
+    __shared__ int s_n[8];
+    const int W = cfg.W, H = cfg.H, Wp = cfg.Wp, A = cfg.A, OB = cfg.OB, BS = cfg.board_stride;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int NQ = OB >> 4;
+    uint8_t* wbase = sm + (size_t)warp * (rec_bytes + 2 * img_bytes);
+    uint32_t* rec = (uint32_t*)wbase;
+    uint8_t* img = wbase + rec_bytes;
+    uint8_t* scr = img + img_bytes;
+    if (threadIdx.x < 28) s_cells[threadIdx.x] = (&c_cells[0][0])[threadIdx.x];
+    if (threadIdx.x < 7) s_n[threadIdx.x] = c_n[threadIdx.x];
+    Tabs tb;
+    tb.cells = s_cells; tb.rowbytes = &c_rowbytes[0][0][0]; tb.n = s_n;
+    for (int i = lane; i < OB; i += 32) {   // bedrock frame of the base and scratch images, once per warp
+        int r = i / Wp, c = i - r * Wp;
+        uint8_t v = (r < H && c >= P && c < P + W) ? 0 : 1;
+        img[i] = v; scr[i] = v;
+    }
+    for (int i = BS / 4 + lane; i < rec_bytes / 4; i += 32) rec[i] = 0;   // ids_get8 may read one word past the id plane
+    __syncthreads();
+    const COLT* cols = (const COLT*)rec;
+    const uint32_t* ids = rec + cfg.ids_off / 4;
+    const COLT playfield = (COLT(1) << H) - 1;
+    for (int64_t e = (int64_t)blockIdx.x * nwarps + warp; e < n; e += (int64_t)gridDim.x * nwarps) {
+        const uint32_t* grec = (const uint32_t*)(board + e * BS);
+        for (int i = lane; i < BS / 4; i += 32) rec[i] = grec[i];
+        const uint32_t w0 = *(const uint32_t*)(hot + e * 32);
+        const int piece = (w0 >> 13) & 7, rot0 = (w0 >> 16) & 3;
+        const bool fh = fill_high && fill_high[e];
+        __syncwarp();
+        if (W == 10 && (H & 3) == 0) {
+            for (int g4 = lane; g4 < (H >> 2); g4 += 32) fill_rows4_w10(ids + 5 * g4, img + g4 * 72);
+        } else if (W == 20 && (H & 1) == 0) {
+            for (int g2 = lane; g2 < (H >> 1); g2 += 32) fill_rows2_w20(ids + 5 * g2, img + g2 * 56);
+        } else {
+            for (int r = lane; r < H; r += 32) fill_board_row<0>(cfg, ids, img, 0, r);
+        }
+        __syncwarp();
+        uint4 basev[NV];
+#pragma unroll
+        for (int j = 0; j < NV; j++) {
+            int q = lane + 32 * j;
+            basev[j] = q < NQ ? ((const uint4*)img)[q] : make_uint4(0, 0, 0, 0);
+        }
+        // placements of this env: lane `l` owns a = 32 * round + l
+        uint32_t info[3];     // kind (bits 0-1: 0 regular, 1 frame -> ones, 2 game over -> zeros, 3 constant fill), bit 2 = rows get cleared
+        uint32_t offlo[3], offhi[3];   // byte offsets of the 4 piece cells inside the board image (16 bits each)
+#pragma unroll
+        for (int rd = 0; rd < 3; rd++) {
+            info[rd] = 3; offlo[rd] = 0; offhi[rd] = 0;
+            const int a = rd * 32 + lane;
+            if (rd * 32 < A && a < A && !fh) {
+                COLT B;
+                Placement pl = eval_placement<COLT>(cfg, tb, cols, piece, rot0, a, B);
+                legal[e * A + a] = pl.kind != 1;
+                uint32_t k = (uint32_t)pl.kind;
+                if (pl.kind == 0) {
+                    uint32_t cells = tb.cells[piece * 4 + pl.rot];
+                    int crow[4], ccol[4];
+                    COLT full = ~COLT(0);
+#pragma unroll
+                    for (int c4 = 0; c4 < 4; c4++) {
+                        int c = (cells >> (4 * c4)) & 15;
+                        crow[c4] = pl.y + (c >> 2); ccol[c4] = pl.x + (c & 3) - P;
+                    }
+                    for (int c = 0; c < W; c++) {
+                        COLT v = cols[c];
+#pragma unroll
+                        for (int c4 = 0; c4 < 4; c4++) if (ccol[c4] == c) v |= COLT(1) << crow[c4];
+                        full &= v;
+                    }
+                    if (full & playfield) k |= 4u;
+                    offlo[rd] = (uint32_t)(crow[0] * Wp + ccol[0] + P) | ((uint32_t)(crow[1] * Wp + ccol[1] + P) << 16);
+                    offhi[rd] = (uint32_t)(crow[2] * Wp + ccol[2] + P) | ((uint32_t)(crow[3] * Wp + ccol[3] + P) << 16);
+                }
+                info[rd] = k;
+            }
+        }
+        const uint32_t fhw = 0x01010101u * (uint32_t)(uint8_t)(cfg.H * cfg.W);
+        uint8_t* genv = boards + (size_t)e * A * OB;
+#pragma unroll
+        for (int rd = 0; rd < 3; rd++) {
+            if (rd * 32 < A) {
+                const int na = min(32, A - rd * 32);
+                for (int src = 0; src < na; src++) {
+                    const uint32_t inf = __shfl_sync(0xffffffffu, info[rd], src);
+                    const int a = rd * 32 + src;
+                    uint4* g = (uint4*)(genv + (size_t)a * OB);
+                    if (!(inf & 4u) || (inf & 3u) != 0) {
+                        const uint32_t kind = inf & 3u;
+                        const uint32_t fw = kind == 1 ? 0x01010101u : (kind == 2 ? 0u : fhw);
+#pragma unroll
+                        for (int j = 0; j < NV; j++) {
+                            int q = lane + 32 * j;
+                            if (q < NQ) g[q] = kind == 0 ? basev[j] : make_uint4(fw, fw, fw, fw);
+                        }
+                    } else {
+                        // rows get cleared: project, compact (Tetris.clear_filled_rows on the copy, wrappers/grouped.py:171-177)
+                        COLT B;
+                        Placement pl = eval_placement<COLT>(cfg, tb, cols, piece, rot0, a, B);
+                        uint32_t cells = tb.cells[piece * 4 + pl.rot];
+                        int crow[4], ccol[4];
+                        COLT full = ~COLT(0);
+#pragma unroll
+                        for (int c4 = 0; c4 < 4; c4++) {
+                            int c = (cells >> (4 * c4)) & 15;
+                            crow[c4] = pl.y + (c >> 2); ccol[c4] = pl.x + (c & 3) - P;
+                        }
+                        for (int c = 0; c < W; c++) {
+                            COLT v = cols[c];
+#pragma unroll
+                            for (int c4 = 0; c4 < 4; c4++) if (ccol[c4] == c) v |= COLT(1) << crow[c4];
+                            full &= v;
+                        }
+                        full &= playfield;
+                        const int nclr = popc_t<COLT>(full);
+                        for (int r = lane; r < H; r += 32) {
+                            uint8_t* row = scr + r * Wp + P;
+                            if (r < nclr) { for (int c = 0; c < W; c++) row[c] = 0; continue; }
+                            int s = r - nclr;   // (r - nclr)-th surviving source row
+                            COLT f = full;
+                            while (f) { int fr = ctz_t<COLT>(f); f &= f - 1; if (fr <= s) s++; }
+                            const uint8_t* srow = img + s * Wp + P;
+                            for (int c = 0; c < W; c++) row[c] = srow[c];
+#pragma unroll
+                            for (int c4 = 0; c4 < 4; c4++) if (crow[c4] == s) row[ccol[c4]] = (uint8_t)(piece + 2);
+                        }
+                        __syncwarp();
+                        for (int q = lane; q < NQ; q += 32) g[q] = ((const uint4*)scr)[q];
+                        __syncwarp();
+                    }
+                }
+            }
+        }
+        __syncwarp();   // orders this warp's image stores before the cell stores below
+#pragma unroll
+        for (int rd = 0; rd < 3; rd++) {
+            const int a = rd * 32 + lane;
+            if (rd * 32 < A && a < A && info[rd] == 0) {
+                uint8_t* g = genv + (size_t)a * OB;
+                const uint8_t v = (uint8_t)(piece + 2);
+                g[offlo[rd] & 0xFFFFu] = v; g[offlo[rd] >> 16] = v; g[offhi[rd] & 0xFFFFu] = v; g[offhi[rd] >> 16] = v;
+            }
+        }
+        __syncwarp();   // rec / img are rewritten by the next env
     }
 }
 
@@ -336,7 +498,30 @@ static int launch_grouped_observe(tg_env* env, tg_state st, int64_t n, uint8_t* 
         else k_grouped_feats<uint32_t><<<g, T, smem, s>>>(d, n, (const uint8_t*)st.hot, (const uint8_t*)st.board, d_feats, d_legal, fill_high, EPB);
         CUDA_TRY(env, cudaGetLastError());
     }
-    if (d_boards) {
+    const bool stream_ok = d_boards && (d.OB & 15) == 0 && (((uintptr_t)d_boards) & 15) == 0 && d.OB <= 4 * 32 * 16 && !getenv("TG_BOARDS_V1");
+    if (stream_ok) {
+        const int T = 256, nw = T / 32;
+        const int NV = (d.OB / 16 + 31) / 32;
+        auto r128 = [](size_t v) { return (int)((v + 127) / 128 * 128); };
+        const int rec_bytes = r128((size_t)d.board_stride + 16), img_bytes = r128((size_t)d.OB);
+        const size_t smem = (size_t)nw * (rec_bytes + 2 * img_bytes);
+        auto launch = [&](auto kern) -> int {
+            CUDA_TRY(env, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int per_sm = 1;
+            CUDA_TRY(env, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, T, smem));
+            int64_t blocks = (n + nw - 1) / nw, cap = (int64_t)env->num_sms * (per_sm > 0 ? per_sm : 1);
+            if (blocks > cap) blocks = cap;
+            kern<<<(unsigned)blocks, T, smem, s>>>(d, n, (const uint8_t*)st.hot, (const uint8_t*)st.board, d_boards, d_legal, fill_high, rec_bytes, img_bytes);
+            CUDA_TRY(env, cudaGetLastError());
+            return TG_OK;
+        };
+        int rc;
+        if (env->col64) rc = NV <= 1 ? launch(k_grouped_boards_stream<uint64_t, 1>) : NV == 2 ? launch(k_grouped_boards_stream<uint64_t, 2>)
+                                   : NV == 3 ? launch(k_grouped_boards_stream<uint64_t, 3>) : launch(k_grouped_boards_stream<uint64_t, 4>);
+        else rc = NV <= 1 ? launch(k_grouped_boards_stream<uint32_t, 1>) : NV == 2 ? launch(k_grouped_boards_stream<uint32_t, 2>)
+                          : NV == 3 ? launch(k_grouped_boards_stream<uint32_t, 3>) : launch(k_grouped_boards_stream<uint32_t, 4>);
+        if (rc) return rc;
+    } else if (d_boards) {
         int T = 256, nw = T / 32;
         size_t smem = (size_t)nw * (((size_t)d.OB + 15) & ~(size_t)15);
         int64_t blocks = (n * d.A + nw - 1) / nw;
