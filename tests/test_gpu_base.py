@@ -253,3 +253,43 @@ def test_masked_reset_and_state_roundtrip():
     assert (empty == 0).all() and (np_(after["y"])[m] == 0).all()
     assert np.array_equal(np_(after["board"])[~m], np_(before["board"])[~m])
     assert np.array_equal(np_(after["x"])[~m], np_(before["x"])[~m]) and np.array_equal(np_(after["queue"])[~m], np_(before["queue"])[~m])
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(width=10, height=20, gravity=True, queue_size=4),    # 24 x 34 px: 8-pixel pair-table path + TMA store
+    dict(width=10, height=20, gravity=True, queue_size=7),
+    dict(width=20, height=40, gravity=True, queue_size=5),    # BASELINE config 5: two-row 20-wide expansion
+    dict(width=16, height=17, gravity=True, queue_size=1),    # 21 x 28 px: 4-pixel path, direct stores
+    dict(width=7, height=10, gravity=True, queue_size=2),     # odd pixel count: generic path
+    dict(width=13, height=30, gravity=False, queue_size=3),
+], ids=lambda c: f"{c['width']}x{c['height']}q{c['queue_size']}")
+def test_rgb_and_feature_wrappers_batched_vs_oracle(cfg):
+    """RgbObservation / FeatureVectorObservation on a ragged batch during random play (swap included, so the holder
+    panel is exercised) against the oracle's per-env rendering."""
+    from tetris_gymnasium_b200.envs.tetris import Tetris
+    from tetris_gymnasium_b200.wrappers import FeatureVectorObservation, RgbObservation
+    from gpu_util import OracleBatch, np_
+
+    n, T, L = 301, 120, 53
+    rng = np.random.default_rng(11)
+    seqs = rng.integers(0, 7, size=(n, L)).astype(np.uint8)
+    env = Tetris(num_envs=n, randomizer_mode="sequence", piece_sequences=seqs, autoreset_mode="next_step", **cfg)
+    rgbw, featw = RgbObservation(env, keep_obs_dict=True), FeatureVectorObservation(env)
+    orc = OracleBatch(n, seqs=seqs, **cfg)
+    env.reset()
+    o2 = orc.reset()
+    for t in range(T):
+        if t % 6 == 0 or t > T - 4:
+            got = np_(rgbw.observation())
+            want = np.stack([e.rgb() for e in orc.envs])
+            assert got.shape == want.shape and got.dtype == np.uint8
+            if not np.array_equal(got, want):
+                bad = np.flatnonzero((got != want).reshape(n, -1).any(1))
+                raise AssertionError(f"t={t}: rgb differs for envs {bad[:8]} (of {len(bad)})")
+            f = np_(featw.observation())
+            fw = np.stack([e.features({k: v[i] for k, v in o2.items()}) for i, e in enumerate(orc.envs)])
+            assert np.array_equal(f, fw), t
+        a = rng.choice([0, 1, 2, 3, 4, 5, 5, 6, 7], size=n)
+        env.step(torch.from_numpy(a))
+        o2, _, _, _ = orc.step(a)
+    env.close()

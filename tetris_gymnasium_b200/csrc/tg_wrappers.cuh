@@ -194,51 +194,92 @@ __global__ void k_grouped_boards(const DevCfg cfg, int64_t n, const uint8_t* hot
     }
 }
 
+// ---- per-warp record prefetch (Ampere-style cp.async, 16-byte chunks; each lane waits for its own copies) ----
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+// record of env e (BS bytes) followed by the first 16 bytes of its hot record, into one warp-private buffer
+__device__ __forceinline__ void warp_prefetch_env(uint8_t* dst, const uint8_t* board, const uint8_t* hot, int64_t e, int BS, int lane) {
+    const uint8_t* src = board + e * BS;
+    for (int i = lane; i < (BS >> 4); i += 32) cp_async16(dst + 16 * i, src + 16 * i);
+    if (lane == 0) cp_async16(dst + BS, hot + e * 32);
+    cp_async_commit();
+}
+
+// prefix / suffix ANDs of the occupancy columns of one env, computed by a warp (lane c holds column c):
+//   pre[c] = AND of columns < c,  suf[c] = AND of columns > c      (see EnvBase in tg_device.cuh)
+template <class COLT>
+__device__ __forceinline__ void warp_pre_suf(const COLT* cols, int W, int lane, COLT* pre, COLT* suf) {
+    COLT v = lane < W ? cols[lane] : ~COLT(0), u = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        COLT t = __shfl_up_sync(0xffffffffu, v, d), s = __shfl_down_sync(0xffffffffu, u, d);
+        if (lane >= d) v &= t;
+        if (lane + d < 32) u &= s;
+    }
+    COLT pe = __shfl_up_sync(0xffffffffu, v, 1), se = __shfl_down_sync(0xffffffffu, u, 1);
+    if (lane < W) { pre[lane] = lane ? pe : ~COLT(0); suf[lane] = lane < 31 ? se : ~COLT(0); }
+}
+
 // grouped observation without wrappers, streaming variant (OB % 16 == 0): one warp per ENV.
-//   1. the env's record is staged in the warp's shared memory and its id plane expanded ONCE into the padded byte image
-//      (bedrock frame persists in shared memory); every lane keeps its 16-byte slices of that image in registers;
-//   2. lane a evaluates placement a (landing row, frame / game-over class, full-row mask) -- 32 placements per round;
-//   3. per placement the warp streams the base image (or a constant fill) with one 128-bit store per lane: the output
-//      of one env is 4W * OB contiguous bytes (17.3 KB at 10x20), written exactly once;
-//   4. after a __syncwarp (orders the stores of the warp), the lane that owns a regular placement drops the four piece
-//      cells on top of its board image with byte stores (they merge in L2);
-//   5. placements that clear rows (rare) are composed row by row in a scratch image and stored from there.
-// HBM bytes per env-step: 4W * OB written + record read; no re-reads.  Bound: HBM write bandwidth.
+//   1. the env's record is prefetched (cp.async, double buffered) into the warp's shared memory and its id plane expanded
+//      ONCE into the padded byte image (bedrock frame persists); every lane keeps its 16-byte slices of it in registers;
+//   2. lane a evaluates placement a (landing row, frame / game-over class, full-row mask via prefix / suffix column ANDs)
+//      -- 32 placements per round; the classes are exchanged as ballot masks, so the composition loops are warp-uniform;
+//   3. the placement images are composed G at a time in a double-buffered group buffer: base image (or a constant fill) from
+//      registers with one 128-bit shared store per lane and slot, the four piece cells dropped in by the owning lane,
+//      row-clearing placements (rare) recomposed row by row;
+//   4. one TMA bulk store per group (G * OB contiguous bytes, 3.4 KB at 10x20); the next group is composed meanwhile.
+// Every output byte is written exactly once, in full 16-byte pieces (measured: patching cells in global memory after the
+// image stores costs 17 % -- partial sector writes).  HBM bytes per env-step: 4W * OB written + record read.
+// Bound: HBM write bandwidth.
 template <class COLT, int NV>
-__global__ void __launch_bounds__(256) k_grouped_boards_stream(const DevCfg cfg, int64_t n, const uint8_t* hot, const uint8_t* board,
-                                                               uint8_t* boards, uint8_t* legal, const uint8_t* fill_high, int rec_bytes,
-                                                               int img_bytes) {
+__global__ void __launch_bounds__(256, 3) k_grouped_boards_stream(const DevCfg cfg, int64_t n, const uint8_t* hot, const uint8_t* board,
+                                                                  uint8_t* boards, uint8_t* legal, const uint8_t* fill_high, int rec_bytes,
+                                                                  int img_bytes, int G, int gbuf_bytes) {
     extern __shared__ __align__(128) uint8_t sm[];
     __shared__ unsigned short s_cells[28];
     __shared__ int s_n[8];
     const int W = cfg.W, H = cfg.H, Wp = cfg.Wp, A = cfg.A, OB = cfg.OB, BS = cfg.board_stride;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     const int NQ = OB >> 4;
-    uint8_t* wbase = sm + (size_t)warp * (rec_bytes + 2 * img_bytes);
-    uint32_t* rec = (uint32_t*)wbase;
-    uint8_t* img = wbase + rec_bytes;
-    uint8_t* scr = img + img_bytes;
+    uint8_t* wbase = sm + (size_t)warp * (2 * rec_bytes + img_bytes + 512 + 2 * gbuf_bytes);
+    uint8_t* recbuf = wbase;                       // two record buffers (record + 16 B of the hot record)
+    uint8_t* img = wbase + 2 * rec_bytes;
+    COLT* s_pre = (COLT*)(img + img_bytes);        // [W] (<= 24 x 8 B)
+    COLT* s_suf = s_pre + 32;
+    uint8_t* gbuf = img + img_bytes + 512;         // two group buffers of G slots (OB bytes each, contiguous)
     if (threadIdx.x < 28) s_cells[threadIdx.x] = (&c_cells[0][0])[threadIdx.x];
     if (threadIdx.x < 7) s_n[threadIdx.x] = c_n[threadIdx.x];
     Tabs tb;
     tb.cells = s_cells; tb.rowbytes = &c_rowbytes[0][0][0]; tb.n = s_n;
-    for (int i = lane; i < OB; i += 32) {   // bedrock frame of the base and scratch images, once per warp
+    for (int i = lane; i < OB; i += 32) {   // bedrock frame of the base image, once per warp
         int r = i / Wp, c = i - r * Wp;
-        uint8_t v = (r < H && c >= P && c < P + W) ? 0 : 1;
-        img[i] = v; scr[i] = v;
+        img[i] = (r < H && c >= P && c < P + W) ? 0 : 1;
     }
-    for (int i = BS / 4 + lane; i < rec_bytes / 4; i += 32) rec[i] = 0;   // ids_get8 may read one word past the id plane
+    for (int i = lane; i < 2 * rec_bytes / 4; i += 32) ((uint32_t*)recbuf)[i] = 0;
     __syncthreads();
-    const COLT* cols = (const COLT*)rec;
-    const uint32_t* ids = rec + cfg.ids_off / 4;
     const COLT playfield = (COLT(1) << H) - 1;
-    for (int64_t e = (int64_t)blockIdx.x * nwarps + warp; e < n; e += (int64_t)gridDim.x * nwarps) {
-        const uint32_t* grec = (const uint32_t*)(board + e * BS);
-        for (int i = lane; i < BS / 4; i += 32) rec[i] = grec[i];
-        const uint32_t w0 = *(const uint32_t*)(hot + e * 32);
+    const int64_t stride = (int64_t)gridDim.x * nwarps;
+    int64_t e = (int64_t)blockIdx.x * nwarps + warp;
+    if (e < n) warp_prefetch_env(recbuf, board, hot, e, BS, lane);
+    bool act[NV];
+#pragma unroll
+    for (int j = 0; j < NV; j++) act[j] = lane + 32 * j < NQ;
+    const uint32_t fhw = 0x01010101u * (uint32_t)(uint8_t)(cfg.H * cfg.W);
+    uint32_t gcount = 0;   // groups issued by this warp (selects the group buffer)
+    for (int it = 0; e < n; e += stride, it++) {
+        const uint32_t* rec = (const uint32_t*)(recbuf + (it & 1) * rec_bytes);
+        const COLT* cols = (const COLT*)rec;
+        const uint32_t* ids = rec + cfg.ids_off / 4;
+        cp_async_wait_all();
+        __syncwarp();
+        if (e + stride < n) warp_prefetch_env(recbuf + ((it + 1) & 1) * rec_bytes, board, hot, e + stride, BS, lane);
+        const uint32_t w0 = rec[BS >> 2];
         const int piece = (w0 >> 13) & 7, rot0 = (w0 >> 16) & 3;
         const bool fh = fill_high && fill_high[e];
-        __syncwarp();
         if (W == 10 && (H & 3) == 0) {
             for (int g4 = lane; g4 < (H >> 2); g4 += 32) fill_rows4_w10(ids + 5 * g4, img + g4 * 72);
         } else if (W == 20 && (H & 1) == 0) {
@@ -246,72 +287,92 @@ __global__ void __launch_bounds__(256) k_grouped_boards_stream(const DevCfg cfg,
         } else {
             for (int r = lane; r < H; r += 32) fill_board_row<0>(cfg, ids, img, 0, r);
         }
+        warp_pre_suf<COLT>(cols, W, lane, s_pre, s_suf);
         __syncwarp();
         uint4 basev[NV];
 #pragma unroll
-        for (int j = 0; j < NV; j++) {
-            int q = lane + 32 * j;
-            basev[j] = q < NQ ? ((const uint4*)img)[q] : make_uint4(0, 0, 0, 0);
-        }
+        for (int j = 0; j < NV; j++) basev[j] = act[j] ? ((const uint4*)img)[lane + 32 * j] : make_uint4(0, 0, 0, 0);
         // placements of this env: lane `l` owns a = 32 * round + l
-        uint32_t info[3];     // kind (bits 0-1: 0 regular, 1 frame -> ones, 2 game over -> zeros, 3 constant fill), bit 2 = rows get cleared
-        uint32_t offlo[3], offhi[3];   // byte offsets of the 4 piece cells inside the board image (16 bits each)
+        // class: 0 regular, 1 frame -> ones, 2 game over -> zeros, 3 constant fill (illegal action + terminate), 4 regular + rows cleared, 8 none
+        uint32_t info[3], offlo[3], offhi[3];   // off*: byte offsets of the 4 piece cells inside the board image (16 bits each)
 #pragma unroll
         for (int rd = 0; rd < 3; rd++) {
-            info[rd] = 3; offlo[rd] = 0; offhi[rd] = 0;
+            info[rd] = 8; offlo[rd] = 0; offhi[rd] = 0;
             const int a = rd * 32 + lane;
-            if (rd * 32 < A && a < A && !fh) {
-                COLT B;
-                Placement pl = eval_placement<COLT>(cfg, tb, cols, piece, rot0, a, B);
-                legal[e * A + a] = pl.kind != 1;
-                uint32_t k = (uint32_t)pl.kind;
-                if (pl.kind == 0) {
-                    uint32_t cells = tb.cells[piece * 4 + pl.rot];
-                    int crow[4], ccol[4];
-                    COLT full = ~COLT(0);
+            if (rd * 32 < A && a < A) {
+                uint32_t k = 3;
+                if (!fh) {
+                    COLT B;
+                    Placement pl = eval_placement<COLT>(cfg, tb, cols, piece, rot0, a, B);
+                    legal[e * A + a] = pl.kind != 1;
+                    k = (uint32_t)pl.kind;
+                    if (pl.kind == 0) {
+                        uint32_t cells = tb.cells[piece * 4 + pl.rot];
+                        int crow[4], ccol[4], c0 = 64, c1 = -1;
 #pragma unroll
-                    for (int c4 = 0; c4 < 4; c4++) {
-                        int c = (cells >> (4 * c4)) & 15;
-                        crow[c4] = pl.y + (c >> 2); ccol[c4] = pl.x + (c & 3) - P;
-                    }
-                    for (int c = 0; c < W; c++) {
-                        COLT v = cols[c];
+                        for (int c4 = 0; c4 < 4; c4++) {
+                            int c = (cells >> (4 * c4)) & 15;
+                            crow[c4] = pl.y + (c >> 2); ccol[c4] = pl.x + (c & 3) - P;
+                            c0 = min(c0, ccol[c4]); c1 = max(c1, ccol[c4]);
+                        }
+                        COLT full = s_pre[c0] & s_suf[c1] & playfield;
 #pragma unroll
-                        for (int c4 = 0; c4 < 4; c4++) if (ccol[c4] == c) v |= COLT(1) << crow[c4];
-                        full &= v;
+                        for (int j = 0; j < 4; j++) {
+                            if (c0 + j <= c1) {
+                                COLT v = cols[c0 + j];
+#pragma unroll
+                                for (int c4 = 0; c4 < 4; c4++) if (ccol[c4] == c0 + j) v |= COLT(1) << crow[c4];
+                                full &= v;
+                            }
+                        }
+                        if (full) k = 4;
+                        offlo[rd] = (uint32_t)(crow[0] * Wp + ccol[0] + P) | ((uint32_t)(crow[1] * Wp + ccol[1] + P) << 16);
+                        offhi[rd] = (uint32_t)(crow[2] * Wp + ccol[2] + P) | ((uint32_t)(crow[3] * Wp + ccol[3] + P) << 16);
                     }
-                    if (full & playfield) k |= 4u;
-                    offlo[rd] = (uint32_t)(crow[0] * Wp + ccol[0] + P) | ((uint32_t)(crow[1] * Wp + ccol[1] + P) << 16);
-                    offhi[rd] = (uint32_t)(crow[2] * Wp + ccol[2] + P) | ((uint32_t)(crow[3] * Wp + ccol[3] + P) << 16);
                 }
                 info[rd] = k;
             }
         }
-        const uint32_t fhw = 0x01010101u * (uint32_t)(uint8_t)(cfg.H * cfg.W);
         uint8_t* genv = boards + (size_t)e * A * OB;
 #pragma unroll
         for (int rd = 0; rd < 3; rd++) {
             if (rd * 32 < A) {
+                const uint32_t m_base = __ballot_sync(0xffffffffu, info[rd] == 0 || info[rd] == 4);
+                const uint32_t m_one = __ballot_sync(0xffffffffu, info[rd] == 1);
+                const uint32_t m_high = __ballot_sync(0xffffffffu, info[rd] == 3);
+                const uint32_t m_slow = __ballot_sync(0xffffffffu, info[rd] == 4);
                 const int na = min(32, A - rd * 32);
-                for (int src = 0; src < na; src++) {
-                    const uint32_t inf = __shfl_sync(0xffffffffu, info[rd], src);
-                    const int a = rd * 32 + src;
-                    uint4* g = (uint4*)(genv + (size_t)a * OB);
-                    if (!(inf & 4u) || (inf & 3u) != 0) {
-                        const uint32_t kind = inf & 3u;
-                        const uint32_t fw = kind == 1 ? 0x01010101u : (kind == 2 ? 0u : fhw);
+                for (int l0 = 0; l0 < na; l0 += G, gcount++) {
+                    uint8_t* buf = gbuf + (gcount & 1u) * gbuf_bytes;
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the store that last used `buf` has read it
+                    __syncwarp();
+                    for (int sl = 0; sl < G; sl++) {
+                        const int bit = l0 + sl;
+                        uint4* d = (uint4*)(buf + sl * OB) + lane;
+                        if ((m_base >> bit) & 1) {
 #pragma unroll
-                        for (int j = 0; j < NV; j++) {
-                            int q = lane + 32 * j;
-                            if (q < NQ) g[q] = kind == 0 ? basev[j] : make_uint4(fw, fw, fw, fw);
+                            for (int j = 0; j < NV; j++) if (act[j]) d[32 * j] = basev[j];
+                        } else {
+                            const uint32_t fw = ((m_one >> bit) & 1) ? 0x01010101u : (((m_high >> bit) & 1) ? fhw : 0u);
+                            const uint4 fv = make_uint4(fw, fw, fw, fw);
+#pragma unroll
+                            for (int j = 0; j < NV; j++) if (act[j]) d[32 * j] = fv;
                         }
-                    } else {
+                    }
+                    __syncwarp();
+                    if (lane >= l0 && lane < l0 + G && info[rd] == 0) {   // project_tetromino: the four cells of this lane's placement
+                        uint8_t* d = buf + (lane - l0) * OB;
+                        const uint8_t v = (uint8_t)(piece + 2);
+                        d[offlo[rd] & 0xFFFFu] = v; d[offlo[rd] >> 16] = v; d[offhi[rd] & 0xFFFFu] = v; d[offhi[rd] >> 16] = v;
+                    }
+                    for (uint32_t m = (m_slow >> l0) & ((G >= 32) ? 0xffffffffu : ((1u << G) - 1)); m; m &= m - 1) {
                         // rows get cleared: project, compact (Tetris.clear_filled_rows on the copy, wrappers/grouped.py:171-177)
+                        const int sl = __ffs((int)m) - 1, a = rd * 32 + l0 + sl;
                         COLT B;
                         Placement pl = eval_placement<COLT>(cfg, tb, cols, piece, rot0, a, B);
                         uint32_t cells = tb.cells[piece * 4 + pl.rot];
                         int crow[4], ccol[4];
-                        COLT full = ~COLT(0);
+                        COLT full = playfield;
 #pragma unroll
                         for (int c4 = 0; c4 < 4; c4++) {
                             int c = (cells >> (4 * c4)) & 15;
@@ -323,10 +384,9 @@ __global__ void __launch_bounds__(256) k_grouped_boards_stream(const DevCfg cfg,
                             for (int c4 = 0; c4 < 4; c4++) if (ccol[c4] == c) v |= COLT(1) << crow[c4];
                             full &= v;
                         }
-                        full &= playfield;
                         const int nclr = popc_t<COLT>(full);
                         for (int r = lane; r < H; r += 32) {
-                            uint8_t* row = scr + r * Wp + P;
+                            uint8_t* row = buf + sl * OB + r * Wp + P;
                             if (r < nclr) { for (int c = 0; c < W; c++) row[c] = 0; continue; }
                             int s = r - nclr;   // (r - nclr)-th surviving source row
                             COLT f = full;
@@ -336,76 +396,111 @@ __global__ void __launch_bounds__(256) k_grouped_boards_stream(const DevCfg cfg,
 #pragma unroll
                             for (int c4 = 0; c4 < 4; c4++) if (crow[c4] == s) row[ccol[c4]] = (uint8_t)(piece + 2);
                         }
-                        __syncwarp();
-                        for (int q = lane; q < NQ; q += 32) g[q] = ((const uint4*)scr)[q];
-                        __syncwarp();
+                    }
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        bulk_s2g(genv + (size_t)(rd * 32 + l0) * OB, buf, (uint32_t)(min(G, na - l0) * OB));
+                        bulk_commit();
                     }
                 }
             }
         }
-        __syncwarp();   // orders this warp's image stores before the cell stores below
-#pragma unroll
-        for (int rd = 0; rd < 3; rd++) {
-            const int a = rd * 32 + lane;
-            if (rd * 32 < A && a < A && info[rd] == 0) {
-                uint8_t* g = genv + (size_t)a * OB;
-                const uint8_t v = (uint8_t)(piece + 2);
-                g[offlo[rd] & 0xFFFFu] = v; g[offlo[rd] >> 16] = v; g[offhi[rd] & 0xFFFFu] = v; g[offhi[rd] >> 16] = v;
-            }
-        }
-        __syncwarp();   // rec / img are rewritten by the next env
+        __syncwarp();   // img / pre / suf are rewritten by the next env
     }
+    if (lane == 0) bulk_wait_all();
 }
 
 // RgbObservation.observation (wrappers/observation.py:38-74): one warp per env, everything per-warp in shared memory:
-//   record (cols + id plane) -> id image [Hp][RW] (bedrock / ones written once per warp, cells + queue + holder + active
-//   piece per env) -> RGB bytes through a 16-entry colour LUT (4 pixels -> 3 words) -> one TMA bulk store per env.
+//   record (prefetched with cp.async, double buffered) -> id image [Hp][RW] (bedrock / ones written once per warp; cells +
+//   queue + holder + active piece per env) -> RGB bytes through a 256-entry PAIR table (two ids -> six colour bytes; eight
+//   pixels = one 64-bit read -> four table reads -> three 64-bit writes) -> one TMA bulk store per env.
+// HBM bytes per env: record + hot read, Hp * RW * 3 written once.  Bound: HBM write bandwidth.
+// 20-wide rows at a 4-byte aligned image row: 2 playfield rows (5 words of the id plane) per call
+__device__ __forceinline__ void fill_rows2_w20_strided(const uint32_t* ids5, uint32_t* o0, uint32_t* o1) {
+    uint32_t w0 = ids5[0], w1 = ids5[1], w2 = ids5[2], w3 = ids5[3], w4 = ids5[4];
+    uint32_t a0, a1, a2, a3, a4, ax, b0, b1, b2, b3, b4, bx;
+    nib8_to_bytes(w0, a0, a1);
+    nib8_to_bytes(w1, a2, a3);
+    nib8_to_bytes(w2 & 0xFFFFu, a4, ax);
+    nib8_to_bytes(__funnelshift_r(w2, w3, 16), b0, b1);
+    nib8_to_bytes(__funnelshift_r(w3, w4, 16), b2, b3);
+    nib8_to_bytes(w4 >> 16, b4, bx);
+    (void)ax; (void)bx;
+    o0[0] = a0; o0[1] = a1; o0[2] = a2; o0[3] = a3; o0[4] = a4;
+    o1[0] = b0; o1[1] = b1; o1[2] = b2; o1[3] = b3; o1[4] = b4;
+}
+
 template <class COLT>
-__global__ void __launch_bounds__(256) k_rgb(const DevCfg cfg, int64_t n, const uint8_t* hot, const uint8_t* board, uint8_t* img,
+__global__ void __launch_bounds__(256, 3) k_rgb(const DevCfg cfg, int64_t n, const uint8_t* hot, const uint8_t* board, uint8_t* img,
                                              int rec_bytes, int pix_bytes, int rgb_bytes) {
     extern __shared__ __align__(128) uint8_t sm[];
     __shared__ uint32_t s_lut[16];
+    __shared__ __align__(8) uint2 s_pair[256];
     __shared__ uint32_t s_rowbytes[112];
-    const int W = cfg.W, H = cfg.H, Wp = cfg.Wp, Hp = cfg.Hp, RW = cfg.rgb_w, Q = cfg.Q;
+    const int W = cfg.W, H = cfg.H, Wp = cfg.Wp, Hp = cfg.Hp, RW = cfg.rgb_w, Q = cfg.Q, BS = cfg.board_stride;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     const int NP = Hp * RW;
-    uint8_t* wbase = sm + (size_t)warp * (rec_bytes + pix_bytes + rgb_bytes);
-    uint32_t* rec = (uint32_t*)wbase;
-    uint8_t* pix = wbase + rec_bytes;
+    uint8_t* wbase = sm + (size_t)warp * (2 * rec_bytes + pix_bytes + rgb_bytes);
+    uint8_t* recbuf = wbase;               // two buffers: record (BS bytes) + hot record (32 B)
+    uint8_t* pix = wbase + 2 * rec_bytes;
     uint8_t* rgb = pix + pix_bytes;
     if (threadIdx.x < 16) s_lut[threadIdx.x] = ((const uint32_t*)c_colors)[threadIdx.x];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {   // pixel pair (lo nibble, hi nibble) -> R0 G0 B0 R1 | G1 B1
+        uint32_t c0 = ((const uint32_t*)c_colors)[i & 15] & 0xFFFFFFu, c1 = ((const uint32_t*)c_colors)[i >> 4] & 0xFFFFFFu;
+        s_pair[i] = make_uint2(c0 | (c1 << 24), c1 >> 8);
+    }
     for (int i = threadIdx.x; i < 112; i += blockDim.x) s_rowbytes[i] = (&c_rowbytes[0][0][0])[i];
     // constant part of the id image: everything that is not a playfield cell, a queue cell or a holder cell is 1
     for (int i = lane; i < NP; i += 32) {
         int r = i / RW, c = i - r * RW;
         pix[i] = (c < Wp && r < H && c >= P && c < P + W) ? 0 : 1;
     }
+    for (int i = lane; i < 2 * rec_bytes / 4; i += 32) ((uint32_t*)recbuf)[i] = 0;
     __syncthreads();
-    const bool fast = (NP & 3) == 0;
+    const bool fast8 = (NP & 7) == 0, fast4 = (NP & 3) == 0;
     const bool tma = ((NP * 3) & 15) == 0 && (((uintptr_t)img) & 15) == 0;
-    for (int64_t e = (int64_t)blockIdx.x * nwarps + warp; e < n; e += (int64_t)gridDim.x * nwarps) {
-        // previous env's bulk store must have finished reading this warp's rgb buffer
-        if (lane == 0) bulk_wait_read();
+    const bool rows20 = W == 20 && (H & 1) == 0 && (RW & 3) == 0;
+    const int64_t stride = (int64_t)gridDim.x * nwarps;
+    int64_t e = (int64_t)blockIdx.x * nwarps + warp;
+    auto prefetch = [&](int64_t ee, uint8_t* dst) {
+        const uint8_t* src = board + ee * BS;
+        for (int i = lane; i < (BS >> 4); i += 32) cp_async16(dst + 16 * i, src + 16 * i);
+        if (lane < 2) cp_async16(dst + BS + 16 * lane, hot + ee * 32 + 16 * lane);
+        cp_async_commit();
+    };
+    if (e < n) prefetch(e, recbuf);
+    for (int it = 0; e < n; e += stride, it++) {
+        const uint32_t* rec = (const uint32_t*)(recbuf + (it & 1) * rec_bytes);
+        cp_async_wait_all();
         __syncwarp();
-        const uint32_t* grec = (const uint32_t*)(board + e * cfg.board_stride);
-        for (int i = lane; i < cfg.board_stride / 4; i += 32) rec[i] = grec[i];
+        if (e + stride < n) prefetch(e + stride, recbuf + ((it + 1) & 1) * rec_bytes);
         Hot h;
-        hot_load(h, (const uint32_t*)(hot + e * 32));
-        __syncwarp();
+        hot_load(h, rec + (BS >> 2));
         const COLT* cols = (const COLT*)rec;
         const uint32_t* ids = rec + cfg.ids_off / 4;
         // board rows (cells only; the frame persists)
-        for (int r = lane; r < H; r += 32) fill_board_row<0>(cfg, ids, pix, 0, r, RW);
-        // queue (top right) and holder (bottom right)
-        for (int it = lane; it < 4 * Q; it += 32) {
-            int i = it / Q, q = it - i * Q;
-            uint32_t wv = s_rowbytes[((int)((h.queue >> (4 * q)) & 15u)) * 16 + i];
-            uint8_t* d = pix + i * RW + Wp + 4 * q;
-            d[0] = (uint8_t)wv; d[1] = (uint8_t)(wv >> 8); d[2] = (uint8_t)(wv >> 16); d[3] = (uint8_t)(wv >> 24);
+        if (rows20) {
+            for (int g2 = lane; g2 < (H >> 1); g2 += 32)
+                fill_rows2_w20_strided(ids + 5 * g2, (uint32_t*)(pix + (2 * g2) * RW + P), (uint32_t*)(pix + (2 * g2 + 1) * RW + P));
+        } else {
+            for (int r = lane; r < H; r += 32) fill_board_row<0>(cfg, ids, pix, 0, r, RW);
         }
-        if (lane < 4) {
-            uint32_t wv = h.hold ? s_rowbytes[((h.hold - 1) * 4 + h.hold_r) * 4 + lane] : 0x01010101u;
-            uint8_t* d = pix + (Hp - P + lane) * RW + Wp;
+        // queue (top right) and holder (bottom right)
+        for (int q = lane; q < Q; q += 32) {
+            const uint4 rb = *(const uint4*)(s_rowbytes + ((int)((h.queue >> (4 * q)) & 15u)) * 16);
+            const uint32_t wv[4] = {rb.x, rb.y, rb.z, rb.w};
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                uint8_t* d = pix + i * RW + Wp + 4 * q;
+                if ((RW & 3) == 0 && (Wp & 3) == 0) *(uint32_t*)d = wv[i];
+                else { d[0] = (uint8_t)wv[i]; d[1] = (uint8_t)(wv[i] >> 8); d[2] = (uint8_t)(wv[i] >> 16); d[3] = (uint8_t)(wv[i] >> 24); }
+            }
+        }
+        if (lane >= 28) {
+            const int i = lane - 28;
+            uint32_t wv = h.hold ? s_rowbytes[((h.hold - 1) * 4 + h.hold_r) * 4 + i] : 0x01010101u;
+            uint8_t* d = pix + (Hp - P + i) * RW + Wp;
             d[0] = (uint8_t)wv; d[1] = (uint8_t)(wv >> 8); d[2] = (uint8_t)(wv >> 16); d[3] = (uint8_t)(wv >> 24);
         }
         __syncwarp();
@@ -415,9 +510,27 @@ __global__ void __launch_bounds__(256) k_rgb(const DevCfg cfg, int64_t n, const 
             int c = (cells >> (4 * lane)) & 15;
             pix[(h.y + (c >> 2)) * RW + h.x + (c & 3)] = (uint8_t)(h.p + 2);
         }
+        // previous env's bulk store must have finished reading this warp's rgb buffer
+        if (lane == 0) bulk_wait_read();
         __syncwarp();
         uint8_t* g = img + (size_t)e * NP * 3;
-        if (fast) {
+        if (fast8 && tma) {
+            for (int q8 = lane; q8 < (NP >> 3); q8 += 32) {
+                const uint2 pv = ((const uint2*)pix)[q8];
+                const uint32_t t0 = (pv.x | (pv.x >> 4)) << 3, t1 = (pv.y | (pv.y >> 4)) << 3;
+                const uint2 A = *(const uint2*)((const uint8_t*)s_pair + (t0 & 0x7F8u));
+                const uint2 Bp = *(const uint2*)((const uint8_t*)s_pair + ((t0 >> 16) & 0x7F8u));
+                const uint2 C = *(const uint2*)((const uint8_t*)s_pair + (t1 & 0x7F8u));
+                const uint2 D = *(const uint2*)((const uint8_t*)s_pair + ((t1 >> 16) & 0x7F8u));
+                uint2* o = (uint2*)(rgb + 24 * q8);
+                o[0] = make_uint2(A.x, __byte_perm(A.y, Bp.x, 0x5410));
+                o[1] = make_uint2(__byte_perm(Bp.x, Bp.y, 0x5432), C.x);
+                o[2] = make_uint2(__byte_perm(C.y, D.x, 0x5410), __byte_perm(D.x, D.y, 0x5432));
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) { bulk_s2g(g, rgb, (uint32_t)(NP * 3)); bulk_commit(); }
+        } else if (fast4) {
             uint32_t* o = tma ? (uint32_t*)rgb : (uint32_t*)g;
             for (int q4 = lane; q4 < NP / 4; q4 += 32) {
                 uint32_t pv = ((const uint32_t*)pix)[q4];
@@ -438,6 +551,7 @@ __global__ void __launch_bounds__(256) k_rgb(const DevCfg cfg, int64_t n, const 
     }
     if (lane == 0) bulk_wait_all();
 }
+
 
 }  // namespace tg
 
@@ -462,10 +576,14 @@ extern "C" int tg_render_rgb(tg_env* env, tg_state st, int64_t n, uint8_t* d_img
     CUDA_TRY(env, cudaSetDevice(env->device));
     const DevCfg& d = env->dev;
     auto r128 = [](size_t v) { return (int)((v + 127) / 128 * 128); };
-    int rec_bytes = r128((size_t)d.board_stride + 16), pix_bytes = r128((size_t)d.Hp * d.rgb_w + 16), rgb_bytes = r128((size_t)d.Hp * d.rgb_w * 3);
-    size_t per_warp = (size_t)rec_bytes + pix_bytes + rgb_bytes;
-    int nw = 8;
-    while (nw > 1 && per_warp * nw > 72 * 1024) nw >>= 1;
+    int rec_bytes = r128((size_t)d.board_stride + 48), pix_bytes = r128((size_t)d.Hp * d.rgb_w + 16), rgb_bytes = r128((size_t)d.Hp * d.rgb_w * 3);
+    size_t per_warp = (size_t)2 * rec_bytes + pix_bytes + rgb_bytes;
+    int nw = 8, best = 0;
+    for (int c = 8; c >= 1; c >>= 1) {   // warps per CTA that keeps the most warps resident (227 KB shared memory, <= 24 warps by registers)
+        int resident = (int)((227 * 1024) / (per_warp * c + 4096)) * c;
+        if (resident > 24) resident = 24;
+        if (resident > best) { best = resident; nw = c; }
+    }
     size_t smem = per_warp * nw;
     if (smem > 227 * 1024) return fail(env, TG_ERR_CONFIG, "tg_render_rgb: image too large for shared memory");
     int T = nw * 32;
@@ -500,18 +618,27 @@ static int launch_grouped_observe(tg_env* env, tg_state st, int64_t n, uint8_t* 
     }
     const bool stream_ok = d_boards && (d.OB & 15) == 0 && (((uintptr_t)d_boards) & 15) == 0 && d.OB <= 4 * 32 * 16 && !getenv("TG_BOARDS_V1");
     if (stream_ok) {
-        const int T = 256, nw = T / 32;
         const int NV = (d.OB / 16 + 31) / 32;
         auto r128 = [](size_t v) { return (int)((v + 127) / 128 * 128); };
-        const int rec_bytes = r128((size_t)d.board_stride + 16), img_bytes = r128((size_t)d.OB);
-        const size_t smem = (size_t)nw * (rec_bytes + 2 * img_bytes);
+        int G = 8;                                   // placements per bulk store: largest power of two with G * OB <= 5 KB
+        while (G > 1 && G * d.OB > 5120) G >>= 1;
+        const int rec_bytes = r128((size_t)d.board_stride + 32), img_bytes = r128((size_t)d.OB), gbuf_bytes = r128((size_t)G * d.OB);
+        const size_t per_warp = (size_t)2 * rec_bytes + img_bytes + 512 + 2 * (size_t)gbuf_bytes;
+        int nw = 8, best = 0;
+        for (int c = 8; c >= 2; c >>= 1) {           // warps per CTA that keeps the most warps resident
+            int resident = (int)((227 * 1024) / (per_warp * c + 2048)) * c;
+            if (resident > 24) resident = 24;
+            if (resident > best) { best = resident; nw = c; }
+        }
+        const int T = nw * 32;
+        const size_t smem = (size_t)nw * per_warp;
         auto launch = [&](auto kern) -> int {
             CUDA_TRY(env, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             int per_sm = 1;
             CUDA_TRY(env, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, T, smem));
             int64_t blocks = (n + nw - 1) / nw, cap = (int64_t)env->num_sms * (per_sm > 0 ? per_sm : 1);
             if (blocks > cap) blocks = cap;
-            kern<<<(unsigned)blocks, T, smem, s>>>(d, n, (const uint8_t*)st.hot, (const uint8_t*)st.board, d_boards, d_legal, fill_high, rec_bytes, img_bytes);
+            kern<<<(unsigned)blocks, T, smem, s>>>(d, n, (const uint8_t*)st.hot, (const uint8_t*)st.board, d_boards, d_legal, fill_high, rec_bytes, img_bytes, G, gbuf_bytes);
             CUDA_TRY(env, cudaGetLastError());
             return TG_OK;
         };
