@@ -83,16 +83,20 @@ def c3_grouped(out):
              "placements_per_s": n * A / dt_env, "with_action_sampling_env_steps_per_s": n / dt_all,
              "GBps": bps * n / dt_env / 1e9, "frac_of_hbm_peak": bps * n / dt_env / 1e9 / PEAK})
         base.close()
-    n = 65536
-    base = Tetris(num_envs=n, gravity=False, queue_size=4)
-    env = GroupedActionsObservations(base)
-    env.reset(seed=42)
-    a = torch.zeros(n, dtype=torch.int32, device="cuda") + 17
-    dt = timed(lambda i=0: env.step(a), 20)
-    bps = 40 * 432 + 944 + 500
-    out({"config": "C3b grouped boards 10x20 (no wrappers)", "envs": n, "ms": dt * 1e3, "env_steps_per_s": n / dt,
-         "placements_per_s": n * 40 / dt, "GBps": bps * n / dt / 1e9, "frac_of_hbm_peak": bps * n / dt / 1e9 / PEAK})
-    base.close()
+    for n, kw, name in ((65536, dict(queue_size=4), "10x20"), (262144, dict(queue_size=4), "10x20"),
+                        (32768, dict(width=20, height=40, queue_size=5), "20x40")):
+        base = Tetris(num_envs=n, gravity=False, **kw)
+        env = GroupedActionsObservations(base)
+        env.reset(seed=42)
+        a = torch.zeros(n, dtype=torch.int32, device="cuda") + 17
+        dt = timed(lambda i=0: env.step(a), 20)
+        lay = base.layout
+        A = lay.n_placements
+        # placement images + legal mask written; state read + written by the placement step; obs dict of the step
+        bps = A * lay.obs_board_bytes + A + 2 * (lay.hot_stride + lay.board_stride) + lay.board_stride + lay.rng_stride + 2 * lay.obs_board_bytes + 16 + lay.obs_queue_bytes + 14
+        out({"config": f"C3b grouped boards {name} (no wrappers)", "envs": n, "ms": dt * 1e3, "env_steps_per_s": n / dt,
+             "placements_per_s": n * A / dt, "GBps": bps * n / dt / 1e9, "frac_of_hbm_peak": bps * n / dt / 1e9 / PEAK})
+        base.close()
 
 
 def c4_rollout(out):

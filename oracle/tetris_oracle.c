@@ -56,7 +56,7 @@ typedef struct {
     orc_piece held;
     int has_swapped, game_over;
     /* randomizer: scripted stream or numpy-exact 7-bag */
-    int rng_mode; /* 0 scripted, 1 numpy PCG64 bag */
+    int rng_mode; /* 0 scripted, 1 numpy PCG64 bag, 2 numpy PCG64 TrueRandomizer */
     const uint8_t *seq;
     int64_t seq_len, seq_cur;
     int8_t bag[7];
@@ -153,8 +153,27 @@ static void shuffle_bag(orc_env *e) {
     }
     e->bag_index = 0;
 }
+/* numpy Generator.integers(0, n) for a scalar draw (numpy/random/_bounded_integers.pyx: _rand_int64 ->
+ * random_bounded_uint64_fill -> buffered_bounded_lemire_uint32, distributions.c): Lemire's
+ * multiply-shift with rejection on next_uint32.  Third-party arithmetic (numpy, poetry.lock pin 2.2.4);
+ * pinned against numpy itself in tests/test_oracle_golden.py::test_numpy_true_randomizer_stream. */
+static uint32_t np_bounded_lemire32(orc_env *e, uint32_t rng) {
+    const uint32_t rng_excl = rng + 1;
+    uint64_t m = (uint64_t)pcg64_next32(e) * rng_excl;
+    uint32_t leftover = (uint32_t)m;
+    if (leftover < rng_excl) {
+        const uint32_t threshold = (0xFFFFFFFFu - rng) % rng_excl;
+        while (leftover < threshold) {
+            m = (uint64_t)pcg64_next32(e) * rng_excl;
+            leftover = (uint32_t)m;
+        }
+    }
+    return (uint32_t)(m >> 32);
+}
 /* Randomizer.get_next_tetromino */
 static int rnd_next(orc_env *e) {
+    /* TrueRandomizer.get_next_tetromino (components/tetromino_randomizer.py:119-121): rng.integers(0, size) */
+    if (e->rng_mode == 2) return (int)np_bounded_lemire32(e, 6);
     if (e->rng_mode == 0) { /* scripted stream (test injection hook) */
         int v = e->seq[e->seq_cur % e->seq_len];
         e->seq_cur++;
@@ -169,7 +188,7 @@ static int rnd_next(orc_env *e) {
 /* BagRandomizer.reset (components/tetromino_randomizer.py:87-91); the reseed itself
  * (Randomizer.reset :34-46, "if seed and seed > 0") is done by the caller via orc_seed_numpy. */
 static void rnd_reset(orc_env *e) {
-    if (e->rng_mode == 0) return;
+    if (e->rng_mode != 1) return; /* scripted; TrueRandomizer.reset only reseeds (:123-127) */
     for (int i = 0; i < 7; i++) e->bag[i] = (int8_t)i;
     shuffle_bag(e);
 }
@@ -306,8 +325,9 @@ void orc_set_sequence(orc_env *e, const uint8_t *seq, int64_t len, int64_t curso
     e->seq_cur = cursor;
 }
 /* numpy-exact 7-bag: st = {state_hi, state_lo, inc_hi, inc_lo} of PCG64(SeedSequence(seed)) */
+void orc_set_true_randomizer(orc_env *e, int on) { e->rng_mode = on ? 2 : 1; }
 void orc_seed_numpy(orc_env *e, const uint64_t *st) {
-    e->rng_mode = 1;
+    if (e->rng_mode == 0) e->rng_mode = 1;
     e->pcg_state_hi = st[0];
     e->pcg_state_lo = st[1];
     e->pcg_inc_hi = st[2];

@@ -38,7 +38,7 @@ def lib():
             "orc_destroy orc_set_sequence orc_seed_numpy orc_get_obs orc_reset orc_features "
             "orc_grouped_observe orc_rgb orc_get_board orc_set_board orc_get_scalars "
             "orc_get_active_matrix orc_get_held_matrix orc_set_active orc_set_flags orc_set_holder "
-            "orc_set_queue orc_vec_step orc_vec_grouped_step orc_rnd_stream orc_grouped_observe_ex"
+            "orc_set_queue orc_vec_step orc_vec_grouped_step orc_rnd_stream orc_grouped_observe_ex orc_set_true_randomizer"
         ).split():
             getattr(L, name).restype = None
         L.orc_step.restype = C.c_int
@@ -98,6 +98,10 @@ class OracleEnv:
     def set_sequence(self, seq, cursor=0):
         self._seq = np.ascontiguousarray(seq, dtype=np.uint8)
         lib().orc_set_sequence(self.h, _p(self._seq), C.c_int64(len(self._seq)), C.c_int64(cursor))
+
+    def set_true_randomizer(self, on=True):
+        """TrueRandomizer (components/tetromino_randomizer.py:105-136) instead of the 7-bag; call before seed_numpy."""
+        lib().orc_set_true_randomizer(self.h, int(on))
 
     def seed_numpy(self, seed):
         st = numpy_pcg64_state(seed)

@@ -137,3 +137,17 @@ def test_numpy_bag_stream():
             assert want[:70] == [int(v) for v in k["seed42_stream"]]
     st = numpy_pcg64_state(42)
     assert st.dtype == np.uint64 and st.shape == (4,)
+
+
+def test_numpy_true_randomizer_stream():
+    """TrueRandomizer (components/tetromino_randomizer.py:105-136): `rng.integers(0, 7)` per draw.  The Lemire
+    bounded-integer restatement (buffered next_uint32 halves of PCG64) == numpy's own Generator.integers stream,
+    also when interleaved with nothing else (reset only reseeds)."""
+    for seed in (42, 1, 7, 2**31 - 1, 123456789):
+        rng = np.random.default_rng(seed)
+        want = [int(rng.integers(0, 7)) for _ in range(2000)]
+        env = OracleEnv()
+        env.set_true_randomizer()
+        env.seed_numpy(seed)
+        assert [int(v) for v in env.rnd_stream(2000)] == want
+    assert len(set(want)) == 7

@@ -28,6 +28,7 @@ struct tg_env {
     int threads_per_env;  // CTA threads = tile * threads_per_env (logic uses one thread per env, image fill uses all)
     int warp_specialized; // 1: k_step_ws (logic warp runs a tile ahead of the image warps)
     int fill_warps;       // image/store warps per CTA of k_step_ws
+    int logic_warps;      // game-logic warps per CTA of k_step_ws (each runs every logic_warps-th tile of the CTA)
     void* rollout_last_action;
     std::string err;
     // tg_step_host staging
@@ -180,9 +181,12 @@ extern "C" int tg_create(const tg_config* cfg, int device, tg_env** out) {
     if (const char* t = getenv("TG_TILE")) { int v = atoi(t); if (v == 32 || v == 64 || v == 96 || v == 128) env->tile = v; }
     if (const char* t = getenv("TG_TPE")) { int v = atoi(t); if (v >= 1 && v <= 8) env->threads_per_env = v; }
     env->warp_specialized = 1;
-    env->fill_warps = 3;
+    env->fill_warps = 4;
     if (const char* t = getenv("TG_WS")) env->warp_specialized = atoi(t) != 0;
-    if (const char* t = getenv("TG_NF")) { int v = atoi(t); if (v >= 1 && v <= 7) env->fill_warps = v; }
+    env->logic_warps = 2;
+    if (const char* t = getenv("TG_NF")) { int v = atoi(t); if (v >= 1 && v <= 6) env->fill_warps = v; }
+    if (const char* t = getenv("TG_NL")) { int v = atoi(t); if (v >= 1 && v <= 4) env->logic_warps = v; }
+    if (env->logic_warps + env->fill_warps > 8) env->fill_warps = 8 - env->logic_warps;
     int rc = upload_tables(env);
     if (rc != TG_OK) { g_create_err = env->err; delete env; return rc; }
     *out = env;
@@ -232,12 +236,14 @@ static int launch_step(tg_env* env, StepParams& p, cudaStream_t s, int force_pla
     const DevCfg& d = env->dev;
     const bool ws = env->warp_specialized && !force_plain;
     int E = ws ? 32 : env->tile;
-    const int NS = ws ? 3 : 2;
+    int NL = ws ? env->logic_warps : 0;
+    int NS = ws ? NL + 2 : 2;
     // shared-memory carve-up
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 127) / 128 * 128; return (int)o; };
     for (;;) {
         off = 0;
+        NS = ws ? NL + 2 : 2;
         p.st_hot = (int)(((size_t)E * 32 + 127) / 128 * 128);
         p.st_brd = (int)(((size_t)E * d.board_stride + 16 + 127) / 128 * 128);
         p.st_rng = (int)(((size_t)E * d.rng_stride + 127) / 128 * 128);
@@ -251,6 +257,8 @@ static int launch_step(tg_env* env, StepParams& p, cudaStream_t s, int force_pla
         p.off_bar = take(32);
         p.off_box = take((size_t)(2 * NS + 1) * E * 4);
         p.off_tab = take(112 * 4 + 64 + 32);
+        // large boards: fewer logic warps (= fewer state stages) while that buys another resident CTA
+        if (ws && NL > 1 && (227 * 1024) / (off + 1024) < 2) { NL--; continue; }
         if (off <= 100 * 1024 || E == 32) break;
         E -= 32;
     }
@@ -260,7 +268,8 @@ static int launch_step(tg_env* env, StepParams& p, cudaStream_t s, int force_pla
     }
     p.cfg = d;
     p.E = E;
-    int T = ws ? 32 * (1 + env->fill_warps) : E * env->threads_per_env;
+    p.NL = NL;
+    int T = ws ? 32 * (NL + env->fill_warps) : E * env->threads_per_env;
     if (T > 256) T = 256;
     if (d.W == 10 && d.H == 20) return launch_step_t<10, 20, uint32_t>(env, p, T, off, ws, s);
     if (d.W == 20 && d.H == 40) return launch_step_t<20, 40, uint64_t>(env, p, T, off, ws, s);

@@ -73,6 +73,7 @@ struct StepParams {
     uint8_t* fill_high;              // grouped mode: u8[n], 1 = illegal action terminated the episode
     int mode;                        // 0 = step, 1 = reset, 2 = grouped placement step
     int E;                           // envs per tile
+    int NL;                          // k_step_ws: logic warps per CTA (state stages = NL + 2)
     // shared-memory carve-up (bytes from the 128-aligned base)
     int off_hot, off_brd, off_rng, off_iboard, off_imask, off_iholder, off_iqueue, off_bar, off_box, off_tab;
     int st_hot, st_brd, st_rng;      // bytes between the two pipeline stages of each state buffer
@@ -463,12 +464,14 @@ template <int WT, int HT, class COLT>
 __global__ void __launch_bounds__(256) k_step_ws(const __grid_constant__ StepParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const DevCfg& cfg = p.cfg;
-    constexpr int E = 32, NS = 3;
+    constexpr int E = 32;
+    const int NL = p.NL, NS = p.NL + 2;             // logic warps; state stages in flight
     const int T = blockDim.x, tid = threadIdx.x;
-    const int FT = T - 32, ft = tid - 32;           // fill threads
+    const int FT = T - 32 * NL, ft = tid - 32 * NL; // fill threads
     const int W = WT ? WT : cfg.W, H = HT ? HT : cfg.H;
     const int Wp = W + 2 * P, Hp = H + P;
     const int OB = Hp * Wp, OQ = cfg.OQ, BS = cfg.board_stride, RS = cfg.rng_stride;
+    const int BAR_FILL = 1 + NS;                    // named barriers: 1 + s = ready[s], 1 + NS = fill warps only
 
     uint8_t* i_board = smem + p.off_iboard;
     uint8_t* i_mask = smem + p.off_imask;
@@ -492,6 +495,7 @@ __global__ void __launch_bounds__(256) k_step_ws(const __grid_constant__ StepPar
     init_cta(E, W, H, s_rowbytes, s_cells, s_n, i_board, i_mask, tid, T);
 
     const int64_t ntiles = (p.n + E - 1) / E;
+    const int64_t G = gridDim.x;
     const bool want_obs = p.o_board != nullptr;
     auto issue_load = [&](int64_t tile, int s) {
         const int64_t base = tile * E;
@@ -501,30 +505,31 @@ __global__ void __launch_bounds__(256) k_step_ws(const __grid_constant__ StepPar
         bulk_g2s(smem + p.off_brd + s * p.st_brd, p.board + base * BS, (uint32_t)(nv * BS), bar + s);
         bulk_g2s(smem + p.off_rng + s * p.st_rng, p.rng + base * RS, (uint32_t)(nv * RS), bar + s);
     };
-    if (tid == 32) {   // the fill leader owns all TMA traffic
-        if ((int64_t)blockIdx.x < ntiles) issue_load(blockIdx.x, 0);
-        if ((int64_t)blockIdx.x + gridDim.x < ntiles) issue_load((int64_t)blockIdx.x + gridDim.x, 1);
+    if (ft == 0) {   // the fill leader owns all TMA traffic: tiles 0 .. NS-2 of this CTA go to stages 0 .. NS-2
+        for (int j = 0; j < NS - 1; j++)
+            if ((int64_t)blockIdx.x + j * G < ntiles) issue_load((int64_t)blockIdx.x + j * G, j);
     }
     __syncthreads();
 
-    if (tid < 32) {
-        // ===== logic warp =====
+    if (tid < 32 * NL) {
+        // ===== logic warps: warp lw runs the game logic of this CTA's tiles k = lw, lw + NL, ... (lane = env) =====
+        const int lw = tid >> 5, lane = tid & 31;
         TileStats st = {0, 0, 0, 0};
-        int k = 0;
-        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, k++) {
-            const int s = k % NS;
+        for (int64_t k = lw; blockIdx.x + k * G < ntiles; k += NL) {
+            const int64_t tile = blockIdx.x + k * G;
+            const int s = (int)(k % NS);
             const int64_t base = tile * E;
             const int nv = (int)min((int64_t)E, p.n - base);
             int action = 0;
-            if (p.mode != 1 && tid < nv) action = p.actions[base + tid];
+            if (p.mode != 1 && lane < nv) action = p.actions[base + lane];
             mbar_wait(bar + s, (uint32_t)((k / NS) & 1));
             uint32_t dirty = 0;
-            if (tid < nv)
-                dirty = logic_one_env<COLT>(p, tb, base + tid, tid, action, (uint32_t*)(smem + p.off_hot + s * p.st_hot),
+            if (lane < nv)
+                dirty = logic_one_env<COLT>(p, tb, base + lane, lane, action, (uint32_t*)(smem + p.off_hot + s * p.st_hot),
                                             smem + p.off_brd + s * p.st_brd, smem + p.off_rng + s * p.st_rng, s_boxes + s * E, st);
-            s_flags[s * E + tid] = dirty;
+            s_flags[s * E + lane] = dirty;
             __syncwarp();
-            named_arrive(1 + s, T);   // ready[s]: the fill warps may consume stage s
+            named_arrive(1 + s, 32 + FT);   // ready[s]: the fill warps may consume stage s
         }
         if (p.stats) {
             for (int o = 16; o > 0; o >>= 1) {
@@ -533,7 +538,7 @@ __global__ void __launch_bounds__(256) k_step_ws(const __grid_constant__ StepPar
                 st.len += __shfl_xor_sync(0xffffffffu, st.len, o);
                 st.lines += __shfl_xor_sync(0xffffffffu, st.lines, o);
             }
-            if (tid == 0 && st.ep > 0) {
+            if (lane == 0 && st.ep > 0) {
                 atomicAdd(p.stats + 0, st.ep); atomicAdd(p.stats + 1, st.ret);
                 atomicAdd(p.stats + 2, st.len); atomicAdd(p.stats + 3, st.lines);
             }
@@ -541,29 +546,29 @@ __global__ void __launch_bounds__(256) k_step_ws(const __grid_constant__ StepPar
     } else {
         // ===== image / store warps =====
         const bool leader = (ft == 0);
-        int nv_prev = 0, k = 0;
-        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, k++) {
-            const int s = k % NS;
+        int nv_prev = 0, s = 0;
+        for (int64_t k = 0; blockIdx.x + k * G < ntiles; k++, s = (s + 1 == NS ? 0 : s + 1)) {
+            const int64_t tile = blockIdx.x + k * G;
             const int64_t base = tile * E;
             const int nv = (int)min((int64_t)E, p.n - base);
             uint32_t* s_hot = (uint32_t*)(smem + p.off_hot + s * p.st_hot);
             uint8_t* s_brd = smem + p.off_brd + s * p.st_brd;
             uint8_t* s_rng = smem + p.off_rng + s * p.st_rng;
-            named_sync(1 + s, T);                       // logic of this tile is done, stage s is final
+            named_sync(1 + s, 32 + FT);                 // logic of this tile is done, stage s is final
             mbar_wait(bar + s, (uint32_t)((k / NS) & 1));   // (already complete) acquire the TMA writes
             bulk_wait_read();                           // stores of the previous tile have left shared memory
-            named_sync(4, FT);
-            // stage (k+2)%NS == (k-1)%NS is free again: prefetch two tiles ahead
-            if (leader && tile + 2 * (int64_t)gridDim.x < ntiles) issue_load(tile + 2 * (int64_t)gridDim.x, (k + 2) % NS);
+            named_sync(BAR_FILL, FT);
+            // the stage of tile k-1 is free again: prefetch NS-1 tiles ahead into it
+            if (leader && tile + (NS - 1) * G < ntiles) issue_load(tile + (NS - 1) * G, s == 0 ? NS - 1 : s - 1);
             if (want_obs) {
                 mask_clear_boxes(s_boxprev, nv_prev, i_mask, OB, Wp, ft, FT);
                 fill_images<WT, HT>(cfg, nv, s_hot, s_brd, s_rowbytes, i_board, i_holder, i_queue, ft, FT);
-                named_sync(4, FT);
+                named_sync(BAR_FILL, FT);
                 mask_set_and_overlay(s_boxes + s * E, nv, s_cells, i_board, i_mask, OB, Wp, ft, FT);
                 for (int i = ft; i < nv; i += FT) s_boxprev[i] = s_boxes[s * E + i];
             }
             fence_async_smem();
-            named_sync(4, FT);
+            named_sync(BAR_FILL, FT);
             if (want_obs) {
                 tile_store(p.o_board + base * OB, i_board, (uint32_t)(nv * OB), leader, ft, FT);
                 tile_store(p.o_mask + base * OB, i_mask, (uint32_t)(nv * OB), leader, ft, FT);

@@ -57,6 +57,54 @@ __global__ void k_ctabulk(uint8_t* out, size_t ntiles, int piece) {
     }
 }
 
+
+// traffic of the per-call step kernel without any compute: per tile of 32 envs TMA-load hot (1 KB) + board records (4.6 KB) +
+// rng (512 B), TMA-store board image + mask image (13.8 KB each) + queue (3.5 KB) + holder (512 B) + hot (1 KB), and for a
+// fraction of the envs a 144-byte board record.  One thread per CTA drives everything; 2 load stages; `sets` image sets.
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile("{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__global__ void k_mimic(uint8_t* hot, uint8_t* brd, uint8_t* rng, uint8_t* ob, uint8_t* om, uint8_t* oq, uint8_t* oh, size_t ntiles, int sets, int commit_pct) {
+    extern __shared__ __align__(128) uint8_t sm[];
+    uint64_t* bar = (uint64_t*)sm;              // 2 barriers
+    uint8_t* stage = sm + 128;                  // 2 x 6272
+    uint8_t* img = stage + 2 * 6272;            // sets x 31744
+    if (threadIdx.x == 0) { mbar_init(bar, 1); mbar_init(bar + 1, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    auto load = [&](size_t t, int s) {
+        mbar_expect_tx(bar + s, 1024 + 4608 + 512);
+        bulk_g2s(stage + s * 6272, hot + t * 1024, 1024, bar + s);
+        bulk_g2s(stage + s * 6272 + 1024, brd + t * 4608, 4608, bar + s);
+        bulk_g2s(stage + s * 6272 + 5632, rng + t * 512, 512, bar + s);
+    };
+    if (blockIdx.x < ntiles) load(blockIdx.x, 0);
+    size_t k = 0;
+    for (size_t t = blockIdx.x; t < ntiles; t += gridDim.x, k++) {
+        int s = k & 1;
+        if (t + gridDim.x < ntiles) load(t + gridDim.x, s ^ 1);
+        mbar_wait(bar + s, (k >> 1) & 1);
+        uint8_t* im = img + (k % sets) * 31744;
+        if (sets == 1) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        else if (sets == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        else asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
+        bulk_s2g(ob + t * 13824, im, 13824);
+        bulk_s2g(om + t * 13824, im + 13824, 13824);
+        bulk_s2g(oq + t * 3584, im + 27648, 3584);
+        bulk_s2g(oh + t * 512, im + 31232, 512);
+        bulk_s2g(hot + t * 1024, stage + s * 6272, 1024);
+        for (int e = 0; e < 32; e++)
+            if ((int)((t * 32 + e) * 2654435761u % 100u) < commit_pct) bulk_s2g(brd + (t * 32 + e) * 144, stage + s * 6272 + 1024 + e * 144, 144);
+        bulk_commit();
+    }
+    bulk_wait_all();
+}
+
 template <class F> static float timeit(F f, int iters = 10) {
     cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
     f(); f(); cudaDeviceSynchronize();
@@ -100,6 +148,20 @@ int main() {
         if ((size_t)piece * per_sm > 200 * 1024) continue;
         ms = timeit([&] { k_ctabulk<<<sms * per_sm, 128, piece>>>(d, nt, piece); });
         printf("CTA tile TMA %6d B, %d CTA/SM   %7.0f GB/s\n", piece, per_sm, nt * (size_t)piece / ms / 1e6);
+    }
+    {
+        const size_t nenv = (size_t)1 << 22, nt = nenv / 32;
+        uint8_t *hot, *brd, *rng, *ob, *om, *oq, *oh;
+        cudaMalloc(&hot, nenv * 32); cudaMalloc(&brd, nenv * 144); cudaMalloc(&rng, nenv * 16);
+        cudaMalloc(&ob, nenv * 432); cudaMalloc(&om, nenv * 432); cudaMalloc(&oq, nenv * 112); cudaMalloc(&oh, nenv * 16);
+        cudaFuncSetAttribute(k_mimic, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        for (int sets : {1, 2, 3}) for (int per_sm : {2, 3, 4, 6}) for (int cp : {0, 21}) {
+            size_t smem = 128 + 2 * 6272 + (size_t)sets * 31744;
+            if (smem * per_sm > 220 * 1024) continue;
+            ms = timeit([&] { k_mimic<<<sms * per_sm, 32, smem>>>(hot, brd, rng, ob, om, oq, oh, nt, sets, cp); });
+            double bytes_env = 32 + 144 + 16 + 432 * 2 + 112 + 16 + 32 + 1.44 * cp;
+            printf("step-traffic mimic: %d image set(s), %d CTA/SM, commit %2d%%:  %6.2f G env/s  %7.0f GB/s\n", sets, per_sm, cp, nenv / ms / 1e6, nenv * bytes_env / ms / 1e6);
+        }
     }
     return 0;
 }
