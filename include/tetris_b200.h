@@ -55,6 +55,11 @@ enum {
                             reshuffle (components/tetromino_randomizer.py:67-91) */
 };
 
+/* randomizer kind (components/tetromino_randomizer.py): BagRandomizer :49-102 | TrueRandomizer :105-136
+ * (`rng.integers(0, 7)` per draw; with TG_RNG_NUMPY bit-exact through numpy's Lemire bounded integers on
+ * PCG64's buffered 32-bit halves, with TG_RNG_PHILOX one Philox4x32-10 block per draw) */
+enum { TG_RANDOMIZER_BAG = 0, TG_RANDOMIZER_TRUE = 1 };
+
 /* Constructor options of the reference env (envs/tetris.py:77-91) + mappings
  * (mappings/actions.py:12-19, mappings/rewards.py:12-15) + wrapper options. */
 typedef struct tg_config {
@@ -69,7 +74,7 @@ typedef struct tg_config {
      * (left,right,down,cw,ccw,swap,hard_drop,no_op; first match wins) is applied by the library. */
     int32_t action_map[8];
     int32_t terminate_on_illegal; /* GroupedActionsObservations(terminate_on_illegal_action) */
-    int32_t reserved0;
+    int32_t randomizer;   /* TG_RANDOMIZER_*: 7-bag (BagRandomizer, the reference default) or uniform (TrueRandomizer) */
     double reward_alife;          /* RewardsMapping.alife          (default 1)    */
     double reward_clear_line;     /* RewardsMapping.clear_line     (unused by the env, kept) */
     double reward_game_over;      /* RewardsMapping.game_over      (default 0)    */

@@ -26,7 +26,7 @@ def load():
         sys.path.insert(0, REF)
     import tetris_gymnasium.envs  # noqa: F401  (registers the env id)
     from tetris_gymnasium.components.tetromino_queue import TetrominoQueue
-    from tetris_gymnasium.components.tetromino_randomizer import Randomizer
+    from tetris_gymnasium.components.tetromino_randomizer import Randomizer, TrueRandomizer
     from tetris_gymnasium.envs.tetris import Tetris
     from tetris_gymnasium.wrappers.grouped import GroupedActionsObservations
     from tetris_gymnasium.wrappers.observation import FeatureVectorObservation, RgbObservation
@@ -47,15 +47,20 @@ def load():
         def reset(self, seed=None):
             pass
 
-    def make(width=10, height=20, gravity=True, queue_size=4, seq=None, **kw):
+    def make(width=10, height=20, gravity=True, queue_size=4, seq=None, true_random=False, **kw):
         env = Tetris(width=width, height=height, gravity=gravity, **kw)
-        if seq is not None:
+        if true_random:
+            # Tetris(randomizer=...) leaves self.randomizer unset (envs/tetris.py:138-141 only assigns the defaults),
+            # so the randomizer is swapped in after construction like the scripted one
+            env.randomizer = TrueRandomizer(len(env.tetrominoes))
+            env.queue = TetrominoQueue(env.randomizer, size=queue_size)
+        elif seq is not None:
             env.randomizer = Scripted(seq)
             env.queue = TetrominoQueue(env.randomizer, size=queue_size)
         elif queue_size != 4:
             env.queue = TetrominoQueue(env.randomizer, size=queue_size)
         return env
 
-    return dict(Tetris=Tetris, make=make, Scripted=Scripted, TetrominoQueue=TetrominoQueue,
+    return dict(Tetris=Tetris, make=make, Scripted=Scripted, TrueRandomizer=TrueRandomizer, TetrominoQueue=TetrominoQueue,
                 GroupedActionsObservations=GroupedActionsObservations,
                 FeatureVectorObservation=FeatureVectorObservation, RgbObservation=RgbObservation)

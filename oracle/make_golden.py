@@ -25,11 +25,13 @@ def record_base(R, name, width, height, gravity, queue_size, seeds, injected, ma
     eps = []
     for s in seeds:
         rng = np.random.default_rng(1000 + s)
-        seq = rng.integers(0, 7, size=256).astype(np.uint8) if injected else np.zeros(0, np.uint8)
-        env = R["make"](width=width, height=height, gravity=gravity, queue_size=queue_size, seq=seq if injected else None)
+        # injected: 0 = seeded numpy 7-bag, 1 = injected piece stream, 2 = seeded TrueRandomizer
+        seq = rng.integers(0, 7, size=256).astype(np.uint8) if injected == 1 else np.zeros(0, np.uint8)
+        env = R["make"](width=width, height=height, gravity=gravity, queue_size=queue_size, seq=seq if injected == 1 else None,
+                        true_random=injected == 2)
         rgbw = R["RgbObservation"](env)
         featw = R["FeatureVectorObservation"](env)
-        obs, _ = env.reset(seed=None if injected else s)
+        obs, _ = env.reset(seed=None if injected == 1 else s)
         rec = dict(board=[obs["board"]], mask=[obs["active_tetromino_mask"]], holder=[obs["holder"]], queue=[obs["queue"]],
                    reward=[], terminated=[], lines=[], actions=[], x=[env.x], y=[env.y], rgb=[], rgb_t=[], feat=[], locked=[env.board.copy()])
         rec["feat"].append(featw.observation({k: v.copy() for k, v in obs.items()}))
@@ -176,6 +178,7 @@ def main():
     n += record_base(R, "x_wide_q5", 20, 40, True, 5, [5, 6], injected=True, max_steps=1500, rgb_every=40)
     n += record_base(R, "odd_13x9_q3", 13, 9, True, 3, [8], injected=True, max_steps=400)
     n += record_o_script(R)
+    n += record_base(R, "d_true_randomizer", 10, 20, True, 4, [42, 9], injected=2, max_steps=900)
     g = 0
     g += record_grouped(R, "d_features_greedy", 10, 20, False, 4, [9, 10], True, 400, greedy=True)
     g += record_grouped(R, "x_features_greedy_q5", 20, 40, False, 5, [11], True, 250, greedy=True)
@@ -188,4 +191,8 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    import sys
+    if len(sys.argv) > 1 and sys.argv[1] == "true_randomizer":   # add just this fixture, leave the others untouched
+        print(record_base(_refload.load(), "d_true_randomizer", 10, 20, True, 4, [42, 9], injected=2, max_steps=900), "steps")
+    else:
+        main()

@@ -3,7 +3,7 @@
 Build-container tool (needs /root/reference); run as `python -m oracle.validate_against_reference`.
 It is also exercised by tests/test_oracle_vs_reference.py (skipped where the reference is absent).
 Covers: base env (all 8 actions, gravity on/off, holder, queue sizes 4/5/7, default and wide
-boards, seeded numpy 7-bag and injected streams, stepping after game over), the
+boards, seeded numpy 7-bag, seeded TrueRandomizer and injected streams, stepping after game over), the
 FeatureVector / Rgb wrappers on the base env, and GroupedActionsObservations (boards, features,
 legal mask, info["board"], illegal actions in both termination modes).
 """
@@ -19,14 +19,16 @@ def _same_obs(a, b):
     return all(np.array_equal(a[k], b[k]) and a[k].dtype == b[k].dtype for k in ("board", "active_tetromino_mask", "holder", "queue"))
 
 
-def check_base(ref, episodes, width, height, gravity, queue_size, seed0, injected, steps_after_over=3, max_steps=4000):
+def check_base(ref, episodes, width, height, gravity, queue_size, seed0, injected, steps_after_over=3, max_steps=4000, true_random=False):
     R = ref
     rng = np.random.default_rng(seed0)
     n_steps = 0
     for ep in range(episodes):
         seq = rng.integers(0, 7, size=512) if injected else None
-        env = R["make"](width=width, height=height, gravity=gravity, queue_size=queue_size, seq=seq)
+        env = R["make"](width=width, height=height, gravity=gravity, queue_size=queue_size, seq=seq, true_random=true_random)
         orc = OracleEnv(width=width, height=height, gravity=gravity, queue_size=queue_size)
+        if true_random:
+            orc.set_true_randomizer()
         rgbw = R["RgbObservation"](env)
         featw = R["FeatureVectorObservation"](env)
         if injected:
@@ -126,6 +128,8 @@ def run(scale=1):
     n += check_base(ref, 3 * scale, 20, 40, True, 5, 4, injected=True)
     n += check_base(ref, 3 * scale, 6, 8, True, 4, 5, injected=False)
     n += check_base(ref, 3 * scale, 13, 9, True, 3, 6, injected=True)
+    n += check_base(ref, 3 * scale, 10, 20, True, 4, 7, injected=False, true_random=True)
+    n += check_base(ref, 2 * scale, 10, 20, False, 7, 8, injected=False, true_random=True, max_steps=1200)
     g = 0
     g += check_grouped(ref, 4 * scale, 10, 20, False, 4, 11, True, True)
     g += check_grouped(ref, 3 * scale, 10, 20, False, 4, 12, False, False)

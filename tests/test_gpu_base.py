@@ -27,11 +27,11 @@ def test_golden_base_trajectories(path):
     W, H, gravity, Q, injected, _ = (int(v) for v in z["meta"])
     for ep in _episodes(z):
         kw = dict(width=W, height=H, gravity=bool(gravity), queue_size=Q, num_envs=1, autoreset_mode="disabled")
-        if injected:
+        if injected == 1:
             env = Tetris(randomizer_mode="sequence", piece_sequences=ep["seq"][None, :], **kw)
             obs, _ = env.reset()
-        else:
-            env = Tetris(randomizer_mode="numpy", **kw)
+        else:   # seeded numpy streams: 0 = 7-bag, 2 = TrueRandomizer
+            env = Tetris(randomizer_mode="numpy", randomizer="true" if injected == 2 else None, **kw)
             obs, _ = env.reset(seed=int(ep["seed"]))
         featw, rgbw = FeatureVectorObservation(env), RgbObservation(env, keep_obs_dict=True)
         rgb_at = {int(t): i for i, t in enumerate(ep["rgb_t"])} if "rgb_t" in ep else {}
@@ -293,3 +293,40 @@ def test_rgb_and_feature_wrappers_batched_vs_oracle(cfg):
         env.step(torch.from_numpy(a))
         o2, _, _, _ = orc.step(a)
     env.close()
+
+
+def test_true_randomizer_numpy_exact_and_philox():
+    """TrueRandomizer (components/tetromino_randomizer.py:105-136): randomizer_mode='numpy' reproduces
+    `default_rng(seed).integers(0, 7)` draw for draw (vs the oracle, itself pinned against numpy and the live reference);
+    the device-native Philox variant is uniform, replayable and independent of the shard layout."""
+    from tetris_gymnasium_b200.components import TetrominoQueue, TrueRandomizer
+    from tetris_gymnasium_b200.envs.tetris import Tetris
+    from gpu_util import OracleBatch, assert_obs_equal, np_
+
+    n = 200
+    r = TrueRandomizer(7)
+    env = Tetris(num_envs=n, randomizer_mode="numpy", queue=TetrominoQueue(r, size=5), autoreset_mode="next_step")
+    assert env.randomizer_kind == "true" and env.queue_size == 5
+    orc = OracleBatch(n, queue_size=5)
+    for i, e in enumerate(orc.envs):
+        e.set_true_randomizer()
+        e.seed_numpy(500 + i)
+    assert_obs_equal(env.reset(seed=500)[0], orc.reset(), "reset")
+    rng = np.random.default_rng(9)
+    for t in range(150):
+        a = rng.choice([0, 1, 3, 5, 5, 5, 6], size=n)
+        obs, rew, term, _, info = env.step(torch.from_numpy(a))
+        o2, r2, t2, l2 = orc.step(a)
+        assert_obs_equal(obs, o2, f"t={t}")
+        assert np.array_equal(np_(rew), r2) and np.array_equal(np_(term), t2)
+    # Philox: uniform pieces (no bag structure), same streams for the same (seed, global env id)
+    n = 4096
+    e1 = Tetris(num_envs=n, randomizer="true", queue_size=16, autoreset_mode="disabled")
+    e1.reset(seed=3)
+    q1 = np_(e1.get_state()["queue"])
+    counts = np.bincount(q1.ravel(), minlength=7)
+    assert counts.min() > 0.8 * q1.size / 7 and counts.max() < 1.2 * q1.size / 7
+    assert (np.sort(q1[:, :7], axis=1) != np.arange(7)).any(axis=1).mean() > 0.9   # not permutations of 0..6
+    e2 = Tetris(num_envs=n // 2, randomizer="true", queue_size=16, autoreset_mode="disabled", env_id_offset=n // 2)
+    e2.reset(seed=3)              # per-env seed = seed + global env id: same (seed, id) pairs as the second half of e1
+    assert np.array_equal(np_(e2.get_state()["queue"]), q1[n // 2:])

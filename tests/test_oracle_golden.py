@@ -24,10 +24,12 @@ def test_base_trajectories(path):
     W, H, gravity, Q, injected, _ = (int(v) for v in z["meta"])
     for ep in _episodes(z):
         env = OracleEnv(width=W, height=H, gravity=bool(gravity), queue_size=Q)
-        if injected:
+        if injected == 1:
             env.set_sequence(ep["seq"])
             obs, _ = env.reset()
         else:
+            if injected == 2:   # seeded TrueRandomizer
+                env.set_true_randomizer()
             obs, _ = env.reset(seed=int(ep["seed"]))
         T = len(ep["actions"])
         rgb_at = {int(t): i for i, t in enumerate(ep["rgb_t"])} if "rgb_t" in ep else {}

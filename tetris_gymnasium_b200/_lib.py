@@ -12,6 +12,7 @@ from . import _build
 TG_OK = 0
 AUTORESET = {"disabled": 0, "next_step": 1, "same_step": 2}
 RNG = {"philox": 0, "sequence": 1, "numpy": 2}
+RANDOMIZER = {"bag": 0, "true": 1}
 TG_SCALARS = 8
 
 
@@ -20,7 +21,7 @@ class TgConfig(C.Structure):
         ("width", C.c_int32), ("height", C.c_int32), ("queue_size", C.c_int32), ("gravity", C.c_int32),
         ("autoreset", C.c_int32), ("rng_mode", C.c_int32),
         ("action_map", C.c_int32 * 8),
-        ("terminate_on_illegal", C.c_int32), ("reserved0", C.c_int32),
+        ("terminate_on_illegal", C.c_int32), ("randomizer", C.c_int32),
         ("reward_alife", C.c_double), ("reward_clear_line", C.c_double),
         ("reward_game_over", C.c_double), ("reward_invalid_action", C.c_double),
         ("seq_len", C.c_int64), ("env_id_offset", C.c_uint64),

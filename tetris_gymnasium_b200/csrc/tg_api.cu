@@ -118,6 +118,7 @@ extern "C" int tg_create(const tg_config* cfg, int device, tg_env** out) {
     if (cfg->queue_size < 1 || cfg->queue_size > TG_MAX_QUEUE)
         return fail(nullptr, TG_ERR_CONFIG, "queue_size %d unsupported (1..16)", cfg->queue_size);
     if (cfg->rng_mode < 0 || cfg->rng_mode > 2) return fail(nullptr, TG_ERR_CONFIG, "rng_mode %d", cfg->rng_mode);
+    if (cfg->randomizer < 0 || cfg->randomizer > 1) return fail(nullptr, TG_ERR_CONFIG, "randomizer %d", cfg->randomizer);
     if (cfg->autoreset < 0 || cfg->autoreset > 2) return fail(nullptr, TG_ERR_CONFIG, "autoreset %d", cfg->autoreset);
     if (cfg->rng_mode == TG_RNG_SEQUENCE && cfg->seq_len < 1) return fail(nullptr, TG_ERR_CONFIG, "seq_len must be >= 1");
     for (int i = 0; i < 8; i++)
@@ -146,6 +147,7 @@ extern "C" int tg_create(const tg_config* cfg, int device, tg_env** out) {
     d.W = cfg->width; d.H = cfg->height; d.Wp = d.W + 2 * TG_PADDING; d.Hp = d.H + TG_PADDING; d.Q = cfg->queue_size;
     d.gravity = cfg->gravity != 0; d.autoreset = cfg->autoreset; d.rng_mode = cfg->rng_mode;
     d.terminate_on_illegal = cfg->terminate_on_illegal != 0;
+    d.rand_kind = cfg->randomizer;
     env->col64 = d.Hp > 32;
     int col_bytes = env->col64 ? 8 : 4;
     d.ids_off = d.W * col_bytes;

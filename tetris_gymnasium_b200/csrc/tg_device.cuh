@@ -28,6 +28,7 @@ enum Op : int { OP_LEFT = 0, OP_RIGHT, OP_DOWN, OP_CW, OP_CCW, OP_SWAP, OP_HARD,
 struct DevCfg {
     int W, H, Wp, Hp, Q;
     int gravity, autoreset, rng_mode, terminate_on_illegal;
+    int rand_kind;     // 0 = 7-bag, 1 = uniform (TrueRandomizer)
     int board_stride;  // bytes per env in state.board
     int ids_off;       // byte offset of the nibble id plane inside a board record
     int ids_words;     // u32 words of the id plane (ceil(H*W/8))
@@ -225,6 +226,25 @@ __device__ __forceinline__ int draw_piece(const DevCfg& cfg, Rng& g, Hot& h) {
         g.dirty = true;
         return g.seq[cur % (uint64_t)cfg.seq_len];
     }
+    if (cfg.rand_kind == 1) {
+        // TrueRandomizer.get_next_tetromino (components/tetromino_randomizer.py:119-121): rng.integers(0, 7)
+        g.dirty = true;
+        if (cfg.rng_mode == 2) {
+            // numpy: Lemire multiply-shift with rejection on next_uint32 (buffered_bounded_lemire_uint32, rng = 6)
+            uint64_t m = (uint64_t)pcg64_next32(g.rec) * 7u;
+            if ((uint32_t)m < 7u) {
+                const uint32_t threshold = (0xFFFFFFFFu - 6u) % 7u;
+                while ((uint32_t)m < threshold) m = (uint64_t)pcg64_next32(g.rec) * 7u;
+            }
+            return (int)(m >> 32);
+        }
+        uint64_t seed = ((uint64_t*)g.rec)[0];
+        uint32_t ctr = g.rec[2];
+        g.rec[2] = ctr + 1;
+        uint32_t c[4] = {ctr, (uint32_t)g.gid, (uint32_t)(g.gid >> 32), 2u};
+        philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+        return (int)__umulhi(c[0], 7u);
+    }
     // BagRandomizer.get_next_tetromino (components/tetromino_randomizer.py:67-80)
     int idx = (h.bag >> 28) & 7;
     int v = (h.bag >> (4 * idx)) & 15;
@@ -251,7 +271,7 @@ __device__ __forceinline__ void env_reset(const DevCfg& cfg, Hot& h, uint32_t* r
     for (int c = 0; c < cfg.W; c++) cols[c] = fl;
     for (int i = 0; i < cfg.ids_words; i++) ids[i] = 0;
     h.over = 0; h.pending = 0;
-    if (cfg.rng_mode != 1) h.bag = shuffle_bag(cfg, g, 0x06543210u);
+    if (cfg.rng_mode != 1 && cfg.rand_kind == 0) h.bag = shuffle_bag(cfg, g, 0x06543210u);   // TrueRandomizer.reset only reseeds
     h.queue = 0;
     for (int i = 0; i < cfg.Q; i++) h.queue |= (uint64_t)draw_piece(cfg, g, h) << (4 * i);
     h.p = queue_pop(cfg, g, h);

@@ -65,8 +65,10 @@ class Tetris:
       queue_size      visible queue length (reference TetrominoQueue default 4; EnvConfig.queue_size)
       padding         must be 4 (derived in the reference, EnvConfig field in the functional env)
       autoreset_mode  "next_step" (gymnasium 1.x vector default) | "same_step" | "disabled"
-      randomizer_mode "philox" (device-native 7-bag) | "numpy" (bit-exact BagRandomizer: PCG64 +
-                      Generator.shuffle) | "sequence" (injected piece streams, `piece_sequences`)
+      randomizer_mode "philox" (device-native streams) | "numpy" (bit-exact numpy streams: PCG64 +
+                      Generator.shuffle / Generator.integers) | "sequence" (injected piece streams, `piece_sequences`)
+      randomizer      None / "bag" / BagRandomizer = 7-bag (reference default); "true" / TrueRandomizer = uniform draws
+                      (components/tetromino_randomizer.py:105-136)
       env_id_offset   global id of env 0 (multi-GPU sharding keeps Philox streams independent of #GPUs)
     """
 
@@ -87,8 +89,17 @@ class Tetris:
             raise NotImplementedError("holder size > 1 is not supported yet (SURVEY 8 f4)")
         if queue is not None and queue_size is None:
             queue_size = int(getattr(queue, "size", queue))
-        if randomizer is not None and isinstance(randomizer, str):
-            randomizer_mode = randomizer
+        if randomizer is None and getattr(queue, "randomizer", None) is not None:
+            randomizer = queue.randomizer
+        self.randomizer_kind = "bag"
+        if randomizer is not None:
+            name = randomizer if isinstance(randomizer, str) else (getattr(randomizer, "kind", None) or type(randomizer).__name__)
+            if name in ("philox", "numpy", "sequence"):
+                randomizer_mode = name
+            elif name in ("true", "TrueRandomizer"):
+                self.randomizer_kind = "true"
+            elif name not in ("bag", "BagRandomizer"):
+                raise NotImplementedError(f"randomizer {name!r}: only the reference's BagRandomizer / TrueRandomizer are built in")
         if not torch.cuda.is_available():
             raise RuntimeError("tetris_gymnasium_b200 needs a CUDA device: there is no CPU fallback")
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
@@ -128,6 +139,7 @@ class Tetris:
         cfg.width, cfg.height, cfg.queue_size, cfg.gravity = self.width, self.height, self.queue_size, int(self.gravity_enabled)
         cfg.autoreset = _lib.AUTORESET[autoreset_mode]
         cfg.rng_mode = _lib.RNG[randomizer_mode]
+        cfg.randomizer = _lib.RANDOMIZER[self.randomizer_kind]
         for i, f in enumerate(fields(ActionsMapping)):
             cfg.action_map[i] = int(getattr(self.actions, f.name))
         cfg.terminate_on_illegal = int(bool(terminate_on_illegal_action))
