@@ -17,7 +17,7 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 from tetris_gymnasium_b200.envs.tetris import Tetris  # noqa: E402
-from tetris_gymnasium_b200.wrappers import FeatureVectorObservation, GroupedActionsObservations, RgbObservation  # noqa: E402
+from tetris_gymnasium_b200.wrappers import CnnObservation, FeatureVectorObservation, GroupedActionsObservations, RgbObservation  # noqa: E402
 
 PEAK = 6553.3
 try:
@@ -125,6 +125,19 @@ def c5_wide_rgb(out):
         bps = 2 * (lay.hot_stride + lay.board_stride * 1.0 + lay.rng_stride) + lay.hot_stride + 0.1 * lay.board_stride + img + 14
         out({"config": "C5 wide 20x40 q5 + RGB image obs", "envs": n, "image_bytes": img, "ms": dt * 1e3, "env_steps_per_s": n / dt,
              "GBps": bps * n / dt / 1e9, "frac_of_hbm_peak": bps * n / dt / 1e9 / PEAK})
+        base.close()
+    for n in (65536, 1 << 18):
+        base = Tetris(num_envs=n, width=20, height=40, queue_size=5)
+        env = CnnObservation(base, shape=(84, 84), stack_size=4, window=28, clip_reward=True)
+        env.reset(seed=42)
+        K = 50
+        acts = torch.randint(0, 8, (K + 3, n), dtype=torch.int32, device="cuda")
+        dt = timed(lambda i=0: env.step(acts[i]), K)
+        lay = base.layout
+        # state read+written by the step, state read by the adapter, one 84x84 frame written (+ 3/28 of a frame for the window slide)
+        bps = 2 * (lay.hot_stride + lay.board_stride * 1.0 + lay.rng_stride) + lay.hot_stride + 0.1 * lay.board_stride + 84 * 84 * (1 + 2 * 3 / 28) + 14
+        out({"config": "C5c wide 20x40 q5 + fused CNN obs (resize 84x84, grey, stack 4)", "envs": n, "frame_bytes": 84 * 84, "ms": dt * 1e3,
+             "env_steps_per_s": n / dt, "GBps": bps * n / dt / 1e9, "frac_of_hbm_peak": bps * n / dt / 1e9 / PEAK})
         base.close()
     base = Tetris(num_envs=1 << 18, width=20, height=40, queue_size=5)
     base.reset(seed=42)

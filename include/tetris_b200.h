@@ -171,6 +171,16 @@ int tg_features(tg_env *env, tg_state st, int64_t n, uint8_t *d_feats, void *str
 /* replaces RgbObservation.observation (wrappers/observation.py:38-74): u8[n][H_pad][rgb_width][3] */
 int tg_render_rgb(tg_env *env, tg_state st, int64_t n, uint8_t *d_img, void *stream);
 
+/* Fused image adapter of the CNN trainer (examples/train_cnn.py:127-147):
+ *     RgbObservation -> gym.wrappers.ResizeObservation((out_h, out_w)) -> gym.wrappers.GrayscaleObservation
+ * (cv2.resize INTER_AREA with an enlarged axis = OpenCV's fixed-point bilinear emulation; grey = floor of the float64
+ * weighted sum).  Writes the grey frame u8[out_h][out_w] of env i at d_frames + i * env_stride.  FrameStackObservation
+ * support: for envs with d_fill_mask[i] != 0 (just reset) the frame is also written to the `fill_count` preceding
+ * frames (d_frames + i * env_stride - k * out_h * out_w, k = 1..fill_count), so a caller that advances d_frames by one
+ * frame per step keeps a sliding stack window per env.  d_fill_mask may be NULL.  Not both axes may shrink. */
+int tg_cnn_observe(tg_env *env, tg_state st, int64_t n, int32_t out_h, int32_t out_w, uint8_t *d_frames,
+                   int64_t env_stride, const uint8_t *d_fill_mask, int32_t fill_count, void *stream);
+
 /* replaces GroupedActionsObservations.observation (wrappers/grouped.py:124-207):
  *   d_feats  : NULL or u8[n][4W][W+3]      (observation_wrappers=[FeatureVectorObservation])
  *   d_boards : NULL or u8[n][4W][H_pad][W_pad] (no observation wrappers)

@@ -48,7 +48,7 @@ class TgStepOut(C.Structure):
 
 EXPORTS = (
     "tg_create tg_destroy tg_get_layout tg_last_error tg_version tg_reset tg_seed_numpy tg_step tg_step_host "
-    "tg_features tg_render_rgb tg_grouped_observe tg_grouped_step tg_rollout tg_get_state tg_set_state tg_debug_set_rollout_trace tg_fn_step"
+    "tg_features tg_render_rgb tg_grouped_observe tg_grouped_step tg_rollout tg_get_state tg_set_state tg_debug_set_rollout_trace tg_fn_step tg_cnn_observe"
 ).split()
 
 _LIB = None
@@ -84,6 +84,7 @@ def load():
     L.tg_step_host.argtypes = [vp, TgState, i64, vp, TgObs, TgStepOut]
     L.tg_features.argtypes = [vp, TgState, i64, vp, vp]
     L.tg_render_rgb.argtypes = [vp, TgState, i64, vp, vp]
+    L.tg_cnn_observe.argtypes = [vp, TgState, i64, C.c_int32, C.c_int32, vp, i64, vp, C.c_int32, vp]
     L.tg_grouped_observe.argtypes = [vp, TgState, i64, vp, vp, vp, vp]
     L.tg_grouped_step.argtypes = [vp, TgState, i64, vp, vp, vp, vp, vp, TgObs, TgStepOut, vp, vp]
     L.tg_rollout.argtypes = [vp, TgState, i64, C.POINTER(C.c_int32), C.c_int32, vp, vp]

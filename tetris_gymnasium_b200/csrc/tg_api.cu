@@ -30,6 +30,7 @@ struct tg_env {
     int fill_warps;       // image/store warps per CTA of k_step_ws
     int logic_warps;      // game-logic warps per CTA of k_step_ws (each runs every logic_warps-th tile of the CTA)
     void* rollout_last_action;
+    int cnn_h, cnn_w;     // output size the tg_cnn_observe tables in stage[4] were built for
     std::string err;
     // tg_step_host staging
     cudaStream_t hs[3];
@@ -134,6 +135,7 @@ extern "C" int tg_create(const tg_config* cfg, int device, tg_env** out) {
     env->device = device;
     env->hs_init = false;
     env->rollout_last_action = nullptr;
+    env->cnn_h = env->cnn_w = 0;
     memset(env->stage, 0, sizeof env->stage);
     memset(env->stage_bytes, 0, sizeof env->stage_bytes);
     cudaError_t e1 = cudaSetDevice(device);
@@ -469,3 +471,4 @@ extern "C" int tg_fn_step(int32_t width, int32_t height, int32_t queue_size, int
 
 // ---- wrappers (tg_wrappers.cuh) ------------------------------------------------------------------------
 #include "tg_wrappers.cuh"
+#include "tg_cnn.cuh"

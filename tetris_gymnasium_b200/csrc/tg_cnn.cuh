@@ -1,0 +1,257 @@
+// tg_cnn.cuh -- fused image adapter of the CNN trainer (examples/train_cnn.py:127-147):
+//     RgbObservation -> gym.wrappers.ResizeObservation((OH, OW)) -> gym.wrappers.GrayscaleObservation
+// in ONE kernel: the RGB image never touches HBM, only the OH x OW grey frame (84 x 84 = 7 KB) is written, straight into
+// the caller's frame-stack window (FrameStackObservation: the reset frame is replicated over the window).
+//   * RgbObservation.observation            wrappers/observation.py:38-74 (id image -> colours)
+//   * ResizeObservation = cv2.resize(INTER_AREA); with an enlarged axis OpenCV emulates it by a bilinear kernel with
+//     `area_mode` coordinates, fixed point with 11-bit coefficients (imgproc/src/resize.cpp: HResizeLinear / VResizeLinear);
+//     offsets / coefficients are computed on the host exactly like cv::hal::resize (tg_api.cu: cnn_axis_tables)
+//   * GrayscaleObservation = floor(R * 0.2125 + G * 0.7154 + B * 0.0721) in float64, summed left to right
+// Third-party arithmetic (gymnasium 1.1.1, OpenCV): restated in oracle/cnn_obs_oracle.py and pinned against cv2 there.
+// One warp per env: record prefetch (cp.async) -> id image in shared memory -> per lane fixed output columns (source
+// offsets / coefficients in registers), horizontal pass kept in registers for the two live source rows, vertical pass +
+// grey conversion per output row -> frame in shared memory -> TMA bulk store(s).
+// Bound: integer issue (about 40 thread-instructions per output pixel), not HBM (7 KB written per env).
+#pragma once
+
+namespace tg {
+
+struct CnnParams {
+    DevCfg cfg;
+    int64_t n;
+    const uint8_t* hot; const uint8_t* board;
+    const int32_t* xtab;      // [OW][4]: sx0, sx1 (pixel offsets inside an image row), a0, a1
+    const int32_t* ytab;      // [OH][4]: sy0, sy1 (clamped source rows), b0, b1
+    const double* gray;       // [3][256]: v * 0.2125, v * 0.7154, v * 0.0721
+    uint8_t* frames;          // frame of env e at frames + e * env_stride
+    int64_t env_stride;
+    const uint8_t* fill_mask; // nullable: envs whose frame is replicated into the `fill_count` preceding frames
+    int fill_count;
+    int OH, OW;
+    int rec_bytes, pix_bytes, out_bytes;
+};
+
+template <class COLT, int NX>
+__global__ void __launch_bounds__(128) k_cnn_obs(const __grid_constant__ CnnParams p) {
+    extern __shared__ __align__(128) uint8_t sm[];
+    __shared__ uint32_t s_lut[16];
+    __shared__ uint32_t s_rowbytes[112];
+    __shared__ __align__(16) int4 s_y[128];
+    __shared__ __align__(8) double s_gray[3 * 256];
+    const DevCfg& cfg = p.cfg;
+    const int W = cfg.W, H = cfg.H, Wp = cfg.Wp, Hp = cfg.Hp, RW = cfg.rgb_w, Q = cfg.Q, BS = cfg.board_stride;
+    const int OH = p.OH, OW = p.OW, FB = OH * OW;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int NP = Hp * RW;
+    uint8_t* wbase = sm + (size_t)warp * (2 * p.rec_bytes + p.pix_bytes + p.out_bytes);
+    uint8_t* recbuf = wbase;
+    uint8_t* pix = wbase + 2 * p.rec_bytes;
+    uint8_t* out = pix + p.pix_bytes;
+    if (threadIdx.x < 16) s_lut[threadIdx.x] = ((const uint32_t*)c_colors)[threadIdx.x];
+    for (int i = threadIdx.x; i < 112; i += blockDim.x) s_rowbytes[i] = (&c_rowbytes[0][0][0])[i];
+    for (int i = threadIdx.x; i < OH; i += blockDim.x) s_y[i] = ((const int4*)p.ytab)[i];
+    for (int i = threadIdx.x; i < 768; i += blockDim.x) s_gray[i] = p.gray[i];
+    for (int i = lane; i < NP; i += 32) {   // constant part of the id image (see k_rgb)
+        int r = i / RW, c = i - r * RW;
+        pix[i] = (c < Wp && r < H && c >= P && c < P + W) ? 0 : 1;
+    }
+    for (int i = lane; i < 2 * p.rec_bytes / 4; i += 32) ((uint32_t*)recbuf)[i] = 0;
+    // this lane's output columns: dx = lane + 32 j
+    int sx0[NX], sx1[NX], a0[NX], a1[NX];
+#pragma unroll
+    for (int j = 0; j < NX; j++) {
+        const int dx = lane + 32 * j;
+        int4 t = dx < OW ? ((const int4*)p.xtab)[dx] : make_int4(0, 0, 0, 0);
+        sx0[j] = t.x; sx1[j] = t.y; a0[j] = t.z; a1[j] = t.w;
+    }
+    __syncthreads();
+    const bool tma = (FB & 15) == 0 && (((uintptr_t)p.frames) & 15) == 0 && (p.env_stride & 15) == 0;
+    const bool rows20 = W == 20 && (H & 1) == 0 && (RW & 3) == 0;
+    const int64_t stride = (int64_t)gridDim.x * nwarps;
+    int64_t e = (int64_t)blockIdx.x * nwarps + warp;
+    auto prefetch = [&](int64_t ee, uint8_t* dst) {
+        const uint8_t* src = p.board + ee * BS;
+        for (int i = lane; i < (BS >> 4); i += 32) cp_async16(dst + 16 * i, src + 16 * i);
+        if (lane < 2) cp_async16(dst + BS + 16 * lane, p.hot + ee * 32 + 16 * lane);
+        cp_async_commit();
+    };
+    if (e < p.n) prefetch(e, recbuf);
+    for (int it = 0; e < p.n; e += stride, it++) {
+        const uint32_t* rec = (const uint32_t*)(recbuf + (it & 1) * p.rec_bytes);
+        cp_async_wait_all();
+        __syncwarp();
+        if (e + stride < p.n) prefetch(e + stride, recbuf + ((it + 1) & 1) * p.rec_bytes);
+        Hot h;
+        hot_load(h, rec + (BS >> 2));
+        const COLT* cols = (const COLT*)rec;
+        const uint32_t* ids = rec + cfg.ids_off / 4;
+        // ---- id image (RgbObservation layout: board | queue top right, holder bottom right) ----
+        if (rows20) {
+            for (int g2 = lane; g2 < (H >> 1); g2 += 32)
+                fill_rows2_w20_strided(ids + 5 * g2, (uint32_t*)(pix + (2 * g2) * RW + P), (uint32_t*)(pix + (2 * g2 + 1) * RW + P));
+        } else {
+            for (int r = lane; r < H; r += 32) fill_board_row<0>(cfg, ids, pix, 0, r, RW);
+        }
+        for (int q = lane; q < Q; q += 32) {
+            const uint4 rb = *(const uint4*)(s_rowbytes + ((int)((h.queue >> (4 * q)) & 15u)) * 16);
+            const uint32_t wv[4] = {rb.x, rb.y, rb.z, rb.w};
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                uint8_t* d = pix + i * RW + Wp + 4 * q;
+                d[0] = (uint8_t)wv[i]; d[1] = (uint8_t)(wv[i] >> 8); d[2] = (uint8_t)(wv[i] >> 16); d[3] = (uint8_t)(wv[i] >> 24);
+            }
+        }
+        if (lane >= 28) {
+            const int i = lane - 28;
+            uint32_t wv = h.hold ? s_rowbytes[((h.hold - 1) * 4 + h.hold_r) * 4 + i] : 0x01010101u;
+            uint8_t* d = pix + (Hp - P + i) * RW + Wp;
+            d[0] = (uint8_t)wv; d[1] = (uint8_t)(wv >> 8); d[2] = (uint8_t)(wv >> 16); d[3] = (uint8_t)(wv >> 24);
+        }
+        __syncwarp();
+        uint32_t cells = c_cells[h.p][h.r];
+        COLT B = bmask<COLT>(cols, W, cells, h.x);
+        if (!((B >> h.y) & 1) && lane < 4) {   // active piece on top (project_tetromino, envs/tetris.py:543-564)
+            int c = (cells >> (4 * lane)) & 15;
+            pix[(h.y + (c >> 2)) * RW + h.x + (c & 3)] = (uint8_t)(h.p + 2);
+        }
+        bulk_wait_read();                  // this lane's stores of the previous env have read `out`
+        __syncwarp();
+        // ---- resize (bilinear kernel, area-mode coordinates) + grey, one output row at a time ----
+        int hc[NX][3], hn[NX][3];          // horizontal pass of the two live source rows, this lane's columns
+        int row_c = -1, row_n = -1;
+        auto hpass = [&](int sy, int (&dst)[NX][3]) {
+            const uint8_t* prow = pix + sy * RW;
+#pragma unroll
+            for (int j = 0; j < NX; j++) {
+                const uint32_t c0 = s_lut[prow[sx0[j]]], c1 = s_lut[prow[sx1[j]]];
+#pragma unroll
+                for (int k = 0; k < 3; k++) dst[j][k] = (int)((c0 >> (8 * k)) & 255u) * a0[j] + (int)((c1 >> (8 * k)) & 255u) * a1[j];
+            }
+        };
+        for (int dy = 0; dy < OH; dy++) {
+            const int4 yt = s_y[dy];       // sy0, sy1, b0, b1 (warp-uniform)
+            if (yt.x != row_c) {
+                if (yt.x == row_n) {
+#pragma unroll
+                    for (int j = 0; j < NX; j++) { hc[j][0] = hn[j][0]; hc[j][1] = hn[j][1]; hc[j][2] = hn[j][2]; }
+                } else hpass(yt.x, hc);
+                row_c = yt.x;
+            }
+            if (yt.y != row_n) {
+                if (yt.y == row_c) {
+#pragma unroll
+                    for (int j = 0; j < NX; j++) { hn[j][0] = hc[j][0]; hn[j][1] = hc[j][1]; hn[j][2] = hc[j][2]; }
+                } else hpass(yt.y, hn);
+                row_n = yt.y;
+            }
+#pragma unroll
+            for (int j = 0; j < NX; j++) {
+                const int dx = lane + 32 * j;
+                int ch[3];
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    int v = (((yt.z * (hc[j][k] >> 4)) >> 16) + ((yt.w * (hn[j][k] >> 4)) >> 16) + 2) >> 2;
+                    ch[k] = min(max(v, 0), 255);
+                }
+                const double g = __dadd_rn(__dadd_rn(s_gray[ch[0]], s_gray[256 + ch[1]]), s_gray[512 + ch[2]]);
+                if (dx < OW) out[dy * OW + dx] = (uint8_t)__double2int_rz(g);
+            }
+        }
+        // ---- store: the frame, plus (reset envs) the preceding frames of the stack window ----
+        uint8_t* g = p.frames + e * p.env_stride;
+        const int reps = 1 + ((p.fill_mask && p.fill_mask[e]) ? p.fill_count : 0);
+        if (tma) {
+            fence_async_smem();
+            __syncwarp();
+            if (lane < reps) { bulk_s2g(g - (size_t)lane * FB, out, (uint32_t)FB); bulk_commit(); }
+            for (int r = 32 + lane; r < reps; r += 32) { bulk_s2g(g - (size_t)r * FB, out, (uint32_t)FB); bulk_commit(); }
+        } else {
+            __syncwarp();
+            for (int r = 0; r < reps; r++)
+                for (int i = lane; i < FB; i += 32) (g - (size_t)r * FB)[i] = out[i];
+        }
+        __syncwarp();
+    }
+    bulk_wait_all();
+}
+
+}  // namespace tg
+
+// ---- host side --------------------------------------------------------------------------------------------------
+#include <math.h>
+// offsets and 11-bit coefficient pairs of one axis, exactly as cv::hal::resize computes them for INTER_AREA when the
+// kernel is the bilinear emulation (area_mode): double scale factors, float fractions, saturate_cast<short> (lrintf).
+// tab[d] = {s0, s1, c0, c1}: source indices (s1 clamped; equal to s0 with c = {2048, 0} at the right / bottom border).
+static void cnn_axis_tables(int ssize, int dsize, std::vector<int32_t>& tab, bool clamp_pair) {
+    const double inv_scale = (double)dsize / ssize, scale = 1. / inv_scale;
+    tab.assign((size_t)dsize * 4, 0);
+    for (int d = 0; d < dsize; d++) {
+        int s = (int)floor(d * scale);
+        float f = (float)((d + 1) - (s + 1) * inv_scale);
+        f = f <= 0 ? 0.f : f - floorf(f);
+        if (s < 0) { f = 0.f; s = 0; }
+        bool border = false;
+        if (s + 1 >= ssize) {
+            border = true;                       // HResizeLinear: dx >= xmax reads S[sx] * ONE
+            if (s >= ssize - 1) { f = 0.f; s = ssize - 1; }
+        }
+        int c0 = (int)lrintf((1.f - f) * 2048.f), c1 = (int)lrintf(f * 2048.f);
+        c0 = c0 > 32767 ? 32767 : (c0 < -32768 ? -32768 : c0);
+        c1 = c1 > 32767 ? 32767 : (c1 < -32768 ? -32768 : c1);
+        int s1 = s + 1 < ssize ? s + 1 : ssize - 1;
+        if (clamp_pair && border) { s1 = s; c0 = 2048; c1 = 0; }
+        tab[4 * d] = s; tab[4 * d + 1] = s1; tab[4 * d + 2] = c0; tab[4 * d + 3] = c1;
+    }
+}
+
+extern "C" int tg_cnn_observe(tg_env* env, tg_state st, int64_t n, int32_t out_h, int32_t out_w, uint8_t* d_frames,
+                              int64_t env_stride, const uint8_t* d_fill_mask, int32_t fill_count, void* stream) {
+    if (!env) return TG_ERR_POINTER;
+    int rc = check_state(env, st); if (rc) return rc;
+    if (!d_frames) return fail(env, TG_ERR_POINTER, "d_frames is NULL");
+    const DevCfg& d = env->dev;
+    if (out_h < 1 || out_w < 1 || out_h > 128 || out_w > 128) return fail(env, TG_ERR_ARG, "tg_cnn_observe: output size must be within 1..128");
+    if (d.rgb_w >= out_w && d.Hp >= out_h)
+        return fail(env, TG_ERR_CONFIG, "tg_cnn_observe: both axes shrink (true area interpolation) -- not supported");
+    if (fill_count < 0 || env_stride < (int64_t)out_h * out_w) return fail(env, TG_ERR_ARG, "tg_cnn_observe: bad fill_count / env_stride");
+    CUDA_TRY(env, cudaSetDevice(env->device));
+    if (env->cnn_h != out_h || env->cnn_w != out_w) {   // (re)build the coefficient tables for this output size
+        std::vector<int32_t> xt, yt;
+        cnn_axis_tables(d.rgb_w, out_w, xt, true);
+        cnn_axis_tables(d.Hp, out_h, yt, false);
+        std::vector<double> gray(768);
+        for (int v = 0; v < 256; v++) { gray[v] = v * 0.2125; gray[256 + v] = v * 0.7154; gray[512 + v] = v * 0.0721; }
+        size_t bytes = (xt.size() + yt.size()) * 4 + gray.size() * 8;
+        rc = ensure_stage(env, 4, bytes); if (rc) return rc;
+        uint8_t* base = (uint8_t*)env->stage[4];
+        CUDA_TRY(env, cudaMemcpy(base, gray.data(), gray.size() * 8, cudaMemcpyHostToDevice));
+        CUDA_TRY(env, cudaMemcpy(base + 6144, xt.data(), xt.size() * 4, cudaMemcpyHostToDevice));
+        CUDA_TRY(env, cudaMemcpy(base + 6144 + xt.size() * 4, yt.data(), yt.size() * 4, cudaMemcpyHostToDevice));
+        env->cnn_h = out_h; env->cnn_w = out_w;
+    }
+    CnnParams p;
+    memset(&p, 0, sizeof p);
+    p.cfg = d; p.n = n; p.hot = (const uint8_t*)st.hot; p.board = (const uint8_t*)st.board;
+    uint8_t* base = (uint8_t*)env->stage[4];
+    p.gray = (const double*)base; p.xtab = (const int32_t*)(base + 6144); p.ytab = p.xtab + (size_t)out_w * 4;
+    p.frames = d_frames; p.env_stride = env_stride; p.fill_mask = d_fill_mask; p.fill_count = fill_count;
+    p.OH = out_h; p.OW = out_w;
+    auto r128 = [](size_t v) { return (int)((v + 127) / 128 * 128); };
+    p.rec_bytes = r128((size_t)d.board_stride + 48); p.pix_bytes = r128((size_t)d.Hp * d.rgb_w + 16); p.out_bytes = r128((size_t)out_h * out_w);
+    const int nw = 4, T = nw * 32;
+    const size_t smem = (size_t)nw * (2 * p.rec_bytes + p.pix_bytes + p.out_bytes);
+    if (smem > 200 * 1024) return fail(env, TG_ERR_CONFIG, "tg_cnn_observe: image too large for shared memory");
+    const int NX = (out_w + 31) / 32;
+    auto launch = [&](auto kern) -> int {
+        CUDA_TRY(env, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 1;
+        CUDA_TRY(env, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, T, smem));
+        int64_t blocks = (n + nw - 1) / nw, cap = (int64_t)env->num_sms * (per_sm > 0 ? per_sm : 1);
+        if (blocks > cap) blocks = cap;
+        kern<<<(unsigned)blocks, T, smem, (cudaStream_t)stream>>>(p);
+        CUDA_TRY(env, cudaGetLastError());
+        return TG_OK;
+    };
+    if (env->col64) return NX == 1 ? launch(k_cnn_obs<uint64_t, 1>) : NX == 2 ? launch(k_cnn_obs<uint64_t, 2>) : NX == 3 ? launch(k_cnn_obs<uint64_t, 3>) : launch(k_cnn_obs<uint64_t, 4>);
+    return NX == 1 ? launch(k_cnn_obs<uint32_t, 1>) : NX == 2 ? launch(k_cnn_obs<uint32_t, 2>) : NX == 3 ? launch(k_cnn_obs<uint32_t, 3>) : launch(k_cnn_obs<uint32_t, 4>);
+}

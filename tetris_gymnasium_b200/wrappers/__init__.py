@@ -1,2 +1,2 @@
 from .grouped import GroupedActionsObservations  # noqa: F401
-from .observation import FeatureVectorObservation, RgbObservation  # noqa: F401
+from .observation import CnnObservation, FeatureVectorObservation, RgbObservation  # noqa: F401
