@@ -6,7 +6,10 @@
 //   * ResizeObservation = cv2.resize(INTER_AREA); with an enlarged axis OpenCV emulates it by a bilinear kernel with
 //     `area_mode` coordinates, fixed point with 11-bit coefficients (imgproc/src/resize.cpp: HResizeLinear / VResizeLinear);
 //     offsets / coefficients are computed on the host exactly like cv::hal::resize (tg_api.cu: cnn_axis_tables)
-//   * GrayscaleObservation = floor(R * 0.2125 + G * 0.7154 + B * 0.0721) in float64, summed left to right
+//   * GrayscaleObservation = floor(R * 0.2125 + G * 0.7154 + B * 0.0721) in float64, summed left to right.  Evaluated in
+//     integers: N = 2125 R + 7154 G + 721 B, grey = N / 10000, minus one for the 63 (R, G, B) triples (all with
+//     N % 10000 == 0) where the float64 sum lands just below the integer; the host finds them by enumerating all 2^24
+//     triples with the float64 expression itself (tg_api.cu: cnn_gray_exceptions) -- at most two per quotient
 // Third-party arithmetic (gymnasium 1.1.1, OpenCV): restated in oracle/cnn_obs_oracle.py and pinned against cv2 there.
 // One warp per env: record prefetch (cp.async) -> id image in shared memory -> per lane fixed output columns (source
 // offsets / coefficients in registers), horizontal pass kept in registers for the two live source rows, vertical pass +
@@ -22,7 +25,7 @@ struct CnnParams {
     const uint8_t* hot; const uint8_t* board;
     const int32_t* xtab;      // [OW][4]: sx0, sx1 (pixel offsets inside an image row), a0, a1
     const int32_t* ytab;      // [OH][4]: sy0, sy1 (clamped source rows), b0, b1
-    const double* gray;       // [3][256]: v * 0.2125, v * 0.7154, v * 0.0721
+    const uint32_t* gray_exc; // [256][2] by quotient: R | G << 8 | B << 16 of up to two exception triples (0xFFFFFFFF = none)
     uint8_t* frames;          // frame of env e at frames + e * env_stride
     int64_t env_stride;
     const uint8_t* fill_mask; // nullable: envs whose frame is replicated into the `fill_count` preceding frames
@@ -37,7 +40,7 @@ __global__ void __launch_bounds__(128) k_cnn_obs(const __grid_constant__ CnnPara
     __shared__ uint32_t s_lut[16];
     __shared__ uint32_t s_rowbytes[112];
     __shared__ __align__(16) int4 s_y[128];
-    __shared__ __align__(8) double s_gray[3 * 256];
+    __shared__ __align__(8) uint2 s_exc[256];
     const DevCfg& cfg = p.cfg;
     const int W = cfg.W, H = cfg.H, Wp = cfg.Wp, Hp = cfg.Hp, RW = cfg.rgb_w, Q = cfg.Q, BS = cfg.board_stride;
     const int OH = p.OH, OW = p.OW, FB = OH * OW;
@@ -50,7 +53,8 @@ __global__ void __launch_bounds__(128) k_cnn_obs(const __grid_constant__ CnnPara
     if (threadIdx.x < 16) s_lut[threadIdx.x] = ((const uint32_t*)c_colors)[threadIdx.x];
     for (int i = threadIdx.x; i < 112; i += blockDim.x) s_rowbytes[i] = (&c_rowbytes[0][0][0])[i];
     for (int i = threadIdx.x; i < OH; i += blockDim.x) s_y[i] = ((const int4*)p.ytab)[i];
-    for (int i = threadIdx.x; i < 768; i += blockDim.x) s_gray[i] = p.gray[i];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_exc[i] = ((const uint2*)p.gray_exc)[i];
+    const uint32_t exc_addr = smem_u32(s_exc);
     for (int i = lane; i < NP; i += 32) {   // constant part of the id image (see k_rgb)
         int r = i / RW, c = i - r * RW;
         pix[i] = (c < Wp && r < H && c >= P && c < P + W) ? 0 : 1;
@@ -125,10 +129,12 @@ __global__ void __launch_bounds__(128) k_cnn_obs(const __grid_constant__ CnnPara
             for (int j = 0; j < NX; j++) {
                 const uint32_t c0 = s_lut[prow[sx0[j]]], c1 = s_lut[prow[sx1[j]]];
 #pragma unroll
-                for (int k = 0; k < 3; k++) dst[j][k] = (int)((c0 >> (8 * k)) & 255u) * a0[j] + (int)((c1 >> (8 * k)) & 255u) * a1[j];
+                for (int k = 0; k < 3; k++)   // kept pre-shifted: the vertical pass only uses h >> 4
+                    dst[j][k] = ((int)((c0 >> (8 * k)) & 255u) * a0[j] + (int)((c1 >> (8 * k)) & 255u) * a1[j]) >> 4;
             }
         };
-        for (int dy = 0; dy < OH; dy++) {
+        uint32_t orow = smem_u32(out) + lane;   // shared-window address of this lane's first pixel of the output row
+        for (int dy = 0; dy < OH; dy++, orow += OW) {
             const int4 yt = s_y[dy];       // sy0, sy1, b0, b1 (warp-uniform)
             if (yt.x != row_c) {
                 if (yt.x == row_n) {
@@ -146,15 +152,18 @@ __global__ void __launch_bounds__(128) k_cnn_obs(const __grid_constant__ CnnPara
             }
 #pragma unroll
             for (int j = 0; j < NX; j++) {
-                const int dx = lane + 32 * j;
-                int ch[3];
-#pragma unroll
-                for (int k = 0; k < 3; k++) {
-                    int v = (((yt.z * (hc[j][k] >> 4)) >> 16) + ((yt.w * (hn[j][k] >> 4)) >> 16) + 2) >> 2;
-                    ch[k] = min(max(v, 0), 255);
-                }
-                const double g = __dadd_rn(__dadd_rn(s_gray[ch[0]], s_gray[256 + ch[1]]), s_gray[512 + ch[2]]);
-                if (dx < OW) out[dy * OW + dx] = (uint8_t)__double2int_rz(g);
+                // colours are <= 240 and the coefficient pairs sum to 2048 +- 1: 0 <= v <= 255 without clamping;
+                // the rounding "+ 2" rides on the first product ((t + (2 << 16)) >> 16 == (t >> 16) + 2)
+                const int r = (((yt.z * hc[j][0] + 0x20000) >> 16) + ((yt.w * hn[j][0]) >> 16)) >> 2;
+                const int g = (((yt.z * hc[j][1] + 0x20000) >> 16) + ((yt.w * hn[j][1]) >> 16)) >> 2;
+                const int b = (((yt.z * hc[j][2] + 0x20000) >> 16) + ((yt.w * hn[j][2]) >> 16)) >> 2;
+                const uint32_t N = (uint32_t)(r * 2125 + g * 7154 + b * 721);
+                const uint32_t q = (uint32_t)(((uint64_t)N * 3518437209ull) >> 45);   // N / 10000 for N <= 2,550,000
+                const uint32_t key = (uint32_t)r | ((uint32_t)g << 8) | ((uint32_t)b << 16);
+                uint32_t t0, t1;
+                asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(t0), "=r"(t1) : "r"(exc_addr + q * 8u));
+                const uint32_t low = (uint32_t)(key == t0) | (uint32_t)(key == t1);
+                if (lane + 32 * j < OW) asm volatile("st.shared.u8 [%0], %1;" ::"r"(orow + 32u * j), "r"(q - low) : "memory");
             }
         }
         // ---- store: the frame, plus (reset envs) the preceding frames of the stack window ----
@@ -204,6 +213,24 @@ static void cnn_axis_tables(int ssize, int dsize, std::vector<int32_t>& tab, boo
     }
 }
 
+// R | G << 8 | B << 16 of the triples whose float64 grey value is one below N / 10000, two slots per quotient
+static int cnn_gray_exceptions(std::vector<uint32_t>& tab) {
+    tab.assign(512, 0xFFFFFFFFu);
+    std::vector<int> cnt(256, 0);
+    for (int r = 0; r < 256; r++)
+        for (int g = 0; g < 256; g++)
+            for (int b = 0; b < 256; b++) {
+                const int N = 2125 * r + 7154 * g + 721 * b, q = N / 10000;
+                volatile double f = r * 0.2125 + g * 0.7154;   // left-to-right float64 sum, no contraction
+                f = f + b * 0.0721;
+                const int v = (int)f;
+                if (v == q) continue;
+                if (v != q - 1 || cnt[q] >= 2) return -1;   // the integer scheme would not hold
+                tab[2 * q + cnt[q]++] = (uint32_t)(r | (g << 8) | (b << 16));
+            }
+    return 0;
+}
+
 extern "C" int tg_cnn_observe(tg_env* env, tg_state st, int64_t n, int32_t out_h, int32_t out_w, uint8_t* d_frames,
                               int64_t env_stride, const uint8_t* d_fill_mask, int32_t fill_count, void* stream) {
     if (!env) return TG_ERR_POINTER;
@@ -219,12 +246,13 @@ extern "C" int tg_cnn_observe(tg_env* env, tg_state st, int64_t n, int32_t out_h
         std::vector<int32_t> xt, yt;
         cnn_axis_tables(d.rgb_w, out_w, xt, true);
         cnn_axis_tables(d.Hp, out_h, yt, false);
-        std::vector<double> gray(768);
-        for (int v = 0; v < 256; v++) { gray[v] = v * 0.2125; gray[256 + v] = v * 0.7154; gray[512 + v] = v * 0.0721; }
-        size_t bytes = (xt.size() + yt.size()) * 4 + gray.size() * 8;
+        std::vector<uint32_t> gray;
+        if (cnn_gray_exceptions(gray)) return fail(env, TG_ERR_CONFIG, "tg_cnn_observe: float64 grey conversion does not follow the integer scheme on this host");
+        gray.resize(1536, 0xFFFFFFFFu);
+        size_t bytes = (xt.size() + yt.size()) * 4 + 6144;
         rc = ensure_stage(env, 4, bytes); if (rc) return rc;
         uint8_t* base = (uint8_t*)env->stage[4];
-        CUDA_TRY(env, cudaMemcpy(base, gray.data(), gray.size() * 8, cudaMemcpyHostToDevice));
+        CUDA_TRY(env, cudaMemcpy(base, gray.data(), 6144, cudaMemcpyHostToDevice));
         CUDA_TRY(env, cudaMemcpy(base + 6144, xt.data(), xt.size() * 4, cudaMemcpyHostToDevice));
         CUDA_TRY(env, cudaMemcpy(base + 6144 + xt.size() * 4, yt.data(), yt.size() * 4, cudaMemcpyHostToDevice));
         env->cnn_h = out_h; env->cnn_w = out_w;
@@ -233,7 +261,7 @@ extern "C" int tg_cnn_observe(tg_env* env, tg_state st, int64_t n, int32_t out_h
     memset(&p, 0, sizeof p);
     p.cfg = d; p.n = n; p.hot = (const uint8_t*)st.hot; p.board = (const uint8_t*)st.board;
     uint8_t* base = (uint8_t*)env->stage[4];
-    p.gray = (const double*)base; p.xtab = (const int32_t*)(base + 6144); p.ytab = p.xtab + (size_t)out_w * 4;
+    p.gray_exc = (const uint32_t*)base; p.xtab = (const int32_t*)(base + 6144); p.ytab = p.xtab + (size_t)out_w * 4;
     p.frames = d_frames; p.env_stride = env_stride; p.fill_mask = d_fill_mask; p.fill_count = fill_count;
     p.OH = out_h; p.OW = out_w;
     auto r128 = [](size_t v) { return (int)((v + 127) / 128 * 128); };

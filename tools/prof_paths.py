@@ -3,7 +3,7 @@
     ncu --set full --clock-control none --import-source on -k regex:k_rgb -s 4 -c 1 -o gpurun_out/prof_rgb \
         python tools/prof_paths.py rgb --envs 262144
 
-paths: step | rgb (wide board + image) | rgb_d (default board + image) | boards | boards_x | feats | rollout"""
+paths: step | cnn (wide board, fused 84x84 grey frame stack) | rgb (wide board + image) | rgb_d (default board + image) | boards | boards_x | feats | rollout"""
 import argparse
 import sys
 
@@ -11,7 +11,7 @@ import torch
 
 sys.path.insert(0, ".")
 from tetris_gymnasium_b200.envs.tetris import Tetris  # noqa: E402
-from tetris_gymnasium_b200.wrappers import FeatureVectorObservation, GroupedActionsObservations, RgbObservation  # noqa: E402
+from tetris_gymnasium_b200.wrappers import CnnObservation, FeatureVectorObservation, GroupedActionsObservations, RgbObservation  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("path")
@@ -40,6 +40,13 @@ elif args.path in ("boards", "boards_x", "feats"):
     for i in range(args.iters):
         a = torch.multinomial(env.legal_actions_mask.float() + 1e-9, 1).squeeze(1).to(torch.int32)
         env.step(a)
+elif args.path == "cnn":
+    base = Tetris(num_envs=n, width=20, height=40, queue_size=5)
+    env = CnnObservation(base)
+    env.reset(seed=42)
+    acts = torch.randint(0, 8, (args.iters, n), dtype=torch.int32, device="cuda")
+    for i in range(args.iters):
+        env.step(acts[i])
 elif args.path == "rollout":
     env = Tetris(num_envs=n, gravity=False, queue_size=7)
     env.reset(seed=42)
