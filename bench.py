@@ -86,11 +86,20 @@ def bytes_per_step(layout, queue, commit_frac):
     return read + write, obs
 
 
+def host_cores():
+    """Host threads the CPU arm uses: every core this process may run on (torchrun exports OMP_NUM_THREADS=1 to its
+    workers, so the OpenMP default is not trusted; the thread count is passed to the oracle explicitly)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_baseline(seconds_target=12.0, n_envs=8192):
     """The oracle port (oracle/tetris_oracle.c, OpenMP over host cores) on a bounded sample of the same workload."""
     from oracle.tetris_oracle import OracleVec, lib
 
-    cores = lib().orc_num_threads()
+    cores = host_cores()
     vec = OracleVec(n_envs, width=WIDTH, height=HEIGHT, gravity=True, queue_size=QUEUE)
     for i, e in enumerate(vec.envs):
         e.seed_numpy(1 + i)
@@ -98,11 +107,11 @@ def cpu_baseline(seconds_target=12.0, n_envs=8192):
     rng = np.random.default_rng(42)
     acts = rng.integers(0, 8, size=(64, n_envs)).astype(np.int32)
     for t in range(3):
-        vec.step(acts[t])
+        vec.step(acts[t], nthreads=cores)
     t0 = time.perf_counter()
     steps = 0
     while True:
-        vec.step(acts[steps % 64])
+        vec.step(acts[steps % 64], nthreads=cores)
         steps += 1
         if time.perf_counter() - t0 > seconds_target:
             break
@@ -117,7 +126,7 @@ def run_reference(args):
         return
     from oracle.tetris_oracle import OracleVec, lib
 
-    cores = lib().orc_num_threads()
+    cores = host_cores()
     n_envs = 16384
     vec = OracleVec(n_envs, width=WIDTH, height=HEIGHT, gravity=True, queue_size=QUEUE)
     for i, e in enumerate(vec.envs):
@@ -126,10 +135,10 @@ def run_reference(args):
     rng = np.random.default_rng(42)
     acts = rng.integers(0, 8, size=(args.warmup + args.steps, n_envs)).astype(np.int32)
     for t in range(args.warmup):
-        vec.step(acts[t])
+        vec.step(acts[t], nthreads=cores)
     t0 = time.perf_counter()
     for t in range(args.steps):
-        vec.step(acts[args.warmup + t])
+        vec.step(acts[args.warmup + t], nthreads=cores)
     dt = time.perf_counter() - t0
     v = n_envs * args.steps / dt
     sample = f"{n_envs} envs per step (bounded sample of the {ENVS_PER_GPU}-env workload), oracle port of the reference NumPy env, OpenMP x{cores}"
