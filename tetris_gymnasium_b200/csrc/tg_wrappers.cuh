@@ -238,7 +238,8 @@ __device__ __forceinline__ void warp_pre_suf(const COLT* cols, int W, int lane, 
 template <class COLT, int NV>
 __global__ void __launch_bounds__(256, 3) k_grouped_boards_stream(const DevCfg cfg, int64_t n, const uint8_t* hot, const uint8_t* board,
                                                                   uint8_t* boards, uint8_t* legal, const uint8_t* fill_high, int rec_bytes,
-                                                                  int img_bytes, int G, int gbuf_bytes) {
+                                                                  int img_bytes, int gbuf_bytes) {
+    constexpr int G = NV == 1 ? 8 : (NV <= 3 ? 4 : 2);   // placements per bulk store (G * OB <= 6 KB)
     extern __shared__ __align__(128) uint8_t sm[];
     __shared__ unsigned short s_cells[28];
     __shared__ int s_n[8];
@@ -294,78 +295,79 @@ __global__ void __launch_bounds__(256, 3) k_grouped_boards_stream(const DevCfg c
         for (int j = 0; j < NV; j++) basev[j] = act[j] ? ((const uint4*)img)[lane + 32 * j] : make_uint4(0, 0, 0, 0);
         // placements of this env: lane `l` owns a = 32 * round + l
         // class: 0 regular, 1 frame -> ones, 2 game over -> zeros, 3 constant fill (illegal action + terminate), 4 regular + rows cleared, 8 none
-        uint32_t info[3], offlo[3], offhi[3];   // off*: byte offsets of the 4 piece cells inside the board image (16 bits each)
-#pragma unroll
-        for (int rd = 0; rd < 3; rd++) {
-            info[rd] = 8; offlo[rd] = 0; offhi[rd] = 0;
-            const int a = rd * 32 + lane;
-            if (rd * 32 < A && a < A) {
-                uint32_t k = 3;
-                if (!fh) {
-                    COLT B;
-                    Placement pl = eval_placement<COLT>(cfg, tb, cols, piece, rot0, a, B);
-                    legal[e * A + a] = pl.kind != 1;
-                    k = (uint32_t)pl.kind;
-                    if (pl.kind == 0) {
-                        uint32_t cells = tb.cells[piece * 4 + pl.rot];
-                        int crow[4], ccol[4], c0 = 64, c1 = -1;
-#pragma unroll
-                        for (int c4 = 0; c4 < 4; c4++) {
-                            int c = (cells >> (4 * c4)) & 15;
-                            crow[c4] = pl.y + (c >> 2); ccol[c4] = pl.x + (c & 3) - P;
-                            c0 = min(c0, ccol[c4]); c1 = max(c1, ccol[c4]);
-                        }
-                        COLT full = s_pre[c0] & s_suf[c1] & playfield;
-#pragma unroll
-                        for (int j = 0; j < 4; j++) {
-                            if (c0 + j <= c1) {
-                                COLT v = cols[c0 + j];
-#pragma unroll
-                                for (int c4 = 0; c4 < 4; c4++) if (ccol[c4] == c0 + j) v |= COLT(1) << crow[c4];
-                                full &= v;
-                            }
-                        }
-                        if (full) k = 4;
-                        offlo[rd] = (uint32_t)(crow[0] * Wp + ccol[0] + P) | ((uint32_t)(crow[1] * Wp + ccol[1] + P) << 16);
-                        offhi[rd] = (uint32_t)(crow[2] * Wp + ccol[2] + P) | ((uint32_t)(crow[3] * Wp + ccol[3] + P) << 16);
-                    }
-                }
-                info[rd] = k;
-            }
-        }
         uint8_t* genv = boards + (size_t)e * A * OB;
+#pragma unroll 1
+        for (int rd = 0; rd * 32 < A; rd++) {   // one round = 32 placements; code is NOT unrolled over rounds (instruction cache)
+            {
+                uint32_t info = 8, offlo = 0, offhi = 0;   // off*: byte offsets of the 4 piece cells inside the board image (16 bits each)
+                const int a = rd * 32 + lane;
+                if (a < A) {
+                    uint32_t k = 3;
+                    if (!fh) {
+                        COLT B;
+                        Placement pl = eval_placement<COLT>(cfg, tb, cols, piece, rot0, a, B);
+                        legal[e * A + a] = pl.kind != 1;
+                        k = (uint32_t)pl.kind;
+                        if (pl.kind == 0) {
+                            uint32_t cells = tb.cells[piece * 4 + pl.rot];
+                            int crow[4], ccol[4], c0 = 64, c1 = -1;
 #pragma unroll
-        for (int rd = 0; rd < 3; rd++) {
-            if (rd * 32 < A) {
-                const uint32_t m_base = __ballot_sync(0xffffffffu, info[rd] == 0 || info[rd] == 4);
-                const uint32_t m_one = __ballot_sync(0xffffffffu, info[rd] == 1);
-                const uint32_t m_high = __ballot_sync(0xffffffffu, info[rd] == 3);
-                const uint32_t m_slow = __ballot_sync(0xffffffffu, info[rd] == 4);
+                            for (int c4 = 0; c4 < 4; c4++) {
+                                int c = (cells >> (4 * c4)) & 15;
+                                crow[c4] = pl.y + (c >> 2); ccol[c4] = pl.x + (c & 3) - P;
+                                c0 = min(c0, ccol[c4]); c1 = max(c1, ccol[c4]);
+                            }
+                            COLT full = s_pre[c0] & s_suf[c1] & playfield;
+#pragma unroll
+                            for (int j = 0; j < 4; j++) {
+                                if (c0 + j <= c1) {
+                                    COLT v = cols[c0 + j];
+#pragma unroll
+                                    for (int c4 = 0; c4 < 4; c4++) if (ccol[c4] == c0 + j) v |= COLT(1) << crow[c4];
+                                    full &= v;
+                                }
+                            }
+                            if (full) k = 4;
+                            offlo = (uint32_t)(crow[0] * Wp + ccol[0] + P) | ((uint32_t)(crow[1] * Wp + ccol[1] + P) << 16);
+                            offhi = (uint32_t)(crow[2] * Wp + ccol[2] + P) | ((uint32_t)(crow[3] * Wp + ccol[3] + P) << 16);
+                        }
+                    }
+                    info = k;
+                }
+                const uint32_t m_base = __ballot_sync(0xffffffffu, info == 0 || info == 4);
+                const uint32_t m_one = __ballot_sync(0xffffffffu, info == 1);
+                const uint32_t m_high = __ballot_sync(0xffffffffu, info == 3);
+                const uint32_t m_slow = __ballot_sync(0xffffffffu, info == 4);
                 const int na = min(32, A - rd * 32);
                 for (int l0 = 0; l0 < na; l0 += G, gcount++) {
                     uint8_t* buf = gbuf + (gcount & 1u) * gbuf_bytes;
                     if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the store that last used `buf` has read it
                     __syncwarp();
-                    for (int sl = 0; sl < G; sl++) {
-                        const int bit = l0 + sl;
-                        uint4* d = (uint4*)(buf + sl * OB) + lane;
-                        if ((m_base >> bit) & 1) {
+                    // base image into every slot of the group (one 128-bit store per lane and slot) ...
+                    {
+                        uint8_t* d = buf + 16 * lane;
 #pragma unroll
-                            for (int j = 0; j < NV; j++) if (act[j]) d[32 * j] = basev[j];
-                        } else {
-                            const uint32_t fw = ((m_one >> bit) & 1) ? 0x01010101u : (((m_high >> bit) & 1) ? fhw : 0u);
-                            const uint4 fv = make_uint4(fw, fw, fw, fw);
+                        for (int sl = 0; sl < G; sl++, d += OB) {
 #pragma unroll
-                            for (int j = 0; j < NV; j++) if (act[j]) d[32 * j] = fv;
+                            for (int j = 0; j < NV; j++) if (act[j]) ((uint4*)d)[32 * j] = basev[j];
                         }
                     }
+                    // ... then the constant fills (frame -> ones, game over -> zeros, illegal + terminate -> high)
+                    for (uint32_t m = (~m_base >> l0) & ((1u << G) - 1); m; m &= m - 1) {
+                        const int sl = __ffs((int)m) - 1, bit = l0 + sl;
+                        const uint32_t fw = ((m_one >> bit) & 1) ? 0x01010101u : (((m_high >> bit) & 1) ? fhw : 0u);
+                        const uint4 fv = make_uint4(fw, fw, fw, fw);
+                        uint4* d = (uint4*)(buf + sl * OB) + lane;
+#pragma unroll
+                        for (int j = 0; j < NV; j++) if (act[j]) d[32 * j] = fv;
+                    }
                     __syncwarp();
-                    if (lane >= l0 && lane < l0 + G && info[rd] == 0) {   // project_tetromino: the four cells of this lane's placement
+                    if (lane >= l0 && lane < l0 + G && info == 0) {   // project_tetromino: the four cells of this lane's placement
                         uint8_t* d = buf + (lane - l0) * OB;
                         const uint8_t v = (uint8_t)(piece + 2);
-                        d[offlo[rd] & 0xFFFFu] = v; d[offlo[rd] >> 16] = v; d[offhi[rd] & 0xFFFFu] = v; d[offhi[rd] >> 16] = v;
+                        d[offlo & 0xFFFFu] = v; d[offlo >> 16] = v; d[offhi & 0xFFFFu] = v; d[offhi >> 16] = v;
                     }
-                    for (uint32_t m = (m_slow >> l0) & ((G >= 32) ? 0xffffffffu : ((1u << G) - 1)); m; m &= m - 1) {
+                    for (uint32_t m = (m_slow >> l0) & ((1u << G) - 1); m; m &= m - 1) {
                         // rows get cleared: project, compact (Tetris.clear_filled_rows on the copy, wrappers/grouped.py:171-177)
                         const int sl = __ffs((int)m) - 1, a = rd * 32 + l0 + sl;
                         COLT B;
@@ -620,8 +622,7 @@ static int launch_grouped_observe(tg_env* env, tg_state st, int64_t n, uint8_t* 
     if (stream_ok) {
         const int NV = (d.OB / 16 + 31) / 32;
         auto r128 = [](size_t v) { return (int)((v + 127) / 128 * 128); };
-        int G = 8;                                   // placements per bulk store: largest power of two with G * OB <= 5 KB
-        while (G > 1 && G * d.OB > 5120) G >>= 1;
+        const int G = NV == 1 ? 8 : (NV <= 3 ? 4 : 2);   // placements per bulk store (matches the kernel template)
         const int rec_bytes = r128((size_t)d.board_stride + 32), img_bytes = r128((size_t)d.OB), gbuf_bytes = r128((size_t)G * d.OB);
         const size_t per_warp = (size_t)2 * rec_bytes + img_bytes + 512 + 2 * (size_t)gbuf_bytes;
         int nw = 8, best = 0;
@@ -638,7 +639,7 @@ static int launch_grouped_observe(tg_env* env, tg_state st, int64_t n, uint8_t* 
             CUDA_TRY(env, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, T, smem));
             int64_t blocks = (n + nw - 1) / nw, cap = (int64_t)env->num_sms * (per_sm > 0 ? per_sm : 1);
             if (blocks > cap) blocks = cap;
-            kern<<<(unsigned)blocks, T, smem, s>>>(d, n, (const uint8_t*)st.hot, (const uint8_t*)st.board, d_boards, d_legal, fill_high, rec_bytes, img_bytes, G, gbuf_bytes);
+            kern<<<(unsigned)blocks, T, smem, s>>>(d, n, (const uint8_t*)st.hot, (const uint8_t*)st.board, d_boards, d_legal, fill_high, rec_bytes, img_bytes, gbuf_bytes);
             CUDA_TRY(env, cudaGetLastError());
             return TG_OK;
         };

@@ -10,6 +10,7 @@ import subprocess
 import sys
 
 rep, launches, out = sys.argv[1], sys.argv[2], sys.argv[3]
+desc = sys.argv[4] if len(sys.argv) > 4 else "`ncu --set full --clock-control none --import-source on -k regex:k_step` on `python bench.py` (10x20, queue 7)"
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units, vals = rows[0], rows[1], rows[-1]
@@ -31,27 +32,30 @@ stalls = {h.replace("smsp__average_warps_issue_stalled_", "").replace("_per_issu
 rd = unit_scale(*m["dram__bytes_read.sum"]); wr = unit_scale(*m["dram__bytes_write.sum"]); dur = unit_scale(*m["gpu__time_duration.sum"])
 summary["derived"] = {"dram_bytes_per_launch": rd + wr, "duration_s": dur, "dram_GBps_under_ncu": (rd + wr) / dur / 1e9}
 summary["stalls_per_issue"] = dict(sorted(stalls.items(), key=lambda kv: -kv[1])[:8])
-# launch list
-ls = list(csv.reader(open(launches)))
-hi = next(i for i, r in enumerate(ls) if r and r[0] == "ID")
-kn, mv = ls[hi].index("Kernel Name"), ls[hi].index("Metric Value")
+summary["kernel"] = m.get("Kernel Name", ("", ""))[0]
+# launch list ("-" = none)
 tot = {}
-for r in ls[hi + 1:]:
-    if len(r) > mv:
-        name = r[kn].split("(")[0][-70:]
-        t = tot.setdefault(name, [0, 0.0]); t[0] += 1; t[1] += float(r[mv].replace(",", ""))
-allns = sum(t[1] for t in tot.values())
+if launches != "-":
+    ls = list(csv.reader(open(launches)))
+    hi = next(i for i, r in enumerate(ls) if r and r[0] == "ID")
+    kn, mv = ls[hi].index("Kernel Name"), ls[hi].index("Metric Value")
+    for r in ls[hi + 1:]:
+        if len(r) > mv:
+            name = r[kn].split("(")[0][-70:]
+            t = tot.setdefault(name, [0, 0.0]); t[0] += 1; t[1] += float(r[mv].replace(",", ""))
+allns = sum(t[1] for t in tot.values()) or 1.0
 summary["launch_list"] = [{"kernel": k, "launches": t[0], "total_us": t[1] / 1e3, "share": t[1] / allns} for k, t in sorted(tot.items(), key=lambda kv: -kv[1][1])[:10]]
 json.dump(summary, open(out + ".json", "w"), indent=1)
 with open(out + ".md", "w") as f:
-    f.write(f"# ncu summary: {rep}\n\nSource: `ncu --set full --clock-control none --import-source on -k regex:k_step` on `python bench.py` (1,048,576 envs, 10x20, queue 7).\n"
+    f.write(f"# ncu summary: {rep}\n\nKernel: `{summary['kernel'][:160]}`\n\nSource: {desc}.\n"
             "Numbers under ncu are serialised / cold-cache: use shares and byte counts, not absolute times.\n\n| metric | value | unit |\n|---|---|---|\n")
     for k in keys:
         if k in m:
             f.write(f"| {k} | {m[k][0]} | {m[k][1]} |\n")
     f.write(f"| dram bytes per launch (read+write) | {rd + wr:.4g} | byte |\n| dram GB/s under ncu | {(rd + wr) / dur / 1e9:.1f} | GB/s |\n")
     f.write("\n## stall reasons (warps per issue-active cycle)\n\n" + "\n".join(f"- {k}: {v:.2f}" for k, v in summary["stalls_per_issue"].items()))
-    f.write(f"\n\n## launch list ({launches}, `--metrics gpu__time_duration.sum`)\n\n| kernel | launches | total us | share |\n|---|---|---|---|\n")
+    if tot:
+        f.write(f"\n\n## launch list ({launches}, `--metrics gpu__time_duration.sum`)\n\n| kernel | launches | total us | share |\n|---|---|---|---|\n")
     for r in summary["launch_list"]:
         f.write(f"| `{r['kernel']}` | {r['launches']} | {r['total_us']:.1f} | {100 * r['share']:.1f}% |\n")
 print(open(out + ".md").read())
