@@ -67,6 +67,7 @@ static const unsigned char kColors[9][3] = {{0, 0, 0}, {128, 128, 128}, {0, 240,
 
 static int upload_tables(tg_env* env) {
     unsigned short cells[7][4];
+    uint2 ptab[7][4];
     unsigned int rowbytes[7][4][4];
     unsigned char colors[16][4];
     memset(colors, 0, sizeof colors);
@@ -94,9 +95,26 @@ static int upload_tables(tg_env* env) {
             }
             if (k != 4) return fail(env, TG_ERR_CONFIG, "piece table: %d cells", k);
             cells[p][r] = c;
+            // column profile (place_fast): row mask, top row, cell count per matrix column; first / last used column
+            unsigned int px = 0, py = 0;
+            int jmin = 4, jmax = -1;
+            for (int j = 0; j < 4; j++) {
+                int mask = 0, top = -1, cnt = 0;
+                for (int i = 0; i < 4; i++)
+                    if (i < n && j < n && m[i * n + j]) { mask |= 1 << i; if (top < 0) top = i; cnt++; }
+                if (cnt) { if (j < jmin) jmin = j; if (j > jmax) jmax = j; }
+                px |= (unsigned)mask << (4 * j);
+                px |= (unsigned)(top < 0 ? 0 : top) << (16 + 2 * j);
+                py |= (unsigned)cnt << (3 * j);
+            }
+            for (int j = jmin; j <= jmax; j++)
+                if (!((px >> (4 * j)) & 15u)) return fail(env, TG_ERR_CONFIG, "piece table: empty column inside a piece");
+            px |= (unsigned)jmin << 24 | (unsigned)jmax << 26;
+            ptab[p][r] = make_uint2(px, py);
         }
     }
     CUDA_TRY(env, cudaMemcpyToSymbol(c_cells, cells, sizeof cells));
+    CUDA_TRY(env, cudaMemcpyToSymbol(c_ptab, ptab, sizeof ptab));
     CUDA_TRY(env, cudaMemcpyToSymbol(c_rowbytes, rowbytes, sizeof rowbytes));
     CUDA_TRY(env, cudaMemcpyToSymbol(c_n, kN, sizeof kN));
     CUDA_TRY(env, cudaMemcpyToSymbol(c_colors, colors, sizeof colors));

@@ -55,18 +55,20 @@ struct DevCfg {
 __constant__ unsigned short c_cells[7][4];
 __constant__ unsigned int c_rowbytes[7][4][4];
 __constant__ int c_n[7];
+__constant__ uint2 c_ptab[7][4];   // column profile per (piece, rotation), see place_fast
 __constant__ unsigned char c_colors[16][4];
 
 // Piece tables as seen by device functions: the hot kernels copy them to shared memory first
 // (per-thread piece indices make constant-cache reads serialise), the others read the __constant__ copy.
 struct Tabs {
+    const uint2* ptab;            // [p * 4 + r]  column profiles (place_fast); nullptr = read c_ptab
     const unsigned short* cells;  // [p * 4 + r]
     const unsigned int* rowbytes; // [(p * 4 + r) * 4 + i]
     const int* n;                 // [p]
 };
 __device__ __forceinline__ Tabs const_tabs() {
     Tabs t;
-    t.cells = &c_cells[0][0]; t.rowbytes = &c_rowbytes[0][0][0]; t.n = &c_n[0];
+    t.ptab = &c_ptab[0][0]; t.cells = &c_cells[0][0]; t.rowbytes = &c_rowbytes[0][0][0]; t.n = &c_n[0];
     return t;
 }
 
@@ -481,6 +483,7 @@ struct EnvBase {
     uint8_t* ho;      // [W]   holes per column
     COLT* pre;        // [W]   AND of columns < c
     COLT* suf;        // [W]   AND of columns > c
+    uint16_t* bs;     // [W]   bumpiness prefix: bs[c] = sum over k < c of |h[k+1] - h[k]|
     int sum_h, holes, bump, max_h;
 };
 template <class COLT>
@@ -497,81 +500,12 @@ __device__ __forceinline__ void env_base_compute(const DevCfg& cfg, const COLT* 
         b.h[c] = (uint8_t)hgt; b.ho[c] = (uint8_t)hol;
         b.sum_h += hgt; b.holes += hol; b.max_h = max(b.max_h, hgt);
         if (c > 0) b.bump += abs(hgt - prev);
+        b.bs[c] = (uint16_t)b.bump;
         prev = hgt;
     }
     acc = ~COLT(0);
     for (int c = W - 1; c >= 0; c--) { b.suf[c] = acc; acc &= cols[c]; }
 }
-// regular placement at (x, y): same results as placement_eval(..., place=true, do_clear=true, rowzero, out).
-// defer_clear: when rows would be cleared return lines = -1 instead of running the full evaluation, so that the
-// caller can batch those (rare) placements instead of paying the slow path under warp divergence.
-template <class COLT>
-__device__ __forceinline__ FeatSum placement_eval_fast(const DevCfg& cfg, const COLT* cols, const EnvBase<COLT>& b, uint32_t cells,
-                                                       int x, int y, COLT rowzero, uint8_t* out, bool defer_clear = false) {
-    const int W = cfg.W, H = cfg.H;
-    int crow[4], ccol[4];
-    int c0 = 64, c1 = -1;
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        int c = (cells >> (4 * k)) & 15;
-        crow[k] = y + (c >> 2);
-        ccol[k] = x + (c & 3) - P;
-        c0 = min(c0, ccol[k]); c1 = max(c1, ccol[k]);
-    }
-    COLT nv[4];
-    COLT full = b.pre[c0] & b.suf[c1];
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-        int c = c0 + j;
-        COLT v = 0;
-        if (c <= c1) {
-            v = cols[c];
-#pragma unroll
-            for (int k = 0; k < 4; k++) if (ccol[k] == c) v |= COLT(1) << crow[k];
-            full &= v;
-        }
-        nv[j] = v;
-    }
-    full &= (COLT(1) << H) - 1;
-    FeatSum fs;
-    if (full) {
-        if (defer_clear) { fs.lines = -1; fs.sum_h = fs.max_h = fs.holes = fs.bump = 0; return fs; }
-        return placement_eval<COLT>(cfg, cols, cells, x, y, true, true, rowzero, out);
-    }
-    fs.lines = 0;
-    int sumh = b.sum_h, holes = b.holes, maxh = b.max_h, bump = b.bump;
-    int nh[4];
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-        int c = c0 + j;
-        nh[j] = 0;
-        if (c <= c1) {
-            int hgt, hol;
-            col_features<COLT>(nv[j] & ~rowzero, H, hgt, hol);
-            sumh += hgt - (int)b.h[c]; holes += hol - (int)b.ho[c]; maxh = max(maxh, hgt);
-            nh[j] = hgt;
-        }
-    }
-    // bumpiness: only the pairs that touch [c0, c1] change
-#pragma unroll
-    for (int j = -1; j < 4; j++) {
-        int c = c0 + j;          // pair (c, c+1)
-        if (c >= 0 && c <= c1 && c + 1 < W) {
-            int a0 = (j >= 0) ? nh[j] : (int)b.h[c];
-            int a1 = (c + 1 <= c1) ? nh[(j + 1) & 3] : (int)b.h[c + 1];
-            bump += abs(a1 - a0) - abs((int)b.h[c + 1] - (int)b.h[c]);
-        }
-    }
-    if (out) {
-        for (int c = 0; c < W; c++) out[c] = b.h[c];
-#pragma unroll
-        for (int j = 0; j < 4; j++) if (c0 + j <= c1) out[c0 + j] = (uint8_t)nh[j];
-        out[W] = (uint8_t)maxh; out[W + 1] = (uint8_t)holes; out[W + 2] = (uint8_t)bump;
-    }
-    fs.sum_h = sumh; fs.max_h = maxh; fs.holes = holes; fs.bump = bump;
-    return fs;
-}
-
 // One placement of GroupedActionsObservations.observation (wrappers/grouped.py:148-181).
 struct Placement { int x, y, rot, kind; };  // kind: 0 regular, 1 illegal (frame), 2 game over
 template <class COLT>
@@ -592,6 +526,75 @@ __device__ __forceinline__ Placement eval_placement(const DevCfg& cfg, const Tab
     pl.kind = frame ? 1 : (((B >> pl.y) & 1) ? 2 : 0);
     Bout = B;
     return pl;
+}
+
+// ---- placement evaluation from column profiles -----------------------------------------------------------------------
+// c_ptab[p][r] describes the 4x4 matrix of a piece orientation by COLUMN j = 0..3:
+//   .x bits  4j..4j+3  row mask of column j          .x bits 16+2j..17+2j  row offset of its top cell
+//   .x bits 24-25 / 26-27  first / last column holding cells          .y bits 3j..3j+2  cells in column j
+// With the per-env base (heights h[], holes ho[], prefix / suffix column ANDs) a regular placement that clears no row
+// needs no bit scan at all: in a touched column the new height is max(h, H - top) (the piece came down from above, but a
+// poked board may hold cells above it) and popc grows by the column's cell count, so holes' = h' - (h - ho) - cells.
+// `colp` is the column array padded with P all-ones wall columns on both sides (colp[c + P] = column c).
+// Returns 0 = regular (fs / out filled), 1 = frame (illegal), 2 = game over, 3 = regular but rows get cleared or a cell
+// lands in the row the feature wrapper zeroes: the caller runs the exact placement_eval (rare).
+template <class COLT>
+__device__ __forceinline__ int place_fast(const DevCfg& cfg, const EnvBase<COLT>& b, const COLT* colp, uint32_t cells, uint2 pt, int x,
+                                          FeatSum& fs, int& y_out, uint8_t* out) {
+    const int W = cfg.W, H = cfg.H;
+    COLT B = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int c = (cells >> (4 * k)) & 15;
+        B |= colp[x + (c & 3)] >> (c >> 2);
+    }
+    const int y = ctz_t<COLT>(B >> 1);   // while !collision(y+1): y++ from y = 0, no test at y = 0
+    y_out = y;
+    const int jmin = (pt.x >> 24) & 3, jmax = (pt.x >> 26) & 3;
+    const int c0 = x + jmin - P, c1 = x + jmax - P;
+    if (c0 < 0 || c1 >= W) return 1;
+    if ((B >> y) & 1) return 2;
+    COLT full = b.pre[c0] & b.suf[c1] & ((COLT(1) << H) - 1);
+    int nh[4], sumh = b.sum_h, holes = b.holes, maxh = b.max_h, bump = b.bump;
+    bool top0 = false;
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+        const int j = jmin + t, c = c0 + t;
+        nh[t] = 0;
+        if (j <= jmax) {
+            full &= colp[c + P] | ((COLT)((pt.x >> (4 * j)) & 15u) << y);
+            const int top = y + (int)((pt.x >> (16 + 2 * j)) & 3u);
+            top0 |= top == 0;
+            const int oh = (int)b.h[c], oho = (int)b.ho[c];
+            const int hn = max(oh, H - top);
+            nh[t] = hn;
+            sumh += hn - oh;
+            holes += hn - (oh - oho) - (int)((pt.y >> (3 * j)) & 7u) - oho;
+            maxh = max(maxh, hn);
+        }
+    }
+    if (full != 0 || top0) return 3;
+    // bumpiness: only the pairs (c, c+1), c = c0-1 .. c1, change; their old sum comes from the prefix array
+    {
+        const int wdt = c1 - c0;       // touched columns - 1
+        const int lo = max(c0 - 1, 0), hi1 = min(c1 + 1, W - 1);
+        int nb = 0;
+        if (c0 > 0) nb += abs(nh[0] - (int)b.h[c0 - 1]);
+        if (wdt >= 1) nb += abs(nh[1] - nh[0]);
+        if (wdt >= 2) nb += abs(nh[2] - nh[1]);
+        if (wdt >= 3) nb += abs(nh[3] - nh[2]);
+        const int last = wdt == 0 ? nh[0] : (wdt == 1 ? nh[1] : (wdt == 2 ? nh[2] : nh[3]));
+        if (c1 < W - 1) nb += abs((int)b.h[c1 + 1] - last);
+        bump += nb - ((int)b.bs[hi1] - (int)b.bs[lo]);
+    }
+    if (out) {
+        for (int c = 0; c < W; c++) out[c] = b.h[c];
+#pragma unroll
+        for (int t = 0; t < 4; t++) if (c0 + t <= c1) out[c0 + t] = (uint8_t)nh[t];
+        out[W] = (uint8_t)maxh; out[W + 1] = (uint8_t)holes; out[W + 2] = (uint8_t)bump;
+    }
+    fs.lines = 0; fs.sum_h = sumh; fs.max_h = maxh; fs.holes = holes; fs.bump = bump;
+    return 0;
 }
 
 }  // namespace tg

@@ -21,30 +21,40 @@ struct RolloutParams {
     int w[4];
     int k_steps;
     double* stats;
-    int rec_words;   // shared-memory words per env record (odd / 8-byte friendly stride)
-    int base_off;    // word offset of the per-thread EnvBase arrays (pre[W], suf[W], h[32 B], ho[32 B]) inside the record slot
+    // shared-memory slot of one env (words): [P wall columns][W columns][P wall columns][id plane (+1 word)][pre W][suf W][h][ho][bs]
+    // -- the record is stored with its columns framed by all-ones walls, so place_fast reads them without bounds checks
+    int rec_words;   // words per slot (odd / 8-byte friendly stride)
+    int ids_off_g;   // byte offset of the id plane inside the HBM record (cfg.ids_off holds the in-slot offset (W + P) * sizeof(COLT))
+    int base_off;    // word offset (from the first column) of pre[W]; suf[W], h[hb bytes], ho[hb bytes], bs[2 hb bytes] follow
+    int hb;          // bytes of the h / ho arrays (W rounded up to 4)
     int32_t* last_action;   // nullable: action chosen at the last step (tests)
 };
 
 template <class COLT>
-__global__ void __launch_bounds__(128) k_rollout(const __grid_constant__ RolloutParams p) {
+__global__ void __launch_bounds__(128, 6) k_rollout(const __grid_constant__ RolloutParams p) {
     extern __shared__ __align__(16) uint32_t rsm[];
     const DevCfg& cfg = p.cfg;
     const int tid = threadIdx.x;
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + tid;
     __shared__ unsigned short s_cells[28];
     __shared__ int s_n[8];
-    if (tid < 28) s_cells[tid] = (&c_cells[0][0])[tid];
+    __shared__ uint2 s_ptab[28];
+    if (tid < 28) { s_cells[tid] = (&c_cells[0][0])[tid]; s_ptab[tid] = (&c_ptab[0][0])[tid]; }
     if (tid < 7) s_n[tid] = c_n[tid];
     __syncthreads();
     Tabs tb;
-    tb.cells = s_cells; tb.rowbytes = &c_rowbytes[0][0][0]; tb.n = s_n;
+    tb.ptab = s_ptab; tb.cells = s_cells; tb.rowbytes = &c_rowbytes[0][0][0]; tb.n = s_n;
     TileStats st = {0, 0, 0, 0};
     if (e < p.n) {
-        uint32_t* rec = rsm + (size_t)tid * p.rec_words;
+        // cfg.ids_off is the IN-SLOT offset (P wall columns sit between the columns and the id plane); p.ids_off_g the HBM one
+        COLT* colp = (COLT*)(rsm + (size_t)tid * p.rec_words);   // colp[c + P] = column c, walls on both sides
+        uint32_t* rec = (uint32_t*)(colp + P);
         const uint32_t* grec = (const uint32_t*)(p.board + e * cfg.board_stride);
-        const int nw = cfg.board_stride / 4;
-        for (int i = 0; i < nw; i++) rec[i] = grec[i];
+        const int ncw = p.ids_off_g / 4, nw = cfg.board_stride / 4;     // column words, record words in HBM
+        uint32_t* ids = rec + cfg.ids_off / 4;
+        for (int i = 0; i < ncw; i++) rec[i] = grec[i];
+        for (int i = ncw; i < nw; i++) ids[i - ncw] = grec[i];
+        for (int c = 0; c < P; c++) { colp[c] = ~COLT(0); colp[P + cfg.W + c] = ~COLT(0); }
         Hot h;
         hot_load(h, (const uint32_t*)(p.hot + e * 32));
         Rng g;
@@ -58,7 +68,8 @@ __global__ void __launch_bounds__(128) k_rollout(const __grid_constant__ Rollout
         eb.pre = (COLT*)(rec + p.base_off);
         eb.suf = eb.pre + cfg.W;
         eb.h = (uint8_t*)(eb.suf + cfg.W);
-        eb.ho = eb.h + 32;
+        eb.ho = eb.h + p.hb;
+        eb.bs = (uint16_t*)(eb.ho + p.hb);
         int last = -1;
         for (int step = 0; step < p.k_steps; step++) {
             if (cfg.autoreset == 1 && h.pending) { env_reset<COLT>(cfg, h, rec, g); last = -1; continue; }
@@ -66,14 +77,16 @@ __global__ void __launch_bounds__(128) k_rollout(const __grid_constant__ Rollout
             int best = -1, best_score = 0, first_legal = -1;
             env_base_compute<COLT>(cfg, cols, COLT(1), eb);
             uint32_t slow[3] = {0u, 0u, 0u};   // placements that clear rows: evaluated in a second, short loop
+            const int xoff = P - tb.n[h.p] / 2;   // wrappers/grouped.py:157-158
             for (int a = 0; a < A; a++) {
-                COLT B;
-                Placement pl = eval_placement<COLT>(cfg, tb, cols, h.p, h.r, a, B);
-                if (pl.kind == 1) continue;
+                const int rot = (h.r + (a & 3)) & 3;   // cumulative rot90 presses (wrappers/grouped.py:153-154)
+                FeatSum fs;
+                int y;
+                const int kind = place_fast<COLT>(cfg, eb, colp, tb.cells[h.p * 4 + rot], tb.ptab[h.p * 4 + rot], (a >> 2) + xoff, fs, y, nullptr);
+                if (kind == 1) continue;
                 if (first_legal < 0) first_legal = a;
-                if (pl.kind == 2) continue;
-                FeatSum fs = placement_eval_fast<COLT>(cfg, cols, eb, tb.cells[h.p * 4 + pl.rot], pl.x, pl.y, COLT(1), nullptr, true);
-                if (fs.lines < 0) { slow[a >> 5] |= 1u << (a & 31); continue; }
+                if (kind == 2) continue;
+                if (kind == 3) { slow[a >> 5] |= 1u << (a & 31); continue; }
                 int score = p.w[0] * fs.sum_h + p.w[2] * (int)(uint8_t)fs.holes + p.w[3] * (int)(uint8_t)fs.bump;
                 if (best < 0 || score > best_score) { best = a; best_score = score; }
             }
@@ -108,7 +121,8 @@ __global__ void __launch_bounds__(128) k_rollout(const __grid_constant__ Rollout
         }
         hot_store(h, (uint32_t*)(p.hot + e * 32));
         uint32_t* wrec = (uint32_t*)(p.board + e * cfg.board_stride);
-        for (int i = 0; i < nw; i++) wrec[i] = rec[i];
+        for (int i = 0; i < ncw; i++) wrec[i] = rec[i];
+        for (int i = ncw; i < nw; i++) wrec[i] = ids[i - ncw];
         if (p.last_action) p.last_action[e] = last;
     }
     if (p.stats) {

@@ -25,43 +25,47 @@ __global__ void k_features(const DevCfg cfg, int64_t n, const uint8_t* hot, cons
 }
 
 // grouped observation with FeatureVectorObservation: feats u8[n][A][F], legal u8[n][A]
-// CTA = EPB envs; one thread per env precomputes the EnvBase, then one thread per (env, placement).
+// CTA = EPB envs; one thread per env precomputes the EnvBase (heights, holes, prefix / suffix column ANDs), then one
+// thread per (env, placement) evaluates it from the piece's column profile (place_fast: no bit scans on the common
+// path); placements that clear rows are batched into a second pass with the exact evaluation.
 template <class COLT>
 __global__ void __launch_bounds__(256) k_grouped_feats(const DevCfg cfg, int64_t n, const uint8_t* hot, const uint8_t* board, uint8_t* feats,
                                                        uint8_t* legal, const uint8_t* fill_high, int EPB) {
     extern __shared__ __align__(16) uint8_t sm[];
-    const int W = cfg.W, A = cfg.A, F = cfg.F;
-    COLT* s_cols = (COLT*)sm;                      // [EPB][W]
-    COLT* s_pre = s_cols + (size_t)EPB * W;        // [EPB][W]
+    const int W = cfg.W, A = cfg.A, F = cfg.F, WP = cfg.W + 2 * P;
+    COLT* s_colp = (COLT*)sm;                      // [EPB][W + 2P]  columns with P wall columns on both sides
+    COLT* s_pre = s_colp + (size_t)EPB * WP;       // [EPB][W]
     COLT* s_suf = s_pre + (size_t)EPB * W;         // [EPB][W]
     int* s_sum = (int*)(s_suf + (size_t)EPB * W);  // [EPB][4]: sum_h, holes, bump, max_h
     uint32_t* s_w0 = (uint32_t*)(s_sum + EPB * 4); // [EPB]
     uint8_t* s_h = (uint8_t*)(s_w0 + EPB);         // [EPB][32]
     uint8_t* s_ho = s_h + EPB * 32;                // [EPB][32]
-    uint8_t* s_feats = s_ho + EPB * 32;            // [EPB][A][F]   (16-aligned: every block above is a multiple of 16 for EPB % 4 == 0)
+    uint16_t* s_bs = (uint16_t*)(s_ho + EPB * 32); // [EPB][32]
+    uint8_t* s_feats = (uint8_t*)(s_bs + EPB * 32);   // [EPB][A][F]   (16-aligned: every block above is a multiple of 16 for EPB % 4 == 0)
     uint8_t* s_legal = s_feats + (size_t)EPB * A * F;
     __shared__ unsigned short s_cells[28];
+    __shared__ uint2 s_ptab[28];
     __shared__ int s_n[8];
     __shared__ unsigned short s_slow[16 * 96];   // EPB <= 16, A <= 96
     __shared__ int s_nslow;
-    if (threadIdx.x < 28) s_cells[threadIdx.x] = (&c_cells[0][0])[threadIdx.x];
+    if (threadIdx.x < 28) { s_cells[threadIdx.x] = (&c_cells[0][0])[threadIdx.x]; s_ptab[threadIdx.x] = (&c_ptab[0][0])[threadIdx.x]; }
     if (threadIdx.x < 7) s_n[threadIdx.x] = c_n[threadIdx.x];
     if (threadIdx.x == 0) s_nslow = 0;
     Tabs tb;
-    tb.cells = s_cells; tb.rowbytes = &c_rowbytes[0][0][0]; tb.n = s_n;
+    tb.ptab = s_ptab; tb.cells = s_cells; tb.rowbytes = &c_rowbytes[0][0][0]; tb.n = s_n;
     const int64_t base = (int64_t)blockIdx.x * EPB;
     const int nv = (int)min((int64_t)EPB, n - base);
-    for (int i = threadIdx.x; i < nv * W; i += blockDim.x) {
-        int e = i / W, c = i - e * W;
-        s_cols[i] = ((const COLT*)(board + (base + e) * cfg.board_stride))[c];
+    for (int i = threadIdx.x; i < nv * WP; i += blockDim.x) {
+        int e = i / WP, c = i - e * WP - P;
+        s_colp[i] = (unsigned)c < (unsigned)W ? ((const COLT*)(board + (base + e) * cfg.board_stride))[c] : ~COLT(0);
     }
     for (int i = threadIdx.x; i < nv; i += blockDim.x) s_w0[i] = *(const uint32_t*)(hot + (base + i) * 32);
     __syncthreads();
     if (threadIdx.x < nv) {
         int e = threadIdx.x;
         EnvBase<COLT> eb;
-        eb.h = s_h + e * 32; eb.ho = s_ho + e * 32; eb.pre = s_pre + e * W; eb.suf = s_suf + e * W;
-        env_base_compute<COLT>(cfg, s_cols + e * W, COLT(1), eb);
+        eb.h = s_h + e * 32; eb.ho = s_ho + e * 32; eb.bs = s_bs + e * 32; eb.pre = s_pre + e * W; eb.suf = s_suf + e * W;
+        env_base_compute<COLT>(cfg, s_colp + e * WP + P, COLT(1), eb);
         s_sum[e * 4] = eb.sum_h; s_sum[e * 4 + 1] = eb.holes; s_sum[e * 4 + 2] = eb.bump; s_sum[e * 4 + 3] = eb.max_h;
     }
     __syncthreads();
@@ -69,7 +73,6 @@ __global__ void __launch_bounds__(256) k_grouped_feats(const DevCfg cfg, int64_t
         int e = it / A, a = it - e * A;
         uint32_t w0 = s_w0[e];
         int piece = (w0 >> 13) & 7, rot0 = (w0 >> 16) & 3;
-        const COLT* cols = s_cols + e * W;
         uint8_t* out = s_feats + (size_t)it * F;
         if (fill_high && fill_high[base + e]) {
             // illegal action + terminate: obs = ones * high (wrappers/grouped.py:221-226); legal mask unchanged
@@ -77,20 +80,22 @@ __global__ void __launch_bounds__(256) k_grouped_feats(const DevCfg cfg, int64_t
             s_legal[it] = legal[(base + e) * A + a];
             continue;
         }
-        COLT B;
-        Placement pl = eval_placement<COLT>(cfg, tb, cols, piece, rot0, a, B);
-        s_legal[it] = pl.kind != 1;
-        if (pl.kind == 1) {          // ones board, row 0 zeroed -> heights H-1
+        EnvBase<COLT> eb;
+        eb.h = s_h + e * 32; eb.ho = s_ho + e * 32; eb.bs = s_bs + e * 32; eb.pre = s_pre + e * W; eb.suf = s_suf + e * W;
+        eb.sum_h = s_sum[e * 4]; eb.holes = s_sum[e * 4 + 1]; eb.bump = s_sum[e * 4 + 2]; eb.max_h = s_sum[e * 4 + 3];
+        const int rot = (rot0 + (a & 3)) & 3;              // cumulative rot90 presses (wrappers/grouped.py:153-154)
+        const int x = (a >> 2) + P - tb.n[piece] / 2;      // wrappers/grouped.py:157-158
+        FeatSum fs;
+        int y;
+        const int kind = place_fast<COLT>(cfg, eb, s_colp + e * WP, tb.cells[piece * 4 + rot], tb.ptab[piece * 4 + rot], x, fs, y, out);
+        s_legal[it] = kind != 1;
+        if (kind == 1) {          // ones board, row 0 zeroed -> heights H-1
             for (int i = 0; i <= W; i++) out[i] = (uint8_t)(cfg.H - 1);
             out[W + 1] = 0; out[W + 2] = 0;
-        } else if (pl.kind == 2) {   // zeros board
+        } else if (kind == 2) {   // zeros board
             for (int i = 0; i < F; i++) out[i] = 0;
-        } else {
-            EnvBase<COLT> eb;
-            eb.h = s_h + e * 32; eb.ho = s_ho + e * 32; eb.pre = s_pre + e * W; eb.suf = s_suf + e * W;
-            eb.sum_h = s_sum[e * 4]; eb.holes = s_sum[e * 4 + 1]; eb.bump = s_sum[e * 4 + 2]; eb.max_h = s_sum[e * 4 + 3];
-            FeatSum fs = placement_eval_fast<COLT>(cfg, cols, eb, tb.cells[piece * 4 + pl.rot], pl.x, pl.y, COLT(1), out, true);
-            if (fs.lines < 0) s_slow[atomicAdd(&s_nslow, 1)] = (unsigned short)it;   // rows get cleared: batch the full evaluation
+        } else if (kind == 3) {
+            s_slow[atomicAdd(&s_nslow, 1)] = (unsigned short)it;   // rows get cleared: batch the exact evaluation
         }
     }
     __syncthreads();
@@ -99,8 +104,8 @@ __global__ void __launch_bounds__(256) k_grouped_feats(const DevCfg cfg, int64_t
         uint32_t w0 = s_w0[e];
         int piece = (w0 >> 13) & 7, rot0 = (w0 >> 16) & 3;
         COLT B;
-        Placement pl = eval_placement<COLT>(cfg, tb, s_cols + e * W, piece, rot0, a, B);
-        placement_eval<COLT>(cfg, s_cols + e * W, tb.cells[piece * 4 + pl.rot], pl.x, pl.y, true, true, COLT(1), s_feats + (size_t)it * F);
+        Placement pl = eval_placement<COLT>(cfg, tb, s_colp + e * WP + P, piece, rot0, a, B);
+        placement_eval<COLT>(cfg, s_colp + e * WP + P, tb.cells[piece * 4 + pl.rot], pl.x, pl.y, true, true, COLT(1), s_feats + (size_t)it * F);
     }
     __syncthreads();
     // coalesced copy-out of the tile (contiguous in global memory)
@@ -608,7 +613,7 @@ static int launch_grouped_observe(tg_env* env, tg_state st, int64_t n, uint8_t* 
     if (d_feats) {
         int EPB = 16, T = 256;
         size_t colb = env->col64 ? 8 : 4;
-        size_t smem = (size_t)3 * EPB * d.W * colb + (size_t)EPB * 16 + (size_t)EPB * 4 + (size_t)EPB * 64 + (size_t)EPB * d.A * d.F + (size_t)EPB * d.A;
+        size_t smem = (size_t)EPB * (3 * d.W + 2 * TG_PADDING) * colb + (size_t)EPB * 16 + (size_t)EPB * 4 + (size_t)EPB * 128 + (size_t)EPB * d.A * d.F + (size_t)EPB * d.A;
         if (smem > 48 * 1024) {
             if (env->col64) cudaFuncSetAttribute(k_grouped_feats<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             else cudaFuncSetAttribute(k_grouped_feats<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -710,10 +715,15 @@ extern "C" int tg_rollout(tg_env* env, tg_state st, int64_t n, const int32_t wei
     for (int i = 0; i < 4; i++) p.w[i] = weights[i];
     p.k_steps = k_steps; p.stats = (double*)d_stats;
     p.last_action = (int32_t*)env->rollout_last_action;
-    int words = (d.board_stride + 4) / 4;                 // +1 word: ids_get8 may read one word past the id plane
+    const int cw = env->col64 ? 2 : 1;                    // words per column
+    int words = (d.W + 2 * TG_PADDING) * cw;              // P wall columns | W columns | P wall columns
+    p.ids_off_g = d.ids_off;
+    p.cfg.ids_off = (d.W + TG_PADDING) * cw * 4;   // in-slot offset of the id plane
+    words += (d.board_stride - d.ids_off) / 4 + 1;        // id plane (+1 word: ids_get8 may read one word past it)
     if (env->col64) words = (words + 1) & ~1;             // keep the EnvBase arrays 8-byte aligned
-    p.base_off = words;
-    words += 2 * d.W * (env->col64 ? 2 : 1) + 16;         // pre[W], suf[W], h[32 B], ho[32 B]
+    p.base_off = words - TG_PADDING * cw;                 // measured from the first column
+    p.hb = (d.W + 3) & ~3;
+    words += 2 * d.W * cw + 4 * p.hb / 4;                 // pre[W], suf[W], h, ho, bs (u16)
     // u32 columns: odd word stride; u64 columns: stride = 2 (mod 4) words keeps 8-byte alignment and spreads the banks
     if (env->col64) { while ((words & 3) != 2) words += 1; } else { words |= 1; }
     p.rec_words = words;
