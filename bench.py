@@ -161,6 +161,7 @@ def main():
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="envs per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the grouped / rollout side measurements")
     ap.add_argument("--no-probe", action="store_true", help="skip the commit-fraction probe (torch kernels) e.g. under ncu")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -252,12 +253,70 @@ def main():
         if world > 1:
             dist.all_reduce(tdt, op=dist.ReduceOp.MAX)
         d2h = sum(int(np.prod(v.shape)) * v.dtype.itemsize for v in bufs.values())
+        # context: the same loop when the policy lives on the GPU -- actions H2D, step, only the 5-tuple scalars D2H
+        # (the observation dict stays in HBM, which is how the device API `env.step(cuda_actions)` is used)
+        h_rew = torch.empty(n, dtype=torch.float32, pin_memory=True)
+        h_term = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+        d_act = torch.empty(n, dtype=torch.int32, device=dev)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        for t in range(Ke):
+            d_act.copy_(h_acts[2 + t], non_blocking=True)
+            _, rew, term, _, _ = env.step(d_act)
+            h_rew.copy_(rew, non_blocking=True)
+            h_term.copy_(term.view(torch.uint8), non_blocking=True)
+            torch.cuda.synchronize()
+        dt_s = time.perf_counter() - t1
+        tds = torch.tensor([dt_s], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tds, op=dist.ReduceOp.MAX)
         e2e = {"value": world * n * Ke / float(tdt[0]), "unit": UNIT, "steps": Ke, "h2d_bytes_per_step": 4 * n, "d2h_bytes_per_step": d2h,
-               "note": "tg_step_host: actions from pinned host memory, full observation dict + reward/terminated/truncated/lines read back to pinned host memory every step"}
+               "note": "tg_step_host: actions from pinned host memory, full observation dict + reward/terminated/truncated/lines read back to pinned host memory every step",
+               "obs_on_device": {"value": world * n * Ke / float(tds[0]), "unit": UNIT, "h2d_bytes_per_step": 4 * n, "d2h_bytes_per_step": 5 * n,
+                                 "note": "same loop with the observation dict left in HBM (GPU-resident policy): actions H2D, step, reward + terminated D2H, synchronised every step"}}
+
+    # ---- the other half of BASELINE's metric: grouped placements/s (config 3) and the fused rollout (config 4), short runs ----
+    extra = None
+    layout = env.layout
+    if not args.no_extra:
+        from tetris_gymnasium_b200.wrappers import FeatureVectorObservation, GroupedActionsObservations
+        del env, acts
+        torch.cuda.empty_cache()
+        ng = min(n, 1 << 20)
+        gbase = Tetris(width=WIDTH, height=HEIGHT, gravity=False, queue_size=4, num_envs=ng, device=dev, env_id_offset=rank * ng)
+        genv = GroupedActionsObservations(gbase, observation_wrappers=[FeatureVectorObservation(gbase)])
+        genv.reset(seed=42)
+        Kg, tg_ms = 24, 0.0
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for t in range(Kg + 4):
+            a = torch.multinomial(genv.legal_actions_mask.float() + 1e-9, 1).squeeze(1).to(torch.int32)   # random legal placement (untimed)
+            g0.record()
+            genv.step(a)
+            g1.record()
+            torch.cuda.synchronize()
+            if t >= 4:
+                tg_ms += g0.elapsed_time(g1)
+        Kr = 128
+        gbase.rollout((-51, 76, -36, -18), 16)
+        g0.record()
+        gbase.rollout((-51, 76, -36, -18), Kr)
+        g1.record()
+        torch.cuda.synchronize()
+        tr_ms = g0.elapsed_time(g1)
+        tt = torch.tensor([tg_ms, tr_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        A = gbase.layout.n_placements
+        extra = {"grouped": {"placements_per_s": world * ng * A * Kg / (float(tt[0]) * 1e-3), "env_steps_per_s": world * ng * Kg / (float(tt[0]) * 1e-3),
+                             "config": f"GroupedActionsObservations + FeatureVectorObservation, {WIDTH}x{HEIGHT}, gravity off, {ng} envs/GPU, "
+                                       f"{A} placements x {A and gbase.layout.n_features} features per env-step, random legal placements, {Kg} steps (one event pair per step)"},
+                 "rollout": {"placements_per_s": world * ng * A * Kr / (float(tt[1]) * 1e-3), "env_steps_per_s": world * ng * Kr / (float(tt[1]) * 1e-3),
+                             "config": f"fused heuristic rollout, K = {Kr} steps per launch, {ng} envs/GPU, weights (-51, 76, -36, -18)"}}
+        gbase.close()
 
     if rank == 0:
         peak, peak_src = peaks()
-        bps, obs_bytes = bytes_per_step(env.layout, QUEUE, commit_frac)
+        bps, obs_bytes = bytes_per_step(layout, QUEUE, commit_frac)
         kernel_ms = ms / K     # rank-0 kernel: one k_step launch per step, back to back on the timed stream
         achieved = bps * n / (kernel_ms * 1e-3) / 1e9
         out = {
@@ -276,6 +335,8 @@ def main():
         }
         if e2e is not None:
             out["e2e"] = e2e
+        if extra is not None:
+            out["extra"] = extra
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline()
         tr = os.path.join(ROOT, "profiles", "traffic_r01.json")

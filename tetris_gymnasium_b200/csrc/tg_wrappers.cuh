@@ -30,9 +30,9 @@ __global__ void k_features(const DevCfg cfg, int64_t n, const uint8_t* hot, cons
 // path); placements that clear rows are batched into a second pass with the exact evaluation.
 template <class COLT>
 __global__ void __launch_bounds__(256) k_grouped_feats(const DevCfg cfg, int64_t n, const uint8_t* hot, const uint8_t* board, uint8_t* feats,
-                                                       uint8_t* legal, const uint8_t* fill_high, int EPB) {
+                                                       uint8_t* legal, const uint8_t* fill_high, int EPB, uint32_t magicA) {
     extern __shared__ __align__(16) uint8_t sm[];
-    const int W = cfg.W, A = cfg.A, F = cfg.F, WP = cfg.W + 2 * P;
+    const int W = cfg.W, A = cfg.A, F = cfg.F, WP = cfg.W + 2 * P;   // magicA = ceil(2^20 / A): it / A == (it * magicA) >> 20 for it < EPB * A
     COLT* s_colp = (COLT*)sm;                      // [EPB][W + 2P]  columns with P wall columns on both sides
     COLT* s_pre = s_colp + (size_t)EPB * WP;       // [EPB][W]
     COLT* s_suf = s_pre + (size_t)EPB * W;         // [EPB][W]
@@ -59,7 +59,8 @@ __global__ void __launch_bounds__(256) k_grouped_feats(const DevCfg cfg, int64_t
         int e = i / WP, c = i - e * WP - P;
         s_colp[i] = (unsigned)c < (unsigned)W ? ((const COLT*)(board + (base + e) * cfg.board_stride))[c] : ~COLT(0);
     }
-    for (int i = threadIdx.x; i < nv; i += blockDim.x) s_w0[i] = *(const uint32_t*)(hot + (base + i) * 32);
+    for (int i = threadIdx.x; i < nv; i += blockDim.x)   // bit 31: illegal action + terminate -> the observation is filled with `high`
+        s_w0[i] = (*(const uint32_t*)(hot + (base + i) * 32) & 0x7FFFFFFFu) | ((fill_high && fill_high[base + i]) ? 0x80000000u : 0u);
     __syncthreads();
     if (threadIdx.x < nv) {
         int e = threadIdx.x;
@@ -70,11 +71,11 @@ __global__ void __launch_bounds__(256) k_grouped_feats(const DevCfg cfg, int64_t
     }
     __syncthreads();
     for (int it = threadIdx.x; it < nv * A; it += blockDim.x) {
-        int e = it / A, a = it - e * A;
+        const int e = (int)(((uint32_t)it * magicA) >> 20), a = it - e * A;
         uint32_t w0 = s_w0[e];
         int piece = (w0 >> 13) & 7, rot0 = (w0 >> 16) & 3;
-        uint8_t* out = s_feats + (size_t)it * F;
-        if (fill_high && fill_high[base + e]) {
+        uint8_t* out = s_feats + it * F;
+        if (w0 >> 31) {
             // illegal action + terminate: obs = ones * high (wrappers/grouped.py:221-226); legal mask unchanged
             for (int i = 0; i < F; i++) out[i] = (uint8_t)(cfg.H * cfg.W);
             s_legal[it] = legal[(base + e) * A + a];
@@ -100,29 +101,29 @@ __global__ void __launch_bounds__(256) k_grouped_feats(const DevCfg cfg, int64_t
     }
     __syncthreads();
     for (int k = threadIdx.x; k < s_nslow; k += blockDim.x) {
-        int it = s_slow[k], e = it / A, a = it - e * A;
+        const int it = s_slow[k], e = (int)(((uint32_t)it * magicA) >> 20), a = it - e * A;
         uint32_t w0 = s_w0[e];
         int piece = (w0 >> 13) & 7, rot0 = (w0 >> 16) & 3;
         COLT B;
         Placement pl = eval_placement<COLT>(cfg, tb, s_colp + e * WP + P, piece, rot0, a, B);
-        placement_eval<COLT>(cfg, s_colp + e * WP + P, tb.cells[piece * 4 + pl.rot], pl.x, pl.y, true, true, COLT(1), s_feats + (size_t)it * F);
+        placement_eval<COLT>(cfg, s_colp + e * WP + P, tb.cells[piece * 4 + pl.rot], pl.x, pl.y, true, true, COLT(1), s_feats + it * F);
     }
     __syncthreads();
     // coalesced copy-out of the tile (contiguous in global memory)
     {
-        size_t bytes = (size_t)nv * A * F;
+        const int bytes = nv * A * F;
         uint8_t* g = feats + (size_t)base * A * F;
         if ((bytes & 15) == 0 && (((uintptr_t)g) & 15) == 0) {
-            for (size_t i = threadIdx.x; i < bytes / 16; i += blockDim.x) ((uint4*)g)[i] = ((const uint4*)s_feats)[i];
+            for (int i = threadIdx.x; i < (bytes >> 4); i += blockDim.x) ((uint4*)g)[i] = ((const uint4*)s_feats)[i];
         } else {
-            for (size_t i = threadIdx.x; i < bytes; i += blockDim.x) g[i] = s_feats[i];
+            for (int i = threadIdx.x; i < bytes; i += blockDim.x) g[i] = s_feats[i];
         }
-        size_t lb = (size_t)nv * A;
+        const int lb = nv * A;
         uint8_t* gl = legal + (size_t)base * A;
         if ((lb & 3) == 0 && (((uintptr_t)gl) & 3) == 0) {
-            for (size_t i = threadIdx.x; i < lb / 4; i += blockDim.x) ((uint32_t*)gl)[i] = ((const uint32_t*)s_legal)[i];
+            for (int i = threadIdx.x; i < (lb >> 2); i += blockDim.x) ((uint32_t*)gl)[i] = ((const uint32_t*)s_legal)[i];
         } else {
-            for (size_t i = threadIdx.x; i < lb; i += blockDim.x) gl[i] = s_legal[i];
+            for (int i = threadIdx.x; i < lb; i += blockDim.x) gl[i] = s_legal[i];
         }
     }
 }
@@ -619,8 +620,9 @@ static int launch_grouped_observe(tg_env* env, tg_state st, int64_t n, uint8_t* 
             else cudaFuncSetAttribute(k_grouped_feats<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         }
         unsigned g = (unsigned)((n + EPB - 1) / EPB);
-        if (env->col64) k_grouped_feats<uint64_t><<<g, T, smem, s>>>(d, n, (const uint8_t*)st.hot, (const uint8_t*)st.board, d_feats, d_legal, fill_high, EPB);
-        else k_grouped_feats<uint32_t><<<g, T, smem, s>>>(d, n, (const uint8_t*)st.hot, (const uint8_t*)st.board, d_feats, d_legal, fill_high, EPB);
+        const uint32_t magicA = ((1u << 20) + d.A - 1) / d.A;   // it / A == (it * magicA) >> 20, exact for it < 16 * A, A = 4W <= 96 (enumerated)
+        if (env->col64) k_grouped_feats<uint64_t><<<g, T, smem, s>>>(d, n, (const uint8_t*)st.hot, (const uint8_t*)st.board, d_feats, d_legal, fill_high, EPB, magicA);
+        else k_grouped_feats<uint32_t><<<g, T, smem, s>>>(d, n, (const uint8_t*)st.hot, (const uint8_t*)st.board, d_feats, d_legal, fill_high, EPB, magicA);
         CUDA_TRY(env, cudaGetLastError());
     }
     const bool stream_ok = d_boards && (d.OB & 15) == 0 && (((uintptr_t)d_boards) & 15) == 0 && d.OB <= 4 * 32 * 16 && !getenv("TG_BOARDS_V1");
