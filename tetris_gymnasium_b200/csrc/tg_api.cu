@@ -29,6 +29,7 @@ struct tg_env {
     int warp_specialized; // 1: k_step_ws (logic warp runs a tile ahead of the image warps)
     int fill_warps;       // image/store warps per CTA of k_step_ws
     int logic_warps;      // game-logic warps per CTA of k_step_ws (each runs every logic_warps-th tile of the CTA)
+    int logic_warps_set, fill_warps_set;   // TG_NL / TG_NF given: use them for every launch
     void* rollout_last_action;
     int cnn_h, cnn_w;     // output size the tg_cnn_observe tables in stage[4] were built for
     std::string err;
@@ -206,8 +207,9 @@ extern "C" int tg_create(const tg_config* cfg, int device, tg_env** out) {
     env->fill_warps = 4;
     if (const char* t = getenv("TG_WS")) env->warp_specialized = atoi(t) != 0;
     env->logic_warps = 2;
-    if (const char* t = getenv("TG_NF")) { int v = atoi(t); if (v >= 1 && v <= 6) env->fill_warps = v; }
-    if (const char* t = getenv("TG_NL")) { int v = atoi(t); if (v >= 1 && v <= 4) env->logic_warps = v; }
+    env->logic_warps_set = env->fill_warps_set = 0;
+    if (const char* t = getenv("TG_NF")) { int v = atoi(t); if (v >= 1 && v <= 6) { env->fill_warps = v; env->fill_warps_set = 1; } }
+    if (const char* t = getenv("TG_NL")) { int v = atoi(t); if (v >= 1 && v <= 6) { env->logic_warps = v; env->logic_warps_set = 1; } }
     if (env->logic_warps + env->fill_warps > 8) env->fill_warps = 8 - env->logic_warps;
     int rc = upload_tables(env);
     if (rc != TG_OK) { g_create_err = env->err; delete env; return rc; }
@@ -258,7 +260,11 @@ static int launch_step(tg_env* env, StepParams& p, cudaStream_t s, int force_pla
     const DevCfg& d = env->dev;
     const bool ws = env->warp_specialized && !force_plain;
     int E = ws ? 32 : env->tile;
-    int NL = ws ? env->logic_warps : 0;
+    const bool want_obs = p.o_board != nullptr;
+    // without the observation dict (image / feature / grouped-feature wrappers) the image warps only store records:
+    // the kernel is bound by the game logic, so run more logic warps and drop the image buffers
+    int NL = ws ? (want_obs || env->logic_warps_set ? env->logic_warps : 4) : 0;
+    const int NF = ws ? (want_obs || env->fill_warps_set ? env->fill_warps : 2) : 0;
     int NS = ws ? NL + 2 : 2;
     // shared-memory carve-up
     size_t off = 0;
@@ -272,13 +278,15 @@ static int launch_step(tg_env* env, StepParams& p, cudaStream_t s, int force_pla
         p.off_hot = take((size_t)NS * p.st_hot);
         p.off_brd = take((size_t)NS * p.st_brd);
         p.off_rng = take((size_t)NS * p.st_rng);
-        p.off_iboard = take((size_t)E * d.OB + 16);
-        p.off_imask = take((size_t)E * d.OB + 16);
-        p.off_iholder = take((size_t)E * 16);
-        p.off_iqueue = take((size_t)E * d.OQ);
+        const size_t img_e = (ws && !want_obs) ? 0 : (size_t)E;   // image buffers only when the dict is written
+        p.off_iboard = take(img_e * d.OB + 16);
+        p.off_imask = take(img_e * d.OB + 16);
+        p.off_iholder = take(img_e * 16 + 16);
+        p.off_iqueue = take(img_e * d.OQ + 16);
         p.off_bar = take(32);
         p.off_box = take((size_t)(2 * NS + 1) * E * 4);
         p.off_tab = take(112 * 4 + 64 + 32);
+        p.off_feat = take((size_t)E * 64);
         // large boards: fewer logic warps (= fewer state stages) while that buys another resident CTA
         if (ws && NL > 1 && (227 * 1024) / (off + 1024) < 2) { NL--; continue; }
         if (off <= 100 * 1024 || E == 32) break;
@@ -291,7 +299,7 @@ static int launch_step(tg_env* env, StepParams& p, cudaStream_t s, int force_pla
     p.cfg = d;
     p.E = E;
     p.NL = NL;
-    int T = ws ? 32 * (NL + env->fill_warps) : E * env->threads_per_env;
+    int T = ws ? 32 * (NL + NF) : E * env->threads_per_env;
     if (T > 256) T = 256;
     if (d.W == 10 && d.H == 20) return launch_step_t<10, 20, uint32_t>(env, p, T, off, ws, s);
     if (d.W == 20 && d.H == 40) return launch_step_t<20, 40, uint64_t>(env, p, T, off, ws, s);

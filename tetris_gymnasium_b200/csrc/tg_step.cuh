@@ -75,7 +75,7 @@ struct StepParams {
     int E;                           // envs per tile
     int NL;                          // k_step_ws: logic warps per CTA (state stages = NL + 2)
     // shared-memory carve-up (bytes from the 128-aligned base)
-    int off_hot, off_brd, off_rng, off_iboard, off_imask, off_iholder, off_iqueue, off_bar, off_box, off_tab;
+    int off_hot, off_brd, off_rng, off_iboard, off_imask, off_iholder, off_iqueue, off_bar, off_box, off_tab, off_feat;
     int st_hot, st_brd, st_rng;      // bytes between the two pipeline stages of each state buffer
 };
 
@@ -179,7 +179,7 @@ struct TileStats { double ep, ret, len, lines; };
 
 // Runs reset / step / grouped placement for env `e` whose records sit at slot `slot` of the staged tile.
 // Returns bit0 = board record dirty, bit1 = rng record dirty.  Writes the 5-tuple scalars and s_box[slot].
-template <class COLT>
+template <class COLT, bool INFO = true>
 __device__ __forceinline__ uint32_t logic_one_env(const StepParams& p, const Tabs& tb, int64_t e, int slot, int action,
                                                   uint32_t* s_hot, uint8_t* s_brd, uint8_t* s_rng, uint32_t* s_box,
                                                   TileStats& st) {
@@ -240,7 +240,7 @@ __device__ __forceinline__ uint32_t logic_one_env(const StepParams& p, const Tab
     const uint32_t show = !((Bact >> h.y) & 1);
     s_box[slot] = (uint32_t)h.x | ((uint32_t)h.y << 8) | ((uint32_t)tb.n[h.p] << 16) | (show << 20) |
                   ((uint32_t)h.p << 24) | ((uint32_t)h.r << 28);
-    if (p.mode == 2 && p.info_board) {
+    if (INFO && p.mode == 2 && p.info_board) {
         // info["board"]: FeatureVectorObservation of the real observation (wrappers/grouped.py:260-264)
         uint8_t f[32];
         int ln;
@@ -328,7 +328,7 @@ __device__ __forceinline__ void init_cta(int E, int W, int H, uint32_t* s_rowbyt
     for (int i = tid; i < 112; i += T) s_rowbytes[i] = (&c_rowbytes[0][0][0])[i];
     for (int i = tid; i < 28; i += T) s_cells[i] = (&c_cells[0][0])[i];
     for (int i = tid; i < 7; i += T) s_n[i] = c_n[i];
-    for (int i = tid; i < OB; i += T) {  // env 0's template ...
+    for (int i = tid; i < (E ? OB : 0); i += T) {  // env 0's template ...
         int r = i / Wp, c = i - r * Wp;
         i_board[i] = (r < H && c >= P && c < P + W) ? 0 : 1;
     }
@@ -492,11 +492,11 @@ __global__ void __launch_bounds__(256) k_step_ws(const __grid_constant__ StepPar
         for (int s = 0; s < NS; s++) mbar_init(bar + s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    init_cta(E, W, H, s_rowbytes, s_cells, s_n, i_board, i_mask, tid, T);
+    const bool want_obs = p.o_board != nullptr;
+    init_cta(want_obs ? E : 0, W, H, s_rowbytes, s_cells, s_n, i_board, i_mask, tid, T);   // no image buffers without the obs dict
 
     const int64_t ntiles = (p.n + E - 1) / E;
     const int64_t G = gridDim.x;
-    const bool want_obs = p.o_board != nullptr;
     auto issue_load = [&](int64_t tile, int s) {
         const int64_t base = tile * E;
         const int nv = (int)min((int64_t)E, p.n - base);
@@ -525,8 +525,8 @@ __global__ void __launch_bounds__(256) k_step_ws(const __grid_constant__ StepPar
             mbar_wait(bar + s, (uint32_t)((k / NS) & 1));
             uint32_t dirty = 0;
             if (lane < nv)
-                dirty = logic_one_env<COLT>(p, tb, base + lane, lane, action, (uint32_t*)(smem + p.off_hot + s * p.st_hot),
-                                            smem + p.off_brd + s * p.st_brd, smem + p.off_rng + s * p.st_rng, s_boxes + s * E, st);
+                dirty = logic_one_env<COLT, false>(p, tb, base + lane, lane, action, (uint32_t*)(smem + p.off_hot + s * p.st_hot),
+                                                   smem + p.off_brd + s * p.st_brd, smem + p.off_rng + s * p.st_rng, s_boxes + s * E, st);
             s_flags[s * E + lane] = dirty;
             __syncwarp();
             named_arrive(1 + s, 32 + FT);   // ready[s]: the fill warps may consume stage s
@@ -566,6 +566,43 @@ __global__ void __launch_bounds__(256) k_step_ws(const __grid_constant__ StepPar
                 named_sync(BAR_FILL, FT);
                 mask_set_and_overlay(s_boxes + s * E, nv, s_cells, i_board, i_mask, OB, Wp, ft, FT);
                 for (int i = ft; i < nv; i += FT) s_boxprev[i] = s_boxes[s * E + i];
+            }
+            if (p.mode == 2 && p.info_board) {
+                // info["board"] = FeatureVectorObservation of the real observation (wrappers/grouped.py:260-264): rows 0-1 zeroed,
+                // active piece projected when it does not collide.  One thread per (env, column), then one thread per env.
+                uint8_t* f_h = smem + p.off_feat;          // [E][32] heights
+                uint8_t* f_o = f_h + E * 32;               // [E][32] holes
+                for (int it = ft; it < nv * W; it += FT) {
+                    const int i = it / W, c = it - i * W;
+                    const uint32_t bx = s_boxes[s * E + i];
+                    COLT v = ((const COLT*)(s_brd + i * BS))[c];
+                    if ((bx >> 20) & 1) {
+                        const uint32_t cells = s_cells[((bx >> 24) & 7) * 4 + (bx >> 28)];
+                        const int x = bx & 255, y = (bx >> 8) & 255;
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            const int cc = (cells >> (4 * k)) & 15;
+                            if (x + (cc & 3) - P == c) v |= COLT(1) << (y + (cc >> 2));
+                        }
+                    }
+                    int hgt, hol;
+                    col_features<COLT>(v & ~COLT(3), H, hgt, hol);
+                    f_h[i * 32 + c] = (uint8_t)hgt; f_o[i * 32 + c] = (uint8_t)hol;
+                }
+                named_sync(BAR_FILL, FT);
+                for (int i = ft; i < nv; i += FT) {
+                    int maxh = 0, holes = 0, bump = 0, prev = 0;
+                    uint8_t* o = p.info_board + (base + i) * cfg.F;
+                    for (int c = 0; c < W; c++) {
+                        const int hgt = f_h[i * 32 + c];
+                        o[c] = (uint8_t)hgt;
+                        holes += f_o[i * 32 + c];
+                        maxh = max(maxh, hgt);
+                        if (c > 0) bump += abs(hgt - prev);
+                        prev = hgt;
+                    }
+                    o[W] = (uint8_t)maxh; o[W + 1] = (uint8_t)holes; o[W + 2] = (uint8_t)bump;   // uint8 wrap
+                }
             }
             fence_async_smem();
             named_sync(BAR_FILL, FT);

@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(256) k_grouped_feats(const DevCfg cfg, int64_t
     __shared__ unsigned short s_cells[28];
     __shared__ uint2 s_ptab[28];
     __shared__ int s_n[8];
-    __shared__ unsigned short s_slow[16 * 96];   // EPB <= 16, A <= 96
+    __shared__ unsigned short s_slow[32 * 96];   // EPB <= 32, A <= 96
     __shared__ int s_nslow;
     if (threadIdx.x < 28) { s_cells[threadIdx.x] = (&c_cells[0][0])[threadIdx.x]; s_ptab[threadIdx.x] = (&c_ptab[0][0])[threadIdx.x]; }
     if (threadIdx.x < 7) s_n[threadIdx.x] = c_n[threadIdx.x];
@@ -612,7 +612,7 @@ static int launch_grouped_observe(tg_env* env, tg_state st, int64_t n, uint8_t* 
                                   const uint8_t* fill_high, cudaStream_t s) {
     const DevCfg& d = env->dev;
     if (d_feats) {
-        int EPB = 16, T = 256;
+        int EPB = 32, T = 256;             // 32 envs x 4W placements = a whole number of 256-thread rounds
         size_t colb = env->col64 ? 8 : 4;
         size_t smem = (size_t)EPB * (3 * d.W + 2 * TG_PADDING) * colb + (size_t)EPB * 16 + (size_t)EPB * 4 + (size_t)EPB * 128 + (size_t)EPB * d.A * d.F + (size_t)EPB * d.A;
         if (smem > 48 * 1024) {
@@ -620,7 +620,7 @@ static int launch_grouped_observe(tg_env* env, tg_state st, int64_t n, uint8_t* 
             else cudaFuncSetAttribute(k_grouped_feats<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         }
         unsigned g = (unsigned)((n + EPB - 1) / EPB);
-        const uint32_t magicA = ((1u << 20) + d.A - 1) / d.A;   // it / A == (it * magicA) >> 20, exact for it < 16 * A, A = 4W <= 96 (enumerated)
+        const uint32_t magicA = ((1u << 20) + d.A - 1) / d.A;   // it / A == (it * magicA) >> 20, exact for it < 32 * A, A = 4W <= 96 (enumerated)
         if (env->col64) k_grouped_feats<uint64_t><<<g, T, smem, s>>>(d, n, (const uint8_t*)st.hot, (const uint8_t*)st.board, d_feats, d_legal, fill_high, EPB, magicA);
         else k_grouped_feats<uint32_t><<<g, T, smem, s>>>(d, n, (const uint8_t*)st.hot, (const uint8_t*)st.board, d_feats, d_legal, fill_high, EPB, magicA);
         CUDA_TRY(env, cudaGetLastError());
