@@ -149,6 +149,27 @@ def c5_wide_rgb(out):
          "GBps": bps * (1 << 18) / dt / 1e9, "frac_of_hbm_peak": bps * (1 << 18) / dt / 1e9 / PEAK})
 
 
+def c6_functional(out):
+    """Functional facade (envs/tetris_fn.py batched_step): explicit State in / out every call (board i8[24,18] + scalars)."""
+    from tetris_gymnasium_b200.envs import tetris_fn as F
+    from tetris_gymnasium_b200.functional.core import EnvConfig
+    from tetris_gymnasium_b200.functional.tetrominoes import TETROMINOES
+
+    cfg = EnvConfig(width=10, height=20, padding=4, queue_size=7)
+    for n in (65536, 1 << 20):
+        keys = torch.stack([torch.arange(n, device="cuda"), torch.full((n,), 42, device="cuda")], dim=1)
+        keys, state, obs = F.batched_reset(TETROMINOES, keys, config=cfg)
+        acts = torch.randint(0, 7, (24, n), dtype=torch.int32, device="cuda")
+        box = {"s": state}
+
+        def step(i=0):
+            box["s"], _, _, _, _ = F.batched_step(TETROMINOES, box["s"], acts[i % 24], config=cfg)
+        dt = timed(step, 20)
+        bps = 2 * 432 + 200 + 2 * 4 * 16 + 4 + 9
+        out({"config": "C6 functional facade batched_step 10x20 (State in/out every call, incl. the host-side State packing)", "envs": n,
+             "ms": dt * 1e3, "env_steps_per_s": n / dt, "GBps": bps * n / dt / 1e9, "frac_of_hbm_peak": bps * n / dt / 1e9 / PEAK})
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=None)
@@ -161,7 +182,7 @@ def main():
         rows.append(d)
         print(json.dumps(d), flush=True)
 
-    for name, fn in (("c1", c1_latency), ("c2", c2_sweep), ("c3", c3_grouped), ("c4", c4_rollout), ("c5", c5_wide_rgb)):
+    for name, fn in (("c1", c1_latency), ("c2", c2_sweep), ("c3", c3_grouped), ("c4", c4_rollout), ("c5", c5_wide_rgb), ("c6", c6_functional)):
         if not args.only or name in args.only.split(","):
             fn(out)
     if args.out:

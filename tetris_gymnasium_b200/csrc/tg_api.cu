@@ -287,9 +287,10 @@ static int launch_step(tg_env* env, StepParams& p, cudaStream_t s, int force_pla
         p.off_box = take((size_t)(2 * NS + 1) * E * 4);
         p.off_tab = take(112 * 4 + 64 + 32);
         p.off_feat = take((size_t)E * 64);
-        // large boards: fewer logic warps (= fewer state stages) while that buys another resident CTA
+        // large boards: fewer logic warps (= fewer state stages), then half tiles, while that buys another resident CTA
         if (ws && NL > 1 && (227 * 1024) / (off + 1024) < 2) { NL--; continue; }
-        if (off <= 100 * 1024 || E == 32) break;
+        if (ws && E == 32 && (227 * 1024) / (off + 1024) < 2 && !getenv("TG_E32")) { E = 16; NL = env->logic_warps; continue; }
+        if (ws || off <= 100 * 1024 || E == 32) break;
         E -= 32;
     }
     if (off > 227 * 1024) {

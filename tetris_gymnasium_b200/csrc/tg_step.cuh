@@ -464,7 +464,7 @@ template <int WT, int HT, class COLT>
 __global__ void __launch_bounds__(256) k_step_ws(const __grid_constant__ StepParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const DevCfg& cfg = p.cfg;
-    constexpr int E = 32;
+    const int E = p.E;                              // envs per tile (<= 32: one logic-warp lane per env)
     const int NL = p.NL, NS = p.NL + 2;             // logic warps; state stages in flight
     const int T = blockDim.x, tid = threadIdx.x;
     const int FT = T - 32 * NL, ft = tid - 32 * NL; // fill threads
@@ -527,7 +527,7 @@ __global__ void __launch_bounds__(256) k_step_ws(const __grid_constant__ StepPar
             if (lane < nv)
                 dirty = logic_one_env<COLT, false>(p, tb, base + lane, lane, action, (uint32_t*)(smem + p.off_hot + s * p.st_hot),
                                                    smem + p.off_brd + s * p.st_brd, smem + p.off_rng + s * p.st_rng, s_boxes + s * E, st);
-            s_flags[s * E + lane] = dirty;
+            if (lane < E) s_flags[s * E + lane] = dirty;
             __syncwarp();
             named_arrive(1 + s, 32 + FT);   // ready[s]: the fill warps may consume stage s
         }
