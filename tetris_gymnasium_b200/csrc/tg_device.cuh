@@ -536,11 +536,15 @@ __device__ __forceinline__ Placement eval_placement(const DevCfg& cfg, const Tab
 // needs no bit scan at all: in a touched column the new height is max(h, H - top) (the piece came down from above, but a
 // poked board may hold cells above it) and popc grows by the column's cell count, so holes' = h' - (h - ho) - cells.
 // `colp` is the column array padded with P all-ones wall columns on both sides (colp[c + P] = column c).
-// Returns 0 = regular (fs / out filled), 1 = frame (illegal), 2 = game over, 3 = regular but rows get cleared or a cell
-// lands in the row the feature wrapper zeroes: the caller runs the exact placement_eval (rare).
+// Row clears stay on this path too: with F = the cleared rows, a column keeps its cells u = v & ~F in order, packed
+// towards the floor, so its top cell (row t = ctz(u)) ends at row t + popc(F >> (t + 1)) and popc(u) cells remain; the
+// result's row 0 is empty after a clear, so the wrapper's row zeroing (Q1) has no effect there.
+// Returns 0 = regular (fs / out filled), 1 = frame (illegal), 2 = game over, 3 = regular, no row cleared, but a cell of the
+// piece lands in playfield row 0, the row the feature wrapper zeroes: the caller runs the exact placement_eval (rare);
+// 4 = rows get cleared and `defer_clear` was set.
 template <class COLT>
 __device__ __forceinline__ int place_fast(const DevCfg& cfg, const EnvBase<COLT>& b, const COLT* colp, uint32_t cells, uint2 pt, int x,
-                                          FeatSum& fs, int& y_out, uint8_t* out) {
+                                          FeatSum& fs, int& y_out, uint8_t* out, bool defer_clear = false) {
     const int W = cfg.W, H = cfg.H;
     COLT B = 0;
 #pragma unroll
@@ -573,7 +577,32 @@ __device__ __forceinline__ int place_fast(const DevCfg& cfg, const EnvBase<COLT>
             maxh = max(maxh, hn);
         }
     }
-    if (full != 0 || top0) return 3;
+    if (full != 0) {
+        if (defer_clear) return 4;   // the caller batches row-clearing placements (warp divergence) and calls again without the flag
+        // Tetris.clear_filled_rows on the projected copy (wrappers/grouped.py:171-177), column by column
+        const COLT keep = ~full & ((COLT(1) << H) - 1);
+        int s_sum = 0, s_max = 0, s_hol = 0, s_bmp = 0, prev = 0;
+        for (int c = 0; c < W; c++) {
+            COLT v = colp[c + P];
+            const int t = c - c0;
+            if ((unsigned)t <= (unsigned)(c1 - c0)) v |= (COLT)((pt.x >> (4 * (jmin + t))) & 15u) << y;
+            const COLT u = v & keep;
+            int hgt = 0, hol = 0;
+            if (u != 0) {
+                const int tp = ctz_t<COLT>(u);
+                hgt = H - tp - popc_t<COLT>((full >> tp) >> 1);
+                hol = hgt - popc_t<COLT>(u);
+            }
+            if (out) out[c] = (uint8_t)hgt;
+            s_sum += hgt; s_hol += hol; s_max = max(s_max, hgt);
+            if (c > 0) s_bmp += abs(hgt - prev);
+            prev = hgt;
+        }
+        if (out) { out[W] = (uint8_t)s_max; out[W + 1] = (uint8_t)s_hol; out[W + 2] = (uint8_t)s_bmp; }
+        fs.lines = popc_t<COLT>(full); fs.sum_h = s_sum; fs.max_h = s_max; fs.holes = s_hol; fs.bump = s_bmp;
+        return 0;
+    }
+    if (top0) return 3;
     // bumpiness: only the pairs (c, c+1), c = c0-1 .. c1, change; their old sum comes from the prefix array
     {
         const int wdt = c1 - c0;       // touched columns - 1

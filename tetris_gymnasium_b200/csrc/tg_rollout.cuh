@@ -76,18 +76,18 @@ __global__ void __launch_bounds__(128, 6) k_rollout(const __grid_constant__ Roll
             // ---- enumerate + score ----
             int best = -1, best_score = 0, first_legal = -1;
             env_base_compute<COLT>(cfg, cols, COLT(1), eb);
-            uint32_t slow[3] = {0u, 0u, 0u};   // placements that clear rows: evaluated in a second, short loop
+            uint32_t slow[3] = {0u, 0u, 0u};    // placements with a piece cell in the zeroed row 0 (rare): exact evaluation in a second loop
             const int xoff = P - tb.n[h.p] / 2;   // wrappers/grouped.py:157-158
             for (int a = 0; a < A; a++) {
                 const int rot = (h.r + (a & 3)) & 3;   // cumulative rot90 presses (wrappers/grouped.py:153-154)
                 FeatSum fs;
                 int y;
-                const int kind = place_fast<COLT>(cfg, eb, colp, tb.cells[h.p * 4 + rot], tb.ptab[h.p * 4 + rot], (a >> 2) + xoff, fs, y, nullptr);
+                const int kind = place_fast<COLT>(cfg, eb, colp, tb.cells[h.p * 4 + rot], tb.ptab[h.p * 4 + rot], (a >> 2) + xoff, fs, y, nullptr, false);
                 if (kind == 1) continue;
                 if (first_legal < 0) first_legal = a;
                 if (kind == 2) continue;
-                if (kind == 3) { slow[a >> 5] |= 1u << (a & 31); continue; }
-                int score = p.w[0] * fs.sum_h + p.w[2] * (int)(uint8_t)fs.holes + p.w[3] * (int)(uint8_t)fs.bump;
+                if (kind >= 3) { slow[a >> 5] |= 1u << (a & 31); continue; }
+                int score = p.w[0] * fs.sum_h + p.w[1] * fs.lines + p.w[2] * (int)(uint8_t)fs.holes + p.w[3] * (int)(uint8_t)fs.bump;
                 if (best < 0 || score > best_score) { best = a; best_score = score; }
             }
 #pragma unroll
@@ -96,9 +96,12 @@ __global__ void __launch_bounds__(128, 6) k_rollout(const __grid_constant__ Roll
                 while (m) {
                     int a = wi * 32 + __ffs((int)m) - 1;
                     m &= m - 1;
-                    COLT B;
-                    Placement pl = eval_placement<COLT>(cfg, tb, cols, h.p, h.r, a, B);
-                    FeatSum fs = placement_eval<COLT>(cfg, cols, tb.cells[h.p * 4 + pl.rot], pl.x, pl.y, true, true, COLT(1), nullptr);
+                    const int rot = (h.r + (a & 3)) & 3;
+                    FeatSum fs;
+                    int y;
+                    const int kind = place_fast<COLT>(cfg, eb, colp, tb.cells[h.p * 4 + rot], tb.ptab[h.p * 4 + rot], (a >> 2) + xoff, fs, y, nullptr, false);
+                    if (kind == 3)   // a piece cell in the zeroed row 0, no clear: exact evaluation
+                        fs = placement_eval<COLT>(cfg, cols, tb.cells[h.p * 4 + rot], (a >> 2) + xoff, y, true, true, COLT(1), nullptr);
                     int score = p.w[0] * fs.sum_h + p.w[1] * fs.lines + p.w[2] * (int)(uint8_t)fs.holes + p.w[3] * (int)(uint8_t)fs.bump;
                     // lowest index among the maxima: a later candidate wins only if strictly better, an earlier one on ties
                     if (best < 0 || score > best_score || (score == best_score && a < best)) { best = a; best_score = score; }

@@ -88,15 +88,15 @@ __global__ void __launch_bounds__(256) k_grouped_feats(const DevCfg cfg, int64_t
         const int x = (a >> 2) + P - tb.n[piece] / 2;      // wrappers/grouped.py:157-158
         FeatSum fs;
         int y;
-        const int kind = place_fast<COLT>(cfg, eb, s_colp + e * WP, tb.cells[piece * 4 + rot], tb.ptab[piece * 4 + rot], x, fs, y, out);
+        const int kind = place_fast<COLT>(cfg, eb, s_colp + e * WP, tb.cells[piece * 4 + rot], tb.ptab[piece * 4 + rot], x, fs, y, out, true);
         s_legal[it] = kind != 1;
         if (kind == 1) {          // ones board, row 0 zeroed -> heights H-1
             for (int i = 0; i <= W; i++) out[i] = (uint8_t)(cfg.H - 1);
             out[W + 1] = 0; out[W + 2] = 0;
         } else if (kind == 2) {   // zeros board
             for (int i = 0; i < F; i++) out[i] = 0;
-        } else if (kind == 3) {
-            s_slow[atomicAdd(&s_nslow, 1)] = (unsigned short)it;   // rows get cleared: batch the exact evaluation
+        } else if (kind >= 3) {
+            s_slow[atomicAdd(&s_nslow, 1)] = (unsigned short)it;   // rows get cleared / a cell in the zeroed row 0: second pass
         }
     }
     __syncthreads();
@@ -104,9 +104,15 @@ __global__ void __launch_bounds__(256) k_grouped_feats(const DevCfg cfg, int64_t
         const int it = s_slow[k], e = (int)(((uint32_t)it * magicA) >> 20), a = it - e * A;
         uint32_t w0 = s_w0[e];
         int piece = (w0 >> 13) & 7, rot0 = (w0 >> 16) & 3;
-        COLT B;
-        Placement pl = eval_placement<COLT>(cfg, tb, s_colp + e * WP + P, piece, rot0, a, B);
-        placement_eval<COLT>(cfg, s_colp + e * WP + P, tb.cells[piece * 4 + pl.rot], pl.x, pl.y, true, true, COLT(1), s_feats + it * F);
+        EnvBase<COLT> eb;
+        eb.h = s_h + e * 32; eb.ho = s_ho + e * 32; eb.bs = s_bs + e * 32; eb.pre = s_pre + e * W; eb.suf = s_suf + e * W;
+        eb.sum_h = s_sum[e * 4]; eb.holes = s_sum[e * 4 + 1]; eb.bump = s_sum[e * 4 + 2]; eb.max_h = s_sum[e * 4 + 3];
+        const int rot = (rot0 + (a & 3)) & 3, x = (a >> 2) + P - tb.n[piece] / 2;
+        FeatSum fs;
+        int y;
+        const int kind = place_fast<COLT>(cfg, eb, s_colp + e * WP, tb.cells[piece * 4 + rot], tb.ptab[piece * 4 + rot], x, fs, y, s_feats + it * F, false);
+        if (kind == 3)
+            placement_eval<COLT>(cfg, s_colp + e * WP + P, tb.cells[piece * 4 + rot], x, y, true, true, COLT(1), s_feats + it * F);
     }
     __syncthreads();
     // coalesced copy-out of the tile (contiguous in global memory)
