@@ -330,3 +330,36 @@ def test_true_randomizer_numpy_exact_and_philox():
     e2 = Tetris(num_envs=n // 2, randomizer="true", queue_size=16, autoreset_mode="disabled", env_id_offset=n // 2)
     e2.reset(seed=3)              # per-env seed = seed + global env id: same (seed, id) pairs as the second half of e1
     assert np.array_equal(np_(e2.get_state()["queue"]), q1[n // 2:])
+
+
+def test_record_episode_statistics_vector_format():
+    """RecordEpisodeStatistics in the SyncVectorEnv info format (examples/train_lin_grouped.py:148, :316-322): episode
+    return / length reported at the terminal step with the `_episode` mask, NEXT_STEP autoreset step not counted; the
+    per-env sums agree with the oracle's trajectories and with the on-device totals (tg_stats)."""
+    from tetris_gymnasium_b200.envs.tetris import Tetris
+    from tetris_gymnasium_b200.wrappers import RecordEpisodeStatistics
+    from gpu_util import OracleBatch, np_
+
+    n, T = 150, 400
+    rng = np.random.default_rng(4)
+    seqs = rng.integers(0, 7, size=(n, 33)).astype(np.uint8)
+    base = Tetris(num_envs=n, randomizer_mode="sequence", piece_sequences=seqs, autoreset_mode="next_step")
+    env = RecordEpisodeStatistics(base)
+    orc = OracleBatch(n, seqs=seqs)
+    env.reset(); orc.reset()
+    base.episode_stats(reset=True)
+    ret, length = np.zeros(n, np.float32), np.zeros(n, np.int64)
+    n_eps, sum_r, sum_l = 0, 0.0, 0
+    for t in range(T):
+        a = rng.choice([0, 1, 3, 5, 5, 6], size=n)
+        pend = orc.pending.copy()
+        _, r, term, trunc, info = env.step(torch.from_numpy(a))
+        _, r2, t2, _ = orc.step(a)
+        ret[pend] = 0; length[pend] = 0
+        ret[~pend] += r2[~pend]; length[~pend] += 1
+        assert np.array_equal(np_(info["_episode"]), t2)
+        assert np.array_equal(np_(info["episode"]["r"]), np.where(t2, ret, 0).astype(np.float32))
+        assert np.array_equal(np_(info["episode"]["l"]), np.where(t2, length, 0))
+        n_eps += int(t2.sum()); sum_r += float(ret[t2].sum()); sum_l += int(length[t2].sum())
+    st = base.episode_stats()
+    assert n_eps > 20 and int(st["episodes"]) == n_eps and int(st["sum_length"]) == sum_l and abs(float(st["sum_return"]) - sum_r) < 1e-3 * max(1.0, sum_r)

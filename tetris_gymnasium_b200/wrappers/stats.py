@@ -1,0 +1,58 @@
+"""Trainer-side bookkeeping wrappers of the reference's examples, on device tensors.
+
+RecordEpisodeStatistics mirrors `gym.wrappers.RecordEpisodeStatistics` as the examples use it inside a
+`SyncVectorEnv` (examples/train_lin_grouped.py:148, examples/train_cnn.py:135), in the vector-env info format
+(`info["episode"] = {"r", "l", "t"}` with the `info["_episode"]` mask; gymnasium 1.x wrappers/vector/common.py -- third-party,
+restated from its published behaviour).  Everything is a handful of elementwise torch ops on [n] tensors: plumbing, not a kernel.
+The library also accumulates whole-run totals on device (`env.unwrapped.episode_stats()`, tg_stats)."""
+import time
+
+import torch
+
+
+class RecordEpisodeStatistics:
+    def __init__(self, env):
+        self.env = env
+        u = env.unwrapped
+        n, dev = u.num_envs, u.device
+        self.episode_returns = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.episode_lengths = torch.zeros(n, dtype=torch.int32, device=dev)
+        self.prev_dones = torch.zeros(n, dtype=torch.bool, device=dev)
+        self.episode_count = 0
+        self._t0 = time.perf_counter()
+        self.action_space = getattr(env, "action_space", None)
+        self.observation_space = getattr(env, "observation_space", None)
+
+    @property
+    def unwrapped(self):
+        return self.env.unwrapped
+
+    def __getattr__(self, name):
+        return getattr(self.env, name)
+
+    def reset(self, *, seed=None, options=None):
+        out = self.env.reset(seed=seed, options=options)
+        self.episode_returns.zero_(); self.episode_lengths.zero_(); self.prev_dones.zero_()
+        self._t0 = time.perf_counter()
+        return out
+
+    def step(self, action):
+        obs, reward, terminated, truncated, info = self.env.step(action)
+        # envs that finished on the previous step are being reset by this call (NEXT_STEP autoreset): start from zero
+        self.episode_returns.masked_fill_(self.prev_dones, 0.0)
+        self.episode_lengths.masked_fill_(self.prev_dones, 0)
+        live = ~self.prev_dones
+        self.episode_returns += reward * live
+        self.episode_lengths += live.to(torch.int32)
+        dones = terminated | truncated
+        self.prev_dones = dones.clone()
+        info = dict(info)
+        zero = torch.zeros((), device=reward.device)
+        info["episode"] = {"r": torch.where(dones, self.episode_returns, zero),
+                           "l": torch.where(dones, self.episode_lengths, zero.to(torch.int32)),
+                           "t": torch.where(dones, torch.full_like(self.episode_returns, time.perf_counter() - self._t0), zero)}
+        info["_episode"] = dones
+        return obs, reward, terminated, truncated, info
+
+    def close(self):
+        return self.env.close()
