@@ -267,8 +267,6 @@ static int launch_step(tg_env* env, StepParams& p, cudaStream_t s, int force_pla
     int NL = ws ? (want_obs || env->logic_warps_set ? env->logic_warps : 4) : 0;
     const int NF = ws ? (want_obs || env->fill_warps_set ? env->fill_warps : 2) : 0;
     int NS = ws ? NL + 2 : 2;
-    int isets = 1;
-    if (const char* t = getenv("TG_ISETS")) isets = atoi(t) == 2 ? 2 : 1;
     // shared-memory carve-up
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 127) / 128 * 128; return (int)o; };
@@ -282,16 +280,12 @@ static int launch_step(tg_env* env, StepParams& p, cudaStream_t s, int force_pla
         p.off_brd = take((size_t)NS * p.st_brd);
         p.off_rng = take((size_t)NS * p.st_rng);
         const size_t img_e = (ws && !want_obs) ? 0 : (size_t)E;   // image buffers only when the dict is written
-        p.isets = (ws && want_obs) ? isets : 1;
-        p.st_iboard = (int)((img_e * d.OB + 16 + 127) / 128 * 128);
-        p.st_iholder = (int)((img_e * 16 + 16 + 127) / 128 * 128);
-        p.st_iqueue = (int)((img_e * d.OQ + 16 + 127) / 128 * 128);
-        p.off_iboard = take((size_t)p.isets * p.st_iboard);
-        p.off_imask = take((size_t)p.isets * p.st_iboard);
-        p.off_iholder = take((size_t)p.isets * p.st_iholder);
-        p.off_iqueue = take((size_t)p.isets * p.st_iqueue);
+        p.off_iboard = take(img_e * d.OB + 16);
+        p.off_imask = take(img_e * d.OB + 16);
+        p.off_iholder = take(img_e * 16 + 16);
+        p.off_iqueue = take(img_e * d.OQ + 16);
         p.off_bar = take(32);
-        p.off_box = take((size_t)(2 * NS + 2) * E * 4);
+        p.off_box = take((size_t)(2 * NS + 1) * E * 4);
         p.off_tab = take(112 * 4 + 64 + 32);
         p.off_feat = take((size_t)E * 64);
         // large boards: fewer logic warps (= fewer state stages), then half tiles, while that buys another resident CTA

@@ -74,8 +74,6 @@ struct StepParams {
     int mode;                        // 0 = step, 1 = reset, 2 = grouped placement step
     int E;                           // envs per tile
     int NL;                          // k_step_ws: logic warps per CTA (state stages = NL + 2)
-    int isets;                       // k_step_ws: image sets per CTA (2: the images of tile k+1 are produced while the stores of tile k read theirs)
-    int st_iboard, st_iholder, st_iqueue;   // bytes between the image sets
     // shared-memory carve-up (bytes from the 128-aligned base)
     int off_hot, off_brd, off_rng, off_iboard, off_imask, off_iholder, off_iqueue, off_bar, off_box, off_tab, off_feat;
     int st_hot, st_brd, st_rng;      // bytes between the two pipeline stages of each state buffer
@@ -482,24 +480,20 @@ __global__ void __launch_bounds__(256) k_step_ws(const __grid_constant__ StepPar
     uint64_t* bar = (uint64_t*)(smem + p.off_bar);     // full[NS]
     uint32_t* s_boxes = (uint32_t*)(smem + p.off_box); // [NS][E] boxes, [NS][E] dirty flags, [E] boxes of the previous tile (fill-private)
     uint32_t* s_flags = s_boxes + NS * E;
-    uint32_t* s_boxprev = s_flags + NS * E;             // [isets][E]
+    uint32_t* s_boxprev = s_flags + NS * E;
     uint32_t* s_rowbytes = (uint32_t*)(smem + p.off_tab);
     unsigned short* s_cells = (unsigned short*)(s_rowbytes + 112);
     int* s_n = (int*)(s_rowbytes + 112 + 16);
     Tabs tb;
     tb.cells = s_cells; tb.rowbytes = s_rowbytes; tb.n = s_n;
 
-    for (int i = tid; i < (2 * NS + 2) * E; i += T) s_boxes[i] = 0;
+    for (int i = tid; i < (2 * NS + 1) * E; i += T) s_boxes[i] = 0;
     if (tid == 0) {
         for (int s = 0; s < NS; s++) mbar_init(bar + s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     const bool want_obs = p.o_board != nullptr;
     init_cta(want_obs ? E : 0, W, H, s_rowbytes, s_cells, s_n, i_board, i_mask, tid, T);   // no image buffers without the obs dict
-    if (want_obs && p.isets == 2) {
-        __syncthreads();
-        init_cta(E, W, H, s_rowbytes, s_cells, s_n, i_board + p.st_iboard, i_mask + p.st_iboard, tid, T);
-    }
 
     const int64_t ntiles = (p.n + E - 1) / E;
     const int64_t G = gridDim.x;
@@ -552,8 +546,7 @@ __global__ void __launch_bounds__(256) k_step_ws(const __grid_constant__ StepPar
     } else {
         // ===== image / store warps =====
         const bool leader = (ft == 0);
-        const bool two = p.isets == 2;
-        int nv_prev[2] = {0, 0}, s = 0;
+        int nv_prev = 0, s = 0;
         for (int64_t k = 0; blockIdx.x + k * G < ntiles; k++, s = (s + 1 == NS ? 0 : s + 1)) {
             const int64_t tile = blockIdx.x + k * G;
             const int64_t base = tile * E;
@@ -561,27 +554,18 @@ __global__ void __launch_bounds__(256) k_step_ws(const __grid_constant__ StepPar
             uint32_t* s_hot = (uint32_t*)(smem + p.off_hot + s * p.st_hot);
             uint8_t* s_brd = smem + p.off_brd + s * p.st_brd;
             uint8_t* s_rng = smem + p.off_rng + s * p.st_rng;
-            const int iset = two ? (int)(k & 1) : 0;     // image set of this tile
-            uint8_t* t_board = i_board + iset * p.st_iboard;
-            uint8_t* t_mask = i_mask + iset * p.st_iboard;
-            uint8_t* t_holder = i_holder + iset * p.st_iholder;
-            uint8_t* t_queue = i_queue + iset * p.st_iqueue;
-            uint32_t* t_boxprev = s_boxprev + iset * E;
             named_sync(1 + s, 32 + FT);                 // logic of this tile is done, stage s is final
             mbar_wait(bar + s, (uint32_t)((k / NS) & 1));   // (already complete) acquire the TMA writes
-            // stores that read the state stage of tile k-1 (hot + dirty records) must be done before that stage is reloaded;
-            // with two image sets the leader's image stores of tile k-1 (its most recent group) may still be reading
-            if (leader && two) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-            else bulk_wait_read();
+            bulk_wait_read();                           // stores of the previous tile have left shared memory
             named_sync(BAR_FILL, FT);
             // the stage of tile k-1 is free again: prefetch NS-1 tiles ahead into it
             if (leader && tile + (NS - 1) * G < ntiles) issue_load(tile + (NS - 1) * G, s == 0 ? NS - 1 : s - 1);
             if (want_obs) {
-                mask_clear_boxes(t_boxprev, nv_prev[iset], t_mask, OB, Wp, ft, FT);
-                fill_images<WT, HT>(cfg, nv, s_hot, s_brd, s_rowbytes, t_board, t_holder, t_queue, ft, FT);
+                mask_clear_boxes(s_boxprev, nv_prev, i_mask, OB, Wp, ft, FT);
+                fill_images<WT, HT>(cfg, nv, s_hot, s_brd, s_rowbytes, i_board, i_holder, i_queue, ft, FT);
                 named_sync(BAR_FILL, FT);
-                mask_set_and_overlay(s_boxes + s * E, nv, s_cells, t_board, t_mask, OB, Wp, ft, FT);
-                for (int i = ft; i < nv; i += FT) t_boxprev[i] = s_boxes[s * E + i];
+                mask_set_and_overlay(s_boxes + s * E, nv, s_cells, i_board, i_mask, OB, Wp, ft, FT);
+                for (int i = ft; i < nv; i += FT) s_boxprev[i] = s_boxes[s * E + i];
             }
             if (p.mode == 2 && p.info_board) {
                 // info["board"] = FeatureVectorObservation of the real observation (wrappers/grouped.py:260-264): rows 0-1 zeroed,
@@ -622,7 +606,14 @@ __global__ void __launch_bounds__(256) k_step_ws(const __grid_constant__ StepPar
             }
             fence_async_smem();
             named_sync(BAR_FILL, FT);
-            // group 1: stores that read the state stage (hot records, dirty board / rng records)
+            if (want_obs) {
+                tile_store(p.o_board + base * OB, i_board, (uint32_t)(nv * OB), leader, ft, FT);
+                tile_store(p.o_mask + base * OB, i_mask, (uint32_t)(nv * OB), leader, ft, FT);
+                if (leader) {
+                    bulk_s2g(p.o_holder + base * 16, i_holder, (uint32_t)(nv * 16));
+                    bulk_s2g(p.o_queue + base * OQ, i_queue, (uint32_t)(nv * OQ));
+                }
+            }
             if (leader) bulk_s2g(p.hot + base * 32, s_hot, (uint32_t)(nv * 32));
             for (int i = ft; i < nv; i += FT) {
                 uint32_t d = s_flags[s * E + i];
@@ -630,17 +621,7 @@ __global__ void __launch_bounds__(256) k_step_ws(const __grid_constant__ StepPar
                 if (d & 2) bulk_s2g(p.rng + (base + i) * RS, s_rng + i * RS, (uint32_t)RS);
             }
             bulk_commit();
-            // group 2 (leader): the observation images of this tile
-            if (want_obs) {
-                tile_store(p.o_board + base * OB, t_board, (uint32_t)(nv * OB), leader, ft, FT);
-                tile_store(p.o_mask + base * OB, t_mask, (uint32_t)(nv * OB), leader, ft, FT);
-                if (leader) {
-                    bulk_s2g(p.o_holder + base * 16, t_holder, (uint32_t)(nv * 16));
-                    bulk_s2g(p.o_queue + base * OQ, t_queue, (uint32_t)(nv * OQ));
-                    bulk_commit();
-                }
-            }
-            nv_prev[iset] = want_obs ? nv : 0;
+            nv_prev = want_obs ? nv : 0;
         }
         bulk_wait_all();
     }
