@@ -260,7 +260,7 @@ static int launch_step(tg_env* env, StepParams& p, cudaStream_t s, int force_pla
     const DevCfg& d = env->dev;
     const bool ws = env->warp_specialized && !force_plain;
     int E = ws ? 32 : env->tile;
-    if (ws) if (const char* t = getenv("TG_E")) { int v = atoi(t); if (v == 8 || v == 16 || v == 32) E = v; }
+    if (ws) if (const char* t = getenv("TG_E")) { int v = atoi(t); if (v >= 8 && v <= 32 && (v & 1) == 0) E = v; }
     const bool want_obs = p.o_board != nullptr;
     // without the observation dict (image / feature / grouped-feature wrappers) the image warps only store records:
     // the kernel is bound by the game logic, so run more logic warps and drop the image buffers
