@@ -29,6 +29,7 @@ struct tg_env {
     int warp_specialized; // 1: k_step_ws (logic warp runs a tile ahead of the image warps)
     int fill_warps;       // image/store warps per CTA of k_step_ws
     int logic_warps;      // game-logic warps per CTA of k_step_ws (each runs every logic_warps-th tile of the CTA)
+    int l2hint;           // TG_L2HINT: L2 eviction-priority hints of the k_step_ws bulk copies (see StepParams::l2hint)
     int logic_warps_set, fill_warps_set;   // TG_NL / TG_NF given: use them for every launch
     void* rollout_last_action;
     int cnn_h, cnn_w;     // output size the tg_cnn_observe tables in stage[4] were built for
@@ -207,6 +208,8 @@ extern "C" int tg_create(const tg_config* cfg, int device, tg_env** out) {
     env->fill_warps = 4;
     if (const char* t = getenv("TG_WS")) env->warp_specialized = atoi(t) != 0;
     env->logic_warps = 2;
+    env->l2hint = 0;
+    if (const char* t = getenv("TG_L2HINT")) env->l2hint = atoi(t) & 7;
     env->logic_warps_set = env->fill_warps_set = 0;
     if (const char* t = getenv("TG_NF")) { int v = atoi(t); if (v >= 1 && v <= 6) { env->fill_warps = v; env->fill_warps_set = 1; } }
     if (const char* t = getenv("TG_NL")) { int v = atoi(t); if (v >= 1 && v <= 6) { env->logic_warps = v; env->logic_warps_set = 1; } }
@@ -301,6 +304,7 @@ static int launch_step(tg_env* env, StepParams& p, cudaStream_t s, int force_pla
     p.cfg = d;
     p.E = E;
     p.NL = NL;
+    p.l2hint = env->l2hint;
     int T = ws ? 32 * (NL + NF) : E * env->threads_per_env;
     if (T > 256) T = 256;
     if (d.W == 10 && d.H == 20) return launch_step_t<10, 20, uint32_t>(env, p, T, off, ws, s);

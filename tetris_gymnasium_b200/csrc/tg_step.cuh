@@ -44,6 +44,29 @@ __device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, u
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes)
                  : "memory");
 }
+// same copies with an L2 eviction-priority hint (createpolicy): the observation images are written once and never read by
+// this kernel again (evict_first), the state records are re-read by the next step (evict_last keeps small batches in L2)
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void bulk_g2s_hint(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar, uint64_t pol) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_s2g_hint(void* dst_gmem, const void* src_smem, uint32_t bytes, uint64_t pol) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)),
+                 "r"(bytes), "l"(pol)
+                 : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -74,6 +97,7 @@ struct StepParams {
     int mode;                        // 0 = step, 1 = reset, 2 = grouped placement step
     int E;                           // envs per tile
     int NL;                          // k_step_ws: logic warps per CTA (state stages = NL + 2)
+    int l2hint;                      // k_step_ws: bit0 obs stores evict_first, bit1 state loads evict_first, bit2 state loads + stores evict_last
     // shared-memory carve-up (bytes from the 128-aligned base)
     int off_hot, off_brd, off_rng, off_iboard, off_imask, off_iholder, off_iqueue, off_bar, off_box, off_tab, off_feat;
     int st_hot, st_brd, st_rng;      // bytes between the two pipeline stages of each state buffer
@@ -497,13 +521,22 @@ __global__ void __launch_bounds__(256) k_step_ws(const __grid_constant__ StepPar
 
     const int64_t ntiles = (p.n + E - 1) / E;
     const int64_t G = gridDim.x;
+    const int hint = p.l2hint;
+    const uint64_t pol_obs = l2_policy_evict_first();
+    const uint64_t pol_st = (hint & 4) ? l2_policy_evict_last() : l2_policy_evict_first();
     auto issue_load = [&](int64_t tile, int s) {
         const int64_t base = tile * E;
         const int nv = (int)min((int64_t)E, p.n - base);
         mbar_expect_tx(bar + s, (uint32_t)(nv * (32 + BS + RS)));
-        bulk_g2s(smem + p.off_hot + s * p.st_hot, p.hot + base * 32, (uint32_t)(nv * 32), bar + s);
-        bulk_g2s(smem + p.off_brd + s * p.st_brd, p.board + base * BS, (uint32_t)(nv * BS), bar + s);
-        bulk_g2s(smem + p.off_rng + s * p.st_rng, p.rng + base * RS, (uint32_t)(nv * RS), bar + s);
+        if (hint & 6) {
+            bulk_g2s_hint(smem + p.off_hot + s * p.st_hot, p.hot + base * 32, (uint32_t)(nv * 32), bar + s, pol_st);
+            bulk_g2s_hint(smem + p.off_brd + s * p.st_brd, p.board + base * BS, (uint32_t)(nv * BS), bar + s, pol_st);
+            bulk_g2s_hint(smem + p.off_rng + s * p.st_rng, p.rng + base * RS, (uint32_t)(nv * RS), bar + s, pol_st);
+        } else {
+            bulk_g2s(smem + p.off_hot + s * p.st_hot, p.hot + base * 32, (uint32_t)(nv * 32), bar + s);
+            bulk_g2s(smem + p.off_brd + s * p.st_brd, p.board + base * BS, (uint32_t)(nv * BS), bar + s);
+            bulk_g2s(smem + p.off_rng + s * p.st_rng, p.rng + base * RS, (uint32_t)(nv * RS), bar + s);
+        }
     };
     if (ft == 0) {   // the fill leader owns all TMA traffic: tiles 0 .. NS-2 of this CTA go to stages 0 .. NS-2
         for (int j = 0; j < NS - 1; j++)
@@ -607,18 +640,36 @@ __global__ void __launch_bounds__(256) k_step_ws(const __grid_constant__ StepPar
             fence_async_smem();
             named_sync(BAR_FILL, FT);
             if (want_obs) {
-                tile_store(p.o_board + base * OB, i_board, (uint32_t)(nv * OB), leader, ft, FT);
-                tile_store(p.o_mask + base * OB, i_mask, (uint32_t)(nv * OB), leader, ft, FT);
-                if (leader) {
-                    bulk_s2g(p.o_holder + base * 16, i_holder, (uint32_t)(nv * 16));
-                    bulk_s2g(p.o_queue + base * OQ, i_queue, (uint32_t)(nv * OQ));
+                if ((hint & 1) && ((nv * OB) & 15) == 0 && ((uintptr_t)(p.o_board + base * OB) & 15u) == 0 && ((uintptr_t)(p.o_mask + base * OB) & 15u) == 0) {
+                    if (leader) {
+                        bulk_s2g_hint(p.o_board + base * OB, i_board, (uint32_t)(nv * OB), pol_obs);
+                        bulk_s2g_hint(p.o_mask + base * OB, i_mask, (uint32_t)(nv * OB), pol_obs);
+                        bulk_s2g_hint(p.o_holder + base * 16, i_holder, (uint32_t)(nv * 16), pol_obs);
+                        bulk_s2g_hint(p.o_queue + base * OQ, i_queue, (uint32_t)(nv * OQ), pol_obs);
+                    }
+                } else {
+                    tile_store(p.o_board + base * OB, i_board, (uint32_t)(nv * OB), leader, ft, FT);
+                    tile_store(p.o_mask + base * OB, i_mask, (uint32_t)(nv * OB), leader, ft, FT);
+                    if (leader) {
+                        bulk_s2g(p.o_holder + base * 16, i_holder, (uint32_t)(nv * 16));
+                        bulk_s2g(p.o_queue + base * OQ, i_queue, (uint32_t)(nv * OQ));
+                    }
                 }
             }
-            if (leader) bulk_s2g(p.hot + base * 32, s_hot, (uint32_t)(nv * 32));
-            for (int i = ft; i < nv; i += FT) {
-                uint32_t d = s_flags[s * E + i];
-                if (d & 1) bulk_s2g(p.board + (base + i) * BS, s_brd + i * BS, (uint32_t)BS);
-                if (d & 2) bulk_s2g(p.rng + (base + i) * RS, s_rng + i * RS, (uint32_t)RS);
+            if (hint & 4) {
+                if (leader) bulk_s2g_hint(p.hot + base * 32, s_hot, (uint32_t)(nv * 32), pol_st);
+                for (int i = ft; i < nv; i += FT) {
+                    uint32_t d = s_flags[s * E + i];
+                    if (d & 1) bulk_s2g_hint(p.board + (base + i) * BS, s_brd + i * BS, (uint32_t)BS, pol_st);
+                    if (d & 2) bulk_s2g_hint(p.rng + (base + i) * RS, s_rng + i * RS, (uint32_t)RS, pol_st);
+                }
+            } else {
+                if (leader) bulk_s2g(p.hot + base * 32, s_hot, (uint32_t)(nv * 32));
+                for (int i = ft; i < nv; i += FT) {
+                    uint32_t d = s_flags[s * E + i];
+                    if (d & 1) bulk_s2g(p.board + (base + i) * BS, s_brd + i * BS, (uint32_t)BS);
+                    if (d & 2) bulk_s2g(p.rng + (base + i) * RS, s_rng + i * RS, (uint32_t)RS);
+                }
             }
             bulk_commit();
             nv_prev = want_obs ? nv : 0;
