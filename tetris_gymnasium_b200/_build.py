@@ -32,7 +32,7 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc not found: cannot build libtetris_b200.so (there is no CPU fallback)")
     cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
            "-Xcompiler", "-fPIC", "-shared", "--use_fast_math", "-Xptxas", "-v" if verbose else "-O3",
-           "-o", LIB, os.path.join(CSRC, "tg_api.cu"), "-lcudart"]
+           "-o", LIB, os.path.join(CSRC, "tg_api.cu"), "-lcudart"] + os.environ.get("TG_NVCC_FLAGS", "").split()
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)

@@ -13,6 +13,7 @@
 #include "tg_step.cuh"
 #include "tg_aux.cuh"
 #include "tg_rollout.cuh"
+#include "tg_gfeats.cuh"
 #include "tg_fn.cuh"
 
 using namespace tg;
@@ -70,6 +71,7 @@ static const unsigned char kColors[9][3] = {{0, 0, 0}, {128, 128, 128}, {0, 240,
 static int upload_tables(tg_env* env) {
     unsigned short cells[7][4];
     uint2 ptab[7][4];
+    uint4 prec[7][4];
     unsigned int rowbytes[7][4][4];
     unsigned char colors[16][4];
     memset(colors, 0, sizeof colors);
@@ -113,10 +115,18 @@ static int upload_tables(tg_env* env) {
                 if (!((px >> (4 * j)) & 15u)) return fail(env, TG_ERR_CONFIG, "piece table: empty column inside a piece");
             px |= (unsigned)jmin << 24 | (unsigned)jmax << 26;
             ptab[p][r] = make_uint2(px, py);
+            // packed-byte profile of k_grouped_feats_x (tg_gfeats.cuh)
+            unsigned int m4 = 0, top4 = 0, mintop = 3;
+            for (int j = 0; j < 4; j++) {
+                unsigned mask = (px >> (4 * j)) & 15u, top = (px >> (16 + 2 * j)) & 3u;
+                if (mask) { m4 |= 0xFFu << (8 * j); top4 |= top << (8 * j); if (top < mintop) mintop = top; }
+            }
+            prec[p][r] = make_uint4((unsigned)c | ((px & 0xFFFFu) << 16), m4, top4, (unsigned)jmin | (unsigned)jmax << 2 | mintop << 4);
         }
     }
     CUDA_TRY(env, cudaMemcpyToSymbol(c_cells, cells, sizeof cells));
     CUDA_TRY(env, cudaMemcpyToSymbol(c_ptab, ptab, sizeof ptab));
+    CUDA_TRY(env, cudaMemcpyToSymbol(c_prec, prec, sizeof prec));
     CUDA_TRY(env, cudaMemcpyToSymbol(c_rowbytes, rowbytes, sizeof rowbytes));
     CUDA_TRY(env, cudaMemcpyToSymbol(c_n, kN, sizeof kN));
     CUDA_TRY(env, cudaMemcpyToSymbol(c_colors, colors, sizeof colors));
@@ -208,7 +218,7 @@ extern "C" int tg_create(const tg_config* cfg, int device, tg_env** out) {
     env->fill_warps = 4;
     if (const char* t = getenv("TG_WS")) env->warp_specialized = atoi(t) != 0;
     env->logic_warps = 2;
-    env->l2hint = 0;
+    env->l2hint = 1;      // observation images: L2 evict_first (+3 % on the 4M-env step; TG_L2HINT=0 restores the default policy)
     if (const char* t = getenv("TG_L2HINT")) env->l2hint = atoi(t) & 7;
     env->logic_warps_set = env->fill_warps_set = 0;
     if (const char* t = getenv("TG_NF")) { int v = atoi(t); if (v >= 1 && v <= 6) { env->fill_warps = v; env->fill_warps_set = 1; } }
@@ -248,6 +258,7 @@ template <int WT, int HT, class COLT>
 static int launch_step_t(tg_env* env, StepParams& p, int T, size_t smem, bool ws, cudaStream_t s) {
     auto kern = ws ? k_step_ws<WT, HT, COLT> : k_step<WT, HT, COLT>;
     CUDA_TRY(env, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (!getenv("TG_NO_CARVEOUT")) CUDA_TRY(env, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     int per_sm = 0;
     CUDA_TRY(env, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, T, smem));
     if (per_sm < 1) return fail(env, TG_ERR_CONFIG, "step kernel does not fit: %zu B shared memory per CTA", smem);
@@ -269,13 +280,15 @@ static int launch_step(tg_env* env, StepParams& p, cudaStream_t s, int force_pla
     // the kernel is bound by the game logic, so run more logic warps and drop the image buffers
     int NL = ws ? (want_obs || env->logic_warps_set ? env->logic_warps : 4) : 0;
     const int NF = ws ? (want_obs || env->fill_warps_set ? env->fill_warps : 2) : 0;
-    int NS = ws ? NL + 2 : 2;
+    int nsx = 2;                                   // stages beyond the ones the logic warps are working on
+    if (const char* t = getenv("TG_NSX")) { int v = atoi(t); if (v >= 2 && v <= 8) nsx = v; }
+    int NS = ws ? NL + nsx : 2;
     // shared-memory carve-up
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 127) / 128 * 128; return (int)o; };
     for (;;) {
         off = 0;
-        NS = ws ? NL + 2 : 2;
+        NS = ws ? NL + nsx : 2;
         p.st_hot = (int)(((size_t)E * 32 + 127) / 128 * 128);
         p.st_brd = (int)(((size_t)E * d.board_stride + 16 + 127) / 128 * 128);
         p.st_rng = (int)(((size_t)E * d.rng_stride + 127) / 128 * 128);
@@ -287,7 +300,7 @@ static int launch_step(tg_env* env, StepParams& p, cudaStream_t s, int force_pla
         p.off_imask = take(img_e * d.OB + 16);
         p.off_iholder = take(img_e * 16 + 16);
         p.off_iqueue = take(img_e * d.OQ + 16);
-        p.off_bar = take(32);
+        p.off_bar = take(8 * 16);
         p.off_box = take((size_t)(2 * NS + 1) * E * 4);
         p.off_tab = take(112 * 4 + 64 + 32);
         p.off_feat = take((size_t)E * 64);
@@ -304,7 +317,10 @@ static int launch_step(tg_env* env, StepParams& p, cudaStream_t s, int force_pla
     p.cfg = d;
     p.E = E;
     p.NL = NL;
+    p.NS = NS;
     p.l2hint = env->l2hint;
+    p.whole_tile_min = E / 2;
+    if (const char* t = getenv("TG_WHOLE")) p.whole_tile_min = atoi(t);
     int T = ws ? 32 * (NL + NF) : E * env->threads_per_env;
     if (T > 256) T = 256;
     if (d.W == 10 && d.H == 20) return launch_step_t<10, 20, uint32_t>(env, p, T, off, ws, s);

@@ -96,7 +96,9 @@ struct StepParams {
     uint8_t* fill_high;              // grouped mode: u8[n], 1 = illegal action terminated the episode
     int mode;                        // 0 = step, 1 = reset, 2 = grouped placement step
     int E;                           // envs per tile
-    int NL;                          // k_step_ws: logic warps per CTA (state stages = NL + 2)
+    int NL;                          // k_step_ws: logic warps per CTA
+    int NS;                          // k_step_ws: state stages in flight (NL + 2 by default)
+    int whole_tile_min;              // k_step_ws: dirty envs in a tile from which the board records leave as one bulk copy
     int l2hint;                      // k_step_ws: bit0 obs stores evict_first, bit1 state loads evict_first, bit2 state loads + stores evict_last
     // shared-memory carve-up (bytes from the 128-aligned base)
     int off_hot, off_brd, off_rng, off_iboard, off_imask, off_iholder, off_iqueue, off_bar, off_box, off_tab, off_feat;
@@ -489,7 +491,7 @@ __global__ void __launch_bounds__(256) k_step_ws(const __grid_constant__ StepPar
     extern __shared__ __align__(128) uint8_t smem[];
     const DevCfg& cfg = p.cfg;
     const int E = p.E;                              // envs per tile (<= 32: one logic-warp lane per env)
-    const int NL = p.NL, NS = p.NL + 2;             // logic warps; state stages in flight
+    const int NL = p.NL, NS = p.NS;                 // logic warps; state stages in flight (>= NL + 2)
     const int T = blockDim.x, tid = threadIdx.x;
     const int FT = T - 32 * NL, ft = tid - 32 * NL; // fill threads
     const int W = WT ? WT : cfg.W, H = HT ? HT : cfg.H;
@@ -560,7 +562,9 @@ __global__ void __launch_bounds__(256) k_step_ws(const __grid_constant__ StepPar
             if (lane < nv)
                 dirty = logic_one_env<COLT, false>(p, tb, base + lane, lane, action, (uint32_t*)(smem + p.off_hot + s * p.st_hot),
                                                    smem + p.off_brd + s * p.st_brd, smem + p.off_rng + s * p.st_rng, s_boxes + s * E, st);
-            if (lane < E) s_flags[s * E + lane] = dirty;
+            // tiles where most envs committed (always in the grouped mode) write their board records back as ONE bulk copy
+            const int ndirty = __popc(__ballot_sync(0xffffffffu, (dirty & 1u) != 0));
+            if (lane < E) s_flags[s * E + lane] = dirty | ((uint32_t)ndirty << 8);
             __syncwarp();
             named_arrive(1 + s, 32 + FT);   // ready[s]: the fill warps may consume stage s
         }
@@ -656,18 +660,21 @@ __global__ void __launch_bounds__(256) k_step_ws(const __grid_constant__ StepPar
                     }
                 }
             }
+            const bool whole = (int)(s_flags[s * E] >> 8) >= p.whole_tile_min;   // unchanged records are rewritten with the same bytes
             if (hint & 4) {
                 if (leader) bulk_s2g_hint(p.hot + base * 32, s_hot, (uint32_t)(nv * 32), pol_st);
+                if (leader && whole) bulk_s2g_hint(p.board + base * BS, s_brd, (uint32_t)(nv * BS), pol_st);
                 for (int i = ft; i < nv; i += FT) {
                     uint32_t d = s_flags[s * E + i];
-                    if (d & 1) bulk_s2g_hint(p.board + (base + i) * BS, s_brd + i * BS, (uint32_t)BS, pol_st);
+                    if ((d & 1) && !whole) bulk_s2g_hint(p.board + (base + i) * BS, s_brd + i * BS, (uint32_t)BS, pol_st);
                     if (d & 2) bulk_s2g_hint(p.rng + (base + i) * RS, s_rng + i * RS, (uint32_t)RS, pol_st);
                 }
             } else {
                 if (leader) bulk_s2g(p.hot + base * 32, s_hot, (uint32_t)(nv * 32));
+                if (leader && whole) bulk_s2g(p.board + base * BS, s_brd, (uint32_t)(nv * BS));
                 for (int i = ft; i < nv; i += FT) {
                     uint32_t d = s_flags[s * E + i];
-                    if (d & 1) bulk_s2g(p.board + (base + i) * BS, s_brd + i * BS, (uint32_t)BS);
+                    if ((d & 1) && !whole) bulk_s2g(p.board + (base + i) * BS, s_brd + i * BS, (uint32_t)BS);
                     if (d & 2) bulk_s2g(p.rng + (base + i) * RS, s_rng + i * RS, (uint32_t)RS);
                 }
             }

@@ -614,10 +614,31 @@ extern "C" int tg_render_rgb(tg_env* env, tg_state st, int64_t n, uint8_t* d_img
     return env->col64 ? launch(k_rgb<uint64_t>) : launch(k_rgb<uint32_t>);
 }
 
+// packed-byte kernel (tg_gfeats.cuh) for the two board widths of BASELINE.json; the generic kernel covers the rest
+static bool gfeats_fast(const tg_env* env, const uint8_t* d_feats, const uint8_t* d_legal) {
+    return d_feats && (env->dev.W == 10 || env->dev.W == 20) && (((uintptr_t)d_feats | (uintptr_t)d_legal) & 15) == 0 && !getenv("TG_GFEATS_V1");
+}
+
+// d_info_board (nullable): info["board"] computed by the packed-byte kernel (only passed when gfeats_fast() holds)
 static int launch_grouped_observe(tg_env* env, tg_state st, int64_t n, uint8_t* d_feats, uint8_t* d_boards, uint8_t* d_legal,
-                                  const uint8_t* fill_high, cudaStream_t s) {
+                                  const uint8_t* fill_high, cudaStream_t s, uint8_t* d_info_board = nullptr) {
     const DevCfg& d = env->dev;
-    if (d_feats) {
+    const bool fast_x = gfeats_fast(env, d_feats, d_legal);
+    if (fast_x) {
+        auto launch = [&](auto kern, size_t smem, int T) -> int {
+            CUDA_TRY(env, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CUDA_TRY(env, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            kern<<<(unsigned)((n + 31) / 32), T, smem, s>>>(d, n, (const uint8_t*)st.hot, (const uint8_t*)st.board, d_feats, d_legal, fill_high, d_info_board);
+            CUDA_TRY(env, cudaGetLastError());
+            return TG_OK;
+        };
+        int rc;
+        if (d.W == 10) rc = env->col64 ? launch(k_grouped_feats_x<10, uint64_t>, GFeatsSmem<10, uint64_t>::bytes, 320)
+                                       : launch(k_grouped_feats_x<10, uint32_t>, GFeatsSmem<10, uint32_t>::bytes, 320);
+        else rc = env->col64 ? launch(k_grouped_feats_x<20, uint64_t>, GFeatsSmem<20, uint64_t>::bytes, 640)
+                             : launch(k_grouped_feats_x<20, uint32_t>, GFeatsSmem<20, uint32_t>::bytes, 640);
+        if (rc) return rc;
+    } else if (d_feats) {
         int EPB = 32, T = 256;             // 32 envs x 4W placements = a whole number of 256-thread rounds
         size_t colb = env->col64 ? 8 : 4;
         size_t smem = (size_t)EPB * (3 * d.W + 2 * TG_PADDING) * colb + (size_t)EPB * 16 + (size_t)EPB * 4 + (size_t)EPB * 128 + (size_t)EPB * d.A * d.F + (size_t)EPB * d.A;
@@ -703,10 +724,14 @@ extern "C" int tg_grouped_step(tg_env* env, tg_state st, int64_t n, const int32_
     p.o_board = obs.board; p.o_mask = obs.mask; p.o_holder = obs.holder; p.o_queue = obs.queue;
     p.reward = out.reward; p.terminated = out.terminated; p.truncated = out.truncated; p.lines = out.lines;
     p.stats = (double*)d_stats;
-    p.legal = d_legal; p.info_board = d_info_board; p.fill_high = (uint8_t*)env->stage[3];
+    // with the packed-byte feature kernel info["board"] is a by-product of its column pass, not of the step kernel
+    const bool info_in_feats = d_info_board && gfeats_fast(env, d_feats, d_legal) && !getenv("TG_INFO_IN_STEP");
+    p.legal = d_legal; p.info_board = info_in_feats ? nullptr : d_info_board; p.fill_high = (uint8_t*)env->stage[3];
     p.mode = 2;
     rc = launch_step(env, p, (cudaStream_t)stream); if (rc) return rc;
-    if (d_feats || d_boards) return launch_grouped_observe(env, st, n, d_feats, d_boards, d_legal, (const uint8_t*)env->stage[3], (cudaStream_t)stream);
+    if (d_feats || d_boards)
+        return launch_grouped_observe(env, st, n, d_feats, d_boards, d_legal, (const uint8_t*)env->stage[3], (cudaStream_t)stream,
+                                      info_in_feats ? d_info_board : nullptr);
     return TG_OK;
 }
 
