@@ -253,3 +253,70 @@ def test_grouped_boards_with_line_clears_vs_oracle(W, H):
         _, wb, wl = o.grouped_observe(features=False, boards=True)
         assert np.array_equal(np_(g)[i], wb) and np.array_equal(np_(info["action_mask"])[i], wl), i
     base.close()
+
+
+@pytest.mark.parametrize("W,H", [(10, 20), (20, 40), (10, 40), (20, 24), (13, 30)], ids=lambda v: str(v))
+def test_grouped_features_on_constructed_boards_vs_oracle(W, H):
+    """Feature enumeration (GroupedActionsObservations + FeatureVectorObservation) on constructed boards: nearly full bottom
+    rows with wells (many of the 4W placements clear 1-4 rows), rubble, and for a third of the envs stacks that reach the
+    spawn rows (placements that end in row 0 / game-over placements).  (10,20) (20,40) (10,40) (20,24) take the packed-byte
+    kernel with u32 / u64 columns, (13,30) the generic one."""
+    from gpu_util import np_
+    from oracle.tetris_oracle import OracleEnv
+    from tetris_gymnasium_b200.envs.tetris import Tetris
+    from tetris_gymnasium_b200.wrappers import FeatureVectorObservation, GroupedActionsObservations
+
+    n, A = 96, 4 * W
+    rng = np.random.default_rng(11 * W + H)
+    seqs = rng.integers(0, 7, size=(n, 31)).astype(np.uint8)
+    base = Tetris(width=W, height=H, gravity=False, queue_size=3, num_envs=n, randomizer_mode="sequence",
+                  piece_sequences=seqs, autoreset_mode="disabled")
+    env = GroupedActionsObservations(base, observation_wrappers=[FeatureVectorObservation(base)])
+    env.reset()
+    orcs = [OracleEnv(width=W, height=H, gravity=False, queue_size=3) for _ in range(n)]
+    boards = np.empty((n, H + 4, W + 8), np.uint8)
+    pieces, rots = rng.integers(0, 7, n), rng.integers(0, 4, n)
+    for i, o in enumerate(orcs):
+        o.set_sequence(seqs[i])
+        o.reset()
+        b = o.board
+        k = int(rng.integers(1, 6))
+        b[H - k:H, 4:4 + W] = rng.integers(2, 9, size=(k, W))
+        wells = rng.choice(W, size=int(rng.integers(1, 3)), replace=False)
+        depth = int(rng.integers(1, k + 1))
+        b[H - k:H - k + depth, 4 + wells] = 0
+        noise = rng.random((3, W)) < 0.3
+        b[H - k - 3:H - k, 4:4 + W] = np.where(noise, rng.integers(2, 9, size=(3, W)), 0)
+        if i % 3 == 0:                                    # towers into the spawn rows, holes inside
+            for c in rng.choice(W, size=int(rng.integers(1, W)), replace=False):
+                top = int(rng.integers(0, 6))
+                col = np.where(rng.random(H - k - top) < 0.8, rng.integers(2, 9, size=H - k - top), 0)
+                col[0] = 3
+                b[top:H - k, 4 + c] = col
+        o.board = b
+        o.set_active(int(pieces[i]), int(rots[i]))
+        boards[i] = b
+    base.set_state(board=boards, piece=pieces, rotation=rots)
+    got = np_(env.observation())
+    cleared = kinds2 = 0
+    want_legal = np.empty((n, A), np.uint8)
+    for i, o in enumerate(orcs):
+        wf, _, wl = o.grouped_observe(features=True, boards=False)
+        _, _, ln = o.grouped_observe_lines()
+        cleared += int((ln > 0).sum())
+        kinds2 += int(((wf == 0).all(1) & (wl > 0)).sum())
+        want_legal[i] = wl
+        if not np.array_equal(got[i], wf):
+            bad = np.flatnonzero((got[i] != wf).any(1))
+            raise AssertionError(f"env {i} piece {pieces[i]} rot {rots[i]}: placements {bad[:6]} differ\n got:\n{got[i][bad[:6]]}\n want:\n{wf[bad[:6]]}")
+    assert np.array_equal(np_(env.legal_actions_mask), want_legal)
+    assert cleared > n and kinds2 > 0
+    a = np.array([int(rng.choice(np.flatnonzero(want_legal[i]))) for i in range(n)])
+    g, r, term, _, info = env.step(torch.from_numpy(a))
+    for i, o in enumerate(orcs):
+        code, rr, tt, ll = o.grouped_step(int(a[i]), True)
+        assert (float(np_(r)[i]), bool(np_(term)[i]), int(np_(info["lines_cleared"])[i])) == (np.float32(rr), tt, ll), i
+        wf, _, wl = o.grouped_observe(features=True, boards=False)
+        assert np.array_equal(np_(g)[i], wf) and np.array_equal(np_(info["action_mask"])[i], wl), i
+        assert np.array_equal(np_(info["board"])[i], o.features(o.obs())), i
+    base.close()

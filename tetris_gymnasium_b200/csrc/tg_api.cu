@@ -12,8 +12,8 @@
 #include "tg_device.cuh"
 #include "tg_step.cuh"
 #include "tg_aux.cuh"
-#include "tg_rollout.cuh"
 #include "tg_gfeats.cuh"
+#include "tg_rollout.cuh"
 #include "tg_fn.cuh"
 
 using namespace tg;

@@ -11,6 +11,7 @@
 // autoreset follow the env config; episode statistics are reduced per CTA and added atomically.
 #pragma once
 #include "tg_device.cuh"
+#include "tg_gfeats.cuh"
 
 namespace tg {
 
@@ -112,6 +113,211 @@ __global__ void __launch_bounds__(128, 6) k_rollout(const __grid_constant__ Roll
             // ---- execute (GroupedActionsObservations.step, wrappers/grouped.py:241-259) ----
             StepResult res;
             h.x = (action >> 2) + P - tb.n[h.p] / 2;
+            h.r = (h.r + (action & 3)) & 3;
+            env_step<COLT>(cfg, tb, h, rec, g, cfg.act_hard, res);
+            h.ep_ret += (float)res.reward; h.ep_len += 1; h.ep_lines += res.lines;
+            if (res.terminated) {
+                st.ep += 1; st.ret += h.ep_ret; st.len += h.ep_len; st.lines += h.ep_lines;
+                h.ep_ret = 0; h.ep_len = 0; h.ep_lines = 0;
+                if (cfg.autoreset == 1) h.pending = 1;
+                else if (cfg.autoreset == 2) env_reset<COLT>(cfg, h, rec, g);
+            }
+        }
+        hot_store(h, (uint32_t*)(p.hot + e * 32));
+        uint32_t* wrec = (uint32_t*)(p.board + e * cfg.board_stride);
+        for (int i = 0; i < ncw; i++) wrec[i] = rec[i];
+        for (int i = ncw; i < nw; i++) wrec[i] = ids[i - ncw];
+        if (p.last_action) p.last_action[e] = last;
+    }
+    if (p.stats) {
+        for (int o = 16; o > 0; o >>= 1) {
+            st.ep += __shfl_xor_sync(0xffffffffu, st.ep, o);
+            st.ret += __shfl_xor_sync(0xffffffffu, st.ret, o);
+            st.len += __shfl_xor_sync(0xffffffffu, st.len, o);
+            st.lines += __shfl_xor_sync(0xffffffffu, st.lines, o);
+        }
+        if ((tid & 31) == 0 && st.ep > 0) {
+            atomicAdd(p.stats + 0, st.ep); atomicAdd(p.stats + 1, st.ret);
+            atomicAdd(p.stats + 2, st.len); atomicAdd(p.stats + 3, st.lines);
+        }
+    }
+}
+
+// ---- packed-byte variant for W = 10 / W = 20 (same arithmetic as k_grouped_feats_x, tg_gfeats.cuh) ----------------------
+// The thread keeps the column heights of its env as packed bytes (registers + a copy in its shared-memory slot for the
+// dynamic 4-byte window at byte x), evaluates the four rotations of every column branch-free (bytewise max under the piece's
+// column mask, IDP.4A for the height / hole sums, VABSDIFF4 for the bumpiness) and defers the rare placements that clear
+// rows or touch the zeroed row 0 to an exact per-column pass.  Same slot layout as k_rollout (the packed heights take the
+// place of its h / ho / bs arrays).
+template <int W, class COLT>
+__global__ void __launch_bounds__(128, 6) k_rollout_x(const __grid_constant__ RolloutParams p) {
+    constexpr int WP = W + 2 * P, HW = (WP + 3) / 4, NH = (W + 3) / 4, VL = W - 4 * (NH - 1), A = 4 * W;
+    extern __shared__ __align__(16) uint32_t rsm[];
+    const DevCfg& cfg = p.cfg;
+    const int tid = threadIdx.x, H = cfg.H;
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + tid;
+    __shared__ unsigned short s_cells[28];
+    __shared__ int s_n[8];
+    __shared__ uint4 s_prec[28];
+    if (tid < 28) { s_cells[tid] = (&c_cells[0][0])[tid]; s_prec[tid] = (&c_prec[0][0])[tid]; }
+    if (tid < 7) s_n[tid] = c_n[tid];
+    __syncthreads();
+    Tabs tb;
+    tb.ptab = nullptr; tb.cells = s_cells; tb.rowbytes = &c_rowbytes[0][0][0]; tb.n = s_n;
+    TileStats st = {0, 0, 0, 0};
+    if (e < p.n) {
+        COLT* colp = (COLT*)(rsm + (size_t)tid * p.rec_words);   // colp[c + P] = column c, walls on both sides
+        uint32_t* rec = (uint32_t*)(colp + P);
+        const uint32_t* grec = (const uint32_t*)(p.board + e * cfg.board_stride);
+        const int ncw = p.ids_off_g / 4, nw = cfg.board_stride / 4;
+        uint32_t* ids = rec + cfg.ids_off / 4;
+        for (int i = 0; i < ncw; i++) rec[i] = grec[i];
+        for (int i = ncw; i < nw; i++) ids[i - ncw] = grec[i];
+        for (int c = 0; c < P; c++) { colp[c] = ~COLT(0); colp[P + W + c] = ~COLT(0); }
+        Hot h;
+        hot_load(h, (const uint32_t*)(p.hot + e * 32));
+        Rng g;
+        g.rec = (uint32_t*)(p.rng + e * cfg.rng_stride);
+        g.seq = p.seq ? p.seq + e * cfg.seq_len : nullptr;
+        g.gid = cfg.env_id_offset + (uint64_t)e;
+        g.dirty = false;
+        const COLT* cols = (const COLT*)rec;
+        COLT* pre = (COLT*)(rec + p.base_off);
+        COLT* suf = pre + W;
+        uint32_t* hv = (uint32_t*)(suf + W);                     // HW words: P pad bytes | W heights | pad
+        const COLT field = (COLT(1) << H) - 1;
+        int last = -1;
+        for (int step = 0; step < p.k_steps; step++) {
+            if (cfg.autoreset == 1 && h.pending) { env_reset<COLT>(cfg, h, rec, g); last = -1; continue; }
+            // ---- per-step base: prefix / suffix column ANDs, heights with row 0 zeroed (Q1), their sums ----
+            uint32_t V[HW];
+#pragma unroll
+            for (int k = 0; k < HW; k++) V[k] = 0;
+            int holes0 = 0, sumh0 = 0;
+            {
+                COLT acc = ~COLT(0);
+#pragma unroll
+                for (int c = 0; c < W; c++) {
+                    const COLT col = cols[c];
+                    pre[c] = acc; acc &= col;
+                    int hgt, hol;
+                    col_features<COLT>(col & ~COLT(1), H, hgt, hol);
+                    V[(P + c) >> 2] |= (uint32_t)hgt << (8 * ((P + c) & 3));
+                    holes0 += hol; sumh0 += hgt;
+                }
+                acc = ~COLT(0);
+#pragma unroll
+                for (int c = W - 1; c >= 0; c--) { suf[c] = acc; acc &= cols[c]; }
+#pragma unroll
+                for (int k = 0; k < HW; k++) hv[k] = V[k];
+            }
+            const uint4* prow = s_prec + h.p * 4;
+            const int rot0 = h.r;
+            const int xoff = P - (h.p == 0 ? 2 : 1);                                 // wrappers/grouped.py:157-158
+            int best = -1, best_score = 0, first_legal = -1;
+            unsigned long long slow_lo = 0;   // placements 0..63 / 64.. that need the exact pass
+            uint32_t slow_hi = 0;
+#pragma unroll 1
+            for (int xb = 0; xb < W; xb++) {
+                const int x = xb + xoff, wi = x >> 2, sh = (x & 3) * 8;
+                const uint32_t Wlo = hv[wi], Whi = hv[wi + 1];
+                const uint32_t O4 = __funnelshift_r(Wlo, Whi, sh);
+                COLT cj[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) cj[j] = colp[x + j];
+#pragma unroll
+                for (int r = 0; r < 4; r++) {
+                    const int a = 4 * xb + r;
+                    const uint4 q = prow[(rot0 + r) & 3];            // cumulative rot90 presses (wrappers/grouped.py:153-154)
+                    COLT B = 0;
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const int c = (q.x >> (4 * k)) & 15;
+                        B |= colp[x + (c & 3)] >> (c >> 2);
+                    }
+                    const int y = ctz_t<COLT>(B >> 1);               // while !collision(y+1): y++ from y = 0
+                    const int jmin = q.w & 3, jmax = (q.w >> 2) & 3, mintop = (q.w >> 4) & 3;
+                    const int c0 = x + jmin - P, c1 = x + jmax - P;
+                    const bool legal = c0 >= 0 && c1 < W;
+                    if (legal && first_legal < 0) first_legal = a;
+                    const bool lands = legal && !((B >> y) & 1);
+                    COLT full = pre[legal ? c0 : 0] & suf[legal ? c1 : 0] & field;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) full &= cj[j] | ((COLT)((q.x >> (16 + 4 * j)) & 15u) << y);
+                    const bool exact = lands && (full != 0 || y + mintop == 0);
+                    if (exact) { if (a < 64) slow_lo |= 1ull << a; else slow_hi |= 1u << (a - 64); }
+                    const uint32_t M4 = q.y;
+                    const uint32_t OM = O4 & M4;
+                    const uint32_t T4 = ((uint32_t)(H - y) * 0x01010101u - q.z) & M4;
+                    const uint32_t N4 = bytemax_lt128(OM, T4);
+                    const int delta = __dp4a((int)OM, (int)0xFFFFFFFFu, __dp4a((int)N4, 0x01010101, 0));   // sum(new) - sum(old)
+                    const uint32_t Nlo = N4 << sh, Nhi = __funnelshift_l(N4, 0u, sh);
+                    const uint32_t Mlo = M4 << sh, Mhi = __funnelshift_l(M4, 0u, sh);
+                    const uint32_t Wl = (Wlo & ~Mlo) | Nlo, Wh = (Whi & ~Mhi) | Nhi;
+                    uint32_t hw[NH];
+#pragma unroll
+                    for (int k = 0; k < NH; k++) hw[k] = (k + 1 == wi) ? Wl : ((k == wi) ? Wh : V[k + 1]);
+                    uint32_t bump = 0;
+#pragma unroll
+                    for (int k = 0; k < NH - 1; k++) bump = __vsadu4(hw[k], __funnelshift_r(hw[k], hw[k + 1], 8)) + bump;
+                    {
+                        const uint32_t l = hw[NH - 1];
+                        const uint32_t aa = VL == 4 ? l : __byte_perm(l, 0, VL == 1 ? 0x4444 : (VL == 2 ? 0x4410 : 0x4210));
+                        const uint32_t bb = __byte_perm(l, 0, VL == 1 ? 0x4444 : (VL == 2 ? 0x4411 : (VL == 3 ? 0x4221 : 0x3321)));
+                        bump = __vsadu4(aa, bb) + bump;
+                    }
+                    // score on the uint8 feature values (holes / bumpiness wrap); no row is cleared on this path
+                    const int score = p.w[0] * (sumh0 + delta) + p.w[2] * ((holes0 - 4 + delta) & 255) + p.w[3] * (int)(bump & 255u);
+                    const bool take = lands && !exact && (best < 0 || score > best_score);
+                    best = take ? a : best;
+                    best_score = take ? score : best_score;
+                }
+            }
+            // ---- exact pass: placements that clear rows / put a cell into the zeroed row 0 (per column, see tg_gfeats.cuh) ----
+            while (slow_lo | slow_hi) {
+                int a;
+                if (slow_lo) { a = __ffsll((long long)slow_lo) - 1; slow_lo &= slow_lo - 1; }
+                else { a = 64 + __ffs((int)slow_hi) - 1; slow_hi &= slow_hi - 1; }
+                const uint4 q = s_prec[h.p * 4 + ((h.r + (a & 3)) & 3)];
+                const int x = (a >> 2) + xoff;
+                COLT B = 0;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int c = (q.x >> (4 * k)) & 15;
+                    B |= colp[x + (c & 3)] >> (c >> 2);
+                }
+                const int y = ctz_t<COLT>(B >> 1);
+                const int jmin = q.w & 3, c0 = x + jmin - P, c1 = x + (int)((q.w >> 2) & 3) - P;
+                COLT full = pre[c0] & suf[c1] & field;
+#pragma unroll
+                for (int j = 0; j < 4; j++) full &= colp[x + j] | ((COLT)((q.x >> (16 + 4 * j)) & 15u) << y);
+                const COLT keep = (full != 0 ? ~full : ~COLT(1)) & field;
+                int s_sum = 0, s_hol = 0, s_bmp = 0, prev = 0;
+#pragma unroll 2
+                for (int c = 0; c < W; c++) {
+                    COLT v = colp[c + P];
+                    const int t = c - c0;
+                    if ((unsigned)t <= (unsigned)(c1 - c0)) v |= (COLT)((q.x >> (16 + 4 * (jmin + t))) & 15u) << y;
+                    const COLT u = v & keep;
+                    int hgt = 0, hol = 0;
+                    if (u != 0) {
+                        const int tp = ctz_t<COLT>(u);
+                        hgt = H - tp - popc_t<COLT>((full >> tp) >> 1);
+                        hol = hgt - popc_t<COLT>(u);
+                    }
+                    s_sum += hgt; s_hol += hol;
+                    if (c > 0) s_bmp += abs(hgt - prev);
+                    prev = hgt;
+                }
+                const int score = p.w[0] * s_sum + p.w[1] * popc_t<COLT>(full) + p.w[2] * (s_hol & 255) + p.w[3] * (s_bmp & 255);
+                // lowest index among the maxima: a later candidate wins only if strictly better, an earlier one on ties
+                if (best < 0 || score > best_score || (score == best_score && a < best)) { best = a; best_score = score; }
+            }
+            const int action = best >= 0 ? best : first_legal;
+            last = action;
+            // ---- execute (GroupedActionsObservations.step, wrappers/grouped.py:241-259) ----
+            StepResult res;
+            h.x = (action >> 2) + xoff;
             h.r = (h.r + (action & 3)) & 3;
             env_step<COLT>(cfg, tb, h, rec, g, cfg.act_hard, res);
             h.ep_ret += (float)res.reward; h.ep_len += 1; h.ep_lines += res.lines;

@@ -642,10 +642,9 @@ static int launch_grouped_observe(tg_env* env, tg_state st, int64_t n, uint8_t* 
         int EPB = 32, T = 256;             // 32 envs x 4W placements = a whole number of 256-thread rounds
         size_t colb = env->col64 ? 8 : 4;
         size_t smem = (size_t)EPB * (3 * d.W + 2 * TG_PADDING) * colb + (size_t)EPB * 16 + (size_t)EPB * 4 + (size_t)EPB * 128 + (size_t)EPB * d.A * d.F + (size_t)EPB * d.A;
-        if (smem > 48 * 1024) {
-            if (env->col64) cudaFuncSetAttribute(k_grouped_feats<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            else cudaFuncSetAttribute(k_grouped_feats<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        }
+        // always opt in: static (tables, slow list) + dynamic shared memory may exceed 48 KB even when the dynamic part does not
+        if (env->col64) CUDA_TRY(env, cudaFuncSetAttribute(k_grouped_feats<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else CUDA_TRY(env, cudaFuncSetAttribute(k_grouped_feats<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         unsigned g = (unsigned)((n + EPB - 1) / EPB);
         const uint32_t magicA = ((1u << 20) + d.A - 1) / d.A;   // it / A == (it * magicA) >> 20, exact for it < 32 * A, A = 4W <= 96 (enumerated)
         if (env->col64) k_grouped_feats<uint64_t><<<g, T, smem, s>>>(d, n, (const uint8_t*)st.hot, (const uint8_t*)st.board, d_feats, d_legal, fill_high, EPB, magicA);
@@ -769,6 +768,10 @@ extern "C" int tg_rollout(tg_env* env, tg_state st, int64_t n, const int32_t wei
         return TG_OK;
     };
     if (smem > 227 * 1024) return fail(env, TG_ERR_CONFIG, "tg_rollout: board record too large for shared memory");
+    if (!getenv("TG_ROLLOUT_V1")) {   // packed-byte variant for the two board widths of BASELINE.json
+        if (d.W == 10) return env->col64 ? launch(k_rollout_x<10, uint64_t>) : launch(k_rollout_x<10, uint32_t>);
+        if (d.W == 20) return env->col64 ? launch(k_rollout_x<20, uint64_t>) : launch(k_rollout_x<20, uint32_t>);
+    }
     return env->col64 ? launch(k_rollout<uint64_t>) : launch(k_rollout<uint32_t>);
 }
 
