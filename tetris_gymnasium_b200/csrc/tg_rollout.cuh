@@ -143,6 +143,10 @@ __global__ void __launch_bounds__(128, 6) k_rollout(const __grid_constant__ Roll
     }
 }
 
+// out-of-line reset: keeps the rollout loop's code footprint (instruction cache) small, resets are rare
+template <class COLT>
+__device__ __noinline__ void env_reset_ni(const DevCfg& cfg, Hot& h, uint32_t* rec, Rng& g) { env_reset<COLT>(cfg, h, rec, g); }
+
 // ---- packed-byte variant for W = 10 / W = 20 (same arithmetic as k_grouped_feats_x, tg_gfeats.cuh) ----------------------
 // The thread keeps the column heights of its env as packed bytes (registers + a copy in its shared-memory slot for the
 // dynamic 4-byte window at byte x), evaluates the four rotations of every column branch-free (bytewise max under the piece's
@@ -188,7 +192,7 @@ __global__ void __launch_bounds__(128, 6) k_rollout_x(const __grid_constant__ Ro
         const COLT field = (COLT(1) << H) - 1;
         int last = -1;
         for (int step = 0; step < p.k_steps; step++) {
-            if (cfg.autoreset == 1 && h.pending) { env_reset<COLT>(cfg, h, rec, g); last = -1; continue; }
+            if (cfg.autoreset == 1 && h.pending) { env_reset_ni<COLT>(cfg, h, rec, g); last = -1; continue; }
             // ---- per-step base: prefix / suffix column ANDs, heights with row 0 zeroed (Q1), their sums ----
             uint32_t V[HW];
 #pragma unroll
@@ -293,7 +297,7 @@ __global__ void __launch_bounds__(128, 6) k_rollout_x(const __grid_constant__ Ro
                 for (int j = 0; j < 4; j++) full &= colp[x + j] | ((COLT)((q.x >> (16 + 4 * j)) & 15u) << y);
                 const COLT keep = (full != 0 ? ~full : ~COLT(1)) & field;
                 int s_sum = 0, s_hol = 0, s_bmp = 0, prev = 0;
-#pragma unroll 2
+#pragma unroll 1
                 for (int c = 0; c < W; c++) {
                     COLT v = colp[c + P];
                     const int t = c - c0;
@@ -325,7 +329,7 @@ __global__ void __launch_bounds__(128, 6) k_rollout_x(const __grid_constant__ Ro
                 st.ep += 1; st.ret += h.ep_ret; st.len += h.ep_len; st.lines += h.ep_lines;
                 h.ep_ret = 0; h.ep_len = 0; h.ep_lines = 0;
                 if (cfg.autoreset == 1) h.pending = 1;
-                else if (cfg.autoreset == 2) env_reset<COLT>(cfg, h, rec, g);
+                else if (cfg.autoreset == 2) env_reset_ni<COLT>(cfg, h, rec, g);
             }
         }
         hot_store(h, (uint32_t*)(p.hot + e * 32));

@@ -755,7 +755,8 @@ extern "C" int tg_rollout(tg_env* env, tg_state st, int64_t n, const int32_t wei
     if (env->col64) words = (words + 1) & ~1;             // keep the EnvBase arrays 8-byte aligned
     p.base_off = words - TG_PADDING * cw;                 // measured from the first column
     p.hb = (d.W + 3) & ~3;
-    words += 2 * d.W * cw + 4 * p.hb / 4;                 // pre[W], suf[W], h, ho, bs (u16)
+    const bool packed = !getenv("TG_ROLLOUT_V1") && (d.W == 10 || d.W == 20);   // k_rollout_x: packed heights instead of h / ho / bs
+    words += 2 * d.W * cw + (packed ? (d.W + 2 * TG_PADDING + 3) / 4 : 4 * p.hb / 4);   // pre[W], suf[W], then h, ho, bs (u16) | packed heights
     // u32 columns: odd word stride; u64 columns: stride = 2 (mod 4) words keeps 8-byte alignment and spreads the banks
     if (env->col64) { while ((words & 3) != 2) words += 1; } else { words |= 1; }
     p.rec_words = words;
@@ -768,7 +769,7 @@ extern "C" int tg_rollout(tg_env* env, tg_state st, int64_t n, const int32_t wei
         return TG_OK;
     };
     if (smem > 227 * 1024) return fail(env, TG_ERR_CONFIG, "tg_rollout: board record too large for shared memory");
-    if (!getenv("TG_ROLLOUT_V1")) {   // packed-byte variant for the two board widths of BASELINE.json
+    if (packed) {   // packed-byte variant for the two board widths of BASELINE.json
         if (d.W == 10) return env->col64 ? launch(k_rollout_x<10, uint64_t>) : launch(k_rollout_x<10, uint32_t>);
         if (d.W == 20) return env->col64 ? launch(k_rollout_x<20, uint64_t>) : launch(k_rollout_x<20, uint32_t>);
     }
