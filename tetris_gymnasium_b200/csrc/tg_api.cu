@@ -30,7 +30,6 @@ struct tg_env {
     int warp_specialized; // 1: k_step_ws (logic warp runs a tile ahead of the image warps)
     int fill_warps;       // image/store warps per CTA of k_step_ws
     int logic_warps;      // game-logic warps per CTA of k_step_ws (each runs every logic_warps-th tile of the CTA)
-    int l2hint;           // TG_L2HINT: L2 eviction-priority hints of the k_step_ws bulk copies (see StepParams::l2hint)
     int logic_warps_set, fill_warps_set;   // TG_NL / TG_NF given: use them for every launch
     void* rollout_last_action;
     int cnn_h, cnn_w;     // output size the tg_cnn_observe tables in stage[4] were built for
@@ -218,8 +217,6 @@ extern "C" int tg_create(const tg_config* cfg, int device, tg_env** out) {
     env->fill_warps = 4;
     if (const char* t = getenv("TG_WS")) env->warp_specialized = atoi(t) != 0;
     env->logic_warps = 2;
-    env->l2hint = 1;      // observation images: L2 evict_first (+3 % on the 4M-env step; TG_L2HINT=0 restores the default policy)
-    if (const char* t = getenv("TG_L2HINT")) env->l2hint = atoi(t) & 7;
     env->logic_warps_set = env->fill_warps_set = 0;
     if (const char* t = getenv("TG_NF")) { int v = atoi(t); if (v >= 1 && v <= 6) { env->fill_warps = v; env->fill_warps_set = 1; } }
     if (const char* t = getenv("TG_NL")) { int v = atoi(t); if (v >= 1 && v <= 6) { env->logic_warps = v; env->logic_warps_set = 1; } }
@@ -256,9 +253,8 @@ static int check_state(tg_env* env, const tg_state& st) {
 // ---- step / reset launcher ----------------------------------------------------------------------
 template <int WT, int HT, class COLT>
 static int launch_step_t(tg_env* env, StepParams& p, int T, size_t smem, bool ws, cudaStream_t s) {
-    auto kern = ws ? k_step_ws<WT, HT, COLT> : k_step<WT, HT, COLT>;
+    auto kern = ws ? (p.mode == 2 ? k_step_ws<WT, HT, COLT, true> : k_step_ws<WT, HT, COLT, false>) : k_step<WT, HT, COLT>;
     CUDA_TRY(env, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (!getenv("TG_NO_CARVEOUT")) CUDA_TRY(env, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     int per_sm = 0;
     CUDA_TRY(env, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, T, smem));
     if (per_sm < 1) return fail(env, TG_ERR_CONFIG, "step kernel does not fit: %zu B shared memory per CTA", smem);
@@ -318,7 +314,6 @@ static int launch_step(tg_env* env, StepParams& p, cudaStream_t s, int force_pla
     p.E = E;
     p.NL = NL;
     p.NS = NS;
-    p.l2hint = env->l2hint;
     p.whole_tile_min = E / 2;
     if (const char* t = getenv("TG_WHOLE")) p.whole_tile_min = atoi(t);
     int T = ws ? 32 * (NL + NF) : E * env->threads_per_env;

@@ -220,32 +220,38 @@ __device__ __noinline__ uint32_t shuffle_bag(const DevCfg& cfg, Rng& g, uint32_t
     return bag & 0x0FFFFFFFu;  // index = 0
 }
 
+// Draws that are not the 7-bag: the injected stream (TG_RNG_SEQUENCE) and TrueRandomizer.  Out of line: the call sites
+// (commit, swap, reset) stay small -- inlined four times the PCG64 / Philox code made up a quarter of the step kernel and
+// pushed it past the instruction cache.  Returns the piece; the caller marks the rng record dirty.
+__device__ __noinline__ int draw_other(int rng_mode, long long seq_len, uint32_t* rec, const uint8_t* seq, uint64_t gid) {
+    if (rng_mode == 1) {
+        uint64_t cur = ((uint64_t*)rec)[0];
+        ((uint64_t*)rec)[0] = cur + 1;
+        return seq[cur % (uint64_t)seq_len];
+    }
+    // TrueRandomizer.get_next_tetromino (components/tetromino_randomizer.py:119-121): rng.integers(0, 7)
+    if (rng_mode == 2) {
+        // numpy: Lemire multiply-shift with rejection on next_uint32 (buffered_bounded_lemire_uint32, rng = 6)
+        uint64_t m = (uint64_t)pcg64_next32(rec) * 7u;
+        if ((uint32_t)m < 7u) {
+            const uint32_t threshold = (0xFFFFFFFFu - 6u) % 7u;
+            while ((uint32_t)m < threshold) m = (uint64_t)pcg64_next32(rec) * 7u;
+        }
+        return (int)(m >> 32);
+    }
+    uint64_t seed = ((uint64_t*)rec)[0];
+    uint32_t ctr = rec[2];
+    rec[2] = ctr + 1;
+    uint32_t c[4] = {ctr, (uint32_t)gid, (uint32_t)(gid >> 32), 2u};
+    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    return (int)__umulhi(c[0], 7u);
+}
+
 // Randomizer.get_next_tetromino
 __device__ __forceinline__ int draw_piece(const DevCfg& cfg, Rng& g, Hot& h) {
-    if (cfg.rng_mode == 1) {
-        uint64_t cur = ((uint64_t*)g.rec)[0];
-        ((uint64_t*)g.rec)[0] = cur + 1;
+    if (cfg.rng_mode == 1 || cfg.rand_kind == 1) {
         g.dirty = true;
-        return g.seq[cur % (uint64_t)cfg.seq_len];
-    }
-    if (cfg.rand_kind == 1) {
-        // TrueRandomizer.get_next_tetromino (components/tetromino_randomizer.py:119-121): rng.integers(0, 7)
-        g.dirty = true;
-        if (cfg.rng_mode == 2) {
-            // numpy: Lemire multiply-shift with rejection on next_uint32 (buffered_bounded_lemire_uint32, rng = 6)
-            uint64_t m = (uint64_t)pcg64_next32(g.rec) * 7u;
-            if ((uint32_t)m < 7u) {
-                const uint32_t threshold = (0xFFFFFFFFu - 6u) % 7u;
-                while ((uint32_t)m < threshold) m = (uint64_t)pcg64_next32(g.rec) * 7u;
-            }
-            return (int)(m >> 32);
-        }
-        uint64_t seed = ((uint64_t*)g.rec)[0];
-        uint32_t ctr = g.rec[2];
-        g.rec[2] = ctr + 1;
-        uint32_t c[4] = {ctr, (uint32_t)g.gid, (uint32_t)(g.gid >> 32), 2u};
-        philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
-        return (int)__umulhi(c[0], 7u);
+        return draw_other(cfg.rng_mode, cfg.seq_len, g.rec, g.seq, g.gid);
     }
     // BagRandomizer.get_next_tetromino (components/tetromino_randomizer.py:67-80)
     int idx = (h.bag >> 28) & 7;

@@ -334,18 +334,28 @@ __global__ void __maxnreg__(W == 10 ? GF_REGS : 96) k_grouped_feats_x(const DevC
             out[W] = (uint8_t)s_max; out[W + 1] = (uint8_t)s_hol; out[W + 2] = (uint8_t)s_bmp;
         }
     }
-    __syncthreads();
-    // ---- phase 5: coalesced copy-out (the tile is contiguous in global memory) ----
+    // ---- phase 5: the tile is contiguous in global memory: full tiles leave as TMA bulk copies issued by one thread ----
     {
-        const int words = nv * W * F;                  // 4-byte words of the feature tile
-        uint32_t* g = (uint32_t*)(feats + (size_t)base * A * F);
-        const int q4 = words >> 2;
-        for (int i = tid; i < q4; i += T) ((uint4*)g)[i] = ((const uint4*)s_featw)[i];
-        for (int i = 4 * q4 + tid; i < words; i += T) g[i] = s_featw[i];
-        uint32_t* gl = (uint32_t*)(legal + (size_t)base * A);
-        if (tid < nv * W) gl[tid] = s_legalw[tid];
-        if (info_board)
-            for (int i = tid; i < nv * F; i += T) info_board[(size_t)base * F + i] = s_info[i];
+        uint8_t* gf = feats + (size_t)base * A * F;
+        uint8_t* gl = legal + (size_t)base * A;
+        if (nv == EPB) {
+            fence_async_smem();            // generic-proxy writes of this thread -> visible to the async proxy
+            __syncthreads();
+            if (tid == 0) {
+                bulk_s2g(gf, s_featw, (uint32_t)(EPB * A * F));
+                bulk_s2g(gl, s_legalw, (uint32_t)(EPB * A));
+                if (info_board) bulk_s2g(info_board + (size_t)base * F, s_info, (uint32_t)(EPB * F));
+                bulk_commit();
+                bulk_wait_read();          // shared memory must stay alive until the copies have read it
+            }
+        } else {
+            __syncthreads();
+            const int words = nv * W * F;
+            for (int i = tid; i < words; i += T) ((uint32_t*)gf)[i] = s_featw[i];
+            if (tid < nv * W) ((uint32_t*)gl)[tid] = s_legalw[tid];
+            if (info_board)
+                for (int i = tid; i < nv * F; i += T) info_board[(size_t)base * F + i] = s_info[i];
+        }
     }
 }
 

@@ -44,28 +44,19 @@ __device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, u
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes)
                  : "memory");
 }
-// same copies with an L2 eviction-priority hint (createpolicy): the observation images are written once and never read by
-// this kernel again (evict_first), the state records are re-read by the next step (evict_last keeps small batches in L2)
-__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+// smem -> global bulk copy of the observation images; -DTG_L2_HINT adds an L2 evict_first hint (createpolicy).  Measured
+// (4 M envs, A/B on one box, 4 runs each): selected at run time inside one binary the hint gained 3 %, but the run-time
+// switch cost 4 % (code size); compiled in unconditionally it LOST 1.7 % against no hint (4.18 vs 4.25 G) -> off.
+__device__ __forceinline__ void bulk_s2g_stream(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+#ifndef TG_L2_HINT
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+#else
     uint64_t pol;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
-}
-__device__ __forceinline__ uint64_t l2_policy_evict_last() {
-    uint64_t pol;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
-}
-__device__ __forceinline__ void bulk_g2s_hint(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar, uint64_t pol) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
-                     smem_u32(dst_smem)),
-                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
-                 : "memory");
-}
-__device__ __forceinline__ void bulk_s2g_hint(void* dst_gmem, const void* src_smem, uint32_t bytes, uint64_t pol) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)),
                  "r"(bytes), "l"(pol)
                  : "memory");
+#endif
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
@@ -73,9 +64,10 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // contiguous smem -> global copy: TMA when size/alignment allow, cooperative stores otherwise
+template <bool STREAM = false>
 __device__ __forceinline__ void tile_store(uint8_t* g, const uint8_t* s, uint32_t bytes, bool leader, int tid, int nthreads) {
     if ((bytes & 15u) == 0 && ((uintptr_t)g & 15u) == 0) {
-        if (leader && bytes) bulk_s2g(g, s, bytes);
+        if (leader && bytes) { if (STREAM) bulk_s2g_stream(g, s, bytes); else bulk_s2g(g, s, bytes); }
     } else {
         for (uint32_t i = tid; i < bytes; i += nthreads) g[i] = s[i];
     }
@@ -99,7 +91,6 @@ struct StepParams {
     int NL;                          // k_step_ws: logic warps per CTA
     int NS;                          // k_step_ws: state stages in flight (NL + 2 by default)
     int whole_tile_min;              // k_step_ws: dirty envs in a tile from which the board records leave as one bulk copy
-    int l2hint;                      // k_step_ws: bit0 obs stores evict_first, bit1 state loads evict_first, bit2 state loads + stores evict_last
     // shared-memory carve-up (bytes from the 128-aligned base)
     int off_hot, off_brd, off_rng, off_iboard, off_imask, off_iholder, off_iqueue, off_bar, off_box, off_tab, off_feat;
     int st_hot, st_brd, st_rng;      // bytes between the two pipeline stages of each state buffer
@@ -205,7 +196,7 @@ struct TileStats { double ep, ret, len, lines; };
 
 // Runs reset / step / grouped placement for env `e` whose records sit at slot `slot` of the staged tile.
 // Returns bit0 = board record dirty, bit1 = rng record dirty.  Writes the 5-tuple scalars and s_box[slot].
-template <class COLT, bool INFO = true>
+template <class COLT, bool INFO = true, bool GROUPED = true>
 __device__ __forceinline__ uint32_t logic_one_env(const StepParams& p, const Tabs& tb, int64_t e, int slot, int action,
                                                   uint32_t* s_hot, uint8_t* s_brd, uint8_t* s_rng, uint32_t* s_box,
                                                   TileStats& st) {
@@ -228,22 +219,28 @@ __device__ __forceinline__ uint32_t logic_one_env(const StepParams& p, const Tab
     } else if (cfg.autoreset == 1 && h.pending) {
         need_reset = true;  // gymnasium NEXT_STEP autoreset: the action is ignored, the env is reset
     } else {
-        if (p.mode == 2) {
+        // one env_step call site for all modes (it is the bulk of the kernel's code: instruction cache)
+        int act = action;
+        bool run = true, invalid = false;
+        if (GROUPED && p.mode == 2) {
             // GroupedActionsObservations.step (wrappers/grouped.py:209-269)
             bool ok = (unsigned)action < (unsigned)cfg.A && p.legal[e * cfg.A + action] != 0;
             p.fill_high[e] = (uint8_t)(!ok && cfg.terminate_on_illegal);
             if (ok) {
                 h.x = (action >> 2) + P - tb.n[h.p] / 2;   // y untouched (wrappers/grouped.py:244-254)
                 h.r = (h.r + (action & 3)) & 3;
-                env_step<COLT>(cfg, tb, h, rec, g, cfg.act_hard, res);
+                act = cfg.act_hard;
             } else if (cfg.terminate_on_illegal) {
                 res.reward = cfg.r_invalid; res.terminated = 1;   // env untouched, episode ends
+                run = false;
             } else {
-                env_step<COLT>(cfg, tb, h, rec, g, cfg.act_noop, res);
-                res.reward = cfg.r_invalid;
+                act = cfg.act_noop;
+                invalid = true;
             }
-        } else {
-            env_step<COLT>(cfg, tb, h, rec, g, action, res);
+        }
+        if (run) {
+            env_step<COLT>(cfg, tb, h, rec, g, act, res);
+            if (invalid) res.reward = cfg.r_invalid;
         }
         h.ep_ret += (float)res.reward; h.ep_len += 1; h.ep_lines += res.lines;
         if (res.terminated) {
@@ -253,8 +250,9 @@ __device__ __forceinline__ uint32_t logic_one_env(const StepParams& p, const Tab
             else if (cfg.autoreset == 2) need_reset = true;
         }
     }
+    // (inline: an out-of-line reset forces the hot record into local memory and cost 6 % on the 4 M-env step)
     if (need_reset) { env_reset<COLT>(cfg, h, rec, g); res.dirty = 1; }
-    if (p.mode == 2 && need_reset) p.fill_high[e] = 0;
+    if (GROUPED && p.mode == 2 && need_reset) p.fill_high[e] = 0;
     hot_store(h, s_hot + slot * 8);
     if (p.mode != 1) {
         p.reward[e] = (float)res.reward;
@@ -266,7 +264,7 @@ __device__ __forceinline__ uint32_t logic_one_env(const StepParams& p, const Tab
     const uint32_t show = !((Bact >> h.y) & 1);
     s_box[slot] = (uint32_t)h.x | ((uint32_t)h.y << 8) | ((uint32_t)tb.n[h.p] << 16) | (show << 20) |
                   ((uint32_t)h.p << 24) | ((uint32_t)h.r << 28);
-    if (INFO && p.mode == 2 && p.info_board) {
+    if (INFO && GROUPED && p.mode == 2 && p.info_board) {
         // info["board"]: FeatureVectorObservation of the real observation (wrappers/grouped.py:260-264)
         uint8_t f[32];
         int ln;
@@ -486,7 +484,9 @@ __global__ void __launch_bounds__(256) k_step(const __grid_constant__ StepParams
 __device__ __forceinline__ void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void named_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
-template <int WT, int HT, class COLT>
+// GROUPED = true: the grouped placement step (mode 2) -- its code (legal-mask test, info board, whole-tile write-back) is
+// compiled out of the step / reset instantiation, whose speed depends on the code footprint (instruction cache).
+template <int WT, int HT, class COLT, bool GROUPED>
 __global__ void __launch_bounds__(256) k_step_ws(const __grid_constant__ StepParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const DevCfg& cfg = p.cfg;
@@ -523,22 +523,13 @@ __global__ void __launch_bounds__(256) k_step_ws(const __grid_constant__ StepPar
 
     const int64_t ntiles = (p.n + E - 1) / E;
     const int64_t G = gridDim.x;
-    const int hint = p.l2hint;
-    const uint64_t pol_obs = l2_policy_evict_first();
-    const uint64_t pol_st = (hint & 4) ? l2_policy_evict_last() : l2_policy_evict_first();
     auto issue_load = [&](int64_t tile, int s) {
         const int64_t base = tile * E;
         const int nv = (int)min((int64_t)E, p.n - base);
         mbar_expect_tx(bar + s, (uint32_t)(nv * (32 + BS + RS)));
-        if (hint & 6) {
-            bulk_g2s_hint(smem + p.off_hot + s * p.st_hot, p.hot + base * 32, (uint32_t)(nv * 32), bar + s, pol_st);
-            bulk_g2s_hint(smem + p.off_brd + s * p.st_brd, p.board + base * BS, (uint32_t)(nv * BS), bar + s, pol_st);
-            bulk_g2s_hint(smem + p.off_rng + s * p.st_rng, p.rng + base * RS, (uint32_t)(nv * RS), bar + s, pol_st);
-        } else {
-            bulk_g2s(smem + p.off_hot + s * p.st_hot, p.hot + base * 32, (uint32_t)(nv * 32), bar + s);
-            bulk_g2s(smem + p.off_brd + s * p.st_brd, p.board + base * BS, (uint32_t)(nv * BS), bar + s);
-            bulk_g2s(smem + p.off_rng + s * p.st_rng, p.rng + base * RS, (uint32_t)(nv * RS), bar + s);
-        }
+        bulk_g2s(smem + p.off_hot + s * p.st_hot, p.hot + base * 32, (uint32_t)(nv * 32), bar + s);
+        bulk_g2s(smem + p.off_brd + s * p.st_brd, p.board + base * BS, (uint32_t)(nv * BS), bar + s);
+        bulk_g2s(smem + p.off_rng + s * p.st_rng, p.rng + base * RS, (uint32_t)(nv * RS), bar + s);
     };
     if (ft == 0) {   // the fill leader owns all TMA traffic: tiles 0 .. NS-2 of this CTA go to stages 0 .. NS-2
         for (int j = 0; j < NS - 1; j++)
@@ -560,10 +551,10 @@ __global__ void __launch_bounds__(256) k_step_ws(const __grid_constant__ StepPar
             mbar_wait(bar + s, (uint32_t)((k / NS) & 1));
             uint32_t dirty = 0;
             if (lane < nv)
-                dirty = logic_one_env<COLT, false>(p, tb, base + lane, lane, action, (uint32_t*)(smem + p.off_hot + s * p.st_hot),
+                dirty = logic_one_env<COLT, false, GROUPED>(p, tb, base + lane, lane, action, (uint32_t*)(smem + p.off_hot + s * p.st_hot),
                                                    smem + p.off_brd + s * p.st_brd, smem + p.off_rng + s * p.st_rng, s_boxes + s * E, st);
-            // tiles where most envs committed (always in the grouped mode) write their board records back as ONE bulk copy
-            const int ndirty = __popc(__ballot_sync(0xffffffffu, (dirty & 1u) != 0));
+            // grouped mode: tiles where most envs committed (nearly always) write their board records back as ONE bulk copy
+            const int ndirty = GROUPED ? __popc(__ballot_sync(0xffffffffu, (dirty & 1u) != 0)) : 0;
             if (lane < E) s_flags[s * E + lane] = dirty | ((uint32_t)ndirty << 8);
             __syncwarp();
             named_arrive(1 + s, 32 + FT);   // ready[s]: the fill warps may consume stage s
@@ -604,7 +595,7 @@ __global__ void __launch_bounds__(256) k_step_ws(const __grid_constant__ StepPar
                 mask_set_and_overlay(s_boxes + s * E, nv, s_cells, i_board, i_mask, OB, Wp, ft, FT);
                 for (int i = ft; i < nv; i += FT) s_boxprev[i] = s_boxes[s * E + i];
             }
-            if (p.mode == 2 && p.info_board) {
+            if (GROUPED && p.mode == 2 && p.info_board) {
                 // info["board"] = FeatureVectorObservation of the real observation (wrappers/grouped.py:260-264): rows 0-1 zeroed,
                 // active piece projected when it does not collide.  One thread per (env, column), then one thread per env.
                 uint8_t* f_h = smem + p.off_feat;          // [E][32] heights
@@ -644,39 +635,20 @@ __global__ void __launch_bounds__(256) k_step_ws(const __grid_constant__ StepPar
             fence_async_smem();
             named_sync(BAR_FILL, FT);
             if (want_obs) {
-                if ((hint & 1) && ((nv * OB) & 15) == 0 && ((uintptr_t)(p.o_board + base * OB) & 15u) == 0 && ((uintptr_t)(p.o_mask + base * OB) & 15u) == 0) {
-                    if (leader) {
-                        bulk_s2g_hint(p.o_board + base * OB, i_board, (uint32_t)(nv * OB), pol_obs);
-                        bulk_s2g_hint(p.o_mask + base * OB, i_mask, (uint32_t)(nv * OB), pol_obs);
-                        bulk_s2g_hint(p.o_holder + base * 16, i_holder, (uint32_t)(nv * 16), pol_obs);
-                        bulk_s2g_hint(p.o_queue + base * OQ, i_queue, (uint32_t)(nv * OQ), pol_obs);
-                    }
-                } else {
-                    tile_store(p.o_board + base * OB, i_board, (uint32_t)(nv * OB), leader, ft, FT);
-                    tile_store(p.o_mask + base * OB, i_mask, (uint32_t)(nv * OB), leader, ft, FT);
-                    if (leader) {
-                        bulk_s2g(p.o_holder + base * 16, i_holder, (uint32_t)(nv * 16));
-                        bulk_s2g(p.o_queue + base * OQ, i_queue, (uint32_t)(nv * OQ));
-                    }
+                tile_store<true>(p.o_board + base * OB, i_board, (uint32_t)(nv * OB), leader, ft, FT);
+                tile_store<true>(p.o_mask + base * OB, i_mask, (uint32_t)(nv * OB), leader, ft, FT);
+                if (leader) {
+                    bulk_s2g_stream(p.o_holder + base * 16, i_holder, (uint32_t)(nv * 16));
+                    bulk_s2g_stream(p.o_queue + base * OQ, i_queue, (uint32_t)(nv * OQ));
                 }
             }
-            const bool whole = (int)(s_flags[s * E] >> 8) >= p.whole_tile_min;   // unchanged records are rewritten with the same bytes
-            if (hint & 4) {
-                if (leader) bulk_s2g_hint(p.hot + base * 32, s_hot, (uint32_t)(nv * 32), pol_st);
-                if (leader && whole) bulk_s2g_hint(p.board + base * BS, s_brd, (uint32_t)(nv * BS), pol_st);
-                for (int i = ft; i < nv; i += FT) {
-                    uint32_t d = s_flags[s * E + i];
-                    if ((d & 1) && !whole) bulk_s2g_hint(p.board + (base + i) * BS, s_brd + i * BS, (uint32_t)BS, pol_st);
-                    if (d & 2) bulk_s2g_hint(p.rng + (base + i) * RS, s_rng + i * RS, (uint32_t)RS, pol_st);
-                }
-            } else {
-                if (leader) bulk_s2g(p.hot + base * 32, s_hot, (uint32_t)(nv * 32));
-                if (leader && whole) bulk_s2g(p.board + base * BS, s_brd, (uint32_t)(nv * BS));
-                for (int i = ft; i < nv; i += FT) {
-                    uint32_t d = s_flags[s * E + i];
-                    if ((d & 1) && !whole) bulk_s2g(p.board + (base + i) * BS, s_brd + i * BS, (uint32_t)BS);
-                    if (d & 2) bulk_s2g(p.rng + (base + i) * RS, s_rng + i * RS, (uint32_t)RS);
-                }
+            const bool whole = GROUPED && (int)(s_flags[s * E] >> 8) >= p.whole_tile_min;   // unchanged records are rewritten with the same bytes
+            if (leader) bulk_s2g(p.hot + base * 32, s_hot, (uint32_t)(nv * 32));
+            if (leader && whole) bulk_s2g(p.board + base * BS, s_brd, (uint32_t)(nv * BS));
+            for (int i = ft; i < nv; i += FT) {
+                uint32_t d = s_flags[s * E + i];
+                if ((d & 1) && !whole) bulk_s2g(p.board + (base + i) * BS, s_brd + i * BS, (uint32_t)BS);
+                if (d & 2) bulk_s2g(p.rng + (base + i) * RS, s_rng + i * RS, (uint32_t)RS);
             }
             bulk_commit();
             nv_prev = want_obs ? nv : 0;

@@ -724,7 +724,7 @@ extern "C" int tg_grouped_step(tg_env* env, tg_state st, int64_t n, const int32_
     p.reward = out.reward; p.terminated = out.terminated; p.truncated = out.truncated; p.lines = out.lines;
     p.stats = (double*)d_stats;
     // with the packed-byte feature kernel info["board"] is a by-product of its column pass, not of the step kernel
-    const bool info_in_feats = d_info_board && gfeats_fast(env, d_feats, d_legal) && !getenv("TG_INFO_IN_STEP");
+    const bool info_in_feats = d_info_board && ((uintptr_t)d_info_board & 15) == 0 && gfeats_fast(env, d_feats, d_legal) && !getenv("TG_INFO_IN_STEP");
     p.legal = d_legal; p.info_board = info_in_feats ? nullptr : d_info_board; p.fill_high = (uint8_t*)env->stage[3];
     p.mode = 2;
     rc = launch_step(env, p, (cudaStream_t)stream); if (rc) return rc;
