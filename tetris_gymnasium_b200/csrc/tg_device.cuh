@@ -188,23 +188,23 @@ __device__ __forceinline__ uint32_t pcg64_next32(uint32_t* rec) {
 }
 
 // in-place Fisher-Yates of the 7-bag (BagRandomizer.shuffle_bag, components/tetromino_randomizer.py:82-85)
-__device__ __noinline__ uint32_t shuffle_bag(const DevCfg& cfg, Rng& g, uint32_t bag) {
+// (plain values in, value out: a reference to the caller's Rng / Hot would pin them in local memory around the hot loop)
+__device__ __noinline__ uint32_t shuffle_bag_raw(int rng_mode, uint32_t* rec, uint64_t gid, uint32_t bag) {
     uint32_t j6[6];
-    g.dirty = true;
-    if (cfg.rng_mode == 2) {
+    if (rng_mode == 2) {
         // numpy Generator.shuffle: for i = 6..1: j = random_interval(i) (masked rejection on next_uint32)
         for (int i = 6; i >= 1; i--) {
             uint32_t mask = i | (i >> 1); mask |= mask >> 2;
             uint32_t v;
-            do { v = pcg64_next32(g.rec) & mask; } while (v > (uint32_t)i);
+            do { v = pcg64_next32(rec) & mask; } while (v > (uint32_t)i);
             j6[6 - i] = v;
         }
     } else {
-        uint64_t seed = ((uint64_t*)g.rec)[0];
-        uint32_t ctr = g.rec[2];
-        g.rec[2] = ctr + 1;
-        uint32_t c[4] = {ctr, (uint32_t)g.gid, (uint32_t)(g.gid >> 32), 0u};
-        uint32_t d[4] = {ctr, (uint32_t)g.gid, (uint32_t)(g.gid >> 32), 1u};
+        uint64_t seed = ((uint64_t*)rec)[0];
+        uint32_t ctr = rec[2];
+        rec[2] = ctr + 1;
+        uint32_t c[4] = {ctr, (uint32_t)gid, (uint32_t)(gid >> 32), 0u};
+        uint32_t d[4] = {ctr, (uint32_t)gid, (uint32_t)(gid >> 32), 1u};
         philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
         philox4x32_10(d, (uint32_t)seed, (uint32_t)(seed >> 32));
         j6[0] = __umulhi(c[0], 7u); j6[1] = __umulhi(c[1], 6u); j6[2] = __umulhi(c[2], 5u);
@@ -218,6 +218,10 @@ __device__ __noinline__ uint32_t shuffle_bag(const DevCfg& cfg, Rng& g, uint32_t
         bag = (bag & ~(15u << (4 * j))) | (vi << (4 * j));
     }
     return bag & 0x0FFFFFFFu;  // index = 0
+}
+__device__ __forceinline__ uint32_t shuffle_bag(const DevCfg& cfg, Rng& g, uint32_t bag) {
+    g.dirty = true;
+    return shuffle_bag_raw(cfg.rng_mode, g.rec, g.gid, bag);
 }
 
 // Draws that are not the 7-bag: the injected stream (TG_RNG_SEQUENCE) and TrueRandomizer.  Out of line: the call sites
