@@ -57,3 +57,47 @@ def test_functional_single_env_signature_and_philox_bags():
         st, _, _, term, _ = fn.step(TETROMINOES, st, 6, cfg)
         seen.append(sorted(st.queue[0].tolist()))
     assert all(s == list(range(7)) for s in seen)
+
+
+def test_functional_state_record_cache_is_invalidated_by_edits():
+    """`_pack` reuses the record array a State came with only while its fields are untouched: attribute assignment,
+    in-place edits and replace() must all be seen by the next step."""
+    from tetris_gymnasium_b200.envs import tetris_fn as fn
+    from tetris_gymnasium_b200.functional import TETROMINOES, EnvConfig
+    from tetris_gymnasium_b200.functional.core import State
+
+    cfg = EnvConfig(width=10, height=20, padding=4, queue_size=7)
+    B = 64
+    keys = torch.stack([torch.arange(B), torch.arange(B) + 7], dim=1)
+    _, st, _ = fn.batched_reset(TETROMINOES, keys, config=cfg)
+    a = torch.full((B,), 2, dtype=torch.int32, device="cuda")
+
+    def fresh(s):   # a State without the cached record array (forces the slow packing path)
+        return State(**{k: getattr(s, k).clone() for k in ("rng_key", "board", "active_tetromino", "rotation", "x", "y", "queue",
+                                                            "queue_index", "game_over", "score")})
+
+    def same(s1, s2):
+        return all(torch.equal(getattr(s1, k), getattr(s2, k)) for k in ("board", "x", "y", "rotation", "active_tetromino", "queue", "score"))
+
+    for _ in range(5):                                   # untouched loop: cached record array
+        ref, *_ = fn.batched_step(TETROMINOES, fresh(st), a, config=cfg)
+        st, *_ = fn.batched_step(TETROMINOES, st, a, config=cfg)
+        assert same(st, ref)
+    st.x.add_(1)                                         # in-place edit of a view field
+    ref, *_ = fn.batched_step(TETROMINOES, fresh(st), a, config=cfg)
+    nxt, *_ = fn.batched_step(TETROMINOES, st, a, config=cfg)
+    assert same(nxt, ref)
+    st = nxt
+    st.score += 5.0                                      # in-place edit of a copied field
+    ref, *_ = fn.batched_step(TETROMINOES, fresh(st), a, config=cfg)
+    nxt, *_ = fn.batched_step(TETROMINOES, st, a, config=cfg)
+    assert same(nxt, ref) and float(nxt.score.min()) >= 5.0
+    st = nxt
+    st.rotation = (st.rotation + 1) & 3                  # attribute assignment
+    ref, *_ = fn.batched_step(TETROMINOES, fresh(st), a, config=cfg)
+    nxt, *_ = fn.batched_step(TETROMINOES, st, a, config=cfg)
+    assert same(nxt, ref)
+    st = nxt.replace(y=nxt.y + 1)                        # replace(): a new State without the tag
+    ref, *_ = fn.batched_step(TETROMINOES, fresh(st), a, config=cfg)
+    nxt, *_ = fn.batched_step(TETROMINOES, st, a, config=cfg)
+    assert same(nxt, ref)

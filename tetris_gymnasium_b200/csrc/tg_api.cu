@@ -507,7 +507,12 @@ extern "C" int tg_fn_step(int32_t width, int32_t height, int32_t queue_size, int
     p.actions = d_actions; p.seq = d_piece_seq; p.seq_len = seq_len;
     p.obs = d_obs; p.reward = d_reward; p.terminated = d_terminated; p.lines = d_lines;
     const int T = 64;
-    k_fn_step<<<(unsigned)((n + T - 1) / T), T, 0, (cudaStream_t)stream>>>(p);
+    int bstr = (p.Hp * p.Wp + 3) / 4 * 4;
+    if (((bstr / 4) & 1) == 0) bstr += 4;                                  // odd word stride: conflict-free per-env access
+    const size_t smem = ((size_t)T * bstr + 15) / 16 * 16 + (size_t)T * p.H * p.W;
+    if (cudaFuncSetAttribute(k_fn_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return fail(nullptr, TG_ERR_CONFIG, "tg_fn_step: board too large for the shared-memory tile (%zu B)", smem);
+    k_fn_step<<<(unsigned)((n + T - 1) / T), T, smem, (cudaStream_t)stream>>>(p, bstr);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(nullptr, TG_ERR_CUDA, "k_fn_step: %s", cudaGetErrorString(e));
     return TG_OK;

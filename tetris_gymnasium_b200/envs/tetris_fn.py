@@ -33,7 +33,19 @@ def _dev(x=None):
     return torch.device("cuda", torch.cuda.current_device())
 
 
+def _fields(st: State):
+    return (st.rng_key, st.active_tetromino, st.rotation, st.x, st.y, st.queue, st.queue_index, st.game_over, st.score)
+
+
 def _pack(state: State, Q: int) -> torch.Tensor:
+    """State -> the i32[B, 9 + Q] record array tg_fn_step reads.  A State that came out of `_unpack` and whose field
+    tensors are still the same objects at the same version (no attribute assignment, no in-place edit, no replace())
+    carries its record array: the usual `state = step(state)` loop packs nothing."""
+    tag = getattr(state, "_tg_packed", None)
+    if tag is not None:
+        sc, sig = tag
+        if sc.shape[1] == _S + Q and all(id(t) == i and t._version == v for t, (i, v) in zip(_fields(state), sig)):
+            return sc
     B = state.board.shape[0]
     sc = torch.empty((B, _S + Q), dtype=torch.int32, device=state.board.device)
     sc[:, 0] = state.active_tetromino
@@ -49,9 +61,11 @@ def _pack(state: State, Q: int) -> torch.Tensor:
 
 
 def _unpack(board: torch.Tensor, sc: torch.Tensor) -> State:
-    return State(rng_key=sc[:, 7:9].to(torch.int64) & 0xFFFFFFFF, board=board, active_tetromino=sc[:, 0], rotation=sc[:, 1],
-                 x=sc[:, 2], y=sc[:, 3], queue=sc[:, _S:], queue_index=sc[:, 4], game_over=sc[:, 5] != 0,
-                 score=sc[:, 6].contiguous().view(torch.float32))
+    st = State(rng_key=sc[:, 7:9].to(torch.int64) & 0xFFFFFFFF, board=board, active_tetromino=sc[:, 0], rotation=sc[:, 1],
+               x=sc[:, 2], y=sc[:, 3], queue=sc[:, _S:], queue_index=sc[:, 4], game_over=sc[:, 5] != 0,
+               score=sc[:, 6].contiguous().view(torch.float32))
+    st._tg_packed = (sc, tuple((id(t), t._version) for t in _fields(st)))
+    return st
 
 
 def _seq(queue_fn, dev):
