@@ -61,12 +61,13 @@ __global__ void __launch_bounds__(128) k_cnn_obs(const __grid_constant__ CnnPara
     }
     for (int i = lane; i < 2 * p.rec_bytes / 4; i += 32) ((uint32_t*)recbuf)[i] = 0;
     // this lane's output columns: dx = lane + 32 j
-    int sx0[NX], sx1[NX], a0[NX], a1[NX];
+    int sx0[NX], sx1[NX];
+    uint32_t acoef[NX];            // a0 | a1 << 16 (11-bit coefficients, 0 <= a <= 2048)
 #pragma unroll
     for (int j = 0; j < NX; j++) {
         const int dx = lane + 32 * j;
         int4 t = dx < OW ? ((const int4*)p.xtab)[dx] : make_int4(0, 0, 0, 0);
-        sx0[j] = t.x; sx1[j] = t.y; a0[j] = t.z; a1[j] = t.w;
+        sx0[j] = t.x; sx1[j] = t.y; acoef[j] = (uint32_t)t.z | ((uint32_t)t.w << 16);
     }
     __syncthreads();
     const bool tma = (FB & 15) == 0 && (((uintptr_t)p.frames) & 15) == 0 && (p.env_stride & 15) == 0;
@@ -128,9 +129,12 @@ __global__ void __launch_bounds__(128) k_cnn_obs(const __grid_constant__ CnnPara
 #pragma unroll
             for (int j = 0; j < NX; j++) {
                 const uint32_t c0 = s_lut[prow[sx0[j]]], c1 = s_lut[prow[sx1[j]]];
-#pragma unroll
-                for (int k = 0; k < 3; k++)   // kept pre-shifted: the vertical pass only uses h >> 4
-                    dst[j][k] = ((int)((c0 >> (8 * k)) & 255u) * a0[j] + (int)((c1 >> (8 * k)) & 255u) * a1[j]) >> 4;
+                // c0 * a0 + c1 * a1 per channel as 16-bit x 8-bit dot products (IDP.2A): bytes (R0, R1, G0, G1) / (B0, B1, -, -);
+                // kept pre-shifted: the vertical pass only uses h >> 4
+                const uint32_t rg = __byte_perm(c0, c1, 0x5140), bb = __byte_perm(c0, c1, 0x7762);
+                dst[j][0] = (int)(__dp2a_lo(acoef[j], rg, 0u) >> 4);
+                dst[j][1] = (int)(__dp2a_hi(acoef[j], rg, 0u) >> 4);
+                dst[j][2] = (int)(__dp2a_lo(acoef[j], bb, 0u) >> 4);
             }
         };
         uint32_t orow = smem_u32(out) + lane;   // shared-window address of this lane's first pixel of the output row
@@ -153,17 +157,19 @@ __global__ void __launch_bounds__(128) k_cnn_obs(const __grid_constant__ CnnPara
 #pragma unroll
             for (int j = 0; j < NX; j++) {
                 // colours are <= 240 and the coefficient pairs sum to 2048 +- 1: 0 <= v <= 255 without clamping;
-                // the rounding "+ 2" rides on the first product ((t + (2 << 16)) >> 16 == (t >> 16) + 2)
-                const int r = (((yt.z * hc[j][0] + 0x20000) >> 16) + ((yt.w * hn[j][0]) >> 16)) >> 2;
-                const int g = (((yt.z * hc[j][1] + 0x20000) >> 16) + ((yt.w * hn[j][1]) >> 16)) >> 2;
-                const int b = (((yt.z * hc[j][2] + 0x20000) >> 16) + ((yt.w * hn[j][2]) >> 16)) >> 2;
-                const uint32_t N = (uint32_t)(r * 2125 + g * 7154 + b * 721);
-                const uint32_t q = (uint32_t)(((uint64_t)N * 3518437209ull) >> 45);   // N / 10000 for N <= 2,550,000
-                const uint32_t key = (uint32_t)r | ((uint32_t)g << 8) | ((uint32_t)b << 16);
+                // VResizeLinear: (((b0 * h0) >> 16) + ((b1 * h1) >> 16) + 2) >> 2
+                const uint32_t r = (uint32_t)((((yt.z * hc[j][0] + 0x20000) >> 16) + ((yt.w * hn[j][0]) >> 16)) >> 2);
+                const uint32_t g = (uint32_t)((((yt.z * hc[j][1] + 0x20000) >> 16) + ((yt.w * hn[j][1]) >> 16)) >> 2);
+                const uint32_t b = (uint32_t)((((yt.z * hc[j][2] + 0x20000) >> 16) + ((yt.w * hn[j][2]) >> 16)) >> 2);
+                const uint32_t N = r * 2125u + g * 7154u + b * 721u;
+                uint32_t q = (uint32_t)(((uint64_t)N * 3518437209ull) >> 45);   // N / 10000 for N <= 2,550,000
+                // (a branch on N == q * 10000 -- the only candidates -- measured 20 % slower than the unconditional lookup,
+                //  and (b * h) >> 16 as IMAD.HI 15 % slower than multiply + shift)
+                const uint32_t key = r | (g << 8) | (b << 16);
                 uint32_t t0, t1;
                 asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(t0), "=r"(t1) : "r"(exc_addr + q * 8u));
-                const uint32_t low = (uint32_t)(key == t0) | (uint32_t)(key == t1);
-                if (lane + 32 * j < OW) asm volatile("st.shared.u8 [%0], %1;" ::"r"(orow + 32u * j), "r"(q - low) : "memory");
+                q -= (uint32_t)(key == t0) | (uint32_t)(key == t1);
+                if (lane + 32 * j < OW) asm volatile("st.shared.u8 [%0], %1;" ::"r"(orow + 32u * j), "r"(q) : "memory");
             }
         }
         // ---- store: the frame, plus (reset envs) the preceding frames of the stack window ----
