@@ -212,7 +212,9 @@ int tg_rollout(tg_env *env, tg_state st, int64_t n, const int32_t weights[4], in
  *           score (float32 bits), rng_key[0], rng_key[1], then the queue
  *   obs     i8[n][H][W] in {-1, 0, 1}   (get_observation, envs/tetris_fn.py:137-158)
  * d_actions == NULL performs reset (scalars_in then only provides rng_key).  d_piece_seq (nullable, u8[n][seq_len])
- * injects the bags: bag k of env e = seq[e][k*Q .. k*Q+Q); otherwise bags come from Philox(rng_key). */
+ * injects the bags: bag k of env e = seq[e][k*Q .. k*Q+Q); otherwise bags come from Philox(rng_key): permutations
+ * (queue.create_bag_queue, functional/queue.py:20-35) when seq_len >= 0, the uniform queue (queue.create_uniform_queue,
+ * functional/queue.py:71-87: Q draws from [0, Q - 1), maxval exclusive as in the reference) when seq_len < 0. */
 #define TG_FN_SCALARS 9
 int tg_fn_step(int32_t width, int32_t height, int32_t queue_size, int32_t gravity, int64_t n,
                const int8_t *d_board_in, const int32_t *d_scalars_in, const int32_t *d_actions,

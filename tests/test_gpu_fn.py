@@ -101,3 +101,33 @@ def test_functional_state_record_cache_is_invalidated_by_edits():
     ref, *_ = fn.batched_step(TETROMINOES, fresh(st), a, config=cfg)
     nxt, *_ = fn.batched_step(TETROMINOES, st, a, config=cfg)
     assert same(nxt, ref)
+
+
+def test_functional_uniform_queue():
+    """queue.create_uniform_queue (functional/queue.py:71-119): every refill draws queue_size values from [0, queue_size - 1)
+    (randint's maxval is exclusive: the reference never yields the last piece), index restarts at 1."""
+    from tetris_gymnasium_b200.envs import tetris_fn as fn
+    from tetris_gymnasium_b200.functional import TETROMINOES, EnvConfig, create_uniform_queue, uniform_queue_get_next_element
+
+    cfg = EnvConfig(width=10, height=20, padding=4, queue_size=7)
+    B = 512
+    keys = torch.stack([torch.arange(B), torch.arange(B) * 3 + 1], dim=1)
+    _, st, _ = fn.batched_reset(TETROMINOES, keys, config=cfg, create_queue_fn=create_uniform_queue)
+    q0 = st.queue.clone()
+    assert int(q0.min()) >= 0 and int(q0.max()) == 5 and bool((st.queue_index == 1).all())
+    assert torch.equal(st.active_tetromino, q0[:, 0])
+    assert len({tuple(r) for r in q0.tolist()}) > B // 2        # not permutations, env-dependent
+    assert any(len(set(r)) < 7 for r in q0.tolist())            # repeats occur (a bag would never repeat)
+    a = torch.full((B,), 6, dtype=torch.int32, device="cuda")   # hard drops: one piece per step
+    seen = [q0]
+    for t in range(30):
+        st, _, _, term, _ = fn.batched_step(TETROMINOES, st, a, config=cfg, queue_fn=uniform_queue_get_next_element)
+        seen.append(st.queue.clone())
+    allq = torch.stack(seen)
+    assert int(allq.max()) == 5 and int(allq.min()) == 0
+    assert not torch.equal(seen[0], seen[-1])                    # refilled along the way
+    # same key, same selector -> same stream; the bag selector gives permutations instead
+    _, st2, _ = fn.batched_reset(TETROMINOES, keys, config=cfg, create_queue_fn="uniform")
+    assert torch.equal(st2.queue, q0)
+    _, st3, _ = fn.batched_reset(TETROMINOES, keys, config=cfg)
+    assert all(sorted(r) == list(range(7)) for r in st3.queue.tolist())

@@ -20,7 +20,7 @@ struct FnParams {
     const int8_t* board_in; int8_t* board_out;
     const int32_t* sc_in; int32_t* sc_out;
     const int32_t* actions;       // NULL = reset
-    const uint8_t* seq; int64_t seq_len;   // injected bags: bag k of env e = seq[e][k*Q .. k*Q+Q) (NULL = Philox bags)
+    const uint8_t* seq; int64_t seq_len;   // injected bags: bag k of env e = seq[e][k*Q .. k*Q+Q); NULL = Philox bags (seq_len >= 0) or the uniform queue (seq_len < 0)
     int8_t* obs; float* reward; uint8_t* terminated; int32_t* lines;
 };
 
@@ -42,6 +42,14 @@ __device__ __forceinline__ void fn_new_bag(const FnParams& p, int64_t e, int32_t
     uint32_t bagno = (uint32_t)sc[FN_KEY1];
     if (p.seq) {
         for (int i = 0; i < p.Q; i++) q[i] = p.seq[e * p.seq_len + ((int64_t)bagno * p.Q + i) % p.seq_len];
+    } else if (p.seq_len < 0) {
+        // queue.create_uniform_queue (functional/queue.py:71-87): randint(key, (Q,), 0, Q - 1) -- maxval is exclusive, so the
+        // reference never draws piece Q - 1; kept.  Values from Philox(key), not threefry (sequences are not JAX-compatible).
+        for (int i = 0; i < p.Q; i++) {
+            uint32_t c[4] = {bagno, (uint32_t)i, (uint32_t)e, (uint32_t)(e >> 32)};
+            philox4x32_10(c, (uint32_t)sc[FN_KEY0], 0x0a11f02du);
+            q[i] = p.Q > 1 ? (int)__umulhi(c[0], (uint32_t)(p.Q - 1)) : 0;
+        }
     } else {
         for (int i = 0; i < p.Q; i++) q[i] = i;
         for (int i = p.Q - 1; i >= 1; i--) {

@@ -9,7 +9,8 @@ executed by `tg_fn_step` (csrc/tg_fn.cuh).
 
 `queue_fn` / `create_queue_fn`: the reference takes JAX callables; here they select the bag source:
 `None`/`"bag"` = device Philox permutations keyed by `state.rng_key` (NOT bit-compatible with
-jax.random.permutation), or a uint8 tensor `[B, L]` of injected bags (bag k = seq[:, k*Q:(k+1)*Q]).
+jax.random.permutation), `"uniform"` (or the reference's uniform-queue callables by name) = the uniform queue of
+functional/queue.py:71-119, or a uint8 tensor `[B, L]` of injected bags (bag k = seq[:, k*Q:(k+1)*Q]).
 """
 import ctypes as C
 
@@ -68,9 +69,19 @@ def _unpack(board: torch.Tensor, sc: torch.Tensor) -> State:
     return st
 
 
+UNIFORM = "uniform"   # queue selector: functional/queue.py:71-119 (create_uniform_queue / uniform_queue_get_next_element)
+
+
+def _is_uniform(queue_fn):
+    return (isinstance(queue_fn, str) and queue_fn == UNIFORM) or getattr(queue_fn, "__name__", "") in (
+        "create_uniform_queue", "uniform_queue_get_next_element")
+
+
 def _seq(queue_fn, dev):
-    if queue_fn is None or isinstance(queue_fn, str):
-        return None
+    """None / "bag" / the bag-queue callables -> Philox permutations; "uniform" / the uniform-queue callables -> uniform
+    queue; a uint8 array [B, L] -> injected bags."""
+    if queue_fn is None or isinstance(queue_fn, str) or callable(queue_fn):
+        return UNIFORM if _is_uniform(queue_fn) else None
     s = torch.as_tensor(np.asarray(queue_fn) if not torch.is_tensor(queue_fn) else queue_fn)
     return s.to(dev, torch.uint8).contiguous()
 
@@ -87,12 +98,15 @@ def _call(config: EnvConfig, board_in, sc_in, actions, seq):
     reward = torch.empty(B, dtype=torch.float32, device=dev)
     term = torch.empty(B, dtype=torch.uint8, device=dev)
     lines = torch.empty(B, dtype=torch.int32, device=dev)
+    uniform = isinstance(seq, str)
+    if uniform:
+        seq = None
     if seq is not None:
         assert seq.shape[0] == B
     with torch.cuda.device(dev):
         rc = L.tg_fn_step(config.width, config.height, config.queue_size, int(bool(config.gravity_enabled)), B,
                           board_in.data_ptr(), sc_in.data_ptr(), actions.data_ptr() if actions is not None else None,
-                          seq.data_ptr() if seq is not None else None, seq.shape[1] if seq is not None else 0,
+                          seq.data_ptr() if seq is not None else None, seq.shape[1] if seq is not None else (-1 if uniform else 0),
                           board_out.data_ptr(), sc_out.data_ptr(), obs.data_ptr(), reward.data_ptr(), term.data_ptr(),
                           lines.data_ptr(), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
     _lib.check(rc)
