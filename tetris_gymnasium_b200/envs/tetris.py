@@ -18,6 +18,7 @@ from ..mappings.actions import ActionsMapping
 from ..mappings.rewards import RewardsMapping
 
 PADDING = 4  # max tetromino matrix dim (reference envs/tetris.py:130)
+_NO_OBS = _lib.TgObs(None, None, None, None)   # all-NULL tg_obs: the step skips the observation dict
 
 
 class _Space:
@@ -103,6 +104,8 @@ class Tetris:
         if not torch.cuda.is_available():
             raise RuntimeError("tetris_gymnasium_b200 needs a CUDA device: there is no CPU fallback")
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        if self.device.type == "cuda" and self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         if self.device.type != "cuda":
             raise RuntimeError("tetris_gymnasium_b200 runs on CUDA devices only")
         self.num_envs = int(num_envs)
@@ -173,18 +176,30 @@ class Tetris:
         self._stats = torch.zeros(4, dtype=torch.float64, device=dev)
         self._seeded = False
         self._has_reset = False
+        self._dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
         self.emit_obs_dict = True   # wrappers that replace the observation (RgbObservation, FeatureVector) switch it off
 
     # ---- plumbing ---------------------------------------------------------------------------
+    # The state / output buffers are allocated once, so the ctypes structs that carry their pointers are built once too
+    # (for small batches the per-call Python overhead, not the kernel, is the step time).
     def _state(self):
-        return _lib.TgState(self._hot.data_ptr(), self._brd.data_ptr(), self._rng.data_ptr(),
-                            self._seq.data_ptr() if self._seq is not None else None)
+        c = self.__dict__.get("_c_state")
+        if c is None:
+            c = self._c_state = _lib.TgState(self._hot.data_ptr(), self._brd.data_ptr(), self._rng.data_ptr(),
+                                             self._seq.data_ptr() if self._seq is not None else None)
+        return c
 
     def _obs_struct(self):
-        return _lib.TgObs(self._o_board.data_ptr(), self._o_mask.data_ptr(), self._o_holder.data_ptr(), self._o_queue.data_ptr())
+        c = self.__dict__.get("_c_obs")
+        if c is None:
+            c = self._c_obs = _lib.TgObs(self._o_board.data_ptr(), self._o_mask.data_ptr(), self._o_holder.data_ptr(), self._o_queue.data_ptr())
+        return c
 
     def _out_struct(self):
-        return _lib.TgStepOut(self._reward.data_ptr(), self._terminated.data_ptr(), self._truncated.data_ptr(), self._lines.data_ptr())
+        c = self.__dict__.get("_c_out")
+        if c is None:
+            c = self._c_out = _lib.TgStepOut(self._reward.data_ptr(), self._terminated.data_ptr(), self._truncated.data_ptr(), self._lines.data_ptr())
+        return c
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
@@ -265,6 +280,9 @@ class Tetris:
 
     # ---- Tetris.step (reference envs/tetris.py:203-272) -------------------------------------------
     def _actions(self, actions):
+        if torch.is_tensor(actions) and actions.dtype == torch.int32 and actions.device == self.device and actions.is_contiguous() \
+                and actions.shape == (self.num_envs,):
+            return actions                                   # the usual case: no conversion kernels, no checks
         a = actions if torch.is_tensor(actions) else torch.as_tensor(np.asarray(actions))
         a = a.to(device=self.device, dtype=torch.int32, non_blocking=True).contiguous()
         if a.dim() == 0:
@@ -276,10 +294,15 @@ class Tetris:
         """One step of every env.  Returns (obs, reward f32[n], terminated bool[n], truncated bool[n],
         {"lines_cleared": i32[n]}) -- tensors are the env's output buffers, overwritten by the next call."""
         a = self._actions(actions)
-        with torch.cuda.device(self.device):
-            obs = self._obs_struct() if self.emit_obs_dict else _lib.TgObs(None, None, None, None)
-            _lib.check(self._L.tg_step(self._h, self._state(), self.num_envs, a.data_ptr(), obs,
-                                       self._out_struct(), self._stats.data_ptr(), self._stream()), self._h)
+        obs = self._obs_struct() if self.emit_obs_dict else _NO_OBS
+        # tg_step selects the env's device itself; the guard only keeps torch's notion of the current device in step
+        if torch.cuda.current_device() == self._dev_index:
+            rc = self._L.tg_step(self._h, self._state(), self.num_envs, a.data_ptr(), obs, self._out_struct(), self._stats.data_ptr(), self._stream())
+        else:
+            with torch.cuda.device(self.device):
+                rc = self._L.tg_step(self._h, self._state(), self.num_envs, a.data_ptr(), obs, self._out_struct(), self._stats.data_ptr(), self._stream())
+        if rc:
+            _lib.check(rc, self._h)
         return (self._obs(), self._reward, self._terminated.view(torch.bool), self._truncated.view(torch.bool),
                 {"lines_cleared": self._lines})
 
