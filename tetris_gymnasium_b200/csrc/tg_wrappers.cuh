@@ -760,7 +760,19 @@ extern "C" int tg_rollout(tg_env* env, tg_state st, int64_t n, const int32_t wei
     // u32 columns: odd word stride; u64 columns: stride = 2 (mod 4) words keeps 8-byte alignment and spreads the banks
     if (env->col64) { while ((words & 3) != 2) words += 1; } else { words |= 1; }
     p.rec_words = words;
-    const int T = 128;
+    // CTA size: the largest of 128 / 64 / 32 threads that keeps the most env slots resident per SM (big boards: a 20x40
+    // slot is ~1 KB, one 128-thread CTA would be alone on its SM)
+    int T = 128;
+    {
+        size_t best = 0;
+        for (int t = 128; t >= 32; t >>= 1) {
+            const size_t per_cta = (size_t)t * words * 4 + 1024;
+            size_t ctas = (227 * 1024) / per_cta;
+            if (ctas > 32) ctas = 32;
+            if (ctas * t > 768) ctas = 768 / t;          // 80 registers per thread: at most 768 threads per SM
+            if (ctas * t > best) { best = ctas * t; T = t; }
+        }
+    }
     size_t smem = (size_t)T * words * 4;
     auto launch = [&](auto kern) -> int {
         CUDA_TRY(env, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
