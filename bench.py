@@ -271,6 +271,7 @@ def main():
         if world > 1:
             dist.all_reduce(tds, op=dist.ReduceOp.MAX)
         e2e = {"value": world * n * Ke / float(tdt[0]), "unit": UNIT, "steps": Ke, "h2d_bytes_per_step": 4 * n, "d2h_bytes_per_step": d2h,
+               "pcie_gb_per_s_per_gpu": (4 * n + d2h) * Ke / float(tdt[0]) / 1e9,   # the host link, not the GPU, bounds this number
                "note": "tg_step_host: actions from pinned host memory, full observation dict + reward/terminated/truncated/lines read back to pinned host memory every step",
                "obs_on_device": {"value": world * n * Ke / float(tds[0]), "unit": UNIT, "h2d_bytes_per_step": 4 * n, "d2h_bytes_per_step": 5 * n,
                                  "note": "same loop with the observation dict left in HBM (GPU-resident policy): actions H2D, step, reward + terminated D2H, synchronised every step"}}
