@@ -329,7 +329,7 @@ def main():
                        "envs_per_gpu": n, "obs_bytes_per_env": obs_bytes, "l2_policy": "working set per step (%.2f GB) exceeds the 126 MB L2" % (bps * n / 1e9),
                        "parallelism": f"envs sharded over {world} GPU(s), no collective on the step path"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                         "kernel": "tg::k_step_ws<10,20,uint32_t,false> (2 logic warps + 4 image warps per CTA)", "bytes_per_env_step": bps, "commit_frac": commit_frac,
+                         "kernel": "tg::k_step_ws<10,20,uint32_t,0> (2 logic warps + 4 image warps per CTA)", "bytes_per_env_step": bps, "commit_frac": commit_frac,
                          "kernel_ms": kernel_ms, "peak_source": peak_src},
             "clocks": sampler.result(),
             "gpu_launches": K,

@@ -253,7 +253,7 @@ static int check_state(tg_env* env, const tg_state& st) {
 // ---- step / reset launcher ----------------------------------------------------------------------
 template <int WT, int HT, class COLT>
 static int launch_step_t(tg_env* env, StepParams& p, int T, size_t smem, bool ws, cudaStream_t s) {
-    auto kern = ws ? (p.mode == 2 ? k_step_ws<WT, HT, COLT, true> : k_step_ws<WT, HT, COLT, false>) : k_step<WT, HT, COLT>;
+    auto kern = ws ? (p.mode == 2 ? k_step_ws<WT, HT, COLT, 2> : p.mode == 1 ? k_step_ws<WT, HT, COLT, 1> : k_step_ws<WT, HT, COLT, 0>) : k_step<WT, HT, COLT>;
     CUDA_TRY(env, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     CUDA_TRY(env, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, T, smem));

@@ -194,9 +194,25 @@ __device__ __forceinline__ void fill_rows2_w20(const uint32_t* ids5, uint8_t* ou
 // ---- per-env logic of one tile slot (shared by both step kernels) -----------------------------------
 struct TileStats { double ep, ret, len, lines; };
 
+// warp reduction + atomic accumulation of the episode statistics, once per warp at the end of the kernel: out of line (320
+// instructions that have no business in the step kernel's instruction-cache footprint)
+__device__ __noinline__ void flush_stats(double* stats, double ep, double ret, double len, double lines) {
+    for (int o = 16; o > 0; o >>= 1) {
+        ep += __shfl_xor_sync(0xffffffffu, ep, o);
+        ret += __shfl_xor_sync(0xffffffffu, ret, o);
+        len += __shfl_xor_sync(0xffffffffu, len, o);
+        lines += __shfl_xor_sync(0xffffffffu, lines, o);
+    }
+    if ((threadIdx.x & 31) == 0 && ep > 0) {
+        atomicAdd(stats + 0, ep); atomicAdd(stats + 1, ret);
+        atomicAdd(stats + 2, len); atomicAdd(stats + 3, lines);
+    }
+}
+
 // Runs reset / step / grouped placement for env `e` whose records sit at slot `slot` of the staged tile.
 // Returns bit0 = board record dirty, bit1 = rng record dirty.  Writes the 5-tuple scalars and s_box[slot].
-template <class COLT, bool INFO = true, bool GROUPED = true>
+// MODE >= 0: the kernel instantiation's fixed mode (0 step, 1 reset, 2 grouped step); -1: p.mode at run time (k_step)
+template <class COLT, bool INFO = true, int MODE = -1>
 __device__ __forceinline__ uint32_t logic_one_env(const StepParams& p, const Tabs& tb, int64_t e, int slot, int action,
                                                   uint32_t* s_hot, uint8_t* s_brd, uint8_t* s_rng, uint32_t* s_box,
                                                   TileStats& st) {
@@ -213,7 +229,8 @@ __device__ __forceinline__ uint32_t logic_one_env(const StepParams& p, const Tab
     g.gid = cfg.env_id_offset + (uint64_t)e;
     g.dirty = false;
     bool need_reset = false;
-    if (p.mode == 1) {
+    const int mode = MODE >= 0 ? MODE : p.mode;
+    if (mode == 1) {
         need_reset = (!p.reset_mask || p.reset_mask[e]);
         if (need_reset && p.seeds && cfg.rng_mode == 0) { ((uint64_t*)g.rec)[0] = p.seeds[e]; g.rec[2] = 0; g.dirty = true; }
     } else if (cfg.autoreset == 1 && h.pending) {
@@ -222,7 +239,7 @@ __device__ __forceinline__ uint32_t logic_one_env(const StepParams& p, const Tab
         // one env_step call site for all modes (it is the bulk of the kernel's code: instruction cache)
         int act = action;
         bool run = true, invalid = false;
-        if (GROUPED && p.mode == 2) {
+        if (mode == 2) {
             // GroupedActionsObservations.step (wrappers/grouped.py:209-269)
             bool ok = (unsigned)action < (unsigned)cfg.A && p.legal[e * cfg.A + action] != 0;
             p.fill_high[e] = (uint8_t)(!ok && cfg.terminate_on_illegal);
@@ -252,9 +269,9 @@ __device__ __forceinline__ uint32_t logic_one_env(const StepParams& p, const Tab
     }
     // (inline: an out-of-line reset forces the hot record into local memory and cost 6 % on the 4 M-env step)
     if (need_reset) { env_reset<COLT>(cfg, h, rec, g); res.dirty = 1; }
-    if (GROUPED && p.mode == 2 && need_reset) p.fill_high[e] = 0;
+    if (mode == 2 && need_reset) p.fill_high[e] = 0;
     hot_store(h, s_hot + slot * 8);
-    if (p.mode != 1) {
+    if (mode != 1) {
         p.reward[e] = (float)res.reward;
         p.terminated[e] = (uint8_t)res.terminated;
         p.truncated[e] = 0;
@@ -264,7 +281,7 @@ __device__ __forceinline__ uint32_t logic_one_env(const StepParams& p, const Tab
     const uint32_t show = !((Bact >> h.y) & 1);
     s_box[slot] = (uint32_t)h.x | ((uint32_t)h.y << 8) | ((uint32_t)tb.n[h.p] << 16) | (show << 20) |
                   ((uint32_t)h.p << 24) | ((uint32_t)h.r << 28);
-    if (INFO && GROUPED && p.mode == 2 && p.info_board) {
+    if (INFO && mode == 2 && p.info_board) {
         // info["board"]: FeatureVectorObservation of the real observation (wrappers/grouped.py:260-264)
         uint8_t f[32];
         int ln;
@@ -484,9 +501,10 @@ __global__ void __launch_bounds__(256) k_step(const __grid_constant__ StepParams
 __device__ __forceinline__ void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void named_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
-// GROUPED = true: the grouped placement step (mode 2) -- its code (legal-mask test, info board, whole-tile write-back) is
-// compiled out of the step / reset instantiation, whose speed depends on the code footprint (instruction cache).
-template <int WT, int HT, class COLT, bool GROUPED>
+// MODE = 0 step, 1 reset, 2 grouped placement step: one instantiation each, so that the step instantiation carries neither
+// the reset-mode code nor the grouped code (legal-mask test, info board, whole-tile write-back) -- its speed depends on the
+// code footprint (instruction cache).
+template <int WT, int HT, class COLT, int MODE>
 __global__ void __launch_bounds__(256) k_step_ws(const __grid_constant__ StepParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const DevCfg& cfg = p.cfg;
@@ -518,6 +536,7 @@ __global__ void __launch_bounds__(256) k_step_ws(const __grid_constant__ StepPar
         for (int s = 0; s < NS; s++) mbar_init(bar + s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    constexpr bool GROUPED = MODE == 2;
     const bool want_obs = p.o_board != nullptr;
     init_cta(want_obs ? E : 0, W, H, s_rowbytes, s_cells, s_n, i_board, i_mask, tid, T);   // no image buffers without the obs dict
 
@@ -547,11 +566,11 @@ __global__ void __launch_bounds__(256) k_step_ws(const __grid_constant__ StepPar
             const int64_t base = tile * E;
             const int nv = (int)min((int64_t)E, p.n - base);
             int action = 0;
-            if (p.mode != 1 && lane < nv) action = p.actions[base + lane];
+            if (MODE != 1 && lane < nv) action = p.actions[base + lane];
             mbar_wait(bar + s, (uint32_t)((k / NS) & 1));
             uint32_t dirty = 0;
             if (lane < nv)
-                dirty = logic_one_env<COLT, false, GROUPED>(p, tb, base + lane, lane, action, (uint32_t*)(smem + p.off_hot + s * p.st_hot),
+                dirty = logic_one_env<COLT, false, MODE>(p, tb, base + lane, lane, action, (uint32_t*)(smem + p.off_hot + s * p.st_hot),
                                                    smem + p.off_brd + s * p.st_brd, smem + p.off_rng + s * p.st_rng, s_boxes + s * E, st);
             // grouped mode: tiles where most envs committed (nearly always) write their board records back as ONE bulk copy
             const int ndirty = GROUPED ? __popc(__ballot_sync(0xffffffffu, (dirty & 1u) != 0)) : 0;
@@ -559,18 +578,7 @@ __global__ void __launch_bounds__(256) k_step_ws(const __grid_constant__ StepPar
             __syncwarp();
             named_arrive(1 + s, 32 + FT);   // ready[s]: the fill warps may consume stage s
         }
-        if (p.stats) {
-            for (int o = 16; o > 0; o >>= 1) {
-                st.ep += __shfl_xor_sync(0xffffffffu, st.ep, o);
-                st.ret += __shfl_xor_sync(0xffffffffu, st.ret, o);
-                st.len += __shfl_xor_sync(0xffffffffu, st.len, o);
-                st.lines += __shfl_xor_sync(0xffffffffu, st.lines, o);
-            }
-            if (lane == 0 && st.ep > 0) {
-                atomicAdd(p.stats + 0, st.ep); atomicAdd(p.stats + 1, st.ret);
-                atomicAdd(p.stats + 2, st.len); atomicAdd(p.stats + 3, st.lines);
-            }
-        }
+        if (p.stats) flush_stats(p.stats, st.ep, st.ret, st.len, st.lines);
     } else {
         // ===== image / store warps =====
         const bool leader = (ft == 0);
@@ -595,7 +603,7 @@ __global__ void __launch_bounds__(256) k_step_ws(const __grid_constant__ StepPar
                 mask_set_and_overlay(s_boxes + s * E, nv, s_cells, i_board, i_mask, OB, Wp, ft, FT);
                 for (int i = ft; i < nv; i += FT) s_boxprev[i] = s_boxes[s * E + i];
             }
-            if (GROUPED && p.mode == 2 && p.info_board) {
+            if (GROUPED && p.info_board) {
                 // info["board"] = FeatureVectorObservation of the real observation (wrappers/grouped.py:260-264): rows 0-1 zeroed,
                 // active piece projected when it does not collide.  One thread per (env, column), then one thread per env.
                 uint8_t* f_h = smem + p.off_feat;          // [E][32] heights
