@@ -261,7 +261,20 @@ static int launch_step_t(tg_env* env, StepParams& p, int T, size_t smem, bool ws
     int64_t ntiles = (p.n + p.E - 1) / p.E;
     int64_t grid = (int64_t)env->num_sms * per_sm;
     if (grid > ntiles) grid = ntiles;
-    kern<<<(unsigned)grid, T, smem, s>>>(p);
+    if (ws && !getenv("TG_NO_PDL")) {
+        // programmatic stream serialization: this grid's prologue may overlap the tail of the previous kernel on the stream
+        // (k_step_ws waits with griddepcontrol.wait before it touches global memory)
+        cudaLaunchConfig_t lc;
+        memset(&lc, 0, sizeof lc);
+        lc.gridDim = dim3((unsigned)grid); lc.blockDim = dim3((unsigned)T); lc.dynamicSmemBytes = smem; lc.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        lc.attrs = at; lc.numAttrs = 1;
+        CUDA_TRY(env, cudaLaunchKernelEx(&lc, kern, p));
+    } else {
+        kern<<<(unsigned)grid, T, smem, s>>>(p);
+    }
     CUDA_TRY(env, cudaGetLastError());
     return TG_OK;
 }

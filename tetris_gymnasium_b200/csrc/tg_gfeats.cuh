@@ -114,6 +114,9 @@ __global__ void __maxnreg__(W == 10 ? GF_REGS : 96) k_grouped_feats_x(const DevC
     // ---- phase 1: thread = (column xb, env e): column -> shared memory, its height / holes with row 0 zeroed (Q1) ----
     if (tid < 28) s_prec[tid] = (&c_prec[0][0])[tid];
     if (tid == 0) s_nslow = 0;
+    // programmatic dependent launch (see k_step_ws): this grid may be scheduled while the placement step drains
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     if (live) {
         const COLT col = ((const COLT*)(board + (base + e) * cfg.board_stride))[xb];
         s_colp[e * CS + P + xb] = col;

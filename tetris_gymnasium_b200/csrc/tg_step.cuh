@@ -550,6 +550,11 @@ __global__ void __launch_bounds__(256) k_step_ws(const __grid_constant__ StepPar
         bulk_g2s(smem + p.off_brd + s * p.st_brd, p.board + base * BS, (uint32_t)(nv * BS), bar + s);
         bulk_g2s(smem + p.off_rng + s * p.st_rng, p.rng + base * RS, (uint32_t)(nv * RS), bar + s);
     };
+    // Programmatic dependent launch: the next launch on the stream (usually the next step) may start its prologue (tables,
+    // image templates, barriers -- everything above) while this grid drains; nothing of the state or of the caller's buffers
+    // is touched before the preceding grid has completed.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     if (ft == 0) {   // the fill leader owns all TMA traffic: tiles 0 .. NS-2 of this CTA go to stages 0 .. NS-2
         for (int j = 0; j < NS - 1; j++)
             if ((int64_t)blockIdx.x + j * G < ntiles) issue_load((int64_t)blockIdx.x + j * G, j);

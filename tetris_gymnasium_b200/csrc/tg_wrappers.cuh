@@ -628,6 +628,16 @@ static int launch_grouped_observe(tg_env* env, tg_state st, int64_t n, uint8_t* 
         auto launch = [&](auto kern, size_t smem, int T) -> int {
             CUDA_TRY(env, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             CUDA_TRY(env, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            if (n >= 16384 && !getenv("TG_NO_PDL")) {   // (tiny batches are bound by the host-side launch cost, which the extended launch raises)
+                cudaLaunchConfig_t lc;
+                memset(&lc, 0, sizeof lc);
+                lc.gridDim = dim3((unsigned)((n + 31) / 32)); lc.blockDim = dim3((unsigned)T); lc.dynamicSmemBytes = smem; lc.stream = s;
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                at[0].val.programmaticStreamSerializationAllowed = 1;
+                lc.attrs = at; lc.numAttrs = 1;
+                CUDA_TRY(env, cudaLaunchKernelEx(&lc, kern, d, n, (const uint8_t*)st.hot, (const uint8_t*)st.board, d_feats, d_legal, fill_high, d_info_board));
+            } else
             kern<<<(unsigned)((n + 31) / 32), T, smem, s>>>(d, n, (const uint8_t*)st.hot, (const uint8_t*)st.board, d_feats, d_legal, fill_high, d_info_board);
             CUDA_TRY(env, cudaGetLastError());
             return TG_OK;
