@@ -531,6 +531,24 @@ extern "C" int tg_fn_step(int32_t width, int32_t height, int32_t queue_size, int
     return TG_OK;
 }
 
+// Launch with programmatic stream serialization (the kernel must execute griddepcontrol.wait before it touches global
+// memory): its CTAs may be scheduled while the previous kernel on the stream drains.  TG_NO_PDL=1: plain launch.
+template <class K, class... A>
+static cudaError_t launch_pdl(K kern, unsigned grid, unsigned block, size_t smem, cudaStream_t s, A... args) {
+    if (getenv("TG_NO_PDL")) {
+        kern<<<grid, block, smem, s>>>(args...);
+        return cudaGetLastError();
+    }
+    cudaLaunchConfig_t lc;
+    memset(&lc, 0, sizeof lc);
+    lc.gridDim = dim3(grid); lc.blockDim = dim3(block); lc.dynamicSmemBytes = smem; lc.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = at; lc.numAttrs = 1;
+    return cudaLaunchKernelEx(&lc, kern, args...);
+}
+
 // ---- wrappers (tg_wrappers.cuh) ------------------------------------------------------------------------
 #include "tg_wrappers.cuh"
 #include "tg_cnn.cuh"

@@ -55,6 +55,8 @@ __global__ void __launch_bounds__(128) k_cnn_obs(const __grid_constant__ CnnPara
     for (int i = threadIdx.x; i < OH; i += blockDim.x) s_y[i] = ((const int4*)p.ytab)[i];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_exc[i] = ((const uint2*)p.gray_exc)[i];
     const uint32_t exc_addr = smem_u32(s_exc);
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // programmatic dependent launch, see k_step_ws
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     for (int i = lane; i < NP; i += 32) {   // constant part of the id image (see k_rgb)
         int r = i / RW, c = i - r * RW;
         pix[i] = (c < Wp && r < H && c >= P && c < P + W) ? 0 : 1;
@@ -282,8 +284,7 @@ extern "C" int tg_cnn_observe(tg_env* env, tg_state st, int64_t n, int32_t out_h
         CUDA_TRY(env, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, T, smem));
         int64_t blocks = (n + nw - 1) / nw, cap = (int64_t)env->num_sms * (per_sm > 0 ? per_sm : 1);
         if (blocks > cap) blocks = cap;
-        kern<<<(unsigned)blocks, T, smem, (cudaStream_t)stream>>>(p);
-        CUDA_TRY(env, cudaGetLastError());
+        CUDA_TRY(env, launch_pdl(kern, (unsigned)blocks, (unsigned)T, smem, (cudaStream_t)stream, p));
         return TG_OK;
     };
     if (env->col64) return NX == 1 ? launch(k_cnn_obs<uint64_t, 1>) : NX == 2 ? launch(k_cnn_obs<uint64_t, 2>) : NX == 3 ? launch(k_cnn_obs<uint64_t, 3>) : launch(k_cnn_obs<uint64_t, 4>);

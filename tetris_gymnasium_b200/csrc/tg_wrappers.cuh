@@ -277,6 +277,8 @@ __global__ void __launch_bounds__(256, 3) k_grouped_boards_stream(const DevCfg c
     const COLT playfield = (COLT(1) << H) - 1;
     const int64_t stride = (int64_t)gridDim.x * nwarps;
     int64_t e = (int64_t)blockIdx.x * nwarps + warp;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // programmatic dependent launch, see k_step_ws
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     if (e < n) warp_prefetch_env(recbuf, board, hot, e, BS, lane);
     bool act[NV];
 #pragma unroll
@@ -483,6 +485,8 @@ __global__ void __launch_bounds__(256, 3) k_rgb(const DevCfg cfg, int64_t n, con
         if (lane < 2) cp_async16(dst + BS + 16 * lane, hot + ee * 32 + 16 * lane);
         cp_async_commit();
     };
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // programmatic dependent launch, see k_step_ws
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     if (e < n) prefetch(e, recbuf);
     for (int it = 0; e < n; e += stride, it++) {
         const uint32_t* rec = (const uint32_t*)(recbuf + (it & 1) * rec_bytes);
@@ -607,8 +611,7 @@ extern "C" int tg_render_rgb(tg_env* env, tg_state st, int64_t n, uint8_t* d_img
         CUDA_TRY(env, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, T, smem));
         int64_t blocks = (n + nw - 1) / nw, cap = (int64_t)env->num_sms * (per_sm > 0 ? per_sm : 1);
         if (blocks > cap) blocks = cap;
-        kern<<<(unsigned)blocks, T, smem, (cudaStream_t)stream>>>(d, n, (const uint8_t*)st.hot, (const uint8_t*)st.board, d_img, rec_bytes, pix_bytes, rgb_bytes);
-        CUDA_TRY(env, cudaGetLastError());
+        CUDA_TRY(env, launch_pdl(kern, (unsigned)blocks, (unsigned)T, smem, (cudaStream_t)stream, d, n, (const uint8_t*)st.hot, (const uint8_t*)st.board, d_img, rec_bytes, pix_bytes, rgb_bytes));
         return TG_OK;
     };
     return env->col64 ? launch(k_rgb<uint64_t>) : launch(k_rgb<uint32_t>);
@@ -682,8 +685,7 @@ static int launch_grouped_observe(tg_env* env, tg_state st, int64_t n, uint8_t* 
             CUDA_TRY(env, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, T, smem));
             int64_t blocks = (n + nw - 1) / nw, cap = (int64_t)env->num_sms * (per_sm > 0 ? per_sm : 1);
             if (blocks > cap) blocks = cap;
-            kern<<<(unsigned)blocks, T, smem, s>>>(d, n, (const uint8_t*)st.hot, (const uint8_t*)st.board, d_boards, d_legal, fill_high, rec_bytes, img_bytes, gbuf_bytes);
-            CUDA_TRY(env, cudaGetLastError());
+            CUDA_TRY(env, launch_pdl(kern, (unsigned)blocks, (unsigned)T, smem, s, d, n, (const uint8_t*)st.hot, (const uint8_t*)st.board, d_boards, d_legal, fill_high, rec_bytes, img_bytes, gbuf_bytes));
             return TG_OK;
         };
         int rc;
