@@ -14,6 +14,9 @@
  *     (PyTorch allocates them; the library never frees them); 16-byte aligned.
  *   - every call is asynchronous on the passed `stream` (a cudaStream_t passed as void*), no
  *     implicit synchronisation; the *_host entry points synchronise before returning.
+ *     The step / wrapper kernels are launched with programmatic stream serialization and execute griddepcontrol.wait before
+ *     their first access to global memory: stream-order semantics are unchanged, only their prologue may overlap the tail
+ *     of the preceding kernel on the stream (TG_NO_PDL=1 selects plain launches).
  *   - return value: 0 = OK, otherwise a TG_ERR_* code; tg_last_error() gives the text.
  *   - invalid *actions* are data errors: the env treats them like the reference's unmatched
  *     elif-chain (no move), it does not abort (reference asserts, envs/tetris.py:215).
