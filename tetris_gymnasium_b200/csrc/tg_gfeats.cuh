@@ -8,8 +8,8 @@
 //     new heights = bytewise max(old, H - y - top offset) under the piece's column mask, re-inserted with two funnel shifts;
 //   * holes' = holes + sum(new) - sum(old) - 4 (IDP.4A), max' = max(max, H - y - min top offset),
 //     bumpiness = sum |h[c+1] - h[c]| over the packed vector (VABSDIFF4 with accumulate), no incremental bookkeeping;
-//   * full rows = pre[c0] & suf[c1] & AND_j (col_j | piece column j << y) over the matrix columns (columns outside the
-//     piece add nothing: they are part of pre / suf or all-ones walls);
+//   * full rows = L & R & AND_j (col_j | piece column j << y) over the four window columns, L / R = prefix / suffix AND of
+//     the field columns left / right of the window (the same for the four rotations; wall columns are all ones);
 //   * placements that clear rows or put a cell into the row the feature wrapper zeroes are rare: they are
 //     collected in shared memory and evaluated column by column (exact row-clear arithmetic) in a dense second pass.
 // The tile [32][4W][F] is staged in shared memory in output layout and leaves with 128-bit stores.
@@ -203,8 +203,9 @@ __global__ void __maxnreg__(W == 10 ? GF_REGS : 96) k_grouped_feats_x(const DevC
             const uint32_t O4 = __funnelshift_r(Wlo, Whi, sh);
             const uint32_t sums = s_sum[e];
             const int holes0 = (int)(sums & 0xFFFFu), maxh0 = (int)(sums >> 16);
-            const COLT* pre = s_pre + e * PS;
-            const COLT* suf = s_suf + e * PS;
+            // full rows = AND over ALL field columns of (column | piece bits): the columns left / right of the 4-column window
+            // are the same for the four rotations (window columns without piece cells contribute themselves, wall columns ones)
+            const COLT LR = s_pre[e * PS + max(x - P, 0)] & s_suf[e * PS + min(x - P + 3, W - 1)] & field;
 #pragma unroll
             for (int r = 0; r < 4; r++) {
                 const int rot = (rot0 + r) & 3;                         // cumulative rot90 presses (wrappers/grouped.py:153-154)
@@ -231,7 +232,7 @@ __global__ void __maxnreg__(W == 10 ? GF_REGS : 96) k_grouped_feats_x(const DevC
                     for (int k = 0; k < NH; k++) hw[k] = 0;
                     summary = 0;                                        // game over: zeros board
                     if (!((B >> y) & 1)) {
-                        COLT full = pre[c0] & suf[c1] & field;
+                        COLT full = LR;
 #pragma unroll
                         for (int j = 0; j < 4; j++) full &= cj[j] | ((COLT)((pr.x >> (16 + 4 * j)) & 15u) << y);
                         if (full != 0 || y + mintop == 0) {

@@ -229,6 +229,8 @@ __global__ void __launch_bounds__(128, 6) k_rollout_x(const __grid_constant__ Ro
                 COLT cj[4];
 #pragma unroll
                 for (int j = 0; j < 4; j++) cj[j] = colp[x + j];
+                // columns left / right of the 4-column window: shared by the four rotations (see tg_gfeats.cuh)
+                const COLT LR = pre[max(x - P, 0)] & suf[min(x - P + 3, W - 1)] & field;
 #pragma unroll
                 for (int r = 0; r < 4; r++) {
                     const int a = 4 * xb + r;
@@ -245,7 +247,7 @@ __global__ void __launch_bounds__(128, 6) k_rollout_x(const __grid_constant__ Ro
                     const bool legal = c0 >= 0 && c1 < W;
                     if (legal && first_legal < 0) first_legal = a;
                     const bool lands = legal && !((B >> y) & 1);
-                    COLT full = pre[legal ? c0 : 0] & suf[legal ? c1 : 0] & field;
+                    COLT full = LR;
 #pragma unroll
                     for (int j = 0; j < 4; j++) full &= cj[j] | ((COLT)((q.x >> (16 + 4 * j)) & 15u) << y);
                     const bool exact = lands && (full != 0 || y + mintop == 0);
