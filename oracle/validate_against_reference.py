@@ -119,6 +119,67 @@ def check_grouped(ref, episodes, width, height, gravity, queue_size, seed0, use_
     return n_steps
 
 
+def check_grouped_constructed(ref, n_boards, width, height, queue_size, seed0, use_features):
+    """GroupedActionsObservations on CONSTRUCTED boards poked into the live reference env the way its own tests do
+    (env.unwrapped.board / active_tetromino): nearly full bottom rows with wells (placements that clear 1-4 rows), rubble,
+    and towers into the spawn rows (placements ending in row 0, game-over placements) -- the rare situations of the placement
+    enumeration.  Every placement's board or feature row, the legal mask and one executed placement."""
+    import copy
+
+    R = ref
+    rng = np.random.default_rng(seed0)
+    W, H = width, height
+    n_checked = cleared = 0
+    for i in range(n_boards):
+        seq = rng.integers(0, 7, size=64)
+        base = R["make"](width=W, height=H, gravity=False, queue_size=queue_size, seq=seq)
+        wrappers = [R["FeatureVectorObservation"](base)] if use_features else None
+        env = R["GroupedActionsObservations"](base, observation_wrappers=wrappers)
+        orc = OracleEnv(width=W, height=H, gravity=False, queue_size=queue_size)
+        orc.set_sequence(seq)
+        env.reset()
+        orc.reset()
+        b = orc.board
+        k = int(rng.integers(1, 6))
+        b[H - k:H, 4:4 + W] = rng.integers(2, 9, size=(k, W))
+        wells = rng.choice(W, size=int(rng.integers(1, 3)), replace=False)
+        depth = int(rng.integers(1, k + 1))
+        b[H - k:H - k + depth, 4 + wells] = 0
+        noise = rng.random((3, W)) < 0.3
+        b[H - k - 3:H - k, 4:4 + W] = np.where(noise, rng.integers(2, 9, size=(3, W)), 0)
+        if i % 3 == 0:
+            for c in rng.choice(W, size=int(rng.integers(1, W)), replace=False):
+                top = int(rng.integers(0, 6))
+                col = np.where(rng.random(H - k - top) < 0.8, rng.integers(2, 9, size=H - k - top), 0)
+                col[0] = 3
+                b[top:H - k, 4 + c] = col
+        piece, rot = int(rng.integers(0, 7)), int(rng.integers(0, 4))
+        orc.board = b
+        orc.set_active(piece, rot)
+        base.board = b.copy()
+        t = copy.deepcopy(base.tetrominoes[piece])
+        for _ in range(rot):
+            t = base.rotate(t, True)
+        base.active_tetromino = t
+        g_ref = env.observation(base._get_obs())
+        f, bb, legal = orc.grouped_observe(features=use_features, boards=not use_features)
+        g_orc = f if use_features else bb
+        assert np.array_equal(g_ref, g_orc), f"constructed board {i}: grouped obs"
+        assert np.array_equal(env.legal_actions_mask.astype(np.uint8), legal), f"constructed board {i}: legal mask"
+        _, _, ln = orc.grouped_observe_lines()
+        cleared += int((ln > 0).sum())
+        a = int(rng.choice(np.flatnonzero(legal)))
+        g_ref, r_ref, term_ref, _, info = env.step(a)
+        code, r_orc, term_orc, l_orc = orc.grouped_step(a, True)
+        assert float(r_ref) == r_orc and bool(term_ref) == term_orc and int(info["lines_cleared"]) == l_orc, f"constructed board {i}: step"
+        assert np.array_equal(base.board, orc.board)
+        f, bb, legal = orc.grouped_observe(features=use_features, boards=not use_features)
+        assert np.array_equal(g_ref, f if use_features else bb), f"constructed board {i}: obs after the step"
+        n_checked += 1
+    assert cleared > n_boards, "the constructed boards should produce many row-clearing placements"
+    return n_checked
+
+
 def run(scale=1):
     ref = _refload.load()
     n = 0
@@ -136,6 +197,9 @@ def run(scale=1):
     g += check_grouped(ref, 3 * scale, 10, 20, True, 4, 13, True, False)
     g += check_grouped(ref, 2 * scale, 20, 40, False, 5, 14, True, True, max_steps=300)
     g += check_grouped(ref, 2 * scale, 7, 10, False, 4, 15, False, True)
+    g += check_grouped_constructed(ref, 60 * scale, 10, 20, 4, 21, True)
+    g += check_grouped_constructed(ref, 30 * scale, 10, 20, 4, 22, False)
+    g += check_grouped_constructed(ref, 16 * scale, 20, 40, 5, 23, True)
     g += check_grouped(ref, 2 * scale, 10, 20, False, 4, 16, True, True, max_steps=400, greedy=True)
     g += check_grouped(ref, 1 * scale, 20, 40, False, 5, 17, True, False, max_steps=250, greedy=True)
     return n, g
