@@ -12,6 +12,8 @@ import torch
 from .. import _lib
 from .observation import FeatureVectorObservation
 
+_NO_OBS = _lib.TgObs(None, None, None, None)
+
 
 class GroupedActionsObservations:
     def __init__(self, env, observation_wrappers=None, terminate_on_illegal_action: bool = True):
@@ -92,9 +94,16 @@ class GroupedActionsObservations:
         u = self.unwrapped
         a = u._actions(action)
         want_dict = self._featw is None
-        obs = u._obs_struct() if want_dict else _lib.TgObs(None, None, None, None)
-        with torch.cuda.device(u.device):
-            _lib.check(u._L.tg_grouped_step(u._h, u._state(), u.num_envs, a.data_ptr(), self._legal.data_ptr(),
-                                            self._ptr(self._feats), self._ptr(self._boards), self._ptr(self._info_board),
-                                            obs, u._out_struct(), u._stats.data_ptr(), u._stream()), u._h)
+        obs = u._obs_struct() if want_dict else _NO_OBS
+        c = self.__dict__.get("_c_ptrs")
+        if c is None:      # the output buffers are allocated once: so are their pointers
+            c = self._c_ptrs = (self._legal.data_ptr(), self._ptr(self._feats), self._ptr(self._boards), self._ptr(self._info_board))
+        args = (u._h, u._state(), u.num_envs, a.data_ptr(), c[0], c[1], c[2], c[3], obs, u._out_struct(), u._stats.data_ptr(), u._stream())
+        if torch.cuda.current_device() == u._dev_index:
+            rc = u._L.tg_grouped_step(*args)
+        else:
+            with torch.cuda.device(u.device):
+                rc = u._L.tg_grouped_step(*args)
+        if rc:
+            _lib.check(rc, u._h)
         return (self._result(), u._reward, u._terminated.view(torch.bool), u._truncated.view(torch.bool), self._info())
