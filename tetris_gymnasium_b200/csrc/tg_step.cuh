@@ -1,15 +1,16 @@
-// tg_step.cuh -- the per-call batched step / reset kernel (BASELINE config 2).
+// tg_step.cuh -- the per-call batched step / reset kernels (BASELINE config 2).
 //
-// One persistent CTA (T threads) loops over tiles of E consecutive envs (T = 4E by default):
-//   1. TMA bulk loads (cp.async.bulk, mbarrier completion) bring the tile's hot records and board
-//      records HBM -> shared memory as two contiguous copies;
-//   2. thread e < E runs the game logic of env e on shared memory (bitboard collision / drop / commit);
-//   3. all T threads expand the nibble id planes into the padded uint8 board image, the mask image,
-//      the holder and the queue images, which live in shared memory with their constant parts
-//      (bedrock, zeros) written once per CTA;
-//   4. TMA bulk stores write the four observation tiles and the hot tile back as contiguous,
-//      fully coalesced copies; board records are written back only for envs that committed a piece.
-// HBM traffic per env-step = hot 32 R + 32 W, board record R (+ W on commit), action 4,
+// k_step_ws (the default): persistent, warp-specialised CTAs loop over tiles of E = 32 consecutive envs
+//   * NL logic warps (lane = env) run the game logic on TMA-staged records in shared memory, NL + 2 state stages in flight
+//     (cp.async.bulk + mbarrier), each logic warp takes every NL-th tile of its CTA;
+//   * the image / store warps expand the nibble id planes into the padded uint8 board image, the mask image, the holder
+//     and the queue images (constant parts -- bedrock, zeros -- written once per CTA) and issue the TMA bulk stores:
+//     four observation tiles + the hot tile as contiguous copies, board records only for envs that committed a piece;
+//   * one instantiation per mode (step / reset / grouped placement step): the step instantiation's speed depends on its
+//     code footprint, so it carries neither the reset-mode nor the grouped code;
+//   * launched with programmatic stream serialization: the prologue overlaps the previous kernel's tail.
+// k_step: the two-stage variant without warp specialisation (very large boards, TG_WS=0).
+// HBM traffic per env-step = hot 32 R + 32 W, board record R (+ W on commit), rng record R, action 4,
 // outputs 10, observation dict Hp*Wp*2 + 16 + 16Q.
 #pragma once
 #include "tg_device.cuh"
@@ -495,9 +496,9 @@ __global__ void __launch_bounds__(256) k_step(const __grid_constant__ StepParams
     }
 }
 
-// ---- warp-specialised variant: warp 0 runs the game logic one tile ahead, the other warps produce and
-// store the observation images.  Three state stages (hot + board + rng records of 32 envs each) are kept
-// in flight by TMA; the roles meet on named barriers (ready[stage]) and mbarriers (full[stage]). ----------
+// ---- warp-specialised variant: the logic warps run ahead of the warps that produce and store the observation
+// images.  NL + 2 state stages (hot + board + rng records of 32 envs each) are kept in flight by TMA; the roles
+// meet on named barriers (ready[stage]) and mbarriers (full[stage]). ----------
 __device__ __forceinline__ void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void named_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
