@@ -1,0 +1,94 @@
+"""Size-independent properties at BASELINE.json's full size (4,194,304 envs, 10x20, queue 7, obs dict every step), where the
+C oracle is far too slow to follow: invariants of the game that tie the observation writer, the state records and the 5-tuple
+together, determinism, and shard invariance (the first 65,536 envs of the big batch equal a 65,536-env run).  The small-batch
+tests (test_gpu_base.py, test_gpu_10k_episodes.py) establish bit-exactness against the oracle; these check that nothing changes
+with size (tile scheduling, persistent CTAs, 32-bit offsets: 4 M envs x 432 B images exceed 2^31 bytes per array)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+N, T, W, H, Q = 1 << 22, 48, 10, 20, 7
+
+
+def _run(n, acts, offset=0):
+    from tetris_gymnasium_b200.envs.tetris import Tetris
+
+    env = Tetris(num_envs=n, queue_size=Q, autoreset_mode="next_step", env_id_offset=offset)
+    obs, _ = env.reset(seed=42)
+    lines_acc = torch.zeros(n, dtype=torch.int32, device="cuda")
+    prev_term = torch.zeros(n, dtype=torch.bool, device="cuda")
+    total_term = 0
+    for t in range(acts.shape[0]):
+        obs, r, term, trunc, info = env.step(acts[t, :n])
+        lines_acc = torch.where(prev_term, torch.zeros_like(lines_acc), lines_acc) + info["lines_cleared"]
+        prev_term = term.clone()
+        total_term += int(term.sum())
+        assert not bool(trunc.any())
+    return env, obs, lines_acc, total_term
+
+
+def test_full_size_invariants_determinism_and_shard_invariance():
+    if torch.cuda.mem_get_info()[0] < 40 * 2**30:
+        pytest.skip("needs about 40 GB of free device memory")
+    g = torch.Generator(device="cuda")
+    g.manual_seed(42)
+    acts = torch.randint(0, 8, (T, N), dtype=torch.int32, device="cuda", generator=g)
+    acts[4::5] = 5                                                # every fifth step: hard drop for everyone (commits, line clears)
+    env, obs, lines_acc, total_term = _run(N, acts)
+    st = env.get_state()
+    board = st["board"]                                           # locked cells, u8 [N, 24, 18]
+    field = board[:, :H, 4:4 + W]
+    # bedrock frame intact, no filled row survives a commit
+    assert bool((board[:, H:, :] == 1).all()) and bool((board[:, :H, :4] == 1).all()) and bool((board[:, :H, 4 + W:] == 1).all())
+    assert not bool((field != 0).all(dim=2).any())
+    assert int(field.max()) <= 8
+    # every commit adds 4 cells, every cleared row removes W: cells + W * lines == 0 (mod 4) since the env's last reset
+    cells = (field != 0).flatten(1).sum(1).to(torch.int32)
+    assert bool(((cells + W * lines_acc) % 4 == 0).all())
+    # observation dict vs state: board image = locked cells + the <= 4 cells of the active piece, inside the n x n mask box
+    diff = obs["board"] != board
+    nd = diff.flatten(1).sum(1)
+    assert bool(((nd == 0) | (nd == 4)).all())
+    assert not bool((diff & (obs["active_tetromino_mask"] == 0)).any())
+    piece = st["piece"]
+    nbox = torch.where(piece == 0, 4, torch.where(piece == 1, 2, 3))
+    assert torch.equal(obs["active_tetromino_mask"].flatten(1).sum(1).to(torch.int64), (nbox * nbox).to(torch.int64))
+    vals = torch.where(diff, obs["board"], torch.zeros_like(board)).flatten(1).max(1).values
+    assert bool(((nd == 0) | (vals.to(torch.int32) == piece + 2)).all())
+    # queue / holder images carry the ids of the state's queue and holder
+    qimg = obs["queue"].view(N, 4, Q, 4)
+    assert torch.equal(qimg.amax(dim=(1, 3)).to(torch.int32), st["queue"] + 2)
+    assert bool(((qimg != 0).sum(dim=(1, 3)) == 4).all())
+    hp = st["holder_piece"]
+    hmax = obs["holder"].flatten(1).max(1).values.to(torch.int32)
+    assert bool(torch.where(hp < 0, hmax == 1, hmax == hp + 2).all())
+    assert total_term > 0 and int(lines_acc.sum()) > 0
+    # determinism: the same run again gives the same bytes
+    keep_board, keep_obs = board.clone(), obs["board"].clone()
+    keep_x, keep_queue = st["x"].clone(), st["queue"].clone()
+    env.close()
+    del env, obs, st, board, field, diff
+    torch.cuda.empty_cache()
+    env2, obs2, _, total_term2 = _run(N, acts)
+    st2 = env2.get_state()
+    assert total_term2 == total_term
+    assert torch.equal(st2["board"], keep_board) and torch.equal(obs2["board"], keep_obs)
+    assert torch.equal(st2["x"], keep_x) and torch.equal(st2["queue"], keep_queue)
+    env2.close()
+    del env2, obs2, st2
+    torch.cuda.empty_cache()
+    # shard invariance: Philox streams are keyed by the global env id, so a 65,536-env run reproduces the first / a middle
+    # slice of the big batch (env_id_offset = global id of local env 0; per-env seeds = 42 + global id)
+    for off in (0, 3 * 65536 + 32):
+        from tetris_gymnasium_b200.envs.tetris import Tetris
+
+        m = 65536
+        env3 = Tetris(num_envs=m, queue_size=Q, autoreset_mode="next_step", env_id_offset=off)
+        env3.reset(seed=torch.arange(off, off + m, dtype=torch.int64) + 42)
+        for t in range(T):
+            o3, *_ = env3.step(acts[t, off:off + m].contiguous())
+        s3 = env3.get_state()
+        assert torch.equal(s3["board"], keep_board[off:off + m]) and torch.equal(o3["board"], keep_obs[off:off + m])
+        assert torch.equal(s3["queue"], keep_queue[off:off + m])
+        env3.close()
