@@ -92,3 +92,39 @@ def test_full_size_invariants_determinism_and_shard_invariance():
         assert torch.equal(s3["board"], keep_board[off:off + m]) and torch.equal(o3["board"], keep_obs[off:off + m])
         assert torch.equal(s3["queue"], keep_queue[off:off + m])
         env3.close()
+
+
+def test_full_size_grouped_feature_rows_are_self_consistent():
+    """1,048,576 envs x 40 placements (BASELINE config 3 at its largest size): every feature row must satisfy the identities
+    of wrappers/observation.py:238-278 -- max height = max of the heights, bumpiness = sum |h[c+1] - h[c]| (uint8 wrap) -- the
+    frame / game-over patterns of wrappers/grouped.py:160-170 must agree with the legal mask, and info["board"] must equal the
+    feature wrapper applied to the real observation (tg_features, an independent kernel)."""
+    from tetris_gymnasium_b200.envs.tetris import Tetris
+    from tetris_gymnasium_b200.wrappers import FeatureVectorObservation, GroupedActionsObservations
+
+    n, A, F = 1 << 20, 4 * W, W + 3
+    base = Tetris(num_envs=n, gravity=False, queue_size=4)
+    env = GroupedActionsObservations(base, observation_wrappers=[FeatureVectorObservation(base)])
+    feats, info = env.reset(seed=7)
+    g = torch.Generator(device="cuda")
+    g.manual_seed(7)
+    ref_feats = torch.empty((n, F), dtype=torch.uint8, device="cuda")
+    for t in range(24):
+        legal = info["action_mask"]
+        h = feats[:, :, :W].to(torch.int32)
+        assert torch.equal(feats[:, :, W].to(torch.int32), h.amax(dim=2)), t
+        bump = (h[:, :, 1:] - h[:, :, :-1]).abs().sum(dim=2) & 255
+        assert torch.equal(feats[:, :, W + 2].to(torch.int32), bump), t
+        assert int(h.max()) <= H
+        # illegal (frame) placements: ones board with row 0 zeroed -> heights and max H - 1, no holes, no bumpiness
+        ill = legal == 0
+        want = torch.tensor([H - 1] * (W + 1) + [0, 0], dtype=torch.uint8, device="cuda")
+        assert bool((feats[ill] == want).all()), t
+        assert bool(legal.any(dim=1).all())
+        # info["board"] vs the stand-alone feature kernel on the same state
+        from tetris_gymnasium_b200 import _lib
+        _lib.check(base._L.tg_features(base._h, base._state(), n, ref_feats.data_ptr(), base._stream()), base._h)
+        assert torch.equal(info["board"], ref_feats), t
+        a = torch.multinomial(legal.float() + 1e-9, 1, generator=g).squeeze(1).to(torch.int32)
+        feats, r, term, trunc, info = env.step(a)
+    base.close()
