@@ -128,3 +128,33 @@ def test_full_size_grouped_feature_rows_are_self_consistent():
         a = torch.multinomial(legal.float() + 1e-9, 1, generator=g).squeeze(1).to(torch.int32)
         feats, r, term, trunc, info = env.step(a)
     base.close()
+
+
+def test_full_size_wide_board_rgb_equals_palette_of_the_obs_dict():
+    """BASELINE config 5 (wide 20x40 board, queue 5, RGB image) at 262,144 envs: the image written by k_rgb must be the palette
+    lookup of the observation dict written by the step kernel for the same state -- Tetris.get_rgb (envs/tetris.py:309-343)
+    restated with torch ops: board | (queue, ones padding, holder) -> colours."""
+    from tetris_gymnasium_b200.envs.tetris import Tetris
+    from tetris_gymnasium_b200.wrappers import RgbObservation
+
+    n, Wd, Hd, Qd = 1 << 18, 20, 40, 5
+    base = Tetris(num_envs=n, width=Wd, height=Hd, queue_size=Qd)
+    env = RgbObservation(base, keep_obs_dict=True)
+    env.reset(seed=11)
+    colors = torch.tensor([[0, 0, 0], [128, 128, 128], [0, 240, 240], [240, 240, 0], [160, 0, 240], [0, 240, 0], [240, 0, 0],
+                           [0, 0, 240], [240, 160, 0]], dtype=torch.uint8, device="cuda")      # envs/tetris.py:45-75
+    g = torch.Generator(device="cuda")
+    g.manual_seed(11)
+    for t in range(12):
+        a = torch.randint(0, 8, (n,), dtype=torch.int32, device="cuda", generator=g)
+        if t % 3 == 2:
+            a.fill_(5)
+        img, *_ = env.step(a)
+        obs = base._obs()
+        Hp, max_len = Hd + 4, 4 * Qd
+        holder = torch.cat([obs["holder"], torch.ones((n, 4, max_len - 4), dtype=torch.uint8, device="cuda")], dim=2)
+        pad = torch.ones((n, Hp - 8, max_len), dtype=torch.uint8, device="cuda")
+        stack = torch.cat([obs["board"], torch.cat([obs["queue"], pad, holder], dim=1)], dim=2)
+        assert img.shape == (n, Hp, Wd + 8 + max_len, 3)
+        assert torch.equal(img, colors[stack.long()]), t
+    base.close()
