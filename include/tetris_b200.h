@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define TG_VERSION 1
+#define TG_VERSION 2
 #define TG_PADDING 4   /* = max tetromino matrix dim, envs/tetris.py:130 */
 #define TG_MAX_QUEUE 16
 #define TG_N_PIECES 7
@@ -156,15 +156,38 @@ int tg_reset(tg_env *env, tg_state st, int64_t n, const uint64_t *d_seeds, const
  * PCG64(SeedSequence(seed)) (Randomizer.reset, components/tetromino_randomizer.py:40-43). */
 int tg_seed_numpy(tg_env *env, tg_state st, int64_t n, const uint64_t *d_pcg, const uint8_t *d_mask, void *stream);
 
+/* Same seeding from the raw seeds: d_seeds = u64[n]; env i gets PCG64(SeedSequence(d_seeds[i])) -- numpy's SeedSequence hash
+ * and pcg_setseq_128_srandom_r run on the device (`np.random.default_rng(seed)`, components/tetromino_randomizer.py:40-43). */
+int tg_seed_numpy_seeds(tg_env *env, tg_state st, int64_t n, const uint64_t *d_seeds, const uint8_t *d_mask, void *stream);
+
 /* replaces Tetris.step (envs/tetris.py:203-272) for n envs, observation dict written every call
  * (pass an all-NULL tg_obs to skip the dict, e.g. when only tg_render_rgb / tg_features output is consumed).
  * d_stats may be NULL. */
 int tg_step(tg_env *env, tg_state st, int64_t n, const int32_t *d_actions, tg_obs obs, tg_step_out out,
             tg_stats *d_stats, void *stream);
 
-/* Same call with HOST buffers (pinned or pageable): copies actions H2D, steps, copies the
- * observation dict and the 5-tuple D2H, chunked over internal streams; synchronous. */
-int tg_step_host(tg_env *env, tg_state st, int64_t n, const int32_t *h_actions, tg_obs h_obs, tg_step_out h_out);
+/* Same call with HOST buffers (the reference's own calling convention: numpy arrays in, numpy arrays out --
+ * Tetris.step returns the dict of envs/tetris.py:566-615 in host memory).  Actions are copied H2D, the envs are stepped, the
+ * observation dict and the 5-tuple arrive in the caller's host arrays; synchronous.  `stream` is the stream the caller's
+ * earlier work on this state (tg_reset, tg_step, tg_set_state ...) was enqueued on: the internal copy streams wait for it.
+ *   TG_HOST_DMA     the dict is produced on the device and DMA-copied (2*Hp*Wp + 16 + 16Q bytes per env over the link);
+ *   TG_HOST_COMPACT the step runs without the dict; the packed records (hot 32 B + board record) cross the link, chunk by
+ *                   chunk, and a pool of host threads rebuilds the dict in the caller's arrays with streaming stores while
+ *                   later chunks are still stepping (format conversion only -- no game logic runs on the host).  Arrays
+ *                   aligned to 64 bytes take the fast path.  Both modes produce identical bytes. */
+enum { TG_HOST_DMA = 0, TG_HOST_COMPACT = 1 };
+int tg_step_host(tg_env *env, tg_state st, int64_t n, const int32_t *h_actions, tg_obs h_obs, tg_step_out h_out,
+                 int32_t mode, void *stream);
+/* host threads of the TG_HOST_COMPACT expansion; 0 = the cores this process may run on / LOCAL_WORLD_SIZE (TG_HOST_THREADS) */
+int tg_set_host_threads(tg_env *env, int32_t threads);
+/* timing of the last tg_step_host call: seconds total, waiting for the device, expanding; number of chunks */
+int tg_host_stats(tg_env *env, double *out4);
+/* The expansion alone, no device involved: packed records in HOST memory (hot u8[n][32], board u8[n][board_stride] as read
+ * back from tg_state) -> observation dict in host arrays. */
+int tg_host_expand(const tg_config *cfg, int64_t n, const void *h_hot, const void *h_board, tg_obs h_obs, int32_t threads);
+/* measurement aid: GB/s of `threads` host threads filling h_dst (64-byte aligned) with streaming stores, `reps` passes --
+ * the ceiling of the TG_HOST_COMPACT expansion's output traffic on this host */
+int tg_host_membw(void *h_dst, int64_t bytes, int32_t threads, int32_t reps, double *gb_per_s);
 
 /* ---- wrappers ---------------------------------------------------------------------------- */
 /* replaces FeatureVectorObservation.observation (wrappers/observation.py:238-278) applied to the

@@ -1,18 +1,36 @@
-"""Import the UNMODIFIED reference NumPy env in the build container (oracle tooling only).
+"""Import the UNMODIFIED reference NumPy env (oracle tooling and the bench's reference arm only).
 
-Puts oracle/gymnasium_shim (only when real gymnasium is absent) and /root/reference on
-sys.path.  /root/reference does not exist on the GPU box: `available()` is False there and
-everything that needs the live reference is skipped.
+Looks for the reference in /root/reference (the build container) and then in baseline/_ref (the pip --target install made
+by oracle/install_reference.py; git-ignored, travels to the GPU box with the snapshot).  oracle/gymnasium_shim goes on sys.path
+only when the real gymnasium is absent.  Where neither copy exists `available()` is False and everything that needs the live
+reference is skipped.
 """
 import os
 import sys
 
-REF = os.environ.get("TETRIS_REFERENCE", "/root/reference")
-SHIM = os.path.join(os.path.dirname(os.path.abspath(__file__)), "gymnasium_shim")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SHIM = os.path.join(_HERE, "gymnasium_shim")
+_CANDIDATES = [os.environ.get("TETRIS_REFERENCE", "/root/reference"), os.path.join(os.path.dirname(_HERE), "baseline", "_ref")]
+
+
+def _find():
+    for c in _CANDIDATES:
+        if c and os.path.isdir(os.path.join(c, "tetris_gymnasium")):
+            return c
+    return None
+
+
+REF = _find() or _CANDIDATES[0]
 
 
 def available():
-    return os.path.isdir(os.path.join(REF, "tetris_gymnasium"))
+    return _find() is not None
+
+
+def where():
+    """'source tree' (/root/reference) or 'baseline/_ref' (installed copy) -- recorded by the bench's reference arm."""
+    f = _find()
+    return None if f is None else ("baseline/_ref" if f.endswith(os.path.join("baseline", "_ref")) else f)
 
 
 def load():

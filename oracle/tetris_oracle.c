@@ -666,6 +666,35 @@ void orc_vec_grouped_step(orc_env **envs, int64_t n, const int32_t *actions, uin
     }
 }
 
+/* ---- bulk helpers of the bench's CPU arm: a million Python-side OracleEnv objects would take minutes to build -------- */
+void orc_vec_create(const orc_config *c, int64_t n, orc_env **out) {
+    for (int64_t i = 0; i < n; i++) out[i] = orc_create(c);
+}
+void orc_vec_destroy(orc_env **envs, int64_t n) {
+    for (int64_t i = 0; i < n; i++) orc_destroy(envs[i]);
+}
+/* words = SeedSequence(seed).generate_state(4, uint64) per env (oracle/np_seed.py, vectorised); this is
+ * pcg_setseq_128_srandom_r(state = w0:w1, seq = w2:w3) of numpy/random/src/pcg64/pcg64.h */
+void orc_vec_seed_words(orc_env **envs, int64_t n, const uint64_t *words) {
+    const unsigned __int128 MULT = ((unsigned __int128)0x2360ED051FC65DA4ULL << 64) | 0x4385DF649FCCF645ULL;
+    for (int64_t i = 0; i < n; i++) {
+        const uint64_t *w = words + 4 * i;
+        unsigned __int128 initstate = ((unsigned __int128)w[0] << 64) | w[1], initseq = ((unsigned __int128)w[2] << 64) | w[3];
+        unsigned __int128 inc = (initseq << 1) | 1, state = inc;
+        state += initstate;
+        state = state * MULT + inc;
+        uint64_t st[4] = {(uint64_t)(state >> 64), (uint64_t)state, (uint64_t)(inc >> 64), (uint64_t)inc};
+        orc_seed_numpy(envs[i], st);
+    }
+}
+void orc_vec_reset(orc_env **envs, int64_t n, int nthreads) {
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#pragma omp parallel for schedule(static)
+#endif
+    for (int64_t i = 0; i < n; i++) orc_reset(envs[i]);
+}
+
 /* randomizer.reset() followed by n draws (pins the numpy-exact 7-bag against numpy itself) */
 void orc_rnd_stream(orc_env *e, int n, uint8_t *out) {
     rnd_reset(e);

@@ -38,7 +38,8 @@ def lib():
             "orc_destroy orc_set_sequence orc_seed_numpy orc_get_obs orc_reset orc_features "
             "orc_grouped_observe orc_rgb orc_get_board orc_set_board orc_get_scalars "
             "orc_get_active_matrix orc_get_held_matrix orc_set_active orc_set_flags orc_set_holder "
-            "orc_set_queue orc_vec_step orc_vec_grouped_step orc_rnd_stream orc_grouped_observe_ex orc_set_true_randomizer"
+            "orc_set_queue orc_vec_step orc_vec_grouped_step orc_rnd_stream orc_grouped_observe_ex orc_set_true_randomizer "
+            "orc_vec_create orc_vec_destroy orc_vec_seed_words orc_vec_reset"
         ).split():
             getattr(L, name).restype = None
         L.orc_step.restype = C.c_int
@@ -221,13 +222,43 @@ class OracleEnv:
 
 
 class OracleVec:
-    """n independent oracle envs stepped with gymnasium's NEXT_STEP autoreset (bench baseline)."""
+    """n independent oracle envs stepped with gymnasium's NEXT_STEP autoreset (bench baseline).
+    bulk=True builds the envs inside the C library (no per-env Python object: `envs` is empty) -- a million envs in about a
+    second instead of minutes; seed them with `seed_all` and reset with `reset_all`."""
 
-    def __init__(self, n, **kw):
-        self.envs = [OracleEnv(**kw) for _ in range(n)]
+    def __init__(self, n, bulk=False, **kw):
         self.n = n
-        self.ptrs = (C.c_void_p * n)(*[e.h for e in self.envs])
-        e = self.envs[0]
+        self._bulk = bulk
+        if bulk:
+            e = OracleEnv(**kw)
+            self._proto = e
+            self.envs = []
+            self.ptrs = (C.c_void_p * n)()
+            lib().orc_vec_create(C.byref(e.cfg), C.c_int64(n), self.ptrs)
+        else:
+            self.envs = [OracleEnv(**kw) for _ in range(n)]
+            self.ptrs = (C.c_void_p * n)(*[e.h for e in self.envs])
+            e = self.envs[0]
+        self._init_buffers(n, e)
+
+    def __del__(self):
+        try:
+            if self._bulk:
+                lib().orc_vec_destroy(self.ptrs, C.c_int64(self.n))
+        except Exception:
+            pass
+
+    def seed_all(self, seeds):
+        """numpy-exact 7-bag streams: env i gets PCG64(SeedSequence(seeds[i])) (vectorised seeding, oracle/np_seed.py)."""
+        from .np_seed import seed_words
+        w = np.ascontiguousarray(seed_words(np.asarray(seeds, dtype=np.uint64)))
+        lib().orc_vec_seed_words(self.ptrs, C.c_int64(self.n), _p(w))
+
+    def reset_all(self, nthreads=0):
+        lib().orc_vec_reset(self.ptrs, C.c_int64(self.n), int(nthreads))
+        self.autoreset[:] = 0
+
+    def _init_buffers(self, n, e):
         self.autoreset = np.zeros(n, np.uint8)
         self.board = np.empty((n, e.Hp, e.Wp), np.uint8)
         self.mask = np.empty((n, e.Hp, e.Wp), np.uint8)

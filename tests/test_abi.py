@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(L, n), f"{n} declared in include/tetris_b200.h but not exported"
     assert set(names) == set(_lib.EXPORTS)
-    assert L.tg_version() == 1
+    assert L.tg_version() == 2
 
 
 def test_struct_layouts_match_header():

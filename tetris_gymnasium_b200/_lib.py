@@ -14,6 +14,8 @@ AUTORESET = {"disabled": 0, "next_step": 1, "same_step": 2}
 RNG = {"philox": 0, "sequence": 1, "numpy": 2}
 RANDOMIZER = {"bag": 0, "true": 1}
 TG_SCALARS = 8
+HOST_MODE = {"dma": 0, "compact": 1}
+TG_VERSION = 2
 
 
 class TgConfig(C.Structure):
@@ -48,7 +50,8 @@ class TgStepOut(C.Structure):
 
 EXPORTS = (
     "tg_create tg_destroy tg_get_layout tg_last_error tg_version tg_reset tg_seed_numpy tg_step tg_step_host "
-    "tg_features tg_render_rgb tg_grouped_observe tg_grouped_step tg_rollout tg_get_state tg_set_state tg_debug_set_rollout_trace tg_fn_step tg_cnn_observe"
+    "tg_features tg_render_rgb tg_grouped_observe tg_grouped_step tg_rollout tg_get_state tg_set_state tg_debug_set_rollout_trace tg_fn_step tg_cnn_observe "
+    "tg_set_host_threads tg_host_stats tg_host_expand tg_seed_numpy_seeds tg_host_membw"
 ).split()
 
 _LIB = None
@@ -80,8 +83,13 @@ def load():
     L.tg_get_layout.argtypes = [vp, C.POINTER(TgLayout)]
     L.tg_reset.argtypes = [vp, TgState, i64, vp, vp, TgObs, vp]
     L.tg_seed_numpy.argtypes = [vp, TgState, i64, vp, vp, vp]
+    L.tg_seed_numpy_seeds.argtypes = [vp, TgState, i64, vp, vp, vp]
     L.tg_step.argtypes = [vp, TgState, i64, vp, TgObs, TgStepOut, vp, vp]
-    L.tg_step_host.argtypes = [vp, TgState, i64, vp, TgObs, TgStepOut]
+    L.tg_step_host.argtypes = [vp, TgState, i64, vp, TgObs, TgStepOut, C.c_int32, vp]
+    L.tg_set_host_threads.argtypes = [vp, C.c_int32]
+    L.tg_host_stats.argtypes = [vp, C.POINTER(C.c_double)]
+    L.tg_host_membw.argtypes = [vp, i64, C.c_int32, C.c_int32, C.POINTER(C.c_double)]
+    L.tg_host_expand.argtypes = [C.POINTER(TgConfig), i64, vp, vp, TgObs, C.c_int32]
     L.tg_features.argtypes = [vp, TgState, i64, vp, vp]
     L.tg_render_rgb.argtypes = [vp, TgState, i64, vp, vp]
     L.tg_cnn_observe.argtypes = [vp, TgState, i64, C.c_int32, C.c_int32, vp, i64, vp, C.c_int32, vp]

@@ -4,6 +4,7 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
+#include <time.h>
 
 #include <string>
 #include <vector>
@@ -15,8 +16,18 @@
 #include "tg_gfeats.cuh"
 #include "tg_rollout.cuh"
 #include "tg_fn.cuh"
+#include "tg_host_expand.h"
 
 using namespace tg;
+
+// piece tables on the host: uploaded to the device by upload_tables, read by the host-side dict expansion
+struct HostTables {
+    unsigned short cells[7][4];
+    uint2 ptab[7][4];
+    uint4 prec[7][4];
+    unsigned int rowbytes[7][4][4];
+    unsigned char colors[16][4];
+};
 
 struct tg_env {
     tg_config cfg;
@@ -39,6 +50,17 @@ struct tg_env {
     bool hs_init;
     void* stage[16];
     size_t stage_bytes[16];
+    // compact host step: pinned ring of packed records, events, expansion pool
+    HostTables tabs;
+    tgh::ExpandCfg xcfg;
+    tgh::Pool* pool;
+    int host_threads;          // 0 = tgh::default_threads()
+    void* hring;               // pinned host memory
+    size_t hring_bytes;
+    cudaEvent_t hev[64];
+    bool hev_init;
+    cudaEvent_t caller_ev;
+    double host_stats[4];      // last tg_step_host call: seconds total, waiting for the device, expanding; chunks
 };
 
 static std::string g_create_err;
@@ -67,12 +89,8 @@ static const unsigned char kBase[7][16] = {
 static const unsigned char kColors[9][3] = {{0, 0, 0}, {128, 128, 128}, {0, 240, 240}, {240, 240, 0}, {160, 0, 240},
                                             {0, 240, 0}, {240, 0, 0}, {0, 0, 240}, {240, 160, 0}};
 
-static int upload_tables(tg_env* env) {
-    unsigned short cells[7][4];
-    uint2 ptab[7][4];
-    uint4 prec[7][4];
-    unsigned int rowbytes[7][4][4];
-    unsigned char colors[16][4];
+static int build_tables(tg_env* env, HostTables& T) {
+    auto& cells = T.cells; auto& ptab = T.ptab; auto& prec = T.prec; auto& rowbytes = T.rowbytes; auto& colors = T.colors;
     memset(colors, 0, sizeof colors);
     for (int v = 0; v < 9; v++) for (int k = 0; k < 3; k++) colors[v][k] = kColors[v][k];
     for (int p = 0; p < 7; p++) {
@@ -123,13 +141,36 @@ static int upload_tables(tg_env* env) {
             prec[p][r] = make_uint4((unsigned)c | ((px & 0xFFFFu) << 16), m4, top4, (unsigned)jmin | (unsigned)jmax << 2 | mintop << 4);
         }
     }
-    CUDA_TRY(env, cudaMemcpyToSymbol(c_cells, cells, sizeof cells));
-    CUDA_TRY(env, cudaMemcpyToSymbol(c_ptab, ptab, sizeof ptab));
-    CUDA_TRY(env, cudaMemcpyToSymbol(c_prec, prec, sizeof prec));
-    CUDA_TRY(env, cudaMemcpyToSymbol(c_rowbytes, rowbytes, sizeof rowbytes));
-    CUDA_TRY(env, cudaMemcpyToSymbol(c_n, kN, sizeof kN));
-    CUDA_TRY(env, cudaMemcpyToSymbol(c_colors, colors, sizeof colors));
     return TG_OK;
+}
+
+static int upload_tables(tg_env* env) {
+    HostTables& T = env->tabs;
+    int rc = build_tables(env, T);
+    if (rc) return rc;
+    CUDA_TRY(env, cudaMemcpyToSymbol(c_cells, T.cells, sizeof T.cells));
+    CUDA_TRY(env, cudaMemcpyToSymbol(c_ptab, T.ptab, sizeof T.ptab));
+    CUDA_TRY(env, cudaMemcpyToSymbol(c_prec, T.prec, sizeof T.prec));
+    CUDA_TRY(env, cudaMemcpyToSymbol(c_rowbytes, T.rowbytes, sizeof T.rowbytes));
+    CUDA_TRY(env, cudaMemcpyToSymbol(c_n, kN, sizeof kN));
+    CUDA_TRY(env, cudaMemcpyToSymbol(c_colors, T.colors, sizeof T.colors));
+    return TG_OK;
+}
+
+// ExpandCfg of the host-side dict expansion from the device config + the piece tables
+static void make_expand_cfg(const DevCfg& d, const HostTables& T, tgh::ExpandCfg& x) {
+    memset(&x, 0, sizeof x);
+    x.W = d.W; x.H = d.H; x.Wp = d.Wp; x.Hp = d.Hp; x.Q = d.Q; x.OB = d.OB; x.OQ = d.OQ;
+    x.board_stride = d.board_stride; x.ids_off = d.ids_off; x.ids_bytes = (d.H * d.W + 1) / 2;
+    for (int p = 0; p < 7; p++) {
+        x.n[p] = kN[p];
+        for (int r = 0; r < 4; r++) {
+            x.cells[p][r] = T.cells[p][r];
+            for (int i = 0; i < 4; i++) x.rowbytes[p][r][i] = T.rowbytes[p][r][i];
+        }
+    }
+    x.n[7] = 3;
+    tgh::build_vector_tables(x);
 }
 
 static int round_up(int v, int m) { return (v + m - 1) / m * m; }
@@ -138,9 +179,7 @@ extern "C" int tg_version(void) { return TG_VERSION; }
 
 extern "C" const char* tg_last_error(const tg_env* env) { return env ? env->err.c_str() : g_create_err.c_str(); }
 
-extern "C" int tg_create(const tg_config* cfg, int device, tg_env** out) {
-    if (!cfg || !out) return fail(nullptr, TG_ERR_POINTER, "tg_create: NULL argument");
-    *out = nullptr;
+static int validate_cfg(const tg_config* cfg) {
     if (cfg->width < 4 || cfg->width + 2 * TG_PADDING > 32)
         return fail(nullptr, TG_ERR_CONFIG, "width %d unsupported (4 <= W <= 24: a padded row must fit 32 bits)", cfg->width);
     if (cfg->height < 4 || cfg->height + TG_PADDING > 64)
@@ -154,33 +193,17 @@ extern "C" int tg_create(const tg_config* cfg, int device, tg_env** out) {
     for (int i = 0; i < 8; i++)
         if (cfg->action_map[i] < 0 || cfg->action_map[i] >= 8)
             return fail(nullptr, TG_ERR_CONFIG, "action_map[%d] = %d outside Discrete(8)", i, cfg->action_map[i]);
-    int ndev = 0;
-    cudaError_t ce = cudaGetDeviceCount(&ndev);
-    if (ce != cudaSuccess || ndev == 0)
-        return fail(nullptr, TG_ERR_CUDA, "no CUDA device (%s); this library has no CPU fallback", cudaGetErrorString(ce));
-    if (device < 0 || device >= ndev) return fail(nullptr, TG_ERR_ARG, "device %d of %d", device, ndev);
-    tg_env* env = new tg_env();
-    env->cfg = *cfg;
-    env->device = device;
-    env->hs_init = false;
-    env->rollout_last_action = nullptr;
-    env->cnn_h = env->cnn_w = 0;
-    memset(env->stage, 0, sizeof env->stage);
-    memset(env->stage_bytes, 0, sizeof env->stage_bytes);
-    cudaError_t e1 = cudaSetDevice(device);
-    if (e1 != cudaSuccess) { int rc = fail(nullptr, TG_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e1)); delete env; return rc; }
-    cudaDeviceProp prop;
-    cudaGetDeviceProperties(&prop, device);
-    env->num_sms = prop.multiProcessorCount;
+    return TG_OK;
+}
 
-    DevCfg& d = env->dev;
+// device config (sizes, strides, LUTs) of a validated tg_config; pure host arithmetic
+static void derive_cfg(const tg_config* cfg, DevCfg& d) {
     memset(&d, 0, sizeof d);
     d.W = cfg->width; d.H = cfg->height; d.Wp = d.W + 2 * TG_PADDING; d.Hp = d.H + TG_PADDING; d.Q = cfg->queue_size;
     d.gravity = cfg->gravity != 0; d.autoreset = cfg->autoreset; d.rng_mode = cfg->rng_mode;
     d.terminate_on_illegal = cfg->terminate_on_illegal != 0;
     d.rand_kind = cfg->randomizer;
-    env->col64 = d.Hp > 32;
-    int col_bytes = env->col64 ? 8 : 4;
+    const int col_bytes = d.Hp > 32 ? 8 : 4;
     d.ids_off = d.W * col_bytes;
     d.ids_words = (d.H * d.W + 7) / 8;
     int bs = round_up(d.ids_off + d.ids_words * 4, 16);
@@ -202,6 +225,37 @@ extern "C" int tg_create(const tg_config* cfg, int device, tg_env** out) {
     d.act_hard = cfg->action_map[5]; d.act_noop = cfg->action_map[7];
     d.r_alife = cfg->reward_alife; d.r_go = cfg->reward_game_over; d.r_invalid = cfg->reward_invalid_action;
     d.seq_len = cfg->seq_len; d.env_id_offset = cfg->env_id_offset;
+}
+
+extern "C" int tg_create(const tg_config* cfg, int device, tg_env** out) {
+    if (!cfg || !out) return fail(nullptr, TG_ERR_POINTER, "tg_create: NULL argument");
+    *out = nullptr;
+    int vrc = validate_cfg(cfg);
+    if (vrc) return vrc;
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0)
+        return fail(nullptr, TG_ERR_CUDA, "no CUDA device (%s); this library has no CPU fallback", cudaGetErrorString(ce));
+    if (device < 0 || device >= ndev) return fail(nullptr, TG_ERR_ARG, "device %d of %d", device, ndev);
+    tg_env* env = new tg_env();
+    env->cfg = *cfg;
+    env->device = device;
+    env->hs_init = false;
+    env->rollout_last_action = nullptr;
+    env->cnn_h = env->cnn_w = 0;
+    env->pool = nullptr; env->host_threads = 0; env->hring = nullptr; env->hring_bytes = 0; env->hev_init = false;
+    memset(env->host_stats, 0, sizeof env->host_stats);
+    memset(env->stage, 0, sizeof env->stage);
+    memset(env->stage_bytes, 0, sizeof env->stage_bytes);
+    cudaError_t e1 = cudaSetDevice(device);
+    if (e1 != cudaSuccess) { int rc = fail(nullptr, TG_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e1)); delete env; return rc; }
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    env->num_sms = prop.multiProcessorCount;
+
+    DevCfg& d = env->dev;
+    derive_cfg(cfg, d);
+    env->col64 = d.Hp > 32;
 
     tg_layout& L = env->layout;
     memset(&L, 0, sizeof L);
@@ -223,6 +277,7 @@ extern "C" int tg_create(const tg_config* cfg, int device, tg_env** out) {
     if (env->logic_warps + env->fill_warps > 8) env->fill_warps = 8 - env->logic_warps;
     int rc = upload_tables(env);
     if (rc != TG_OK) { g_create_err = env->err; delete env; return rc; }
+    make_expand_cfg(env->dev, env->tabs, env->xcfg);
     *out = env;
     return TG_OK;
 }
@@ -231,6 +286,9 @@ extern "C" int tg_destroy(tg_env* env) {
     if (!env) return TG_OK;
     cudaSetDevice(env->device);
     if (env->hs_init) for (int i = 0; i < 3; i++) cudaStreamDestroy(env->hs[i]);
+    if (env->hev_init) { for (int i = 0; i < 64; i++) cudaEventDestroy(env->hev[i]); cudaEventDestroy(env->caller_ev); }
+    if (env->hring) cudaFreeHost(env->hring);
+    delete env->pool;
     for (int i = 0; i < 16; i++) if (env->stage[i]) cudaFree(env->stage[i]);
     delete env;
     return TG_OK;
@@ -390,72 +448,238 @@ static int ensure_stage(tg_env* env, int slot, size_t bytes) {
     return TG_OK;
 }
 
-extern "C" int tg_step_host(tg_env* env, tg_state st, int64_t n, const int32_t* h_actions, tg_obs h_obs, tg_step_out h_out) {
+// make the internal copy streams wait for the work the caller enqueued on `stream` before this call (reset / step / set_state)
+static int host_streams_begin(tg_env* env, cudaStream_t caller) {
+    if (!env->hs_init) {
+        for (int i = 0; i < 3; i++) CUDA_TRY(env, cudaStreamCreateWithFlags(&env->hs[i], cudaStreamNonBlocking));
+        env->hs_init = true;
+    }
+    if (!env->hev_init) {
+        for (int i = 0; i < 64; i++) CUDA_TRY(env, cudaEventCreateWithFlags(&env->hev[i], cudaEventDisableTiming));
+        CUDA_TRY(env, cudaEventCreateWithFlags(&env->caller_ev, cudaEventDisableTiming));
+        env->hev_init = true;
+    }
+    CUDA_TRY(env, cudaEventRecord(env->caller_ev, caller));
+    for (int i = 0; i < 3; i++) CUDA_TRY(env, cudaStreamWaitEvent(env->hs[i], env->caller_ev, 0));
+    return TG_OK;
+}
+
+static double wall_now() {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+
+// one chunk [b, b + m) of the env range on stream s: actions H2D, step kernel (obs = all-NULL -> no dict), scalars D2H
+static int host_chunk_step(tg_env* env, const tg_state& st, int64_t b, int64_t m, const int32_t* h_actions, int32_t* s_act,
+                           const tg_obs& d_obs, float* s_rew, int32_t* s_lines, uint8_t* s_term, uint8_t* s_trunc, cudaStream_t s) {
+    const DevCfg& d = env->dev;
+    CUDA_TRY(env, cudaMemcpyAsync(s_act + b, h_actions + b, (size_t)m * 4, cudaMemcpyHostToDevice, s));
+    StepParams p;
+    memset(&p, 0, sizeof p);
+    p.n = m;
+    p.hot = (uint8_t*)st.hot + b * 32; p.board = (uint8_t*)st.board + b * d.board_stride; p.rng = (uint8_t*)st.rng + b * d.rng_stride;
+    p.seq = st.piece_seq ? st.piece_seq + b * d.seq_len : nullptr;
+    p.actions = s_act + b;
+    if (d_obs.board) { p.o_board = d_obs.board + b * d.OB; p.o_mask = d_obs.mask + b * d.OB; p.o_holder = d_obs.holder + b * 16; p.o_queue = d_obs.queue + b * d.OQ; }
+    p.reward = s_rew + b; p.terminated = s_term + b; p.truncated = s_trunc + b; p.lines = s_lines + b;
+    p.mode = 0;
+    DevCfg saved = env->dev;
+    env->dev.env_id_offset += (unsigned long long)b;
+    int rc = launch_step(env, p, s);
+    env->dev = saved;
+    return rc;
+}
+
+struct ExpandJob {
+    const tgh::ExpandCfg* cfg;
+    tgh::ExpandArgs args;     // pointers biased so that env index = global env index
+    int64_t base, count, per; // items cover [base + i * per, base + min((i + 1) * per, count))
+};
+static void expand_item(void* ctx, int64_t i) {
+    const ExpandJob& j = *(const ExpandJob*)ctx;
+    const int64_t e0 = j.base + i * j.per, e1 = j.base + (((i + 1) * j.per < j.count) ? (i + 1) * j.per : j.count);
+    tgh::expand_range(*j.cfg, j.args, e0, e1);
+}
+static void run_expand(tgh::Pool& pool, const tgh::ExpandCfg& cfg, const tgh::ExpandArgs& args, int64_t base, int64_t count) {
+    ExpandJob j;
+    j.cfg = &cfg; j.args = args; j.base = base; j.count = count;
+    int64_t items = (int64_t)pool.size() * 2;
+    int64_t per = (count + items - 1) / items;
+    per = (per + 127) / 128 * 128;      // whole cache lines in every output array
+    if (per < 128) per = 128;
+    j.per = per;
+    pool.run((count + per - 1) / per, expand_item, &j);
+}
+
+extern "C" int tg_set_host_threads(tg_env* env, int32_t threads) {
+    if (!env) return TG_ERR_POINTER;
+    if (threads < 0 || threads > 1024) return fail(env, TG_ERR_ARG, "host threads %d", threads);
+    if (env->pool && env->pool->size() != (threads ? threads : tgh::default_threads())) { delete env->pool; env->pool = nullptr; }
+    env->host_threads = threads;
+    return TG_OK;
+}
+
+extern "C" int tg_host_stats(tg_env* env, double* out4) {
+    if (!env || !out4) return TG_ERR_POINTER;
+    for (int i = 0; i < 4; i++) out4[i] = env->host_stats[i];
+    return TG_OK;
+}
+
+extern "C" int tg_step_host(tg_env* env, tg_state st, int64_t n, const int32_t* h_actions, tg_obs h_obs, tg_step_out h_out,
+                            int32_t mode, void* stream) {
     if (!env) return TG_ERR_POINTER;
     if (n <= 0) return fail(env, TG_ERR_ARG, "n must be positive");
+    if (mode != TG_HOST_DMA && mode != TG_HOST_COMPACT) return fail(env, TG_ERR_ARG, "tg_step_host: mode %d", mode);
     if (!h_actions || !h_obs.board || !h_obs.mask || !h_obs.holder || !h_obs.queue || !h_out.reward || !h_out.terminated ||
         !h_out.truncated || !h_out.lines)
         return fail(env, TG_ERR_POINTER, "host buffer is NULL");
     int rc = check_state(env, st); if (rc) return rc;
     CUDA_TRY(env, cudaSetDevice(env->device));
-    if (!env->hs_init) {
-        for (int i = 0; i < 3; i++) CUDA_TRY(env, cudaStreamCreateWithFlags(&env->hs[i], cudaStreamNonBlocking));
-        env->hs_init = true;
-    }
+    const double t_begin = wall_now();
+    rc = host_streams_begin(env, (cudaStream_t)stream); if (rc) return rc;
     const DevCfg& d = env->dev;
-    // chunk the env range so that the D2H of chunk k overlaps the kernel of chunk k+1
-    int NCH = 3;
-    if (const char* t = getenv("TG_HOST_CHUNKS")) { int v = atoi(t); if (v >= 1 && v <= 64) NCH = v; }
-    int64_t chunk = (n + NCH - 1) / NCH;
-    chunk = (chunk + 127) / 128 * 128;  // keeps every chunk's base 16-byte aligned in all arrays
     auto r16 = [](size_t v) { return (v + 15) / 16 * 16; };
-    const size_t o_mask = r16((size_t)n * d.OB), o_holder = o_mask + r16((size_t)n * d.OB), o_queue = o_holder + (size_t)n * 16;
-    const size_t obs_total = o_queue + (size_t)n * d.OQ;
     const size_t o_lines = r16((size_t)n * 4), o_term = o_lines + r16((size_t)n * 4), o_trunc = o_term + r16((size_t)n);
     const size_t out_total = o_trunc + r16((size_t)n);
     rc = ensure_stage(env, 0, (size_t)n * 4); if (rc) return rc;   // actions
-    rc = ensure_stage(env, 1, obs_total); if (rc) return rc;       // observation dict
     rc = ensure_stage(env, 2, out_total); if (rc) return rc;       // reward, lines, terminated, truncated
-    uint8_t* s_board = (uint8_t*)env->stage[1];
-    uint8_t* s_mask = s_board + o_mask;
-    uint8_t* s_holder = s_board + o_holder;
-    uint8_t* s_queue = s_board + o_queue;
     uint8_t* so = (uint8_t*)env->stage[2];
     float* s_rew = (float*)so;
     int32_t* s_lines = (int32_t*)(so + o_lines);
     uint8_t* s_term = so + o_term;
     uint8_t* s_trunc = so + o_trunc;
     int32_t* s_act = (int32_t*)env->stage[0];
-    int k = 0;
-    for (int64_t b = 0; b < n; b += chunk, k++) {
-        int64_t m = n - b < chunk ? n - b : chunk;
-        cudaStream_t s = env->hs[k % 3];
-        CUDA_TRY(env, cudaMemcpyAsync(s_act + b, h_actions + b, (size_t)m * 4, cudaMemcpyHostToDevice, s));
-        tg_state sc = st;
-        sc.hot = (uint8_t*)st.hot + b * 32; sc.board = (uint8_t*)st.board + b * d.board_stride; sc.rng = (uint8_t*)st.rng + b * d.rng_stride;
-        if (st.piece_seq) sc.piece_seq = st.piece_seq + b * d.seq_len;
-        StepParams p;
-        memset(&p, 0, sizeof p);
-        p.n = m; p.hot = (uint8_t*)sc.hot; p.board = (uint8_t*)sc.board; p.rng = (uint8_t*)sc.rng; p.seq = sc.piece_seq;
-        p.actions = s_act + b;
-        p.o_board = s_board + b * d.OB; p.o_mask = s_mask + b * d.OB; p.o_holder = s_holder + b * 16; p.o_queue = s_queue + b * d.OQ;
-        p.reward = s_rew + b; p.terminated = s_term + b; p.truncated = s_trunc + b; p.lines = s_lines + b;
-        p.mode = 0;
-        DevCfg saved = env->dev;
-        env->dev.env_id_offset += (unsigned long long)b;
-        rc = launch_step(env, p, s);
-        env->dev = saved;
-        if (rc) return rc;
-        CUDA_TRY(env, cudaMemcpyAsync(h_obs.board + b * d.OB, p.o_board, (size_t)m * d.OB, cudaMemcpyDeviceToHost, s));
-        CUDA_TRY(env, cudaMemcpyAsync(h_obs.mask + b * d.OB, p.o_mask, (size_t)m * d.OB, cudaMemcpyDeviceToHost, s));
-        CUDA_TRY(env, cudaMemcpyAsync(h_obs.holder + b * 16, p.o_holder, (size_t)m * 16, cudaMemcpyDeviceToHost, s));
-        CUDA_TRY(env, cudaMemcpyAsync(h_obs.queue + b * d.OQ, p.o_queue, (size_t)m * d.OQ, cudaMemcpyDeviceToHost, s));
-        CUDA_TRY(env, cudaMemcpyAsync(h_out.reward + b, p.reward, (size_t)m * 4, cudaMemcpyDeviceToHost, s));
-        CUDA_TRY(env, cudaMemcpyAsync(h_out.lines + b, p.lines, (size_t)m * 4, cudaMemcpyDeviceToHost, s));
-        CUDA_TRY(env, cudaMemcpyAsync(h_out.terminated + b, p.terminated, (size_t)m, cudaMemcpyDeviceToHost, s));
-        CUDA_TRY(env, cudaMemcpyAsync(h_out.truncated + b, p.truncated, (size_t)m, cudaMemcpyDeviceToHost, s));
+
+    if (mode == TG_HOST_DMA) {
+        // the whole dict is produced on the device and copied: chunk the env range so that the D2H of chunk k overlaps the
+        // kernel of chunk k+1
+        int NCH = 3;
+        if (const char* t = getenv("TG_HOST_CHUNKS")) { int v = atoi(t); if (v >= 1 && v <= 64) NCH = v; }
+        int64_t chunk = (n + NCH - 1) / NCH;
+        chunk = (chunk + 127) / 128 * 128;  // keeps every chunk's base 16-byte aligned in all arrays
+        const size_t o_mask = r16((size_t)n * d.OB), o_holder = o_mask + r16((size_t)n * d.OB), o_queue = o_holder + (size_t)n * 16;
+        const size_t obs_total = o_queue + (size_t)n * d.OQ;
+        rc = ensure_stage(env, 1, obs_total); if (rc) return rc;       // observation dict
+        tg_obs d_obs;
+        d_obs.board = (uint8_t*)env->stage[1]; d_obs.mask = d_obs.board + o_mask; d_obs.holder = d_obs.board + o_holder; d_obs.queue = d_obs.board + o_queue;
+        int k = 0;
+        for (int64_t b = 0; b < n; b += chunk, k++) {
+            int64_t m = n - b < chunk ? n - b : chunk;
+            cudaStream_t s = env->hs[k % 3];
+            rc = host_chunk_step(env, st, b, m, h_actions, s_act, d_obs, s_rew, s_lines, s_term, s_trunc, s); if (rc) return rc;
+            CUDA_TRY(env, cudaMemcpyAsync(h_obs.board + b * d.OB, d_obs.board + b * d.OB, (size_t)m * d.OB, cudaMemcpyDeviceToHost, s));
+            CUDA_TRY(env, cudaMemcpyAsync(h_obs.mask + b * d.OB, d_obs.mask + b * d.OB, (size_t)m * d.OB, cudaMemcpyDeviceToHost, s));
+            CUDA_TRY(env, cudaMemcpyAsync(h_obs.holder + b * 16, d_obs.holder + b * 16, (size_t)m * 16, cudaMemcpyDeviceToHost, s));
+            CUDA_TRY(env, cudaMemcpyAsync(h_obs.queue + b * d.OQ, d_obs.queue + b * d.OQ, (size_t)m * d.OQ, cudaMemcpyDeviceToHost, s));
+            CUDA_TRY(env, cudaMemcpyAsync(h_out.reward + b, s_rew + b, (size_t)m * 4, cudaMemcpyDeviceToHost, s));
+            CUDA_TRY(env, cudaMemcpyAsync(h_out.lines + b, s_lines + b, (size_t)m * 4, cudaMemcpyDeviceToHost, s));
+            CUDA_TRY(env, cudaMemcpyAsync(h_out.terminated + b, s_term + b, (size_t)m, cudaMemcpyDeviceToHost, s));
+            CUDA_TRY(env, cudaMemcpyAsync(h_out.truncated + b, s_trunc + b, (size_t)m, cudaMemcpyDeviceToHost, s));
+        }
+        const double t_w = wall_now();
+        for (int i = 0; i < 3; i++) CUDA_TRY(env, cudaStreamSynchronize(env->hs[i]));
+        const double t_end = wall_now();
+        env->host_stats[0] = t_end - t_begin; env->host_stats[1] = t_end - t_w; env->host_stats[2] = 0; env->host_stats[3] = k;
+        return TG_OK;
+    }
+
+    // ---- compact: the step runs WITHOUT the observation dict; the packed records (hot + board) cross the link and the dict is
+    // rebuilt in the caller's arrays by the host pool while later chunks are still stepping / copying -------------------------
+    if (!env->pool) env->pool = new tgh::Pool(env->host_threads ? env->host_threads : tgh::default_threads());
+    int64_t chunk = 131072;
+    if (const char* t = getenv("TG_HOST_CHUNK")) { long v = atol(t); if (v >= 128) chunk = v; }
+    chunk = (chunk + 127) / 128 * 128;
+    if (chunk > n) chunk = (n + 127) / 128 * 128;
+    const int64_t NCH = (n + chunk - 1) / chunk;
+    int NB = 4;                                   // ring slots of packed records in pinned host memory
+    if (const char* t = getenv("TG_HOST_RING")) { int v = atoi(t); if (v >= 2 && v <= 32) NB = v; }
+    if (NB > NCH) NB = (int)NCH;
+    const size_t slot_hot = ((size_t)chunk * 32 + 63) / 64 * 64, slot_brd = ((size_t)chunk * d.board_stride + 64 + 63) / 64 * 64;
+    const size_t slot = slot_hot + slot_brd;
+    if (env->hring_bytes < slot * NB) {
+        if (env->hring) cudaFreeHost(env->hring);
+        env->hring = nullptr; env->hring_bytes = 0;
+        CUDA_TRY(env, cudaHostAlloc(&env->hring, slot * NB, cudaHostAllocDefault));
+        env->hring_bytes = slot * NB;
+    }
+    memset(h_out.truncated, 0, (size_t)n);        // always False (envs/tetris.py:219)
+    tg_obs no_obs;
+    memset(&no_obs, 0, sizeof no_obs);
+    double t_wait = 0, t_exp = 0;
+    int64_t next_enq = 0;
+    for (int64_t c = 0; c < NCH; c++) {
+        for (; next_enq < NCH && next_enq < c + NB; next_enq++) {
+            const int64_t b = next_enq * chunk, m = n - b < chunk ? n - b : chunk;
+            cudaStream_t s = env->hs[next_enq % 3];
+            uint8_t* ring = (uint8_t*)env->hring + (size_t)(next_enq % NB) * slot;
+            rc = host_chunk_step(env, st, b, m, h_actions, s_act, no_obs, s_rew, s_lines, s_term, s_trunc, s); if (rc) return rc;
+            CUDA_TRY(env, cudaMemcpyAsync(ring, (uint8_t*)st.hot + b * 32, (size_t)m * 32, cudaMemcpyDeviceToHost, s));
+            CUDA_TRY(env, cudaMemcpyAsync(ring + slot_hot, (uint8_t*)st.board + b * d.board_stride, (size_t)m * d.board_stride, cudaMemcpyDeviceToHost, s));
+            CUDA_TRY(env, cudaMemcpyAsync(h_out.reward + b, s_rew + b, (size_t)m * 4, cudaMemcpyDeviceToHost, s));
+            CUDA_TRY(env, cudaMemcpyAsync(h_out.lines + b, s_lines + b, (size_t)m * 4, cudaMemcpyDeviceToHost, s));
+            CUDA_TRY(env, cudaMemcpyAsync(h_out.terminated + b, s_term + b, (size_t)m, cudaMemcpyDeviceToHost, s));
+            CUDA_TRY(env, cudaEventRecord(env->hev[next_enq % NB], s));
+        }
+        const double t0 = wall_now();
+        CUDA_TRY(env, cudaEventSynchronize(env->hev[c % NB]));
+        const double t1 = wall_now();
+        const int64_t b = c * chunk, m = n - b < chunk ? n - b : chunk;
+        const uint8_t* ring = (const uint8_t*)env->hring + (size_t)(c % NB) * slot;
+        tgh::ExpandArgs xa;
+        xa.hot = ring - b * 32; xa.board = ring + slot_hot - b * d.board_stride;   // biased: indexed by the global env id
+        xa.board_end = ring + slot;
+        xa.o_board = h_obs.board; xa.o_mask = h_obs.mask; xa.o_holder = h_obs.holder; xa.o_queue = h_obs.queue;
+        run_expand(*env->pool, env->xcfg, xa, b, m);
+        t_wait += t1 - t0; t_exp += wall_now() - t1;
     }
     for (int i = 0; i < 3; i++) CUDA_TRY(env, cudaStreamSynchronize(env->hs[i]));
+    env->host_stats[0] = wall_now() - t_begin; env->host_stats[1] = t_wait; env->host_stats[2] = t_exp; env->host_stats[3] = (double)NCH;
+    return TG_OK;
+}
+
+// Host-memory write ceiling: `threads` host threads fill h_dst (64-byte aligned, `bytes` long) with streaming stores `reps` times;
+// returns GB/s in *gb_per_s.  The output traffic of the TG_HOST_COMPACT expansion is bounded by this number (bench.py: e2e.roofline).
+struct FillJob { uint8_t* dst; size_t per, bytes; int value; };
+static void fill_item(void* ctx, int64_t i) {
+    const FillJob& j = *(const FillJob*)ctx;
+    const size_t o = (size_t)i * j.per, m = o + j.per <= j.bytes ? j.per : j.bytes - o;
+    tgh::stream_fill(j.dst + o, m, j.value);
+}
+extern "C" int tg_host_membw(void* h_dst, int64_t bytes, int32_t threads, int32_t reps, double* gb_per_s) {
+    if (!h_dst || !gb_per_s || bytes < 4096 || ((uintptr_t)h_dst & 63)) return fail(nullptr, TG_ERR_POINTER, "tg_host_membw: bad buffer");
+    tgh::Pool pool(threads > 0 ? threads : tgh::default_threads());
+    FillJob j;
+    j.dst = (uint8_t*)h_dst; j.bytes = (size_t)bytes & ~(size_t)63;
+    j.per = (j.bytes / ((size_t)pool.size() * 4) + 4095) & ~(size_t)4095;
+    const int64_t items = (int64_t)((j.bytes + j.per - 1) / j.per);
+    j.value = 0;
+    pool.run(items, fill_item, &j);                 // warm-up: page faults, thread start
+    const double t0 = wall_now();
+    for (int r = 0; r < (reps > 0 ? reps : 1); r++) { j.value = r; pool.run(items, fill_item, &j); }
+    *gb_per_s = (double)j.bytes * (reps > 0 ? reps : 1) / (wall_now() - t0) / 1e9;
+    return TG_OK;
+}
+
+// Pure host entry point of the same expansion: packed records in host memory -> observation dict (no device involved; used by
+// callers that fetch the packed state themselves, and by the CPU tests of the expansion).
+extern "C" int tg_host_expand(const tg_config* cfg, int64_t n, const void* h_hot, const void* h_board, tg_obs h_obs, int32_t threads) {
+    if (!cfg || !h_hot || !h_board || !h_obs.board || !h_obs.mask || !h_obs.holder || !h_obs.queue)
+        return fail(nullptr, TG_ERR_POINTER, "tg_host_expand: NULL argument");
+    if (n <= 0) return fail(nullptr, TG_ERR_ARG, "n must be positive");
+    int rc = validate_cfg(cfg); if (rc) return rc;
+    DevCfg d;
+    derive_cfg(cfg, d);
+    HostTables T;
+    rc = build_tables(nullptr, T); if (rc) return rc;
+    tgh::ExpandCfg x;
+    make_expand_cfg(d, T, x);
+    tgh::ExpandArgs xa;
+    xa.hot = (const uint8_t*)h_hot; xa.board = (const uint8_t*)h_board;
+    xa.board_end = xa.board + (size_t)n * d.board_stride;
+    xa.o_board = h_obs.board; xa.o_mask = h_obs.mask; xa.o_holder = h_obs.holder; xa.o_queue = h_obs.queue;
+    tgh::Pool pool(threads > 0 ? threads : tgh::default_threads());
+    run_expand(pool, x, xa, 0, n);
     return TG_OK;
 }
 
@@ -467,6 +691,17 @@ extern "C" int tg_seed_numpy(tg_env* env, tg_state st, int64_t n, const uint64_t
     CUDA_TRY(env, cudaSetDevice(env->device));
     int T = 256;
     k_seed_numpy<<<(unsigned)((n + T - 1) / T), T, 0, (cudaStream_t)stream>>>((uint8_t*)st.rng, env->dev.rng_stride, n, d_pcg, d_mask);
+    CUDA_TRY(env, cudaGetLastError());
+    return TG_OK;
+}
+
+extern "C" int tg_seed_numpy_seeds(tg_env* env, tg_state st, int64_t n, const uint64_t* d_seeds, const uint8_t* d_mask, void* stream) {
+    if (!env) return TG_ERR_POINTER;
+    if (env->cfg.rng_mode != TG_RNG_NUMPY) return fail(env, TG_ERR_ARG, "tg_seed_numpy_seeds needs rng_mode = TG_RNG_NUMPY");
+    if (!d_seeds || !st.rng) return fail(env, TG_ERR_POINTER, "NULL pointer");
+    CUDA_TRY(env, cudaSetDevice(env->device));
+    int T = 256;
+    k_seed_numpy_seeds<<<(unsigned)((n + T - 1) / T), T, 0, (cudaStream_t)stream>>>((uint8_t*)st.rng, env->dev.rng_stride, n, d_seeds, d_mask);
     CUDA_TRY(env, cudaGetLastError());
     return TG_OK;
 }

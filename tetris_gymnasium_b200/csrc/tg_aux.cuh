@@ -15,6 +15,53 @@ __global__ void k_seed_numpy(uint8_t* rng, int stride, int64_t n, const uint64_t
     r[5] = 0;
 }
 
+// numpy's SeedSequence(seed) -> PCG64 seeding on the device (Randomizer.reset, components/tetromino_randomizer.py:40-43:
+// `np.random.default_rng(seed)`): the seed's two 32-bit words are hashed into the 4-word pool (hashmix / mix), 8 words are
+// generated (generate_state(4, uint64)) and PCG64 is seeded with pcg_setseq_128_srandom_r(state = w0:w1, seq = w2:w3).
+// Published algorithm of numpy/random/bit_generator.pyx + src/pcg64/pcg64.h; pinned against numpy for 10^5 seeds
+// (tests/test_gpu_seeding.py; the same arithmetic in numpy form: oracle/np_seed.py, tests/test_oracle_seeding.py).
+__device__ __forceinline__ uint32_t ss_hashmix(uint32_t v, uint32_t& hc) {
+    v ^= hc; hc *= 0x931E8875u; v *= hc;
+    return v ^ (v >> 16);
+}
+__device__ __forceinline__ uint32_t ss_mix(uint32_t x, uint32_t y) {
+    const uint32_t r = 0xCA01F9DDu * x - 0x4973F715u * y;
+    return r ^ (r >> 16);
+}
+__global__ void k_seed_numpy_seeds(uint8_t* rng, int stride, int64_t n, const uint64_t* seeds, const uint8_t* mask) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n || (mask && !mask[e])) return;
+    const uint64_t seed = seeds[e];
+    uint32_t hc = 0x43B0D7E5u, pool[4];
+    pool[0] = ss_hashmix((uint32_t)seed, hc);
+    pool[1] = ss_hashmix((uint32_t)(seed >> 32), hc);   // an absent word hashes like 0
+    pool[2] = ss_hashmix(0u, hc);
+    pool[3] = ss_hashmix(0u, hc);
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (i != j) pool[j] = ss_mix(pool[j], ss_hashmix(pool[i], hc));
+    uint32_t hb = 0x8B51F9DDu, w[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        uint32_t d = pool[i & 3] ^ hb;
+        hb *= 0x58F38DEDu;
+        d *= hb;
+        w[i] = d ^ (d >> 16);
+    }
+    const unsigned __int128 MULT = ((unsigned __int128)0x2360ED051FC65DA4ULL << 64) | 0x4385DF649FCCF645ULL;
+    const unsigned __int128 initstate = ((unsigned __int128)((uint64_t)w[0] | ((uint64_t)w[1] << 32)) << 64) | ((uint64_t)w[2] | ((uint64_t)w[3] << 32));
+    const unsigned __int128 initseq = ((unsigned __int128)((uint64_t)w[4] | ((uint64_t)w[5] << 32)) << 64) | ((uint64_t)w[6] | ((uint64_t)w[7] << 32));
+    const unsigned __int128 inc = (initseq << 1) | 1;
+    unsigned __int128 state = inc;          // (0 * MULT + inc)
+    state += initstate;
+    state = state * MULT + inc;
+    uint64_t* r = (uint64_t*)(rng + e * stride);
+    r[0] = (uint64_t)(state >> 64); r[1] = (uint64_t)state; r[2] = (uint64_t)(inc >> 64); r[3] = (uint64_t)inc;
+    r[4] = 0; r[5] = 0;
+}
+
 template <class COLT>
 __global__ void k_get_state(const DevCfg cfg, int64_t n, const uint8_t* hot, const uint8_t* board, uint8_t* o_board,
                             int32_t* o_scalars) {

@@ -10,6 +10,8 @@ from dataclasses import fields
 from typing import Any, Optional
 
 import ctypes as C
+import os
+
 import numpy as np
 import torch
 
@@ -233,24 +235,35 @@ class Tetris:
         return s
 
     def _seed_numpy(self, seeds, mask=None):
-        """Randomizer.reset (components/tetromino_randomizer.py:34-46): PCG64(SeedSequence(seed)) for seed > 0."""
-        st = np.empty((self.num_envs, 4), dtype=np.uint64)
-        m64 = (1 << 64) - 1
-        sel = np.ones(self.num_envs, dtype=np.uint8) if mask is None else mask.copy()
-        for i in range(self.num_envs):
-            if not sel[i]:
-                continue
-            s = None if seeds is None else int(seeds[i])
-            if s is not None and s <= 0:
-                if self._seeded:      # "if seed and seed > 0" -- seed 0 keeps the running generator
-                    sel[i] = 0
-                    continue
-                s = None
-            pcg = np.random.PCG64(np.random.SeedSequence(s)).state["state"]
-            st[i] = (pcg["state"] >> 64, pcg["state"] & m64, pcg["inc"] >> 64, pcg["inc"] & m64)
-        d_st = torch.from_numpy(st.view(np.int64)).to(self.device)
+        """Randomizer.reset (components/tetromino_randomizer.py:34-46): `default_rng(seed)` = PCG64(SeedSequence(seed)) for
+        seed > 0; seed None / 0 keeps the running generator, which starts from OS entropy like `default_rng()`.  The
+        SeedSequence hash and the PCG64 seeding run on the device (tg_seed_numpy_seeds): no per-env host work."""
+        n = self.num_envs
+        sel = np.ones(n, dtype=np.uint8) if mask is None else np.asarray(mask, dtype=np.uint8).copy()
+        entropy = np.frombuffer(os.urandom(8 * n), dtype=np.uint64)
+        if seeds is None:
+            s = entropy
+            if self._seeded:
+                sel[:] = 0
+        else:
+            s = np.asarray(seeds, dtype=np.uint64).copy()
+            unseeded = s == 0                                             # "if seed and seed > 0"
+            s[unseeded] = entropy[unseeded]
+            if self._seeded:
+                sel[unseeded] = 0
+        if not self._seeded:
+            # first seeding: every env needs a valid generator, also the ones a partial reset leaves alone (an all-zero PCG64
+            # state / increment is a degenerate stream)
+            outside = sel == 0
+            s = s.copy()
+            s[outside] = entropy[outside]
+            sel[:] = 1
+        if not sel.any():
+            return
+        d_s = torch.from_numpy(s.view(np.int64)).to(self.device)
         d_m = torch.from_numpy(sel).to(self.device)
-        _lib.check(self._L.tg_seed_numpy(self._h, self._state(), self.num_envs, d_st.data_ptr(), d_m.data_ptr(), self._stream()), self._h)
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.tg_seed_numpy_seeds(self._h, self._state(), n, d_s.data_ptr(), d_m.data_ptr(), self._stream()), self._h)
 
     def reset(self, *, seed=None, options: "dict[str, Any] | None" = None):
         """Reset all envs (or `options["reset_mask"]`).  `seed`: int (env i gets seed + i, like
@@ -306,18 +319,37 @@ class Tetris:
         return (self._obs(), self._reward, self._terminated.view(torch.bool), self._truncated.view(torch.bool),
                 {"lines_cleared": self._lines})
 
-    def step_host(self, actions: np.ndarray, out: "dict[str, np.ndarray] | None" = None):
-        """Same step through host buffers (tg_step_host): actions H2D, observation dict + 5-tuple D2H.
-        `out` may hold preallocated (ideally pinned) numpy arrays; returns numpy arrays."""
-        n, lay = self.num_envs, self.layout
-        a = np.ascontiguousarray(actions, dtype=np.int32)
+    def step_host(self, actions: np.ndarray, out: "dict[str, np.ndarray] | None" = None, mode: str = "compact"):
+        """Same step with HOST arrays in and out (tg_step_host) -- the reference's own calling convention.
+        mode="compact" (default): the step runs without the dict, the packed state records cross PCIe and the dict is rebuilt
+        in `out` by the library's host threads; mode="dma": the dict is written on the device and DMA-copied.  Both give
+        identical arrays.  `out` may hold preallocated (ideally pinned, `alloc_host_buffers`) numpy arrays; returns them."""
+        n = self.num_envs
+        a = actions if (isinstance(actions, np.ndarray) and actions.dtype == np.int32 and actions.flags.c_contiguous) \
+            else np.ascontiguousarray(actions, dtype=np.int32)
+        assert a.shape == (n,), f"actions must have shape ({n},)"
         if out is None:
             out = self.alloc_host_buffers(pinned=False)
-        ho = _lib.TgObs(out["board"].ctypes.data, out["active_tetromino_mask"].ctypes.data, out["holder"].ctypes.data, out["queue"].ctypes.data)
-        so = _lib.TgStepOut(out["reward"].ctypes.data, out["terminated"].ctypes.data, out["truncated"].ctypes.data, out["lines_cleared"].ctypes.data)
+        key = (id(out), mode)
+        cached = self.__dict__.get("_c_host")
+        if cached is None or cached[0] != key:
+            ho = _lib.TgObs(out["board"].ctypes.data, out["active_tetromino_mask"].ctypes.data, out["holder"].ctypes.data, out["queue"].ctypes.data)
+            so = _lib.TgStepOut(out["reward"].ctypes.data, out["terminated"].ctypes.data, out["truncated"].ctypes.data, out["lines_cleared"].ctypes.data)
+            cached = self._c_host = (key, ho, so, out)      # keeps `out` alive while its pointers are cached
         with torch.cuda.device(self.device):
-            _lib.check(self._L.tg_step_host(self._h, self._state(), n, a.ctypes.data, ho, so), self._h)
+            _lib.check(self._L.tg_step_host(self._h, self._state(), n, a.ctypes.data, cached[1], cached[2],
+                                            _lib.HOST_MODE[mode], self._stream()), self._h)
         return out
+
+    def set_host_threads(self, threads: int = 0):
+        """Host threads of step_host(mode="compact"); 0 = cores of this process / LOCAL_WORLD_SIZE."""
+        _lib.check(self._L.tg_set_host_threads(self._h, int(threads)), self._h)
+
+    def host_stats(self):
+        """Timing of the last step_host call: seconds total / waiting for the device / expanding, and the chunk count."""
+        v = (C.c_double * 4)()
+        _lib.check(self._L.tg_host_stats(self._h, v), self._h)
+        return {"total_s": v[0], "wait_s": v[1], "expand_s": v[2], "chunks": int(v[3])}
 
     def alloc_host_buffers(self, pinned=True):
         n, lay = self.num_envs, self.layout
