@@ -385,7 +385,7 @@ def leg_e2e(env, acts, n, K, world, rank, dev, barrier, allmax, allsum):
         return allmax(dt)[0], wait / steps, exp / steps
 
     dt_c, wait_c, exp_c = run("compact", Ke)
-    d2h_c = n * (lay.hot_stride + lay.board_stride) + (scal_bytes - n)      # packed records + reward / terminated / lines (truncated is constant)
+    d2h_c = n * lay.host_record_bytes + (scal_bytes - n)      # packed link records + reward / terminated / lines (truncated is constant)
     Kd = min(Ke, 5)
     dt_d, _, _ = run("dma", Kd)
     d2h_d = dict_bytes + scal_bytes
@@ -407,8 +407,8 @@ def leg_e2e(env, acts, n, K, world, rank, dev, barrier, allmax, allsum):
     host_written = (dict_bytes + d2h_c + n) * Ke / dt_c / 1e9        # per GPU: dict (streaming stores) + packed records and scalars (DMA)
     return {"value": v, "unit": UNIT, "steps": Ke, "h2d_bytes_per_step": 4 * n, "d2h_bytes_per_step": d2h_c,
             "mode": "compact", "host_threads_per_gpu": threads, "ms_per_step": 1e3 * dt_c / Ke,
-            "note": "Tetris.step_host(mode='compact') = tg_step_host(TG_HOST_COMPACT): actions from pinned host memory; the step runs without the dict, the packed "
-                    "records (hot 32 B + board record) and reward / terminated / lines cross PCIe chunk by chunk, and the library's host threads rebuild the full "
+            "note": "Tetris.step_host(mode='compact') = tg_step_host(TG_HOST_COMPACT): actions from pinned host memory; the step runs without the dict, packed "
+                    "link records (hot words 0, 2, 3 + nibble id plane) and reward / terminated / lines cross PCIe chunk by chunk, and the library's host threads rebuild the full "
                     "observation dict in the caller's pinned arrays with streaming stores while later chunks are still in flight; every step delivers the same "
                     "bytes as the device-written dict (tests/test_gpu_host_step.py)",
             "breakdown_ms_per_step_rank0": {"waiting_for_device": 1e3 * wait_c, "expanding": 1e3 * exp_c},

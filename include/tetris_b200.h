@@ -100,7 +100,7 @@ typedef struct tg_layout {
     int32_t n_placements;   /* 4 * W   (grouped action space, wrappers/grouped.py:57) */
     int32_t n_features;     /* W + 3   (wrappers/observation.py:149-160) */
     int32_t rgb_width;      /* W_pad + max(queue_size, 1) * P (wrappers/observation.py:25-33) */
-    int32_t reserved;
+    int32_t host_record_bytes; /* bytes/env TG_HOST_COMPACT moves over the link: 12 (hot words 0, 2, 3) + nibble id plane, 16-byte rounded */
 } tg_layout;
 
 /* Device state of n envs, structure-of-records resident in HBM (caller-allocated). */
@@ -171,10 +171,11 @@ int tg_step(tg_env *env, tg_state st, int64_t n, const int32_t *d_actions, tg_ob
  * observation dict and the 5-tuple arrive in the caller's host arrays; synchronous.  `stream` is the stream the caller's
  * earlier work on this state (tg_reset, tg_step, tg_set_state ...) was enqueued on: the internal copy streams wait for it.
  *   TG_HOST_DMA     the dict is produced on the device and DMA-copied (2*Hp*Wp + 16 + 16Q bytes per env over the link);
- *   TG_HOST_COMPACT the step runs without the dict; the packed records (hot 32 B + board record) cross the link, chunk by
- *                   chunk, and a pool of host threads rebuilds the dict in the caller's arrays with streaming stores while
- *                   later chunks are still stepping (format conversion only -- no game logic runs on the host).  Arrays
- *                   aligned to 64 bytes take the fast path.  Both modes produce identical bytes. */
+ *   TG_HOST_COMPACT the step runs without the dict; what the dict is a function of -- per env hot words 0, 2, 3 and the nibble
+ *                   id plane, tg_layout.host_record_bytes (112 B at 10x20 against 992 B of dict) -- is packed on the device
+ *                   and crosses the link chunk by chunk, and a pool of host threads rebuilds the dict in the caller's arrays
+ *                   with streaming stores while later chunks are still stepping (format conversion only -- no game logic runs
+ *                   on the host).  Arrays aligned to 64 bytes take the fast path.  Both modes produce identical bytes. */
 enum { TG_HOST_DMA = 0, TG_HOST_COMPACT = 1 };
 int tg_step_host(tg_env *env, tg_state st, int64_t n, const int32_t *h_actions, tg_obs h_obs, tg_step_out h_out,
                  int32_t mode, void *stream);

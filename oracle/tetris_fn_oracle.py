@@ -10,9 +10,12 @@ Bags are therefore INJECTED (bag k = seq[k*Q:(k+1)*Q]), which is the reference's
 (tests/test_oracle_fn.py): score table (tests/test_functional/test_core/test_scoring.py:11-17), line-clear
 counts and shifting (test_core/test_line_clear.py:14-71), step-when-game-over no-op (test_env/test_step.py:16-25),
 observation value set / shape (test_env/test_observations.py).
-Open point (SURVEY 3.4): clear_filled_rows uses jnp.take(..., fill_value=0) with index -H for cleared rows;
-if -H wraps to row 0 the new top rows would copy old row 0 instead of zeros.  Identical whenever row 0 is
-empty; this restatement (and the CUDA facade) produce zeros.
+clear_filled_rows (SURVEY 3.4 open point, now decided): the reference gathers rows with jnp.take(..., fill_value=0) and
+gives cleared rows the index -H.  jnp.take's default mode "fill" wraps negative indices numpy-style before the bounds
+check (jax/_src/numpy/lax_numpy.py `_take`: `indices = where(indices < 0, indices + axis_size, indices)`), so -H is row 0,
+in bounds: the n new top rows are copies of the OLD ROW 0, not zeros.  Identical whenever row 0 is empty.  This
+restatement and the CUDA facade follow that published semantics (tests/fn_kats.py::kat_line_clear_row0_occupied); it is
+pinned to the documented behaviour of jax 0.5.3, not to an execution (jax is not installed here).
 """
 import numpy as np
 
@@ -47,7 +50,10 @@ def clear_filled_rows(board, W, H):  # core.clear_filled_rows :185-227
     n = int(filled.sum())
     if n == 0:
         return board, 0
-    new_sub = np.concatenate([np.zeros((n, W), np.int8), sub[~filled]], axis=0)
+    # indices = sort(where(filled, -H, arange(H))); jnp.take(sub, indices, axis=0, fill_value=0): in the default mode "fill"
+    # jnp.take first wraps negative indices numpy-style (index + axis_size), so -H addresses row 0 -- a valid index: the n
+    # new top rows are COPIES OF THE OLD ROW 0, not zeros (identical whenever row 0 is empty)
+    new_sub = np.concatenate([np.repeat(sub[0:1], n, axis=0), sub[~filled]], axis=0)
     return np.pad(new_sub, ((0, P), (P, P)), constant_values=1), n
 
 

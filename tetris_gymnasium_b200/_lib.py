@@ -33,7 +33,7 @@ class TgConfig(C.Structure):
 class TgLayout(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "width_padded", "height_padded", "hot_stride", "board_stride", "rng_stride", "obs_board_bytes",
-        "obs_holder_bytes", "obs_queue_bytes", "n_placements", "n_features", "rgb_width", "reserved")]
+        "obs_holder_bytes", "obs_queue_bytes", "n_placements", "n_features", "rgb_width", "host_record_bytes")]
 
 
 class TgState(C.Structure):

@@ -52,7 +52,9 @@ struct tg_env {
     size_t stage_bytes[16];
     // compact host step: pinned ring of packed records, events, expansion pool
     HostTables tabs;
-    tgh::ExpandCfg xcfg;
+    tgh::ExpandCfg xcfg;       // device record layout (tg_host_expand)
+    tgh::ExpandCfg xcfg_pk;    // packed link records (tg_step_host, TG_HOST_COMPACT)
+    int pk_bytes;              // bytes per env of a packed link record: 12 + id plane, rounded up to 16
     tgh::Pool* pool;
     int host_threads;          // 0 = tgh::default_threads()
     void* hring;               // pinned host memory
@@ -262,6 +264,7 @@ extern "C" int tg_create(const tg_config* cfg, int device, tg_env** out) {
     L.width_padded = d.Wp; L.height_padded = d.Hp; L.hot_stride = 32; L.board_stride = d.board_stride;
     L.rng_stride = d.rng_stride; L.obs_board_bytes = d.OB; L.obs_holder_bytes = 16; L.obs_queue_bytes = d.OQ;
     L.n_placements = d.A; L.n_features = d.F; L.rgb_width = d.rgb_w;
+    L.host_record_bytes = (12 + d.ids_words * 4 + 15) / 16 * 16;
 
     env->tile = 32;
     env->threads_per_env = 4;
@@ -278,6 +281,10 @@ extern "C" int tg_create(const tg_config* cfg, int device, tg_env** out) {
     int rc = upload_tables(env);
     if (rc != TG_OK) { g_create_err = env->err; delete env; return rc; }
     make_expand_cfg(env->dev, env->tabs, env->xcfg);
+    env->pk_bytes = (12 + env->dev.ids_words * 4 + 15) / 16 * 16;
+    env->xcfg_pk = env->xcfg;
+    env->xcfg_pk.board_stride = env->pk_bytes;
+    env->xcfg_pk.ids_off = 12;
     *out = env;
     return TG_OK;
 }
@@ -595,14 +602,15 @@ extern "C" int tg_step_host(tg_env* env, tg_state st, int64_t n, const int32_t* 
     int NB = 4;                                   // ring slots of packed records in pinned host memory
     if (const char* t = getenv("TG_HOST_RING")) { int v = atoi(t); if (v >= 2 && v <= 32) NB = v; }
     if (NB > NCH) NB = (int)NCH;
-    const size_t slot_hot = ((size_t)chunk * 32 + 63) / 64 * 64, slot_brd = ((size_t)chunk * d.board_stride + 64 + 63) / 64 * 64;
-    const size_t slot = slot_hot + slot_brd;
+    const int pk = env->pk_bytes;
+    const size_t slot = ((size_t)chunk * pk + 64 + 63) / 64 * 64;
     if (env->hring_bytes < slot * NB) {
         if (env->hring) cudaFreeHost(env->hring);
         env->hring = nullptr; env->hring_bytes = 0;
         CUDA_TRY(env, cudaHostAlloc(&env->hring, slot * NB, cudaHostAllocDefault));
         env->hring_bytes = slot * NB;
     }
+    rc = ensure_stage(env, 3, slot * NB); if (rc) return rc;      // packed records of the chunks in flight (device side of the ring)
     memset(h_out.truncated, 0, (size_t)n);        // always False (envs/tetris.py:219)
     tg_obs no_obs;
     memset(&no_obs, 0, sizeof no_obs);
@@ -614,8 +622,14 @@ extern "C" int tg_step_host(tg_env* env, tg_state st, int64_t n, const int32_t* 
             cudaStream_t s = env->hs[next_enq % 3];
             uint8_t* ring = (uint8_t*)env->hring + (size_t)(next_enq % NB) * slot;
             rc = host_chunk_step(env, st, b, m, h_actions, s_act, no_obs, s_rew, s_lines, s_term, s_trunc, s); if (rc) return rc;
-            CUDA_TRY(env, cudaMemcpyAsync(ring, (uint8_t*)st.hot + b * 32, (size_t)m * 32, cudaMemcpyDeviceToHost, s));
-            CUDA_TRY(env, cudaMemcpyAsync(ring + slot_hot, (uint8_t*)st.board + b * d.board_stride, (size_t)m * d.board_stride, cudaMemcpyDeviceToHost, s));
+            uint8_t* dpk = (uint8_t*)env->stage[3] + (size_t)(next_enq % NB) * slot;
+            {
+                const int64_t words = m * (pk / 4);
+                k_pack_host<<<(unsigned)((words + 255) / 256), 256, 0, s>>>((const uint8_t*)st.hot + b * 32, (const uint8_t*)st.board + b * d.board_stride,
+                                                                          d.board_stride, d.ids_off, d.ids_words, pk / 4, m, (uint32_t*)dpk);
+                CUDA_TRY(env, cudaGetLastError());
+            }
+            CUDA_TRY(env, cudaMemcpyAsync(ring, dpk, (size_t)m * pk, cudaMemcpyDeviceToHost, s));
             CUDA_TRY(env, cudaMemcpyAsync(h_out.reward + b, s_rew + b, (size_t)m * 4, cudaMemcpyDeviceToHost, s));
             CUDA_TRY(env, cudaMemcpyAsync(h_out.lines + b, s_lines + b, (size_t)m * 4, cudaMemcpyDeviceToHost, s));
             CUDA_TRY(env, cudaMemcpyAsync(h_out.terminated + b, s_term + b, (size_t)m, cudaMemcpyDeviceToHost, s));
@@ -627,10 +641,10 @@ extern "C" int tg_step_host(tg_env* env, tg_state st, int64_t n, const int32_t* 
         const int64_t b = c * chunk, m = n - b < chunk ? n - b : chunk;
         const uint8_t* ring = (const uint8_t*)env->hring + (size_t)(c % NB) * slot;
         tgh::ExpandArgs xa;
-        xa.hot = ring - b * 32; xa.board = ring + slot_hot - b * d.board_stride;   // biased: indexed by the global env id
+        xa.hot = nullptr; xa.board = ring - b * (int64_t)pk;   // biased: indexed by the global env id
         xa.board_end = ring + slot;
         xa.o_board = h_obs.board; xa.o_mask = h_obs.mask; xa.o_holder = h_obs.holder; xa.o_queue = h_obs.queue;
-        run_expand(*env->pool, env->xcfg, xa, b, m);
+        run_expand(*env->pool, env->xcfg_pk, xa, b, m);
         t_wait += t1 - t0; t_exp += wall_now() - t1;
     }
     for (int i = 0; i < 3; i++) CUDA_TRY(env, cudaStreamSynchronize(env->hs[i]));

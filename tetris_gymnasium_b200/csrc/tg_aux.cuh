@@ -62,6 +62,21 @@ __global__ void k_seed_numpy_seeds(uint8_t* rng, int stride, int64_t n, const ui
     r[4] = 0; r[5] = 0;
 }
 
+// Compact host step (tg_step_host, TG_HOST_COMPACT): what the observation dict is a function of, packed for the PCIe link --
+// per env `pk` bytes = hot words 0, 2, 3 (position / piece / rotation / holder, queue) followed by the nibble id plane.
+// One warp copies 32 / (pk / 4) ... simply: thread = (env, word), coalesced word stores.
+__global__ void k_pack_host(const uint8_t* __restrict__ hot, const uint8_t* __restrict__ board, int board_stride, int ids_off,
+                            int ids_words, int pk_words, int64_t n, uint32_t* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * pk_words) return;
+    const int64_t e = i / pk_words;
+    const int w = (int)(i - e * pk_words);
+    uint32_t v = 0;
+    if (w < 3) v = ((const uint32_t*)(hot + e * 32))[w == 0 ? 0 : w + 1];
+    else if (w - 3 < ids_words) v = ((const uint32_t*)(board + e * board_stride + ids_off))[w - 3];
+    out[i] = v;
+}
+
 template <class COLT>
 __global__ void k_get_state(const DevCfg cfg, int64_t n, const uint8_t* hot, const uint8_t* board, uint8_t* o_board,
                             int32_t* o_scalars) {

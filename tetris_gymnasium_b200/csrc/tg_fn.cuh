@@ -152,7 +152,10 @@ __global__ void k_fn_step(const FnParams p, int bstr /* bytes per staged board, 
                     if (dst != r) for (int c = 0; c < p.W; c++) b[dst * p.Wp + P + c] = b[r * p.Wp + P + c];
                     dst--;
                 }
-                for (; dst >= 0 && lines > 0; dst--) for (int c = 0; c < p.W; c++) b[dst * p.Wp + P + c] = 0;
+                // the n new top rows: the reference gathers them with jnp.take(sub_board, -H, fill_value=0); jnp.take's default
+                // mode "fill" wraps negative indices numpy-style first, so -H is row 0 (in bounds): COPIES OF THE OLD ROW 0, not
+                // zeros -- identical whenever row 0 is empty.  Row 0 itself is still in place here (rows are only moved downwards).
+                for (; dst >= 1 && lines > 0; dst--) for (int c = 0; c < p.W; c++) b[dst * p.Wp + P + c] = b[P + c];
                 lock_reward = lines == 0 ? 0 : (lines == 4 ? 800 : lines * 200 - 100);   // core.score
                 // next piece: queue.bag_queue_get_next_element (functional/queue.py:38-67)
                 if (sc[FN_QIDX] >= p.Q) { fn_new_bag(p, e, sc); piece = sc[FN_S]; sc[FN_QIDX] = 1; }

@@ -93,14 +93,17 @@ int default_threads() {
     return n < 1 ? 1 : n;
 }
 
-// ---- pool: nthreads - 1 workers + the caller; items are handed out with an atomic counter -------------------------------------
+// ---- pool: nthreads - 1 workers + the caller; items are handed out with an atomic counter.  A host step runs one parallel-for
+// per chunk, a few hundred microseconds apart: workers spin on the generation counter for a short while before they go to sleep
+// on the condition variable, so that back-to-back chunks do not pay a futex wake-up each -----------------------------------------
 struct Pool::Impl {
     std::vector<std::thread> workers;
     std::mutex mu;
-    std::condition_variable cv_start, cv_done;
-    uint64_t generation = 0;
-    int active = 0;
-    bool stop = false;
+    std::condition_variable cv_start;
+    std::atomic<uint64_t> generation{0};
+    std::atomic<int> active{0};
+    std::atomic<int> sleepers{0};
+    std::atomic<bool> stop{false};
     void (*fn)(void*, int64_t) = nullptr;
     void* ctx = nullptr;
     int64_t n_items = 0;
@@ -116,17 +119,18 @@ struct Pool::Impl {
     void loop() {
         uint64_t seen = 0;
         for (;;) {
-            {
+            int spins = 0;
+            while (generation.load(std::memory_order_acquire) == seen && !stop.load(std::memory_order_relaxed)) {
+                if (++spins < 20000) { _mm_pause(); continue; }        // ~ 1 ms of spinning, then sleep
                 std::unique_lock<std::mutex> lk(mu);
-                cv_start.wait(lk, [&] { return stop || generation != seen; });
-                if (stop) return;
-                seen = generation;
+                sleepers.fetch_add(1);
+                cv_start.wait(lk, [&] { return stop.load() || generation.load() != seen; });
+                sleepers.fetch_sub(1);
             }
+            if (stop.load()) return;
+            seen = generation.load(std::memory_order_acquire);
             work();
-            {
-                std::lock_guard<std::mutex> lk(mu);
-                if (--active == 0) cv_done.notify_one();
-            }
+            active.fetch_sub(1, std::memory_order_acq_rel);
         }
     }
 };
@@ -137,7 +141,7 @@ Pool::Pool(int threads) : impl_(new Impl), nthreads_(threads < 1 ? 1 : threads) 
 Pool::~Pool() {
     {
         std::lock_guard<std::mutex> lk(impl_->mu);
-        impl_->stop = true;
+        impl_->stop.store(true);
     }
     impl_->cv_start.notify_all();
     for (auto& t : impl_->workers) t.join();
@@ -146,17 +150,20 @@ Pool::~Pool() {
 void Pool::run(int64_t n_items, void (*fn)(void*, int64_t), void* ctx) {
     if (n_items <= 0) return;
     Impl& p = *impl_;
+    p.fn = fn; p.ctx = ctx; p.n_items = n_items;
+    p.next.store(0, std::memory_order_relaxed);
+    p.active.store((int)p.workers.size(), std::memory_order_relaxed);
     {
-        std::lock_guard<std::mutex> lk(p.mu);
-        p.fn = fn; p.ctx = ctx; p.n_items = n_items;
-        p.next.store(0, std::memory_order_relaxed);
-        p.active = (int)p.workers.size();
-        p.generation++;
+        std::lock_guard<std::mutex> lk(p.mu);          // (a sleeper checks the generation under this lock)
+        p.generation.fetch_add(1, std::memory_order_release);
     }
-    p.cv_start.notify_all();
+    if (p.sleepers.load() > 0) p.cv_start.notify_all();
     p.work();
-    std::unique_lock<std::mutex> lk(p.mu);
-    p.cv_done.wait(lk, [&] { return p.active == 0; });
+    int spins = 0;
+    while (p.active.load(std::memory_order_acquire) != 0) {
+        if (++spins < 4000) _mm_pause();
+        else std::this_thread::yield();
+    }
 }
 
 }  // namespace tgh

@@ -30,8 +30,11 @@ struct ExpandCfg {
 void build_vector_tables(ExpandCfg& c);   // fills nvec .. vidx from W, H
 
 struct ExpandArgs {
-    const uint8_t* hot;     // [n][32]
-    const uint8_t* board;   // [n][board_stride]
+    // state records: either the device layout (hot [n][32] + board [n][board_stride], ids at ids_off) or, with hot == nullptr,
+    // the packed link format (board = [n][board_stride] with hot words 0, 2, 3 in the first 12 bytes and the id plane behind:
+    // the caller passes an ExpandCfg whose board_stride / ids_off describe that record)
+    const uint8_t* hot;
+    const uint8_t* board;
     const uint8_t* board_end;   // first byte after the readable board records (the vector path reads whole 64-byte windows)
     uint8_t* o_board;       // [n][Hp][Wp]
     uint8_t* o_mask;        // [n][Hp][Wp]
