@@ -53,6 +53,22 @@ def c2_sweep(out):
         env.close()
 
 
+def c2n_multi_step(out):
+    """Config 2 at its small end through tg_step_n: K steps per native call, records resident in shared memory, obs dict +
+    5-tuple of EVERY step written to [K][n] rollout storage.  HBM bytes per env-step: dict + 10 B outputs + 4 B action."""
+    for n in (4096, 16384, 65536, 131072):
+        env = Tetris(num_envs=n, queue_size=7)
+        env.reset(seed=42)
+        K = 64
+        acts = torch.randint(0, 8, (4, K, n), dtype=torch.int32, device="cuda")
+        dt = timed(lambda i=0: env.step_n(acts[i % 4]), 10) / K
+        lay = env.layout
+        bps = 2 * lay.obs_board_bytes + 16 + 16 * 7 + 10 + 4
+        out({"config": f"C2n tg_step_n 10x20 q7, K={K} steps per call, obs dict of every step", "envs": n, "ms": dt * 1e3, "us_per_step": dt * 1e6,
+             "env_steps_per_s": n / dt, "GBps": bps * n / dt / 1e9, "frac_of_hbm_peak": bps * n / dt / 1e9 / PEAK})
+        env.close()
+
+
 def c1_latency(out):
     env = Tetris(num_envs=1, queue_size=7)
     env.reset(seed=42)
@@ -182,7 +198,7 @@ def main():
         rows.append(d)
         print(json.dumps(d), flush=True)
 
-    for name, fn in (("c1", c1_latency), ("c2", c2_sweep), ("c3", c3_grouped), ("c4", c4_rollout), ("c5", c5_wide_rgb), ("c6", c6_functional)):
+    for name, fn in (("c1", c1_latency), ("c2", c2_sweep), ("c2n", c2n_multi_step), ("c3", c3_grouped), ("c4", c4_rollout), ("c5", c5_wide_rgb), ("c6", c6_functional)):
         if not args.only or name in args.only.split(","):
             fn(out)
     if args.out:

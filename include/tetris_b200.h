@@ -166,6 +166,14 @@ int tg_seed_numpy_seeds(tg_env *env, tg_state st, int64_t n, const uint64_t *d_s
 int tg_step(tg_env *env, tg_state st, int64_t n, const int32_t *d_actions, tg_obs obs, tg_step_out out,
             tg_stats *d_stats, void *stream);
 
+/* K consecutive Tetris.step calls in one launch: d_actions = i32[k_steps][n].  The observation dict / 5-tuple arrays of step k
+ * start `k * obs_stride` / `k * out_stride` ENVS behind the passed pointers (stride n = [K][n] rollout storage; stride 0 = one
+ * set of arrays: the 5-tuple of every step overwrites the previous one and only the last step's dict is written).  Batches whose
+ * packed records fit in shared memory (up to ~10^5 envs at 10x20) run as ONE persistent launch with the records resident on chip
+ * for all K steps; larger ones as K back-to-back launches.  Same results as K tg_step calls. */
+int tg_step_n(tg_env *env, tg_state st, int64_t n, int32_t k_steps, const int32_t *d_actions, tg_obs obs, int64_t obs_stride,
+              tg_step_out out, int64_t out_stride, tg_stats *d_stats, void *stream);
+
 /* Same call with HOST buffers (the reference's own calling convention: numpy arrays in, numpy arrays out --
  * Tetris.step returns the dict of envs/tetris.py:566-615 in host memory).  Actions are copied H2D, the envs are stepped, the
  * observation dict and the 5-tuple arrive in the caller's host arrays; synchronous.  `stream` is the stream the caller's

@@ -51,7 +51,7 @@ class TgStepOut(C.Structure):
 EXPORTS = (
     "tg_create tg_destroy tg_get_layout tg_last_error tg_version tg_reset tg_seed_numpy tg_step tg_step_host "
     "tg_features tg_render_rgb tg_grouped_observe tg_grouped_step tg_rollout tg_get_state tg_set_state tg_debug_set_rollout_trace tg_fn_step tg_cnn_observe "
-    "tg_set_host_threads tg_host_stats tg_host_expand tg_seed_numpy_seeds tg_host_membw"
+    "tg_set_host_threads tg_host_stats tg_host_expand tg_seed_numpy_seeds tg_host_membw tg_step_n"
 ).split()
 
 _LIB = None
@@ -85,6 +85,7 @@ def load():
     L.tg_seed_numpy.argtypes = [vp, TgState, i64, vp, vp, vp]
     L.tg_seed_numpy_seeds.argtypes = [vp, TgState, i64, vp, vp, vp]
     L.tg_step.argtypes = [vp, TgState, i64, vp, TgObs, TgStepOut, vp, vp]
+    L.tg_step_n.argtypes = [vp, TgState, i64, C.c_int32, vp, TgObs, i64, TgStepOut, i64, vp, vp]
     L.tg_step_host.argtypes = [vp, TgState, i64, vp, TgObs, TgStepOut, C.c_int32, vp]
     L.tg_set_host_threads.argtypes = [vp, C.c_int32]
     L.tg_host_stats.argtypes = [vp, C.POINTER(C.c_double)]

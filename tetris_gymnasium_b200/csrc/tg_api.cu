@@ -12,6 +12,7 @@
 #include "../../include/tetris_b200.h"
 #include "tg_device.cuh"
 #include "tg_step.cuh"
+#include "tg_stepn.cuh"
 #include "tg_aux.cuh"
 #include "tg_gfeats.cuh"
 #include "tg_rollout.cuh"
@@ -29,7 +30,19 @@ struct HostTables {
     unsigned char colors[16][4];
 };
 
+struct StepPlan {
+    bool valid = false;
+    StepParams p;          // tile size, warp roles, shared-memory offsets (pointers unset)
+    void* kern = nullptr;
+    int threads = 0;
+    size_t smem = 0;
+    int64_t grid_max = 0;  // resident CTAs of the whole device
+    bool ws = false, pdl = false;
+};
+
 struct tg_env {
+    StepPlan plans[6];     // [mode * 2 + with dict]
+    size_t stepn_smem = 0; // dynamic shared memory the resident multi-step kernel has been configured for
     tg_config cfg;
     DevCfg dev;
     tg_layout layout;
@@ -316,40 +329,21 @@ static int check_state(tg_env* env, const tg_state& st) {
 }
 
 // ---- step / reset launcher ----------------------------------------------------------------------
+// Everything that does not depend on the call (tile size, warp roles, shared-memory carve-up, occupancy, kernel instantiation,
+// the diagnostic environment switches) is worked out once per (mode, with / without dict, kernel family) and cached in the
+// handle: a small batch's step is bound by the host-side cost of the call, and getenv + occupancy queries were half of it.
+typedef void (*step_kernel_t)(const StepParams);
 template <int WT, int HT, class COLT>
-static int launch_step_t(tg_env* env, StepParams& p, int T, size_t smem, bool ws, cudaStream_t s) {
-    auto kern = ws ? (p.mode == 2 ? k_step_ws<WT, HT, COLT, 2> : p.mode == 1 ? k_step_ws<WT, HT, COLT, 1> : k_step_ws<WT, HT, COLT, 0>) : k_step<WT, HT, COLT>;
-    CUDA_TRY(env, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    CUDA_TRY(env, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, T, smem));
-    if (per_sm < 1) return fail(env, TG_ERR_CONFIG, "step kernel does not fit: %zu B shared memory per CTA", smem);
-    int64_t ntiles = (p.n + p.E - 1) / p.E;
-    int64_t grid = (int64_t)env->num_sms * per_sm;
-    if (grid > ntiles) grid = ntiles;
-    if (ws && !getenv("TG_NO_PDL")) {
-        // programmatic stream serialization: this grid's prologue may overlap the tail of the previous kernel on the stream
-        // (k_step_ws waits with griddepcontrol.wait before it touches global memory)
-        cudaLaunchConfig_t lc;
-        memset(&lc, 0, sizeof lc);
-        lc.gridDim = dim3((unsigned)grid); lc.blockDim = dim3((unsigned)T); lc.dynamicSmemBytes = smem; lc.stream = s;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        at[0].val.programmaticStreamSerializationAllowed = 1;
-        lc.attrs = at; lc.numAttrs = 1;
-        CUDA_TRY(env, cudaLaunchKernelEx(&lc, kern, p));
-    } else {
-        kern<<<(unsigned)grid, T, smem, s>>>(p);
-    }
-    CUDA_TRY(env, cudaGetLastError());
-    return TG_OK;
+static step_kernel_t pick_kernel(bool ws, int mode) {
+    if (!ws) return (step_kernel_t)k_step<WT, HT, COLT>;
+    return mode == 2 ? (step_kernel_t)k_step_ws<WT, HT, COLT, 2> : mode == 1 ? (step_kernel_t)k_step_ws<WT, HT, COLT, 1> : (step_kernel_t)k_step_ws<WT, HT, COLT, 0>;
 }
 
-static int launch_step(tg_env* env, StepParams& p, cudaStream_t s, int force_plain = 0) {
+static int build_plan(tg_env* env, StepPlan& pl, int mode, bool want_obs, int force_plain) {
     const DevCfg& d = env->dev;
     const bool ws = env->warp_specialized && !force_plain;
     int E = ws ? 32 : env->tile;
     if (ws) if (const char* t = getenv("TG_E")) { int v = atoi(t); if (v >= 8 && v <= 32 && (v & 1) == 0) E = v; }
-    const bool want_obs = p.o_board != nullptr;
     // without the observation dict (image / feature / grouped-feature wrappers) the image warps only store records:
     // the kernel is bound by the game logic, so run more logic warps and drop the image buffers
     int NL = ws ? (want_obs || env->logic_warps_set ? env->logic_warps : 4) : 0;
@@ -357,7 +351,8 @@ static int launch_step(tg_env* env, StepParams& p, cudaStream_t s, int force_pla
     int nsx = 2;                                   // stages beyond the ones the logic warps are working on
     if (const char* t = getenv("TG_NSX")) { int v = atoi(t); if (v >= 2 && v <= 8) nsx = v; }
     int NS = ws ? NL + nsx : 2;
-    // shared-memory carve-up
+    StepParams& p = pl.p;
+    memset(&p, 0, sizeof p);
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 127) / 128 * 128; return (int)o; };
     for (;;) {
@@ -385,21 +380,60 @@ static int launch_step(tg_env* env, StepParams& p, cudaStream_t s, int force_pla
         E -= 32;
     }
     if (off > 227 * 1024) {
-        if (ws) return launch_step(env, p, s, 1);   // three state stages do not fit: two-stage kernel
+        if (ws) return build_plan(env, pl, mode, want_obs, 1);   // three state stages do not fit: two-stage kernel
         return fail(env, TG_ERR_CONFIG, "board too large for the shared-memory tile (%zu B)", off);
     }
     p.cfg = d;
     p.E = E;
     p.NL = NL;
     p.NS = NS;
+    p.mode = mode;
     p.whole_tile_min = E / 2;
     if (const char* t = getenv("TG_WHOLE")) p.whole_tile_min = atoi(t);
     int T = ws ? 32 * (NL + NF) : E * env->threads_per_env;
     if (T > 256) T = 256;
-    if (d.W == 10 && d.H == 20) return launch_step_t<10, 20, uint32_t>(env, p, T, off, ws, s);
-    if (d.W == 20 && d.H == 40) return launch_step_t<20, 40, uint64_t>(env, p, T, off, ws, s);
-    if (env->col64) return launch_step_t<0, 0, uint64_t>(env, p, T, off, ws, s);
-    return launch_step_t<0, 0, uint32_t>(env, p, T, off, ws, s);
+    pl.threads = T; pl.smem = off; pl.ws = ws;
+    pl.pdl = ws && !getenv("TG_NO_PDL");
+    if (d.W == 10 && d.H == 20) pl.kern = (void*)pick_kernel<10, 20, uint32_t>(ws, mode);
+    else if (d.W == 20 && d.H == 40) pl.kern = (void*)pick_kernel<20, 40, uint64_t>(ws, mode);
+    else if (env->col64) pl.kern = (void*)pick_kernel<0, 0, uint64_t>(ws, mode);
+    else pl.kern = (void*)pick_kernel<0, 0, uint32_t>(ws, mode);
+    CUDA_TRY(env, cudaFuncSetAttribute(pl.kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)off));
+    int per_sm = 0;
+    CUDA_TRY(env, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pl.kern, T, off));
+    if (per_sm < 1) return fail(env, TG_ERR_CONFIG, "step kernel does not fit: %zu B shared memory per CTA", off);
+    pl.grid_max = (int64_t)env->num_sms * per_sm;
+    pl.valid = true;
+    return TG_OK;
+}
+
+// `p` carries the per-call pointers (and p.mode); the plan supplies the rest
+static int launch_step(tg_env* env, StepParams& p, cudaStream_t s) {
+    const bool want_obs = p.o_board != nullptr;
+    StepPlan& pl = env->plans[p.mode * 2 + (want_obs ? 1 : 0)];
+    if (!pl.valid) { int rc = build_plan(env, pl, p.mode, want_obs, 0); if (rc) return rc; }
+    const StepParams& q = pl.p;
+    p.cfg = env->dev;           // (env_id_offset may differ per call: tg_step_host steps chunks)
+    p.E = q.E; p.NL = q.NL; p.NS = q.NS; p.whole_tile_min = q.whole_tile_min;
+    p.off_hot = q.off_hot; p.off_brd = q.off_brd; p.off_rng = q.off_rng; p.off_iboard = q.off_iboard; p.off_imask = q.off_imask;
+    p.off_iholder = q.off_iholder; p.off_iqueue = q.off_iqueue; p.off_bar = q.off_bar; p.off_box = q.off_box; p.off_tab = q.off_tab;
+    p.off_feat = q.off_feat; p.st_hot = q.st_hot; p.st_brd = q.st_brd; p.st_rng = q.st_rng;
+    const int64_t ntiles = (p.n + p.E - 1) / p.E;
+    const int64_t grid = pl.grid_max < ntiles ? pl.grid_max : ntiles;
+    cudaLaunchConfig_t lc;
+    memset(&lc, 0, sizeof lc);
+    lc.gridDim = dim3((unsigned)grid); lc.blockDim = dim3((unsigned)pl.threads); lc.dynamicSmemBytes = pl.smem; lc.stream = s;
+    cudaLaunchAttribute at[1];
+    if (pl.pdl) {
+        // programmatic stream serialization: this grid's prologue may overlap the tail of the previous kernel on the stream
+        // (k_step_ws waits with griddepcontrol.wait before it touches global memory)
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        lc.attrs = at; lc.numAttrs = 1;
+    }
+    void* args[1] = {(void*)&p};
+    CUDA_TRY(env, cudaLaunchKernelExC(&lc, pl.kern, args));
+    return TG_OK;
 }
 
 static int check_obs(tg_env* env, const tg_obs& o) {
@@ -443,6 +477,100 @@ extern "C" int tg_step(tg_env* env, tg_state st, int64_t n, const int32_t* d_act
     p.stats = (double*)d_stats;
     p.mode = 0;
     return launch_step(env, p, (cudaStream_t)stream);
+}
+
+// ---- K steps per call (small batches: records resident in shared memory for all K steps) ------------------------------------------
+typedef void (*stepn_kernel_t)(const StepNParams);
+extern "C" int tg_step_n(tg_env* env, tg_state st, int64_t n, int32_t k_steps, const int32_t* d_actions, tg_obs obs, int64_t obs_stride,
+                         tg_step_out out, int64_t out_stride, tg_stats* d_stats, void* stream) {
+    if (!env) return TG_ERR_POINTER;
+    if (n <= 0 || k_steps <= 0) return fail(env, TG_ERR_ARG, "n and k_steps must be positive");
+    if ((obs_stride != 0 && obs_stride < n) || (out_stride != 0 && out_stride < n)) return fail(env, TG_ERR_ARG, "step strides must be 0 or >= n");
+    int rc = check_state(env, st); if (rc) return rc;
+    rc = check_obs(env, obs); if (rc) return rc;
+    if (!d_actions || !out.reward || !out.terminated || !out.truncated || !out.lines)
+        return fail(env, TG_ERR_POINTER, "actions / step outputs pointer is NULL");
+    CUDA_TRY(env, cudaSetDevice(env->device));
+    const DevCfg& d = env->dev;
+    cudaStream_t s = (cudaStream_t)stream;
+    // ---- resident plan: the whole batch's records stay in shared memory ----
+    const int E = 32, NF = 4, T = 32 * (1 + NF);
+    const int64_t ntiles = (n + E - 1) / E;
+    StepNParams q;
+    memset(&q, 0, sizeof q);
+    StepParams& p = q.sp;
+    size_t smem = 0;
+    int64_t grid = 0;
+    bool resident = env->warp_specialized && (((uintptr_t)obs.board | (uintptr_t)obs.mask) & 15) == 0 && (d.OB & 15) == 0 &&
+                    (obs_stride * d.OB) % 16 == 0 && !getenv("TG_NO_RESIDENT");
+    if (resident) {
+        resident = false;
+        for (int per_sm = 3; per_sm >= 1 && !resident; per_sm--) {
+            grid = (int64_t)env->num_sms * per_sm;
+            if (grid > ntiles) grid = ntiles;
+            const int64_t TL = (ntiles + grid - 1) / grid;
+            if (TL > 64) continue;
+            size_t off = 0;
+            auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 127) / 128 * 128; return (int)o; };
+            p.st_hot = (int)(((size_t)E * 32 + 127) / 128 * 128);
+            p.st_brd = (int)(((size_t)E * d.board_stride + 16 + 127) / 128 * 128);
+            p.st_rng = (int)(((size_t)E * d.rng_stride + 127) / 128 * 128);
+            p.off_hot = take((size_t)TL * p.st_hot);
+            p.off_brd = take((size_t)TL * p.st_brd);
+            p.off_rng = take((size_t)TL * p.st_rng);
+            p.off_iboard = take((size_t)E * d.OB + 16);
+            p.off_imask = take((size_t)E * d.OB + 16);
+            p.off_iholder = take((size_t)E * 16 + 16);
+            p.off_iqueue = take((size_t)E * d.OQ + 16);
+            p.off_bar = take(16);
+            p.off_box = take((size_t)(TL + 1) * E * 4);
+            p.off_tab = take(112 * 4 + 64 + 32);
+            q.off_cnt = take(16);
+            q.off_dirty = take((size_t)TL * E * 4);
+            if (off + 1024 <= (size_t)(227 * 1024) / per_sm) { resident = true; q.TL = (int)TL; smem = off; }
+        }
+    }
+    if (resident) {
+        p.cfg = d; p.n = n; p.E = E; p.mode = 0;
+        p.hot = (uint8_t*)st.hot; p.board = (uint8_t*)st.board; p.rng = (uint8_t*)st.rng; p.seq = st.piece_seq;
+        p.actions = d_actions;
+        p.o_board = obs.board; p.o_mask = obs.mask; p.o_holder = obs.holder; p.o_queue = obs.queue;
+        p.reward = out.reward; p.terminated = out.terminated; p.truncated = out.truncated; p.lines = out.lines;
+        p.stats = (double*)d_stats;
+        q.K = k_steps; q.obs_stride = obs_stride; q.out_stride = out_stride;
+        stepn_kernel_t kern;
+        if (d.W == 10 && d.H == 20) kern = k_step_resident<10, 20, uint32_t>;
+        else if (d.W == 20 && d.H == 40) kern = k_step_resident<20, 40, uint64_t>;
+        else if (env->col64) kern = k_step_resident<0, 0, uint64_t>;
+        else kern = k_step_resident<0, 0, uint32_t>;
+        if (env->stepn_smem < smem) {
+            CUDA_TRY(env, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            env->stepn_smem = smem;
+        }
+        cudaLaunchConfig_t lc;
+        memset(&lc, 0, sizeof lc);
+        lc.gridDim = dim3((unsigned)grid); lc.blockDim = dim3((unsigned)T); lc.dynamicSmemBytes = smem; lc.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        lc.attrs = at; lc.numAttrs = 1;
+        CUDA_TRY(env, cudaLaunchKernelEx(&lc, kern, q));
+        return TG_OK;
+    }
+    // ---- large batches: one launch per step (back to back, programmatic dependent launches) ----
+    for (int k = 0; k < k_steps; k++) {
+        StepParams pk;
+        memset(&pk, 0, sizeof pk);
+        pk.n = n; pk.hot = (uint8_t*)st.hot; pk.board = (uint8_t*)st.board; pk.rng = (uint8_t*)st.rng; pk.seq = st.piece_seq;
+        pk.actions = d_actions + (int64_t)k * n;
+        const int64_t ob = (int64_t)k * obs_stride, oo = (int64_t)k * out_stride;
+        pk.o_board = obs.board + ob * d.OB; pk.o_mask = obs.mask + ob * d.OB; pk.o_holder = obs.holder + ob * 16; pk.o_queue = obs.queue + ob * d.OQ;
+        pk.reward = out.reward + oo; pk.terminated = out.terminated + oo; pk.truncated = out.truncated + oo; pk.lines = out.lines + oo;
+        pk.stats = (double*)d_stats;
+        pk.mode = 0;
+        rc = launch_step(env, pk, s); if (rc) return rc;
+    }
+    return TG_OK;
 }
 
 // ---- host-buffer step (e2e path): H2D actions, step, D2H observation dict + 5-tuple -----------------

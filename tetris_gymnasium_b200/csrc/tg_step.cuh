@@ -213,10 +213,11 @@ __device__ __noinline__ void flush_stats(double* stats, double ep, double ret, d
 // Runs reset / step / grouped placement for env `e` whose records sit at slot `slot` of the staged tile.
 // Returns bit0 = board record dirty, bit1 = rng record dirty.  Writes the 5-tuple scalars and s_box[slot].
 // MODE >= 0: the kernel instantiation's fixed mode (0 step, 1 reset, 2 grouped step); -1: p.mode at run time (k_step)
+// `eo`: index of the env's 5-tuple outputs (== e except in the multi-step kernel, whose outputs are [step][env])
 template <class COLT, bool INFO = true, int MODE = -1>
 __device__ __forceinline__ uint32_t logic_one_env(const StepParams& p, const Tabs& tb, int64_t e, int slot, int action,
                                                   uint32_t* s_hot, uint8_t* s_brd, uint8_t* s_rng, uint32_t* s_box,
-                                                  TileStats& st) {
+                                                  TileStats& st, int64_t eo) {
     const DevCfg& cfg = p.cfg;
     const int BS = cfg.board_stride, RS = cfg.rng_stride;
     StepResult res;
@@ -273,10 +274,10 @@ __device__ __forceinline__ uint32_t logic_one_env(const StepParams& p, const Tab
     if (mode == 2 && need_reset) p.fill_high[e] = 0;
     hot_store(h, s_hot + slot * 8);
     if (mode != 1) {
-        p.reward[e] = (float)res.reward;
-        p.terminated[e] = (uint8_t)res.terminated;
-        p.truncated[e] = 0;
-        p.lines[e] = res.lines;
+        p.reward[eo] = (float)res.reward;
+        p.terminated[eo] = (uint8_t)res.terminated;
+        p.truncated[eo] = 0;
+        p.lines[eo] = res.lines;
     }
     COLT Bact = bmask<COLT>((const COLT*)rec, cfg.W, tb.cells[h.p * 4 + h.r], h.x);
     const uint32_t show = !((Bact >> h.y) & 1);
@@ -444,7 +445,7 @@ __global__ void __launch_bounds__(256) k_step(const __grid_constant__ StepParams
             int action = 0;
             if (p.mode != 1) action = p.actions[e];
             mbar_wait(bar + b, (uint32_t)((k >> 1) & 1));
-            dirty = logic_one_env<COLT>(p, tb, e, tid, action, s_hot, s_brd, s_rng, s_box, st);
+            dirty = logic_one_env<COLT>(p, tb, e, tid, action, s_hot, s_brd, s_rng, s_box, st, e);
         }
         // the previous tile's stores must have finished reading shared memory (images + the other state stage)
         bulk_wait_read();
@@ -577,7 +578,7 @@ __global__ void __launch_bounds__(256) k_step_ws(const __grid_constant__ StepPar
             uint32_t dirty = 0;
             if (lane < nv)
                 dirty = logic_one_env<COLT, false, MODE>(p, tb, base + lane, lane, action, (uint32_t*)(smem + p.off_hot + s * p.st_hot),
-                                                   smem + p.off_brd + s * p.st_brd, smem + p.off_rng + s * p.st_rng, s_boxes + s * E, st);
+                                                   smem + p.off_brd + s * p.st_brd, smem + p.off_rng + s * p.st_rng, s_boxes + s * E, st, base + lane);
             // grouped mode: tiles where most envs committed (nearly always) write their board records back as ONE bulk copy
             const int ndirty = GROUPED ? __popc(__ballot_sync(0xffffffffu, (dirty & 1u) != 0)) : 0;
             if (lane < E) s_flags[s * E + lane] = dirty | ((uint32_t)ndirty << 8);

@@ -319,6 +319,42 @@ class Tetris:
         return (self._obs(), self._reward, self._terminated.view(torch.bool), self._truncated.view(torch.bool),
                 {"lines_cleared": self._lines})
 
+    def step_n(self, actions, keep_all: bool = True):
+        """K consecutive steps in one native call (tg_step_n): `actions` int32 [K, num_envs] on the device.
+        keep_all=True returns rollout storage with a leading step axis -- obs dict arrays [K, n, ...], reward / terminated /
+        truncated [K, n], info["lines_cleared"] [K, n] (buffers reused by the next call of the same K); keep_all=False keeps
+        only the last step's observation and 5-tuple in the env's usual output buffers.  Batches whose records fit in shared
+        memory run as ONE persistent launch with the state resident on chip for all K steps (small batches are otherwise bound
+        by launch / call latency, not by work); results are identical to K step() calls."""
+        a = actions if torch.is_tensor(actions) else torch.as_tensor(np.asarray(actions))
+        a = a.to(device=self.device, dtype=torch.int32).contiguous()
+        assert a.dim() == 2 and a.shape[1] == self.num_envs, f"actions must have shape (K, {self.num_envs})"
+        K, n, lay, u8 = int(a.shape[0]), self.num_envs, self.layout, torch.uint8
+        if keep_all:
+            st = self.__dict__.get("_stepn")
+            if st is None or st["K"] != K:
+                dev = self.device
+                st = self._stepn = {
+                    "K": K,
+                    "board": torch.empty((K, n, lay.height_padded, lay.width_padded), dtype=u8, device=dev),
+                    "mask": torch.empty((K, n, lay.height_padded, lay.width_padded), dtype=u8, device=dev),
+                    "holder": torch.empty((K, n, PADDING, PADDING), dtype=u8, device=dev),
+                    "queue": torch.empty((K, n, PADDING, PADDING * self.queue_size), dtype=u8, device=dev),
+                    "reward": torch.empty((K, n), dtype=torch.float32, device=dev), "terminated": torch.empty((K, n), dtype=u8, device=dev),
+                    "truncated": torch.empty((K, n), dtype=u8, device=dev), "lines": torch.empty((K, n), dtype=torch.int32, device=dev)}
+                st["c_obs"] = _lib.TgObs(st["board"].data_ptr(), st["mask"].data_ptr(), st["holder"].data_ptr(), st["queue"].data_ptr())
+                st["c_out"] = _lib.TgStepOut(st["reward"].data_ptr(), st["terminated"].data_ptr(), st["truncated"].data_ptr(), st["lines"].data_ptr())
+            obs, out, stride = st["c_obs"], st["c_out"], n
+        else:
+            obs, out, stride = self._obs_struct(), self._out_struct(), 0
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.tg_step_n(self._h, self._state(), n, K, a.data_ptr(), obs, stride, out, stride, self._stats.data_ptr(),
+                                         self._stream()), self._h)
+        if keep_all:
+            return ({"board": st["board"], "active_tetromino_mask": st["mask"], "holder": st["holder"], "queue": st["queue"]},
+                    st["reward"], st["terminated"].view(torch.bool), st["truncated"].view(torch.bool), {"lines_cleared": st["lines"]})
+        return (self._obs(), self._reward, self._terminated.view(torch.bool), self._truncated.view(torch.bool), {"lines_cleared": self._lines})
+
     def step_host(self, actions: np.ndarray, out: "dict[str, np.ndarray] | None" = None, mode: str = "compact"):
         """Same step with HOST arrays in and out (tg_step_host) -- the reference's own calling convention.
         mode="compact" (default): the step runs without the dict, the packed state records cross PCIe and the dict is rebuilt
