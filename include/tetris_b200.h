@@ -21,6 +21,7 @@
  *   - invalid *actions* are data errors: the env treats them like the reference's unmatched
  *     elif-chain (no move), it does not abort (reference asserts, envs/tetris.py:215).
  *   - a tg_env handle is not re-entrant; distinct handles are independent and thread-safe.
+ *   - every entry point selects the env's device for the duration of the call and restores the caller's current device.
  *   - there is NO CPU fallback: without a CUDA device tg_create fails with TG_ERR_CUDA.
  */
 #ifndef TETRIS_B200_H
@@ -141,6 +142,10 @@ typedef struct tg_env tg_env;
 int tg_create(const tg_config *cfg, int device, tg_env **out);
 int tg_destroy(tg_env *env);
 int tg_get_layout(const tg_env *env, tg_layout *out);
+/* options that may change after construction: GroupedActionsObservations(terminate_on_illegal_action) is a WRAPPER option in the
+ * reference (wrappers/grouped.py:44-49), so the wrapper sets it on the handle it wraps */
+enum { TG_OPT_TERMINATE_ON_ILLEGAL = 1, TG_OPT_HOST_THREADS = 2 };
+int tg_set_option(tg_env *env, int32_t option, int64_t value);
 const char *tg_last_error(const tg_env *env); /* env may be NULL: error of the last failed tg_create */
 int tg_version(void);
 

@@ -69,3 +69,34 @@ def test_fn_kat_on_gpu_and_against_oracle(case):
     assert len(got) == len(want) and len(got) > 0
     for i, (g, w) in enumerate(zip(got, want)):
         assert _eq(g, w), f"{case.__name__}: trace element {i} differs\n gpu:\n{g}\n oracle:\n{w}"
+
+
+def test_queue_functions_called_directly():
+    """functional/queue.py used as plain functions (tests/test_functional/test_queue.py:23-90): shapes, ranges, determinism, the
+    refill after seven elements; and a queue built here equals the queue reset(key) starts with."""
+    from tetris_gymnasium_b200.envs import tetris_fn as F
+    from tetris_gymnasium_b200.functional import (EnvConfig, bag_queue_get_next_element, create_bag_queue, create_uniform_queue,
+                                                  uniform_queue_get_next_element)
+    from tetris_gymnasium_b200.functional.tetrominoes import TETROMINOES
+
+    cfg = EnvConfig(width=10, height=20, padding=4, queue_size=7, gravity_enabled=True)
+    key = torch.tensor([0, 0])
+    queue, index = create_bag_queue(cfg, key)
+    assert queue.shape == (7,) and int(index) == 0 and set(queue.tolist()) == set(range(7))
+    q2, _ = create_bag_queue(cfg, key)
+    assert torch.equal(queue, q2)                                    # deterministic with the same key
+    _, state, _ = F.reset(TETROMINOES, key, cfg)
+    assert torch.equal(state.queue[0], queue)
+    elem, nq, ni, _ = bag_queue_get_next_element(cfg, queue, index, key)
+    assert int(ni) == 1 and int(elem) == int(queue[0])
+    elements, k, q, i = [], key, queue, index
+    for _ in range(7):
+        e, q, i, k = bag_queue_get_next_element(cfg, q, i, k)
+        elements.append(int(e))
+    assert set(elements) == set(range(7))
+    e, q, i, k = bag_queue_get_next_element(cfg, q, i, k)              # refill after exhaustion
+    assert 0 <= int(e) < 7 and int(i) == 1 and set(q.tolist()) == set(range(7))
+    uq, ui = create_uniform_queue(cfg, key)
+    assert uq.shape == (7,) and int(ui) == 0 and bool((uq >= 0).all()) and bool((uq < cfg.queue_size - 1).all())
+    e, _, ni, _ = uniform_queue_get_next_element(cfg, uq, ui, key)
+    assert int(ni) == 1 and int(e) == int(uq[0])

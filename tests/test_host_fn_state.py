@@ -51,8 +51,10 @@ def test_queue_selectors():
     assert fn._seq(uniform_queue_get_next_element, "cpu") == fn.UNIFORM
     seq = fn._seq([[0, 1, 2], [3, 4, 5]], "cpu")
     assert seq.dtype == torch.uint8 and seq.shape == (2, 3)
-    try:
-        create_uniform_queue(EnvConfig(width=10, height=20, padding=4, queue_size=7), None)
-        raise AssertionError("selectors are not callable")
-    except TypeError:
-        pass
+    # called directly they need the device (they run the facade's own bag routine): without one they fail loudly, no CPU path
+    if not torch.cuda.is_available():
+        try:
+            create_uniform_queue(EnvConfig(width=10, height=20, padding=4, queue_size=7), torch.tensor([0, 1]))
+            raise AssertionError("no CPU fallback expected")
+        except RuntimeError:
+            pass

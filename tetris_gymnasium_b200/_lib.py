@@ -14,6 +14,7 @@ AUTORESET = {"disabled": 0, "next_step": 1, "same_step": 2}
 RNG = {"philox": 0, "sequence": 1, "numpy": 2}
 RANDOMIZER = {"bag": 0, "true": 1}
 TG_SCALARS = 8
+TG_OPT_TERMINATE_ON_ILLEGAL, TG_OPT_HOST_THREADS = 1, 2
 HOST_MODE = {"dma": 0, "compact": 1}
 TG_VERSION = 2
 
@@ -51,7 +52,7 @@ class TgStepOut(C.Structure):
 EXPORTS = (
     "tg_create tg_destroy tg_get_layout tg_last_error tg_version tg_reset tg_seed_numpy tg_step tg_step_host "
     "tg_features tg_render_rgb tg_grouped_observe tg_grouped_step tg_rollout tg_get_state tg_set_state tg_debug_set_rollout_trace tg_fn_step tg_cnn_observe "
-    "tg_set_host_threads tg_host_stats tg_host_expand tg_seed_numpy_seeds tg_host_membw tg_step_n"
+    "tg_set_host_threads tg_host_stats tg_host_expand tg_seed_numpy_seeds tg_host_membw tg_step_n tg_set_option"
 ).split()
 
 _LIB = None
@@ -80,6 +81,7 @@ def load():
     L.tg_last_error.argtypes = [vp]
     L.tg_create.argtypes = [C.POINTER(TgConfig), C.c_int, C.POINTER(vp)]
     L.tg_destroy.argtypes = [vp]
+    L.tg_set_option.argtypes = [vp, C.c_int32, i64]
     L.tg_get_layout.argtypes = [vp, C.POINTER(TgLayout)]
     L.tg_reset.argtypes = [vp, TgState, i64, vp, vp, TgObs, vp]
     L.tg_seed_numpy.argtypes = [vp, TgState, i64, vp, vp, vp]

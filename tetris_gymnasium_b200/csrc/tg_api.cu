@@ -42,7 +42,6 @@ struct StepPlan {
 
 struct tg_env {
     StepPlan plans[6];     // [mode * 2 + with dict]
-    size_t stepn_smem = 0; // dynamic shared memory the resident multi-step kernel has been configured for
     tg_config cfg;
     DevCfg dev;
     tg_layout layout;
@@ -79,6 +78,19 @@ struct tg_env {
 };
 
 static std::string g_create_err;
+
+// Every entry point runs on the env's device and leaves the caller's current device as it found it (a single-process
+// multi-GPU program, or a destructor run by the garbage collector, must not see its current device change).
+struct DeviceGuard {
+    int prev = -1;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) err = cudaSetDevice(dev); else prev = -1;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define ON_DEVICE(env) DeviceGuard _guard((env)->device); CUDA_TRY(env, _guard.err)
 
 static int fail(tg_env* env, int code, const char* fmt, ...) {
     char buf[512];
@@ -187,6 +199,8 @@ static void make_expand_cfg(const DevCfg& d, const HostTables& T, tgh::ExpandCfg
     x.n[7] = 3;
     tgh::build_vector_tables(x);
 }
+
+extern "C" int tg_set_host_threads(tg_env* env, int32_t threads);
 
 static int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
@@ -304,7 +318,7 @@ extern "C" int tg_create(const tg_config* cfg, int device, tg_env** out) {
 
 extern "C" int tg_destroy(tg_env* env) {
     if (!env) return TG_OK;
-    cudaSetDevice(env->device);
+    DeviceGuard guard(env->device);
     if (env->hs_init) for (int i = 0; i < 3; i++) cudaStreamDestroy(env->hs[i]);
     if (env->hev_init) { for (int i = 0; i < 64; i++) cudaEventDestroy(env->hev[i]); cudaEventDestroy(env->caller_ev); }
     if (env->hring) cudaFreeHost(env->hring);
@@ -312,6 +326,15 @@ extern "C" int tg_destroy(tg_env* env) {
     for (int i = 0; i < 16; i++) if (env->stage[i]) cudaFree(env->stage[i]);
     delete env;
     return TG_OK;
+}
+
+extern "C" int tg_set_option(tg_env* env, int32_t option, int64_t value) {
+    if (!env) return TG_ERR_POINTER;
+    switch (option) {
+    case TG_OPT_TERMINATE_ON_ILLEGAL: env->dev.terminate_on_illegal = value != 0; env->cfg.terminate_on_illegal = value != 0; return TG_OK;
+    case TG_OPT_HOST_THREADS: return tg_set_host_threads(env, (int32_t)value);
+    default: return fail(env, TG_ERR_ARG, "tg_set_option: unknown option %d", option);
+    }
 }
 
 extern "C" int tg_get_layout(const tg_env* env, tg_layout* out) {
@@ -325,6 +348,25 @@ static int check_state(tg_env* env, const tg_state& st) {
     if (!st.hot || !st.board || !st.rng) return fail(env, TG_ERR_POINTER, "state pointer is NULL");
     if (misaligned(st.hot) || misaligned(st.board) || misaligned(st.rng)) return fail(env, TG_ERR_POINTER, "state pointer not 16-byte aligned");
     if (env->cfg.rng_mode == TG_RNG_SEQUENCE && !st.piece_seq) return fail(env, TG_ERR_POINTER, "piece_seq is NULL in TG_RNG_SEQUENCE mode");
+    return TG_OK;
+}
+
+// The dynamic shared-memory limit is an attribute of the KERNEL (per device), shared by every plan and every handle that
+// launches the instantiation: it is only ever raised.
+#include <mutex>
+static int raise_smem_limit(tg_env* env, const void* kern, size_t bytes) {
+    static std::mutex mu;
+    static std::vector<std::pair<std::pair<int, const void*>, size_t>> seen;
+    std::lock_guard<std::mutex> lk(mu);
+    for (auto& e : seen)
+        if (e.first.first == env->device && e.first.second == kern) {
+            if (e.second >= bytes) return TG_OK;
+            CUDA_TRY(env, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+            e.second = bytes;
+            return TG_OK;
+        }
+    CUDA_TRY(env, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    seen.push_back({{env->device, kern}, bytes});
     return TG_OK;
 }
 
@@ -398,7 +440,7 @@ static int build_plan(tg_env* env, StepPlan& pl, int mode, bool want_obs, int fo
     else if (d.W == 20 && d.H == 40) pl.kern = (void*)pick_kernel<20, 40, uint64_t>(ws, mode);
     else if (env->col64) pl.kern = (void*)pick_kernel<0, 0, uint64_t>(ws, mode);
     else pl.kern = (void*)pick_kernel<0, 0, uint32_t>(ws, mode);
-    CUDA_TRY(env, cudaFuncSetAttribute(pl.kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)off));
+    { int rc = raise_smem_limit(env, pl.kern, off); if (rc) return rc; }
     int per_sm = 0;
     CUDA_TRY(env, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pl.kern, T, off));
     if (per_sm < 1) return fail(env, TG_ERR_CONFIG, "step kernel does not fit: %zu B shared memory per CTA", off);
@@ -449,7 +491,7 @@ extern "C" int tg_reset(tg_env* env, tg_state st, int64_t n, const uint64_t* d_s
     if (n <= 0) return fail(env, TG_ERR_ARG, "n must be positive");
     int rc = check_state(env, st); if (rc) return rc;
     rc = check_obs(env, obs); if (rc) return rc;
-    CUDA_TRY(env, cudaSetDevice(env->device));
+    ON_DEVICE(env);
     StepParams p;
     memset(&p, 0, sizeof p);
     p.n = n; p.hot = (uint8_t*)st.hot; p.board = (uint8_t*)st.board; p.rng = (uint8_t*)st.rng; p.seq = st.piece_seq;
@@ -467,7 +509,7 @@ extern "C" int tg_step(tg_env* env, tg_state st, int64_t n, const int32_t* d_act
     if (obs.board || obs.mask || obs.holder || obs.queue) { rc = check_obs(env, obs); if (rc) return rc; }  // all NULL = no dict
     if (!d_actions || !out.reward || !out.terminated || !out.truncated || !out.lines)
         return fail(env, TG_ERR_POINTER, "actions / step outputs pointer is NULL");
-    CUDA_TRY(env, cudaSetDevice(env->device));
+    ON_DEVICE(env);
     StepParams p;
     memset(&p, 0, sizeof p);
     p.n = n; p.hot = (uint8_t*)st.hot; p.board = (uint8_t*)st.board; p.rng = (uint8_t*)st.rng; p.seq = st.piece_seq;
@@ -490,11 +532,11 @@ extern "C" int tg_step_n(tg_env* env, tg_state st, int64_t n, int32_t k_steps, c
     rc = check_obs(env, obs); if (rc) return rc;
     if (!d_actions || !out.reward || !out.terminated || !out.truncated || !out.lines)
         return fail(env, TG_ERR_POINTER, "actions / step outputs pointer is NULL");
-    CUDA_TRY(env, cudaSetDevice(env->device));
+    ON_DEVICE(env);
     const DevCfg& d = env->dev;
     cudaStream_t s = (cudaStream_t)stream;
     // ---- resident plan: the whole batch's records stay in shared memory ----
-    const int E = 32, NF = 4, T = 32 * (1 + NF);
+    const int E = 32, NF = 4, NLR = 2, T = 32 * (NLR + NF);
     const int64_t ntiles = (n + E - 1) / E;
     StepNParams q;
     memset(&q, 0, sizeof q);
@@ -505,11 +547,13 @@ extern "C" int tg_step_n(tg_env* env, tg_state st, int64_t n, int32_t k_steps, c
                     (obs_stride * d.OB) % 16 == 0 && !getenv("TG_NO_RESIDENT");
     if (resident) {
         resident = false;
-        for (int per_sm = 3; per_sm >= 1 && !resident; per_sm--) {
+        // (fewer CTAs per SM would make room for more resident tiles, but the logic warps of one CTA then serialise them: beyond
+        // ~10^5 envs at 10x20 one launch per step is faster)
+        for (int per_sm = 3; per_sm >= 2 && !resident; per_sm--) {
             grid = (int64_t)env->num_sms * per_sm;
             if (grid > ntiles) grid = ntiles;
             const int64_t TL = (ntiles + grid - 1) / grid;
-            if (TL > 64) continue;
+            if (TL > 8) continue;
             size_t off = 0;
             auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 127) / 128 * 128; return (int)o; };
             p.st_hot = (int)(((size_t)E * 32 + 127) / 128 * 128);
@@ -537,16 +581,13 @@ extern "C" int tg_step_n(tg_env* env, tg_state st, int64_t n, int32_t k_steps, c
         p.o_board = obs.board; p.o_mask = obs.mask; p.o_holder = obs.holder; p.o_queue = obs.queue;
         p.reward = out.reward; p.terminated = out.terminated; p.truncated = out.truncated; p.lines = out.lines;
         p.stats = (double*)d_stats;
-        q.K = k_steps; q.obs_stride = obs_stride; q.out_stride = out_stride;
+        q.K = k_steps; q.NL = NLR; q.obs_stride = obs_stride; q.out_stride = out_stride;
         stepn_kernel_t kern;
         if (d.W == 10 && d.H == 20) kern = k_step_resident<10, 20, uint32_t>;
         else if (d.W == 20 && d.H == 40) kern = k_step_resident<20, 40, uint64_t>;
         else if (env->col64) kern = k_step_resident<0, 0, uint64_t>;
         else kern = k_step_resident<0, 0, uint32_t>;
-        if (env->stepn_smem < smem) {
-            CUDA_TRY(env, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            env->stepn_smem = smem;
-        }
+        rc = raise_smem_limit(env, (const void*)kern, smem); if (rc) return rc;
         cudaLaunchConfig_t lc;
         memset(&lc, 0, sizeof lc);
         lc.gridDim = dim3((unsigned)grid); lc.blockDim = dim3((unsigned)T); lc.dynamicSmemBytes = smem; lc.stream = s;
@@ -670,7 +711,7 @@ extern "C" int tg_step_host(tg_env* env, tg_state st, int64_t n, const int32_t* 
         !h_out.truncated || !h_out.lines)
         return fail(env, TG_ERR_POINTER, "host buffer is NULL");
     int rc = check_state(env, st); if (rc) return rc;
-    CUDA_TRY(env, cudaSetDevice(env->device));
+    ON_DEVICE(env);
     const double t_begin = wall_now();
     rc = host_streams_begin(env, (cudaStream_t)stream); if (rc) return rc;
     const DevCfg& d = env->dev;
@@ -738,7 +779,7 @@ extern "C" int tg_step_host(tg_env* env, tg_state st, int64_t n, const int32_t* 
         CUDA_TRY(env, cudaHostAlloc(&env->hring, slot * NB, cudaHostAllocDefault));
         env->hring_bytes = slot * NB;
     }
-    rc = ensure_stage(env, 3, slot * NB); if (rc) return rc;      // packed records of the chunks in flight (device side of the ring)
+    rc = ensure_stage(env, 5, slot * NB); if (rc) return rc;      // packed records of the chunks in flight (device side of the ring)
     memset(h_out.truncated, 0, (size_t)n);        // always False (envs/tetris.py:219)
     tg_obs no_obs;
     memset(&no_obs, 0, sizeof no_obs);
@@ -750,7 +791,7 @@ extern "C" int tg_step_host(tg_env* env, tg_state st, int64_t n, const int32_t* 
             cudaStream_t s = env->hs[next_enq % 3];
             uint8_t* ring = (uint8_t*)env->hring + (size_t)(next_enq % NB) * slot;
             rc = host_chunk_step(env, st, b, m, h_actions, s_act, no_obs, s_rew, s_lines, s_term, s_trunc, s); if (rc) return rc;
-            uint8_t* dpk = (uint8_t*)env->stage[3] + (size_t)(next_enq % NB) * slot;
+            uint8_t* dpk = (uint8_t*)env->stage[5] + (size_t)(next_enq % NB) * slot;
             {
                 const int64_t words = m * (pk / 4);
                 k_pack_host<<<(unsigned)((words + 255) / 256), 256, 0, s>>>((const uint8_t*)st.hot + b * 32, (const uint8_t*)st.board + b * d.board_stride,
@@ -830,7 +871,7 @@ extern "C" int tg_seed_numpy(tg_env* env, tg_state st, int64_t n, const uint64_t
     if (!env) return TG_ERR_POINTER;
     if (env->cfg.rng_mode != TG_RNG_NUMPY) return fail(env, TG_ERR_ARG, "tg_seed_numpy needs rng_mode = TG_RNG_NUMPY");
     if (!d_pcg || !st.rng) return fail(env, TG_ERR_POINTER, "NULL pointer");
-    CUDA_TRY(env, cudaSetDevice(env->device));
+    ON_DEVICE(env);
     int T = 256;
     k_seed_numpy<<<(unsigned)((n + T - 1) / T), T, 0, (cudaStream_t)stream>>>((uint8_t*)st.rng, env->dev.rng_stride, n, d_pcg, d_mask);
     CUDA_TRY(env, cudaGetLastError());
@@ -841,7 +882,7 @@ extern "C" int tg_seed_numpy_seeds(tg_env* env, tg_state st, int64_t n, const ui
     if (!env) return TG_ERR_POINTER;
     if (env->cfg.rng_mode != TG_RNG_NUMPY) return fail(env, TG_ERR_ARG, "tg_seed_numpy_seeds needs rng_mode = TG_RNG_NUMPY");
     if (!d_seeds || !st.rng) return fail(env, TG_ERR_POINTER, "NULL pointer");
-    CUDA_TRY(env, cudaSetDevice(env->device));
+    ON_DEVICE(env);
     int T = 256;
     k_seed_numpy_seeds<<<(unsigned)((n + T - 1) / T), T, 0, (cudaStream_t)stream>>>((uint8_t*)st.rng, env->dev.rng_stride, n, d_seeds, d_mask);
     CUDA_TRY(env, cudaGetLastError());
@@ -852,7 +893,7 @@ extern "C" int tg_seed_numpy_seeds(tg_env* env, tg_state st, int64_t n, const ui
 extern "C" int tg_get_state(tg_env* env, tg_state st, int64_t n, uint8_t* d_board, int32_t* d_scalars, void* stream) {
     if (!env) return TG_ERR_POINTER;
     int rc = check_state(env, st); if (rc) return rc;
-    CUDA_TRY(env, cudaSetDevice(env->device));
+    ON_DEVICE(env);
     int T = 128;
     if (env->col64) k_get_state<uint64_t><<<(unsigned)((n + T - 1) / T), T, 0, (cudaStream_t)stream>>>(env->dev, n, (const uint8_t*)st.hot, (const uint8_t*)st.board, d_board, d_scalars);
     else k_get_state<uint32_t><<<(unsigned)((n + T - 1) / T), T, 0, (cudaStream_t)stream>>>(env->dev, n, (const uint8_t*)st.hot, (const uint8_t*)st.board, d_board, d_scalars);
@@ -864,7 +905,7 @@ extern "C" int tg_set_state(tg_env* env, tg_state st, int64_t n, const uint8_t* 
                             const uint8_t* d_mask, void* stream) {
     if (!env) return TG_ERR_POINTER;
     int rc = check_state(env, st); if (rc) return rc;
-    CUDA_TRY(env, cudaSetDevice(env->device));
+    ON_DEVICE(env);
     int T = 128;
     if (env->col64) k_set_state<uint64_t><<<(unsigned)((n + T - 1) / T), T, 0, (cudaStream_t)stream>>>(env->dev, n, (uint8_t*)st.hot, (uint8_t*)st.board, d_board, d_scalars, d_mask);
     else k_set_state<uint32_t><<<(unsigned)((n + T - 1) / T), T, 0, (cudaStream_t)stream>>>(env->dev, n, (uint8_t*)st.hot, (uint8_t*)st.board, d_board, d_scalars, d_mask);

@@ -117,11 +117,14 @@ __global__ void k_set_state(const DevCfg cfg, int64_t n, uint8_t* hot, uint8_t* 
         Hot h;
         hot_load(h, (const uint32_t*)(hot + e * 32));
         const int32_t* s = i_scalars + e * (8 + cfg.Q);
-        h.x = s[0]; h.y = s[1]; h.p = s[2]; h.r = s[3] & 3; h.hold = s[4] < 0 ? 0 : s[4] + 1; h.hold_r = s[5] & 3;
+        // out-of-range pokes are clamped into the record's bit fields (x: 6 bits inside the padded width, y: 7 bits inside the
+        // padded height, piece 0..6): a bad value must not spill into the neighbouring fields or index past the piece tables
+        h.x = min(max(s[0], 0), cfg.Wp - 1); h.y = min(max(s[1], 0), cfg.Hp - 1); h.p = min(max(s[2], 0), 6); h.r = s[3] & 3;
+        h.hold = s[4] < 0 ? 0 : min(s[4], 6) + 1; h.hold_r = s[5] & 3;
         h.swapped = s[6] != 0; h.over = s[7] != 0;
         h.pending = 0;
         h.queue = 0;
-        for (int q = 0; q < cfg.Q; q++) h.queue |= (uint64_t)(s[8 + q] & 15) << (4 * q);
+        for (int q = 0; q < cfg.Q; q++) h.queue |= (uint64_t)min(max(s[8 + q], 0), 6) << (4 * q);
         hot_store(h, (uint32_t*)(hot + e * 32));
     }
     if (i_board) {

@@ -249,7 +249,7 @@ extern "C" int tg_cnn_observe(tg_env* env, tg_state st, int64_t n, int32_t out_h
     if (d.rgb_w >= out_w && d.Hp >= out_h)
         return fail(env, TG_ERR_CONFIG, "tg_cnn_observe: both axes shrink (true area interpolation) -- not supported");
     if (fill_count < 0 || env_stride < (int64_t)out_h * out_w) return fail(env, TG_ERR_ARG, "tg_cnn_observe: bad fill_count / env_stride");
-    CUDA_TRY(env, cudaSetDevice(env->device));
+    ON_DEVICE(env);
     if (env->cnn_h != out_h || env->cnn_w != out_w) {   // (re)build the coefficient tables for this output size
         std::vector<int32_t> xt, yt;
         cnn_axis_tables(d.rgb_w, out_w, xt, true);

@@ -182,7 +182,7 @@ __global__ void __maxnreg__(W == 10 ? GF_REGS : 96) k_grouped_feats_x(const DevC
         uint32_t legal_w = 0;
         if (w0 >> 31) {
             // illegal action + terminate: obs = ones * high (wrappers/grouped.py:221-226); legal mask unchanged
-            const uint32_t hi = (uint32_t)(uint8_t)(H * W) * 0x01010101u;
+            const uint32_t hi = (uint32_t)min(255, H * W) * 0x01010101u;
 #pragma unroll
             for (int i = 0; i < F; i++) o[i] = hi;
             legal_w = ((const uint32_t*)legal)[(base + e) * W + xb];

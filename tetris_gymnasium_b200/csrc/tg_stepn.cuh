@@ -4,10 +4,11 @@
 // state per tile, drain (12 us per call at 4,096 envs for 2.5 us of logic + image work).  Envs are independent, so nothing forces
 // a trip through HBM between two steps: here every CTA keeps the records of ITS tiles resident in shared memory for all K steps
 // (loaded once, written back once), reads the step's actions, and writes the observation dict + 5-tuple of every step.
-//   * warp 0: game logic, lane = env, walks (step, tile) in order;
-//   * the other warps: observation images of the same (step, tile) sequence, one item behind, TMA bulk stores;
-//   * the two roles meet on two counters in shared memory: a tile's records are stepped again only after the image warps have
-//     finished expanding them (with a single resident tile per CTA the roles alternate; with several they overlap).
+//   * NL logic warps: game logic, lane = env; warp w owns the resident tiles j = w, w + NL, ... and walks (step, own tile) in order;
+//   * the other warps: observation images of the whole (step, tile) sequence, behind the logic, TMA bulk stores;
+//   * the roles meet on counters in shared memory (one per logic warp + one for the image warps): a tile's records are stepped
+//     again only after the image warps have finished expanding them (with a single resident tile per CTA the roles alternate;
+//     with several they overlap).
 // HBM traffic per env-step: observation dict + 10 B of outputs + 4 B of action; the state traffic is amortised over K.
 // Outputs: obs / 5-tuple arrays of step k start at element offset k * obs_stride (in envs; 0 = every step overwrites the same
 // arrays, n = [K][n] rollout storage).
@@ -20,9 +21,10 @@ struct StepNParams {
     StepParams sp;          // cfg, state pointers, output base pointers, E, image / table offsets (off_hot / off_brd / off_rng = slot arrays)
     int K;
     int TL;                 // resident tile slots per CTA
+    int NL;                 // logic warps
     int64_t obs_stride;     // envs between the observation arrays of consecutive steps
     int64_t out_stride;     // envs between the 5-tuple arrays of consecutive steps
-    int off_cnt;            // two counters + the load barrier
+    int off_cnt;            // NL + 1 counters
     int off_dirty;          // [TL][E] accumulated dirty flags
 };
 
@@ -41,7 +43,8 @@ __global__ void __launch_bounds__(256) k_step_resident(const __grid_constant__ S
     const StepParams& p = q.sp;
     const DevCfg& cfg = p.cfg;
     const int E = p.E, T = blockDim.x, tid = threadIdx.x;
-    const int FT = T - 32, ft = tid - 32;
+    const int NL = q.NL;
+    const int FT = T - 32 * NL, ft = tid - 32 * NL;
     const int W = WT ? WT : cfg.W, H = HT ? HT : cfg.H;
     const int Wp = W + 2 * P, Hp = H + P;
     const int OB = Hp * Wp, OQ = cfg.OQ, BS = cfg.board_stride, RS = cfg.rng_stride;
@@ -55,7 +58,7 @@ __global__ void __launch_bounds__(256) k_step_resident(const __grid_constant__ S
     uint32_t* s_boxes = (uint32_t*)(smem + p.off_box);            // [TL][E] boxes, then [E] boxes of the previous item
     uint32_t* s_boxprev = s_boxes + q.TL * E;
     uint32_t* s_dirty = (uint32_t*)(smem + q.off_dirty);          // [TL][E]
-    uint32_t* s_cnt = (uint32_t*)(smem + q.off_cnt);              // [0] items finished by the logic warp, [1] by the image warps
+    uint32_t* s_cnt = (uint32_t*)(smem + q.off_cnt);              // [w] own items finished by logic warp w, [NL] items finished by the image warps
     uint32_t* s_rowbytes = (uint32_t*)(smem + p.off_tab);
     unsigned short* s_cells = (unsigned short*)(s_rowbytes + 112);
     int* s_n = (int*)(s_rowbytes + 112 + 16);
@@ -70,7 +73,7 @@ __global__ void __launch_bounds__(256) k_step_resident(const __grid_constant__ S
     for (int i = tid; i < (q.TL + 1) * E; i += T) s_boxes[i] = 0;       // boxes of the resident tiles + boxes of the previous item
     for (int i = tid; i < q.TL * E; i += T) s_dirty[i] = 0;
     if (tid == 0) {
-        s_cnt[0] = 0; s_cnt[1] = 0;
+        for (int w = 0; w <= NL; w++) s_cnt[w] = 0;
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -78,7 +81,7 @@ __global__ void __launch_bounds__(256) k_step_resident(const __grid_constant__ S
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
     __syncthreads();
-    if (tid == 32) {   // all resident tiles with one barrier
+    if (ft == 0) {   // all resident tiles with one barrier
         uint32_t bytes = 0;
         for (int j = 0; j < nt; j++) {
             const int64_t base = ((int64_t)blockIdx.x + j * G) * E;
@@ -95,20 +98,20 @@ __global__ void __launch_bounds__(256) k_step_resident(const __grid_constant__ S
     }
     const int items = q.K * nt;
 
-    if (tid < 32) {
-        // ===== logic warp =====
-        const int lane = tid;
+    if (tid < 32 * NL) {
+        // ===== logic warps =====
+        const int lw = tid >> 5, lane = tid & 31;
         TileStats st = {0, 0, 0, 0};
         mbar_wait(bar, 0);
-        int i = 0;
+        uint32_t own = 0;
         for (int k = 0; k < q.K; k++) {
-            for (int j = 0; j < nt; j++, i++) {
+            for (int j = lw; j < nt; j += NL) {
                 const int64_t base = ((int64_t)blockIdx.x + j * G) * E;
                 const int nv = (int)min((int64_t)E, p.n - base);
                 int action = 0;
                 if (lane < nv) action = p.actions[(int64_t)k * p.n + base + lane];
-                // the image warps must be done with this slot's records of the previous step
-                if (k > 0) { const uint32_t need = (uint32_t)(i - nt + 1); while (ld_volatile_s(s_cnt + 1) < need) {} }
+                // the image warps must be done with this slot's records of the previous step: item (k - 1, j)
+                if (k > 0) { const uint32_t need = (uint32_t)((k - 1) * nt + j + 1); while (ld_volatile_s(s_cnt + NL) < need) {} }
                 uint32_t dirty = 0;
                 if (lane < nv)
                     dirty = logic_one_env<COLT, false, 0>(p, tb, base + lane, lane, action, (uint32_t*)(smem + p.off_hot + j * p.st_hot),
@@ -117,7 +120,8 @@ __global__ void __launch_bounds__(256) k_step_resident(const __grid_constant__ S
                 if (lane < E) s_dirty[j * E + lane] |= dirty;
                 __syncwarp();
                 __threadfence_block();
-                if (lane == 0) st_volatile_s(s_cnt, (uint32_t)(i + 1));
+                own++;
+                if (lane == 0) st_volatile_s(s_cnt + lw, own);
             }
         }
         if (p.stats) flush_stats(p.stats, st.ep, st.ret, st.len, st.lines);
@@ -132,11 +136,14 @@ __global__ void __launch_bounds__(256) k_step_resident(const __grid_constant__ S
                 const int64_t base = ((int64_t)blockIdx.x + j * G) * E;
                 const int nv = (int)min((int64_t)E, p.n - base);
                 const int64_t ob = (int64_t)k * q.obs_stride + base;
+                // item (k, j) belongs to logic warp j % NL and is its (k * own tiles + j / NL)-th item
+                const int ow = j % NL;
+                const uint32_t need = (uint32_t)(k * ((nt - ow + NL - 1) / NL) + j / NL + 1);
                 if (!every_step && k != q.K - 1) {          // nothing to emit: only release the slot (the box stays with the last emitted item)
-                    if (leader) { while (ld_volatile_s(s_cnt) < (uint32_t)(i + 1)) {} st_volatile_s(s_cnt + 1, (uint32_t)(i + 1)); }
+                    if (leader) { while (ld_volatile_s(s_cnt + ow) < need) {} st_volatile_s(s_cnt + NL, (uint32_t)(i + 1)); }
                     continue;
                 }
-                if (leader) { while (ld_volatile_s(s_cnt) < (uint32_t)(i + 1)) {} __threadfence_block(); }
+                if (leader) { while (ld_volatile_s(s_cnt + ow) < need) {} __threadfence_block(); }
                 bulk_wait_read();                           // stores of the previous item have left the image buffers
                 named_sync(BAR_FILL, FT);
                 __threadfence_block();
@@ -149,7 +156,7 @@ __global__ void __launch_bounds__(256) k_step_resident(const __grid_constant__ S
                 for (int t = ft; t < nv; t += FT) s_boxprev[t] = s_boxes[j * E + t];
                 fence_async_smem();
                 named_sync(BAR_FILL, FT);
-                if (leader) st_volatile_s(s_cnt + 1, (uint32_t)(i + 1));     // the records of slot j may be stepped again
+                if (leader) st_volatile_s(s_cnt + NL, (uint32_t)(i + 1));    // the records of slot j may be stepped again
                 tile_store<true>(p.o_board + ob * OB, i_board, (uint32_t)(nv * OB), leader, ft, FT);
                 tile_store<true>(p.o_mask + ob * OB, i_mask, (uint32_t)(nv * OB), leader, ft, FT);
                 if (leader) {

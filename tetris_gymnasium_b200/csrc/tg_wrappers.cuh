@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(256) k_grouped_feats(const DevCfg cfg, int64_t
         uint8_t* out = s_feats + it * F;
         if (w0 >> 31) {
             // illegal action + terminate: obs = ones * high (wrappers/grouped.py:221-226); legal mask unchanged
-            for (int i = 0; i < F; i++) out[i] = (uint8_t)(cfg.H * cfg.W);
+            for (int i = 0; i < F; i++) out[i] = (uint8_t)min(255, cfg.H * cfg.W);   // observation_space.high = H * W, saturated to the uint8 range
             s_legal[it] = legal[(base + e) * A + a];
             continue;
         }
@@ -156,7 +156,7 @@ __global__ void k_grouped_boards(const DevCfg cfg, int64_t n, const uint8_t* hot
         int fillv = -1;
         Placement pl;
         COLT B;
-        if (fill_high && fill_high[e]) fillv = (uint8_t)(cfg.H * cfg.W);
+        if (fill_high && fill_high[e]) fillv = (uint8_t)min(255, cfg.H * cfg.W);
         else {
             pl = eval_placement<COLT>(cfg, const_tabs(), cols, piece, rot0, a, B);
             if (lane == 0) legal[it] = pl.kind != 1;
@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(256, 3) k_grouped_boards_stream(const DevCfg c
     bool act[NV];
 #pragma unroll
     for (int j = 0; j < NV; j++) act[j] = lane + 32 * j < NQ;
-    const uint32_t fhw = 0x01010101u * (uint32_t)(uint8_t)(cfg.H * cfg.W);
+    const uint32_t fhw = 0x01010101u * (uint32_t)min(255, cfg.H * cfg.W);
     uint32_t gcount = 0;   // groups issued by this warp (selects the group buffer)
     for (int it = 0; e < n; e += stride, it++) {
         const uint32_t* rec = (const uint32_t*)(recbuf + (it & 1) * rec_bytes);
@@ -578,7 +578,7 @@ extern "C" int tg_features(tg_env* env, tg_state st, int64_t n, uint8_t* d_feats
     if (!env) return TG_ERR_POINTER;
     int rc = check_state(env, st); if (rc) return rc;
     if (!d_feats) return fail(env, TG_ERR_POINTER, "d_feats is NULL");
-    CUDA_TRY(env, cudaSetDevice(env->device));
+    ON_DEVICE(env);
     int T = 128;
     unsigned g = (unsigned)((n + T - 1) / T);
     if (env->col64) k_features<uint64_t><<<g, T, 0, (cudaStream_t)stream>>>(env->dev, n, (const uint8_t*)st.hot, (const uint8_t*)st.board, d_feats);
@@ -591,7 +591,7 @@ extern "C" int tg_render_rgb(tg_env* env, tg_state st, int64_t n, uint8_t* d_img
     if (!env) return TG_ERR_POINTER;
     int rc = check_state(env, st); if (rc) return rc;
     if (!d_img) return fail(env, TG_ERR_POINTER, "d_img is NULL");
-    CUDA_TRY(env, cudaSetDevice(env->device));
+    ON_DEVICE(env);
     const DevCfg& d = env->dev;
     auto r128 = [](size_t v) { return (int)((v + 127) / 128 * 128); };
     int rec_bytes = r128((size_t)d.board_stride + 48), pix_bytes = r128((size_t)d.Hp * d.rgb_w + 16), rgb_bytes = r128((size_t)d.Hp * d.rgb_w * 3);
@@ -712,7 +712,7 @@ extern "C" int tg_grouped_observe(tg_env* env, tg_state st, int64_t n, uint8_t* 
     if (!env) return TG_ERR_POINTER;
     int rc = check_state(env, st); if (rc) return rc;
     if (!d_legal || (!d_feats && !d_boards)) return fail(env, TG_ERR_POINTER, "grouped_observe: need d_legal and d_feats or d_boards");
-    CUDA_TRY(env, cudaSetDevice(env->device));
+    ON_DEVICE(env);
     return launch_grouped_observe(env, st, n, d_feats, d_boards, d_legal, nullptr, (cudaStream_t)stream);
 }
 
@@ -726,7 +726,7 @@ extern "C" int tg_grouped_step(tg_env* env, tg_state st, int64_t n, const int32_
         return fail(env, TG_ERR_POINTER, "grouped_step: NULL pointer");
     bool any_obs = obs.board || obs.mask || obs.holder || obs.queue;
     if (any_obs) { rc = check_obs(env, obs); if (rc) return rc; }
-    CUDA_TRY(env, cudaSetDevice(env->device));
+    ON_DEVICE(env);
     rc = ensure_stage(env, 3, (size_t)n); if (rc) return rc;  // per-env "illegal + terminate" flags
     StepParams p;
     memset(&p, 0, sizeof p);
@@ -751,7 +751,7 @@ extern "C" int tg_rollout(tg_env* env, tg_state st, int64_t n, const int32_t wei
     if (!env) return TG_ERR_POINTER;
     if (n <= 0 || k_steps < 0 || !weights) return fail(env, TG_ERR_ARG, "tg_rollout: bad argument");
     int rc = check_state(env, st); if (rc) return rc;
-    CUDA_TRY(env, cudaSetDevice(env->device));
+    ON_DEVICE(env);
     const DevCfg& d = env->dev;
     RolloutParams p;
     memset(&p, 0, sizeof p);

@@ -83,7 +83,7 @@ class Tetris:
                  render_upscale: int = 10, *, num_envs: int = 1, device=None, queue_size: Optional[int] = None,
                  padding: Optional[int] = None, autoreset_mode: str = "next_step",
                  randomizer_mode: str = "philox", piece_sequences=None, env_id_offset: int = 0,
-                 terminate_on_illegal_action: bool = True):
+                 terminate_on_illegal_action: bool = True, report_invalid_actions: bool = False):
         if base_pixels is not None or tetrominoes is not None:
             raise NotImplementedError("custom pixel / tetromino sets are not supported yet (SURVEY 8 f4)")
         if padding not in (None, PADDING):
@@ -179,6 +179,8 @@ class Tetris:
         self._seeded = False
         self._has_reset = False
         self._dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.report_invalid_actions = bool(report_invalid_actions)
+        self._all_true = torch.ones(n, dtype=torch.bool, device=dev)
         self.emit_obs_dict = True   # wrappers that replace the observation (RgbObservation, FeatureVector) switch it off
 
     # ---- plumbing ---------------------------------------------------------------------------
@@ -205,6 +207,15 @@ class Tetris:
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _vector_info(self, info):
+        """gymnasium's vector-env info format (SyncVectorEnv._add_info): every key `k` comes with a boolean mask `_k` saying which
+        envs reported it -- here every env reports every key every step (examples/train_lin_grouped.py:316-322 reads
+        infos["board"][0], infos["action_mask"][0])."""
+        for k in list(info):
+            if not k.startswith("_") and ("_" + k) not in info:
+                info["_" + k] = self._all_true
+        return info
 
     def _obs(self):
         return {"board": self._o_board, "active_tetromino_mask": self._o_mask, "holder": self._o_holder, "queue": self._o_queue}
@@ -289,7 +300,7 @@ class Tetris:
                                         self._obs_struct(), self._stream()), self._h)
         self._has_reset = True
         self._lines.zero_()
-        return self._obs(), {"lines_cleared": self._lines}
+        return self._obs(), self._vector_info({"lines_cleared": self._lines})
 
     # ---- Tetris.step (reference envs/tetris.py:203-272) -------------------------------------------
     def _actions(self, actions):
@@ -316,8 +327,12 @@ class Tetris:
                 rc = self._L.tg_step(self._h, self._state(), self.num_envs, a.data_ptr(), obs, self._out_struct(), self._stats.data_ptr(), self._stream())
         if rc:
             _lib.check(rc, self._h)
-        return (self._obs(), self._reward, self._terminated.view(torch.bool), self._truncated.view(torch.bool),
-                {"lines_cleared": self._lines})
+        info = {"lines_cleared": self._lines}
+        if self.report_invalid_actions:
+            # the reference asserts on an action outside the action space (envs/tetris.py:215); the batched env treats it as the
+            # unmatched elif chain (no move) and reports it per env instead of aborting the whole batch
+            info["invalid_action"] = (a < 0) | (a >= 8)
+        return (self._obs(), self._reward, self._terminated.view(torch.bool), self._truncated.view(torch.bool), self._vector_info(info))
 
     def step_n(self, actions, keep_all: bool = True):
         """K consecutive steps in one native call (tg_step_n): `actions` int32 [K, num_envs] on the device.

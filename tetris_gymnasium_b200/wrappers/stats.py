@@ -32,26 +32,43 @@ class RecordEpisodeStatistics:
 
     def reset(self, *, seed=None, options=None):
         out = self.env.reset(seed=seed, options=options)
-        self.episode_returns.zero_(); self.episode_lengths.zero_(); self.prev_dones.zero_()
+        mask = None
+        if options and options.get("reset_mask") is not None:
+            mask = torch.as_tensor(options["reset_mask"]).to(self.episode_returns.device).to(torch.bool)
+        if mask is None:
+            self.episode_returns.zero_(); self.episode_lengths.zero_(); self.prev_dones.zero_()
+        else:   # a partial reset only restarts the masked envs' episodes
+            self.episode_returns.masked_fill_(mask, 0.0); self.episode_lengths.masked_fill_(mask, 0); self.prev_dones.masked_fill_(mask, False)
         self._t0 = time.perf_counter()
         return out
 
     def step(self, action):
         obs, reward, terminated, truncated, info = self.env.step(action)
-        # envs that finished on the previous step are being reset by this call (NEXT_STEP autoreset): start from zero
-        self.episode_returns.masked_fill_(self.prev_dones, 0.0)
-        self.episode_lengths.masked_fill_(self.prev_dones, 0)
-        live = ~self.prev_dones
-        self.episode_returns += reward * live
-        self.episode_lengths += live.to(torch.int32)
+        next_step = getattr(self.unwrapped, "autoreset_mode", "next_step") == "next_step"
+        if next_step:
+            # envs that finished on the previous step are being reset by this call (NEXT_STEP autoreset: their action is ignored,
+            # reward 0): the call is not a step of any episode
+            self.episode_returns.masked_fill_(self.prev_dones, 0.0)
+            self.episode_lengths.masked_fill_(self.prev_dones, 0)
+            live = ~self.prev_dones
+            self.episode_returns += reward * live
+            self.episode_lengths += live.to(torch.int32)
+        else:
+            # SAME_STEP / disabled autoreset: every call is a real step; the accumulators restart right after an episode is reported
+            self.episode_returns += reward
+            self.episode_lengths += 1
         dones = terminated | truncated
-        self.prev_dones = dones.clone()
         info = dict(info)
         zero = torch.zeros((), device=reward.device)
         info["episode"] = {"r": torch.where(dones, self.episode_returns, zero),
                            "l": torch.where(dones, self.episode_lengths, zero.to(torch.int32)),
                            "t": torch.where(dones, torch.full_like(self.episode_returns, time.perf_counter() - self._t0), zero)}
         info["_episode"] = dones
+        if next_step:
+            self.prev_dones = dones.clone()
+        else:
+            self.episode_returns = self.episode_returns.masked_fill(dones, 0.0)     # (new tensors: the reported ones stay valid)
+            self.episode_lengths = self.episode_lengths.masked_fill(dones, 0)
         return obs, reward, terminated, truncated, info
 
     def close(self):
