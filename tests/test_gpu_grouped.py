@@ -175,7 +175,7 @@ def test_grouped_random_and_greedy_vs_oracle(cfg):
         g2n, legal2n = orc_observe()
         # illegal + terminate: obs is filled with `high`, mask unchanged, env untouched
         for i in np.flatnonzero(high_rows):
-            g2n[i] = np.uint8((H * W) & 255)
+            g2n[i] = np.uint8(min(H * W, 255))      # observation_space.high = H * W, saturated to the uint8 range
             legal2n[i] = legal[i]
         assert np.array_equal(np_(r), r2), t
         assert np.array_equal(np_(term), t2) and np.array_equal(np_(info["lines_cleared"]), l2)

@@ -59,19 +59,18 @@ template <int W, class COLT>
 struct GFeatsSmem {
     static constexpr int EPB = 32, A = 4 * W, F = W + 3, WP = W + 2 * P;
     static constexpr int CS = WP | 1;                 // column row stride (odd: lanes = envs hit distinct banks)
-    static constexpr int PS = W | 1;                  // pre / suf row stride
     static constexpr int HW = (WP + 3) / 4;           // words of the padded height vector
     static constexpr int HS = HW | 1;
     static constexpr size_t off_colp = 0;
-    static constexpr size_t off_pre = off_colp + sizeof(COLT) * EPB * CS;
-    static constexpr size_t off_suf = off_pre + sizeof(COLT) * EPB * PS;
-    static constexpr size_t off_hv = off_suf + sizeof(COLT) * EPB * PS;
+    static constexpr size_t off_hv = off_colp + sizeof(COLT) * EPB * CS;
     static constexpr size_t off_hol = off_hv + 4 * EPB * HS;              // u8 [EPB][W padded to 4]
     static constexpr size_t off_w0 = off_hol + EPB * ((W + 3) & ~3);
-    static constexpr size_t off_sum = off_w0 + 4 * EPB;
-    static constexpr size_t off_slow = off_sum + 4 * EPB;                 // u16 [EPB * A]
-    static constexpr size_t off_prec = (off_slow + 2 * EPB * A + 15) & ~size_t(15);
-    static constexpr size_t off_feats = off_prec + 16 * 28;
+    static constexpr size_t off_slow = off_w0 + 4 * EPB;                  // u16 [EPB * A]
+    static constexpr size_t off_prec = (off_slow + 2 * EPB * A + 127) & ~size_t(127);
+    // piece table, 8 replicas interleaved: entry i of replica g at [i * 8 + g], i.e. always in 16-byte bank group g.  A 128-bit
+    // shared load is served a quarter warp at a time; lanes read the entry of THEIR env's piece, and with one copy the 28 entries
+    // fall into two bank groups per rotation (index 4 * piece + rot): 3 - 4 wavefronts per quarter instead of one
+    static constexpr size_t off_feats = off_prec + 16 * 28 * 8;
     static constexpr size_t off_legal = off_feats + (size_t)EPB * A * F;  // A * F is a multiple of 4
     static constexpr size_t off_ih = off_legal + (size_t)EPB * A;         // info["board"]: u8 [EPB][W4] heights, holes
     static constexpr size_t off_iho = off_ih + EPB * ((W + 3) & ~3);
@@ -85,16 +84,13 @@ __global__ void __maxnreg__(W == 10 ? GF_REGS : 96) k_grouped_feats_x(const DevC
                                                             uint8_t* legal, const uint8_t* __restrict__ fill_high,
                                                             uint8_t* __restrict__ info_board) {
     using S = GFeatsSmem<W, COLT>;
-    constexpr int EPB = S::EPB, A = S::A, F = S::F, CS = S::CS, PS = S::PS, HW = S::HW, HS = S::HS;
+    constexpr int EPB = S::EPB, A = S::A, F = S::F, CS = S::CS, HW = S::HW, HS = S::HS;
     constexpr int NH = (W + 3) / 4, VL = W - 4 * (NH - 1), T = 32 * W;
     extern __shared__ __align__(16) uint8_t sm[];
     COLT* s_colp = (COLT*)(sm + S::off_colp);
-    COLT* s_pre = (COLT*)(sm + S::off_pre);
-    COLT* s_suf = (COLT*)(sm + S::off_suf);
     uint32_t* s_hv = (uint32_t*)(sm + S::off_hv);
     uint8_t* s_hol = sm + S::off_hol;
     uint32_t* s_w0 = (uint32_t*)(sm + S::off_w0);
-    uint32_t* s_sum = (uint32_t*)(sm + S::off_sum);
     unsigned short* s_slow = (unsigned short*)(sm + S::off_slow);
     uint4* s_prec = (uint4*)(sm + S::off_prec);
     uint32_t* s_featw = (uint32_t*)(sm + S::off_feats);
@@ -112,7 +108,7 @@ __global__ void __maxnreg__(W == 10 ? GF_REGS : 96) k_grouped_feats_x(const DevC
     const COLT field = (COLT(1) << H) - 1;
 
     // ---- phase 1: thread = (column xb, env e): column -> shared memory, its height / holes with row 0 zeroed (Q1) ----
-    if (tid < 28) s_prec[tid] = (&c_prec[0][0])[tid];
+    if (tid < 28 * 8) s_prec[tid] = (&c_prec[0][0])[tid >> 3];
     if (tid == 0) s_nslow = 0;
     // programmatic dependent launch (see k_step_ws): this grid may be scheduled while the placement step drains
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -128,29 +124,9 @@ __global__ void __maxnreg__(W == 10 ? GF_REGS : 96) k_grouped_feats_x(const DevC
         if (xb < P) hv[xb] = 0;
         if (P + W + xb < 4 * HW) hv[P + W + xb] = 0;
         s_hol[e * ((W + 3) & ~3) + xb] = (uint8_t)hol;
+        if (W + xb < ((W + 3) & ~3)) s_hol[e * ((W + 3) & ~3) + W + xb] = 0;
         if (xb == 0)   // bit 31: illegal action + terminate -> the observation is filled with `high`
             s_w0[e] = (*(const uint32_t*)(hot + (base + e) * 32) & 0x7FFFFFFFu) | ((fill_high && fill_high[base + e]) ? 0x80000000u : 0u);
-    }
-    __syncthreads();
-    // ---- phase 2: per-env scans, one warp each: prefix ANDs, suffix ANDs, holes + max height ----
-    if (live) {
-        const COLT* cols = s_colp + e * CS + P;
-        if (xb == 0) {
-            COLT acc = ~COLT(0);
-#pragma unroll
-            for (int c = 0; c < W; c++) { s_pre[e * PS + c] = acc; acc &= cols[c]; }
-        } else if (xb == 1) {
-            COLT acc = ~COLT(0);
-#pragma unroll
-            for (int c = W - 1; c >= 0; c--) { s_suf[e * PS + c] = acc; acc &= cols[c]; }
-        } else if (xb == 2) {
-            const uint8_t* hv = (const uint8_t*)(s_hv + e * HS) + P;
-            const uint8_t* ho = s_hol + e * ((W + 3) & ~3);
-            int holes = 0, maxh = 0;
-#pragma unroll
-            for (int c = 0; c < W; c++) { holes += ho[c]; maxh = max(maxh, (int)hv[c]); }
-            s_sum[e] = (uint32_t)holes | ((uint32_t)maxh << 16);
-        }
     }
     __syncthreads();
     // ---- phase 3: the four rotations of (env e, column xb) ----
@@ -159,7 +135,7 @@ __global__ void __maxnreg__(W == 10 ? GF_REGS : 96) k_grouped_feats_x(const DevC
         // (SURVEY Q1), the active piece projected when it does not collide.  This thread: column xb of env e.
         const uint32_t w0 = s_w0[e];
         const int xa = w0 & 63, ya = (w0 >> 6) & 127;
-        const uint4 pa = s_prec[((w0 >> 13) & 7) * 4 + ((w0 >> 16) & 3)];
+        const uint4 pa = s_prec[(((w0 >> 13) & 7) * 4 + ((w0 >> 16) & 3)) * 8 + (e & 7)];
         const COLT* colp = s_colp + e * CS;
         COLT Ba = 0;
 #pragma unroll
@@ -201,15 +177,30 @@ __global__ void __maxnreg__(W == 10 ? GF_REGS : 96) k_grouped_feats_x(const DevC
             const int wi = x >> 2, sh = (x & 3) * 8;
             const uint32_t Wlo = hvw[wi], Whi = hvw[wi + 1];
             const uint32_t O4 = __funnelshift_r(Wlo, Whi, sh);
-            const uint32_t sums = s_sum[e];
-            const int holes0 = (int)(sums & 0xFFFFu), maxh0 = (int)(sums >> 16);
+            // holes and max height of the env's board: sums / maxima over the packed bytes (every thread of the env derives them
+            // itself -- a per-env scan by three of the ten warps plus a CTA barrier cost more than the ~25 instructions here)
+            int holes0 = 0;
+            uint32_t mx4 = 0;
+            {
+                const uint32_t* how = (const uint32_t*)(s_hol + e * W4);
+#pragma unroll
+                for (int k = 0; k < W4 / 4; k++) holes0 = __dp4a(how[k], 0x01010101u, (uint32_t)holes0);   // bytes beyond W are zero
+#pragma unroll
+                for (int k = 0; k < HW; k++) mx4 = __vmaxu4(mx4, V[k]);
+            }
+            const int maxh0 = (int)max(max(mx4 & 255u, (mx4 >> 8) & 255u), max((mx4 >> 16) & 255u, mx4 >> 24));
             // full rows = AND over ALL field columns of (column | piece bits): the columns left / right of the 4-column window
             // are the same for the four rotations (window columns without piece cells contribute themselves, wall columns ones)
-            const COLT LR = s_pre[e * PS + max(x - P, 0)] & s_suf[e * PS + min(x - P + 3, W - 1)] & field;
+            COLT LR = field;
+#pragma unroll
+            for (int c = 0; c < W; c++) {
+                const COLT v = colp[P + c];
+                LR &= ((unsigned)(c + P - x) < 4u) ? ~COLT(0) : v;
+            }
 #pragma unroll
             for (int r = 0; r < 4; r++) {
                 const int rot = (rot0 + r) & 3;                         // cumulative rot90 presses (wrappers/grouped.py:153-154)
-                const uint4 pr = s_prec[piece * 4 + rot];
+                const uint4 pr = s_prec[(piece * 4 + rot) * 8 + (e & 7)];
                 COLT B = 0;
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
@@ -302,7 +293,7 @@ __global__ void __maxnreg__(W == 10 ? GF_REGS : 96) k_grouped_feats_x(const DevC
             const uint32_t w0 = s_w0[es];
             const int piece = (w0 >> 13) & 7, rot = (int)(((w0 >> 16) & 3) + (a & 3)) & 3;
             const int x = (a >> 2) + P - (piece == 0 ? 2 : 1);
-            const uint4 pr = s_prec[piece * 4 + rot];
+            const uint4 pr = s_prec[(piece * 4 + rot) * 8 + (tid & 7)];
             const COLT* colp = s_colp + es * CS;
             COLT B = 0;
 #pragma unroll
@@ -312,9 +303,13 @@ __global__ void __maxnreg__(W == 10 ? GF_REGS : 96) k_grouped_feats_x(const DevC
             }
             const int y = ctz_t<COLT>(B >> 1);
             const int jmin = pr.w & 3, c0 = x + jmin - P, c1 = x + (int)((pr.w >> 2) & 3) - P;
-            COLT full = s_pre[es * PS + c0] & s_suf[es * PS + c1] & field;
-#pragma unroll
-            for (int j = 0; j < 4; j++) full &= colp[x + j] | ((COLT)((pr.x >> (16 + 4 * j)) & 15u) << y);
+            COLT full = field;
+            for (int c = 0; c < W; c++) {
+                COLT v = colp[P + c];
+                const int j = c + P - x;
+                if ((unsigned)j < 4u) v |= (COLT)((pr.x >> (16 + 4 * j)) & 15u) << y;
+                full &= v;
+            }
             const COLT keep = (full != 0 ? ~full : ~COLT(1)) & field;
             uint8_t* out = s_feats + (size_t)it * F;
             int s_max = 0, s_hol = 0, s_bmp = 0, prev = 0;
