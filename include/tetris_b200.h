@@ -86,6 +86,9 @@ typedef struct tg_config {
     int64_t seq_len;              /* TG_RNG_SEQUENCE: entries per env in piece_seq */
     uint64_t env_id_offset;       /* global id of local env 0 (multi-GPU sharding: Philox streams
                                      are keyed by global id so results do not depend on #GPUs) */
+    int32_t holder_size;          /* TetrominoHolder(size) (components/tetromino_holder.py:14-21): 1..4; 0 = 1 (the reference default).
+                                     A FIFO: a swap stores the active piece and, once the holder is full, hands back the oldest one. */
+    int32_t reserved0;
 } tg_config;
 
 /* Sizes of the per-env state arrays the caller must allocate (bytes per env). */
@@ -116,7 +119,8 @@ typedef struct tg_state {
 typedef struct tg_obs {
     uint8_t *board;  /* [n][H_pad][W_pad]  locked board + active piece ids          */
     uint8_t *mask;   /* [n][H_pad][W_pad]  active_tetromino_mask (n x n bounding box) */
-    uint8_t *holder; /* [n][P][P]                                                    */
+    uint8_t *holder; /* [n][P][P*holder_size]  held pieces oldest first, ones in the empty slots (holder_size 1: the reference's
+                        array; > 1: fixed shape where the reference's np.hstack of the held pieces is ragged)            */
     uint8_t *queue;  /* [n][P][P*queue_size]                                         */
 } tg_obs;
 
@@ -268,8 +272,9 @@ int tg_debug_set_rollout_trace(tg_env *env, int32_t *d_last_action);
 /* ---- state access (replaces Tetris.get_state/set_state, envs/tetris.py:681-708, and the direct
  * env.unwrapped.board/x/y/active_tetromino pokes of the reference tests) ---------------------- */
 /* canonical, unpacked views: board u8[n][H_pad][W_pad] (locked cells, bedrock = 1);
- * scalars i32[n][TG_SCALARS + queue_size] = x, y, piece (0..6), rotation (0..3 rot90(k=+1) presses),
- * holder piece (-1 = empty), holder rotation, has_swapped, game_over, then the queue. */
+ * scalars i32[n][TG_SCALARS + queue_size (+ 2 * holder_size if holder_size > 1)] = x, y, piece (0..6), rotation (0..3 rot90(k=+1)
+ * presses), holder piece (-1 = empty), holder rotation, has_swapped, game_over, then the queue; with holder_size > 1 columns 4 / 5
+ * hold the number of held pieces / 0, and the held (piece, rotation) pairs follow the queue, oldest first (-1 = empty slot). */
 #define TG_SCALARS 8
 int tg_get_state(tg_env *env, tg_state st, int64_t n, uint8_t *d_board, int32_t *d_scalars, void *stream);
 int tg_set_state(tg_env *env, tg_state st, int64_t n, const uint8_t *d_board, const int32_t *d_scalars,

@@ -52,8 +52,9 @@ typedef struct {
     orc_piece active;
     int x, y;
     int queue[ORC_MAXQ]; /* deque of piece indices, front = [0] (components/tetromino_queue.py) */
-    int holder_len;      /* TetrominoHolder size 1 (components/tetromino_holder.py:14-21) */
-    orc_piece held;
+    int holder_len;      /* TetrominoHolder (components/tetromino_holder.py:14-21): deque(maxlen = size), oldest first */
+    int holder_size;     /* 1 (reference default) .. 4 */
+    orc_piece held[4];
     int has_swapped, game_over;
     /* randomizer: scripted stream or numpy-exact 7-bag */
     int rng_mode; /* 0 scripted, 1 numpy PCG64 bag, 2 numpy PCG64 TrueRandomizer */
@@ -310,12 +311,26 @@ orc_env *orc_create(const orc_config *c) {
     create_board(e, e->board);
     e->active.idx = -1;
     e->rng_mode = 0;
+    e->holder_size = 1;
     return e;
 }
 void orc_destroy(orc_env *e) {
     if (!e) return;
     free(e->board);
     free(e);
+}
+/* TetrominoHolder(size): the reference can only get a bigger holder by assigning env.holder after construction */
+void orc_set_holder_size(orc_env *e, int size) {
+    e->holder_size = size < 1 ? 1 : (size > 4 ? 4 : size);
+    e->holder_len = 0;
+}
+int orc_get_holder_len(const orc_env *e) { return e->holder_len; }
+/* slot-th held piece (0 = oldest): returns its index or -1, matrix as n x n in m16 */
+int orc_get_held_slot(const orc_env *e, int slot, int32_t *n, uint8_t *m16) {
+    if (slot < 0 || slot >= e->holder_len) { *n = 0; return -1; }
+    *n = e->held[slot].n;
+    memcpy(m16, e->held[slot].m, 16);
+    return e->held[slot].idx;
 }
 /* scripted randomizer: stream of piece indices consumed in order (wraps at len) */
 void orc_set_sequence(orc_env *e, const uint8_t *seq, int64_t len, int64_t cursor) {
@@ -347,12 +362,17 @@ void orc_get_obs(const orc_env *e, uint8_t *board, uint8_t *mask, uint8_t *holde
             for (int j = 0; j < e->active.n; j++) mask[(e->y + i) * Wp + (e->x + j)] = 1;
     }
     if (holder) {
-        if (e->holder_len > 0) {
-            memset(holder, 0, 16);
-            for (int i = 0; i < e->held.n; i++)
-                for (int j = 0; j < e->held.n; j++) holder[i * ORC_P + j] = e->held.m[i * e->held.n + j];
-        } else {
-            memset(holder, 1, 16); /* np.ones((max_size, max_size * holder.size)) :594 */
+        /* :578-594.  size 1: the held piece padded to P x P, or np.ones((P, P * size)) when the holder is empty.  size > 1: the
+         * reference hstacks the held pieces only -- an array whose WIDTH depends on how many pieces are held; here the array
+         * has the fixed shape (P, P * size): the held pieces oldest first, ones in the empty slots (identical when the holder
+         * is empty or full; RgbObservation pads the ragged array with ones up to the queue's width, :49-58, which gives
+         * exactly this layout). */
+        int HW = ORC_P * e->holder_size;
+        memset(holder, 1, (size_t)ORC_P * HW);
+        for (int s = 0; s < e->holder_len; s++) {
+            const orc_piece *t = &e->held[s];
+            for (int i = 0; i < ORC_P; i++)
+                for (int j = 0; j < ORC_P; j++) holder[i * HW + s * ORC_P + j] = (i < t->n && j < t->n) ? t->m[i * t->n + j] : 0;
         }
     }
     if (queue) {
@@ -401,14 +421,14 @@ int orc_step(orc_env *e, int action, double *reward, int *terminated, int *lines
         if (!e->has_swapped) {
             /* TetrominoHolder.swap (components/tetromino_holder.py:31-49) */
             orc_piece cur = e->active;
-            if (e->holder_len < 1) {
-                e->held = cur;
-                e->holder_len = 1;
+            if (e->holder_len < e->holder_size) { /* not full: store, nothing comes back */
+                e->held[e->holder_len++] = cur;
                 e->has_swapped = 1;
                 (void)spawn(e); /* result ignored :250 */
-            } else {
-                e->active = e->held;
-                e->held = cur;
+            } else { /* full: the oldest piece comes back (popleft), the active one is appended */
+                e->active = e->held[0];
+                for (int s = 1; s < e->holder_size; s++) e->held[s - 1] = e->held[s];
+                e->held[e->holder_size - 1] = cur;
                 e->has_swapped = 1;
                 reset_position(e);
             }
@@ -543,7 +563,7 @@ void orc_rgb(const orc_env *e, uint8_t *out) {
     int max_len = P * (e->Q > 1 ? e->Q : 1);
     int OW = Wp + max_len;
     uint8_t *board = (uint8_t *)malloc((size_t)Hp * Wp);
-    uint8_t holder[16], queue[4 * 4 * ORC_MAXQ];
+    uint8_t holder[16 * 4], queue[4 * 4 * ORC_MAXQ];
     orc_get_obs(e, board, NULL, holder, queue);
     for (int r = 0; r < Hp; r++)
         for (int c = 0; c < OW; c++) {
@@ -555,7 +575,7 @@ void orc_rgb(const orc_env *e, uint8_t *out) {
                 if (r < P)
                     v = queue[r * (P * e->Q) + cc]; /* queue is max_len wide (Q >= holder) */
                 else if (r >= Hp - P)
-                    v = cc < P ? holder[(r - (Hp - P)) * P + cc] : 1;
+                    v = cc < P * e->holder_size ? holder[(r - (Hp - P)) * (P * e->holder_size) + cc] : 1;
                 else
                     v = 1;
             }
@@ -573,7 +593,7 @@ void orc_get_scalars(const orc_env *e, int32_t *out) {
     out[0] = e->x;
     out[1] = e->y;
     out[2] = e->active.idx;
-    out[3] = e->holder_len ? e->held.idx : -1;
+    out[3] = e->holder_len ? e->held[0].idx : -1;
     out[4] = e->has_swapped;
     out[5] = e->game_over;
     for (int q = 0; q < e->Q; q++) out[6 + q] = e->queue[q];
@@ -583,8 +603,8 @@ void orc_get_active_matrix(const orc_env *e, int32_t *n, uint8_t *m16) {
     memcpy(m16, e->active.m, 16);
 }
 void orc_get_held_matrix(const orc_env *e, int32_t *n, uint8_t *m16) {
-    *n = e->holder_len ? e->held.n : 0;
-    memcpy(m16, e->held.m, 16);
+    *n = e->holder_len ? e->held[0].n : 0;
+    memcpy(m16, e->held[0].m, 16);
 }
 /* set the active piece to TETROMINOES[idx] rotated `rot` times with rot90(k=+1) */
 void orc_set_active(orc_env *e, int idx, int rot, int x, int y) {
@@ -602,8 +622,8 @@ void orc_set_holder(orc_env *e, int idx, int rot) {
         e->holder_len = 0;
         return;
     }
-    make_piece(&e->held, idx);
-    for (int k = 0; k < (rot & 3); k++) rotate_piece(&e->held, &e->held, 1);
+    make_piece(&e->held[0], idx);
+    for (int k = 0; k < (rot & 3); k++) rotate_piece(&e->held[0], &e->held[0], 1);
     e->holder_len = 1;
 }
 void orc_set_queue(orc_env *e, const int32_t *q) {
@@ -632,7 +652,7 @@ void orc_vec_step(orc_env **envs, int64_t n, const int32_t *actions, uint8_t *au
             orc_step(e, actions[i], &r, &t, &l);
         }
         orc_get_obs(e, board ? board + i * bsz : NULL, mask ? mask + i * bsz : NULL,
-                    holder ? holder + i * 16 : NULL, queue ? queue + i * (16 * (size_t)e->Q) : NULL);
+                    holder ? holder + i * (16 * (size_t)e->holder_size) : NULL, queue ? queue + i * (16 * (size_t)e->Q) : NULL);
         reward[i] = (float)r;
         terminated[i] = (uint8_t)t;
         lines[i] = l;

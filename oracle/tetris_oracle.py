@@ -39,12 +39,14 @@ def lib():
             "orc_grouped_observe orc_rgb orc_get_board orc_set_board orc_get_scalars "
             "orc_get_active_matrix orc_get_held_matrix orc_set_active orc_set_flags orc_set_holder "
             "orc_set_queue orc_vec_step orc_vec_grouped_step orc_rnd_stream orc_grouped_observe_ex orc_set_true_randomizer "
-            "orc_vec_create orc_vec_destroy orc_vec_seed_words orc_vec_reset"
+            "orc_vec_create orc_vec_destroy orc_vec_seed_words orc_vec_reset orc_set_holder_size"
         ).split():
             getattr(L, name).restype = None
         L.orc_step.restype = C.c_int
         L.orc_grouped_step.restype = C.c_int
         L.orc_num_threads.restype = C.c_int
+        L.orc_get_holder_len.restype = C.c_int
+        L.orc_get_held_slot.restype = C.c_int
         _LIB = L
     return _LIB
 
@@ -68,7 +70,7 @@ class OracleEnv:
                    rotate_counterclockwise=4, hard_drop=5, swap=6, no_op=7)
 
     def __init__(self, width=10, height=20, gravity=True, queue_size=4, actions=None,
-                 alife=1.0, clear_line=1.0, game_over=0.0, invalid_action=-0.1):
+                 alife=1.0, clear_line=1.0, game_over=0.0, invalid_action=-0.1, holder_size=1):
         L = lib()
         a = dict(self.ACTIONS)
         if actions:
@@ -84,6 +86,9 @@ class OracleEnv:
         self.h = C.c_void_p(L.orc_create(C.byref(cfg)))
         if not self.h:
             raise ValueError("bad oracle config")
+        self.holder_size = holder_size
+        if holder_size != 1:
+            L.orc_set_holder_size(self.h, int(holder_size))
         self.W, self.H, self.Q = width, height, queue_size
         self.Wp, self.Hp = width + 8, height + 4
         self._seq = None
@@ -119,7 +124,7 @@ class OracleEnv:
         o = {
             "board": np.empty((self.Hp, self.Wp), np.uint8),
             "active_tetromino_mask": np.empty((self.Hp, self.Wp), np.uint8),
-            "holder": np.empty((4, 4), np.uint8),
+            "holder": np.empty((4, 4 * self.holder_size), np.uint8),
             "queue": np.empty((4, 4 * self.Q), np.uint8),
         }
         lib().orc_get_obs(self.h, _p(o["board"]), _p(o["active_tetromino_mask"]), _p(o["holder"]), _p(o["queue"]))
@@ -169,8 +174,21 @@ class OracleEnv:
                                       C.byref(r), C.byref(t), C.byref(l))
         return code, r.value, bool(t.value), l.value
 
+    def holder_len(self):
+        return int(lib().orc_get_holder_len(self.h))
+
+    def held_slots(self):
+        """[(piece index, n x n id-valued matrix)] of the held pieces, oldest first."""
+        out = []
+        for s in range(self.holder_len()):
+            n = C.c_int32()
+            m = np.zeros(16, np.uint8)
+            idx = lib().orc_get_held_slot(self.h, s, C.byref(n), _p(m))
+            out.append((int(idx), m[: n.value * n.value].reshape(n.value, n.value).copy()))
+        return out
+
     def rgb(self):
-        out = np.empty((self.Hp, self.Wp + 4 * max(self.Q, 1), 3), np.uint8)
+        out = np.empty((self.Hp, self.Wp + 4 * max(self.Q, self.holder_size, 1), 3), np.uint8)
         lib().orc_rgb(self.h, _p(out))
         return out
 
@@ -262,7 +280,7 @@ class OracleVec:
         self.autoreset = np.zeros(n, np.uint8)
         self.board = np.empty((n, e.Hp, e.Wp), np.uint8)
         self.mask = np.empty((n, e.Hp, e.Wp), np.uint8)
-        self.holder = np.empty((n, 4, 4), np.uint8)
+        self.holder = np.empty((n, 4, 4 * e.holder_size), np.uint8)
         self.queue = np.empty((n, 4, 4 * e.Q), np.uint8)
         self.reward = np.empty(n, np.float32)
         self.terminated = np.empty(n, np.uint8)

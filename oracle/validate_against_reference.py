@@ -65,6 +65,50 @@ def check_base(ref, episodes, width, height, gravity, queue_size, seed0, injecte
     return n_steps
 
 
+def check_holder(ref, episodes, holder_size, width, height, gravity, queue_size, seed0, max_steps=1500):
+    """TetrominoHolder(size > 1) (components/tetromino_holder.py:14-57).  `Tetris(holder=...)` leaves self.holder unset in the
+    reference (envs/tetris.py:140-145 only assigns the default), so the bigger holder is assigned after construction, like the
+    scripted queue.  The reference's "holder" observation is RAGGED for a partly filled holder (np.hstack of the held pieces
+    only); the oracle / CUDA env use the fixed shape (P, P * size): held pieces oldest first, ones in the empty slots.
+    Checked: everything else bit for bit; holder[:, :P * held] == the reference's array and ones behind it; the RGB image
+    (which pads the ragged array with ones itself, wrappers/observation.py:49-58) bit for bit."""
+    R = ref
+    rng = np.random.default_rng(seed0)
+    n_steps = 0
+    for ep in range(episodes):
+        seq = rng.integers(0, 7, size=512)
+        env = R["make"](width=width, height=height, gravity=gravity, queue_size=queue_size, seq=seq)
+        env.holder = R["TetrominoHolder"](size=holder_size)
+        orc = OracleEnv(width=width, height=height, gravity=gravity, queue_size=queue_size, holder_size=holder_size)
+        orc.set_sequence(seq)
+        rgbw = R["RgbObservation"](env)
+        o_ref, _ = env.reset()
+        o_orc, _ = orc.reset()
+        for t in range(max_steps):
+            a = int(rng.choice([0, 1, 2, 3, 4, 5, 5, 6, 6, 6, 7]))
+            o_ref, r_ref, term_ref, _, info_ref = env.step(a)
+            o_orc, r_orc, term_orc, _, info_orc = orc.step(a)
+            n_steps += 1
+            for k in ("board", "active_tetromino_mask", "queue"):
+                assert np.array_equal(o_ref[k], o_orc[k]), f"{k} ep{ep} t{t} a{a}"
+            held = len(env.holder.get_tetrominoes())
+            assert held == orc.holder_len(), f"held ep{ep} t{t}"
+            h_ref, h_orc = o_ref["holder"], o_orc["holder"]
+            assert h_orc.shape == (4, 4 * holder_size)
+            if held == 0:
+                assert h_ref.shape == h_orc.shape and np.array_equal(h_ref, h_orc)
+            else:
+                assert h_ref.shape == (4, 4 * held) and np.array_equal(h_ref, h_orc[:, :4 * held]) and np.all(h_orc[:, 4 * held:] == 1), f"holder ep{ep} t{t}"
+            assert float(r_ref) == r_orc and bool(term_ref) == term_orc and int(info_ref["lines_cleared"]) == info_orc["lines_cleared"]
+            assert (env.x, env.y, bool(env.has_swapped)) == (orc.scalars()["x"], orc.scalars()["y"], orc.scalars()["has_swapped"])
+            assert np.array_equal(env.active_tetromino.matrix, orc.active_matrix())
+            if t % 5 == 0 and queue_size >= holder_size:
+                assert np.array_equal(rgbw.observation(o_ref), orc.rgb()), f"rgb ep{ep} t{t}"
+            if term_ref:
+                break
+    return n_steps
+
+
 def check_grouped(ref, episodes, width, height, gravity, queue_size, seed0, use_features, terminate_on_illegal, max_steps=600, greedy=False):
     from .make_golden import greedy_action
 
@@ -191,6 +235,10 @@ def run(scale=1):
     n += check_base(ref, 3 * scale, 13, 9, True, 3, 6, injected=True)
     n += check_base(ref, 3 * scale, 10, 20, True, 4, 7, injected=False, true_random=True)
     n += check_base(ref, 2 * scale, 10, 20, False, 7, 8, injected=False, true_random=True, max_steps=1200)
+    n += check_holder(ref, 3 * scale, 2, 10, 20, True, 4, 31)
+    n += check_holder(ref, 2 * scale, 3, 10, 20, False, 4, 32, max_steps=800)
+    n += check_holder(ref, 2 * scale, 4, 10, 20, True, 7, 33)
+    n += check_holder(ref, 1 * scale, 2, 20, 40, True, 5, 34)
     g = 0
     g += check_grouped(ref, 4 * scale, 10, 20, False, 4, 11, True, True)
     g += check_grouped(ref, 3 * scale, 10, 20, False, 4, 12, False, False)

@@ -46,10 +46,16 @@ def pack_records(envs):
         p = s["active"]
         r = rotation_of(p, e.active_matrix())
         hold, hold_r = 0, 0
-        hm = e.held_matrix()
-        if hm is not None:
-            hold = s["holder"] + 1
-            hold_r = rotation_of(s["holder"], hm)
+        if e.holder_size > 1:      # FIFO word: count | slots (piece | rotation << 3), oldest first
+            hq = 0
+            for k, (idx, m) in enumerate(e.held_slots()):
+                hq |= (idx | (rotation_of(idx, m) << 3)) << (3 + 5 * k)
+            hot[i, 7] = hq | e.holder_len()
+        else:
+            hm = e.held_matrix()
+            if hm is not None:
+                hold = s["holder"] + 1
+                hold_r = rotation_of(s["holder"], hm)
         hot[i, 0] = s["x"] | (s["y"] << 6) | (p << 13) | (r << 16) | (hold << 18) | (hold_r << 22)
         q = 0
         for k, v in enumerate(s["queue"]):
@@ -62,11 +68,11 @@ def pack_records(envs):
     return hot.view(np.uint8).reshape(len(envs), 32), brd
 
 
-def expand(W, H, Q, hot, brd, threads=2, misalign=0):
+def expand(W, H, Q, hot, brd, threads=2, misalign=0, holder_size=1):
     n = len(hot)
     L = _lib.load()
     cfg = _lib.TgConfig()
-    cfg.width, cfg.height, cfg.queue_size = W, H, Q
+    cfg.width, cfg.height, cfg.queue_size, cfg.holder_size = W, H, Q, holder_size
     for i in range(8):
         cfg.action_map[i] = i
     Hp, Wp = H + 4, W + 8
@@ -76,7 +82,7 @@ def expand(W, H, Q, hot, brd, threads=2, misalign=0):
         off = (-raw.ctypes.data) % 64 + misalign
         return raw[off:off + int(np.prod(shape))].reshape(shape)
 
-    out = {"board": buf((n, Hp, Wp)), "active_tetromino_mask": buf((n, Hp, Wp)), "holder": buf((n, 4, 4)), "queue": buf((n, 4, 4 * Q))}
+    out = {"board": buf((n, Hp, Wp)), "active_tetromino_mask": buf((n, Hp, Wp)), "holder": buf((n, 4, 4 * holder_size)), "queue": buf((n, 4, 4 * Q))}
     ho = _lib.TgObs(out["board"].ctypes.data, out["active_tetromino_mask"].ctypes.data, out["holder"].ctypes.data, out["queue"].ctypes.data)
     hot = np.ascontiguousarray(hot)
     brd = np.ascontiguousarray(brd)
@@ -105,6 +111,25 @@ def test_expand_matches_oracle_obs(W, H, Q, n, steps, misalign):
             for k in got:
                 w = np.stack([o[k] for o in want])
                 assert np.array_equal(got[k], w), (k, t, np.flatnonzero((got[k] != w).reshape(n, -1).any(1))[:5])
+
+
+@pytest.mark.parametrize("S,n", [(2, 200), (3, 131), (4, 64)])
+def test_expand_with_a_fifo_holder(S, n):
+    rng = np.random.default_rng(S)
+    envs = [OracleEnv(queue_size=4, holder_size=S) for _ in range(n)]
+    for e in envs:
+        e.set_sequence(rng.integers(0, 7, size=64).astype(np.uint8))
+        e.reset()
+    for t in range(60):
+        for e in envs:
+            if not e.scalars()["game_over"]:
+                e.step(int(rng.choice([0, 1, 3, 5, 6, 6, 6, 7])))
+        if t % 6 == 5:
+            hot, brd = pack_records(envs)
+            got = expand(10, 20, 4, hot, brd, holder_size=S)
+            want = [e.obs() for e in envs]
+            for k in got:
+                assert np.array_equal(got[k], np.stack([o[k] for o in want])), (k, t)
 
 
 def test_expand_game_over_piece_not_projected():

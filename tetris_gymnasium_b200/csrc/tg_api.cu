@@ -188,6 +188,7 @@ static int upload_tables(tg_env* env) {
 static void make_expand_cfg(const DevCfg& d, const HostTables& T, tgh::ExpandCfg& x) {
     memset(&x, 0, sizeof x);
     x.W = d.W; x.H = d.H; x.Wp = d.Wp; x.Hp = d.Hp; x.Q = d.Q; x.OB = d.OB; x.OQ = d.OQ;
+    x.holder_size = d.holder_size; x.OH = d.OH; x.hdr = 12;
     x.board_stride = d.board_stride; x.ids_off = d.ids_off; x.ids_bytes = (d.H * d.W + 1) / 2;
     for (int p = 0; p < 7; p++) {
         x.n[p] = kN[p];
@@ -218,6 +219,7 @@ static int validate_cfg(const tg_config* cfg) {
     if (cfg->rng_mode < 0 || cfg->rng_mode > 2) return fail(nullptr, TG_ERR_CONFIG, "rng_mode %d", cfg->rng_mode);
     if (cfg->randomizer < 0 || cfg->randomizer > 1) return fail(nullptr, TG_ERR_CONFIG, "randomizer %d", cfg->randomizer);
     if (cfg->autoreset < 0 || cfg->autoreset > 2) return fail(nullptr, TG_ERR_CONFIG, "autoreset %d", cfg->autoreset);
+    if (cfg->holder_size < 0 || cfg->holder_size > 4) return fail(nullptr, TG_ERR_CONFIG, "holder_size %d unsupported (1..4)", cfg->holder_size);
     if (cfg->rng_mode == TG_RNG_SEQUENCE && cfg->seq_len < 1) return fail(nullptr, TG_ERR_CONFIG, "seq_len must be >= 1");
     for (int i = 0; i < 8; i++)
         if (cfg->action_map[i] < 0 || cfg->action_map[i] >= 8)
@@ -240,7 +242,9 @@ static void derive_cfg(const tg_config* cfg, DevCfg& d) {
     d.board_stride = bs;
     d.rng_stride = cfg->rng_mode == TG_RNG_NUMPY ? 48 : 16;
     d.OB = d.Hp * d.Wp; d.OQ = 16 * d.Q; d.A = 4 * d.W; d.F = d.W + 3;
-    d.rgb_w = d.Wp + 4 * (d.Q > 1 ? d.Q : 1);
+    d.holder_size = cfg->holder_size > 0 ? cfg->holder_size : 1;
+    d.OH = 16 * d.holder_size;
+    d.rgb_w = d.Wp + 4 * (d.Q > d.holder_size ? d.Q : d.holder_size);   // max(holder, queue) pieces wide (wrappers/observation.py:49-58)
     for (int p = 0; p < 7; p++) d.spawn_x[p] = d.Wp / 2 - kN[p] / 2;
     // elif chain of Tetris.step (envs/tetris.py:223-256): first matching name wins
     static const int order[8] = {0, 1, 2, 3, 4, 6, 5, 7};  // left,right,down,cw,ccw,swap,hard_drop,no_op
@@ -289,9 +293,9 @@ extern "C" int tg_create(const tg_config* cfg, int device, tg_env** out) {
     tg_layout& L = env->layout;
     memset(&L, 0, sizeof L);
     L.width_padded = d.Wp; L.height_padded = d.Hp; L.hot_stride = 32; L.board_stride = d.board_stride;
-    L.rng_stride = d.rng_stride; L.obs_board_bytes = d.OB; L.obs_holder_bytes = 16; L.obs_queue_bytes = d.OQ;
+    L.rng_stride = d.rng_stride; L.obs_board_bytes = d.OB; L.obs_holder_bytes = d.OH; L.obs_queue_bytes = d.OQ;
     L.n_placements = d.A; L.n_features = d.F; L.rgb_width = d.rgb_w;
-    L.host_record_bytes = (12 + d.ids_words * 4 + 15) / 16 * 16;
+    L.host_record_bytes = ((d.holder_size > 1 ? 16 : 12) + d.ids_words * 4 + 15) / 16 * 16;
 
     env->tile = 32;
     env->threads_per_env = 4;
@@ -308,10 +312,12 @@ extern "C" int tg_create(const tg_config* cfg, int device, tg_env** out) {
     int rc = upload_tables(env);
     if (rc != TG_OK) { g_create_err = env->err; delete env; return rc; }
     make_expand_cfg(env->dev, env->tabs, env->xcfg);
-    env->pk_bytes = (12 + env->dev.ids_words * 4 + 15) / 16 * 16;
+    const int hdr = env->dev.holder_size > 1 ? 16 : 12;          // hot words 0, 2, 3 (+ the holder FIFO word)
+    env->pk_bytes = (hdr + env->dev.ids_words * 4 + 15) / 16 * 16;
     env->xcfg_pk = env->xcfg;
     env->xcfg_pk.board_stride = env->pk_bytes;
-    env->xcfg_pk.ids_off = 12;
+    env->xcfg_pk.ids_off = hdr;
+    env->xcfg_pk.hdr = hdr;
     *out = env;
     return TG_OK;
 }
@@ -409,7 +415,7 @@ static int build_plan(tg_env* env, StepPlan& pl, int mode, bool want_obs, int fo
         const size_t img_e = (ws && !want_obs) ? 0 : (size_t)E;   // image buffers only when the dict is written
         p.off_iboard = take(img_e * d.OB + 16);
         p.off_imask = take(img_e * d.OB + 16);
-        p.off_iholder = take(img_e * 16 + 16);
+        p.off_iholder = take(img_e * d.OH + 16);
         p.off_iqueue = take(img_e * d.OQ + 16);
         p.off_bar = take(8 * 16);
         p.off_box = take((size_t)(2 * NS + 1) * E * 4);
@@ -564,7 +570,7 @@ extern "C" int tg_step_n(tg_env* env, tg_state st, int64_t n, int32_t k_steps, c
             p.off_rng = take((size_t)TL * p.st_rng);
             p.off_iboard = take((size_t)E * d.OB + 16);
             p.off_imask = take((size_t)E * d.OB + 16);
-            p.off_iholder = take((size_t)E * 16 + 16);
+            p.off_iholder = take((size_t)E * d.OH + 16);
             p.off_iqueue = take((size_t)E * d.OQ + 16);
             p.off_bar = take(16);
             p.off_box = take((size_t)(TL + 1) * E * 4);
@@ -605,7 +611,7 @@ extern "C" int tg_step_n(tg_env* env, tg_state st, int64_t n, int32_t k_steps, c
         pk.n = n; pk.hot = (uint8_t*)st.hot; pk.board = (uint8_t*)st.board; pk.rng = (uint8_t*)st.rng; pk.seq = st.piece_seq;
         pk.actions = d_actions + (int64_t)k * n;
         const int64_t ob = (int64_t)k * obs_stride, oo = (int64_t)k * out_stride;
-        pk.o_board = obs.board + ob * d.OB; pk.o_mask = obs.mask + ob * d.OB; pk.o_holder = obs.holder + ob * 16; pk.o_queue = obs.queue + ob * d.OQ;
+        pk.o_board = obs.board + ob * d.OB; pk.o_mask = obs.mask + ob * d.OB; pk.o_holder = obs.holder + ob * d.OH; pk.o_queue = obs.queue + ob * d.OQ;
         pk.reward = out.reward + oo; pk.terminated = out.terminated + oo; pk.truncated = out.truncated + oo; pk.lines = out.lines + oo;
         pk.stats = (double*)d_stats;
         pk.mode = 0;
@@ -657,7 +663,7 @@ static int host_chunk_step(tg_env* env, const tg_state& st, int64_t b, int64_t m
     p.hot = (uint8_t*)st.hot + b * 32; p.board = (uint8_t*)st.board + b * d.board_stride; p.rng = (uint8_t*)st.rng + b * d.rng_stride;
     p.seq = st.piece_seq ? st.piece_seq + b * d.seq_len : nullptr;
     p.actions = s_act + b;
-    if (d_obs.board) { p.o_board = d_obs.board + b * d.OB; p.o_mask = d_obs.mask + b * d.OB; p.o_holder = d_obs.holder + b * 16; p.o_queue = d_obs.queue + b * d.OQ; }
+    if (d_obs.board) { p.o_board = d_obs.board + b * d.OB; p.o_mask = d_obs.mask + b * d.OB; p.o_holder = d_obs.holder + b * d.OH; p.o_queue = d_obs.queue + b * d.OQ; }
     p.reward = s_rew + b; p.terminated = s_term + b; p.truncated = s_trunc + b; p.lines = s_lines + b;
     p.mode = 0;
     DevCfg saved = env->dev;
@@ -734,7 +740,7 @@ extern "C" int tg_step_host(tg_env* env, tg_state st, int64_t n, const int32_t* 
         if (const char* t = getenv("TG_HOST_CHUNKS")) { int v = atoi(t); if (v >= 1 && v <= 64) NCH = v; }
         int64_t chunk = (n + NCH - 1) / NCH;
         chunk = (chunk + 127) / 128 * 128;  // keeps every chunk's base 16-byte aligned in all arrays
-        const size_t o_mask = r16((size_t)n * d.OB), o_holder = o_mask + r16((size_t)n * d.OB), o_queue = o_holder + (size_t)n * 16;
+        const size_t o_mask = r16((size_t)n * d.OB), o_holder = o_mask + r16((size_t)n * d.OB), o_queue = o_holder + (size_t)n * d.OH;
         const size_t obs_total = o_queue + (size_t)n * d.OQ;
         rc = ensure_stage(env, 1, obs_total); if (rc) return rc;       // observation dict
         tg_obs d_obs;
@@ -746,7 +752,7 @@ extern "C" int tg_step_host(tg_env* env, tg_state st, int64_t n, const int32_t* 
             rc = host_chunk_step(env, st, b, m, h_actions, s_act, d_obs, s_rew, s_lines, s_term, s_trunc, s); if (rc) return rc;
             CUDA_TRY(env, cudaMemcpyAsync(h_obs.board + b * d.OB, d_obs.board + b * d.OB, (size_t)m * d.OB, cudaMemcpyDeviceToHost, s));
             CUDA_TRY(env, cudaMemcpyAsync(h_obs.mask + b * d.OB, d_obs.mask + b * d.OB, (size_t)m * d.OB, cudaMemcpyDeviceToHost, s));
-            CUDA_TRY(env, cudaMemcpyAsync(h_obs.holder + b * 16, d_obs.holder + b * 16, (size_t)m * 16, cudaMemcpyDeviceToHost, s));
+            CUDA_TRY(env, cudaMemcpyAsync(h_obs.holder + b * d.OH, d_obs.holder + b * d.OH, (size_t)m * d.OH, cudaMemcpyDeviceToHost, s));
             CUDA_TRY(env, cudaMemcpyAsync(h_obs.queue + b * d.OQ, d_obs.queue + b * d.OQ, (size_t)m * d.OQ, cudaMemcpyDeviceToHost, s));
             CUDA_TRY(env, cudaMemcpyAsync(h_out.reward + b, s_rew + b, (size_t)m * 4, cudaMemcpyDeviceToHost, s));
             CUDA_TRY(env, cudaMemcpyAsync(h_out.lines + b, s_lines + b, (size_t)m * 4, cudaMemcpyDeviceToHost, s));
@@ -795,7 +801,7 @@ extern "C" int tg_step_host(tg_env* env, tg_state st, int64_t n, const int32_t* 
             {
                 const int64_t words = m * (pk / 4);
                 k_pack_host<<<(unsigned)((words + 255) / 256), 256, 0, s>>>((const uint8_t*)st.hot + b * 32, (const uint8_t*)st.board + b * d.board_stride,
-                                                                          d.board_stride, d.ids_off, d.ids_words, pk / 4, m, (uint32_t*)dpk);
+                                                                          d.board_stride, d.ids_off, d.ids_words, pk / 4, env->xcfg_pk.hdr / 4, m, (uint32_t*)dpk);
                 CUDA_TRY(env, cudaGetLastError());
             }
             CUDA_TRY(env, cudaMemcpyAsync(ring, dpk, (size_t)m * pk, cudaMemcpyDeviceToHost, s));

@@ -63,17 +63,17 @@ __global__ void k_seed_numpy_seeds(uint8_t* rng, int stride, int64_t n, const ui
 }
 
 // Compact host step (tg_step_host, TG_HOST_COMPACT): what the observation dict is a function of, packed for the PCIe link --
-// per env `pk` bytes = hot words 0, 2, 3 (position / piece / rotation / holder, queue) followed by the nibble id plane.
-// One warp copies 32 / (pk / 4) ... simply: thread = (env, word), coalesced word stores.
+// per env `pk` bytes = hot words 0, 2, 3 (position / piece / rotation / holder, queue; plus word 7, the holder FIFO, when
+// holder_size > 1) followed by the nibble id plane.  Thread = (env, word), coalesced word stores.
 __global__ void k_pack_host(const uint8_t* __restrict__ hot, const uint8_t* __restrict__ board, int board_stride, int ids_off,
-                            int ids_words, int pk_words, int64_t n, uint32_t* __restrict__ out) {
+                            int ids_words, int pk_words, int hdr_words, int64_t n, uint32_t* __restrict__ out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n * pk_words) return;
     const int64_t e = i / pk_words;
     const int w = (int)(i - e * pk_words);
     uint32_t v = 0;
-    if (w < 3) v = ((const uint32_t*)(hot + e * 32))[w == 0 ? 0 : w + 1];
-    else if (w - 3 < ids_words) v = ((const uint32_t*)(board + e * board_stride + ids_off))[w - 3];
+    if (w < hdr_words) v = ((const uint32_t*)(hot + e * 32))[w == 0 ? 0 : (w == 3 ? 7 : w + 1)];     // hot words 0, 2, 3 (, 7)
+    else if (w - hdr_words < ids_words) v = ((const uint32_t*)(board + e * board_stride + ids_off))[w - hdr_words];
     out[i] = v;
 }
 
@@ -85,8 +85,18 @@ __global__ void k_get_state(const DevCfg cfg, int64_t n, const uint8_t* hot, con
     Hot h;
     hot_load(h, (const uint32_t*)(hot + e * 32));
     if (o_scalars) {
-        int32_t* s = o_scalars + e * (8 + cfg.Q);
+        const int HS = cfg.holder_size, NSC = 8 + cfg.Q + (HS > 1 ? 2 * HS : 0);
+        int32_t* s = o_scalars + e * NSC;
         s[0] = h.x; s[1] = h.y; s[2] = h.p; s[3] = h.r; s[4] = h.hold ? h.hold - 1 : -1; s[5] = h.hold_r;
+        if (HS > 1) {   // columns 4 / 5: number of held pieces / 0; the (piece, rotation) pairs follow the queue, oldest first
+            const int cnt = (int)(h.hq & 7u);
+            s[4] = cnt; s[5] = 0;
+            for (int k = 0; k < HS; k++) {
+                const uint32_t sl = (h.hq >> (3 + 5 * k)) & 31u;
+                s[8 + cfg.Q + 2 * k] = k < cnt ? (int)(sl & 7u) : -1;
+                s[8 + cfg.Q + 2 * k + 1] = k < cnt ? (int)(sl >> 3) : 0;
+            }
+        }
         s[6] = h.swapped; s[7] = h.over;
         for (int q = 0; q < cfg.Q; q++) s[8 + q] = (int)((h.queue >> (4 * q)) & 15u);
     }
@@ -116,11 +126,24 @@ __global__ void k_set_state(const DevCfg cfg, int64_t n, uint8_t* hot, uint8_t* 
     if (i_scalars) {
         Hot h;
         hot_load(h, (const uint32_t*)(hot + e * 32));
-        const int32_t* s = i_scalars + e * (8 + cfg.Q);
+        const int HS = cfg.holder_size, NSC = 8 + cfg.Q + (HS > 1 ? 2 * HS : 0);
+        const int32_t* s = i_scalars + e * NSC;
         // out-of-range pokes are clamped into the record's bit fields (x: 6 bits inside the padded width, y: 7 bits inside the
         // padded height, piece 0..6): a bad value must not spill into the neighbouring fields or index past the piece tables
         h.x = min(max(s[0], 0), cfg.Wp - 1); h.y = min(max(s[1], 0), cfg.Hp - 1); h.p = min(max(s[2], 0), 6); h.r = s[3] & 3;
         h.hold = s[4] < 0 ? 0 : min(s[4], 6) + 1; h.hold_r = s[5] & 3;
+        if (HS > 1) {
+            h.hold = 0; h.hold_r = 0;
+            uint32_t slots = 0;
+            int cnt = 0;
+            for (int k = 0; k < HS; k++) {
+                const int pc = s[8 + cfg.Q + 2 * k];
+                if (pc < 0) break;
+                slots |= (uint32_t)(min(pc, 6) | ((s[8 + cfg.Q + 2 * k + 1] & 3) << 3)) << (5 * cnt);
+                cnt++;
+            }
+            h.hq = (slots << 3) | (uint32_t)cnt;
+        }
         h.swapped = s[6] != 0; h.over = s[7] != 0;
         h.pending = 0;
         h.queue = 0;

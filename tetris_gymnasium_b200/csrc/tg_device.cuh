@@ -36,7 +36,9 @@ struct DevCfg {
     int OB;            // obs board bytes = Hp*Wp
     int OQ;            // obs queue bytes = 16*Q
     int A, F;          // placements 4W, features W+3
-    int rgb_w;         // Wp + 4*max(Q,1)
+    int rgb_w;         // Wp + 4*max(Q, holder_size, 1)
+    int holder_size;   // TetrominoHolder(size): 1..4
+    int OH;            // obs holder bytes = 16 * holder_size
     int spawn_x[7];    // W_pad//2 - n//2  (Tetris.reset_tetromino_position, envs/tetris.py:536-541)
     unsigned char op_lut[8];    // action id -> Op following the elif order of envs/tetris.py:223-256
     unsigned char skipgrav[8];  // action == actions.hard_drop (envs/tetris.py:259)
@@ -76,6 +78,7 @@ __device__ __forceinline__ Tabs const_tabs() {
 struct Hot {
     int x, y, p, r, hold, hold_r, swapped, over, pending;
     uint32_t bag;  // 7 nibbles + index in bits 28..30
+    uint32_t hq;   // holder_size > 1: FIFO of held pieces -- bits 0..2 count, slot k (0 = oldest) at bits 3 + 5k: piece | rotation << 3
     uint64_t queue;
     float ep_ret;
     uint32_t ep_len, ep_lines;
@@ -88,6 +91,7 @@ __device__ __forceinline__ void hot_load(Hot& h, const uint32_t* w) {
     h.bag = w[1];
     h.queue = (uint64_t)w[2] | ((uint64_t)w[3] << 32);
     h.ep_ret = __uint_as_float(w[4]); h.ep_len = w[5]; h.ep_lines = w[6];
+    h.hq = w[7];
 }
 __device__ __forceinline__ void hot_store(const Hot& h, uint32_t* w) {
     w[0] = (uint32_t)h.x | ((uint32_t)h.y << 6) | ((uint32_t)h.p << 13) | ((uint32_t)h.r << 16) |
@@ -95,7 +99,7 @@ __device__ __forceinline__ void hot_store(const Hot& h, uint32_t* w) {
            ((uint32_t)h.over << 25) | ((uint32_t)h.pending << 26);
     w[1] = h.bag;
     w[2] = (uint32_t)h.queue; w[3] = (uint32_t)(h.queue >> 32);
-    w[4] = __float_as_uint(h.ep_ret); w[5] = h.ep_len; w[6] = h.ep_lines; w[7] = 0;
+    w[4] = __float_as_uint(h.ep_ret); w[5] = h.ep_len; w[6] = h.ep_lines; w[7] = h.hq;
 }
 
 // ---- column bitboards -----------------------------------------------------------------------
@@ -288,7 +292,7 @@ __device__ __forceinline__ void env_reset(const DevCfg& cfg, Hot& h, uint32_t* r
     for (int i = 0; i < cfg.Q; i++) h.queue |= (uint64_t)draw_piece(cfg, g, h) << (4 * i);
     h.p = queue_pop(cfg, g, h);
     h.r = 0; h.x = cfg.spawn_x[h.p]; h.y = 0;
-    h.hold = 0; h.hold_r = 0; h.swapped = 0;
+    h.hold = 0; h.hold_r = 0; h.swapped = 0; h.hq = 0;
     h.ep_ret = 0.f; h.ep_len = 0; h.ep_lines = 0;
 }
 
@@ -323,6 +327,30 @@ __device__ __noinline__ void clear_rows(const DevCfg& cfg, COLT* cols, uint32_t*
         }
         cols[c] = v;
     }
+}
+
+// TetrominoHolder.swap for size > 1 (components/tetromino_holder.py:31-49): a FIFO -- while it is not full the piece is stored
+// and nothing comes back; once full the oldest piece comes back.  Values in, values out (out of line: rare, and the step
+// kernel's speed depends on its code footprint).  Returns new hq | (1 + piece + 8 * rotation of the piece handed back, 0 = none) << 32.
+__device__ __noinline__ uint64_t holder_fifo_swap(uint32_t hq, int size, int p, int r) {
+    int cnt = (int)(hq & 7u);
+    uint32_t slots = hq >> 3, back = 0;
+    if (cnt >= size) {
+        back = 1u + (slots & 31u);          // oldest: piece | rotation << 3
+        slots >>= 5;
+        cnt--;
+    }
+    slots |= (uint32_t)(p | (r << 3)) << (5 * cnt);
+    cnt++;
+    return (uint64_t)((slots << 3) | (uint32_t)cnt) | ((uint64_t)back << 32);
+}
+
+// Row i of the holder image's slot s (Tetris._get_obs, envs/tetris.py:578-592): the held piece's matrix row as four id bytes,
+// ones for an empty slot.  rowbytes = [(piece * 4 + rotation) * 4 + row].
+__device__ __forceinline__ uint32_t holder_row(const DevCfg& cfg, const Hot& h, const uint32_t* rowbytes, int s, int i) {
+    if (cfg.holder_size <= 1) return h.hold ? rowbytes[((h.hold - 1) * 4 + h.hold_r) * 4 + i] : 0x01010101u;
+    const uint32_t sl = (h.hq >> (3 + 5 * s)) & 31u;
+    return s < (int)(h.hq & 7u) ? rowbytes[((int)(sl & 7u) * 4 + (int)(sl >> 3)) * 4 + i] : 0x01010101u;
 }
 
 struct StepResult {
@@ -384,9 +412,17 @@ __device__ __forceinline__ void env_step(const DevCfg& cfg, const Tabs& tb, Hot&
     if ((unsigned)action < 8u) { op = cfg.op_lut[action]; skipgrav = cfg.skipgrav[action]; }
     if (op == OP_SWAP && !h.swapped) {  // envs/tetris.py:242-252 + TetrominoHolder.swap
         int np, nr;
-        if (h.hold == 0) { np = queue_pop(cfg, g, h); nr = 0; }
-        else { np = h.hold - 1; nr = h.hold_r; }
-        h.hold = h.p + 1; h.hold_r = h.r;
+        if (cfg.holder_size > 1) {
+            const uint64_t res = holder_fifo_swap(h.hq, cfg.holder_size, h.p, h.r);
+            h.hq = (uint32_t)res;
+            const uint32_t back = (uint32_t)(res >> 32);
+            if (back == 0) { np = queue_pop(cfg, g, h); nr = 0; }
+            else { np = (int)((back - 1) & 7u); nr = (int)((back - 1) >> 3); }
+        } else {
+            if (h.hold == 0) { np = queue_pop(cfg, g, h); nr = 0; }
+            else { np = h.hold - 1; nr = h.hold_r; }
+            h.hold = h.p + 1; h.hold_r = h.r;
+        }
         h.p = np; h.r = nr; h.swapped = 1;
         h.x = cfg.spawn_x[np]; h.y = 0;
     }

@@ -14,6 +14,8 @@ namespace tgh {
 struct ExpandCfg {
     int W, H, Wp, Hp, Q;
     int OB, OQ;          // bytes per env of the board / mask image and of the queue image
+    int holder_size, OH; // TetrominoHolder(size) and bytes per env of the holder image (16 * size)
+    int hdr;             // packed link records: bytes of hot words in front of the id plane (12, or 16 with the holder FIFO word)
     int board_stride;    // bytes per env of the packed board record
     int ids_off;         // byte offset of the nibble id plane inside a board record
     int ids_bytes;       // bytes of the id plane that hold cells (ceil(H * W / 2))

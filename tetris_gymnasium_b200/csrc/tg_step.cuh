@@ -338,11 +338,24 @@ __device__ __forceinline__ void fill_images(const DevCfg& cfg, int nv, const uin
         uint32_t* qo = (uint32_t*)i_queue + e * 4 * Q + q;
         qo[0] = rb.x; qo[Q] = rb.y; qo[2 * Q] = rb.z; qo[3 * Q] = rb.w;
     }
-    for (int it = t; it < nv * 4; it += nt) {
-        int e = it >> 2, i = it & 3;
-        uint32_t w0 = s_hot[e * 8];
-        int hold = (w0 >> 18) & 15, hr = (w0 >> 22) & 3;
-        ((uint32_t*)i_holder)[it] = hold ? s_rowbytes[((hold - 1) * 4 + hr) * 4 + i] : 0x01010101u;
+    if (cfg.holder_size <= 1) {
+        for (int it = t; it < nv * 4; it += nt) {
+            int e = it >> 2, i = it & 3;
+            uint32_t w0 = s_hot[e * 8];
+            int hold = (w0 >> 18) & 15, hr = (w0 >> 22) & 3;
+            ((uint32_t*)i_holder)[it] = hold ? s_rowbytes[((hold - 1) * 4 + hr) * 4 + i] : 0x01010101u;
+        }
+    } else {   // holder_size > 1: the held pieces side by side, oldest first; ones in the empty slots
+        const int S = cfg.holder_size;
+        for (int it = t; it < nv * 4; it += nt) {
+            int e = it >> 2, i = it & 3;
+            const uint32_t hq = s_hot[e * 8 + 7];
+            const int cnt = (int)(hq & 7u);
+            for (int s = 0; s < S; s++) {
+                const uint32_t sl = (hq >> (3 + 5 * s)) & 31u;
+                ((uint32_t*)i_holder)[it * S + s] = s < cnt ? s_rowbytes[((int)(sl & 7u) * 4 + (int)(sl >> 3)) * 4 + i] : 0x01010101u;
+            }
+        }
     }
 }
 // active piece overlay + bounding-box mask (Tetris._get_obs, envs/tetris.py:566-576)
@@ -470,7 +483,7 @@ __global__ void __launch_bounds__(256) k_step(const __grid_constant__ StepParams
             tile_store(p.o_board + base * OB, i_board, (uint32_t)(nv * OB), leader, tid, T);
             tile_store(p.o_mask + base * OB, i_mask, (uint32_t)(nv * OB), leader, tid, T);
             if (leader) {
-                bulk_s2g(p.o_holder + base * 16, i_holder, (uint32_t)(nv * 16));
+                bulk_s2g(p.o_holder + base * cfg.OH, i_holder, (uint32_t)(nv * cfg.OH));
                 bulk_s2g(p.o_queue + base * OQ, i_queue, (uint32_t)(nv * OQ));
             }
         }
@@ -653,7 +666,7 @@ __global__ void __launch_bounds__(256) k_step_ws(const __grid_constant__ StepPar
                 tile_store<true>(p.o_board + base * OB, i_board, (uint32_t)(nv * OB), leader, ft, FT);
                 tile_store<true>(p.o_mask + base * OB, i_mask, (uint32_t)(nv * OB), leader, ft, FT);
                 if (leader) {
-                    bulk_s2g_stream(p.o_holder + base * 16, i_holder, (uint32_t)(nv * 16));
+                    bulk_s2g_stream(p.o_holder + base * cfg.OH, i_holder, (uint32_t)(nv * cfg.OH));
                     bulk_s2g_stream(p.o_queue + base * OQ, i_queue, (uint32_t)(nv * OQ));
                 }
             }

@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(256) k_step_resident(const __grid_constant__ S
                 tile_store<true>(p.o_board + ob * OB, i_board, (uint32_t)(nv * OB), leader, ft, FT);
                 tile_store<true>(p.o_mask + ob * OB, i_mask, (uint32_t)(nv * OB), leader, ft, FT);
                 if (leader) {
-                    bulk_s2g_stream(p.o_holder + ob * 16, i_holder, (uint32_t)(nv * 16));
+                    bulk_s2g_stream(p.o_holder + ob * cfg.OH, i_holder, (uint32_t)(nv * cfg.OH));
                     bulk_s2g_stream(p.o_queue + ob * OQ, i_queue, (uint32_t)(nv * OQ));
                 }
                 bulk_commit();

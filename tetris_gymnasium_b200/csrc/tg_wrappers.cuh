@@ -515,10 +515,10 @@ __global__ void __launch_bounds__(256, 3) k_rgb(const DevCfg cfg, int64_t n, con
                 else { d[0] = (uint8_t)wv[i]; d[1] = (uint8_t)(wv[i] >> 8); d[2] = (uint8_t)(wv[i] >> 16); d[3] = (uint8_t)(wv[i] >> 24); }
             }
         }
-        if (lane >= 28) {
-            const int i = lane - 28;
-            uint32_t wv = h.hold ? s_rowbytes[((h.hold - 1) * 4 + h.hold_r) * 4 + i] : 0x01010101u;
-            uint8_t* d = pix + (Hp - P + i) * RW + Wp;
+        if (lane >= 16 && ((lane - 16) >> 2) < cfg.holder_size) {   // up to four held pieces side by side, four rows each
+            const int s = (lane - 16) >> 2, i = lane & 3;
+            const uint32_t wv = holder_row(cfg, h, s_rowbytes, s, i);
+            uint8_t* d = pix + (Hp - P + i) * RW + Wp + 4 * s;
             d[0] = (uint8_t)wv; d[1] = (uint8_t)(wv >> 8); d[2] = (uint8_t)(wv >> 16); d[3] = (uint8_t)(wv >> 24);
         }
         __syncwarp();

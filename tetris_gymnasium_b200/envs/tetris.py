@@ -88,8 +88,9 @@ class Tetris:
             raise NotImplementedError("custom pixel / tetromino sets are not supported yet (SURVEY 8 f4)")
         if padding not in (None, PADDING):
             raise ValueError("padding is derived from the tetromino set and must be 4")
-        if holder is not None and getattr(holder, "size", 1) != 1:
-            raise NotImplementedError("holder size > 1 is not supported yet (SURVEY 8 f4)")
+        holder_size = int(getattr(holder, "size", holder)) if holder is not None else 1
+        if not 1 <= holder_size <= 4:
+            raise ValueError("holder size must be 1..4")
         if queue is not None and queue_size is None:
             queue_size = int(getattr(queue, "size", queue))
         if randomizer is None and getattr(queue, "randomizer", None) is not None:
@@ -116,7 +117,7 @@ class Tetris:
         self.width_padded = self.width + 2 * self.padding
         self.height_padded = self.height + self.padding
         self.queue_size = 4 if queue_size is None else int(queue_size)
-        self.holder_size = 1
+        self.holder_size = holder_size   # > 1: a FIFO (TetrominoHolder.swap); the "holder" observation has the fixed shape (P, P * size)
         self.gravity_enabled = bool(gravity)
         self.actions, self.rewards = actions_mapping, rewards_mapping
         self.render_mode = render_mode
@@ -151,6 +152,7 @@ class Tetris:
         cfg.reward_alife, cfg.reward_clear_line = float(self.rewards.alife), float(self.rewards.clear_line)
         cfg.reward_game_over, cfg.reward_invalid_action = float(self.rewards.game_over), float(self.rewards.invalid_action)
         cfg.seq_len, cfg.env_id_offset = seq_len, self.env_id_offset
+        cfg.holder_size = self.holder_size
         self._cfg = cfg
         self._L = _lib.load()
         h = C.c_void_p()
@@ -169,7 +171,7 @@ class Tetris:
         # outputs (overwritten by every reset/step call)
         self._o_board = torch.empty((n, lay.height_padded, lay.width_padded), dtype=u8, device=dev)
         self._o_mask = torch.empty_like(self._o_board)
-        self._o_holder = torch.empty((n, PADDING, PADDING), dtype=u8, device=dev)
+        self._o_holder = torch.empty((n, PADDING, PADDING * self.holder_size), dtype=u8, device=dev)
         self._o_queue = torch.empty((n, PADDING, PADDING * self.queue_size), dtype=u8, device=dev)
         self._reward = torch.zeros(n, dtype=torch.float32, device=dev)
         self._terminated = torch.zeros(n, dtype=u8, device=dev)
@@ -353,7 +355,7 @@ class Tetris:
                     "K": K,
                     "board": torch.empty((K, n, lay.height_padded, lay.width_padded), dtype=u8, device=dev),
                     "mask": torch.empty((K, n, lay.height_padded, lay.width_padded), dtype=u8, device=dev),
-                    "holder": torch.empty((K, n, PADDING, PADDING), dtype=u8, device=dev),
+                    "holder": torch.empty((K, n, PADDING, PADDING * self.holder_size), dtype=u8, device=dev),
                     "queue": torch.empty((K, n, PADDING, PADDING * self.queue_size), dtype=u8, device=dev),
                     "reward": torch.empty((K, n), dtype=torch.float32, device=dev), "terminated": torch.empty((K, n), dtype=u8, device=dev),
                     "truncated": torch.empty((K, n), dtype=u8, device=dev), "lines": torch.empty((K, n), dtype=torch.int32, device=dev)}
@@ -410,7 +412,7 @@ class Tetris:
         return {
             "board": mk((n, lay.height_padded, lay.width_padded), torch.uint8),
             "active_tetromino_mask": mk((n, lay.height_padded, lay.width_padded), torch.uint8),
-            "holder": mk((n, PADDING, PADDING), torch.uint8),
+            "holder": mk((n, PADDING, PADDING * self.holder_size), torch.uint8),
             "queue": mk((n, PADDING, PADDING * self.queue_size), torch.uint8),
             "reward": mk((n,), torch.float32), "terminated": mk((n,), torch.uint8),
             "truncated": mk((n,), torch.uint8), "lines_cleared": mk((n,), torch.int32),
@@ -444,12 +446,19 @@ class Tetris:
         """Unpacked state: board u8[n,Hp,Wp] (locked cells), x, y, piece, rotation, holder, ... tensors."""
         n, lay = self.num_envs, self.layout
         board = torch.empty((n, lay.height_padded, lay.width_padded), dtype=torch.uint8, device=self.device)
-        sc = torch.empty((n, _lib.TG_SCALARS + self.queue_size), dtype=torch.int32, device=self.device)
+        Q, S = self.queue_size, self.holder_size
+        sc = torch.empty((n, _lib.TG_SCALARS + Q + (2 * S if S > 1 else 0)), dtype=torch.int32, device=self.device)
         _lib.check(self._L.tg_get_state(self._h, self._state(), n, board.data_ptr(), sc.data_ptr(), self._stream()), self._h)
-        return {"board": board, "x": sc[:, 0], "y": sc[:, 1], "piece": sc[:, 2], "rotation": sc[:, 3],
-                "holder_piece": sc[:, 4], "holder_rotation": sc[:, 5], "has_swapped": sc[:, 6], "game_over": sc[:, 7],
-                "queue": sc[:, 8:], "_scalars": sc,
-                "_raw": (self._hot.clone(), self._brd.clone(), self._rng.clone())}
+        st = {"board": board, "x": sc[:, 0], "y": sc[:, 1], "piece": sc[:, 2], "rotation": sc[:, 3],
+              "holder_piece": sc[:, 4], "holder_rotation": sc[:, 5], "has_swapped": sc[:, 6], "game_over": sc[:, 7],
+              "queue": sc[:, 8:8 + Q], "_scalars": sc,
+              "_raw": (self._hot.clone(), self._brd.clone(), self._rng.clone())}
+        if S > 1:   # FIFO holder: number of held pieces, then (piece, rotation) per slot, oldest first, -1 = empty slot
+            del st["holder_piece"], st["holder_rotation"]
+            st["holder_count"] = sc[:, 4]
+            st["holder_pieces"] = sc[:, 8 + Q::2]
+            st["holder_rotations"] = sc[:, 9 + Q::2]
+        return st
 
     def set_state(self, state=None, *, board=None, env_mask=None, **scalars):
         """Restore a `get_state()` snapshot, or poke fields: set_state(board=..., x=..., piece=..., ...)."""
@@ -460,9 +469,14 @@ class Tetris:
         cur = self.get_state() if state is None else state
         sc = cur["_scalars"].clone()
         names = {"x": 0, "y": 1, "piece": 2, "rotation": 3, "holder_piece": 4, "holder_rotation": 5, "has_swapped": 6, "game_over": 7}
+        Q = self.queue_size
         for k, v in scalars.items():
             if k == "queue":
-                sc[:, 8:] = torch.as_tensor(v, device=self.device).to(torch.int32)
+                sc[:, 8:8 + Q] = torch.as_tensor(v, device=self.device).to(torch.int32)
+            elif k == "holder_pieces":
+                sc[:, 8 + Q::2] = torch.as_tensor(v, device=self.device).to(torch.int32)
+            elif k == "holder_rotations":
+                sc[:, 9 + Q::2] = torch.as_tensor(v, device=self.device).to(torch.int32)
             else:
                 sc[:, names[k]] = torch.as_tensor(v, device=self.device).to(torch.int32)
         b = None
