@@ -88,7 +88,15 @@ typedef struct tg_config {
                                      are keyed by global id so results do not depend on #GPUs) */
     int32_t holder_size;          /* TetrominoHolder(size) (components/tetromino_holder.py:14-21): 1..4; 0 = 1 (the reference default).
                                      A FIFO: a swap stores the active piece and, once the holder is full, hands back the oldest one. */
-    int32_t reserved0;
+    /* Tetris(tetrominoes=[...]) (envs/tetris.py:88-89, 113-132): 0 = the reference's seven pieces; else 1..7 custom pieces, piece i
+     * an n x n matrix (piece_n[i] <= 4, row-major in piece_matrix[i], non-zero = cell) with EXACTLY FOUR cells and colour
+     * piece_color[i].  The reference derives the padding from the set (largest matrix dimension); this library is built on
+     * padding 4, so the largest matrix of the set must be 4 x 4.  Cell values on the board are i + 2 as in the reference. */
+    int32_t n_pieces;
+    uint8_t piece_n[8];
+    uint8_t piece_matrix[7][16];
+    uint8_t piece_color[7][3];
+    uint8_t reserved1[3];
 } tg_config;
 
 /* Sizes of the per-env state arrays the caller must allocate (bytes per env). */

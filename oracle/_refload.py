@@ -43,6 +43,7 @@ def load():
     if REF not in sys.path:
         sys.path.insert(0, REF)
     import tetris_gymnasium.envs  # noqa: F401  (registers the env id)
+    from tetris_gymnasium.components.tetromino import Tetromino
     from tetris_gymnasium.components.tetromino_holder import TetrominoHolder
     from tetris_gymnasium.components.tetromino_queue import TetrominoQueue
     from tetris_gymnasium.components.tetromino_randomizer import Randomizer, TrueRandomizer
@@ -80,6 +81,6 @@ def load():
             env.queue = TetrominoQueue(env.randomizer, size=queue_size)
         return env
 
-    return dict(Tetris=Tetris, make=make, TetrominoHolder=TetrominoHolder, Scripted=Scripted, TrueRandomizer=TrueRandomizer, TetrominoQueue=TetrominoQueue,
+    return dict(Tetris=Tetris, make=make, TetrominoHolder=TetrominoHolder, Tetromino=Tetromino, Scripted=Scripted, TrueRandomizer=TrueRandomizer, TetrominoQueue=TetrominoQueue,
                 GroupedActionsObservations=GroupedActionsObservations,
                 FeatureVectorObservation=FeatureVectorObservation, RgbObservation=RgbObservation)

@@ -62,6 +62,11 @@ typedef struct {
     int64_t seq_len, seq_cur;
     int8_t bag[7];
     int bag_index;
+    /* the tetromino set (Tetris(tetrominoes=...), envs/tetris.py:117-127): defaults to TETROMINOES */
+    int np;
+    int base_n[7];
+    uint8_t base_m[7][16];
+    uint8_t colors[16][3];
     uint64_t pcg_state_hi, pcg_state_lo, pcg_inc_hi, pcg_inc_lo;
     int pcg_has32;
     uint32_t pcg_u32;
@@ -83,13 +88,13 @@ static const uint8_t COLORS[9][3] = {{0, 0, 0},     {128, 128, 128}, {0, 240, 24
                                      {240, 240, 0}, {160, 0, 240},   {0, 240, 0},
                                      {240, 0, 0},   {0, 0, 240},     {240, 160, 0}};
 
-static void make_piece(orc_piece *p, int idx) {
+static void make_piece(const orc_env *e, orc_piece *p, int idx) {
     /* tetrominoes[i].matrix * (i + offset), offset = len(base_pixels) = 2 (envs/tetris.py:675-677) */
     p->idx = idx;
     p->id = idx + 2;
-    p->n = BASE_N[idx];
+    p->n = e->base_n[idx];
     memset(p->m, 0, 16);
-    for (int k = 0; k < p->n * p->n; k++) p->m[k] = (uint8_t)(BASE_M[idx][k] * (idx + 2));
+    for (int k = 0; k < p->n * p->n; k++) p->m[k] = (uint8_t)(e->base_m[idx][k] * (idx + 2));
 }
 
 /* Tetris.rotate (envs/tetris.py:429-443): np.rot90(matrix, k = 1 if clockwise else -1).
@@ -146,7 +151,7 @@ static uint32_t np_random_interval(orc_env *e, uint32_t max) {
 /* BagRandomizer.shuffle_bag (components/tetromino_randomizer.py:82-85): rng.shuffle(bag) in
  * place (Generator.shuffle -> _shuffle_raw: for i = n-1 .. 1: j = random_interval(i); swap). */
 static void shuffle_bag(orc_env *e) {
-    for (int i = 6; i >= 1; i--) {
+    for (int i = e->np - 1; i >= 1; i--) {
         int j = (int)np_random_interval(e, (uint32_t)i);
         int8_t t = e->bag[i];
         e->bag[i] = e->bag[j];
@@ -174,7 +179,7 @@ static uint32_t np_bounded_lemire32(orc_env *e, uint32_t rng) {
 /* Randomizer.get_next_tetromino */
 static int rnd_next(orc_env *e) {
     /* TrueRandomizer.get_next_tetromino (components/tetromino_randomizer.py:119-121): rng.integers(0, size) */
-    if (e->rng_mode == 2) return (int)np_bounded_lemire32(e, 6);
+    if (e->rng_mode == 2) return e->np > 1 ? (int)np_bounded_lemire32(e, (uint32_t)(e->np - 1)) : 0; /* empty range: numpy returns `low` without drawing */
     if (e->rng_mode == 0) { /* scripted stream (test injection hook) */
         int v = e->seq[e->seq_cur % e->seq_len];
         e->seq_cur++;
@@ -183,14 +188,14 @@ static int rnd_next(orc_env *e) {
     /* BagRandomizer.get_next_tetromino (components/tetromino_randomizer.py:67-80) */
     int v = e->bag[e->bag_index];
     e->bag_index++;
-    if (e->bag_index >= 7) shuffle_bag(e);
+    if (e->bag_index >= e->np) shuffle_bag(e);
     return v;
 }
 /* BagRandomizer.reset (components/tetromino_randomizer.py:87-91); the reseed itself
  * (Randomizer.reset :34-46, "if seed and seed > 0") is done by the caller via orc_seed_numpy. */
 static void rnd_reset(orc_env *e) {
     if (e->rng_mode != 1) return; /* scripted; TrueRandomizer.reset only reseeds (:123-127) */
-    for (int i = 0; i < 7; i++) e->bag[i] = (int8_t)i;
+    for (int i = 0; i < e->np; i++) e->bag[i] = (int8_t)i;
     shuffle_bag(e);
 }
 
@@ -272,7 +277,7 @@ static void reset_position(orc_env *e) {
 }
 /* Tetris.spawn_tetromino (envs/tetris.py:393-401) */
 static int spawn(orc_env *e) {
-    make_piece(&e->active, queue_pop(e));
+    make_piece(e, &e->active, queue_pop(e));
     reset_position(e);
     return !collision(e, e->board, &e->active, e->x, e->y);
 }
@@ -312,12 +317,28 @@ orc_env *orc_create(const orc_config *c) {
     e->active.idx = -1;
     e->rng_mode = 0;
     e->holder_size = 1;
+    e->np = 7;
+    for (int p = 0; p < 7; p++) {
+        e->base_n[p] = BASE_N[p];
+        memcpy(e->base_m[p], BASE_M[p], 16);
+    }
+    memcpy(e->colors, COLORS, sizeof COLORS);
     return e;
 }
 void orc_destroy(orc_env *e) {
     if (!e) return;
     free(e->board);
     free(e);
+}
+/* Tetris(tetrominoes=[...]) (envs/tetris.py:117-132): np pieces, piece i an n[i] x n[i] binary matrix (row-major in m[i]) with
+ * colour rgb[i]; board values are i + 2 (offset_tetromino_id multiplies the matrix by index + offset).  Call before reset. */
+void orc_set_tetrominoes(orc_env *e, int np, const int32_t *n, const uint8_t *m, const uint8_t *rgb) {
+    e->np = np;
+    for (int p = 0; p < np; p++) {
+        e->base_n[p] = n[p];
+        for (int k = 0; k < 16; k++) e->base_m[p][k] = m[p * 16 + k] != 0;
+        memcpy(e->colors[p + 2], rgb + 3 * p, 3);
+    }
 }
 /* TetrominoHolder(size): the reference can only get a bigger holder by assigning env.holder after construction */
 void orc_set_holder_size(orc_env *e, int size) {
@@ -380,7 +401,7 @@ void orc_get_obs(const orc_env *e, uint8_t *board, uint8_t *mask, uint8_t *holde
         memset(queue, 0, (size_t)ORC_P * QW);
         for (int q = 0; q < e->Q; q++) {
             orc_piece t;
-            make_piece(&t, e->queue[q]);
+            make_piece(e, &t, e->queue[q]);
             for (int i = 0; i < t.n; i++)
                 for (int j = 0; j < t.n; j++) queue[i * QW + q * ORC_P + j] = t.m[i * t.n + j];
         }
@@ -392,7 +413,7 @@ void orc_reset(orc_env *e) {
     create_board(e, e->board);
     e->game_over = 0;
     queue_reset(e);
-    make_piece(&e->active, queue_pop(e));
+    make_piece(e, &e->active, queue_pop(e));
     reset_position(e);
     e->holder_len = 0;
     e->has_swapped = 0;
@@ -579,7 +600,7 @@ void orc_rgb(const orc_env *e, uint8_t *out) {
                 else
                     v = 1;
             }
-            memcpy(out + ((size_t)r * OW + c) * 3, COLORS[v], 3);
+            memcpy(out + ((size_t)r * OW + c) * 3, e->colors[v & 15], 3);
         }
     free(board);
 }
@@ -608,7 +629,7 @@ void orc_get_held_matrix(const orc_env *e, int32_t *n, uint8_t *m16) {
 }
 /* set the active piece to TETROMINOES[idx] rotated `rot` times with rot90(k=+1) */
 void orc_set_active(orc_env *e, int idx, int rot, int x, int y) {
-    make_piece(&e->active, idx);
+    make_piece(e, &e->active, idx);
     for (int k = 0; k < (rot & 3); k++) rotate_piece(&e->active, &e->active, 1);
     e->x = x;
     e->y = y;
@@ -622,7 +643,7 @@ void orc_set_holder(orc_env *e, int idx, int rot) {
         e->holder_len = 0;
         return;
     }
-    make_piece(&e->held[0], idx);
+    make_piece(e, &e->held[0], idx);
     for (int k = 0; k < (rot & 3); k++) rotate_piece(&e->held[0], &e->held[0], 1);
     e->holder_len = 1;
 }

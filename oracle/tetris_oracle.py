@@ -39,7 +39,7 @@ def lib():
             "orc_grouped_observe orc_rgb orc_get_board orc_set_board orc_get_scalars "
             "orc_get_active_matrix orc_get_held_matrix orc_set_active orc_set_flags orc_set_holder "
             "orc_set_queue orc_vec_step orc_vec_grouped_step orc_rnd_stream orc_grouped_observe_ex orc_set_true_randomizer "
-            "orc_vec_create orc_vec_destroy orc_vec_seed_words orc_vec_reset orc_set_holder_size"
+            "orc_vec_create orc_vec_destroy orc_vec_seed_words orc_vec_reset orc_set_holder_size orc_set_tetrominoes"
         ).split():
             getattr(L, name).restype = None
         L.orc_step.restype = C.c_int
@@ -99,6 +99,16 @@ class OracleEnv:
             lib().orc_destroy(self.h)
         except Exception:
             pass
+
+    def set_tetrominoes(self, matrices, colors):
+        """Tetris(tetrominoes=[...]): square binary matrices (<= 4 x 4) and RGB colours; call before reset."""
+        n = np.array([len(m) for m in matrices], np.int32)
+        mm = np.zeros((len(matrices), 16), np.uint8)
+        for i, m in enumerate(matrices):
+            mm[i, : n[i] * n[i]] = (np.asarray(m) != 0).astype(np.uint8).reshape(-1)
+        rgb = np.ascontiguousarray(colors, dtype=np.uint8)
+        lib().orc_set_tetrominoes(self.h, len(matrices), _p(n), _p(mm), _p(rgb))
+        self._pieces = [np.asarray(m) != 0 for m in matrices]
 
     # -- randomizer ---------------------------------------------------------------------
     def set_sequence(self, seq, cursor=0):

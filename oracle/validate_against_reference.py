@@ -109,6 +109,72 @@ def check_holder(ref, episodes, holder_size, width, height, gravity, queue_size,
     return n_steps
 
 
+CUSTOM_SETS = {
+    # a subset of the reference's pieces with other colours (bag of three)
+    "iot": ([[[0, 0, 0, 0], [1, 1, 1, 1], [0, 0, 0, 0], [0, 0, 0, 0]], [[1, 1], [1, 1]], [[0, 1, 0], [1, 1, 1], [0, 0, 0]]],
+            [[10, 200, 30], [250, 1, 99], [77, 77, 200]]),
+    # five four-cell shapes that are not in the reference's set: a low I, an O in a corner of a 3 x 3 box, a T pointing down, two
+    # bars with a gap between them (cells of a column need not be contiguous), a long L
+    "odd5": ([[[0, 0, 0, 0], [0, 0, 0, 0], [1, 1, 1, 1], [0, 0, 0, 0]], [[1, 1, 0], [1, 1, 0], [0, 0, 0]], [[1, 1, 1], [0, 1, 0], [0, 0, 0]],
+              [[1, 1, 0], [0, 0, 0], [1, 1, 0]], [[1, 0, 0, 0], [1, 0, 0, 0], [1, 1, 0, 0], [0, 0, 0, 0]]],
+             [[1, 2, 3], [40, 50, 60], [200, 100, 0], [9, 99, 199], [255, 255, 255]]),
+    # a single piece: the bag never shuffles
+    "only_i": ([[[0, 0, 0, 0], [1, 1, 1, 1], [0, 0, 0, 0], [0, 0, 0, 0]]], [[0, 240, 240]]),
+}
+
+
+def check_custom_set(ref, name, episodes, width, height, gravity, queue_size, seed0, grouped, true_random=False, max_steps=1200):
+    """Tetris(tetrominoes=[...]) (envs/tetris.py:88-89, 117-132): custom matrices / colours / set size, seeded numpy bag of
+    len(set) pieces (or TrueRandomizer), base env + RGB image, or the grouped wrapper with features."""
+    R = ref
+    mats, cols = CUSTOM_SETS[name]
+    rng = np.random.default_rng(seed0)
+    n_steps = 0
+    for ep in range(episodes):
+        tets = [R["Tetromino"](i, list(c), np.array(m, dtype=np.uint8)) for i, (m, c) in enumerate(zip(mats, cols))]
+        env = R["Tetris"](width=width, height=height, gravity=gravity, tetrominoes=tets)
+        if true_random:
+            env.randomizer = R["TrueRandomizer"](len(tets))
+        env.queue = R["TetrominoQueue"](env.randomizer, size=queue_size)
+        orc = OracleEnv(width=width, height=height, gravity=gravity, queue_size=queue_size)
+        orc.set_tetrominoes(mats, cols)
+        if true_random:
+            orc.set_true_randomizer()
+        seed = int(rng.integers(1, 2**31))
+        if grouped:
+            g = R["GroupedActionsObservations"](env, observation_wrappers=[R["FeatureVectorObservation"](env)])
+            f_ref, info = g.reset(seed=seed)
+            orc.reset(seed=seed)
+            for t in range(max_steps):
+                f_orc, _, legal = orc.grouped_observe()
+                assert np.array_equal(np.asarray(f_ref, dtype=np.uint8), f_orc) and np.array_equal(np.asarray(info["action_mask"]).astype(np.uint8), legal), f"{name} grouped ep{ep} t{t}"
+                a = int(rng.choice(np.flatnonzero(legal))) if rng.random() > 0.05 and legal.any() else int(rng.integers(0, 4 * width))
+                f_ref, r_ref, term_ref, _, info = g.step(a)
+                code, r_orc, term_orc, l_orc = orc.grouped_step(a)
+                n_steps += 1
+                assert float(r_ref) == r_orc and bool(term_ref) == term_orc and np.array_equal(env.board, orc.board), f"{name} grouped step ep{ep} t{t}"
+                if term_ref:
+                    break
+            continue
+        rgbw = R["RgbObservation"](env)
+        o_ref, _ = env.reset(seed=seed)
+        o_orc, _ = orc.reset(seed=seed)
+        assert _same_obs(o_ref, o_orc), f"{name} reset"
+        for t in range(max_steps):
+            a = int(rng.integers(0, 8))
+            o_ref, r_ref, term_ref, _, info_ref = env.step(a)
+            o_orc, r_orc, term_orc, _, info_orc = orc.step(a)
+            n_steps += 1
+            assert _same_obs(o_ref, o_orc), f"{name} obs ep{ep} t{t} a{a}"
+            assert float(r_ref) == r_orc and bool(term_ref) == term_orc and int(info_ref["lines_cleared"]) == info_orc["lines_cleared"]
+            assert np.array_equal(env.board, orc.board) and np.array_equal(env.active_tetromino.matrix, orc.active_matrix())
+            if t % 6 == 0:
+                assert np.array_equal(rgbw.observation(o_ref), orc.rgb()), f"{name} rgb"
+            if term_ref:
+                break
+    return n_steps
+
+
 def check_grouped(ref, episodes, width, height, gravity, queue_size, seed0, use_features, terminate_on_illegal, max_steps=600, greedy=False):
     from .make_golden import greedy_action
 
@@ -239,7 +305,13 @@ def run(scale=1):
     n += check_holder(ref, 2 * scale, 3, 10, 20, False, 4, 32, max_steps=800)
     n += check_holder(ref, 2 * scale, 4, 10, 20, True, 7, 33)
     n += check_holder(ref, 1 * scale, 2, 20, 40, True, 5, 34)
+    n += check_custom_set(ref, "iot", 3 * scale, 10, 20, True, 4, 41, grouped=False)
+    n += check_custom_set(ref, "odd5", 3 * scale, 10, 20, True, 4, 42, grouped=False)
+    n += check_custom_set(ref, "odd5", 2 * scale, 12, 16, False, 7, 43, grouped=False, true_random=True)
+    n += check_custom_set(ref, "only_i", 1 * scale, 10, 20, True, 4, 44, grouped=False)
     g = 0
+    g += check_custom_set(ref, "odd5", 2 * scale, 10, 20, False, 4, 45, grouped=True, max_steps=300)
+    g += check_custom_set(ref, "iot", 2 * scale, 10, 20, False, 4, 46, grouped=True, max_steps=300)
     g += check_grouped(ref, 4 * scale, 10, 20, False, 4, 11, True, True)
     g += check_grouped(ref, 3 * scale, 10, 20, False, 4, 12, False, False)
     g += check_grouped(ref, 3 * scale, 10, 20, True, 4, 13, True, False)

@@ -31,7 +31,7 @@ def test_struct_layouts_match_header():
     from tetris_gymnasium_b200 import _lib
 
     # sizes implied by the C declarations (natural alignment)
-    assert C.sizeof(_lib.TgConfig) == 6 * 4 + 8 * 4 + 2 * 4 + 4 * 8 + 8 + 8 + 2 * 4
+    assert C.sizeof(_lib.TgConfig) == 6 * 4 + 8 * 4 + 2 * 4 + 4 * 8 + 8 + 8 + 2 * 4 + 8 + 7 * 16 + 7 * 3 + 3
     assert C.sizeof(_lib.TgLayout) == 12 * 4
     assert C.sizeof(_lib.TgState) == 4 * 8 and C.sizeof(_lib.TgObs) == 4 * 8 and C.sizeof(_lib.TgStepOut) == 4 * 8
 

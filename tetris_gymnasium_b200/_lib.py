@@ -28,7 +28,8 @@ class TgConfig(C.Structure):
         ("reward_alife", C.c_double), ("reward_clear_line", C.c_double),
         ("reward_game_over", C.c_double), ("reward_invalid_action", C.c_double),
         ("seq_len", C.c_int64), ("env_id_offset", C.c_uint64),
-        ("holder_size", C.c_int32), ("reserved0", C.c_int32),
+        ("holder_size", C.c_int32), ("n_pieces", C.c_int32),
+        ("piece_n", C.c_uint8 * 8), ("piece_matrix", (C.c_uint8 * 16) * 7), ("piece_color", (C.c_uint8 * 3) * 7), ("reserved1", C.c_uint8 * 3),
     ]
 
 

@@ -7,9 +7,9 @@ class Randomizer:
     kind = None
 
     def __init__(self, size: int = 7):
-        if size != 7:
-            raise NotImplementedError("custom tetromino sets are not supported: size must be 7")
-        self.size = size
+        if not 1 <= size <= 7:
+            raise ValueError("tetromino sets hold 1..7 pieces")
+        self.size = size    # informational: the device draws from the env's tetromino set
 
 
 class BagRandomizer(Randomizer):

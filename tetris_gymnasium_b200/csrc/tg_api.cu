@@ -23,11 +23,15 @@ using namespace tg;
 
 // piece tables on the host: uploaded to the device by upload_tables, read by the host-side dict expansion
 struct HostTables {
+    int np;                       // pieces of the set (7 for the reference's)
+    int n[7];                     // matrix sizes
+    unsigned char base[7][16];    // base matrices, n x n row-major, 0 / 1
     unsigned short cells[7][4];
     uint2 ptab[7][4];
     uint4 prec[7][4];
     unsigned int rowbytes[7][4][4];
     unsigned char colors[16][4];
+    uint64_t hash;
 };
 
 struct StepPlan {
@@ -90,7 +94,9 @@ struct DeviceGuard {
     }
     ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
-#define ON_DEVICE(env) DeviceGuard _guard((env)->device); CUDA_TRY(env, _guard.err)
+struct tg_env;
+static int ensure_env_tables(tg_env* env);
+#define ON_DEVICE(env) DeviceGuard _guard((env)->device); CUDA_TRY(env, _guard.err); { int _t = ensure_env_tables(env); if (_t) return _t; }
 
 static int fail(tg_env* env, int code, const char* fmt, ...) {
     char buf[512];
@@ -116,14 +122,35 @@ static const unsigned char kBase[7][16] = {
 static const unsigned char kColors[9][3] = {{0, 0, 0}, {128, 128, 128}, {0, 240, 240}, {240, 240, 0}, {160, 0, 240},
                                             {0, 240, 0}, {240, 0, 0}, {0, 0, 240}, {240, 160, 0}};
 
+// the piece set of a config: the reference's seven tetrominoes, or Tetris(tetrominoes=[...]) (cfg->n_pieces > 0)
+static void piece_set(const tg_config* cfg, HostTables& T) {
+    memset(&T, 0, sizeof T);
+    for (int v = 0; v < 2; v++) for (int k = 0; k < 3; k++) T.colors[v][k] = kColors[v][k];      // BASE_PIXELS: empty, bedrock
+    if (!cfg || cfg->n_pieces <= 0) {
+        T.np = 7;
+        for (int p = 0; p < 7; p++) {
+            T.n[p] = kN[p];
+            memcpy(T.base[p], kBase[p], 16);
+            for (int k = 0; k < 3; k++) T.colors[p + 2][k] = kColors[p + 2][k];
+        }
+        return;
+    }
+    T.np = cfg->n_pieces;
+    for (int p = 0; p < T.np; p++) {
+        T.n[p] = cfg->piece_n[p];
+        for (int k = 0; k < 16; k++) T.base[p][k] = cfg->piece_matrix[p][k] != 0;
+        for (int k = 0; k < 3; k++) T.colors[p + 2][k] = cfg->piece_color[p][k];
+    }
+}
+
+// fills the derived tables of T from T.np / T.n / T.base (set by piece_set)
 static int build_tables(tg_env* env, HostTables& T) {
-    auto& cells = T.cells; auto& ptab = T.ptab; auto& prec = T.prec; auto& rowbytes = T.rowbytes; auto& colors = T.colors;
-    memset(colors, 0, sizeof colors);
-    for (int v = 0; v < 9; v++) for (int k = 0; k < 3; k++) colors[v][k] = kColors[v][k];
-    for (int p = 0; p < 7; p++) {
-        int n = kN[p];
+    auto& cells = T.cells; auto& ptab = T.ptab; auto& prec = T.prec; auto& rowbytes = T.rowbytes;
+    memset(cells, 0, sizeof cells); memset(ptab, 0, sizeof ptab); memset(prec, 0, sizeof prec); memset(rowbytes, 0, sizeof rowbytes);
+    for (int p = 0; p < T.np; p++) {
+        int n = T.n[p];
         unsigned char m[16], t[16];
-        memcpy(m, kBase[p], 16);
+        memcpy(m, T.base[p], 16);
         for (int r = 0; r < 4; r++) {
             if (r > 0) {  // np.rot90(m, k=1): out[i][j] = m[j][n-1-i]  (Tetris.rotate, envs/tetris.py:429-443)
                 for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) t[i * n + j] = m[j * n + (n - 1 - i)];
@@ -168,19 +195,28 @@ static int build_tables(tg_env* env, HostTables& T) {
             prec[p][r] = make_uint4((unsigned)c | ((px & 0xFFFFu) << 16), m4, top4, (unsigned)jmin | (unsigned)jmax << 2 | mintop << 4);
         }
     }
+    // identity of the set: the constant tables are per DEVICE, shared by every handle
+    uint64_t hsh = 1469598103934665603ull;
+    auto mix = [&](const void* d, size_t nbytes) { for (size_t i = 0; i < nbytes; i++) { hsh ^= ((const unsigned char*)d)[i]; hsh *= 1099511628211ull; } };
+    mix(&T.np, sizeof T.np); mix(T.n, sizeof T.n); mix(T.base, sizeof T.base); mix(T.colors, sizeof T.colors);
+    T.hash = hsh;
     return TG_OK;
 }
 
-static int upload_tables(tg_env* env) {
-    HostTables& T = env->tabs;
-    int rc = build_tables(env, T);
-    if (rc) return rc;
+// The piece tables live in __constant__ memory: one copy per device, shared by every handle.  Handles with different piece sets
+// may coexist; whichever set the next launch needs is made resident first (after the device has drained: kernels in flight
+// still read the old tables).  Switching is rare -- it happens only when envs with different sets alternate on one device.
+static uint64_t g_resident_tables[64];
+static int ensure_tables(tg_env* env, const HostTables& T, int device) {
+    if (g_resident_tables[device & 63] == T.hash) return TG_OK;
+    CUDA_TRY(env, cudaDeviceSynchronize());
     CUDA_TRY(env, cudaMemcpyToSymbol(c_cells, T.cells, sizeof T.cells));
     CUDA_TRY(env, cudaMemcpyToSymbol(c_ptab, T.ptab, sizeof T.ptab));
     CUDA_TRY(env, cudaMemcpyToSymbol(c_prec, T.prec, sizeof T.prec));
     CUDA_TRY(env, cudaMemcpyToSymbol(c_rowbytes, T.rowbytes, sizeof T.rowbytes));
-    CUDA_TRY(env, cudaMemcpyToSymbol(c_n, kN, sizeof kN));
+    CUDA_TRY(env, cudaMemcpyToSymbol(c_n, T.n, sizeof T.n));
     CUDA_TRY(env, cudaMemcpyToSymbol(c_colors, T.colors, sizeof T.colors));
+    g_resident_tables[device & 63] = T.hash;
     return TG_OK;
 }
 
@@ -191,7 +227,7 @@ static void make_expand_cfg(const DevCfg& d, const HostTables& T, tgh::ExpandCfg
     x.holder_size = d.holder_size; x.OH = d.OH; x.hdr = 12;
     x.board_stride = d.board_stride; x.ids_off = d.ids_off; x.ids_bytes = (d.H * d.W + 1) / 2;
     for (int p = 0; p < 7; p++) {
-        x.n[p] = kN[p];
+        x.n[p] = p < T.np ? T.n[p] : 3;
         for (int r = 0; r < 4; r++) {
             x.cells[p][r] = T.cells[p][r];
             for (int i = 0; i < 4; i++) x.rowbytes[p][r][i] = T.rowbytes[p][r][i];
@@ -204,6 +240,8 @@ static void make_expand_cfg(const DevCfg& d, const HostTables& T, tgh::ExpandCfg
 extern "C" int tg_set_host_threads(tg_env* env, int32_t threads);
 
 static int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+static int ensure_env_tables(tg_env* env) { return ensure_tables(env, env->tabs, env->device); }
 
 extern "C" int tg_version(void) { return TG_VERSION; }
 
@@ -224,11 +262,24 @@ static int validate_cfg(const tg_config* cfg) {
     for (int i = 0; i < 8; i++)
         if (cfg->action_map[i] < 0 || cfg->action_map[i] >= 8)
             return fail(nullptr, TG_ERR_CONFIG, "action_map[%d] = %d outside Discrete(8)", i, cfg->action_map[i]);
+    if (cfg->n_pieces < 0 || cfg->n_pieces > 7) return fail(nullptr, TG_ERR_CONFIG, "n_pieces %d unsupported (custom sets hold 1..7 pieces)", cfg->n_pieces);
+    int max_n = cfg->n_pieces ? 0 : 4;
+    for (int p = 0; p < cfg->n_pieces; p++) {
+        const int n = cfg->piece_n[p];
+        if (n < 1 || n > 4) return fail(nullptr, TG_ERR_CONFIG, "tetromino %d: matrix size %d unsupported (1..4)", p, n);
+        int cells = 0;
+        for (int k = 0; k < n * n; k++) cells += cfg->piece_matrix[p][k] != 0;
+        if (cells != 4) return fail(nullptr, TG_ERR_CONFIG, "tetromino %d has %d cells: the kernels are built on four-cell pieces", p, cells);
+        if (n > max_n) max_n = n;
+    }
+    if (max_n != TG_PADDING)
+        return fail(nullptr, TG_ERR_CONFIG, "the tetromino set's largest matrix is %d x %d: the reference would derive padding %d from it "
+                    "(envs/tetris.py:130), this library is built on padding 4", max_n, max_n, max_n);
     return TG_OK;
 }
 
 // device config (sizes, strides, LUTs) of a validated tg_config; pure host arithmetic
-static void derive_cfg(const tg_config* cfg, DevCfg& d) {
+static void derive_cfg(const tg_config* cfg, const HostTables& T, DevCfg& d) {
     memset(&d, 0, sizeof d);
     d.W = cfg->width; d.H = cfg->height; d.Wp = d.W + 2 * TG_PADDING; d.Hp = d.H + TG_PADDING; d.Q = cfg->queue_size;
     d.gravity = cfg->gravity != 0; d.autoreset = cfg->autoreset; d.rng_mode = cfg->rng_mode;
@@ -245,7 +296,13 @@ static void derive_cfg(const tg_config* cfg, DevCfg& d) {
     d.holder_size = cfg->holder_size > 0 ? cfg->holder_size : 1;
     d.OH = 16 * d.holder_size;
     d.rgb_w = d.Wp + 4 * (d.Q > d.holder_size ? d.Q : d.holder_size);   // max(holder, queue) pieces wide (wrappers/observation.py:49-58)
-    for (int p = 0; p < 7; p++) d.spawn_x[p] = d.Wp / 2 - kN[p] / 2;
+    d.NPC = T.np;
+    d.nhalf3 = 0;
+    for (int p = 0; p < 7; p++) {
+        const int n = p < T.np ? T.n[p] : 3;
+        d.spawn_x[p] = d.Wp / 2 - n / 2;
+        d.nhalf3 |= (unsigned)(n / 2) << (3 * p);
+    }
     // elif chain of Tetris.step (envs/tetris.py:223-256): first matching name wins
     static const int order[8] = {0, 1, 2, 3, 4, 6, 5, 7};  // left,right,down,cw,ccw,swap,hard_drop,no_op
     static const int ops[8] = {OP_LEFT, OP_RIGHT, OP_DOWN, OP_CW, OP_CCW, OP_HARD, OP_SWAP, OP_NOOP};
@@ -286,8 +343,10 @@ extern "C" int tg_create(const tg_config* cfg, int device, tg_env** out) {
     cudaGetDeviceProperties(&prop, device);
     env->num_sms = prop.multiProcessorCount;
 
+    piece_set(cfg, env->tabs);
+    { int trc = build_tables(nullptr, env->tabs); if (trc) { delete env; return trc; } }
     DevCfg& d = env->dev;
-    derive_cfg(cfg, d);
+    derive_cfg(cfg, env->tabs, d);
     env->col64 = d.Hp > 32;
 
     tg_layout& L = env->layout;
@@ -309,7 +368,7 @@ extern "C" int tg_create(const tg_config* cfg, int device, tg_env** out) {
     if (const char* t = getenv("TG_NF")) { int v = atoi(t); if (v >= 1 && v <= 6) { env->fill_warps = v; env->fill_warps_set = 1; } }
     if (const char* t = getenv("TG_NL")) { int v = atoi(t); if (v >= 1 && v <= 6) { env->logic_warps = v; env->logic_warps_set = 1; } }
     if (env->logic_warps + env->fill_warps > 8) env->fill_warps = 8 - env->logic_warps;
-    int rc = upload_tables(env);
+    int rc = ensure_tables(env, env->tabs, device);
     if (rc != TG_OK) { g_create_err = env->err; delete env; return rc; }
     make_expand_cfg(env->dev, env->tabs, env->xcfg);
     const int hdr = env->dev.holder_size > 1 ? 16 : 12;          // hot words 0, 2, 3 (+ the holder FIFO word)
@@ -858,9 +917,10 @@ extern "C" int tg_host_expand(const tg_config* cfg, int64_t n, const void* h_hot
     if (n <= 0) return fail(nullptr, TG_ERR_ARG, "n must be positive");
     int rc = validate_cfg(cfg); if (rc) return rc;
     DevCfg d;
-    derive_cfg(cfg, d);
     HostTables T;
+    piece_set(cfg, T);
     rc = build_tables(nullptr, T); if (rc) return rc;
+    derive_cfg(cfg, T, d);
     tgh::ExpandCfg x;
     make_expand_cfg(d, T, x);
     tgh::ExpandArgs xa;
@@ -920,7 +980,6 @@ extern "C" int tg_set_state(tg_env* env, tg_state st, int64_t n, const uint8_t* 
 }
 
 // ---- functional facade ------------------------------------------------------------------------------------
-static bool g_fn_tables[64] = {false};
 extern "C" int tg_fn_step(int32_t width, int32_t height, int32_t queue_size, int32_t gravity, int64_t n,
                           const int8_t* d_board_in, const int32_t* d_scalars_in, const int32_t* d_actions,
                           const uint8_t* d_piece_seq, int64_t seq_len, int8_t* d_board_out, int32_t* d_scalars_out,
@@ -931,11 +990,13 @@ extern "C" int tg_fn_step(int32_t width, int32_t height, int32_t queue_size, int
     if (n <= 0 || !d_board_in || !d_board_out || !d_scalars_in || !d_scalars_out) return fail(nullptr, TG_ERR_POINTER, "tg_fn_step: NULL pointer");
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return fail(nullptr, TG_ERR_CUDA, "tg_fn_step: no CUDA device (no CPU fallback)");
-    if (!g_fn_tables[dev & 63]) {   // piece tables for the current device (same tables as tg_create uploads)
+    {   // the functional env always plays the reference's seven pieces: make that set resident on the current device
+        static HostTables std_tabs;
+        static bool built = false;
+        if (!built) { piece_set(nullptr, std_tabs); build_tables(nullptr, std_tabs); built = true; }
         tg_env tmp;
-        int rc = upload_tables(&tmp);
+        int rc = ensure_tables(&tmp, std_tabs, dev);
         if (rc) return fail(nullptr, rc, "tg_fn_step: %s", tmp.err.c_str());
-        g_fn_tables[dev & 63] = true;
     }
     FnParams p;
     memset(&p, 0, sizeof p);

@@ -37,6 +37,8 @@ struct DevCfg {
     int OQ;            // obs queue bytes = 16*Q
     int A, F;          // placements 4W, features W+3
     int rgb_w;         // Wp + 4*max(Q, holder_size, 1)
+    int NPC;           // pieces of the tetromino set (7 for the reference's; Tetris(tetrominoes=[...]): 1..7)
+    unsigned nhalf3;   // n // 2 of piece p in bits 3p..3p+2 (GroupedActionsObservations: x = column + padding - n // 2)
     int holder_size;   // TetrominoHolder(size): 1..4
     int OH;            // obs holder bytes = 16 * holder_size
     int spawn_x[7];    // W_pad//2 - n//2  (Tetris.reset_tetromino_position, envs/tetris.py:536-541)
@@ -193,16 +195,28 @@ __device__ __forceinline__ uint32_t pcg64_next32(uint32_t* rec) {
 
 // in-place Fisher-Yates of the 7-bag (BagRandomizer.shuffle_bag, components/tetromino_randomizer.py:82-85)
 // (plain values in, value out: a reference to the caller's Rng / Hot would pin them in local memory around the hot loop)
-__device__ __noinline__ uint32_t shuffle_bag_raw(int rng_mode, uint32_t* rec, uint64_t gid, uint32_t bag) {
-    uint32_t j6[6];
+// (npc = pieces in the bag: 7 for the reference's set)
+__device__ __noinline__ uint32_t shuffle_bag_raw(int rng_mode, uint32_t* rec, uint64_t gid, uint32_t bag, int npc) {
+    uint32_t j6[6] = {0, 0, 0, 0, 0, 0};
+    const int top = npc - 1;
     if (rng_mode == 2) {
-        // numpy Generator.shuffle: for i = 6..1: j = random_interval(i) (masked rejection on next_uint32)
-        for (int i = 6; i >= 1; i--) {
+        // numpy Generator.shuffle: for i = n-1..1: j = random_interval(i) (masked rejection on next_uint32)
+        for (int i = top; i >= 1; i--) {
             uint32_t mask = i | (i >> 1); mask |= mask >> 2;
             uint32_t v;
             do { v = pcg64_next32(rec) & mask; } while (v > (uint32_t)i);
-            j6[6 - i] = v;
+            j6[top - i] = v;
         }
+    } else if (npc != 7) {
+        uint64_t seed = ((uint64_t*)rec)[0];
+        uint32_t ctr = rec[2];
+        rec[2] = ctr + 1;
+        uint32_t c[4] = {ctr, (uint32_t)gid, (uint32_t)(gid >> 32), 0u};
+        uint32_t d[4] = {ctr, (uint32_t)gid, (uint32_t)(gid >> 32), 1u};
+        philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+        philox4x32_10(d, (uint32_t)seed, (uint32_t)(seed >> 32));
+        const uint32_t u[6] = {c[0], c[1], c[2], c[3], d[0], d[1]};
+        for (int i = top; i >= 1; i--) j6[top - i] = __umulhi(u[top - i], (uint32_t)(i + 1));
     } else {
         uint64_t seed = ((uint64_t*)rec)[0];
         uint32_t ctr = rec[2];
@@ -214,9 +228,8 @@ __device__ __noinline__ uint32_t shuffle_bag_raw(int rng_mode, uint32_t* rec, ui
         j6[0] = __umulhi(c[0], 7u); j6[1] = __umulhi(c[1], 6u); j6[2] = __umulhi(c[2], 5u);
         j6[3] = __umulhi(c[3], 4u); j6[4] = __umulhi(d[0], 3u); j6[5] = __umulhi(d[1], 2u);
     }
-#pragma unroll
-    for (int i = 6; i >= 1; i--) {
-        uint32_t j = j6[6 - i];
+    for (int i = top; i >= 1; i--) {
+        uint32_t j = j6[top - i];
         uint32_t vi = (bag >> (4 * i)) & 15u, vj = (bag >> (4 * j)) & 15u;
         bag = (bag & ~(15u << (4 * i))) | (vj << (4 * i));
         bag = (bag & ~(15u << (4 * j))) | (vi << (4 * j));
@@ -225,25 +238,27 @@ __device__ __noinline__ uint32_t shuffle_bag_raw(int rng_mode, uint32_t* rec, ui
 }
 __device__ __forceinline__ uint32_t shuffle_bag(const DevCfg& cfg, Rng& g, uint32_t bag) {
     g.dirty = true;
-    return shuffle_bag_raw(cfg.rng_mode, g.rec, g.gid, bag);
+    return shuffle_bag_raw(cfg.rng_mode, g.rec, g.gid, bag, cfg.NPC);
 }
 
 // Draws that are not the 7-bag: the injected stream (TG_RNG_SEQUENCE) and TrueRandomizer.  Out of line: the call sites
 // (commit, swap, reset) stay small -- inlined four times the PCG64 / Philox code made up a quarter of the step kernel and
 // pushed it past the instruction cache.  Returns the piece; the caller marks the rng record dirty.
-__device__ __noinline__ int draw_other(int rng_mode, long long seq_len, uint32_t* rec, const uint8_t* seq, uint64_t gid) {
+__device__ __noinline__ int draw_other(int rng_mode, long long seq_len, uint32_t* rec, const uint8_t* seq, uint64_t gid, int npc) {
     if (rng_mode == 1) {
         uint64_t cur = ((uint64_t*)rec)[0];
         ((uint64_t*)rec)[0] = cur + 1;
         return seq[cur % (uint64_t)seq_len];
     }
-    // TrueRandomizer.get_next_tetromino (components/tetromino_randomizer.py:119-121): rng.integers(0, 7)
+    // TrueRandomizer.get_next_tetromino (components/tetromino_randomizer.py:119-121): rng.integers(0, size)
+    if (npc <= 1) return 0;                     // numpy returns `low` for an empty range without drawing
+    const uint32_t un = (uint32_t)npc;
     if (rng_mode == 2) {
-        // numpy: Lemire multiply-shift with rejection on next_uint32 (buffered_bounded_lemire_uint32, rng = 6)
-        uint64_t m = (uint64_t)pcg64_next32(rec) * 7u;
-        if ((uint32_t)m < 7u) {
-            const uint32_t threshold = (0xFFFFFFFFu - 6u) % 7u;
-            while ((uint32_t)m < threshold) m = (uint64_t)pcg64_next32(rec) * 7u;
+        // numpy: Lemire multiply-shift with rejection on next_uint32 (buffered_bounded_lemire_uint32, rng = size - 1)
+        uint64_t m = (uint64_t)pcg64_next32(rec) * un;
+        if ((uint32_t)m < un) {
+            const uint32_t threshold = (0xFFFFFFFFu - (un - 1u)) % un;
+            while ((uint32_t)m < threshold) m = (uint64_t)pcg64_next32(rec) * un;
         }
         return (int)(m >> 32);
     }
@@ -252,20 +267,20 @@ __device__ __noinline__ int draw_other(int rng_mode, long long seq_len, uint32_t
     rec[2] = ctr + 1;
     uint32_t c[4] = {ctr, (uint32_t)gid, (uint32_t)(gid >> 32), 2u};
     philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
-    return (int)__umulhi(c[0], 7u);
+    return (int)__umulhi(c[0], un);
 }
 
 // Randomizer.get_next_tetromino
 __device__ __forceinline__ int draw_piece(const DevCfg& cfg, Rng& g, Hot& h) {
     if (cfg.rng_mode == 1 || cfg.rand_kind == 1) {
         g.dirty = true;
-        return draw_other(cfg.rng_mode, cfg.seq_len, g.rec, g.seq, g.gid);
+        return draw_other(cfg.rng_mode, cfg.seq_len, g.rec, g.seq, g.gid, cfg.NPC);
     }
     // BagRandomizer.get_next_tetromino (components/tetromino_randomizer.py:67-80)
     int idx = (h.bag >> 28) & 7;
     int v = (h.bag >> (4 * idx)) & 15;
     idx++;
-    if (idx >= 7) h.bag = shuffle_bag(cfg, g, h.bag);
+    if (idx >= cfg.NPC) h.bag = shuffle_bag(cfg, g, h.bag);
     else h.bag = (h.bag & 0x0FFFFFFFu) | ((uint32_t)idx << 28);
     return v;
 }

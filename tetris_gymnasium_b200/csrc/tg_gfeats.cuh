@@ -164,7 +164,7 @@ __global__ void __maxnreg__(W == 10 ? GF_REGS : 96) k_grouped_feats_x(const DevC
             legal_w = ((const uint32_t*)legal)[(base + e) * W + xb];
         } else {
             const int piece = (w0 >> 13) & 7, rot0 = (w0 >> 16) & 3;
-            const int nhalf = piece == 0 ? 2 : 1;                       // n // 2 (n = 4 for I, 2 for O, 3 otherwise)
+            const int nhalf = (int)((cfg.nhalf3 >> (3 * piece)) & 7u);    // n // 2 (reference set: 2 for I, 1 otherwise)
             const int x = xb + P - nhalf;                               // wrappers/grouped.py:157-158
             const COLT* colp = s_colp + e * CS;
             COLT cj[4];
@@ -292,7 +292,7 @@ __global__ void __maxnreg__(W == 10 ? GF_REGS : 96) k_grouped_feats_x(const DevC
             const int it = s_slow[k], es = it / A, a = it - es * A;
             const uint32_t w0 = s_w0[es];
             const int piece = (w0 >> 13) & 7, rot = (int)(((w0 >> 16) & 3) + (a & 3)) & 3;
-            const int x = (a >> 2) + P - (piece == 0 ? 2 : 1);
+            const int x = (a >> 2) + P - (int)((cfg.nhalf3 >> (3 * piece)) & 7u);
             const uint4 pr = s_prec[(piece * 4 + rot) * 8 + (tid & 7)];
             const COLT* colp = s_colp + es * CS;
             COLT B = 0;

@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(128, 6) k_rollout_x(const __grid_constant__ Ro
             }
             const uint4* prow = s_prec + h.p * 4;
             const int rot0 = h.r;
-            const int xoff = P - (h.p == 0 ? 2 : 1);                                 // wrappers/grouped.py:157-158
+            const int xoff = P - (int)((cfg.nhalf3 >> (3 * h.p)) & 7u);               // wrappers/grouped.py:157-158 (n // 2)
             int best = -1, best_score = 0, first_legal = -1;
             unsigned long long slow_lo = 0;   // placements 0..63 / 64.. that need the exact pass
             uint32_t slow_hi = 0;

@@ -16,6 +16,7 @@ import numpy as np
 import torch
 
 from .. import _lib
+from ..components.tetromino import Pixel, Tetromino
 from ..mappings.actions import ActionsMapping
 from ..mappings.rewards import RewardsMapping
 
@@ -47,7 +48,7 @@ def _spaces(env):
         mk_box = lambda hi, shape: _Space(shape, np.uint8, 0, hi)  # noqa: E731
         disc = _Space(n=8, dtype=np.int64)
         dct = dict
-    n_pix = 9  # len(self.pixels): 2 base pixels + 7 tetrominoes (reference envs/tetris.py:127)
+    n_pix = 2 + (7 if env.tetrominoes is None else len(env.tetrominoes))  # len(self.pixels) (reference envs/tetris.py:127)
     obs = dct({
         "board": mk_box(n_pix, (env.height_padded, env.width_padded)),
         "active_tetromino_mask": mk_box(1, (env.height_padded, env.width_padded)),
@@ -77,6 +78,18 @@ class Tetris:
 
     metadata = {"render_modes": ["rgb_array", "ansi"], "render_fps": 1}
 
+    # the reference's class attributes (envs/tetris.py:45-75): users build custom sets from copies of these
+    BASE_PIXELS = [Pixel(0, [0, 0, 0]), Pixel(1, [128, 128, 128])]
+    TETROMINOES = [
+        Tetromino(0, [0, 240, 240], np.array([[0, 0, 0, 0], [1, 1, 1, 1], [0, 0, 0, 0], [0, 0, 0, 0]], dtype=np.uint8)),
+        Tetromino(1, [240, 240, 0], np.array([[1, 1], [1, 1]], dtype=np.uint8)),
+        Tetromino(2, [160, 0, 240], np.array([[0, 1, 0], [1, 1, 1], [0, 0, 0]], dtype=np.uint8)),
+        Tetromino(3, [0, 240, 0], np.array([[0, 1, 1], [1, 1, 0], [0, 0, 0]], dtype=np.uint8)),
+        Tetromino(4, [240, 0, 0], np.array([[1, 1, 0], [0, 1, 1], [0, 0, 0]], dtype=np.uint8)),
+        Tetromino(5, [0, 0, 240], np.array([[1, 0, 0], [1, 1, 1], [0, 0, 0]], dtype=np.uint8)),
+        Tetromino(6, [240, 160, 0], np.array([[0, 0, 1], [1, 1, 1], [0, 0, 0]], dtype=np.uint8)),
+    ]
+
     def __init__(self, render_mode=None, width=10, height=20, gravity=True,
                  actions_mapping=ActionsMapping(), rewards_mapping=RewardsMapping(),
                  queue=None, holder=None, randomizer=None, base_pixels=None, tetrominoes=None,
@@ -84,8 +97,12 @@ class Tetris:
                  padding: Optional[int] = None, autoreset_mode: str = "next_step",
                  randomizer_mode: str = "philox", piece_sequences=None, env_id_offset: int = 0,
                  terminate_on_illegal_action: bool = True, report_invalid_actions: bool = False):
-        if base_pixels is not None or tetrominoes is not None:
-            raise NotImplementedError("custom pixel / tetromino sets are not supported yet (SURVEY 8 f4)")
+        if base_pixels is not None:
+            # (the reference itself never assigns self.base_pixels when the argument is given, envs/tetris.py:113-115)
+            raise NotImplementedError("custom base pixels are not supported: the empty / bedrock values 0 / 1 are built into the kernels")
+        self.tetrominoes = None if tetrominoes is None else list(tetrominoes)
+        if self.tetrominoes is not None and not 1 <= len(self.tetrominoes) <= 7:
+            raise ValueError("a custom tetromino set holds 1..7 pieces")
         if padding not in (None, PADDING):
             raise ValueError("padding is derived from the tetromino set and must be 4")
         holder_size = int(getattr(holder, "size", holder)) if holder is not None else 1
@@ -153,6 +170,18 @@ class Tetris:
         cfg.reward_game_over, cfg.reward_invalid_action = float(self.rewards.game_over), float(self.rewards.invalid_action)
         cfg.seq_len, cfg.env_id_offset = seq_len, self.env_id_offset
         cfg.holder_size = self.holder_size
+        if self.tetrominoes is not None:
+            # Tetris(tetrominoes=[...]) (envs/tetris.py:117-132): matrices are used as binary masks, board values are index + 2
+            cfg.n_pieces = len(self.tetrominoes)
+            for i, t in enumerate(self.tetrominoes):
+                m = np.asarray(t.matrix)
+                if m.ndim != 2 or m.shape[0] != m.shape[1] or m.shape[0] > 4:
+                    raise ValueError(f"tetromino {i}: the matrix must be square and at most 4 x 4")
+                cfg.piece_n[i] = m.shape[0]
+                for k, v in enumerate((m != 0).astype(np.uint8).reshape(-1)):
+                    cfg.piece_matrix[i][k] = int(v)
+                for k in range(3):
+                    cfg.piece_color[i][k] = int(t.color_rgb[k])
         self._cfg = cfg
         self._L = _lib.load()
         h = C.c_void_p()
