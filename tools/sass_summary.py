@@ -22,7 +22,7 @@ for line in sass.splitlines():
     if m:
         cur = kernels.setdefault(m.group(1), collections.Counter())
         continue
-    m = re.match(r"\s*/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_]*)", line)
+    m = re.match(r"\s*/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P[T\d]+\s+)?([A-Z][A-Z0-9_]*)", line)
     if m and cur is not None:
         cur[m.group(1)] += 1
 KEY = ["UBLKCP", "SYNCS", "ACQBULK", "LDGSTS", "IDP", "VABSDIFF4", "VIMNMX", "PRMT", "LOP3", "SHF", "POPC", "FLO", "BREV", "BAR", "LDS", "STS", "LDG", "STG",
@@ -36,7 +36,8 @@ with open(out, "w") as f:
     tot = collections.Counter()
     for name, c in kernels.items():
         d = demangle(name)
-        d = re.sub(r"^void ", "", d).split("(")[0]
+        d = re.sub(r"\((?:int|bool)\)", "", re.sub(r"^void ", "", d))
+        d = d[:d.rfind(">(") + 1] if ">(" in d else d.split("(")[0]
         f.write(f"| `{d[:70]}` | {sum(c.values())} | " + " | ".join(str(c.get(k, 0)) for k in KEY) + " |\n")
         tot.update(c)
     f.write(f"| **all kernels** | {sum(tot.values())} | " + " | ".join(str(tot.get(k, 0)) for k in KEY) + " |\n")
