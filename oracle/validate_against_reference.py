@@ -113,10 +113,11 @@ CUSTOM_SETS = {
     # a subset of the reference's pieces with other colours (bag of three)
     "iot": ([[[0, 0, 0, 0], [1, 1, 1, 1], [0, 0, 0, 0], [0, 0, 0, 0]], [[1, 1], [1, 1]], [[0, 1, 0], [1, 1, 1], [0, 0, 0]]],
             [[10, 200, 30], [250, 1, 99], [77, 77, 200]]),
-    # five four-cell shapes that are not in the reference's set: a low I, an O in a corner of a 3 x 3 box, a T pointing down, two
-    # bars with a gap between them (cells of a column need not be contiguous), a long L
+    # five four-cell shapes that are not in the reference's set: a low I, an O in a corner of a 3 x 3 box, a T pointing down, a
+    # skewed S, a long L (every column between a piece's first and last occupied one must hold a cell in each rotation, which is
+    # true of every connected shape: the placement kernels describe a piece by its column profile)
     "odd5": ([[[0, 0, 0, 0], [0, 0, 0, 0], [1, 1, 1, 1], [0, 0, 0, 0]], [[1, 1, 0], [1, 1, 0], [0, 0, 0]], [[1, 1, 1], [0, 1, 0], [0, 0, 0]],
-              [[1, 1, 0], [0, 0, 0], [1, 1, 0]], [[1, 0, 0, 0], [1, 0, 0, 0], [1, 1, 0, 0], [0, 0, 0, 0]]],
+              [[0, 1, 0], [0, 1, 1], [0, 0, 1]], [[1, 0, 0, 0], [1, 0, 0, 0], [1, 1, 0, 0], [0, 0, 0, 0]]],
              [[1, 2, 3], [40, 50, 60], [200, 100, 0], [9, 99, 199], [255, 255, 255]]),
     # a single piece: the bag never shuffles
     "only_i": ([[[0, 0, 0, 0], [1, 1, 1, 1], [0, 0, 0, 0], [0, 0, 0, 0]]], [[0, 240, 240]]),

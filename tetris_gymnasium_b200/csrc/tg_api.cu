@@ -440,10 +440,15 @@ static int raise_smem_limit(tg_env* env, const void* kern, size_t bytes) {
 // the diagnostic environment switches) is worked out once per (mode, with / without dict, kernel family) and cached in the
 // handle: a small batch's step is bound by the host-side cost of the call, and getenv + occupancy queries were half of it.
 typedef void (*step_kernel_t)(const StepParams);
+template <int WT, int HT, class COLT, bool XT>
+static step_kernel_t pick_kernel_x(int mode) {
+    return mode == 2 ? (step_kernel_t)k_step_ws<WT, HT, COLT, 2, XT> : mode == 1 ? (step_kernel_t)k_step_ws<WT, HT, COLT, 1, XT> : (step_kernel_t)k_step_ws<WT, HT, COLT, 0, XT>;
+}
+// xt: custom tetromino set or holder FIFO -- the reference configuration runs the leaner instantiation (tg_device.cuh: XT)
 template <int WT, int HT, class COLT>
-static step_kernel_t pick_kernel(bool ws, int mode) {
+static step_kernel_t pick_kernel(bool ws, int mode, bool xt) {
     if (!ws) return (step_kernel_t)k_step<WT, HT, COLT>;
-    return mode == 2 ? (step_kernel_t)k_step_ws<WT, HT, COLT, 2> : mode == 1 ? (step_kernel_t)k_step_ws<WT, HT, COLT, 1> : (step_kernel_t)k_step_ws<WT, HT, COLT, 0>;
+    return xt ? pick_kernel_x<WT, HT, COLT, true>(mode) : pick_kernel_x<WT, HT, COLT, false>(mode);
 }
 
 static int build_plan(tg_env* env, StepPlan& pl, int mode, bool want_obs, int force_plain) {
@@ -501,10 +506,11 @@ static int build_plan(tg_env* env, StepPlan& pl, int mode, bool want_obs, int fo
     if (T > 256) T = 256;
     pl.threads = T; pl.smem = off; pl.ws = ws;
     pl.pdl = ws && !getenv("TG_NO_PDL");
-    if (d.W == 10 && d.H == 20) pl.kern = (void*)pick_kernel<10, 20, uint32_t>(ws, mode);
-    else if (d.W == 20 && d.H == 40) pl.kern = (void*)pick_kernel<20, 40, uint64_t>(ws, mode);
-    else if (env->col64) pl.kern = (void*)pick_kernel<0, 0, uint64_t>(ws, mode);
-    else pl.kern = (void*)pick_kernel<0, 0, uint32_t>(ws, mode);
+    const bool xt = d.NPC != 7 || d.holder_size > 1;
+    if (d.W == 10 && d.H == 20) pl.kern = (void*)pick_kernel<10, 20, uint32_t>(ws, mode, xt);
+    else if (d.W == 20 && d.H == 40) pl.kern = (void*)pick_kernel<20, 40, uint64_t>(ws, mode, xt);
+    else if (env->col64) pl.kern = (void*)pick_kernel<0, 0, uint64_t>(ws, mode, xt);
+    else pl.kern = (void*)pick_kernel<0, 0, uint32_t>(ws, mode, xt);
     { int rc = raise_smem_limit(env, pl.kern, off); if (rc) return rc; }
     int per_sm = 0;
     CUDA_TRY(env, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pl.kern, T, off));

@@ -85,6 +85,10 @@ struct Hot {
     float ep_ret;
     uint32_t ep_len, ep_lines;
 };
+// XT ("extended", template flag of the step path): the env has a custom tetromino set (NPC != 7) or a holder FIFO (size > 1).
+// The XT = false instantiations of the per-call step kernel keep the reference configuration's code exactly as small as it was
+// before those options existed (bag of 7 unrolled, no FIFO word, 16-byte holder image): its speed depends on its code footprint.
+template <bool XT = true>
 __device__ __forceinline__ void hot_load(Hot& h, const uint32_t* w) {
     uint32_t a = w[0];
     h.x = a & 63; h.y = (a >> 6) & 127; h.p = (a >> 13) & 7; h.r = (a >> 16) & 3;
@@ -93,15 +97,16 @@ __device__ __forceinline__ void hot_load(Hot& h, const uint32_t* w) {
     h.bag = w[1];
     h.queue = (uint64_t)w[2] | ((uint64_t)w[3] << 32);
     h.ep_ret = __uint_as_float(w[4]); h.ep_len = w[5]; h.ep_lines = w[6];
-    h.hq = w[7];
+    h.hq = XT ? w[7] : 0u;
 }
+template <bool XT = true>
 __device__ __forceinline__ void hot_store(const Hot& h, uint32_t* w) {
     w[0] = (uint32_t)h.x | ((uint32_t)h.y << 6) | ((uint32_t)h.p << 13) | ((uint32_t)h.r << 16) |
            ((uint32_t)h.hold << 18) | ((uint32_t)h.hold_r << 22) | ((uint32_t)h.swapped << 24) |
            ((uint32_t)h.over << 25) | ((uint32_t)h.pending << 26);
     w[1] = h.bag;
     w[2] = (uint32_t)h.queue; w[3] = (uint32_t)(h.queue >> 32);
-    w[4] = __float_as_uint(h.ep_ret); w[5] = h.ep_len; w[6] = h.ep_lines; w[7] = h.hq;
+    w[4] = __float_as_uint(h.ep_ret); w[5] = h.ep_len; w[6] = h.ep_lines; w[7] = XT ? h.hq : 0u;
 }
 
 // ---- column bitboards -----------------------------------------------------------------------
@@ -207,7 +212,7 @@ __device__ __noinline__ uint32_t shuffle_bag_raw(int rng_mode, uint32_t* rec, ui
             do { v = pcg64_next32(rec) & mask; } while (v > (uint32_t)i);
             j6[top - i] = v;
         }
-    } else if (npc != 7) {
+    } else {
         uint64_t seed = ((uint64_t*)rec)[0];
         uint32_t ctr = rec[2];
         rec[2] = ctr + 1;
@@ -216,7 +221,26 @@ __device__ __noinline__ uint32_t shuffle_bag_raw(int rng_mode, uint32_t* rec, ui
         philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
         philox4x32_10(d, (uint32_t)seed, (uint32_t)(seed >> 32));
         const uint32_t u[6] = {c[0], c[1], c[2], c[3], d[0], d[1]};
-        for (int i = top; i >= 1; i--) j6[top - i] = __umulhi(u[top - i], (uint32_t)(i + 1));
+        for (int i = top; i >= 1; i--) j6[top - i] = __umulhi(u[top - i], (uint32_t)(i + 1));   // 7 pieces: umulhi(u0, 7), (u1, 6), ... (u5, 2)
+    }
+    for (int i = top; i >= 1; i--) {
+        uint32_t j = j6[top - i];
+        uint32_t vi = (bag >> (4 * i)) & 15u, vj = (bag >> (4 * j)) & 15u;
+        bag = (bag & ~(15u << (4 * i))) | (vj << (4 * i));
+        bag = (bag & ~(15u << (4 * j))) | (vi << (4 * j));
+    }
+    return bag & 0x0FFFFFFFu;  // index = 0
+}
+// the reference's seven pieces: same draws, loops unrolled over constants
+__device__ __noinline__ uint32_t shuffle_bag7_raw(int rng_mode, uint32_t* rec, uint64_t gid, uint32_t bag) {
+    uint32_t j6[6];
+    if (rng_mode == 2) {
+        for (int i = 6; i >= 1; i--) {
+            uint32_t mask = i | (i >> 1); mask |= mask >> 2;
+            uint32_t v;
+            do { v = pcg64_next32(rec) & mask; } while (v > (uint32_t)i);
+            j6[6 - i] = v;
+        }
     } else {
         uint64_t seed = ((uint64_t*)rec)[0];
         uint32_t ctr = rec[2];
@@ -228,16 +252,19 @@ __device__ __noinline__ uint32_t shuffle_bag_raw(int rng_mode, uint32_t* rec, ui
         j6[0] = __umulhi(c[0], 7u); j6[1] = __umulhi(c[1], 6u); j6[2] = __umulhi(c[2], 5u);
         j6[3] = __umulhi(c[3], 4u); j6[4] = __umulhi(d[0], 3u); j6[5] = __umulhi(d[1], 2u);
     }
-    for (int i = top; i >= 1; i--) {
-        uint32_t j = j6[top - i];
+#pragma unroll
+    for (int i = 6; i >= 1; i--) {
+        uint32_t j = j6[6 - i];
         uint32_t vi = (bag >> (4 * i)) & 15u, vj = (bag >> (4 * j)) & 15u;
         bag = (bag & ~(15u << (4 * i))) | (vj << (4 * i));
         bag = (bag & ~(15u << (4 * j))) | (vi << (4 * j));
     }
     return bag & 0x0FFFFFFFu;  // index = 0
 }
+template <bool XT = true>
 __device__ __forceinline__ uint32_t shuffle_bag(const DevCfg& cfg, Rng& g, uint32_t bag) {
     g.dirty = true;
+    if (!XT) return shuffle_bag7_raw(cfg.rng_mode, g.rec, g.gid, bag);
     return shuffle_bag_raw(cfg.rng_mode, g.rec, g.gid, bag, cfg.NPC);
 }
 
@@ -271,30 +298,32 @@ __device__ __noinline__ int draw_other(int rng_mode, long long seq_len, uint32_t
 }
 
 // Randomizer.get_next_tetromino
+template <bool XT = true>
 __device__ __forceinline__ int draw_piece(const DevCfg& cfg, Rng& g, Hot& h) {
     if (cfg.rng_mode == 1 || cfg.rand_kind == 1) {
         g.dirty = true;
-        return draw_other(cfg.rng_mode, cfg.seq_len, g.rec, g.seq, g.gid, cfg.NPC);
+        return draw_other(cfg.rng_mode, cfg.seq_len, g.rec, g.seq, g.gid, XT ? cfg.NPC : 7);
     }
     // BagRandomizer.get_next_tetromino (components/tetromino_randomizer.py:67-80)
     int idx = (h.bag >> 28) & 7;
     int v = (h.bag >> (4 * idx)) & 15;
     idx++;
-    if (idx >= cfg.NPC) h.bag = shuffle_bag(cfg, g, h.bag);
+    if (idx >= (XT ? cfg.NPC : 7)) h.bag = shuffle_bag<XT>(cfg, g, h.bag);
     else h.bag = (h.bag & 0x0FFFFFFFu) | ((uint32_t)idx << 28);
     return v;
 }
 // TetrominoQueue.get_next_tetromino (components/tetromino_queue.py:35-42)
+template <bool XT = true>
 __device__ __forceinline__ int queue_pop(const DevCfg& cfg, Rng& g, Hot& h) {
     int v = (int)(h.queue & 15u);
-    uint64_t nv = (uint64_t)draw_piece(cfg, g, h);
+    uint64_t nv = (uint64_t)draw_piece<XT>(cfg, g, h);
     h.queue = (h.queue >> 4) | (nv << (4 * (cfg.Q - 1)));
     return v;
 }
 
 // ---- env logic (one thread = one env; board record in shared memory) --------------------------
 // Tetris.reset (envs/tetris.py:274-307) + TetrominoQueue.reset + BagRandomizer.reset
-template <class COLT>
+template <class COLT, bool XT = true>
 __device__ __forceinline__ void env_reset(const DevCfg& cfg, Hot& h, uint32_t* rec, Rng& g) {
     COLT* cols = (COLT*)rec;
     uint32_t* ids = rec + cfg.ids_off / 4;
@@ -302,10 +331,10 @@ __device__ __forceinline__ void env_reset(const DevCfg& cfg, Hot& h, uint32_t* r
     for (int c = 0; c < cfg.W; c++) cols[c] = fl;
     for (int i = 0; i < cfg.ids_words; i++) ids[i] = 0;
     h.over = 0; h.pending = 0;
-    if (cfg.rng_mode != 1 && cfg.rand_kind == 0) h.bag = shuffle_bag(cfg, g, 0x06543210u);   // TrueRandomizer.reset only reseeds
+    if (cfg.rng_mode != 1 && cfg.rand_kind == 0) h.bag = shuffle_bag<XT>(cfg, g, 0x06543210u);   // TrueRandomizer.reset only reseeds
     h.queue = 0;
-    for (int i = 0; i < cfg.Q; i++) h.queue |= (uint64_t)draw_piece(cfg, g, h) << (4 * i);
-    h.p = queue_pop(cfg, g, h);
+    for (int i = 0; i < cfg.Q; i++) h.queue |= (uint64_t)draw_piece<XT>(cfg, g, h) << (4 * i);
+    h.p = queue_pop<XT>(cfg, g, h);
     h.r = 0; h.x = cfg.spawn_x[h.p]; h.y = 0;
     h.hold = 0; h.hold_r = 0; h.swapped = 0; h.hq = 0;
     h.ep_ret = 0.f; h.ep_len = 0; h.ep_lines = 0;
@@ -377,7 +406,7 @@ struct StepResult {
 };
 
 // Tetris.commit_active_tetromino (envs/tetris.py:450-479); B = bmask of the active piece at h.x
-template <class COLT>
+template <class COLT, bool XT = true>
 __device__ __forceinline__ void env_commit(const DevCfg& cfg, const Tabs& tb, Hot& h, uint32_t* rec, Rng& g, COLT B,
                                            StepResult& res) {
     COLT* cols = (COLT*)rec;
@@ -405,7 +434,7 @@ __device__ __forceinline__ void env_commit(const DevCfg& cfg, const Tabs& tb, Ho
     res.lines = lines;
     res.reward = (double)(lines * lines * cfg.W);  // Tetris.score (envs/tetris.py:621-630)
     // spawn_tetromino (envs/tetris.py:393-401)
-    h.p = queue_pop(cfg, g, h);
+    h.p = queue_pop<XT>(cfg, g, h);
     h.r = 0; h.x = cfg.spawn_x[h.p]; h.y = 0;
     COLT Bn = bmask<COLT>(cols, cfg.W, tb.cells[h.p * 4], h.x);
     h.over = (int)(Bn & 1);
@@ -418,7 +447,7 @@ __device__ __forceinline__ void env_commit(const DevCfg& cfg, const Tabs& tb, Ho
 // Tetris.step (envs/tetris.py:203-272) with the vector-env autoreset policy around it.
 // `force_x/force_r` >= 0: grouped placement (GroupedActionsObservations.step sets env.x and the
 // rotated piece, y untouched, then base hard_drop; wrappers/grouped.py:241-259).
-template <class COLT>
+template <class COLT, bool XT = true>
 __device__ __forceinline__ void env_step(const DevCfg& cfg, const Tabs& tb, Hot& h, uint32_t* rec, Rng& g, int action,
                                          StepResult& res) {
     COLT* cols = (COLT*)rec;
@@ -427,14 +456,14 @@ __device__ __forceinline__ void env_step(const DevCfg& cfg, const Tabs& tb, Hot&
     if ((unsigned)action < 8u) { op = cfg.op_lut[action]; skipgrav = cfg.skipgrav[action]; }
     if (op == OP_SWAP && !h.swapped) {  // envs/tetris.py:242-252 + TetrominoHolder.swap
         int np, nr;
-        if (cfg.holder_size > 1) {
+        if (XT && cfg.holder_size > 1) {
             const uint64_t res = holder_fifo_swap(h.hq, cfg.holder_size, h.p, h.r);
             h.hq = (uint32_t)res;
             const uint32_t back = (uint32_t)(res >> 32);
-            if (back == 0) { np = queue_pop(cfg, g, h); nr = 0; }
+            if (back == 0) { np = queue_pop<XT>(cfg, g, h); nr = 0; }
             else { np = (int)((back - 1) & 7u); nr = (int)((back - 1) >> 3); }
         } else {
-            if (h.hold == 0) { np = queue_pop(cfg, g, h); nr = 0; }
+            if (h.hold == 0) { np = queue_pop<XT>(cfg, g, h); nr = 0; }
             else { np = h.hold - 1; nr = h.hold_r; }
             h.hold = h.p + 1; h.hold_r = h.r;
         }
@@ -453,7 +482,7 @@ __device__ __forceinline__ void env_step(const DevCfg& cfg, const Tabs& tb, Hot&
         if (!((B >> (h.y + 1)) & 1)) h.y += 1;
         else do_commit = true;
     }
-    if (do_commit) env_commit<COLT>(cfg, tb, h, rec, g, B, res);
+    if (do_commit) env_commit<COLT, XT>(cfg, tb, h, rec, g, B, res);
     res.terminated = h.over;
 }
 

@@ -214,7 +214,7 @@ __device__ __noinline__ void flush_stats(double* stats, double ep, double ret, d
 // Returns bit0 = board record dirty, bit1 = rng record dirty.  Writes the 5-tuple scalars and s_box[slot].
 // MODE >= 0: the kernel instantiation's fixed mode (0 step, 1 reset, 2 grouped step); -1: p.mode at run time (k_step)
 // `eo`: index of the env's 5-tuple outputs (== e except in the multi-step kernel, whose outputs are [step][env])
-template <class COLT, bool INFO = true, int MODE = -1>
+template <class COLT, bool INFO = true, int MODE = -1, bool XT = true>
 __device__ __forceinline__ uint32_t logic_one_env(const StepParams& p, const Tabs& tb, int64_t e, int slot, int action,
                                                   uint32_t* s_hot, uint8_t* s_brd, uint8_t* s_rng, uint32_t* s_box,
                                                   TileStats& st, int64_t eo) {
@@ -224,7 +224,7 @@ __device__ __forceinline__ uint32_t logic_one_env(const StepParams& p, const Tab
     res.dirty = 0; res.reward = 0; res.lines = 0; res.terminated = 0;
     Hot h;
     uint32_t* rec = (uint32_t*)(s_brd + slot * BS);
-    hot_load(h, s_hot + slot * 8);
+    hot_load<XT>(h, s_hot + slot * 8);
     Rng g;
     g.rec = (uint32_t*)(s_rng + slot * RS);
     g.seq = p.seq ? p.seq + e * cfg.seq_len : nullptr;
@@ -258,7 +258,7 @@ __device__ __forceinline__ uint32_t logic_one_env(const StepParams& p, const Tab
             }
         }
         if (run) {
-            env_step<COLT>(cfg, tb, h, rec, g, act, res);
+            env_step<COLT, XT>(cfg, tb, h, rec, g, act, res);
             if (invalid) res.reward = cfg.r_invalid;
         }
         h.ep_ret += (float)res.reward; h.ep_len += 1; h.ep_lines += res.lines;
@@ -270,9 +270,9 @@ __device__ __forceinline__ uint32_t logic_one_env(const StepParams& p, const Tab
         }
     }
     // (inline: an out-of-line reset forces the hot record into local memory and cost 6 % on the 4 M-env step)
-    if (need_reset) { env_reset<COLT>(cfg, h, rec, g); res.dirty = 1; }
+    if (need_reset) { env_reset<COLT, XT>(cfg, h, rec, g); res.dirty = 1; }
     if (mode == 2 && need_reset) p.fill_high[e] = 0;
-    hot_store(h, s_hot + slot * 8);
+    hot_store<XT>(h, s_hot + slot * 8);
     if (mode != 1) {
         p.reward[eo] = (float)res.reward;
         p.terminated[eo] = (uint8_t)res.terminated;
@@ -306,7 +306,7 @@ __device__ __forceinline__ void mask_clear_boxes(const uint32_t* boxes, int n_en
         }
     }
 }
-template <int WT, int HT>
+template <int WT, int HT, bool XT = true>
 __device__ __forceinline__ void fill_images(const DevCfg& cfg, int nv, const uint32_t* s_hot, const uint8_t* s_brd,
                                             const uint32_t* s_rowbytes, uint8_t* i_board, uint8_t* i_holder, uint8_t* i_queue,
                                             int t, int nt) {
@@ -338,7 +338,7 @@ __device__ __forceinline__ void fill_images(const DevCfg& cfg, int nv, const uin
         uint32_t* qo = (uint32_t*)i_queue + e * 4 * Q + q;
         qo[0] = rb.x; qo[Q] = rb.y; qo[2 * Q] = rb.z; qo[3 * Q] = rb.w;
     }
-    if (cfg.holder_size <= 1) {
+    if (!XT || cfg.holder_size <= 1) {
         for (int it = t; it < nv * 4; it += nt) {
             int e = it >> 2, i = it & 3;
             uint32_t w0 = s_hot[e * 8];
@@ -519,7 +519,8 @@ __device__ __forceinline__ void named_arrive(int id, int count) { asm volatile("
 // MODE = 0 step, 1 reset, 2 grouped placement step: one instantiation each, so that the step instantiation carries neither
 // the reset-mode code nor the grouped code (legal-mask test, info board, whole-tile write-back) -- its speed depends on the
 // code footprint (instruction cache).
-template <int WT, int HT, class COLT, int MODE>
+// XT: custom tetromino set or holder FIFO (tg_device.cuh); the reference configuration runs the XT = false instantiation.
+template <int WT, int HT, class COLT, int MODE, bool XT>
 __global__ void __launch_bounds__(256) k_step_ws(const __grid_constant__ StepParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const DevCfg& cfg = p.cfg;
@@ -530,6 +531,7 @@ __global__ void __launch_bounds__(256) k_step_ws(const __grid_constant__ StepPar
     const int W = WT ? WT : cfg.W, H = HT ? HT : cfg.H;
     const int Wp = W + 2 * P, Hp = H + P;
     const int OB = Hp * Wp, OQ = cfg.OQ, BS = cfg.board_stride, RS = cfg.rng_stride;
+    const int OH = XT ? cfg.OH : 16;
     const int BAR_FILL = 1 + NS;                    // named barriers: 1 + s = ready[s], 1 + NS = fill warps only
 
     uint8_t* i_board = smem + p.off_iboard;
@@ -590,7 +592,7 @@ __global__ void __launch_bounds__(256) k_step_ws(const __grid_constant__ StepPar
             mbar_wait(bar + s, (uint32_t)((k / NS) & 1));
             uint32_t dirty = 0;
             if (lane < nv)
-                dirty = logic_one_env<COLT, false, MODE>(p, tb, base + lane, lane, action, (uint32_t*)(smem + p.off_hot + s * p.st_hot),
+                dirty = logic_one_env<COLT, false, MODE, XT>(p, tb, base + lane, lane, action, (uint32_t*)(smem + p.off_hot + s * p.st_hot),
                                                    smem + p.off_brd + s * p.st_brd, smem + p.off_rng + s * p.st_rng, s_boxes + s * E, st, base + lane);
             // grouped mode: tiles where most envs committed (nearly always) write their board records back as ONE bulk copy
             const int ndirty = GROUPED ? __popc(__ballot_sync(0xffffffffu, (dirty & 1u) != 0)) : 0;
@@ -618,7 +620,7 @@ __global__ void __launch_bounds__(256) k_step_ws(const __grid_constant__ StepPar
             if (leader && tile + (NS - 1) * G < ntiles) issue_load(tile + (NS - 1) * G, s == 0 ? NS - 1 : s - 1);
             if (want_obs) {
                 mask_clear_boxes(s_boxprev, nv_prev, i_mask, OB, Wp, ft, FT);
-                fill_images<WT, HT>(cfg, nv, s_hot, s_brd, s_rowbytes, i_board, i_holder, i_queue, ft, FT);
+                fill_images<WT, HT, XT>(cfg, nv, s_hot, s_brd, s_rowbytes, i_board, i_holder, i_queue, ft, FT);
                 named_sync(BAR_FILL, FT);
                 mask_set_and_overlay(s_boxes + s * E, nv, s_cells, i_board, i_mask, OB, Wp, ft, FT);
                 for (int i = ft; i < nv; i += FT) s_boxprev[i] = s_boxes[s * E + i];
@@ -666,7 +668,7 @@ __global__ void __launch_bounds__(256) k_step_ws(const __grid_constant__ StepPar
                 tile_store<true>(p.o_board + base * OB, i_board, (uint32_t)(nv * OB), leader, ft, FT);
                 tile_store<true>(p.o_mask + base * OB, i_mask, (uint32_t)(nv * OB), leader, ft, FT);
                 if (leader) {
-                    bulk_s2g_stream(p.o_holder + base * cfg.OH, i_holder, (uint32_t)(nv * cfg.OH));
+                    bulk_s2g_stream(p.o_holder + base * OH, i_holder, (uint32_t)(nv * OH));
                     bulk_s2g_stream(p.o_queue + base * OQ, i_queue, (uint32_t)(nv * OQ));
                 }
             }
