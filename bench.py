@@ -304,7 +304,7 @@ def main():
             "dtype": "u8", "data": "synthetic",
             "config": workload_config(n, world),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                         "kernel": "tg::k_step_ws<10,20,uint32_t,0> (2 logic warps + 4 image warps per CTA)", "bytes_per_env_step": bps,
+                         "kernel": "tg::k_step_ws<10,20,uint32_t,0,false> (2 logic warps + 4 image warps per CTA)", "bytes_per_env_step": bps,
                          "commit_frac": write_frac, "kernel_ms": kernel_ms, "peak_source": peak_src},
             "steady_state": steady,
             "clocks": sampler.result(),
