@@ -320,3 +320,39 @@ def test_grouped_features_on_constructed_boards_vs_oracle(W, H):
         assert np.array_equal(np_(g)[i], wf) and np.array_equal(np_(info["action_mask"])[i], wl), i
         assert np.array_equal(np_(info["board"])[i], o.features(o.obs())), i
     base.close()
+
+
+@pytest.mark.parametrize("n,terminate,autoreset", [(4096 + 17, True, "next_step"), (1000, False, "same_step"), (33, True, "disabled")])
+def test_fused_grouped_step_equals_two_kernel_path(n, terminate, autoreset, monkeypatch):
+    """tg_grouped_step has two implementations for the feature observation of the 10-wide board: one persistent kernel
+    (k_grouped_step_feats: logic warps + feature warps, small batches) and k_step_ws<.., 2> followed by k_grouped_feats_x.  Same
+    seeds, same actions (random legal placements with some illegal ones): every output of every step must be identical."""
+    from tetris_gymnasium_b200.envs.tetris import Tetris
+    from tetris_gymnasium_b200.wrappers import FeatureVectorObservation, GroupedActionsObservations
+
+    def make():
+        base = Tetris(num_envs=n, gravity=False, queue_size=4, autoreset_mode=autoreset)
+        return base, GroupedActionsObservations(base, observation_wrappers=[FeatureVectorObservation(base)], terminate_on_illegal_action=terminate)
+
+    (ba, ea), (bb, eb) = make(), make()
+    monkeypatch.setenv("TG_GROUPED_SPLIT", "1")
+    oa, ia = ea.reset(seed=7)
+    ob, ib = eb.reset(seed=7)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    for t in range(60):
+        a = torch.multinomial(ea.legal_actions_mask.float() + 1e-9, 1, generator=g).squeeze(1).to(torch.int32)
+        if t % 7 == 3:   # some arbitrary (often illegal) placements
+            a = torch.where(torch.rand(n, device="cuda", generator=g) < 0.2, torch.randint(0, 40, (n,), device="cuda", generator=g, dtype=torch.int32), a)
+        monkeypatch.setenv("TG_GROUPED_SPLIT", "1")
+        monkeypatch.delenv("TG_GROUPED_FUSED", raising=False)
+        ra = ea.step(a)
+        monkeypatch.delenv("TG_GROUPED_SPLIT")
+        monkeypatch.setenv("TG_GROUPED_FUSED", "1")
+        rb = eb.step(a)
+        torch.cuda.synchronize()
+        assert torch.equal(ra[0], rb[0]), f"features differ at step {t}"
+        assert torch.equal(ra[1], rb[1]) and torch.equal(ra[2], rb[2]) and torch.equal(ra[3], rb[3]), f"5-tuple differs at step {t}"
+        for k in ("action_mask", "board", "lines_cleared"):
+            assert torch.equal(ra[4][k], rb[4][k]), f"info[{k}] differs at step {t}"
+        for k in ("_hot", "_brd", "_rng"):   # the packed state records themselves
+            assert torch.equal(getattr(ba, k), getattr(bb, k)), f"state {k} differs at step {t}"

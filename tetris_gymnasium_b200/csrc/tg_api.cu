@@ -29,6 +29,7 @@ struct HostTables {
     unsigned short cells[7][4];
     uint2 ptab[7][4];
     uint4 prec[7][4];
+    unsigned int bot4[7][4];      // byte j = row offset of the lowest cell of matrix column j (0 where the column is empty)
     unsigned int rowbytes[7][4][4];
     unsigned char colors[16][4];
     uint64_t hash;
@@ -65,6 +66,7 @@ struct tg_env {
     cudaStream_t hs[3];
     bool hs_init;
     void* stage[16];
+    int64_t fused_grid_max = 0;   // resident CTAs of k_grouped_step_feats (0 = not yet queried)
     size_t stage_bytes[16];
     // compact host step: pinned ring of packed records, events, expansion pool
     HostTables tabs;
@@ -146,7 +148,7 @@ static void piece_set(const tg_config* cfg, HostTables& T) {
 // fills the derived tables of T from T.np / T.n / T.base (set by piece_set)
 static int build_tables(tg_env* env, HostTables& T) {
     auto& cells = T.cells; auto& ptab = T.ptab; auto& prec = T.prec; auto& rowbytes = T.rowbytes;
-    memset(cells, 0, sizeof cells); memset(ptab, 0, sizeof ptab); memset(prec, 0, sizeof prec); memset(rowbytes, 0, sizeof rowbytes);
+    memset(cells, 0, sizeof cells); memset(ptab, 0, sizeof ptab); memset(prec, 0, sizeof prec); memset(rowbytes, 0, sizeof rowbytes); memset(T.bot4, 0, sizeof T.bot4);
     for (int p = 0; p < T.np; p++) {
         int n = T.n[p];
         unsigned char m[16], t[16];
@@ -187,11 +189,16 @@ static int build_tables(tg_env* env, HostTables& T) {
             px |= (unsigned)jmin << 24 | (unsigned)jmax << 26;
             ptab[p][r] = make_uint2(px, py);
             // packed-byte profile of k_grouped_feats_x (tg_gfeats.cuh)
-            unsigned int m4 = 0, top4 = 0, mintop = 3;
+            unsigned int m4 = 0, top4 = 0, mintop = 3, bot4 = 0;
             for (int j = 0; j < 4; j++) {
                 unsigned mask = (px >> (4 * j)) & 15u, top = (px >> (16 + 2 * j)) & 3u;
-                if (mask) { m4 |= 0xFFu << (8 * j); top4 |= top << (8 * j); if (top < mintop) mintop = top; }
+                if (mask) {
+                    m4 |= 0xFFu << (8 * j); top4 |= top << (8 * j); if (top < mintop) mintop = top;
+                    unsigned bot = 3; while (!((mask >> bot) & 1u)) bot--;
+                    bot4 |= bot << (8 * j);
+                }
             }
+            T.bot4[p][r] = bot4;
             prec[p][r] = make_uint4((unsigned)c | ((px & 0xFFFFu) << 16), m4, top4, (unsigned)jmin | (unsigned)jmax << 2 | mintop << 4);
         }
     }
@@ -213,6 +220,7 @@ static int ensure_tables(tg_env* env, const HostTables& T, int device) {
     CUDA_TRY(env, cudaMemcpyToSymbol(c_cells, T.cells, sizeof T.cells));
     CUDA_TRY(env, cudaMemcpyToSymbol(c_ptab, T.ptab, sizeof T.ptab));
     CUDA_TRY(env, cudaMemcpyToSymbol(c_prec, T.prec, sizeof T.prec));
+    CUDA_TRY(env, cudaMemcpyToSymbol(c_bot4, T.bot4, sizeof T.bot4));
     CUDA_TRY(env, cudaMemcpyToSymbol(c_rowbytes, T.rowbytes, sizeof T.rowbytes));
     CUDA_TRY(env, cudaMemcpyToSymbol(c_n, T.n, sizeof T.n));
     CUDA_TRY(env, cudaMemcpyToSymbol(c_colors, T.colors, sizeof T.colors));

@@ -21,6 +21,8 @@ namespace tg {
 // .y = byte j 0xFF if column j holds cells, .z = byte j = row offset of the top cell of column j,
 // .w = first column | last column << 2 | smallest top offset << 4
 __constant__ uint4 c_prec[7][4];
+// per (piece, rotation): byte j = row offset of the LOWEST cell of matrix column j (0 where the column is empty)
+__constant__ unsigned int c_bot4[7][4];
 
 __device__ __forceinline__ uint32_t bytemax_lt128(uint32_t a, uint32_t b) {   // bytewise max, all bytes < 128
     const uint32_t d = (a | 0x80808080u) - b;                    // bit 7 of byte i = (a_i >= b_i), no borrow between bytes
@@ -78,15 +80,25 @@ struct GFeatsSmem {
     static constexpr size_t bytes = off_info + (size_t)EPB * F;
 };
 
-template <int W, class COLT>
-__global__ void __maxnreg__(W == 10 ? GF_REGS : 96) k_grouped_feats_x(const DevCfg cfg, int64_t n, const uint8_t* __restrict__ hot,
-                                                            const uint8_t* __restrict__ board, uint8_t* __restrict__ feats,
-                                                            uint8_t* legal, const uint8_t* __restrict__ fill_high,
-                                                            uint8_t* __restrict__ info_board) {
+// tile_sync<FUSED>: the W feature warps of a CTA meet; in the fused kernel a logic warp shares the CTA, so they use a named barrier
+template <int W, bool FUSED>
+__device__ __forceinline__ void gf_sync() {
+    if (FUSED) asm volatile("bar.sync 1, %0;" ::"n"(32 * W) : "memory");
+    else __syncthreads();
+}
+
+// One tile of 32 envs (thread = (column xb, env e), tid < 32 * W).  `hot_t` / `board_t` point at the tile's first record (global
+// memory, or the shared-memory stage of the fused kernel), `fill_t` (nullable) at its "illegal action + terminate" flags.
+// FUSED (persistent CTA, the tile buffers are reused): the caller's thread 0 waits for the previous tile's bulk stores before
+// the first barrier; here the stores are only committed.
+template <int W, class COLT, bool FUSED>
+__device__ __forceinline__ void gfeats_tile(const DevCfg& cfg, uint8_t* sm, int& s_nslow, const uint32_t* s_bot, int tid, int64_t base, int nv,
+                                            const uint8_t* hot_t, const uint8_t* board_t, const uint8_t* fill_t,
+                                            uint8_t* __restrict__ feats, uint8_t* legal, uint8_t* __restrict__ info_board,
+                                            int consumed_bar = 0) {
     using S = GFeatsSmem<W, COLT>;
     constexpr int EPB = S::EPB, A = S::A, F = S::F, CS = S::CS, HW = S::HW, HS = S::HS;
     constexpr int NH = (W + 3) / 4, VL = W - 4 * (NH - 1), T = 32 * W;
-    extern __shared__ __align__(16) uint8_t sm[];
     COLT* s_colp = (COLT*)(sm + S::off_colp);
     uint32_t* s_hv = (uint32_t*)(sm + S::off_hv);
     uint8_t* s_hol = sm + S::off_hol;
@@ -99,22 +111,15 @@ __global__ void __maxnreg__(W == 10 ? GF_REGS : 96) k_grouped_feats_x(const DevC
     uint8_t* s_iho = sm + S::off_iho;
     uint8_t* s_info = sm + S::off_info;
     constexpr int W4 = (W + 3) & ~3;
-    __shared__ int s_nslow;
 
-    const int H = cfg.H, tid = threadIdx.x, e = tid & 31, xb = tid >> 5;
-    const int64_t base = (int64_t)blockIdx.x * EPB;
-    const int nv = (int)min((int64_t)EPB, n - base);
+    const int H = cfg.H, e = tid & 31, xb = tid >> 5;
     const bool live = e < nv;
     const COLT field = (COLT(1) << H) - 1;
 
     // ---- phase 1: thread = (column xb, env e): column -> shared memory, its height / holes with row 0 zeroed (Q1) ----
-    if (tid < 28 * 8) s_prec[tid] = (&c_prec[0][0])[tid >> 3];
     if (tid == 0) s_nslow = 0;
-    // programmatic dependent launch (see k_step_ws): this grid may be scheduled while the placement step drains
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    asm volatile("griddepcontrol.wait;" ::: "memory");
     if (live) {
-        const COLT col = ((const COLT*)(board + (base + e) * cfg.board_stride))[xb];
+        const COLT col = ((const COLT*)(board_t + (size_t)e * cfg.board_stride))[xb];
         s_colp[e * CS + P + xb] = col;
         if (xb < 2 * P) s_colp[e * CS + (xb < P ? xb : W + xb)] = ~COLT(0);          // bedrock wall columns
         int hgt, hol;
@@ -126,9 +131,11 @@ __global__ void __maxnreg__(W == 10 ? GF_REGS : 96) k_grouped_feats_x(const DevC
         s_hol[e * ((W + 3) & ~3) + xb] = (uint8_t)hol;
         if (W + xb < ((W + 3) & ~3)) s_hol[e * ((W + 3) & ~3) + W + xb] = 0;
         if (xb == 0)   // bit 31: illegal action + terminate -> the observation is filled with `high`
-            s_w0[e] = (*(const uint32_t*)(hot + (base + e) * 32) & 0x7FFFFFFFu) | ((fill_high && fill_high[base + e]) ? 0x80000000u : 0u);
+            s_w0[e] = (*(const uint32_t*)(hot_t + (size_t)e * 32) & 0x7FFFFFFFu) | ((fill_t && fill_t[e]) ? 0x80000000u : 0u);
     }
-    __syncthreads();
+    gf_sync<W, FUSED>();
+    // fused kernel: the staged records are not read any more -- the logic warp may load the tile after next into this stage
+    if (FUSED && consumed_bar) asm volatile("bar.arrive %0, %1;" ::"r"(consumed_bar), "n"(32 * W + 32) : "memory");
     // ---- phase 3: the four rotations of (env e, column xb) ----
     if (live && info_board) {
         // info["board"] = FeatureVectorObservation of the real observation (wrappers/grouped.py:260-264): rows 0-1 zeroed
@@ -197,17 +204,27 @@ __global__ void __maxnreg__(W == 10 ? GF_REGS : 96) k_grouped_feats_x(const DevC
                 const COLT v = colp[P + c];
                 LR &= ((unsigned)(c + P - x) < 4u) ? ~COLT(0) : v;
             }
+            // rows that are full whatever the piece does (a poked board may hold them), and cells in row 0 under the window
+            const COLT preFull = LR & cj[0] & cj[1] & cj[2] & cj[3];
+            COLT top0 = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) top0 |= ((unsigned)(x + j - P) < (unsigned)W) ? cj[j] : COLT(0);
+            const bool odd = ((uint32_t)top0 & 1u) != 0 || preFull != 0;
 #pragma unroll
             for (int r = 0; r < 4; r++) {
                 const int rot = (rot0 + r) & 3;                         // cumulative rot90 presses (wrappers/grouped.py:153-154)
                 const uint4 pr = s_prec[(piece * 4 + rot) * 8 + (e & 7)];
-                COLT B = 0;
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const int c = (pr.x >> (4 * k)) & 15;
-                    B |= colp[x + (c & 3)] >> (c >> 2);
-                }
-                const int y = ctz_t<COLT>(B >> 1);                      // while !collision(y+1): y++ from y = 0
+                const uint32_t bot4 = s_bot[piece * 4 + rot];
+                // Landing row from the column heights: the piece comes down from row 0 through empty rows, so the first collision
+                // is its lowest cell of some column j meeting that column's top cell, at y* = min_j (H - h_j - bot_j); it rests at
+                // y = y* - 1 (wrappers/grouped.py:160-161: while !collision(y+1): y++ from y = 0).  Exact when the heights
+                // are the true column tops (no cell in row 0 under the window: the heights have row 0 zeroed, Q1) and y* >= 1;
+                // every other placement is evaluated from the column bitboards in the dense second pass.
+                const uint32_t M4 = pr.y;
+                const uint32_t OM = O4 & M4;
+                const uint32_t Tb = OM + bot4;                          // all bytes < 128
+                const uint32_t m2 = __vmaxu4(Tb, Tb >> 16);
+                const int y = H - 1 - (int)max(m2 & 255u, (m2 >> 8) & 255u);
                 const int jmin = pr.w & 3, jmax = (pr.w >> 2) & 3, mintop = (pr.w >> 4) & 3;
                 const int c0 = x + jmin - P, c1 = x + jmax - P;
                 uint32_t hw[NH];
@@ -221,16 +238,12 @@ __global__ void __maxnreg__(W == 10 ? GF_REGS : 96) k_grouped_feats_x(const DevC
                     legal_w |= 1u << (8 * r);
 #pragma unroll
                     for (int k = 0; k < NH; k++) hw[k] = 0;
-                    summary = 0;                                        // game over: zeros board
-                    if (!((B >> y) & 1)) {
-                        COLT full = LR;
-#pragma unroll
-                        for (int j = 0; j < 4; j++) full &= cj[j] | ((COLT)((pr.x >> (16 + 4 * j)) & 15u) << y);
-                        if (full != 0 || y + mintop == 0) {
+                    summary = 0;                                        // game over (decided in the second pass): zeros board
+                    {
+                        // a row can only fill up where the columns outside the window are all set: LR bits y .. y + 3
+                        if (odd || y < 0 || y + mintop == 0 || ((uint32_t)(LR >> (y & (8 * (int)sizeof(COLT) - 1))) & 15u) != 0) {
                             s_slow[atomicAdd(&s_nslow, 1)] = (unsigned short)(e * A + 4 * xb + r);
                         } else {
-                            const uint32_t M4 = pr.y;
-                            const uint32_t OM = O4 & M4;
                             const uint32_t T4 = ((uint32_t)(H - y) * 0x01010101u - pr.z) & M4;
                             const uint32_t N4 = bytemax_lt128(OM, T4);
                             // all bytes < 128: signed dot products; sum(new) - sum(old) - 4 cells
@@ -267,7 +280,7 @@ __global__ void __maxnreg__(W == 10 ? GF_REGS : 96) k_grouped_feats_x(const DevC
         for (int i = 0; i < F; i++) dst[i] = o[i];
         s_legalw[e * W + xb] = legal_w;
     }
-    __syncthreads();
+    gf_sync<W, FUSED>();
     if (info_board && xb == W - 1 && live) {
         int maxh = 0, holes = 0, bump = 0, prev = 0;
 #pragma unroll
@@ -301,7 +314,8 @@ __global__ void __maxnreg__(W == 10 ? GF_REGS : 96) k_grouped_feats_x(const DevC
                 const int c = (pr.x >> (4 * q)) & 15;
                 B |= colp[x + (c & 3)] >> (c >> 2);
             }
-            const int y = ctz_t<COLT>(B >> 1);
+            const int y = ctz_t<COLT>(B >> 1);                          // while !collision(y+1): y++ from y = 0
+            if ((B >> y) & 1) continue;                                 // game over: the staged row is already the zeros board
             const int jmin = pr.w & 3, c0 = x + jmin - P, c1 = x + (int)((pr.w >> 2) & 3) - P;
             COLT full = field;
             for (int c = 0; c < W; c++) {
@@ -310,9 +324,55 @@ __global__ void __maxnreg__(W == 10 ? GF_REGS : 96) k_grouped_feats_x(const DevC
                 if ((unsigned)j < 4u) v |= (COLT)((pr.x >> (16 + 4 * j)) & 15u) << y;
                 full &= v;
             }
-            const COLT keep = (full != 0 ? ~full : ~COLT(1)) & field;
             uint8_t* out = s_feats + (size_t)it * F;
-            int s_max = 0, s_hol = 0, s_bmp = 0, prev = 0;
+            if (full == 0) {
+                // no row is cleared (the usual reason to be here: the piece lands in the top rows): only the window's columns change.
+                // Their heights / holes come from the bitboards with row 0 zeroed (Q1); the rest of the row is the env's base vector.
+                const COLT keep0 = ~COLT(1) & field;
+                uint32_t N4 = 0;
+                int holes = 0;
+                {
+                    const uint32_t* how = (const uint32_t*)(s_hol + es * W4);
+#pragma unroll
+                    for (int q = 0; q < W4 / 4; q++) holes = __dp4a(how[q], 0x01010101u, (uint32_t)holes);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int c = x + j - P;
+                    if ((unsigned)c < (unsigned)W) {
+                        const COLT u = (colp[x + j] | ((COLT)((pr.x >> (16 + 4 * j)) & 15u) << y)) & keep0;
+                        const int hgt = u != 0 ? H - ctz_t<COLT>(u) : 0;
+                        N4 |= (uint32_t)hgt << (8 * j);
+                        holes += hgt - popc_t<COLT>(u) - (int)s_hol[es * W4 + c];
+                    }
+                }
+                const uint32_t* hvw = s_hv + es * HS;
+                const int wi = x >> 2, sh = (x & 3) * 8;
+                const uint32_t Nlo = N4 << sh, Nhi = __funnelshift_l(N4, 0u, sh);
+                const uint32_t Mlo = 0xFFFFFFFFu << sh, Mhi = __funnelshift_l(0xFFFFFFFFu, 0u, sh);
+                const uint32_t Wl = (hvw[wi] & ~Mlo) | Nlo, Wh = (hvw[wi + 1] & ~Mhi) | Nhi;
+                uint32_t hw[NH];
+#pragma unroll
+                for (int q = 0; q < NH; q++) hw[q] = (q + 1 == wi) ? Wl : ((q == wi) ? Wh : hvw[q + 1]);
+                uint32_t bump = 0, mx4 = 0;
+#pragma unroll
+                for (int q = 0; q < NH - 1; q++) bump = __vsadu4(hw[q], __funnelshift_r(hw[q], hw[q + 1], 8)) + bump;
+                {
+                    const uint32_t l = hw[NH - 1];
+                    const uint32_t a2 = VL == 4 ? l : __byte_perm(l, 0, VL == 1 ? 0x4444 : (VL == 2 ? 0x4410 : 0x4210));
+                    const uint32_t b2 = __byte_perm(l, 0, VL == 1 ? 0x4444 : (VL == 2 ? 0x4411 : (VL == 3 ? 0x4221 : 0x3321)));
+                    bump = __vsadu4(a2, b2) + bump;
+                }
+#pragma unroll
+                for (int q = 0; q < NH; q++) mx4 = __vmaxu4(mx4, hw[q]);   // (bytes beyond W in the last word are pad zeros)
+                const uint32_t maxh = max(max(mx4 & 255u, (mx4 >> 8) & 255u), max((mx4 >> 16) & 255u, mx4 >> 24));
+#pragma unroll
+                for (int c = 0; c < W; c++) out[c] = (uint8_t)(hw[c >> 2] >> (8 * (c & 3)));
+                out[W] = (uint8_t)maxh; out[W + 1] = (uint8_t)holes; out[W + 2] = (uint8_t)bump;
+                continue;
+            }
+            const COLT keep = ~full & field;
+            int t_max = 0, t_hol = 0, t_bmp = 0, prev = 0;
 #pragma unroll 2
             for (int c = 0; c < W; c++) {
                 COLT v = colp[c + P];
@@ -326,11 +386,11 @@ __global__ void __maxnreg__(W == 10 ? GF_REGS : 96) k_grouped_feats_x(const DevC
                     hol = hgt - popc_t<COLT>(u);
                 }
                 out[c] = (uint8_t)hgt;
-                s_hol += hol; s_max = max(s_max, hgt);
-                if (c > 0) s_bmp += abs(hgt - prev);
+                t_hol += hol; t_max = max(t_max, hgt);
+                if (c > 0) t_bmp += abs(hgt - prev);
                 prev = hgt;
             }
-            out[W] = (uint8_t)s_max; out[W + 1] = (uint8_t)s_hol; out[W + 2] = (uint8_t)s_bmp;
+            out[W] = (uint8_t)t_max; out[W + 1] = (uint8_t)t_hol; out[W + 2] = (uint8_t)t_bmp;
         }
     }
     // ---- phase 5: the tile is contiguous in global memory: full tiles leave as TMA bulk copies issued by one thread ----
@@ -339,22 +399,177 @@ __global__ void __maxnreg__(W == 10 ? GF_REGS : 96) k_grouped_feats_x(const DevC
         uint8_t* gl = legal + (size_t)base * A;
         if (nv == EPB) {
             fence_async_smem();            // generic-proxy writes of this thread -> visible to the async proxy
-            __syncthreads();
+            gf_sync<W, FUSED>();
             if (tid == 0) {
                 bulk_s2g(gf, s_featw, (uint32_t)(EPB * A * F));
                 bulk_s2g(gl, s_legalw, (uint32_t)(EPB * A));
                 if (info_board) bulk_s2g(info_board + (size_t)base * F, s_info, (uint32_t)(EPB * F));
                 bulk_commit();
-                bulk_wait_read();          // shared memory must stay alive until the copies have read it
+                if (!FUSED) bulk_wait_read();   // shared memory must stay alive until the copies have read it
             }
         } else {
-            __syncthreads();
+            gf_sync<W, FUSED>();
             const int words = nv * W * F;
             for (int i = tid; i < words; i += T) ((uint32_t*)gf)[i] = s_featw[i];
             if (tid < nv * W) ((uint32_t*)gl)[tid] = s_legalw[tid];
             if (info_board)
                 for (int i = tid; i < nv * F; i += T) info_board[(size_t)base * F + i] = s_info[i];
         }
+    }
+}
+
+template <int W, class COLT>
+__global__ void __maxnreg__(W == 10 ? GF_REGS : 96) k_grouped_feats_x(const DevCfg cfg, int64_t n, const uint8_t* __restrict__ hot,
+                                                            const uint8_t* __restrict__ board, uint8_t* __restrict__ feats,
+                                                            uint8_t* legal, const uint8_t* __restrict__ fill_high,
+                                                            uint8_t* __restrict__ info_board) {
+    using S = GFeatsSmem<W, COLT>;
+    extern __shared__ __align__(16) uint8_t sm[];
+    __shared__ int s_nslow;
+    __shared__ uint32_t s_bot[28];
+    const int tid = threadIdx.x;
+    const int64_t base = (int64_t)blockIdx.x * S::EPB;
+    const int nv = (int)min((int64_t)S::EPB, n - base);
+    if (tid < 28 * 8) ((uint4*)(sm + S::off_prec))[tid] = (&c_prec[0][0])[tid >> 3];
+    if (tid >= 256 && tid < 256 + 28) s_bot[tid - 256] = (&c_bot4[0][0])[tid - 256];
+    // programmatic dependent launch (see k_step_ws): this grid may be scheduled while the placement step drains
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    gfeats_tile<W, COLT, false>(cfg, sm, s_nslow, s_bot, tid, base, nv, hot + base * 32, board + base * cfg.board_stride,
+                                fill_high ? fill_high + base : nullptr, feats, legal, info_board);
+}
+
+// ---- fused placement step + enumeration (GroupedActionsObservations.step, wrappers/grouped.py:209-269, followed by the
+// observation of the new state) -- one persistent kernel instead of k_step_ws<.., 2> + k_grouped_feats_x.
+// CTA = W feature warps + NLW logic warps.  The logic warps (lane = env; warp lw takes every NLW-th tile of the CTA) run ahead:
+// each waits for the TMA-staged records of its next tile (NS = 2 NLW stages), applies the placement (decode, legality, hard
+// drop, commit, line clear, spawn, autoreset), writes the 5-tuple and sends the records back with bulk stores, while the
+// feature warps enumerate the 4W placements of the tile before, straight from the staged records.  The feature kernel is bound
+// by integer issue with a third of its issue slots idle (barrier phases); the ~40 M warp instructions of the step hide there,
+// and the records are read from HBM once instead of twice.  Named barriers: 1 = feature warps, 2 + s = ready[s] (logic ->
+// features), 2 + NS + s = consumed[s] (features -> logic: stage s may be reloaded).
+template <int W, class COLT>
+struct GFusedSmem {
+    using S = GFeatsSmem<W, COLT>;
+    static constexpr int NLW = 2, NS = 2 * NLW;
+    static constexpr size_t off_tab = (S::bytes + 127) & ~size_t(127);        // rowbytes[112] u32, cells[28] u16 (+8 pad), n[7] i32
+    static constexpr size_t off_bar = off_tab + 112 * 4 + 64 + 32;
+    static constexpr size_t off_box = off_bar + 64;                           // [32] boxes (unused by the features), [NS][32] fill flags
+    static constexpr size_t off_stage = (off_box + 32 * 4 + NS * 32 + 127) & ~size_t(127);
+    static __host__ __device__ size_t stage_bytes(const DevCfg& d) { return (((size_t)32 * 32 + 127) & ~size_t(127)) + (((size_t)32 * d.board_stride + 16 + 127) & ~size_t(127)) + (((size_t)32 * d.rng_stride + 127) & ~size_t(127)); }
+    static size_t bytes(const DevCfg& d) { return off_stage + NS * stage_bytes(d); }
+    static constexpr int threads = 32 * (W + NLW);
+};
+
+#ifndef GFU_REGS
+#define GFU_REGS 40   // 12 warps x 40 registers: 4 CTAs per SM
+#endif
+template <int W, class COLT, bool XT>
+__global__ void __maxnreg__(GFU_REGS) k_grouped_step_feats(const __grid_constant__ StepParams p, uint8_t* __restrict__ feats, uint8_t* legal,
+                                                          uint8_t* __restrict__ info_board) {
+    using S = GFeatsSmem<W, COLT>;
+    using FS = GFusedSmem<W, COLT>;
+    constexpr int E = 32, TF = 32 * W, NLW = FS::NLW, NS = FS::NS;
+    extern __shared__ __align__(128) uint8_t sm[];
+    __shared__ int s_nslow;
+    __shared__ uint32_t s_bot[28];
+    const DevCfg& cfg = p.cfg;
+    const int tid = threadIdx.x;
+    const int BS = cfg.board_stride, RS = cfg.rng_stride;
+    uint32_t* s_rowbytes = (uint32_t*)(sm + FS::off_tab);
+    unsigned short* s_cells = (unsigned short*)(s_rowbytes + 112);
+    int* s_n = (int*)(s_rowbytes + 112 + 16);
+    uint64_t* bar = (uint64_t*)(sm + FS::off_bar);
+    uint32_t* s_box = (uint32_t*)(sm + FS::off_box);
+    uint8_t* s_fill = (uint8_t*)(s_box + 32);          // [NS][32]
+    const size_t st_hot = ((size_t)E * 32 + 127) & ~size_t(127), st_brd = ((size_t)E * BS + 16 + 127) & ~size_t(127);
+    const size_t st_all = FS::stage_bytes(cfg);
+    uint8_t* stage0 = sm + FS::off_stage;
+
+    if (tid < 28 * 8) ((uint4*)(sm + S::off_prec))[tid] = (&c_prec[0][0])[tid >> 3];
+    if (tid >= 256 && tid < 256 + 28) s_bot[tid - 256] = (&c_bot4[0][0])[tid - 256];
+    for (int i = tid; i < 112; i += blockDim.x) s_rowbytes[i] = (&c_rowbytes[0][0][0])[i];
+    if (tid < 28) s_cells[tid] = (&c_cells[0][0])[tid];
+    if (tid < 7) s_n[tid] = c_n[tid];
+    if (tid == 0) {
+        for (int s = 0; s < NS; s++) mbar_init(bar + s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    const int64_t ntiles = (p.n + E - 1) / E;
+    const int64_t G = gridDim.x;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    __syncthreads();
+
+    if (tid >= TF) {
+        // ===== logic warps: TMA producer + game logic, ahead of the feature warps =====
+        const int lane = tid & 31, lw = (tid - TF) >> 5;
+        Tabs tb;
+        tb.cells = s_cells; tb.rowbytes = s_rowbytes; tb.n = s_n; tb.ptab = nullptr;
+        auto issue_load = [&](int64_t tile, int s) {
+            const int64_t base = tile * E;
+            const int nv = (int)min((int64_t)E, p.n - base);
+            uint8_t* st = stage0 + s * st_all;
+            mbar_expect_tx(bar + s, (uint32_t)(nv * (32 + BS + RS)));
+            bulk_g2s(st, p.hot + base * 32, (uint32_t)(nv * 32), bar + s);
+            bulk_g2s(st + st_hot, p.board + base * BS, (uint32_t)(nv * BS), bar + s);
+            bulk_g2s(st + st_hot + st_brd, p.rng + base * RS, (uint32_t)(nv * RS), bar + s);
+        };
+        if (lane == 0) {   // this warp's first two tiles: k = lw and k = lw + NLW
+            if ((int64_t)blockIdx.x + lw * G < ntiles) issue_load((int64_t)blockIdx.x + lw * G, lw);
+            if ((int64_t)blockIdx.x + (lw + NLW) * G < ntiles) issue_load((int64_t)blockIdx.x + (lw + NLW) * G, lw + NLW);
+        }
+        TileStats stt = {0, 0, 0, 0};
+        for (int64_t k = lw; blockIdx.x + k * G < ntiles; k += NLW) {
+            const int64_t tile = blockIdx.x + k * G, base = tile * E;
+            const int s = (int)(k % NS);
+            const int nv = (int)min((int64_t)E, p.n - base);
+            uint8_t* st = stage0 + s * st_all;
+            int action = 0;
+            if (lane < nv) action = p.actions[base + lane];
+            mbar_wait(bar + s, (uint32_t)((k / NS) & 1));
+            uint32_t dirty = 0;
+            if (lane < nv)
+                dirty = logic_one_env<COLT, false, 2, XT>(p, tb, base + lane, lane, action, (uint32_t*)st, st + st_hot, st + st_hot + st_brd, s_box, stt, base + lane);
+            s_fill[s * 32 + lane] = (uint8_t)((dirty >> 2) & 1u);
+            const int ndirty = __popc(__ballot_sync(0xffffffffu, (dirty & 1u) != 0));
+            fence_async_smem();
+            __syncwarp();
+            asm volatile("bar.arrive %0, %1;" ::"r"(2 + s), "n"(TF + 32) : "memory");   // ready[s]: the feature warps may read stage s
+            // write-back: hot tile, board records (whole tile when most envs committed -- the rule in the grouped mode), rng records
+            const bool whole = ndirty >= p.whole_tile_min;
+            if (lane == 0) {
+                bulk_s2g(p.hot + base * 32, st, (uint32_t)(nv * 32));
+                if (whole) bulk_s2g(p.board + base * BS, st + st_hot, (uint32_t)(nv * BS));
+            }
+            if (lane < nv) {
+                if ((dirty & 1) && !whole) bulk_s2g(p.board + (base + lane) * BS, st + st_hot + lane * BS, (uint32_t)BS);
+                if (dirty & 2) bulk_s2g(p.rng + (base + lane) * RS, st + st_hot + st_brd + lane * RS, (uint32_t)RS);
+            }
+            bulk_commit();
+            // stage s is free again once the feature warps have copied tile k's columns and the stores above have read it
+            if (blockIdx.x + (k + NS) * G < ntiles) {
+                asm volatile("bar.sync %0, %1;" ::"r"(2 + NS + s), "n"(TF + 32) : "memory");   // consumed[s]
+                bulk_wait_read();
+                __syncwarp();
+                if (lane == 0) issue_load(blockIdx.x + (k + NS) * G, s);
+            }
+        }
+        bulk_wait_all();
+        if (p.stats) flush_stats(p.stats, stt.ep, stt.ret, stt.len, stt.lines);
+    } else {
+        // ===== feature warps =====
+        for (int64_t k = 0; blockIdx.x + k * G < ntiles; k++) {
+            const int64_t tile = blockIdx.x + k * G, base = tile * E;
+            const int s = (int)(k % NS);
+            const int nv = (int)min((int64_t)E, p.n - base);
+            const uint8_t* st = stage0 + s * st_all;
+            asm volatile("bar.sync %0, %1;" ::"r"(2 + s), "n"(TF + 32) : "memory");       // ready[s]
+            if (tid == 0) bulk_wait_read();     // the previous tile's feature stores have left the staging buffers
+            gfeats_tile<W, COLT, true>(cfg, sm, s_nslow, s_bot, tid, base, nv, st, st + st_hot, s_fill + s * 32, feats, legal, info_board,
+                                       blockIdx.x + (k + NS) * G < ntiles ? 2 + NS + s : 0);
+        }
+        if (tid == 0) bulk_wait_all();
     }
 }
 

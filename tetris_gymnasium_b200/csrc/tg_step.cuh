@@ -230,7 +230,7 @@ __device__ __forceinline__ uint32_t logic_one_env(const StepParams& p, const Tab
     g.seq = p.seq ? p.seq + e * cfg.seq_len : nullptr;
     g.gid = cfg.env_id_offset + (uint64_t)e;
     g.dirty = false;
-    bool need_reset = false;
+    bool need_reset = false, run_ok = true;
     const int mode = MODE >= 0 ? MODE : p.mode;
     if (mode == 1) {
         need_reset = (!p.reset_mask || p.reset_mask[e]);
@@ -251,7 +251,7 @@ __device__ __forceinline__ uint32_t logic_one_env(const StepParams& p, const Tab
                 act = cfg.act_hard;
             } else if (cfg.terminate_on_illegal) {
                 res.reward = cfg.r_invalid; res.terminated = 1;   // env untouched, episode ends
-                run = false;
+                run = false; run_ok = false;
             } else {
                 act = cfg.act_noop;
                 invalid = true;
@@ -290,7 +290,8 @@ __device__ __forceinline__ uint32_t logic_one_env(const StepParams& p, const Tab
         placement_features<COLT>(cfg, (const COLT*)rec, tb.cells[h.p * 4 + h.r], h.x, h.y, show != 0, false, COLT(3), f, ln);
         for (int i = 0; i < cfg.F; i++) p.info_board[e * cfg.F + i] = f[i];
     }
-    return (uint32_t)res.dirty | ((uint32_t)g.dirty << 1);
+    // bit 2 (grouped mode): an illegal action ended the episode -- the observation is filled with `high` (= p.fill_high[e])
+    return (uint32_t)res.dirty | ((uint32_t)g.dirty << 1) | ((mode == 2 && !need_reset && res.terminated && !run_ok) ? 4u : 0u);
 }
 
 // ---- observation images of one tile (called by `nt` cooperating threads, `t` = index among them) ------

@@ -739,6 +739,34 @@ extern "C" int tg_grouped_step(tg_env* env, tg_state st, int64_t n, const int32_
     const bool info_in_feats = d_info_board && ((uintptr_t)d_info_board & 15) == 0 && gfeats_fast(env, d_feats, d_legal) && !getenv("TG_INFO_IN_STEP");
     p.legal = d_legal; p.info_board = info_in_feats ? nullptr : d_info_board; p.fill_high = (uint8_t*)env->stage[3];
     p.mode = 2;
+    // Feature observation of the reference board on 32-bit columns, small batches: ONE persistent kernel applies the placement and
+    // enumerates the next state's placements (k_grouped_step_feats, tg_gfeats.cuh) -- one launch and one pass over the records
+    // instead of two (4,096 envs: 16 instead of 20 us per step).  From 64 K envs on the two-kernel path is faster (1 M envs: 505
+    // against 609 us: the fused kernel's code no longer fits the instruction cache next to 40 feature warps per SM).
+    // TG_GROUPED_SPLIT=1 / TG_GROUPED_FUSED=1 force one or the other.
+    const bool fused_ok = !any_obs && !d_boards && d_feats && env->dev.W == 10 && !env->col64 && gfeats_fast(env, d_feats, d_legal) &&
+                          (!d_info_board || info_in_feats);
+    if (fused_ok && !getenv("TG_GROUPED_SPLIT") && (n < 65536 || getenv("TG_GROUPED_FUSED"))) {
+        const DevCfg& d = env->dev;
+        const bool xt = d.NPC != 7 || d.holder_size > 1;
+        typedef void (*fused_t)(const StepParams, uint8_t*, uint8_t*, uint8_t*);
+        fused_t kern = xt ? (fused_t)k_grouped_step_feats<10, uint32_t, true> : (fused_t)k_grouped_step_feats<10, uint32_t, false>;
+        const size_t smem = GFusedSmem<10, uint32_t>::bytes(d);
+        rc = raise_smem_limit(env, (void*)kern, smem); if (rc) return rc;
+        if (env->fused_grid_max <= 0) {
+            int per_sm = 0;
+            CUDA_TRY(env, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            CUDA_TRY(env, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, GFusedSmem<10, uint32_t>::threads, smem));
+            if (per_sm < 1) return fail(env, TG_ERR_CONFIG, "fused grouped kernel does not fit: %zu B shared memory per CTA", smem);
+            env->fused_grid_max = (int64_t)env->num_sms * per_sm;
+        }
+        p.cfg = d; p.E = 32; p.whole_tile_min = 16;
+        if (const char* t = getenv("TG_WHOLE")) p.whole_tile_min = atoi(t);
+        const int64_t ntiles = (n + 31) / 32;
+        const int64_t grid = env->fused_grid_max < ntiles ? env->fused_grid_max : ntiles;
+        CUDA_TRY(env, launch_pdl(kern, (unsigned)grid, (unsigned)GFusedSmem<10, uint32_t>::threads, smem, (cudaStream_t)stream, p, d_feats, d_legal, d_info_board));
+        return TG_OK;
+    }
     rc = launch_step(env, p, (cudaStream_t)stream); if (rc) return rc;
     if (d_feats || d_boards)
         return launch_grouped_observe(env, st, n, d_feats, d_boards, d_legal, (const uint8_t*)env->stage[3], (cudaStream_t)stream,
