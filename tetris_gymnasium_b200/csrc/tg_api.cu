@@ -1018,6 +1018,17 @@ extern "C" int tg_fn_step(int32_t width, int32_t height, int32_t queue_size, int
     p.n = n; p.board_in = d_board_in; p.board_out = d_board_out; p.sc_in = d_scalars_in; p.sc_out = d_scalars_out;
     p.actions = d_actions; p.seq = d_piece_seq; p.seq_len = seq_len;
     p.obs = d_obs; p.reward = d_reward; p.terminated = d_terminated; p.lines = d_lines;
+    // the tile kernel (bulk copies of whole tiles) needs 16-byte aligned arrays; TG_FN_V1=1 keeps the thread-per-env kernel
+    const bool aligned = (((uintptr_t)d_board_in | (uintptr_t)d_board_out | (uintptr_t)d_scalars_in | (uintptr_t)d_scalars_out | (uintptr_t)d_obs) & 15) == 0;
+    if (aligned && p.H <= 64 && !getenv("TG_FN_V1")) {
+        const FnTileSmem m = fn_tile_smem(p.Hp * p.Wp, p.H * p.W, FN_S + p.Q);
+        if (cudaFuncSetAttribute(k_fn_step_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, m.bytes) != cudaSuccess)
+            return fail(nullptr, TG_ERR_CONFIG, "tg_fn_step: board too large for the shared-memory tile (%d B)", m.bytes);
+        k_fn_step_tile<<<(unsigned)((n + 31) / 32), 256, (size_t)m.bytes, (cudaStream_t)stream>>>(p);
+        cudaError_t e2 = cudaGetLastError();
+        if (e2 != cudaSuccess) return fail(nullptr, TG_ERR_CUDA, "k_fn_step_tile: %s", cudaGetErrorString(e2));
+        return TG_OK;
+    }
     const int T = 64;
     int bstr = (p.Hp * p.Wp + 3) / 4 * 4;
     if (((bstr / 4) & 1) == 0) bstr += 4;                                  // odd word stride: conflict-free per-env access

@@ -8,6 +8,7 @@
 // in, new arrays out (in == out aliases are allowed).  One thread per env on byte boards staged in shared memory.
 #pragma once
 #include "tg_device.cuh"
+#include "tg_step.cuh"   // mbarrier / bulk-copy wrappers
 
 namespace tg {
 
@@ -212,6 +213,219 @@ __global__ void k_fn_step(const FnParams p, int bstr /* bytes per staged board, 
             else
                 for (int k = tid; k < bytes; k += T) og[k] = s_obs[k];
         }
+    }
+}
+
+// ---- tile variant (the default): CTA = 32 envs x 8 threads ---------------------------------------------------------------
+// The tile's boards, scalars and observations are contiguous in global memory, so they move with 1-D bulk TMA copies (one
+// thread issues them; full tiles) and sit in shared memory in the SAME layout.  Thread (e, t): t = 0 owns env e's game logic
+// (owners are spread over all eight warps: four envs per warp keep the divergence of the per-env branches small); the row scan
+// of core.clear_filled_rows and the observation are produced by all eight threads of the env.
+//   A  owner: action, gravity, lock decision, place the piece's cells
+//   B  all:   full-row mask of the env (rows t, t + 8, ...), OR-combined with three shuffles
+//   C  owner: row compaction when a row is full (rare), score, next piece, game-over test, scalars and 5-tuple out
+//   D  all:   observation words ((board > 0), cropped);  owner: active piece overlay
+//   E  bulk stores of the three tiles
+struct FnTileSmem {
+    int off_sc, off_obs, off_bar, bytes;
+};
+__host__ __device__ inline FnTileSmem fn_tile_smem(int OB, int HW, int NS) {
+    FnTileSmem m;
+    int o = (32 * OB + 15) & ~15;
+    m.off_sc = o; o += 32 * NS * 4;
+    m.off_obs = o; o += (32 * HW + 15) & ~15;
+    m.off_bar = o; o += 16;
+    m.bytes = o;
+    return m;
+}
+
+__global__ void __launch_bounds__(256) k_fn_step_tile(const FnParams p) {
+    extern __shared__ __align__(128) uint8_t fsm[];
+    constexpr int E = 32, TPE = 8;
+    const int tid = threadIdx.x, e_l = tid >> 3, t = tid & 7;
+    const int64_t base = (int64_t)blockIdx.x * E;
+    const int nv = (int)min((int64_t)E, p.n - base);
+    const int OB = p.Hp * p.Wp, NS = FN_S + p.Q, HW = p.H * p.W;
+    const FnTileSmem m = fn_tile_smem(OB, HW, NS);
+    int8_t* s_board = (int8_t*)fsm;                       // [E][OB]
+    int32_t* s_sc = (int32_t*)(fsm + m.off_sc);           // [E][NS]
+    int8_t* s_obs = (int8_t*)(fsm + m.off_obs);           // [E][HW]
+    uint64_t* bar = (uint64_t*)(fsm + m.off_bar);
+    const bool full_tile = nv == E;
+    if (tid == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    __syncthreads();
+    if (full_tile) {
+        if (tid == 0) {
+            mbar_expect_tx(bar, (uint32_t)(E * (OB + NS * 4)));
+            bulk_g2s(s_board, p.board_in + base * OB, (uint32_t)(E * OB), bar);
+            bulk_g2s(s_sc, p.sc_in + base * NS, (uint32_t)(E * NS * 4), bar);
+        }
+        mbar_wait(bar, 0);
+    } else {
+        for (int k = tid; k < nv * OB; k += 256) s_board[k] = p.board_in[base * OB + k];
+        for (int k = tid; k < nv * NS; k += 256) s_sc[k] = p.sc_in[base * NS + k];
+        __syncthreads();
+    }
+    const bool live = e_l < nv, owner = live && t == 0;
+    const int64_t e = base + e_l;
+    int8_t* b = s_board + (size_t)e_l * OB;
+    int32_t* sc = s_sc + e_l * NS;
+    const int spawn_x = p.Wp / 2 - 2;   // core.get_initial_x_y: 4x4 matrices (functional/core.py:66-83)
+    float old_score = 0.f;
+    int piece = 0, rot = 0, x = 0, y = 0, drop_reward = 0;
+    bool locked = false;
+    // ---- A
+    if (!p.actions) {
+        // tetris_fn.reset (envs/tetris_fn.py:318-367): the board by all eight threads, the scalars by the owner
+        if (live)
+            for (int k = t; k < OB; k += TPE) {
+                const int r = k / p.Wp, c = k - r * p.Wp;
+                b[k] = (r < p.H && c >= P && c < P + p.W) ? 0 : 1;
+            }
+        if (owner) {
+            sc[FN_KEY1] = 0;
+            fn_new_bag(p, e, sc);
+            sc[FN_ACTIVE] = sc[FN_S]; sc[FN_QIDX] = 1;
+            sc[FN_ROT] = 0; sc[FN_X] = spawn_x; sc[FN_Y] = 0; sc[FN_OVER] = 0; sc[FN_SCORE] = __float_as_int(0.f);
+        }
+    } else if (owner) {
+        old_score = __int_as_float(sc[FN_SCORE]);
+        if (!sc[FN_OVER]) {
+            // tetris_fn.update_state (envs/tetris_fn.py:161-273)
+            const int a = p.actions[e];
+            piece = sc[FN_ACTIVE]; rot = sc[FN_ROT]; x = sc[FN_X]; y = sc[FN_Y];
+            uint32_t cells = c_cells[piece][rot];
+            if (a == 0) { if (!fn_collision(p, b, cells, x - 1, y)) x -= 1; }
+            else if (a == 1) { if (!fn_collision(p, b, cells, x + 1, y)) x += 1; }
+            else if (a == 2) { if (!fn_collision(p, b, cells, x, y + 1)) { y += 1; drop_reward = 1; } }
+            else if (a == 3 || a == 4) {
+                int nr = (rot + (a == 4 ? 1 : 3)) & 3;   // 3 = counter-clockwise, 4 = clockwise (envs/tetris_fn.py:470-478)
+                if (!fn_collision(p, b, c_cells[piece][nr], x, y)) { rot = nr; cells = c_cells[piece][nr]; }
+            } else if (a == 6) {                          // core.hard_drop (functional/core.py:230-251)
+                int ny = y;
+                while (!fn_collision(p, b, cells, x, ny + 1)) ny++;
+                drop_reward = 2 * (ny - y);
+                y = ny;
+            }
+            int yg = y;
+            if (p.gravity && !fn_collision(p, b, cells, x, y + 1)) yg = y + 1;   // core.graviy_step
+            const bool should_lock = (yg == y) && p.gravity;
+            y = yg;
+            locked = should_lock || a == 6;
+            if (locked) {
+                // place_active_tetromino (envs/tetris_fn.py:370-413) / core.lock_active_tetromino
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    int c = (cells >> (4 * k)) & 15;
+                    b[(y + (c >> 2)) * p.Wp + x + (c & 3)] += (int8_t)(piece + 2);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // ---- B: core.clear_filled_rows' row test (functional/core.py:185-227: all(sub_board > 0)), every row, every env
+    uint32_t fmask_lo = 0, fmask_hi = 0;
+    if (live && p.actions) {
+        for (int r = t; r < p.H; r += TPE) {
+            const int8_t* row = b + r * p.Wp + P;
+            bool full = true;
+            for (int c = 0; c < p.W; c++) full &= row[c] > 0;
+            if (full) { if (r < 32) fmask_lo |= 1u << r; else fmask_hi |= 1u << (r - 32); }
+        }
+    }
+#pragma unroll
+    for (int o = 1; o < TPE; o <<= 1) {
+        fmask_lo |= __shfl_xor_sync(0xffffffffu, fmask_lo, o);
+        fmask_hi |= __shfl_xor_sync(0xffffffffu, fmask_hi, o);
+    }
+    // ---- C
+    int lines = 0;
+    if (owner && p.actions) {
+        if (locked) {
+            lines = __popc(fmask_lo) + __popc(fmask_hi);
+            if (lines) {
+                // survivors keep their order, packed towards the floor
+                int dst = p.H - 1;
+                for (int r = p.H - 1; r >= 0; r--) {
+                    const bool full = r < 32 ? (fmask_lo >> r) & 1u : (fmask_hi >> (r - 32)) & 1u;
+                    if (full) continue;
+                    if (dst != r) for (int c = 0; c < p.W; c++) b[dst * p.Wp + P + c] = b[r * p.Wp + P + c];
+                    dst--;
+                }
+                // the n new top rows: the reference gathers them with jnp.take(sub_board, -H, fill_value=0); jnp.take's default
+                // mode "fill" wraps negative indices numpy-style first, so -H is row 0 (in bounds): COPIES OF THE OLD ROW 0, not
+                // zeros -- identical whenever row 0 is empty.  Row 0 itself is still in place here (rows are only moved downwards).
+                for (; dst >= 1; dst--) for (int c = 0; c < p.W; c++) b[dst * p.Wp + P + c] = b[P + c];
+            }
+            const int lock_reward = lines == 0 ? 0 : (lines == 4 ? 800 : lines * 200 - 100);   // core.score
+            drop_reward += lock_reward;
+            // next piece: queue.bag_queue_get_next_element (functional/queue.py:38-67)
+            if (sc[FN_QIDX] >= p.Q) { fn_new_bag(p, e, sc); piece = sc[FN_S]; sc[FN_QIDX] = 1; }
+            else { piece = sc[FN_S + sc[FN_QIDX]]; sc[FN_QIDX] += 1; }
+            rot = 0; x = spawn_x; y = 0;
+            sc[FN_OVER] = fn_collision(p, b, c_cells[piece][0], x, y) ? 1 : 0;   // core.check_game_over
+        }
+        if (locked || !sc[FN_OVER]) {   // (a finished game is frozen: nothing is written)
+            sc[FN_ACTIVE] = piece; sc[FN_ROT] = rot; sc[FN_X] = x; sc[FN_Y] = y;
+            sc[FN_SCORE] = __float_as_int(old_score + (float)drop_reward);
+        }
+    }
+    if (owner) {
+        if (p.reward) p.reward[e] = __int_as_float(sc[FN_SCORE]) - old_score;
+        if (p.terminated) p.terminated[e] = (uint8_t)sc[FN_OVER];
+        if (p.lines) p.lines[e] = lines;
+    }
+    __syncthreads();
+    // ---- D: get_observation (envs/tetris_fn.py:137-158): (board > 0) + active piece * (-1), cropped to H x W
+    if (p.obs) {
+        if (live) {
+            int8_t* o = s_obs + (size_t)e_l * HW;
+            const uint32_t invW = 65536u / (uint32_t)p.W + 1u;   // i / W for i < 4096
+            if ((HW & 3) == 0) {
+                for (int k = t; k < (HW >> 2); k += TPE) {
+                    uint32_t w = 0;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const uint32_t i = 4u * k + j, r = (i * invW) >> 16, c = i - r * p.W;
+                        w |= (uint32_t)(b[r * p.Wp + P + c] > 0) << (8 * j);
+                    }
+                    ((uint32_t*)o)[k] = w;
+                }
+            } else {
+                for (int i = t; i < HW; i += TPE) {
+                    const uint32_t r = ((uint32_t)i * invW) >> 16, c = i - r * p.W;
+                    o[i] = b[r * p.Wp + P + c] > 0;
+                }
+            }
+        }
+        __syncthreads();
+        if (owner && !sc[FN_OVER]) {
+            int8_t* o = s_obs + (size_t)e_l * HW;
+            const uint32_t cells = c_cells[sc[FN_ACTIVE]][sc[FN_ROT]];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int c = (cells >> (4 * k)) & 15;
+                const int r = sc[FN_Y] + (c >> 2), col = sc[FN_X] + (c & 3) - P;
+                if ((unsigned)r < (unsigned)p.H && (unsigned)col < (unsigned)p.W) o[r * p.W + col] -= 1;
+            }
+        }
+    }
+    // ---- E
+    if (full_tile) {
+        fence_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+            bulk_s2g(p.board_out + base * OB, s_board, (uint32_t)(E * OB));
+            bulk_s2g(p.sc_out + base * NS, s_sc, (uint32_t)(E * NS * 4));
+            if (p.obs) bulk_s2g(p.obs + base * HW, s_obs, (uint32_t)(E * HW));
+            bulk_commit();
+            bulk_wait_read();
+        }
+    } else {
+        __syncthreads();
+        for (int k = tid; k < nv * OB; k += 256) p.board_out[base * OB + k] = s_board[k];
+        for (int k = tid; k < nv * NS; k += 256) p.sc_out[base * NS + k] = s_sc[k];
+        if (p.obs) for (int k = tid; k < nv * HW; k += 256) p.obs[base * HW + k] = s_obs[k];
     }
 }
 

@@ -3,7 +3,7 @@
     ncu --set full --clock-control none --import-source on -k regex:k_rgb -s 4 -c 1 -o gpurun_out/prof_rgb \
         python tools/prof_paths.py rgb --envs 262144
 
-paths: step | cnn (wide board, fused 84x84 grey frame stack) | rgb (wide board + image) | rgb_d (default board + image) | boards | boards_x | feats | rollout"""
+paths: step | cnn (wide board, fused 84x84 grey frame stack) | rgb (wide board + image) | rgb_d (default board + image) | boards | boards_x | feats | rollout | fn (functional facade batched_step)"""
 import argparse
 import sys
 
@@ -52,4 +52,14 @@ elif args.path == "rollout":
     env.reset(seed=42)
     for i in range(3):
         env.rollout((-51, 76, -36, -18), 64)
+elif args.path == "fn":
+    from tetris_gymnasium_b200.envs import tetris_fn as F
+    from tetris_gymnasium_b200.functional.core import EnvConfig
+    from tetris_gymnasium_b200.functional.tetrominoes import TETROMINOES
+    cfg = EnvConfig(width=10, height=20, padding=4, queue_size=7)
+    keys = torch.stack([torch.arange(n, device="cuda"), torch.full((n,), 42, device="cuda")], dim=1)
+    keys, state, obs = F.batched_reset(TETROMINOES, keys, config=cfg)
+    acts = torch.randint(0, 7, (args.iters, n), dtype=torch.int32, device="cuda")
+    for i in range(args.iters):
+        state, _, _, _, _ = F.batched_step(TETROMINOES, state, acts[i], config=cfg)
 torch.cuda.synchronize()
