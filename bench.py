@@ -426,6 +426,23 @@ def leg_e2e(env, acts, n, K, world, rank, dev, barrier, allmax, allsum):
                               "note": "same loop with the observation dict left in HBM (GPU-resident policy): actions H2D, step, reward + terminated D2H, synchronised every step"}}
 
 
+def issue_block(rate_env_steps, profiles_and_envs, sm_mhz=1965.0, sms=148):
+    """Issue-slot roofline of an integer-issue-bound leg: warp instructions per env-step (smsp__inst_executed.sum of the ncu
+    captures under profiles/ divided by the env-steps of the captured launch) x the env-step rate measured HERE, against the
+    issue peak of the chip (SMs x 4 schedulers x 1 warp instruction per clock at the maximum SM clock)."""
+    per_step, src = 0.0, []
+    for name, env_steps in profiles_and_envs:
+        try:
+            j = json.load(open(os.path.join(ROOT, "profiles", name)))
+            per_step += float(j["smsp__inst_executed.sum"]["value"]) / env_steps
+            src.append(f"profiles/{name}")
+        except Exception:
+            return None
+    peak_issue = sms * 4 * sm_mhz * 1e6
+    return {"bound": "issue", "warp_inst_per_env_step": per_step, "achieved": per_step * rate_env_steps / 1e9, "peak": peak_issue / 1e9,
+            "unit": "G warp-inst/s", "frac": per_step * rate_env_steps / peak_issue, "source": " + ".join(src) + " (smsp__inst_executed.sum / env-steps of the captured launch)"}
+
+
 def leg_extra(n, world, rank, dev, barrier, allmax):
     """The other BASELINE configs, short runs, each with a roofline block (HBM bytes are algorithmic, per our layout)."""
     import torch
@@ -462,8 +479,9 @@ def leg_extra(n, world, rank, dev, barrier, allmax):
                         "config": f"GroupedActionsObservations + FeatureVectorObservation, {WIDTH}x{HEIGHT}, gravity off, {ng} envs/GPU, "
                                   f"{A} placements x {F} features per env-step, random legal placements, {Kg} steps (one event pair per step)",
                         "roofline": {"bound": "hbm", "achieved": g_bytes * g_rate / 1e9, "peak": peak, "unit": "GB/s", "frac": g_bytes * g_rate / 1e9 / peak,
-                                     "bytes_per_env_step": g_bytes, "kernels": "tg::k_step_ws<10,20,u32,2> + tg::k_grouped_feats_x<10,u32>",
-                                     "note": "integer-issue bound, not HBM bound: issue-slot utilisation from the ncu capture under profiles/ (see profiles/README.md)"}}
+                                     "bytes_per_env_step": g_bytes, "kernels": "tg::k_step_ws<10,20,u32,2,false> + tg::k_grouped_feats_x<10,u32>",
+                                     "note": "integer-issue bound, not HBM bound: see the `issue` block"}}
+    extra["grouped"]["issue"] = issue_block(g_rate, [("r02_gfeats_x_steady.json", 1 << 20), ("r02_step_grouped_steady.json", 1 << 20)])
     gbase.close()
     del genv, gbase
     torch.cuda.empty_cache()
@@ -491,7 +509,8 @@ def leg_extra(n, world, rank, dev, barrier, allmax):
                         "episode_stats_all_ranks": {"episodes": st[0], "mean_return": st[1] / max(st[0], 1), "mean_length": st[2] / max(st[0], 1), "mean_lines": st[3] / max(st[0], 1)},
                         "roofline": {"bound": "hbm", "achieved": r_bytes * r_rate / 1e9, "peak": peak, "unit": "GB/s", "frac": r_bytes * r_rate / 1e9 / peak,
                                      "bytes_per_env_step": r_bytes, "kernels": "tg::k_rollout_x<10,u32>",
-                                     "note": "state touches HBM once per K steps: integer-issue bound by design; issue-slot utilisation in the ncu capture under profiles/"}}
+                                     "note": "state touches HBM once per K steps: integer-issue bound by design, see the `issue` block"}}
+    extra["rollout"]["issue"] = issue_block(r_rate, [("r02_rollout.json", (1 << 20) * 64)])
     rbase.close()
     del rbase
     torch.cuda.empty_cache()
@@ -546,8 +565,37 @@ def leg_extra(n, world, rank, dev, barrier, allmax):
                          "config": f"20x40 board, queue 5, fused CNN adapter (RGB -> 84x84 INTER_AREA -> grey -> 4-frame stack, clip reward), {nc} envs/GPU, {Kw} steps",
                          "roofline": {"bound": "hbm", "achieved": c_bytes * c_rate / 1e9, "peak": peak, "unit": "GB/s", "frac": c_bytes * c_rate / 1e9 / peak,
                                       "bytes_per_env_step": c_bytes, "kernels": "tg::k_step_ws<20,40,u64,0> (no dict) + tg::k_cnn_obs",
-                                      "note": "integer-issue bound (fixed-point resize + grey per output pixel)"}}
+                                      "note": "integer-issue bound (fixed-point resize + grey per output pixel), see the `issue` block"}}
+    extra["wide_cnn"]["issue"] = issue_block(c_rate, [("r02_cnn.json", 1 << 16)])
     cbase.close()
+    del cenv, cbase
+    torch.cuda.empty_cache()
+
+    # ---- functional facade: batched_step with the State in and out every call -----------------------------
+    from tetris_gymnasium_b200.envs import tetris_fn as FN
+    from tetris_gymnasium_b200.functional.core import EnvConfig
+    from tetris_gymnasium_b200.functional.tetrominoes import TETROMINOES
+    nf = min(n, 1 << 20)
+    fcfg = EnvConfig(width=10, height=20, padding=4, queue_size=7)
+    with torch.cuda.device(dev):
+        keys = torch.stack([torch.arange(nf, device=dev) + rank * nf, torch.full((nf,), 42, device=dev)], dim=1)
+        keys, fstate, _ = FN.batched_reset(TETROMINOES, keys, config=fcfg)
+        fa = torch.randint(0, 7, (8, nf), dtype=torch.int32, device=dev, generator=gq)
+        for t in range(8):
+            fstate, _, _, _, _ = FN.batched_step(TETROMINOES, fstate, fa[t % 8], config=fcfg)
+        barrier()
+        ev0.record()
+        for t in range(Kw):
+            fstate, _, _, _, _ = FN.batched_step(TETROMINOES, fstate, fa[t % 8], config=fcfg)
+        ev1.record()
+        barrier()
+    tf_ms = allmax(ev0.elapsed_time(ev1))[0]
+    f_bytes = 2 * 24 * 18 + 200 + 2 * 4 * 16 + 4 + 9      # board i8 in + out, observation i8[20,10], scalars in + out, action, 5-tuple
+    f_rate = nf * Kw / (tf_ms * 1e-3)
+    extra["functional"] = {"env_steps_per_s": world * f_rate,
+                           "config": f"functional facade batched_step (envs/tetris_fn.py), 10x20, queue 7, {nf} envs/GPU, State (int8 board + scalars) in and out every call, {Kw} steps",
+                           "roofline": {"bound": "hbm", "achieved": f_bytes * f_rate / 1e9, "peak": peak, "unit": "GB/s", "frac": f_bytes * f_rate / 1e9 / peak,
+                                        "bytes_per_env_step": f_bytes, "kernels": "tg::k_fn_step_tile"}}
     return extra
 
 
