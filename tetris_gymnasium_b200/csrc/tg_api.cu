@@ -61,6 +61,7 @@ struct tg_env {
     int logic_warps_set, fill_warps_set;   // TG_NL / TG_NF given: use them for every launch
     void* rollout_last_action;
     int cnn_h, cnn_w;     // output size the tg_cnn_observe tables in stage[4] were built for
+    int cnn_nax = 0, cnn_axv[4] = {-1, -1, -1, -1};   // classes of the x coefficient sums (k_cnn_obs2)
     std::string err;
     // tg_step_host staging
     cudaStream_t hs[3];

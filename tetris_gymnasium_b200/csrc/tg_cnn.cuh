@@ -32,6 +32,11 @@ struct CnnParams {
     int fill_count;
     int OH, OW;
     int rec_bytes, pix_bytes, out_bytes;
+    // k_cnn_obs2: grey value of a pixel whose four source pixels hold the same id: gtab[(dy * 4 + class of a0 + a1) * 16 + id]
+    const uint8_t* gtab;
+    int axv[4];               // the (up to four) distinct sums a0 + a1 of the x coefficient pairs; class = index in here
+    int list_bytes;           // per-warp list of the pixels that need the full interpolation
+    int chunk_rows;           // k_cnn_obs2: output rows per staged chunk (two chunk buffers of out_bytes each per warp)
 };
 
 template <class COLT, int NX>
@@ -192,7 +197,231 @@ __global__ void __launch_bounds__(128) k_cnn_obs(const __grid_constant__ CnnPara
     bulk_wait_all();
 }
 
+// ---- k_cnn_obs2: the same frame, two passes ---------------------------------------------------------------------------------
+// An output pixel interpolates a 2 x 2 neighbourhood of the id image, and nearly all neighbourhoods hold ONE id (empty field,
+// bedrock frame, the inside of a piece: 96 % of the pixels of a wide board in play).  For those the whole chain -- horizontal
+// pass, vertical pass, grey conversion -- is a function of (id, a0 + a1 of the column, output row): a 5 KB table built on the
+// host with the same integer / float64 expressions (tg_cnn_observe: cnn_uniform_table).  Pass 1 (lane = output columns, row by
+// row): compare the ids, write the table value or append the pixel to the warp's list (ballot compaction, no atomics).
+// Pass 2: the listed pixels, 32 at a time, through the full fixed-point interpolation of k_cnn_obs.  A neighbour with a zero
+// coefficient does not count (a1 = 0 at the right border, b1 = 0 where an output row sits on a source row).
+template <class COLT, int NX>
+__global__ void __launch_bounds__(256, 3) k_cnn_obs2(const __grid_constant__ CnnParams p) {
+    extern __shared__ __align__(128) uint8_t sm[];
+    __shared__ uint32_t s_lut[16];
+    __shared__ uint32_t s_rowbytes[112];
+    __shared__ __align__(16) int4 s_y[128];
+    __shared__ __align__(16) int4 s_x[128];
+    __shared__ __align__(8) uint2 s_exc[256];
+    __shared__ __align__(16) uint8_t s_g[128 * 64];
+    const DevCfg& cfg = p.cfg;
+    const int W = cfg.W, H = cfg.H, Wp = cfg.Wp, Hp = cfg.Hp, RW = cfg.rgb_w, Q = cfg.Q, BS = cfg.board_stride;
+    const int OH = p.OH, OW = p.OW, FB = OH * OW;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int NP = Hp * RW;
+    uint8_t* wbase = sm + (size_t)warp * (2 * p.rec_bytes + p.pix_bytes + 2 * p.out_bytes + p.list_bytes);
+    uint8_t* recbuf = wbase;
+    uint8_t* pix = wbase + 2 * p.rec_bytes;
+    uint8_t* out0 = pix + p.pix_bytes;     // two chunk buffers: one is filled while the bulk store of the other drains
+    unsigned short* list = (unsigned short*)(out0 + 2 * p.out_bytes);
+    const int CR = p.chunk_rows;
+    uint32_t nchunk = 0;                   // chunks staged by this warp so far (buffer = nchunk & 1)
+    const int LCAP = p.list_bytes / 2;
+    if (threadIdx.x < 16) s_lut[threadIdx.x] = ((const uint32_t*)c_colors)[threadIdx.x];
+    for (int i = threadIdx.x; i < 112; i += blockDim.x) s_rowbytes[i] = (&c_rowbytes[0][0][0])[i];
+    for (int i = threadIdx.x; i < OH; i += blockDim.x) s_y[i] = ((const int4*)p.ytab)[i];
+    for (int i = threadIdx.x; i < OW; i += blockDim.x) s_x[i] = ((const int4*)p.xtab)[i];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_exc[i] = ((const uint2*)p.gray_exc)[i];
+    for (int i = threadIdx.x; i < OH * 4; i += blockDim.x) ((uint4*)s_g)[i] = ((const uint4*)p.gtab)[i];
+    const uint32_t exc_addr = smem_u32(s_exc);
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // programmatic dependent launch, see k_step_ws
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    for (int i = lane; i < NP; i += 32) {   // constant part of the id image (see k_rgb)
+        int r = i / RW, c = i - r * RW;
+        pix[i] = (c < Wp && r < H && c >= P && c < P + W) ? 0 : 1;
+    }
+    for (int i = lane; i < 2 * p.rec_bytes / 4; i += 32) ((uint32_t*)recbuf)[i] = 0;
+    // this lane's output columns: dx = lane + 32 j
+    int sx0[NX], sx1[NX], gofs[NX];
+#pragma unroll
+    for (int j = 0; j < NX; j++) {
+        const int dx = lane + 32 * j;
+        int4 t = dx < OW ? ((const int4*)p.xtab)[dx] : make_int4(0, 0, 2048, 0);
+        sx0[j] = t.x; sx1[j] = t.w == 0 ? t.x : t.y;          // a neighbour with a zero coefficient does not count
+        const int ax = t.z + t.w;
+        gofs[j] = 16 * ((ax == p.axv[1]) + 2 * (ax == p.axv[2]) + 3 * (ax == p.axv[3]));
+    }
+    __syncthreads();
+    const bool tma = (FB & 15) == 0 && (((uintptr_t)p.frames) & 15) == 0 && (p.env_stride & 15) == 0;
+    const bool rows20 = W == 20 && (H & 1) == 0 && (RW & 3) == 0;
+    const int64_t stride = (int64_t)gridDim.x * nwarps;
+    int64_t e = (int64_t)blockIdx.x * nwarps + warp;
+    auto prefetch = [&](int64_t ee, uint8_t* dst) {
+        const uint8_t* src = p.board + ee * BS;
+        for (int i = lane; i < (BS >> 4); i += 32) cp_async16(dst + 16 * i, src + 16 * i);
+        if (lane < 2) cp_async16(dst + BS + 16 * lane, p.hot + ee * 32 + 16 * lane);
+        cp_async_commit();
+    };
+    // pass 2: the full interpolation of the listed pixels (entry = dy | dx << 8), 32 at a time
+    auto flush = [&](int cnt, uint8_t* out, int row0) {
+        __syncwarp();
+        for (int k = lane; k < cnt; k += 32) {
+            const int ent = list[k], dy = ent & 255, dx = ent >> 8;
+            const int4 yt = s_y[dy], xt = s_x[dx];
+            const uint32_t acoef = (uint32_t)xt.z | ((uint32_t)xt.w << 16);
+            const uint8_t* r0 = pix + yt.x * RW;
+            const uint8_t* r1 = pix + yt.y * RW;
+            int hc[3], hn[3];
+            {
+                const uint32_t c0 = s_lut[r0[xt.x]], c1 = s_lut[r0[xt.y]];
+                const uint32_t rg = __byte_perm(c0, c1, 0x5140), bb = __byte_perm(c0, c1, 0x7762);
+                hc[0] = (int)(__dp2a_lo(acoef, rg, 0u) >> 4); hc[1] = (int)(__dp2a_hi(acoef, rg, 0u) >> 4); hc[2] = (int)(__dp2a_lo(acoef, bb, 0u) >> 4);
+            }
+            {
+                const uint32_t c0 = s_lut[r1[xt.x]], c1 = s_lut[r1[xt.y]];
+                const uint32_t rg = __byte_perm(c0, c1, 0x5140), bb = __byte_perm(c0, c1, 0x7762);
+                hn[0] = (int)(__dp2a_lo(acoef, rg, 0u) >> 4); hn[1] = (int)(__dp2a_hi(acoef, rg, 0u) >> 4); hn[2] = (int)(__dp2a_lo(acoef, bb, 0u) >> 4);
+            }
+            // VResizeLinear: (((b0 * h0) >> 16) + ((b1 * h1) >> 16) + 2) >> 2 (colours <= 240, pairs sum to 2048 +- 1: no clamping)
+            const uint32_t r = (uint32_t)((((yt.z * hc[0] + 0x20000) >> 16) + ((yt.w * hn[0]) >> 16)) >> 2);
+            const uint32_t g = (uint32_t)((((yt.z * hc[1] + 0x20000) >> 16) + ((yt.w * hn[1]) >> 16)) >> 2);
+            const uint32_t b = (uint32_t)((((yt.z * hc[2] + 0x20000) >> 16) + ((yt.w * hn[2]) >> 16)) >> 2);
+            const uint32_t N = r * 2125u + g * 7154u + b * 721u;
+            uint32_t q = (uint32_t)(((uint64_t)N * 3518437209ull) >> 45);   // N / 10000 for N <= 2,550,000
+            const uint32_t key = r | (g << 8) | (b << 16);
+            uint32_t t0, t1;
+            asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(t0), "=r"(t1) : "r"(exc_addr + q * 8u));
+            q -= (uint32_t)(key == t0) | (uint32_t)(key == t1);
+            out[(dy - row0) * OW + dx] = (uint8_t)q;
+        }
+        __syncwarp();
+    };
+    if (e < p.n) prefetch(e, recbuf);
+    for (int it = 0; e < p.n; e += stride, it++) {
+        const uint32_t* rec = (const uint32_t*)(recbuf + (it & 1) * p.rec_bytes);
+        cp_async_wait_all();
+        __syncwarp();
+        if (e + stride < p.n) prefetch(e + stride, recbuf + ((it + 1) & 1) * p.rec_bytes);
+        Hot h;
+        hot_load(h, rec + (BS >> 2));
+        const COLT* cols = (const COLT*)rec;
+        const uint32_t* ids = rec + cfg.ids_off / 4;
+        // ---- id image (RgbObservation layout: board | queue top right, holder bottom right) ----
+        if (rows20) {
+            for (int g2 = lane; g2 < (H >> 1); g2 += 32)
+                fill_rows2_w20_strided(ids + 5 * g2, (uint32_t*)(pix + (2 * g2) * RW + P), (uint32_t*)(pix + (2 * g2 + 1) * RW + P));
+        } else {
+            for (int r = lane; r < H; r += 32) fill_board_row<0>(cfg, ids, pix, 0, r, RW);
+        }
+        for (int q = lane; q < Q; q += 32) {
+            const uint4 rb = *(const uint4*)(s_rowbytes + ((int)((h.queue >> (4 * q)) & 15u)) * 16);
+            const uint32_t wv[4] = {rb.x, rb.y, rb.z, rb.w};
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                uint8_t* d = pix + i * RW + Wp + 4 * q;
+                d[0] = (uint8_t)wv[i]; d[1] = (uint8_t)(wv[i] >> 8); d[2] = (uint8_t)(wv[i] >> 16); d[3] = (uint8_t)(wv[i] >> 24);
+            }
+        }
+        if (lane >= 16 && ((lane - 16) >> 2) < cfg.holder_size) {   // up to four held pieces side by side, four rows each
+            const int s = (lane - 16) >> 2, i = lane & 3;
+            const uint32_t wv = holder_row(cfg, h, s_rowbytes, s, i);
+            uint8_t* d = pix + (Hp - P + i) * RW + Wp + 4 * s;
+            d[0] = (uint8_t)wv; d[1] = (uint8_t)(wv >> 8); d[2] = (uint8_t)(wv >> 16); d[3] = (uint8_t)(wv >> 24);
+        }
+        __syncwarp();
+        uint32_t cells = c_cells[h.p][h.r];
+        COLT B = bmask<COLT>(cols, W, cells, h.x);
+        if (!((B >> h.y) & 1) && lane < 4) {   // active piece on top (project_tetromino, envs/tetris.py:543-564)
+            int c = (cells >> (4 * lane)) & 15;
+            pix[(h.y + (c >> 2)) * RW + h.x + (c & 3)] = (uint8_t)(h.p + 2);
+        }
+        __syncwarp();
+        // ---- pass 1: per column the id its source pixel pair shares in the current / next source row (0xFF = two ids);
+        //      uniform neighbourhoods read the table (explicit shared-window addresses: no generic loads / stores) ----
+        uint32_t uc[NX], un[NX];
+        int row_c = -1, row_n = -1, cnt = 0;
+        auto pairs = [&](int sy, uint32_t (&dst)[NX]) {
+            const uint8_t* prow = pix + sy * RW;
+#pragma unroll
+            for (int j = 0; j < NX; j++) {
+                const uint32_t a = prow[sx0[j]], b2 = prow[sx1[j]];
+                dst[j] = a == b2 ? a : 0xFFu;
+            }
+        };
+        const uint32_t g_addr = smem_u32(s_g);
+        uint8_t* g = p.frames + e * p.env_stride;
+        const int reps = 1 + ((p.fill_mask && p.fill_mask[e]) ? p.fill_count : 0);   // reset envs: the frame fills the stack window
+        for (int c0 = 0; c0 < OH; c0 += CR, nchunk++) {
+            const int c1 = min(OH, c0 + CR);
+            uint8_t* out = out0 + (nchunk & 1u) * p.out_bytes;
+            if (tma) { bulk_wait_read1(); __syncwarp(); }   // the store that read this buffer two chunks ago is done
+            const uint32_t o_addr = smem_u32(out) + lane - c0 * OW;
+            for (int dy = c0; dy < c1; dy++) {
+                const int4 yt = s_y[dy];       // sy0, sy1, b0, b1 (warp-uniform)
+                if (yt.x != row_c) {
+                    if (yt.x == row_n) {
+#pragma unroll
+                        for (int j = 0; j < NX; j++) uc[j] = un[j];
+                    } else pairs(yt.x, uc);
+                    row_c = yt.x;
+                }
+                if (yt.y != row_n) {
+                    if (yt.y == row_c) {
+#pragma unroll
+                        for (int j = 0; j < NX; j++) un[j] = uc[j];
+                    } else pairs(yt.y, un);
+                    row_n = yt.y;
+                }
+                const bool one_row = yt.w == 0;            // the output row sits on a source row: the next row does not count
+                const uint32_t grow = g_addr + dy * 64, orow = o_addr + dy * OW;
+                bool rest = false;
+#pragma unroll
+                for (int j = 0; j < NX; j++) {
+                    const bool in = lane + 32 * j < OW;
+                    const bool uni = uc[j] != 0xFFu && (one_row || un[j] == uc[j]);
+                    if (in && uni) {
+                        uint32_t v;
+                        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(grow + gofs[j] + uc[j]));
+                        asm volatile("st.shared.u8 [%0], %1;" ::"r"(orow + 32u * j), "r"(v) : "memory");
+                    }
+                    rest |= in && !uni;
+                }
+                if (__any_sync(0xffffffffu, rest)) {       // (warp-uniform) append this row's other pixels to the list
+#pragma unroll
+                    for (int j = 0; j < NX; j++) {
+                        const bool in = lane + 32 * j < OW;
+                        const bool uni = uc[j] != 0xFFu && (one_row || un[j] == uc[j]);
+                        const unsigned m = __ballot_sync(0xffffffffu, in && !uni);
+                        if (in && !uni) list[cnt + __popc(m & ((1u << lane) - 1u))] = (unsigned short)(dy | ((lane + 32 * j) << 8));
+                        cnt += __popc(m);
+                    }
+                    if (cnt > LCAP - 32 * NX) { flush(cnt, out, c0); cnt = 0; }
+                }
+            }
+            flush(cnt, out, c0);
+            cnt = 0;
+            // ---- store the chunk (reset envs: also into the preceding frames of the stack window) ----
+            const uint32_t cb = (uint32_t)((c1 - c0) * OW);
+            uint8_t* gc = g + (size_t)c0 * OW;
+            if (tma) {
+                fence_async_smem();
+                __syncwarp();
+                for (int r = lane; r < reps; r += 32) bulk_s2g(gc - (size_t)r * FB, out, cb);
+                bulk_commit();   // (every lane commits a group per chunk, empty for most: wait_group.read 1 counts groups)
+            } else {
+                __syncwarp();
+                for (int r = 0; r < reps; r++)
+                    for (int i = lane; i < (int)cb; i += 32) (gc - (size_t)r * FB)[i] = out[i];
+                __syncwarp();
+            }
+        }
+        __syncwarp();
+    }
+    bulk_wait_all();
+}
+
 }  // namespace tg
+
 
 // ---- host side --------------------------------------------------------------------------------------------------
 #include <math.h>
@@ -239,6 +468,19 @@ static int cnn_gray_exceptions(std::vector<uint32_t>& tab) {
     return 0;
 }
 
+// grey value of an output pixel whose source pixels all hold colour (R, G, B): the chain of k_cnn_obs with h0 = h1 = c * ax
+static uint8_t cnn_uniform_value(const unsigned char* rgb, int ax, int b0, int b1) {
+    int v[3];
+    for (int k = 0; k < 3; k++) {
+        const int hh = ((int)rgb[k] * ax) >> 4;
+        v[k] = (((b0 * hh) >> 16) + ((b1 * hh) >> 16) + 2) >> 2;
+        v[k] = v[k] < 0 ? 0 : (v[k] > 255 ? 255 : v[k]);
+    }
+    volatile double f = v[0] * 0.2125 + v[1] * 0.7154;   // GrayscaleObservation: float64, summed left to right
+    f = f + v[2] * 0.0721;
+    return (uint8_t)(int)f;
+}
+
 extern "C" int tg_cnn_observe(tg_env* env, tg_state st, int64_t n, int32_t out_h, int32_t out_w, uint8_t* d_frames,
                               int64_t env_stride, const uint8_t* d_fill_mask, int32_t fill_count, void* stream) {
     if (!env) return TG_ERR_POINTER;
@@ -257,12 +499,28 @@ extern "C" int tg_cnn_observe(tg_env* env, tg_state st, int64_t n, int32_t out_h
         std::vector<uint32_t> gray;
         if (cnn_gray_exceptions(gray)) return fail(env, TG_ERR_CONFIG, "tg_cnn_observe: float64 grey conversion does not follow the integer scheme on this host");
         gray.resize(1536, 0xFFFFFFFFu);
-        size_t bytes = (xt.size() + yt.size()) * 4 + 6144;
+        // k_cnn_obs2: classes of a0 + a1 (at most four, else the one-pass kernel runs) and the uniform-neighbourhood table
+        env->cnn_nax = 0;
+        for (int dx = 0; dx < out_w; dx++) {
+            const int ax = xt[4 * dx + 2] + xt[4 * dx + 3];
+            int k = 0;
+            while (k < env->cnn_nax && env->cnn_axv[k] != ax) k++;
+            if (k == env->cnn_nax) { if (k < 4) env->cnn_axv[k] = ax; env->cnn_nax++; }
+        }
+        for (int k = env->cnn_nax; k < 4; k++) env->cnn_axv[k] = -1;
+        std::vector<uint8_t> gt((size_t)out_h * 64, 0);
+        if (env->cnn_nax <= 4)
+            for (int dy = 0; dy < out_h; dy++)
+                for (int k = 0; k < env->cnn_nax; k++)
+                    for (int id = 0; id < 16; id++)
+                        gt[((size_t)dy * 4 + k) * 16 + id] = cnn_uniform_value(env->tabs.colors[id], env->cnn_axv[k], yt[4 * dy + 2], yt[4 * dy + 3]);
+        size_t bytes = (xt.size() + yt.size()) * 4 + 6144 + gt.size();
         rc = ensure_stage(env, 4, bytes); if (rc) return rc;
         uint8_t* base = (uint8_t*)env->stage[4];
         CUDA_TRY(env, cudaMemcpy(base, gray.data(), 6144, cudaMemcpyHostToDevice));
         CUDA_TRY(env, cudaMemcpy(base + 6144, xt.data(), xt.size() * 4, cudaMemcpyHostToDevice));
         CUDA_TRY(env, cudaMemcpy(base + 6144 + xt.size() * 4, yt.data(), yt.size() * 4, cudaMemcpyHostToDevice));
+        CUDA_TRY(env, cudaMemcpy(base + 6144 + (xt.size() + yt.size()) * 4, gt.data(), gt.size(), cudaMemcpyHostToDevice));
         env->cnn_h = out_h; env->cnn_w = out_w;
     }
     CnnParams p;
@@ -274,8 +532,25 @@ extern "C" int tg_cnn_observe(tg_env* env, tg_state st, int64_t n, int32_t out_h
     p.OH = out_h; p.OW = out_w;
     auto r128 = [](size_t v) { return (int)((v + 127) / 128 * 128); };
     p.rec_bytes = r128((size_t)d.board_stride + 48); p.pix_bytes = r128((size_t)d.Hp * d.rgb_w + 16); p.out_bytes = r128((size_t)out_h * out_w);
-    const int nw = 4, T = nw * 32;
-    const size_t smem = (size_t)nw * (2 * p.rec_bytes + p.pix_bytes + p.out_bytes);
+    const bool two_pass = env->cnn_nax <= 4 && !getenv("TG_CNN_V1");   // TG_CNN_V1=1: the one-pass kernel
+    p.gtab = base + 6144 + ((size_t)out_w + out_h) * 16;
+    for (int k = 0; k < 4; k++) p.axv[k] = env->cnn_axv[k];
+    p.list_bytes = two_pass ? 1024 : 0;
+    int nw = two_pass ? 8 : 4;
+    if (const char* t = getenv("TG_CNN_NW")) { int v = atoi(t); if (v >= 1 && v <= 8) nw = v; }
+    if (two_pass) {
+        // the frame leaves in chunks of whole rows whose byte count is a multiple of 16 (bulk copies): two small chunk buffers
+        // per warp instead of a whole frame keep three 8-warp CTAs resident
+        int cr = 8;
+        if (((size_t)out_h * out_w) % 16 == 0) while (((size_t)cr * out_w) % 16) cr++;
+        else cr = out_h;                       // (plain stores: any chunking works; keep one)
+        if (const char* t = getenv("TG_CNN_CR")) { int v = atoi(t); if (v >= 1 && ((size_t)v * out_w) % 16 == 0) cr = v; }
+        if (cr > out_h) cr = out_h;
+        p.chunk_rows = cr;
+        p.out_bytes = r128((size_t)cr * out_w);
+    }
+    const int T = nw * 32;
+    const size_t smem = (size_t)nw * (2 * p.rec_bytes + p.pix_bytes + (two_pass ? 2 : 1) * p.out_bytes + p.list_bytes);
     if (smem > 200 * 1024) return fail(env, TG_ERR_CONFIG, "tg_cnn_observe: image too large for shared memory");
     const int NX = (out_w + 31) / 32;
     auto launch = [&](auto kern) -> int {
@@ -287,6 +562,10 @@ extern "C" int tg_cnn_observe(tg_env* env, tg_state st, int64_t n, int32_t out_h
         CUDA_TRY(env, launch_pdl(kern, (unsigned)blocks, (unsigned)T, smem, (cudaStream_t)stream, p));
         return TG_OK;
     };
+    if (two_pass) {
+        if (env->col64) return NX == 1 ? launch(k_cnn_obs2<uint64_t, 1>) : NX == 2 ? launch(k_cnn_obs2<uint64_t, 2>) : NX == 3 ? launch(k_cnn_obs2<uint64_t, 3>) : launch(k_cnn_obs2<uint64_t, 4>);
+        return NX == 1 ? launch(k_cnn_obs2<uint32_t, 1>) : NX == 2 ? launch(k_cnn_obs2<uint32_t, 2>) : NX == 3 ? launch(k_cnn_obs2<uint32_t, 3>) : launch(k_cnn_obs2<uint32_t, 4>);
+    }
     if (env->col64) return NX == 1 ? launch(k_cnn_obs<uint64_t, 1>) : NX == 2 ? launch(k_cnn_obs<uint64_t, 2>) : NX == 3 ? launch(k_cnn_obs<uint64_t, 3>) : launch(k_cnn_obs<uint64_t, 4>);
     return NX == 1 ? launch(k_cnn_obs<uint32_t, 1>) : NX == 2 ? launch(k_cnn_obs<uint32_t, 2>) : NX == 3 ? launch(k_cnn_obs<uint32_t, 3>) : launch(k_cnn_obs<uint32_t, 4>);
 }

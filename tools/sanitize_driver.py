@@ -85,8 +85,41 @@ def functional(n):
         state, obs, rew, term, info = F.batched_step(None, state, torch.full((n,), t % 7, dtype=torch.int32, device="cuda"), config=cfg)
 
 
+def round2_paths(n):
+    """Kernels added in round 2: holder FIFO / custom piece set (the XT instantiations), K steps per launch (k_step_resident),
+    both modes of the host-buffer step, the two implementations of the grouped step, device-side numpy seeding."""
+    from tetris_gymnasium_b200.components import Tetromino, TetrominoHolder
+    tets = [Tetromino(0, [0, 240, 240], np.array([[0, 0, 0, 0], [1, 1, 1, 1], [0, 0, 0, 0], [0, 0, 0, 0]], dtype=np.uint8)),
+            Tetromino(1, [240, 240, 0], np.array([[1, 1], [1, 1]], dtype=np.uint8)),
+            Tetromino(2, [160, 0, 240], np.array([[0, 1, 0], [1, 1, 1], [0, 0, 0]], dtype=np.uint8))]
+    for kw in (dict(holder=TetrominoHolder(size=3)), dict(tetrominoes=tets), dict()):
+        env = Tetris(num_envs=n, randomizer_mode="numpy", **kw)
+        env.reset(seed=9)
+        g = torch.Generator(device="cuda")
+        g.manual_seed(2)
+        for t in range(STEPS):
+            env.step(torch.randint(0, 8, (n,), dtype=torch.int32, device="cuda", generator=g))
+        env.step_n(torch.randint(0, 8, (6, n), dtype=torch.int32, device="cuda", generator=g))
+        bufs = env.alloc_host_buffers(pinned=True)
+        for mode in ("compact", "dma"):
+            env.step_host(np.full(n, 5, np.int32), bufs, mode=mode)
+        env.close()
+    for var in ("TG_GROUPED_SPLIT", "TG_GROUPED_FUSED"):
+        os.environ[var] = "1"
+        base = Tetris(num_envs=n, gravity=False, queue_size=4)
+        env = GroupedActionsObservations(base, observation_wrappers=[FeatureVectorObservation(base)])
+        env.reset(seed=13)
+        for t in range(STEPS):
+            a = torch.multinomial(env.legal_actions_mask.float() + 1e-9, 1).squeeze(1).to(torch.int32)
+            env.step(a)
+        base.close()
+        del os.environ[var]
+
+
 def main():
     base_paths(77)
+    round2_paths(77)
+    round2_paths(160)
     base_paths(45, width=20, height=40, queue_size=5)
     base_paths(33, width=7, height=12, queue_size=3)
     wrappers(77, queue_size=4)
@@ -94,6 +127,7 @@ def main():
     wrappers(19, width=7, height=12, queue_size=3)
     try:
         functional(50)
+        functional(96)
     except Exception as ex:  # the facade's Python signature is not what this driver is about
         print("functional facade skipped:", repr(ex)[:200])
     torch.cuda.synchronize()
