@@ -218,28 +218,45 @@ __global__ void k_fn_step(const FnParams p, int bstr /* bytes per staged board, 
 
 // ---- tile variant (the default): CTA = 32 envs x 8 threads ---------------------------------------------------------------
 // The tile's boards, scalars and observations are contiguous in global memory, so they move with 1-D bulk TMA copies (one
-// thread issues them; full tiles) and sit in shared memory in the SAME layout.  Thread (e, t): t = 0 owns env e's game logic
-// (owners are spread over all eight warps: four envs per warp keep the divergence of the per-env branches small); the row scan
-// of core.clear_filled_rows and the observation are produced by all eight threads of the env.
-//   A  owner: action, gravity, lock decision, place the piece's cells
-//   B  all:   full-row mask of the env (rows t, t + 8, ...), OR-combined with three shuffles
+// thread issues them; full tiles) and sit in shared memory in the SAME layout.  Two thread mappings:
+//   owner:  warp 0, lane = env -- the game logic (32 lanes on the divergent per-action branches instead of 8 x 4);
+//   coop:   thread (e = tid / 8, t = tid % 8) -- the row scan of core.clear_filled_rows and the observation, a word at a time.
+//   A  owner: action, gravity, lock decision, place the piece's cells            -> s_lock[e]
+//   B  coop:  full-row mask of the envs that locked (rows t, t + 8, ...), OR-combined with three shuffles -> s_fm[e]
 //   C  owner: row compaction when a row is full (rare), score, next piece, game-over test, scalars and 5-tuple out
-//   D  all:   observation words ((board > 0), cropped);  owner: active piece overlay
+//   D  coop:  observation words ((board > 0), cropped);  owner: active piece overlay
 //   E  bulk stores of the three tiles
 struct FnTileSmem {
-    int off_sc, off_obs, off_bar, bytes;
+    int off_sc, off_obs, off_misc, off_bar, bytes;
 };
 __host__ __device__ inline FnTileSmem fn_tile_smem(int OB, int HW, int NS) {
     FnTileSmem m;
     int o = (32 * OB + 15) & ~15;
     m.off_sc = o; o += 32 * NS * 4;
     m.off_obs = o; o += (32 * HW + 15) & ~15;
+    m.off_misc = o; o += 32 * 4 * 3;          // lock flags, full-row masks (lo, hi)
     m.off_bar = o; o += 16;
     m.bytes = o;
     return m;
 }
 
-__global__ void __launch_bounds__(256) k_fn_step_tile(const FnParams p) {
+// bit 7 of byte i set <=> byte i of v is > 0 as int8 (non-zero, sign bit clear)
+__device__ __forceinline__ uint32_t fn_pos4(uint32_t v) {
+    return ((((v & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | v) & ~v) & 0x80808080u;
+}
+// four consecutive bytes at shared-window byte address `a` (any alignment; may read up to 3 bytes past them)
+__device__ __forceinline__ uint32_t fn_ld4(uint32_t a) {
+    uint32_t w0, w1;
+    const uint32_t al = a & ~3u;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(al));
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w1) : "r"(al + 4u));
+    return __funnelshift_r(w0, w1, (a & 3u) * 8u);
+}
+
+#ifndef FN_MINB
+#define FN_MINB 8   // 32 registers (100 B of spills in the owner logic): 8 CTAs = 64 warps per SM; 5 CTAs at 48 registers measured 18 % slower
+#endif
+__global__ void __launch_bounds__(256, FN_MINB) k_fn_step_tile(const FnParams p) {
     extern __shared__ __align__(128) uint8_t fsm[];
     constexpr int E = 32, TPE = 8;
     const int tid = threadIdx.x, e_l = tid >> 3, t = tid & 7;
@@ -247,12 +264,15 @@ __global__ void __launch_bounds__(256) k_fn_step_tile(const FnParams p) {
     const int nv = (int)min((int64_t)E, p.n - base);
     const int OB = p.Hp * p.Wp, NS = FN_S + p.Q, HW = p.H * p.W;
     const FnTileSmem m = fn_tile_smem(OB, HW, NS);
-    int8_t* s_board = (int8_t*)fsm;                       // [E][OB]
+    int8_t* s_board = (int8_t*)fsm;                       // [E][OB] (+ 16 bytes of slack: word reads past a row stay inside)
     int32_t* s_sc = (int32_t*)(fsm + m.off_sc);           // [E][NS]
     int8_t* s_obs = (int8_t*)(fsm + m.off_obs);           // [E][HW]
+    uint32_t* s_lock = (uint32_t*)(fsm + m.off_misc);     // [E]
+    uint32_t* s_fm = s_lock + E;                          // [2][E]
     uint64_t* bar = (uint64_t*)(fsm + m.off_bar);
     const bool full_tile = nv == E;
     if (tid == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (tid < E) s_lock[tid] = 0;
     __syncthreads();
     if (full_tile) {
         if (tid == 0) {
@@ -266,10 +286,12 @@ __global__ void __launch_bounds__(256) k_fn_step_tile(const FnParams p) {
         for (int k = tid; k < nv * NS; k += 256) s_sc[k] = p.sc_in[base * NS + k];
         __syncthreads();
     }
-    const bool live = e_l < nv, owner = live && t == 0;
-    const int64_t e = base + e_l;
+    const bool live = e_l < nv;                 // coop mapping
     int8_t* b = s_board + (size_t)e_l * OB;
-    int32_t* sc = s_sc + e_l * NS;
+    const bool owner = tid < nv;                // owner mapping: warp 0, lane = env
+    const int64_t e = base + tid;
+    int8_t* ob = s_board + (size_t)(tid & 31) * OB;
+    int32_t* sc = s_sc + (tid & 31) * NS;
     const int spawn_x = p.Wp / 2 - 2;   // core.get_initial_x_y: 4x4 matrices (functional/core.py:66-83)
     float old_score = 0.f;
     int piece = 0, rot = 0, x = 0, y = 0, drop_reward = 0;
@@ -295,20 +317,20 @@ __global__ void __launch_bounds__(256) k_fn_step_tile(const FnParams p) {
             const int a = p.actions[e];
             piece = sc[FN_ACTIVE]; rot = sc[FN_ROT]; x = sc[FN_X]; y = sc[FN_Y];
             uint32_t cells = c_cells[piece][rot];
-            if (a == 0) { if (!fn_collision(p, b, cells, x - 1, y)) x -= 1; }
-            else if (a == 1) { if (!fn_collision(p, b, cells, x + 1, y)) x += 1; }
-            else if (a == 2) { if (!fn_collision(p, b, cells, x, y + 1)) { y += 1; drop_reward = 1; } }
+            if (a == 0) { if (!fn_collision(p, ob, cells, x - 1, y)) x -= 1; }
+            else if (a == 1) { if (!fn_collision(p, ob, cells, x + 1, y)) x += 1; }
+            else if (a == 2) { if (!fn_collision(p, ob, cells, x, y + 1)) { y += 1; drop_reward = 1; } }
             else if (a == 3 || a == 4) {
                 int nr = (rot + (a == 4 ? 1 : 3)) & 3;   // 3 = counter-clockwise, 4 = clockwise (envs/tetris_fn.py:470-478)
-                if (!fn_collision(p, b, c_cells[piece][nr], x, y)) { rot = nr; cells = c_cells[piece][nr]; }
+                if (!fn_collision(p, ob, c_cells[piece][nr], x, y)) { rot = nr; cells = c_cells[piece][nr]; }
             } else if (a == 6) {                          // core.hard_drop (functional/core.py:230-251)
                 int ny = y;
-                while (!fn_collision(p, b, cells, x, ny + 1)) ny++;
+                while (!fn_collision(p, ob, cells, x, ny + 1)) ny++;
                 drop_reward = 2 * (ny - y);
                 y = ny;
             }
             int yg = y;
-            if (p.gravity && !fn_collision(p, b, cells, x, y + 1)) yg = y + 1;   // core.graviy_step
+            if (p.gravity && !fn_collision(p, ob, cells, x, y + 1)) yg = y + 1;   // core.graviy_step
             const bool should_lock = (yg == y) && p.gravity;
             y = yg;
             locked = should_lock || a == 6;
@@ -317,20 +339,32 @@ __global__ void __launch_bounds__(256) k_fn_step_tile(const FnParams p) {
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
                     int c = (cells >> (4 * k)) & 15;
-                    b[(y + (c >> 2)) * p.Wp + x + (c & 3)] += (int8_t)(piece + 2);
+                    ob[(y + (c >> 2)) * p.Wp + x + (c & 3)] += (int8_t)(piece + 2);
                 }
+                s_lock[tid] = 1;
             }
         }
     }
     __syncthreads();
-    // ---- B: core.clear_filled_rows' row test (functional/core.py:185-227: all(sub_board > 0)), every row, every env
+    // ---- B: core.clear_filled_rows' row test (functional/core.py:185-227: all(sub_board > 0)), every row of the envs that locked
     uint32_t fmask_lo = 0, fmask_hi = 0;
-    if (live && p.actions) {
+    if (live && s_lock[e_l]) {
+        const uint32_t b0 = smem_u32(b) + P;
         for (int r = t; r < p.H; r += TPE) {
-            const int8_t* row = b + r * p.Wp + P;
-            bool full = true;
-            for (int c = 0; c < p.W; c++) full &= row[c] > 0;
-            if (full) { if (r < 32) fmask_lo |= 1u << r; else fmask_hi |= 1u << (r - 32); }
+            const uint32_t a0 = b0 + r * p.Wp, al = a0 & ~3u, lead = a0 & 3u;
+            const int nw = (int)(lead + p.W + 3) >> 2;
+            uint32_t ok = 0x80808080u;
+            for (int i = 0; i < nw; i++) {
+                uint32_t v;
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(al + 4u * i));
+                if (i == 0) { const uint32_t lm = (1u << (8 * lead)) - 1u; v = (v & ~lm) | (0x01010101u & lm); }   // bytes in front of the row
+                if (i == nw - 1) {
+                    const uint32_t endb = (lead + p.W) & 3u;                                     // bytes of the last word inside the row
+                    if (endb) v = (v & ((1u << (8 * endb)) - 1u)) | (0x01010101u & ~((1u << (8 * endb)) - 1u));
+                }
+                ok &= fn_pos4(v);
+            }
+            if (ok == 0x80808080u) { if (r < 32) fmask_lo |= 1u << r; else fmask_hi |= 1u << (r - 32); }
         }
     }
 #pragma unroll
@@ -338,10 +372,13 @@ __global__ void __launch_bounds__(256) k_fn_step_tile(const FnParams p) {
         fmask_lo |= __shfl_xor_sync(0xffffffffu, fmask_lo, o);
         fmask_hi |= __shfl_xor_sync(0xffffffffu, fmask_hi, o);
     }
+    if (t == 0) { s_fm[e_l] = fmask_lo; s_fm[E + e_l] = fmask_hi; }
+    __syncthreads();
     // ---- C
     int lines = 0;
     if (owner && p.actions) {
         if (locked) {
+            fmask_lo = s_fm[tid]; fmask_hi = s_fm[E + tid];
             lines = __popc(fmask_lo) + __popc(fmask_hi);
             if (lines) {
                 // survivors keep their order, packed towards the floor
@@ -349,13 +386,13 @@ __global__ void __launch_bounds__(256) k_fn_step_tile(const FnParams p) {
                 for (int r = p.H - 1; r >= 0; r--) {
                     const bool full = r < 32 ? (fmask_lo >> r) & 1u : (fmask_hi >> (r - 32)) & 1u;
                     if (full) continue;
-                    if (dst != r) for (int c = 0; c < p.W; c++) b[dst * p.Wp + P + c] = b[r * p.Wp + P + c];
+                    if (dst != r) for (int c = 0; c < p.W; c++) ob[dst * p.Wp + P + c] = ob[r * p.Wp + P + c];
                     dst--;
                 }
                 // the n new top rows: the reference gathers them with jnp.take(sub_board, -H, fill_value=0); jnp.take's default
                 // mode "fill" wraps negative indices numpy-style first, so -H is row 0 (in bounds): COPIES OF THE OLD ROW 0, not
                 // zeros -- identical whenever row 0 is empty.  Row 0 itself is still in place here (rows are only moved downwards).
-                for (; dst >= 1; dst--) for (int c = 0; c < p.W; c++) b[dst * p.Wp + P + c] = b[P + c];
+                for (; dst >= 1; dst--) for (int c = 0; c < p.W; c++) ob[dst * p.Wp + P + c] = ob[P + c];
             }
             const int lock_reward = lines == 0 ? 0 : (lines == 4 ? 800 : lines * 200 - 100);   // core.score
             drop_reward += lock_reward;
@@ -363,7 +400,7 @@ __global__ void __launch_bounds__(256) k_fn_step_tile(const FnParams p) {
             if (sc[FN_QIDX] >= p.Q) { fn_new_bag(p, e, sc); piece = sc[FN_S]; sc[FN_QIDX] = 1; }
             else { piece = sc[FN_S + sc[FN_QIDX]]; sc[FN_QIDX] += 1; }
             rot = 0; x = spawn_x; y = 0;
-            sc[FN_OVER] = fn_collision(p, b, c_cells[piece][0], x, y) ? 1 : 0;   // core.check_game_over
+            sc[FN_OVER] = fn_collision(p, ob, c_cells[piece][0], x, y) ? 1 : 0;   // core.check_game_over
         }
         if (locked || !sc[FN_OVER]) {   // (a finished game is frozen: nothing is written)
             sc[FN_ACTIVE] = piece; sc[FN_ROT] = rot; sc[FN_X] = x; sc[FN_Y] = y;
@@ -381,15 +418,18 @@ __global__ void __launch_bounds__(256) k_fn_step_tile(const FnParams p) {
         if (live) {
             int8_t* o = s_obs + (size_t)e_l * HW;
             const uint32_t invW = 65536u / (uint32_t)p.W + 1u;   // i / W for i < 4096
-            if ((HW & 3) == 0) {
+            if ((HW & 3) == 0 && p.W >= 4) {
+                const uint32_t b0 = smem_u32(b) + P;
                 for (int k = t; k < (HW >> 2); k += TPE) {
-                    uint32_t w = 0;
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        const uint32_t i = 4u * k + j, r = (i * invW) >> 16, c = i - r * p.W;
-                        w |= (uint32_t)(b[r * p.Wp + P + c] > 0) << (8 * j);
+                    const uint32_t i = 4u * k, r = (i * invW) >> 16, c = i - r * p.W;
+                    uint32_t v = fn_ld4(b0 + r * p.Wp + c);
+                    const uint32_t n1 = p.W - c;                 // cells left in row r
+                    if (n1 < 4u) {                               // the word continues at the start of row r + 1
+                        const uint32_t v2 = fn_ld4(b0 + (r + 1) * p.Wp);
+                        const uint32_t keep = (1u << (8 * n1)) - 1u;
+                        v = (v & keep) | (v2 << (8 * n1));
                     }
-                    ((uint32_t*)o)[k] = w;
+                    ((uint32_t*)o)[k] = fn_pos4(v) >> 7;
                 }
             } else {
                 for (int i = t; i < HW; i += TPE) {
@@ -400,7 +440,7 @@ __global__ void __launch_bounds__(256) k_fn_step_tile(const FnParams p) {
         }
         __syncthreads();
         if (owner && !sc[FN_OVER]) {
-            int8_t* o = s_obs + (size_t)e_l * HW;
+            int8_t* o = s_obs + (size_t)tid * HW;
             const uint32_t cells = c_cells[sc[FN_ACTIVE]][sc[FN_ROT]];
 #pragma unroll
             for (int k = 0; k < 4; k++) {
