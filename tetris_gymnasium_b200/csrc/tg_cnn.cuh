@@ -37,6 +37,7 @@ struct CnnParams {
     int axv[4];               // the (up to four) distinct sums a0 + a1 of the x coefficient pairs; class = index in here
     int list_bytes;           // per-warp list of the pixels that need the full interpolation
     int chunk_rows;           // k_cnn_obs2: output rows per staged chunk (two chunk buffers of out_bytes each per warp)
+    int gtab_bytes;           // k_cnn_obs2: bytes of the table at the front of the dynamic shared memory
 };
 
 template <class COLT, int NX>
@@ -206,20 +207,20 @@ __global__ void __launch_bounds__(128) k_cnn_obs(const __grid_constant__ CnnPara
 // Pass 2: the listed pixels, 32 at a time, through the full fixed-point interpolation of k_cnn_obs.  A neighbour with a zero
 // coefficient does not count (a1 = 0 at the right border, b1 = 0 where an output row sits on a source row).
 template <class COLT, int NX>
-__global__ void __launch_bounds__(256, 3) k_cnn_obs2(const __grid_constant__ CnnParams p) {
+__global__ void __launch_bounds__(256, 4) k_cnn_obs2(const __grid_constant__ CnnParams p) {
     extern __shared__ __align__(128) uint8_t sm[];
     __shared__ uint32_t s_lut[16];
     __shared__ uint32_t s_rowbytes[112];
     __shared__ __align__(16) int4 s_y[128];
-    __shared__ __align__(16) int4 s_x[128];
     __shared__ __align__(8) uint2 s_exc[256];
-    __shared__ __align__(16) uint8_t s_g[128 * 64];
     const DevCfg& cfg = p.cfg;
     const int W = cfg.W, H = cfg.H, Wp = cfg.Wp, Hp = cfg.Hp, RW = cfg.rgb_w, Q = cfg.Q, BS = cfg.board_stride;
     const int OH = p.OH, OW = p.OW, FB = OH * OW;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     const int NP = Hp * RW;
-    uint8_t* wbase = sm + (size_t)warp * (2 * p.rec_bytes + p.pix_bytes + 2 * p.out_bytes + p.list_bytes);
+    uint8_t* s_g = sm;                     // [OH][4][16] uniform-neighbourhood table, then one region per warp
+    const int4* s_x = (const int4*)p.xtab; // (pass 2 only: read through L1)
+    uint8_t* wbase = sm + p.gtab_bytes + (size_t)warp * (2 * p.rec_bytes + p.pix_bytes + 2 * p.out_bytes + p.list_bytes);
     uint8_t* recbuf = wbase;
     uint8_t* pix = wbase + 2 * p.rec_bytes;
     uint8_t* out0 = pix + p.pix_bytes;     // two chunk buffers: one is filled while the bulk store of the other drains
@@ -230,7 +231,6 @@ __global__ void __launch_bounds__(256, 3) k_cnn_obs2(const __grid_constant__ Cnn
     if (threadIdx.x < 16) s_lut[threadIdx.x] = ((const uint32_t*)c_colors)[threadIdx.x];
     for (int i = threadIdx.x; i < 112; i += blockDim.x) s_rowbytes[i] = (&c_rowbytes[0][0][0])[i];
     for (int i = threadIdx.x; i < OH; i += blockDim.x) s_y[i] = ((const int4*)p.ytab)[i];
-    for (int i = threadIdx.x; i < OW; i += blockDim.x) s_x[i] = ((const int4*)p.xtab)[i];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_exc[i] = ((const uint2*)p.gray_exc)[i];
     for (int i = threadIdx.x; i < OH * 4; i += blockDim.x) ((uint4*)s_g)[i] = ((const uint4*)p.gtab)[i];
     const uint32_t exc_addr = smem_u32(s_exc);
@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(256, 3) k_cnn_obs2(const __grid_constant__ Cnn
         __syncwarp();
         for (int k = lane; k < cnt; k += 32) {
             const int ent = list[k], dy = ent & 255, dx = ent >> 8;
-            const int4 yt = s_y[dy], xt = s_x[dx];
+            const int4 yt = s_y[dy], xt = __ldg(s_x + dx);
             const uint32_t acoef = (uint32_t)xt.z | ((uint32_t)xt.w << 16);
             const uint8_t* r0 = pix + yt.x * RW;
             const uint8_t* r1 = pix + yt.y * RW;
@@ -535,7 +535,8 @@ extern "C" int tg_cnn_observe(tg_env* env, tg_state st, int64_t n, int32_t out_h
     const bool two_pass = env->cnn_nax <= 4 && !getenv("TG_CNN_V1");   // TG_CNN_V1=1: the one-pass kernel
     p.gtab = base + 6144 + ((size_t)out_w + out_h) * 16;
     for (int k = 0; k < 4; k++) p.axv[k] = env->cnn_axv[k];
-    p.list_bytes = two_pass ? 1024 : 0;
+    p.list_bytes = two_pass ? 512 : 0;
+    p.gtab_bytes = two_pass ? r128((size_t)out_h * 64) : 0;
     int nw = two_pass ? 8 : 4;
     if (const char* t = getenv("TG_CNN_NW")) { int v = atoi(t); if (v >= 1 && v <= 8) nw = v; }
     if (two_pass) {
@@ -550,7 +551,7 @@ extern "C" int tg_cnn_observe(tg_env* env, tg_state st, int64_t n, int32_t out_h
         p.out_bytes = r128((size_t)cr * out_w);
     }
     const int T = nw * 32;
-    const size_t smem = (size_t)nw * (2 * p.rec_bytes + p.pix_bytes + (two_pass ? 2 : 1) * p.out_bytes + p.list_bytes);
+    const size_t smem = (size_t)p.gtab_bytes + (size_t)nw * (2 * p.rec_bytes + p.pix_bytes + (two_pass ? 2 : 1) * p.out_bytes + p.list_bytes);
     if (smem > 200 * 1024) return fail(env, TG_ERR_CONFIG, "tg_cnn_observe: image too large for shared memory");
     const int NX = (out_w + 31) / 32;
     auto launch = [&](auto kern) -> int {
