@@ -479,6 +479,12 @@ static int build_plan(tg_env* env, StepPlan& pl, int mode, bool want_obs, int fo
     for (;;) {
         off = 0;
         NS = ws ? NL + nsx : 2;
+        // NS must be a multiple of NL: logic warp w visits the stages (w + i * NL) % NS, and it tells a stage's reload from the
+        // data of the tile before only by the PARITY of the stage's mbarrier phase.  With NS % NL != 0 (it was 4 + 2) a warp comes
+        // back to a stage two phases later without having waited on the phase in between; if that phase's load has not landed yet
+        // (loads are issued in order but need not complete in order -- seen with a second grouped env on another stream) the
+        // parity test passes on the OLD phase and the warp steps stale records.  4 logic warps -> 8 stages, 3 -> 6, 2 -> 4.
+        if (ws && NL > 0) NS = (NS + NL - 1) / NL * NL;
         p.st_hot = (int)(((size_t)E * 32 + 127) / 128 * 128);
         p.st_brd = (int)(((size_t)E * d.board_stride + 16 + 127) / 128 * 128);
         p.st_rng = (int)(((size_t)E * d.rng_stride + 127) / 128 * 128);
@@ -495,6 +501,9 @@ static int build_plan(tg_env* env, StepPlan& pl, int mode, bool want_obs, int fo
         p.off_tab = take(112 * 4 + 64 + 32);
         p.off_feat = take((size_t)E * 64);
         // large boards: fewer logic warps (= fewer state stages), then half tiles, while that buys another resident CTA
+        // (dict-less step of the 20x40 board: 3 logic warps x 6 stages of 24-env tiles -- with 32-env tiles only 2 logic warps fit
+        // next to a second CTA: 0.72 vs 0.52 G env-steps/s with the RGB image kernel behind it)
+        if (ws && !want_obs && NL == 3 && E == 32 && (227 * 1024) / (off + 1024) < 2 && !getenv("TG_E")) { E = 24; continue; }
         if (ws && NL > 1 && (227 * 1024) / (off + 1024) < 2) { NL--; continue; }
         if (ws && E == 32 && (227 * 1024) / (off + 1024) < 2 && !getenv("TG_E32")) { E = 16; NL = env->logic_warps; continue; }
         if (ws || off <= 100 * 1024 || E == 32) break;

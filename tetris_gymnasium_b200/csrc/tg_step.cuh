@@ -599,6 +599,10 @@ __global__ void __launch_bounds__(256) k_step_ws(const __grid_constant__ StepPar
             // grouped mode: tiles where most envs committed (nearly always) write their board records back as ONE bulk copy
             const int ndirty = GROUPED ? __popc(__ballot_sync(0xffffffffu, (dirty & 1u) != 0)) : 0;
             if (lane < E) s_flags[s * E + lane] = dirty | ((uint32_t)ndirty << 8);
+            // the records this warp just wrote leave through bulk (async-proxy) stores issued by the fill warps: the WRITER orders its
+            // generic-proxy writes before them (without it two grouped envs on two streams corrupted board records: the dict-less
+            // fill warps issue the whole-tile store right behind the barrier)
+            fence_async_smem();
             __syncwarp();
             named_arrive(1 + s, 32 + FT);   // ready[s]: the fill warps may consume stage s
         }

@@ -170,9 +170,10 @@ __global__ void __launch_bounds__(256) k_step_resident(const __grid_constant__ S
         bulk_wait_all();
     }
     (void)items;
-    __syncthreads();
-    // state write-back, once: hot records always, board / rng records of the tiles that changed
+    // state write-back, once: hot records always, board / rng records of the tiles that changed (the logic warps order their
+    // generic-proxy writes before the bulk stores: fence, then the barrier, then one thread issues)
     fence_async_smem();
+    __syncthreads();
     if (tid == 0) {
         for (int j = 0; j < nt; j++) {
             const int64_t base = ((int64_t)blockIdx.x + j * G) * E;

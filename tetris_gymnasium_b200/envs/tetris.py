@@ -205,6 +205,8 @@ class Tetris:
         self._reward = torch.zeros(n, dtype=torch.float32, device=dev)
         self._terminated = torch.zeros(n, dtype=u8, device=dev)
         self._truncated = torch.zeros(n, dtype=u8, device=dev)
+        # the bool views the 5-tuple returns are made once (a tensor view costs more than a microsecond per call)
+        self._terminated_b, self._truncated_b = self._terminated.view(torch.bool), self._truncated.view(torch.bool)
         self._lines = torch.zeros(n, dtype=torch.int32, device=dev)
         self._stats = torch.zeros(4, dtype=torch.float64, device=dev)
         self._seeded = False
@@ -358,12 +360,13 @@ class Tetris:
                 rc = self._L.tg_step(self._h, self._state(), self.num_envs, a.data_ptr(), obs, self._out_struct(), self._stats.data_ptr(), self._stream())
         if rc:
             _lib.check(rc, self._h)
-        info = {"lines_cleared": self._lines}
+        info = {"lines_cleared": self._lines, "_lines_cleared": self._all_true}
         if self.report_invalid_actions:
             # the reference asserts on an action outside the action space (envs/tetris.py:215); the batched env treats it as the
             # unmatched elif chain (no move) and reports it per env instead of aborting the whole batch
             info["invalid_action"] = (a < 0) | (a >= 8)
-        return (self._obs(), self._reward, self._terminated.view(torch.bool), self._truncated.view(torch.bool), self._vector_info(info))
+            info["_invalid_action"] = self._all_true
+        return (self._obs(), self._reward, self._terminated_b, self._truncated_b, info)
 
     def step_n(self, actions, keep_all: bool = True):
         """K consecutive steps in one native call (tg_step_n): `actions` int32 [K, num_envs] on the device.
@@ -399,7 +402,7 @@ class Tetris:
         if keep_all:
             return ({"board": st["board"], "active_tetromino_mask": st["mask"], "holder": st["holder"], "queue": st["queue"]},
                     st["reward"], st["terminated"].view(torch.bool), st["truncated"].view(torch.bool), {"lines_cleared": st["lines"]})
-        return (self._obs(), self._reward, self._terminated.view(torch.bool), self._truncated.view(torch.bool), {"lines_cleared": self._lines})
+        return (self._obs(), self._reward, self._terminated_b, self._truncated_b, {"lines_cleared": self._lines})
 
     def step_host(self, actions: np.ndarray, out: "dict[str, np.ndarray] | None" = None, mode: str = "compact"):
         """Same step with HOST arrays in and out (tg_step_host) -- the reference's own calling convention.

@@ -146,4 +146,4 @@ class GroupedActionsObservations:
                 rc = u._L.tg_grouped_step(*args)
         if rc:
             _lib.check(rc, u._h)
-        return (self._result(), u._reward, u._terminated.view(torch.bool), u._truncated.view(torch.bool), self._info())
+        return (self._result(), u._reward, u._terminated_b, u._truncated_b, self._info())
