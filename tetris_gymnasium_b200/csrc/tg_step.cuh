@@ -1,7 +1,7 @@
 // tg_step.cuh -- the per-call batched step / reset kernels (BASELINE config 2).
 //
 // k_step_ws (the default): persistent, warp-specialised CTAs loop over tiles of E = 32 consecutive envs
-//   * NL logic warps (lane = env) run the game logic on TMA-staged records in shared memory, NL + 2 state stages in flight
+//   * NL logic warps (lane = env) run the game logic on TMA-staged records in shared memory, NS >= NL + 2 state stages in flight
 //     (cp.async.bulk + mbarrier), each logic warp takes every NL-th tile of its CTA;
 //   * the image / store warps expand the nibble id planes into the padded uint8 board image, the mask image, the holder
 //     and the queue images (constant parts -- bedrock, zeros -- written once per CTA) and issue the TMA bulk stores:
@@ -91,7 +91,7 @@ struct StepParams {
     int mode;                        // 0 = step, 1 = reset, 2 = grouped placement step
     int E;                           // envs per tile
     int NL;                          // k_step_ws: logic warps per CTA
-    int NS;                          // k_step_ws: state stages in flight (NL + 2 by default)
+    int NS;                          // k_step_ws: state stages in flight (>= NL + 2 and a multiple of NL: tg_api.cu build_plan)
     int whole_tile_min;              // k_step_ws: dirty envs in a tile from which the board records leave as one bulk copy
     // shared-memory carve-up (bytes from the 128-aligned base)
     int off_hot, off_brd, off_rng, off_iboard, off_imask, off_iholder, off_iqueue, off_bar, off_box, off_tab, off_feat;
@@ -513,7 +513,7 @@ __global__ void __launch_bounds__(256) k_step(const __grid_constant__ StepParams
 }
 
 // ---- warp-specialised variant: the logic warps run ahead of the warps that produce and store the observation
-// images.  NL + 2 state stages (hot + board + rng records of 32 envs each) are kept in flight by TMA; the roles
+// images.  NS state stages (hot + board + rng records of 32 envs each; NS >= NL + 2, NS % NL == 0) are kept in flight by TMA; the roles
 // meet on named barriers (ready[stage]) and mbarriers (full[stage]). ----------
 __device__ __forceinline__ void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void named_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
@@ -527,7 +527,7 @@ __global__ void __launch_bounds__(256) k_step_ws(const __grid_constant__ StepPar
     extern __shared__ __align__(128) uint8_t smem[];
     const DevCfg& cfg = p.cfg;
     const int E = p.E;                              // envs per tile (<= 32: one logic-warp lane per env)
-    const int NL = p.NL, NS = p.NS;                 // logic warps; state stages in flight (>= NL + 2)
+    const int NL = p.NL, NS = p.NS;                 // logic warps; state stages in flight (>= NL + 2, a multiple of NL)
     const int T = blockDim.x, tid = threadIdx.x;
     const int FT = T - 32 * NL, ft = tid - 32 * NL; // fill threads
     const int W = WT ? WT : cfg.W, H = HT ? HT : cfg.H;
