@@ -1031,10 +1031,14 @@ extern "C" int tg_fn_step(int32_t width, int32_t height, int32_t queue_size, int
     // the tile kernel (bulk copies of whole tiles) needs 16-byte aligned arrays; TG_FN_V1=1 keeps the thread-per-env kernel
     const bool aligned = (((uintptr_t)d_board_in | (uintptr_t)d_board_out | (uintptr_t)d_scalars_in | (uintptr_t)d_scalars_out | (uintptr_t)d_obs) & 15) == 0;
     if (aligned && p.H <= 64 && !getenv("TG_FN_V1")) {
-        const FnTileSmem m = fn_tile_smem(p.Hp * p.Wp, p.H * p.W, FN_S + p.Q);
-        if (cudaFuncSetAttribute(k_fn_step_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, m.bytes) != cudaSuccess)
+        // envs per tile: 16 (sixteen 128-thread CTAs per SM) unless TG_FN_E=32 / 8
+        static const int fn_e = [] { const char* v = getenv("TG_FN_E"); const int e = v ? atoi(v) : 16; return (e == 8 || e == 32) ? e : 16; }();
+        const FnTileSmem m = fn_tile_smem(p.Hp * p.Wp, p.H * p.W, FN_S + p.Q, fn_e);
+        auto kern = fn_e == 32 ? k_fn_step_tile<32> : (fn_e == 8 ? k_fn_step_tile<8> : k_fn_step_tile<16>);
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, m.bytes) != cudaSuccess)
             return fail(nullptr, TG_ERR_CONFIG, "tg_fn_step: board too large for the shared-memory tile (%d B)", m.bytes);
-        k_fn_step_tile<<<(unsigned)((n + 31) / 32), 256, (size_t)m.bytes, (cudaStream_t)stream>>>(p);
+        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        kern<<<(unsigned)((n + fn_e - 1) / fn_e), fn_e * 8, (size_t)m.bytes, (cudaStream_t)stream>>>(p);
         cudaError_t e2 = cudaGetLastError();
         if (e2 != cudaSuccess) return fail(nullptr, TG_ERR_CUDA, "k_fn_step_tile: %s", cudaGetErrorString(e2));
         return TG_OK;

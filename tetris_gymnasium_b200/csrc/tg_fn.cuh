@@ -229,12 +229,12 @@ __global__ void k_fn_step(const FnParams p, int bstr /* bytes per staged board, 
 struct FnTileSmem {
     int off_sc, off_obs, off_misc, off_bar, bytes;
 };
-__host__ __device__ inline FnTileSmem fn_tile_smem(int OB, int HW, int NS) {
+__host__ __device__ inline FnTileSmem fn_tile_smem(int OB, int HW, int NS, int E = 32) {
     FnTileSmem m;
-    int o = (32 * OB + 15) & ~15;
-    m.off_sc = o; o += 32 * NS * 4;
-    m.off_obs = o; o += (32 * HW + 15) & ~15;
-    m.off_misc = o; o += 32 * 4 * 3;          // lock flags, full-row masks (lo, hi)
+    int o = (E * OB + 15) & ~15;
+    m.off_sc = o; o += E * NS * 4;
+    m.off_obs = o; o += (E * HW + 15) & ~15;
+    m.off_misc = o; o += E * 4 * 3;           // lock flags, full-row masks (lo, hi)
     m.off_bar = o; o += 16;
     m.bytes = o;
     return m;
@@ -253,17 +253,18 @@ __device__ __forceinline__ uint32_t fn_ld4(uint32_t a) {
     return __funnelshift_r(w0, w1, (a & 3u) * 8u);
 }
 
-#ifndef FN_MINB
-#define FN_MINB 8   // 32 registers (100 B of spills in the owner logic): 8 CTAs = 64 warps per SM; 5 CTAs at 48 registers measured 18 % slower
-#endif
-__global__ void __launch_bounds__(256, FN_MINB) k_fn_step_tile(const FnParams p) {
+// 32 registers (100 B of spills in the owner logic): 2048 threads = 64 warps per SM; 5 CTAs of 256 threads at 48 registers
+// measured 18 % slower.  E = envs per tile (32 or 16): the CTA is a chain of barrier-separated phases with ONE warp on the game
+// logic, so smaller tiles put more independent chains on an SM (E = 16: sixteen 128-thread CTAs per SM, owner lanes 0..15).
+template <int E>
+__global__ void __launch_bounds__(E * 8, 2048 / (E * 8)) k_fn_step_tile(const FnParams p) {
     extern __shared__ __align__(128) uint8_t fsm[];
-    constexpr int E = 32, TPE = 8;
+    constexpr int TPE = 8, T = E * TPE;
     const int tid = threadIdx.x, e_l = tid >> 3, t = tid & 7;
     const int64_t base = (int64_t)blockIdx.x * E;
     const int nv = (int)min((int64_t)E, p.n - base);
     const int OB = p.Hp * p.Wp, NS = FN_S + p.Q, HW = p.H * p.W;
-    const FnTileSmem m = fn_tile_smem(OB, HW, NS);
+    const FnTileSmem m = fn_tile_smem(OB, HW, NS, E);
     int8_t* s_board = (int8_t*)fsm;                       // [E][OB] (+ 16 bytes of slack: word reads past a row stay inside)
     int32_t* s_sc = (int32_t*)(fsm + m.off_sc);           // [E][NS]
     int8_t* s_obs = (int8_t*)(fsm + m.off_obs);           // [E][HW]
@@ -282,16 +283,16 @@ __global__ void __launch_bounds__(256, FN_MINB) k_fn_step_tile(const FnParams p)
         }
         mbar_wait(bar, 0);
     } else {
-        for (int k = tid; k < nv * OB; k += 256) s_board[k] = p.board_in[base * OB + k];
-        for (int k = tid; k < nv * NS; k += 256) s_sc[k] = p.sc_in[base * NS + k];
+        for (int k = tid; k < nv * OB; k += T) s_board[k] = p.board_in[base * OB + k];
+        for (int k = tid; k < nv * NS; k += T) s_sc[k] = p.sc_in[base * NS + k];
         __syncthreads();
     }
     const bool live = e_l < nv;                 // coop mapping
     int8_t* b = s_board + (size_t)e_l * OB;
     const bool owner = tid < nv;                // owner mapping: warp 0, lane = env
     const int64_t e = base + tid;
-    int8_t* ob = s_board + (size_t)(tid & 31) * OB;
-    int32_t* sc = s_sc + (tid & 31) * NS;
+    int8_t* ob = s_board + (size_t)(tid & (E - 1)) * OB;
+    int32_t* sc = s_sc + (tid & (E - 1)) * NS;
     const int spawn_x = p.Wp / 2 - 2;   // core.get_initial_x_y: 4x4 matrices (functional/core.py:66-83)
     float old_score = 0.f;
     int piece = 0, rot = 0, x = 0, y = 0, drop_reward = 0;
@@ -463,9 +464,9 @@ __global__ void __launch_bounds__(256, FN_MINB) k_fn_step_tile(const FnParams p)
         }
     } else {
         __syncthreads();
-        for (int k = tid; k < nv * OB; k += 256) p.board_out[base * OB + k] = s_board[k];
-        for (int k = tid; k < nv * NS; k += 256) p.sc_out[base * NS + k] = s_sc[k];
-        if (p.obs) for (int k = tid; k < nv * HW; k += 256) p.obs[base * HW + k] = s_obs[k];
+        for (int k = tid; k < nv * OB; k += T) p.board_out[base * OB + k] = s_board[k];
+        for (int k = tid; k < nv * NS; k += T) p.sc_out[base * NS + k] = s_sc[k];
+        if (p.obs) for (int k = tid; k < nv * HW; k += T) p.obs[base * HW + k] = s_obs[k];
     }
 }
 

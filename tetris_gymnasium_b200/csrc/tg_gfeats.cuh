@@ -30,6 +30,35 @@ __device__ __forceinline__ uint32_t bytemax_lt128(uint32_t a, uint32_t b) {   //
     return (a & m) | (b & ~m);
 }
 
+// max of the four bytes of v (__vmaxu4 is emulated on sm_100a: ~8 instructions per call)
+__device__ __forceinline__ uint32_t max4bytes(uint32_t v) {
+    return max(max(v & 255u, __byte_perm(v, 0u, 0x4441)), max(__byte_perm(v, 0u, 0x4442), v >> 24));
+}
+// PRMT with a selector whose nibbles are already 0..7 (__byte_perm masks its selector with 0x7777: one LOP3 per use)
+__device__ __forceinline__ uint32_t prmt_raw(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+// Window merge selectors: hw[k] = prmt_raw(V[k + 1], N4, sel[k]) replaces the bytes x .. x + 3 of the padded height vector by
+// the window N4 (byte g of the vector = byte g - 4 (k + 1) of word k + 1); one row of 8 selectors per x.
+template <int NH>
+__device__ __forceinline__ void build_sel_table(uint32_t* s_sel, int nx, int tid, int nthreads) {
+    for (int i = tid; i < nx * 8; i += nthreads) {
+        const int x = i >> 3, k = i & 7;
+        uint32_t sel = 0x3210u;
+        if (k < NH) {
+            const int d = 4 * (k + 1) - x;
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                const int t = d + b;
+                if (t >= 0 && t < 4) sel = (sel & ~(0xFu << (4 * b))) | ((uint32_t)(4 + t) << (4 * b));
+            }
+        }
+        s_sel[i] = sel;
+    }
+}
+
 // OR `nb` low bytes of v into the byte stream o[] at the compile-time byte offset OFF
 template <int OFF, int NB, int NWORDS>
 __device__ __forceinline__ void put_bytes(uint32_t (&o)[NWORDS], uint32_t v) {
@@ -92,7 +121,7 @@ __device__ __forceinline__ void gf_sync() {
 // FUSED (persistent CTA, the tile buffers are reused): the caller's thread 0 waits for the previous tile's bulk stores before
 // the first barrier; here the stores are only committed.
 template <int W, class COLT, bool FUSED>
-__device__ __forceinline__ void gfeats_tile(const DevCfg& cfg, uint8_t* sm, int& s_nslow, const uint32_t* s_bot, int tid, int64_t base, int nv,
+__device__ __forceinline__ void gfeats_tile(const DevCfg& cfg, uint8_t* sm, int& s_nslow, const uint32_t* s_bot, const uint32_t* s_sel, int tid, int64_t base, int nv,
                                             const uint8_t* hot_t, const uint8_t* board_t, const uint8_t* fill_t,
                                             uint8_t* __restrict__ feats, uint8_t* legal, uint8_t* __restrict__ info_board,
                                             int consumed_bar = 0) {
@@ -182,20 +211,25 @@ __device__ __forceinline__ void gfeats_tile(const DevCfg& cfg, uint8_t* sm, int&
 #pragma unroll
             for (int k = 0; k < HW; k++) V[k] = hvw[k];
             const int wi = x >> 2, sh = (x & 3) * 8;
-            const uint32_t Wlo = hvw[wi], Whi = hvw[wi + 1];
-            const uint32_t O4 = __funnelshift_r(Wlo, Whi, sh);
+            const uint32_t O4 = __funnelshift_r(hvw[wi], hvw[wi + 1], sh);   // the window: heights of board columns x - P .. x - P + 3 (pads 0)
+            uint32_t sel[8];
+            {
+                const uint4 sa = ((const uint4*)s_sel)[2 * x];
+                sel[0] = sa.x; sel[1] = sa.y; sel[2] = sa.z; sel[3] = sa.w;
+                if (NH > 4) { const uint4 sb = ((const uint4*)s_sel)[2 * x + 1]; sel[4] = sb.x; sel[5] = sb.y; sel[6] = sb.z; sel[7] = sb.w; }
+            }
             // holes and max height of the env's board: sums / maxima over the packed bytes (every thread of the env derives them
-            // itself -- a per-env scan by three of the ten warps plus a CTA barrier cost more than the ~25 instructions here)
+            // itself -- a per-env scan by three of the ten warps plus a CTA barrier cost more than the instructions here)
             int holes0 = 0;
-            uint32_t mx4 = 0;
+            uint32_t mx4 = V[1];
             {
                 const uint32_t* how = (const uint32_t*)(s_hol + e * W4);
 #pragma unroll
                 for (int k = 0; k < W4 / 4; k++) holes0 = __dp4a(how[k], 0x01010101u, (uint32_t)holes0);   // bytes beyond W are zero
 #pragma unroll
-                for (int k = 0; k < HW; k++) mx4 = __vmaxu4(mx4, V[k]);
+                for (int k = 2; k <= NH; k++) mx4 = bytemax_lt128(mx4, V[k]);   // heights sit in words 1 .. NH (pads are zero)
             }
-            const int maxh0 = (int)max(max(mx4 & 255u, (mx4 >> 8) & 255u), max((mx4 >> 16) & 255u, mx4 >> 24));
+            const int maxh0 = (int)max4bytes(mx4);
             // full rows = AND over ALL field columns of (column | piece bits): the columns left / right of the 4-column window
             // are the same for the four rotations (window columns without piece cells contribute themselves, wall columns ones)
             COLT LR = field;
@@ -210,6 +244,7 @@ __device__ __forceinline__ void gfeats_tile(const DevCfg& cfg, uint8_t* sm, int&
 #pragma unroll
             for (int j = 0; j < 4; j++) top0 |= ((unsigned)(x + j - P) < (unsigned)W) ? cj[j] : COLT(0);
             const bool odd = ((uint32_t)top0 & 1u) != 0 || preFull != 0;
+            uint32_t slowmask = 0;   // rotations that go to the dense second pass
 #pragma unroll
             for (int r = 0; r < 4; r++) {
                 const int rot = (rot0 + r) & 3;                         // cumulative rot90 presses (wrappers/grouped.py:153-154)
@@ -223,8 +258,7 @@ __device__ __forceinline__ void gfeats_tile(const DevCfg& cfg, uint8_t* sm, int&
                 const uint32_t M4 = pr.y;
                 const uint32_t OM = O4 & M4;
                 const uint32_t Tb = OM + bot4;                          // all bytes < 128
-                const uint32_t m2 = __vmaxu4(Tb, Tb >> 16);
-                const int y = H - 1 - (int)max(m2 & 255u, (m2 >> 8) & 255u);
+                const int y = H - 1 - (int)max4bytes(Tb);
                 const int jmin = pr.w & 3, jmax = (pr.w >> 2) & 3, mintop = (pr.w >> 4) & 3;
                 const int c0 = x + jmin - P, c1 = x + jmax - P;
                 uint32_t hw[NH];
@@ -242,18 +276,16 @@ __device__ __forceinline__ void gfeats_tile(const DevCfg& cfg, uint8_t* sm, int&
                     {
                         // a row can only fill up where the columns outside the window are all set: LR bits y .. y + 3
                         if (odd || y < 0 || y + mintop == 0 || ((uint32_t)(LR >> (y & (8 * (int)sizeof(COLT) - 1))) & 15u) != 0) {
-                            s_slow[atomicAdd(&s_nslow, 1)] = (unsigned short)(e * A + 4 * xb + r);
+                            slowmask |= 1u << r;
                         } else {
+                            // new window: columns under piece cells rise to H - y - top offset, the others keep their height
                             const uint32_t T4 = ((uint32_t)(H - y) * 0x01010101u - pr.z) & M4;
-                            const uint32_t N4 = bytemax_lt128(OM, T4);
+                            const uint32_t N4 = bytemax_lt128(O4, T4);
                             // all bytes < 128: signed dot products; sum(new) - sum(old) - 4 cells
-                            const int holes = __dp4a((int)OM, (int)0xFFFFFFFFu /* 4 x -1 */, __dp4a((int)N4, 0x01010101, holes0 - 4));
+                            const int holes = __dp4a((int)O4, (int)0xFFFFFFFFu /* 4 x -1 */, __dp4a((int)N4, 0x01010101, holes0 - 4));
                             const int maxh = max(maxh0, H - y - mintop);
-                            const uint32_t Nlo = N4 << sh, Nhi = __funnelshift_l(N4, 0u, sh);
-                            const uint32_t Mlo = M4 << sh, Mhi = __funnelshift_l(M4, 0u, sh);
-                            const uint32_t Wl = (Wlo & ~Mlo) | Nlo, Wh = (Whi & ~Mhi) | Nhi;
 #pragma unroll
-                            for (int k = 0; k < NH; k++) hw[k] = (k + 1 == wi) ? Wl : ((k == wi) ? Wh : V[k + 1]);
+                            for (int k = 0; k < NH; k++) hw[k] = prmt_raw(V[k + 1], N4, sel[k]);
                             // bumpiness over the packed heights (pairs (c, c+1), c < W - 1)
                             uint32_t bump = 0;
 #pragma unroll
@@ -273,6 +305,12 @@ __device__ __forceinline__ void gfeats_tile(const DevCfg& cfg, uint8_t* sm, int&
                 else if (r == 1) put_row<W, 1, F>(o, hw, summary);
                 else if (r == 2) put_row<W, 2, F>(o, hw, summary);
                 else put_row<W, 3, F>(o, hw, summary);
+            }
+            if (slowmask) {   // one append per thread (its staged rows are already the zeros board)
+                int pos = atomicAdd(&s_nslow, __popc(slowmask));
+#pragma unroll
+                for (int r = 0; r < 4; r++)
+                    if ((slowmask >> r) & 1u) s_slow[pos++] = (unsigned short)(e * A + 4 * xb + r);
             }
         }
         uint32_t* dst = s_featw + (size_t)e * (W * F) + xb * F;
@@ -347,13 +385,9 @@ __device__ __forceinline__ void gfeats_tile(const DevCfg& cfg, uint8_t* sm, int&
                     }
                 }
                 const uint32_t* hvw = s_hv + es * HS;
-                const int wi = x >> 2, sh = (x & 3) * 8;
-                const uint32_t Nlo = N4 << sh, Nhi = __funnelshift_l(N4, 0u, sh);
-                const uint32_t Mlo = 0xFFFFFFFFu << sh, Mhi = __funnelshift_l(0xFFFFFFFFu, 0u, sh);
-                const uint32_t Wl = (hvw[wi] & ~Mlo) | Nlo, Wh = (hvw[wi + 1] & ~Mhi) | Nhi;
                 uint32_t hw[NH];
 #pragma unroll
-                for (int q = 0; q < NH; q++) hw[q] = (q + 1 == wi) ? Wl : ((q == wi) ? Wh : hvw[q + 1]);
+                for (int q = 0; q < NH; q++) hw[q] = prmt_raw(hvw[q + 1], N4, s_sel[8 * x + q]);   // (window bytes beside the field are pad zeros in both)
                 uint32_t bump = 0, mx4 = 0;
 #pragma unroll
                 for (int q = 0; q < NH - 1; q++) bump = __vsadu4(hw[q], __funnelshift_r(hw[q], hw[q + 1], 8)) + bump;
@@ -364,8 +398,8 @@ __device__ __forceinline__ void gfeats_tile(const DevCfg& cfg, uint8_t* sm, int&
                     bump = __vsadu4(a2, b2) + bump;
                 }
 #pragma unroll
-                for (int q = 0; q < NH; q++) mx4 = __vmaxu4(mx4, hw[q]);   // (bytes beyond W in the last word are pad zeros)
-                const uint32_t maxh = max(max(mx4 & 255u, (mx4 >> 8) & 255u), max((mx4 >> 16) & 255u, mx4 >> 24));
+                for (int q = 0; q < NH; q++) mx4 = bytemax_lt128(mx4, hw[q]);   // (bytes beyond W in the last word are pad zeros)
+                const uint32_t maxh = max4bytes(mx4);
 #pragma unroll
                 for (int c = 0; c < W; c++) out[c] = (uint8_t)(hw[c >> 2] >> (8 * (c & 3)));
                 out[W] = (uint8_t)maxh; out[W + 1] = (uint8_t)holes; out[W + 2] = (uint8_t)bump;
@@ -427,15 +461,17 @@ __global__ void __maxnreg__(W == 10 ? GF_REGS : 96) k_grouped_feats_x(const DevC
     extern __shared__ __align__(16) uint8_t sm[];
     __shared__ int s_nslow;
     __shared__ uint32_t s_bot[28];
+    __shared__ __align__(16) uint32_t s_sel[(W + P) * 8];
     const int tid = threadIdx.x;
     const int64_t base = (int64_t)blockIdx.x * S::EPB;
     const int nv = (int)min((int64_t)S::EPB, n - base);
     if (tid < 28 * 8) ((uint4*)(sm + S::off_prec))[tid] = (&c_prec[0][0])[tid >> 3];
     if (tid >= 256 && tid < 256 + 28) s_bot[tid - 256] = (&c_bot4[0][0])[tid - 256];
+    build_sel_table<(W + 3) / 4>(s_sel, W + P, tid, 32 * W);
     // programmatic dependent launch (see k_step_ws): this grid may be scheduled while the placement step drains
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    gfeats_tile<W, COLT, false>(cfg, sm, s_nslow, s_bot, tid, base, nv, hot + base * 32, board + base * cfg.board_stride,
+    gfeats_tile<W, COLT, false>(cfg, sm, s_nslow, s_bot, s_sel, tid, base, nv, hot + base * 32, board + base * cfg.board_stride,
                                 fill_high ? fill_high + base : nullptr, feats, legal, info_board);
 }
 
@@ -473,6 +509,7 @@ __global__ void __maxnreg__(GFU_REGS) k_grouped_step_feats(const __grid_constant
     extern __shared__ __align__(128) uint8_t sm[];
     __shared__ int s_nslow;
     __shared__ uint32_t s_bot[28];
+    __shared__ __align__(16) uint32_t s_sel[(W + P) * 8];
     const DevCfg& cfg = p.cfg;
     const int tid = threadIdx.x;
     const int BS = cfg.board_stride, RS = cfg.rng_stride;
@@ -488,6 +525,7 @@ __global__ void __maxnreg__(GFU_REGS) k_grouped_step_feats(const __grid_constant
 
     if (tid < 28 * 8) ((uint4*)(sm + S::off_prec))[tid] = (&c_prec[0][0])[tid >> 3];
     if (tid >= 256 && tid < 256 + 28) s_bot[tid - 256] = (&c_bot4[0][0])[tid - 256];
+    build_sel_table<(W + 3) / 4>(s_sel, W + P, tid, (int)blockDim.x);
     for (int i = tid; i < 112; i += blockDim.x) s_rowbytes[i] = (&c_rowbytes[0][0][0])[i];
     if (tid < 28) s_cells[tid] = (&c_cells[0][0])[tid];
     if (tid < 7) s_n[tid] = c_n[tid];
@@ -566,7 +604,7 @@ __global__ void __maxnreg__(GFU_REGS) k_grouped_step_feats(const __grid_constant
             const uint8_t* st = stage0 + s * st_all;
             asm volatile("bar.sync %0, %1;" ::"r"(2 + s), "n"(TF + 32) : "memory");       // ready[s]
             if (tid == 0) bulk_wait_read();     // the previous tile's feature stores have left the staging buffers
-            gfeats_tile<W, COLT, true>(cfg, sm, s_nslow, s_bot, tid, base, nv, st, st + st_hot, s_fill + s * 32, feats, legal, info_board,
+            gfeats_tile<W, COLT, true>(cfg, sm, s_nslow, s_bot, s_sel, tid, base, nv, st, st + st_hot, s_fill + s * 32, feats, legal, info_board,
                                        blockIdx.x + (k + NS) * G < ntiles ? 2 + NS + s : 0);
         }
         if (tid == 0) bulk_wait_all();
