@@ -163,8 +163,10 @@ __global__ void __launch_bounds__(128, 6) k_rollout_x(const __grid_constant__ Ro
     __shared__ unsigned short s_cells[28];
     __shared__ int s_n[8];
     __shared__ uint4 s_prec[28];
+    __shared__ __align__(16) uint32_t s_sel[(W + P) * 8];          // window merge selectors per x (tg_gfeats.cuh)
     if (tid < 28) { s_cells[tid] = (&c_cells[0][0])[tid]; s_prec[tid] = (&c_prec[0][0])[tid]; }
     if (tid < 7) s_n[tid] = c_n[tid];
+    build_sel_table<NH>(s_sel, W + P, tid, (int)blockDim.x);
     __syncthreads();
     Tabs tb;
     tb.ptab = nullptr; tb.cells = s_cells; tb.rowbytes = &c_rowbytes[0][0][0]; tb.n = s_n;
@@ -224,8 +226,13 @@ __global__ void __launch_bounds__(128, 6) k_rollout_x(const __grid_constant__ Ro
 #pragma unroll 1
             for (int xb = 0; xb < W; xb++) {
                 const int x = xb + xoff, wi = x >> 2, sh = (x & 3) * 8;
-                const uint32_t Wlo = hv[wi], Whi = hv[wi + 1];
-                const uint32_t O4 = __funnelshift_r(Wlo, Whi, sh);
+                const uint32_t O4 = __funnelshift_r(hv[wi], hv[wi + 1], sh);
+                uint32_t sel[8];
+                {
+                    const uint4 sa = ((const uint4*)s_sel)[2 * x];
+                    sel[0] = sa.x; sel[1] = sa.y; sel[2] = sa.z; sel[3] = sa.w;
+                    if (NH > 4) { const uint4 sb = ((const uint4*)s_sel)[2 * x + 1]; sel[4] = sb.x; sel[5] = sb.y; sel[6] = sb.z; sel[7] = sb.w; }
+                }
                 COLT cj[4];
 #pragma unroll
                 for (int j = 0; j < 4; j++) cj[j] = colp[x + j];
@@ -253,16 +260,13 @@ __global__ void __launch_bounds__(128, 6) k_rollout_x(const __grid_constant__ Ro
                     const bool exact = lands && (full != 0 || y + mintop == 0);
                     if (exact) { if (a < 64) slow_lo |= 1ull << a; else slow_hi |= 1u << (a - 64); }
                     const uint32_t M4 = q.y;
-                    const uint32_t OM = O4 & M4;
+                    // new window: columns under piece cells rise to H - y - top offset, the others keep their height (tg_gfeats.cuh)
                     const uint32_t T4 = ((uint32_t)(H - y) * 0x01010101u - q.z) & M4;
-                    const uint32_t N4 = bytemax_lt128(OM, T4);
-                    const int delta = __dp4a((int)OM, (int)0xFFFFFFFFu, __dp4a((int)N4, 0x01010101, 0));   // sum(new) - sum(old)
-                    const uint32_t Nlo = N4 << sh, Nhi = __funnelshift_l(N4, 0u, sh);
-                    const uint32_t Mlo = M4 << sh, Mhi = __funnelshift_l(M4, 0u, sh);
-                    const uint32_t Wl = (Wlo & ~Mlo) | Nlo, Wh = (Whi & ~Mhi) | Nhi;
+                    const uint32_t N4 = bytemax_lt128(O4, T4);
+                    const int delta = __dp4a((int)O4, (int)0xFFFFFFFFu, __dp4a((int)N4, 0x01010101, 0));   // sum(new) - sum(old)
                     uint32_t hw[NH];
 #pragma unroll
-                    for (int k = 0; k < NH; k++) hw[k] = (k + 1 == wi) ? Wl : ((k == wi) ? Wh : V[k + 1]);
+                    for (int k = 0; k < NH; k++) hw[k] = prmt_raw(V[k + 1], N4, sel[k]);
                     uint32_t bump = 0;
 #pragma unroll
                     for (int k = 0; k < NH - 1; k++) bump = __vsadu4(hw[k], __funnelshift_r(hw[k], hw[k + 1], 8)) + bump;
