@@ -20,6 +20,7 @@ namespace tg {
 // per (piece, rotation): .x = cells (16 bit) | row masks of matrix columns 0..3 (nibbles) << 16,
 // .y = byte j 0xFF if column j holds cells, .z = byte j = row offset of the top cell of column j,
 // .w = first column | last column << 2 | smallest top offset << 4
+// (the packed-byte kernels re-code .w for their width when they stage the table: prec_w_for_width)
 __constant__ uint4 c_prec[7][4];
 // per (piece, rotation): byte j = row offset of the LOWEST cell of matrix column j (0 where the column is empty)
 __constant__ unsigned int c_bot4[7][4];
@@ -30,6 +31,16 @@ __device__ __forceinline__ uint32_t bytemax_lt128(uint32_t a, uint32_t b) {   //
     return (a & m) | (b & ~m);
 }
 
+// .w of a staged c_prec entry for board width W: bit x (x < 28) = the placement at matrix position x keeps the piece inside the
+// field (collision_with_frame, wrappers/grouped.py:101-122: x + first column >= P and x + last column < W + P),
+// smallest top offset << 28, first column << 30 (the last column is the top byte of .y's column mask)
+template <int W>
+__device__ __forceinline__ uint32_t prec_w_for_width(uint32_t w) {
+    static_assert(W + P <= 28, "x mask and the two small fields share one word");
+    const int jmin = w & 3, jmax = (w >> 2) & 3, mintop = (w >> 4) & 3;
+    const uint32_t xmask = ((1u << (W + P - jmax)) - 1u) & ~((1u << (P - jmin)) - 1u);
+    return xmask | ((uint32_t)mintop << 28) | ((uint32_t)jmin << 30);
+}
 // max of the four bytes of v (__vmaxu4 is emulated on sm_100a: ~8 instructions per call)
 __device__ __forceinline__ uint32_t max4bytes(uint32_t v) {
     return max(max(v & 255u, __byte_perm(v, 0u, 0x4441)), max(__byte_perm(v, 0u, 0x4442), v >> 24));
@@ -121,7 +132,7 @@ __device__ __forceinline__ void gf_sync() {
 // FUSED (persistent CTA, the tile buffers are reused): the caller's thread 0 waits for the previous tile's bulk stores before
 // the first barrier; here the stores are only committed.
 template <int W, class COLT, bool FUSED>
-__device__ __forceinline__ void gfeats_tile(const DevCfg& cfg, uint8_t* sm, int& s_nslow, const uint32_t* s_bot, const uint32_t* s_sel, int tid, int64_t base, int nv,
+__device__ __forceinline__ void gfeats_tile(const DevCfg& cfg, uint8_t* sm, int* s_nslow, const uint32_t* s_bot, const uint32_t* s_sel, int tid, int64_t base, int nv,
                                             const uint8_t* hot_t, const uint8_t* board_t, const uint8_t* fill_t,
                                             uint8_t* __restrict__ feats, uint8_t* legal, uint8_t* __restrict__ info_board,
                                             int consumed_bar = 0) {
@@ -146,7 +157,7 @@ __device__ __forceinline__ void gfeats_tile(const DevCfg& cfg, uint8_t* sm, int&
     const COLT field = (COLT(1) << H) - 1;
 
     // ---- phase 1: thread = (column xb, env e): column -> shared memory, its height / holes with row 0 zeroed (Q1) ----
-    if (tid == 0) s_nslow = 0;
+    if (tid < 2) s_nslow[tid] = 0;
     if (live) {
         const COLT col = ((const COLT*)(board_t + (size_t)e * cfg.board_stride))[xb];
         s_colp[e * CS + P + xb] = col;
@@ -259,11 +270,10 @@ __device__ __forceinline__ void gfeats_tile(const DevCfg& cfg, uint8_t* sm, int&
                 const uint32_t OM = O4 & M4;
                 const uint32_t Tb = OM + bot4;                          // all bytes < 128
                 const int y = H - 1 - (int)max4bytes(Tb);
-                const int jmin = pr.w & 3, jmax = (pr.w >> 2) & 3, mintop = (pr.w >> 4) & 3;
-                const int c0 = x + jmin - P, c1 = x + jmax - P;
+                const int mintop = (pr.w >> 28) & 3;
                 uint32_t hw[NH];
                 uint32_t summary;
-                if (c0 < 0 || c1 >= W) {
+                if (!((pr.w >> x) & 1u)) {
                     // collision_with_frame: ones board, row 0 zeroed -> heights H - 1, max H - 1, no holes, no bumpiness
 #pragma unroll
                     for (int k = 0; k < NH; k++) hw[k] = (uint32_t)(H - 1) * 0x01010101u;
@@ -306,11 +316,17 @@ __device__ __forceinline__ void gfeats_tile(const DevCfg& cfg, uint8_t* sm, int&
                 else if (r == 2) put_row<W, 2, F>(o, hw, summary);
                 else put_row<W, 3, F>(o, hw, summary);
             }
-            if (slowmask) {   // one append per thread (its staged rows are already the zeros board)
-                int pos = atomicAdd(&s_nslow, __popc(slowmask));
+            if (slowmask) {
+                // one append per thread (its staged rows are already the zeros board).  Two lists in one array: placements that cannot
+                // complete a row whatever their landing row (LR == 0: nearly all of them under random play) grow from the front,
+                // the others from the back -- the second pass runs the full-row scan only for the back list
+                const int cnt = __popc(slowmask);
+                const bool back = LR != 0;
+                const int p0 = atomicAdd(s_nslow + (back ? 1 : 0), cnt);
+                int pos = back ? EPB * A - 1 - p0 : p0, dp = back ? -1 : 1;
 #pragma unroll
                 for (int r = 0; r < 4; r++)
-                    if ((slowmask >> r) & 1u) s_slow[pos++] = (unsigned short)(e * A + 4 * xb + r);
+                    if ((slowmask >> r) & 1u) { s_slow[pos] = (unsigned short)(e * A + 4 * xb + r); pos += dp; }
             }
         }
         uint32_t* dst = s_featw + (size_t)e * (W * F) + xb * F;
@@ -337,10 +353,11 @@ __device__ __forceinline__ void gfeats_tile(const DevCfg& cfg, uint8_t* sm, int&
     // its cells u = v & ~F in order, packed towards the floor: the top cell (row t = ctz(u)) ends at t + popc(F >> (t+1)) and
     // popc(u) cells remain.  After a clear row 0 is empty, so the wrapper's row zeroing (Q1) only applies when F = 0.
     {
-        const int ns = s_nslow;
+        const int ns0 = s_nslow[0], ns = ns0 + s_nslow[1];
         uint8_t* s_feats = sm + S::off_feats;
         for (int k = tid; k < ns; k += T) {
-            const int it = s_slow[k], es = it / A, a = it - es * A;
+            const bool scan = k >= ns0;                                 // back list: a row may fill up
+            const int it = s_slow[scan ? EPB * A - 1 - (k - ns0) : k], es = it / A, a = it - es * A;
             const uint32_t w0 = s_w0[es];
             const int piece = (w0 >> 13) & 7, rot = (int)(((w0 >> 16) & 3) + (a & 3)) & 3;
             const int x = (a >> 2) + P - (int)((cfg.nhalf3 >> (3 * piece)) & 7u);
@@ -354,13 +371,16 @@ __device__ __forceinline__ void gfeats_tile(const DevCfg& cfg, uint8_t* sm, int&
             }
             const int y = ctz_t<COLT>(B >> 1);                          // while !collision(y+1): y++ from y = 0
             if ((B >> y) & 1) continue;                                 // game over: the staged row is already the zeros board
-            const int jmin = pr.w & 3, c0 = x + jmin - P, c1 = x + (int)((pr.w >> 2) & 3) - P;
-            COLT full = field;
-            for (int c = 0; c < W; c++) {
-                COLT v = colp[P + c];
-                const int j = c + P - x;
-                if ((unsigned)j < 4u) v |= (COLT)((pr.x >> (16 + 4 * j)) & 15u) << y;
-                full &= v;
+            const int jmin = pr.w >> 30, c0 = x + jmin - P, c1 = x + ((31 - __clz((int)pr.y)) >> 3) - P;
+            COLT full = 0;
+            if (scan) {
+                full = field;
+                for (int c = 0; c < W; c++) {
+                    COLT v = colp[P + c];
+                    const int j = c + P - x;
+                    if ((unsigned)j < 4u) v |= (COLT)((pr.x >> (16 + 4 * j)) & 15u) << y;
+                    full &= v;
+                }
             }
             uint8_t* out = s_feats + (size_t)it * F;
             if (full == 0) {
@@ -459,18 +479,23 @@ __global__ void __maxnreg__(W == 10 ? GF_REGS : 96) k_grouped_feats_x(const DevC
                                                             uint8_t* __restrict__ info_board) {
     using S = GFeatsSmem<W, COLT>;
     extern __shared__ __align__(16) uint8_t sm[];
-    __shared__ int s_nslow;
+    __shared__ int s_nslow[2];
     __shared__ uint32_t s_bot[28];
     __shared__ __align__(16) uint32_t s_sel[(W + P) * 8];
     const int tid = threadIdx.x;
     const int64_t base = (int64_t)blockIdx.x * S::EPB;
     const int nv = (int)min((int64_t)S::EPB, n - base);
-    if (tid < 28 * 8) ((uint4*)(sm + S::off_prec))[tid] = (&c_prec[0][0])[tid >> 3];
+    if (tid < 28 * 8) {
+        uint4 v = (&c_prec[0][0])[tid >> 3];
+        v.w = prec_w_for_width<W>(v.w);
+        ((uint4*)(sm + S::off_prec))[tid] = v;
+    }
     if (tid >= 256 && tid < 256 + 28) s_bot[tid - 256] = (&c_bot4[0][0])[tid - 256];
     build_sel_table<(W + 3) / 4>(s_sel, W + P, tid, 32 * W);
     // programmatic dependent launch (see k_step_ws): this grid may be scheduled while the placement step drains
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    // (one tile per CTA: a persistent variant -- 4 CTAs per SM looping over tiles, tables staged once -- measured 15 % SLOWER)
     gfeats_tile<W, COLT, false>(cfg, sm, s_nslow, s_bot, s_sel, tid, base, nv, hot + base * 32, board + base * cfg.board_stride,
                                 fill_high ? fill_high + base : nullptr, feats, legal, info_board);
 }
@@ -507,7 +532,7 @@ __global__ void __maxnreg__(GFU_REGS) k_grouped_step_feats(const __grid_constant
     using FS = GFusedSmem<W, COLT>;
     constexpr int E = 32, TF = 32 * W, NLW = FS::NLW, NS = FS::NS;
     extern __shared__ __align__(128) uint8_t sm[];
-    __shared__ int s_nslow;
+    __shared__ int s_nslow[2];
     __shared__ uint32_t s_bot[28];
     __shared__ __align__(16) uint32_t s_sel[(W + P) * 8];
     const DevCfg& cfg = p.cfg;
@@ -523,7 +548,11 @@ __global__ void __maxnreg__(GFU_REGS) k_grouped_step_feats(const __grid_constant
     const size_t st_all = FS::stage_bytes(cfg);
     uint8_t* stage0 = sm + FS::off_stage;
 
-    if (tid < 28 * 8) ((uint4*)(sm + S::off_prec))[tid] = (&c_prec[0][0])[tid >> 3];
+    if (tid < 28 * 8) {
+        uint4 v = (&c_prec[0][0])[tid >> 3];
+        v.w = prec_w_for_width<W>(v.w);
+        ((uint4*)(sm + S::off_prec))[tid] = v;
+    }
     if (tid >= 256 && tid < 256 + 28) s_bot[tid - 256] = (&c_bot4[0][0])[tid - 256];
     build_sel_table<(W + 3) / 4>(s_sel, W + P, tid, (int)blockDim.x);
     for (int i = tid; i < 112; i += blockDim.x) s_rowbytes[i] = (&c_rowbytes[0][0][0])[i];
