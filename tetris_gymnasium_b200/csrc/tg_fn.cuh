@@ -318,17 +318,30 @@ __global__ void __launch_bounds__(E * 8, 2048 / (E * 8)) k_fn_step_tile(const Fn
             const int a = p.actions[e];
             piece = sc[FN_ACTIVE]; rot = sc[FN_ROT]; x = sc[FN_X]; y = sc[FN_Y];
             uint32_t cells = c_cells[piece][rot];
-            if (a == 0) { if (!fn_collision(p, ob, cells, x - 1, y)) x -= 1; }
-            else if (a == 1) { if (!fn_collision(p, ob, cells, x + 1, y)) x += 1; }
-            else if (a == 2) { if (!fn_collision(p, ob, cells, x, y + 1)) { y += 1; drop_reward = 1; } }
-            else if (a == 3 || a == 4) {
-                int nr = (rot + (a == 4 ? 1 : 3)) & 3;   // 3 = counter-clockwise, 4 = clockwise (envs/tetris_fn.py:470-478)
-                if (!fn_collision(p, ob, c_cells[piece][nr], x, y)) { rot = nr; cells = c_cells[piece][nr]; }
-            } else if (a == 6) {                          // core.hard_drop (functional/core.py:230-251)
-                int ny = y;
-                while (!fn_collision(p, ob, cells, x, ny + 1)) ny++;
-                drop_reward = 2 * (ny - y);
-                y = ny;
+            if ((unsigned)a <= 4u) {
+                // left / right / down / rotate: ONE collision test of the candidate (the per-action branches, each with its own
+                // inlined test, ran one after the other on the owner warp)
+                const int dx = (a == 1) - (a == 0), dy = (a == 2);
+                const int nr = (rot + (a == 4 ? 1 : (a == 3 ? 3 : 0))) & 3;   // 3 = counter-clockwise, 4 = clockwise (envs/tetris_fn.py:470-478)
+                const uint32_t ncells = c_cells[piece][nr];
+                if (!fn_collision(p, ob, ncells, x + dx, y + dy)) { x += dx; y += dy; rot = nr; cells = ncells; drop_reward = dy; }
+            } else if (a == 6) {                          // core.hard_drop (functional/core.py:230-251): while !collision(y + 1): y++
+                // column by column: the cells of a tetromino column are contiguous (rows top .. bot of the matrix), so the column first
+                // collides at y' = max(y + 1, g - bot), g = the first filled board row at or below y + 1 + top (bedrock ends the scan)
+                const uint4 pr = c_prec[piece][rot];
+                const uint32_t bot4 = c_bot4[piece][rot];
+                int nyp = 1 << 20;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    if ((pr.y >> (8 * j)) & 1u) {
+                        const int8_t* q = ob + (y + 1 + (int)((pr.z >> (8 * j)) & 3u)) * p.Wp + x + j;
+                        int g = 0;
+                        while (q[g * p.Wp] <= 0) g++;
+                        nyp = min(nyp, max(y + 1, y + 1 + (int)((pr.z >> (8 * j)) & 3u) + g - (int)((bot4 >> (8 * j)) & 3u)));
+                    }
+                }
+                drop_reward = 2 * (nyp - 1 - y);
+                y = nyp - 1;
             }
             int yg = y;
             if (p.gravity && !fn_collision(p, ob, cells, x, y + 1)) yg = y + 1;   // core.graviy_step
@@ -419,16 +432,21 @@ __global__ void __launch_bounds__(E * 8, 2048 / (E * 8)) k_fn_step_tile(const Fn
         if (live) {
             int8_t* o = s_obs + (size_t)e_l * HW;
             const uint32_t invW = 65536u / (uint32_t)p.W + 1u;   // i / W for i < 4096
-            if ((HW & 3) == 0 && p.W >= 4) {
+            if ((HW & 3) == 0 && (OB & 3) == 0 && p.W >= 4) {
+                // Wp = W + 2 P and P = 4: cell (r, c) sits at board byte r Wp + 4 + c = r W + c (mod 4), the alignment of its
+                // observation byte r W + c.  Observation word k (cells 4k .. 4k + 3) is therefore ONE aligned board word when it
+                // lies in one row, and a byte-wise select of two aligned board words when it continues in the next row.
                 const uint32_t b0 = smem_u32(b) + P;
                 for (int k = t; k < (HW >> 2); k += TPE) {
                     const uint32_t i = 4u * k, r = (i * invW) >> 16, c = i - r * p.W;
-                    uint32_t v = fn_ld4(b0 + r * p.Wp + c);
+                    uint32_t v;
+                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(b0 + r * p.Wp + c));
                     const uint32_t n1 = p.W - c;                 // cells left in row r
-                    if (n1 < 4u) {                               // the word continues at the start of row r + 1
-                        const uint32_t v2 = fn_ld4(b0 + (r + 1) * p.Wp);
+                    if (n1 < 4u) {                               // bytes n1 .. 3 are the first cells of row r + 1
+                        uint32_t v2;
+                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v2) : "r"(b0 + (r + 1) * p.Wp - n1));
                         const uint32_t keep = (1u << (8 * n1)) - 1u;
-                        v = (v & keep) | (v2 << (8 * n1));
+                        v = (v & keep) | (v2 & ~keep);
                     }
                     ((uint32_t*)o)[k] = fn_pos4(v) >> 7;
                 }
