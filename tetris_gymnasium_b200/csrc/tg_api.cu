@@ -1025,6 +1025,7 @@ extern "C" int tg_fn_step(int32_t width, int32_t height, int32_t queue_size, int
     FnParams p;
     memset(&p, 0, sizeof p);
     p.W = width; p.H = height; p.Wp = width + 2 * TG_PADDING; p.Hp = height + TG_PADDING; p.Q = queue_size; p.gravity = gravity != 0;
+    p.invW = 65536u / (uint32_t)width + 1u;
     p.n = n; p.board_in = d_board_in; p.board_out = d_board_out; p.sc_in = d_scalars_in; p.sc_out = d_scalars_out;
     p.actions = d_actions; p.seq = d_piece_seq; p.seq_len = seq_len;
     p.obs = d_obs; p.reward = d_reward; p.terminated = d_terminated; p.lines = d_lines;

@@ -17,6 +17,7 @@ enum { FN_ACTIVE = 0, FN_ROT, FN_X, FN_Y, FN_QIDX, FN_OVER, FN_SCORE /* float bi
 
 struct FnParams {
     int W, H, Wp, Hp, Q, gravity;
+    uint32_t invW;                // 65536 / W + 1: i / W == (i * invW) >> 16 for i < 4096 (host-computed: a division per thread otherwise)
     int64_t n;
     const int8_t* board_in; int8_t* board_out;
     const int32_t* sc_in; int32_t* sc_out;
@@ -38,7 +39,7 @@ __device__ __forceinline__ bool fn_collision(const FnParams& p, const int8_t* b,
 // queue.create_bag_queue (functional/queue.py:20-35): a permutation of arange(Q).  The reference draws it with
 // jax.random.permutation (threefry); ours comes from Philox(key) or from the injected stream -- the facade's
 // piece sequences are not JAX-bit-compatible (parity unpinned for key-derived sequences).
-__device__ __forceinline__ void fn_new_bag(const FnParams& p, int64_t e, int32_t* sc) {
+__device__ __noinline__ void fn_new_bag(const FnParams& p, int64_t e, int32_t* sc) {
     int32_t* q = sc + FN_S;
     uint32_t bagno = (uint32_t)sc[FN_KEY1];
     if (p.seq) {
@@ -67,7 +68,7 @@ __device__ __forceinline__ void fn_new_bag(const FnParams& p, int64_t e, int32_t
 // per env with an odd word stride), the game logic runs thread-per-env on the staged bytes, the observation is built per env
 // into a shared tile and leaves coalesced.  (The first version worked on the byte boards in global memory and spent most of
 // its time in per-byte index divisions of the observation loop: 1.2 ms per 1 M envs.)
-__global__ void k_fn_step(const FnParams p, int bstr /* bytes per staged board, multiple of 4, odd word count */) {
+__global__ void k_fn_step(const __grid_constant__ FnParams p, int bstr /* bytes per staged board, multiple of 4, odd word count */) {
     extern __shared__ __align__(16) uint8_t fsm[];
     const int tid = threadIdx.x, T = blockDim.x;
     const int64_t base = (int64_t)blockIdx.x * T;
@@ -257,7 +258,7 @@ __device__ __forceinline__ uint32_t fn_ld4(uint32_t a) {
 // measured 18 % slower.  E = envs per tile (32 or 16): the CTA is a chain of barrier-separated phases with ONE warp on the game
 // logic, so smaller tiles put more independent chains on an SM (E = 16: sixteen 128-thread CTAs per SM, owner lanes 0..15).
 template <int E>
-__global__ void __launch_bounds__(E * 8, 2048 / (E * 8)) k_fn_step_tile(const FnParams p) {
+__global__ void __launch_bounds__(E * 8, 2048 / (E * 8)) k_fn_step_tile(const __grid_constant__ FnParams p) {
     extern __shared__ __align__(128) uint8_t fsm[];
     constexpr int TPE = 8, T = E * TPE;
     const int tid = threadIdx.x, e_l = tid >> 3, t = tid & 7;
@@ -431,7 +432,7 @@ __global__ void __launch_bounds__(E * 8, 2048 / (E * 8)) k_fn_step_tile(const Fn
     if (p.obs) {
         if (live) {
             int8_t* o = s_obs + (size_t)e_l * HW;
-            const uint32_t invW = 65536u / (uint32_t)p.W + 1u;   // i / W for i < 4096
+            const uint32_t invW = p.invW;                        // i / W for i < 4096
             if ((HW & 3) == 0 && (OB & 3) == 0 && p.W >= 4) {
                 // Wp = W + 2 P and P = 4: cell (r, c) sits at board byte r Wp + 4 + c = r W + c (mod 4), the alignment of its
                 // observation byte r W + c.  Observation word k (cells 4k .. 4k + 3) is therefore ONE aligned board word when it
