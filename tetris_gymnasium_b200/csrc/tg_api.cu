@@ -62,6 +62,7 @@ struct tg_env {
     void* rollout_last_action;
     int cnn_h, cnn_w;     // output size the tg_cnn_observe tables in stage[4] were built for
     int cnn_nax = 0, cnn_axv[4] = {-1, -1, -1, -1};   // classes of the x coefficient sums (k_cnn_obs2)
+    bool cnn_v3_ok = false;                           // the word-wise kernel k_cnn_obs3 applies to the current tables
     std::string err;
     // tg_step_host staging
     cudaStream_t hs[3];
