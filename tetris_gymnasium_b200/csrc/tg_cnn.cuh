@@ -442,13 +442,13 @@ __global__ void __launch_bounds__(256, 4) k_cnn_obs3(const __grid_constant__ Cnn
     __shared__ __align__(16) int4 s_y[128];
     __shared__ __align__(8) uint2 s_exc[256];
     __shared__ uint8_t s_cls[128];
+    __shared__ __align__(16) int4 s_xt[128];   // sx0, sx1, a0, a1 per output column
     const DevCfg& cfg = p.cfg;
     const int W = cfg.W, H = cfg.H, Wp = cfg.Wp, Hp = cfg.Hp, RW = cfg.rgb_w, Q = cfg.Q, BS = cfg.board_stride;
     const int OH = p.OH, OW = p.OW, FB = OH * OW, NWD = OW >> 2;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     const int NP = Hp * RW;
     uint32_t* s_gt = (uint32_t*)sm;        // [OH][16] transposed uniform-neighbourhood table, then one region per warp
-    const int4* s_x = (const int4*)p.xtab; // (passes B / C: read through L1)
     uint8_t* wbase = sm + p.gtab_bytes + (size_t)warp * (2 * p.rec_bytes + p.pix_bytes + 2 * p.out_bytes + p.wlist_bytes + p.list_bytes);
     uint8_t* recbuf = wbase;
     uint8_t* pix = wbase + 2 * p.rec_bytes;
@@ -463,7 +463,7 @@ __global__ void __launch_bounds__(256, 4) k_cnn_obs3(const __grid_constant__ Cnn
     for (int i = threadIdx.x; i < OH; i += blockDim.x) s_y[i] = ((const int4*)p.ytab)[i];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_exc[i] = ((const uint2*)p.gray_exc)[i];
     for (int i = threadIdx.x; i < OH * 16; i += blockDim.x) s_gt[i] = p.gtabT[i];
-    for (int i = threadIdx.x; i < OW; i += blockDim.x) s_cls[i] = p.xcls[i];
+    for (int i = threadIdx.x; i < OW; i += blockDim.x) { s_cls[i] = p.xcls[i]; s_xt[i] = ((const int4*)p.xtab)[i]; }
     const uint32_t exc_addr = smem_u32(s_exc);
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // programmatic dependent launch, see k_step_ws
     asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -492,7 +492,7 @@ __global__ void __launch_bounds__(256, 4) k_cnn_obs3(const __grid_constant__ Cnn
         __syncwarp();
         for (int k = lane; k < cnt; k += 32) {
             const int ent = list[k], dy = ent & 255, dx = ent >> 8;
-            const int4 yt = s_y[dy], xt = __ldg(s_x + dx);
+            const int4 yt = s_y[dy], xt = s_xt[dx];
             const uint32_t acoef = (uint32_t)xt.z | ((uint32_t)xt.w << 16);
             const uint8_t* r0 = pix + yt.x * RW;
             const uint8_t* r1 = pix + yt.y * RW;
@@ -568,8 +568,8 @@ __global__ void __launch_bounds__(256, 4) k_cnn_obs3(const __grid_constant__ Cnn
             const int c1 = min(OH, c0 + CR);
             uint8_t* out = out0 + (nchunk & 1u) * p.out_bytes;
             if (tma) { bulk_wait_read1(); __syncwarp(); }   // the store that read this buffer two chunks ago is done
-            const uint32_t o_addr = smem_u32(out) + 4u * lane - c0 * OW;
-            // ---- pass A: one output word per lane and row ----
+            const uint32_t ob_addr = smem_u32(out), o_addr = ob_addr + 4u * lane - c0 * OW;
+            // ---- pass A: one output word per lane and row (explicit shared-window addresses: no generic loads / stores) ----
             int wcnt = 0;
             for (int dy = c0; dy < c1; dy++) {
                 const int4 yt = s_y[dy];                       // sy0, sy1, b0, b1 (warp-uniform)
@@ -597,6 +597,8 @@ __global__ void __launch_bounds__(256, 4) k_cnn_obs3(const __grid_constant__ Cnn
                     const uint32_t v = prmt_raw(t, 0u, w_sel);
                     asm volatile("st.shared.u32 [%0], %1;" ::"r"(o_addr + (uint32_t)(dy * OW)), "r"(v) : "memory");
                 }
+                // (a per-lane bit mask of the chunk's rows + one scan per chunk instead of a ballot per row measured slower: the lanes on
+                //  the field's walls append in every row and the others wait for their loop)
                 const bool slow = wlane && !fast;
                 const unsigned m = __ballot_sync(0xffffffffu, slow);
                 if (slow) wlist[wcnt + __popc(m & ((1u << lane) - 1u))] = (unsigned short)(dy | (lane << 8));
@@ -613,14 +615,18 @@ __global__ void __launch_bounds__(256, 4) k_cnn_obs3(const __grid_constant__ Cnn
                 if (valid) {
                     const int ent = wlist[k >> 2];
                     dy = ent & 255; dx = 4 * (ent >> 8) + (k & 3);
-                    const int4 yt = s_y[dy], xt = __ldg(s_x + dx);
-                    const int sxb = xt.w == 0 ? xt.x : xt.y;   // a neighbour with a zero coefficient does not count
-                    const uint8_t* r0 = pix + yt.x * RW;
-                    const uint8_t* r1 = pix + (yt.w == 0 ? yt.x : yt.y) * RW;
-                    const uint32_t a = r0[xt.x], b2 = r0[sxb], c2 = r1[xt.x], d2 = r1[sxb];
+                    const int4 yt = s_y[dy], xt = s_xt[dx];
+                    const uint32_t sxb = (uint32_t)(xt.w == 0 ? xt.x : xt.y);   // a neighbour with a zero coefficient does not count
+                    const uint32_t r0 = pix_addr + (uint32_t)(yt.x * RW), r1 = pix_addr + (uint32_t)((yt.w == 0 ? yt.x : yt.y) * RW);
+                    uint32_t a, b2, c2, d2;
+                    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(a) : "r"(r0 + (uint32_t)xt.x));
+                    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(b2) : "r"(r0 + sxb));
+                    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(c2) : "r"(r1 + (uint32_t)xt.x));
+                    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(d2) : "r"(r1 + sxb));
                     if (a == b2 && a == c2 && a == d2) {
-                        const uint32_t t = s_gt[dy * 16 + (int)a];
-                        out[(dy - c0) * OW + dx] = (uint8_t)(t >> (8 * s_cls[dx]));
+                        uint32_t v;   // byte (class of a0 + a1) of the table word of (dy, id)
+                        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(gt_addr + (uint32_t)(dy * 16 + (int)a) * 4u + (uint32_t)s_cls[dx]));
+                        asm volatile("st.shared.u8 [%0], %1;" ::"r"(ob_addr + (uint32_t)((dy - c0) * OW + dx)), "r"(v) : "memory");
                     } else rest = true;
                 }
                 const unsigned m = __ballot_sync(0xffffffffu, rest);
@@ -800,7 +806,7 @@ extern "C" int tg_cnn_observe(tg_env* env, tg_state st, int64_t n, int32_t out_h
     p.xcls = (const uint8_t*)(p.wtab + (size_t)(out_w / 4 > 0 ? out_w / 4 : 1) * 4);
     for (int k = 0; k < 4; k++) p.axv[k] = env->cnn_axv[k];
     // TG_CNN_V2=1: the per-pixel two-pass kernel instead of the word-wise one
-    const bool word_wise = two_pass && env->cnn_v3_ok && !getenv("TG_CNN_V2");
+    bool word_wise = two_pass && env->cnn_v3_ok && !getenv("TG_CNN_V2");
     p.list_bytes = two_pass ? 512 : 0;
     p.gtab_bytes = two_pass ? r128((size_t)out_h * 64) : 0;
     int nw = two_pass ? 8 : 4;
