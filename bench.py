@@ -564,7 +564,7 @@ def leg_extra(n, world, rank, dev, barrier, allmax):
     extra["wide_cnn"] = {"env_steps_per_s": world * c_rate,
                          "config": f"20x40 board, queue 5, fused CNN adapter (RGB -> 84x84 INTER_AREA -> grey -> 4-frame stack, clip reward), {nc} envs/GPU, {Kw} steps",
                          "roofline": {"bound": "hbm", "achieved": c_bytes * c_rate / 1e9, "peak": peak, "unit": "GB/s", "frac": c_bytes * c_rate / 1e9 / peak,
-                                      "bytes_per_env_step": c_bytes, "kernels": "tg::k_step_ws<20,40,u64,0> (no dict) + tg::k_cnn_obs",
+                                      "bytes_per_env_step": c_bytes, "kernels": "tg::k_step_ws<20,40,u64,0> (no dict) + tg::k_cnn_obs3",
                                       "note": "integer-issue bound (fixed-point resize + grey per output pixel), see the `issue` block"}}
     extra["wide_cnn"]["issue"] = issue_block(c_rate, [("r02_cnn.json", 1 << 16)])
     cbase.close()
@@ -595,7 +595,7 @@ def leg_extra(n, world, rank, dev, barrier, allmax):
     extra["functional"] = {"env_steps_per_s": world * f_rate,
                            "config": f"functional facade batched_step (envs/tetris_fn.py), 10x20, queue 7, {nf} envs/GPU, State (int8 board + scalars) in and out every call, {Kw} steps",
                            "roofline": {"bound": "hbm", "achieved": f_bytes * f_rate / 1e9, "peak": peak, "unit": "GB/s", "frac": f_bytes * f_rate / 1e9 / peak,
-                                        "bytes_per_env_step": f_bytes, "kernels": "tg::k_fn_step_tile"}}
+                                        "bytes_per_env_step": f_bytes, "kernels": "tg::k_fn_step_tile<16>"}}
     return extra
 
 
