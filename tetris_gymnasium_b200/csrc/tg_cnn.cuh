@@ -434,7 +434,8 @@ __global__ void __launch_bounds__(256, 4) k_cnn_obs2(const __grid_constant__ Cnn
 //   pass B  the listed words pixel by pixel, 32 at a time (dense): 2 x 2 ids equal -> table byte, else -> pixel list;
 //   pass C  the listed pixels through the full fixed-point interpolation (as k_cnn_obs2's pass 2).
 // k_cnn_obs2 spent ~25 thread-instructions per pixel in its row loop whatever the pixel was; here a fast word costs ~6 per pixel.
-template <class COLT>
+// RW4: the id image's row stride is a multiple of 4 (W = 20: 48), so the alignment of a lane's source fetch is the same in every row
+template <class COLT, bool RW4>
 __global__ void __launch_bounds__(256, 4) k_cnn_obs3(const __grid_constant__ CnnParams p) {
     extern __shared__ __align__(128) uint8_t sm[];
     __shared__ uint32_t s_lut[16];
@@ -561,7 +562,12 @@ __global__ void __launch_bounds__(256, 4) k_cnn_obs3(const __grid_constant__ Cnn
             pix[(h.y + (c >> 2)) * RW + h.x + (c & 3)] = (uint8_t)(h.p + 2);
         }
         __syncwarp();
-        const uint32_t pix_addr = smem_u32(pix), gt_addr = smem_u32(s_gt);
+        uint32_t pix_addr = smem_u32(pix), gt_addr = smem_u32(s_gt);
+        // (opaque copies: under register pressure the compiler re-derives the shared-window addresses -- S2R SR_CgaCtaId + five
+        //  instructions -- inside the row loop instead of keeping them)
+        asm volatile("mov.u32 %0, %0;" : "+r"(pix_addr));
+        asm volatile("mov.u32 %0, %0;" : "+r"(gt_addr));
+        const uint32_t f_al = (pix_addr + w_lo) & ~3u, f_sh = ((pix_addr + w_lo) & 3u) * 8u;   // RW4: aligned word / shift of this lane's fetch
         uint8_t* g = p.frames + e * p.env_stride;
         const int reps = 1 + ((p.fill_mask && p.fill_mask[e]) ? p.fill_count : 0);   // reset envs: the frame fills the stack window
         for (int c0 = 0; c0 < OH; c0 += CR, nchunk++) {
@@ -576,18 +582,18 @@ __global__ void __launch_bounds__(256, 4) k_cnn_obs3(const __grid_constant__ Cnn
                 const int sy1 = yt.w == 0 ? yt.x : yt.y;       // the output row sits on a source row: the next row does not count
                 uint32_t f0, f1;
                 {
-                    const uint32_t a = pix_addr + yt.x * RW + w_lo, al = a & ~3u;
+                    const uint32_t a = pix_addr + yt.x * RW + w_lo, al = RW4 ? f_al + yt.x * RW : (a & ~3u);
                     uint32_t lo, hi;
                     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(lo) : "r"(al));
                     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(hi) : "r"(al + 4u));
-                    f0 = __funnelshift_r(lo, hi, (a & 3u) * 8u);
+                    f0 = __funnelshift_r(lo, hi, RW4 ? f_sh : (a & 3u) * 8u);
                 }
                 {
-                    const uint32_t a = pix_addr + sy1 * RW + w_lo, al = a & ~3u;
+                    const uint32_t a = pix_addr + sy1 * RW + w_lo, al = RW4 ? f_al + sy1 * RW : (a & ~3u);
                     uint32_t lo, hi;
                     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(lo) : "r"(al));
                     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(hi) : "r"(al + 4u));
-                    f1 = __funnelshift_r(lo, hi, (a & 3u) * 8u);
+                    f1 = __funnelshift_r(lo, hi, RW4 ? f_sh : (a & 3u) * 8u);
                 }
                 const uint32_t id = f0 & 255u, rep4 = id * 0x01010101u;
                 const bool fast = (((f0 ^ rep4) | (f1 ^ rep4)) & w_mask) == 0;
@@ -837,7 +843,10 @@ extern "C" int tg_cnn_observe(tg_env* env, tg_state st, int64_t n, int32_t out_h
         CUDA_TRY(env, launch_pdl(kern, (unsigned)blocks, (unsigned)T, smem, (cudaStream_t)stream, p));
         return TG_OK;
     };
-    if (word_wise) return env->col64 ? launch(k_cnn_obs3<uint64_t>) : launch(k_cnn_obs3<uint32_t>);
+    if (word_wise) {
+        if ((d.rgb_w & 3) == 0) return env->col64 ? launch(k_cnn_obs3<uint64_t, true>) : launch(k_cnn_obs3<uint32_t, true>);
+        return env->col64 ? launch(k_cnn_obs3<uint64_t, false>) : launch(k_cnn_obs3<uint32_t, false>);
+    }
     if (two_pass) {
         if (env->col64) return NX == 1 ? launch(k_cnn_obs2<uint64_t, 1>) : NX == 2 ? launch(k_cnn_obs2<uint64_t, 2>) : NX == 3 ? launch(k_cnn_obs2<uint64_t, 3>) : launch(k_cnn_obs2<uint64_t, 4>);
         return NX == 1 ? launch(k_cnn_obs2<uint32_t, 1>) : NX == 2 ? launch(k_cnn_obs2<uint32_t, 2>) : NX == 3 ? launch(k_cnn_obs2<uint32_t, 3>) : launch(k_cnn_obs2<uint32_t, 4>);
