@@ -439,16 +439,14 @@ __global__ void __launch_bounds__(E * 8, 2048 / (E * 8)) k_fn_step_tile(const __
                 // lies in one row, and a byte-wise select of two aligned board words when it continues in the next row.
                 const uint32_t b0 = smem_u32(b) + P;
                 for (int k = t; k < (HW >> 2); k += TPE) {
-                    const uint32_t i = 4u * k, r = (i * invW) >> 16, c = i - r * p.W;
-                    uint32_t v;
-                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(b0 + r * p.Wp + c));
-                    const uint32_t n1 = p.W - c;                 // cells left in row r
-                    if (n1 < 4u) {                               // bytes n1 .. 3 are the first cells of row r + 1
-                        uint32_t v2;
-                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v2) : "r"(b0 + (r + 1) * p.Wp - n1));
-                        const uint32_t keep = (1u << (8 * n1)) - 1u;
-                        v = (v & keep) | (v2 & ~keep);
-                    }
+                    const uint32_t i = 4u * k, r = (i * invW) >> 16, n1 = (r + 1u) * p.W - i;   // cells left in row r
+                    // board byte of cell i: r Wp + c = i + 8 r; the cells of the next row sit Wp - W = 8 bytes further, same byte positions
+                    const uint32_t a = b0 + i + 8u * r;
+                    uint32_t v, v2;
+                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+                    asm volatile("ld.shared.u32 %0, [%1+8];" : "=r"(v2) : "r"(a));        // (masked out when the word stays in its row)
+                    const uint32_t keep = n1 >= 4u ? 0xFFFFFFFFu : (1u << (8 * n1)) - 1u;
+                    v = (v & keep) | (v2 & ~keep);
                     ((uint32_t*)o)[k] = fn_pos4(v) >> 7;
                 }
             } else {
