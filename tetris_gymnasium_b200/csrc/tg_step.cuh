@@ -584,14 +584,18 @@ __global__ void __launch_bounds__(256) k_step_ws(const __grid_constant__ StepPar
         // ===== logic warps: warp lw runs the game logic of this CTA's tiles k = lw, lw + NL, ... (lane = env) =====
         const int lw = tid >> 5, lane = tid & 31;
         TileStats st = {0, 0, 0, 0};
-        for (int64_t k = lw; blockIdx.x + k * G < ntiles; k += NL) {
+        // stage s = k % NS and mbarrier phase (k / NS) & 1 of this warp's tiles k = lw, lw + NL, ...: kept incrementally (NL <= NS;
+        // with a 64-bit k both were calls of the 64-bit division routine, once per tile)
+        int s = lw;
+        uint32_t ph = 0;
+        for (int64_t k = lw; blockIdx.x + k * G < ntiles; k += NL, s += NL) {
+            if (s >= NS) { s -= NS; ph ^= 1u; }
             const int64_t tile = blockIdx.x + k * G;
-            const int s = (int)(k % NS);
             const int64_t base = tile * E;
             const int nv = (int)min((int64_t)E, p.n - base);
             int action = 0;
             if (MODE != 1 && lane < nv) action = p.actions[base + lane];
-            mbar_wait(bar + s, (uint32_t)((k / NS) & 1));
+            mbar_wait(bar + s, ph);
             uint32_t dirty = 0;
             if (lane < nv)
                 dirty = logic_one_env<COLT, false, MODE, XT>(p, tb, base + lane, lane, action, (uint32_t*)(smem + p.off_hot + s * p.st_hot),
@@ -611,7 +615,8 @@ __global__ void __launch_bounds__(256) k_step_ws(const __grid_constant__ StepPar
         // ===== image / store warps =====
         const bool leader = (ft == 0);
         int nv_prev = 0, s = 0;
-        for (int64_t k = 0; blockIdx.x + k * G < ntiles; k++, s = (s + 1 == NS ? 0 : s + 1)) {
+        uint32_t ph = 0;                                // mbarrier phase (k / NS) & 1 of tile k
+        for (int64_t k = 0; blockIdx.x + k * G < ntiles; k++, ph ^= (s + 1 == NS ? 1u : 0u), s = (s + 1 == NS ? 0 : s + 1)) {
             const int64_t tile = blockIdx.x + k * G;
             const int64_t base = tile * E;
             const int nv = (int)min((int64_t)E, p.n - base);
@@ -619,7 +624,7 @@ __global__ void __launch_bounds__(256) k_step_ws(const __grid_constant__ StepPar
             uint8_t* s_brd = smem + p.off_brd + s * p.st_brd;
             uint8_t* s_rng = smem + p.off_rng + s * p.st_rng;
             named_sync(1 + s, 32 + FT);                 // logic of this tile is done, stage s is final
-            mbar_wait(bar + s, (uint32_t)((k / NS) & 1));   // (already complete) acquire the TMA writes
+            mbar_wait(bar + s, ph);                     // (already complete) acquire the TMA writes
             bulk_wait_read();                           // stores of the previous tile have left shared memory
             named_sync(BAR_FILL, FT);
             // the stage of tile k-1 is free again: prefetch NS-1 tiles ahead into it
