@@ -303,6 +303,7 @@ static void derive_cfg(const tg_config* cfg, const HostTables& T, DevCfg& d) {
     d.board_stride = bs;
     d.rng_stride = cfg->rng_mode == TG_RNG_NUMPY ? 48 : 16;
     d.OB = d.Hp * d.Wp; d.OQ = 16 * d.Q; d.A = 4 * d.W; d.F = d.W + 3;
+    d.inv_q = 65536u / (unsigned)d.Q + 1u;
     d.holder_size = cfg->holder_size > 0 ? cfg->holder_size : 1;
     d.OH = 16 * d.holder_size;
     d.rgb_w = d.Wp + 4 * (d.Q > d.holder_size ? d.Q : d.holder_size);   // max(holder, queue) pieces wide (wrappers/observation.py:49-58)

@@ -35,6 +35,7 @@ struct DevCfg {
     int rng_stride;
     int OB;            // obs board bytes = Hp*Wp
     int OQ;            // obs queue bytes = 16*Q
+    unsigned int inv_q; // 65536 / Q + 1: it / Q == (it * inv_q) >> 16 for it < 4096 (host-computed: the image warps divided once per tile)
     int A, F;          // placements 4W, features W+3
     int rgb_w;         // Wp + 4*max(Q, holder_size, 1)
     int NPC;           // pieces of the tetromino set (7 for the reference's; Tetris(tetrominoes=[...]): 1..7)

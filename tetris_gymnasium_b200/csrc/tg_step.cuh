@@ -332,7 +332,7 @@ __device__ __forceinline__ void fill_images(const DevCfg& cfg, int nv, const uin
             fill_board_row<WT>(cfg, (const uint32_t*)(s_brd + e * BS + cfg.ids_off), i_board, e * OB, row);
         }
     }
-    const uint32_t invQ = 65536u / (uint32_t)Q + 1u;   // it / Q for it < 4096 without a division
+    const uint32_t invQ = cfg.inv_q;                     // it / Q for it < 4096 without a division
     for (int it = t; it < nv * Q; it += nt) {          // queue: one piece per item, its 4 matrix rows in one 128-bit read
         int e = (int)(((uint32_t)it * invQ) >> 16), q = it - e * Q;
         uint64_t queue = (uint64_t)s_hot[e * 8 + 2] | ((uint64_t)s_hot[e * 8 + 3] << 32);
