@@ -404,6 +404,7 @@ struct StepResult {
     int terminated;
     int dirty;  // board record changed
     int did_reset;
+    unsigned long long Bfin;   // env_step: collision mask (bmask) of the piece that is active AFTER the step, at its x / rotation
 };
 
 // Tetris.commit_active_tetromino (envs/tetris.py:450-479); B = bmask of the active piece at h.x
@@ -415,6 +416,7 @@ __device__ __forceinline__ void env_commit(const DevCfg& cfg, const Tabs& tb, Ho
     if ((B >> h.y) & 1) {
         res.reward = cfg.r_go;
         h.over = 1;
+        res.Bfin = (unsigned long long)B;   // the piece stays where it is
         return;
     }
     h.y += ctz_t<COLT>(B >> (h.y + 1));  // drop_active_tetromino
@@ -438,6 +440,7 @@ __device__ __forceinline__ void env_commit(const DevCfg& cfg, const Tabs& tb, Ho
     h.p = queue_pop<XT>(cfg, g, h);
     h.r = 0; h.x = cfg.spawn_x[h.p]; h.y = 0;
     COLT Bn = bmask<COLT>(cols, cfg.W, tb.cells[h.p * 4], h.x);
+    res.Bfin = (unsigned long long)Bn;
     h.over = (int)(Bn & 1);
     res.reward += cfg.r_alife;
     if (h.over) res.reward = cfg.r_go;
@@ -483,6 +486,7 @@ __device__ __forceinline__ void env_step(const DevCfg& cfg, const Tabs& tb, Hot&
         if (!((B >> (h.y + 1)) & 1)) h.y += 1;
         else do_commit = true;
     }
+    res.Bfin = (unsigned long long)B;       // B belongs to (h.p, h.r, h.x) on every path above; a commit replaces it
     if (do_commit) env_commit<COLT, XT>(cfg, tb, h, rec, g, B, res);
     res.terminated = h.over;
 }

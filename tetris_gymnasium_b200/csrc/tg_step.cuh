@@ -231,7 +231,7 @@ __device__ __forceinline__ uint32_t logic_one_env(const StepParams& p, const Tab
     g.seq = p.seq ? p.seq + e * cfg.seq_len : nullptr;
     g.gid = cfg.env_id_offset + (uint64_t)e;
     g.dirty = false;
-    bool need_reset = false, run_ok = true;
+    bool need_reset = false, run_ok = true, have_B = false;
     const int mode = MODE >= 0 ? MODE : p.mode;
     if (mode == 1) {
         need_reset = (!p.reset_mask || p.reset_mask[e]);
@@ -260,6 +260,7 @@ __device__ __forceinline__ uint32_t logic_one_env(const StepParams& p, const Tab
         }
         if (run) {
             env_step<COLT, XT>(cfg, tb, h, rec, g, act, res);
+            have_B = true;
             if (invalid) res.reward = cfg.r_invalid;
         }
         h.ep_ret += (float)res.reward; h.ep_len += 1; h.ep_lines += res.lines;
@@ -280,7 +281,9 @@ __device__ __forceinline__ uint32_t logic_one_env(const StepParams& p, const Tab
         p.truncated[eo] = 0;
         p.lines[eo] = res.lines;
     }
-    COLT Bact = bmask<COLT>((const COLT*)rec, cfg.W, tb.cells[h.p * 4 + h.r], h.x);
+    // the active piece is drawn unless it collides where it stands: env_step leaves the collision mask of the piece that is
+    // active after the step (one bmask = 4 shared loads + ~30 instructions per env less on the logic warps)
+    const COLT Bact = (have_B && !need_reset) ? (COLT)res.Bfin : bmask<COLT>((const COLT*)rec, cfg.W, tb.cells[h.p * 4 + h.r], h.x);
     const uint32_t show = !((Bact >> h.y) & 1);
     s_box[slot] = (uint32_t)h.x | ((uint32_t)h.y << 8) | ((uint32_t)tb.n[h.p] << 16) | (show << 20) |
                   ((uint32_t)h.p << 24) | ((uint32_t)h.r << 28);
