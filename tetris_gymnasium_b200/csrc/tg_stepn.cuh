@@ -131,14 +131,15 @@ __global__ void __launch_bounds__(256) k_step_resident(const __grid_constant__ S
         mbar_wait(bar, 0);                                  // acquire the TMA writes of the resident records
         const bool every_step = q.obs_stride != 0 || q.K == 1;   // obs_stride 0: one set of arrays, only the last step's dict is kept
         int nv_prev = 0, i = 0;
+        const int own_q = nt / NL, own_r = nt - own_q * NL;   // logic warp w owns own_q + (w < own_r) of the CTA's tiles
         for (int k = 0; k < q.K; k++) {
-            for (int j = 0; j < nt; j++, i++) {
+            int ow = 0, jq = 0;                              // j % NL and j / NL, kept incrementally (three divisions per item otherwise)
+            for (int j = 0; j < nt; j++, i++, jq += (ow + 1 == NL), ow = (ow + 1 == NL ? 0 : ow + 1)) {
                 const int64_t base = ((int64_t)blockIdx.x + j * G) * E;
                 const int nv = (int)min((int64_t)E, p.n - base);
                 const int64_t ob = (int64_t)k * q.obs_stride + base;
                 // item (k, j) belongs to logic warp j % NL and is its (k * own tiles + j / NL)-th item
-                const int ow = j % NL;
-                const uint32_t need = (uint32_t)(k * ((nt - ow + NL - 1) / NL) + j / NL + 1);
+                const uint32_t need = (uint32_t)(k * (own_q + (ow < own_r ? 1 : 0)) + jq + 1);
                 if (!every_step && k != q.K - 1) {          // nothing to emit: only release the slot (the box stays with the last emitted item)
                     if (leader) { while (ld_volatile_s(s_cnt + ow) < need) {} st_volatile_s(s_cnt + NL, (uint32_t)(i + 1)); }
                     continue;
