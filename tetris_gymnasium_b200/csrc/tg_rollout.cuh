@@ -164,7 +164,12 @@ __global__ void __launch_bounds__(128, 6) k_rollout_x(const __grid_constant__ Ro
     __shared__ int s_n[8];
     __shared__ uint4 s_prec[28];
     __shared__ __align__(16) uint32_t s_sel[(W + P) * 8];          // window merge selectors per x (tg_gfeats.cuh)
-    if (tid < 28) { s_cells[tid] = (&c_cells[0][0])[tid]; s_prec[tid] = (&c_prec[0][0])[tid]; }
+    if (tid < 28) {
+        s_cells[tid] = (&c_cells[0][0])[tid];
+        uint4 v = (&c_prec[0][0])[tid];
+        v.w = prec_w_for_width<W>(v.w);   // x-legality mask | smallest top offset << 28 | first column << 30 (tg_gfeats.cuh)
+        s_prec[tid] = v;
+    }
     if (tid < 7) s_n[tid] = c_n[tid];
     build_sel_table<NH>(s_sel, W + P, tid, (int)blockDim.x);
     __syncthreads();
@@ -249,9 +254,8 @@ __global__ void __launch_bounds__(128, 6) k_rollout_x(const __grid_constant__ Ro
                         B |= colp[x + (c & 3)] >> (c >> 2);
                     }
                     const int y = ctz_t<COLT>(B >> 1);               // while !collision(y+1): y++ from y = 0
-                    const int jmin = q.w & 3, jmax = (q.w >> 2) & 3, mintop = (q.w >> 4) & 3;
-                    const int c0 = x + jmin - P, c1 = x + jmax - P;
-                    const bool legal = c0 >= 0 && c1 < W;
+                    const int mintop = (q.w >> 28) & 3;
+                    const bool legal = ((q.w >> x) & 1u) != 0;       // the piece stays inside the field (collision_with_frame)
                     if (legal && first_legal < 0) first_legal = a;
                     const bool lands = legal && !((B >> y) & 1);
                     COLT full = LR;
@@ -297,7 +301,7 @@ __global__ void __launch_bounds__(128, 6) k_rollout_x(const __grid_constant__ Ro
                     B |= colp[x + (c & 3)] >> (c >> 2);
                 }
                 const int y = ctz_t<COLT>(B >> 1);
-                const int jmin = q.w & 3, c0 = x + jmin - P, c1 = x + (int)((q.w >> 2) & 3) - P;
+                const int jmin = q.w >> 30, c0 = x + jmin - P, c1 = x + ((31 - __clz((int)q.y)) >> 3) - P;
                 COLT full = pre[c0] & suf[c1] & field;
 #pragma unroll
                 for (int j = 0; j < 4; j++) full &= colp[x + j] | ((COLT)((q.x >> (16 + 4 * j)) & 15u) << y);
