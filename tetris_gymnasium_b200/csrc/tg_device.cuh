@@ -217,11 +217,11 @@ __device__ __noinline__ uint32_t shuffle_bag_raw(int rng_mode, uint32_t* rec, ui
         uint64_t seed = ((uint64_t*)rec)[0];
         uint32_t ctr = rec[2];
         rec[2] = ctr + 1;
+        // ONE Philox call per shuffle: draws 0..3 take a word each (umulhi(u, i + 1)); draws 4 and 5 reuse the fractions the first
+        // two left over (u * m mod 2^32 is uniform again up to 2^-29: the multiply-shift chain of a mixed-radix expansion)
         uint32_t c[4] = {ctr, (uint32_t)gid, (uint32_t)(gid >> 32), 0u};
-        uint32_t d[4] = {ctr, (uint32_t)gid, (uint32_t)(gid >> 32), 1u};
         philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
-        philox4x32_10(d, (uint32_t)seed, (uint32_t)(seed >> 32));
-        const uint32_t u[6] = {c[0], c[1], c[2], c[3], d[0], d[1]};
+        const uint32_t u[6] = {c[0], c[1], c[2], c[3], top >= 1 ? c[0] * (uint32_t)(top + 1) : 0u, top >= 2 ? c[1] * (uint32_t)top : 0u};
         for (int i = top; i >= 1; i--) j6[top - i] = __umulhi(u[top - i], (uint32_t)(i + 1));   // 7 pieces: umulhi(u0, 7), (u1, 6), ... (u5, 2)
     }
     for (int i = top; i >= 1; i--) {
@@ -246,12 +246,11 @@ __device__ __noinline__ uint32_t shuffle_bag7_raw(int rng_mode, uint32_t* rec, u
         uint64_t seed = ((uint64_t*)rec)[0];
         uint32_t ctr = rec[2];
         rec[2] = ctr + 1;
+        // ONE Philox call per shuffle (see shuffle_bag_raw): the last two draws reuse the fractions left over by the first two
         uint32_t c[4] = {ctr, (uint32_t)gid, (uint32_t)(gid >> 32), 0u};
-        uint32_t d[4] = {ctr, (uint32_t)gid, (uint32_t)(gid >> 32), 1u};
         philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
-        philox4x32_10(d, (uint32_t)seed, (uint32_t)(seed >> 32));
         j6[0] = __umulhi(c[0], 7u); j6[1] = __umulhi(c[1], 6u); j6[2] = __umulhi(c[2], 5u);
-        j6[3] = __umulhi(c[3], 4u); j6[4] = __umulhi(d[0], 3u); j6[5] = __umulhi(d[1], 2u);
+        j6[3] = __umulhi(c[3], 4u); j6[4] = __umulhi(c[0] * 7u, 3u); j6[5] = __umulhi(c[1] * 6u, 2u);
     }
 #pragma unroll
     for (int i = 6; i >= 1; i--) {
