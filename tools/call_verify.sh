@@ -8,4 +8,4 @@ python bench.py > gpurun_out/verify_bench.log 2> gpurun_out/verify_bench.err; ta
 python bench_suite.py --out gpurun_out/verify_suite > gpurun_out/verify_suite.log 2>&1; tail -2 gpurun_out/verify_suite.log | cut -c1-200
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_fn_step_tile -s 6 -c 1 -f -o gpurun_out/verify_fn python tools/prof_paths.py fn --envs 1048576 > gpurun_out/verify_fn.log 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_cnn_obs3 -s 6 -c 1 -f -o gpurun_out/verify_cnn python tools/prof_paths.py cnn --envs 65536 > gpurun_out/verify_cnn.log 2>&1
-ls gpurun_out | grep r02f
+ls gpurun_out | grep verify_ || true
